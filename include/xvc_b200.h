@@ -1,0 +1,329 @@
+/*
+ * xvc_b200 -- C ABI of the B200-native xvc hot path (libxvc_b200.so).
+ *
+ * This is the drop-in boundary.  Everything a host encoder/decoder loop needs from the
+ * GPU goes through the plain-C entry points below: no C++ types, no torch types, plain
+ * pointers and sizes.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference tree, divideon/xvc @ e875a2e).
+ *
+ * Three flavours:
+ *  (A) table-shaped, HOST pointers, one block per call -- the exact signatures of
+ *      xvc's SIMD function tables (SampleMetric::SimdFunc, InterPrediction::SimdFunc)
+ *      plus the scalar class methods that have no table entry in the reference
+ *      (transform, quant, dequant).  Correctness vehicle / drop-in for the table, slow
+ *      by construction (one launch + two copies per block).
+ *  (B) batched, DEVICE-resident pictures -- the performance surface.  Pictures live in
+ *      HBM in "slots"; work is described by arrays of CU descriptors and launched per
+ *      picture.  Asynchronous on the context stream; xvcb200_sync() returns the sticky
+ *      status.
+ *  (C) picture-level: xvcb200_encode_picture() chains ME -> MC -> T/Q/recon -> deblock
+ *      -> pad for one inter picture.
+ *
+ * Sample = uint16_t (reference default build HIGH_BITDEPTH=ON, common.h:34-38),
+ * Coeff = Residual = int16_t (common.h:39-40).  Strides are in elements, not bytes.
+ * Error convention: table-shaped calls return their value / void like the reference and
+ * record failures in a process-wide sticky status (xvcb200_last_error); batched calls
+ * return an xvcb200_status and never throw.
+ */
+#ifndef XVC_B200_H_
+#define XVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  XVCB200_OK = 0,
+  XVCB200_INVALID_ARGUMENT = 1,   /* cf. XVC_ENC_INVALID_ARGUMENT, xvcenc.h:45-61 */
+  XVCB200_NO_DEVICE = 2,
+  XVCB200_CUDA_ERROR = 3,
+  XVCB200_OUT_OF_MEMORY = 4,
+  XVCB200_UNSUPPORTED = 5
+} xvcb200_status;
+
+/* sticky process-wide status for the void/value-returning table calls */
+int xvcb200_last_error(void);
+const char *xvcb200_last_error_string(void);
+void xvcb200_clear_error(void);
+/* number of kernels this library has launched since load (bench.py gpu_launches) */
+uint64_t xvcb200_launch_count(void);
+const char *xvcb200_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * (A) table-shaped entry points, host pointers
+ * ---------------------------------------------------------------------------------- */
+
+/* SampleMetric::SimdFunc (xvc_enc_lib/sample_metric.h:166-191); C defaults
+ * ComputeSad_c / ComputeSsd_c (sample_metric.cc:671-684, 301-314). */
+int xvcb200_sad_sample_sample(int width, int height, const uint16_t *src1, ptrdiff_t stride1,
+                              const uint16_t *src2, ptrdiff_t stride2);
+int xvcb200_sad_short_sample(int width, int height, const int16_t *src1, ptrdiff_t stride1,
+                             const uint16_t *src2, ptrdiff_t stride2);
+uint64_t xvcb200_ssd_sample_sample(int width, int height, const uint16_t *src1, ptrdiff_t stride1,
+                                   const uint16_t *src2, ptrdiff_t stride2);
+uint64_t xvcb200_ssd_short_sample(int width, int height, const int16_t *src1, ptrdiff_t stride1,
+                                  const uint16_t *src2, ptrdiff_t stride2);
+uint64_t xvcb200_ssd_short_short(int width, int height, const int16_t *src1, ptrdiff_t stride1,
+                                 const int16_t *src2, ptrdiff_t stride2);
+
+/* SampleMetric::Compare (sample_metric.cc:171-298): metric selected like MetricType
+ * (sample_metric.h:34-44), result before the chroma weight (weight applied by caller). */
+enum { XVCB200_METRIC_SSD = 0, XVCB200_METRIC_SATD = 1, XVCB200_METRIC_SAD = 2,
+       XVCB200_METRIC_SAD_FAST = 3 };
+uint64_t xvcb200_compare_sample_sample(int metric, int bitdepth, int width, int height,
+                                       const uint16_t *src1, ptrdiff_t stride1,
+                                       const uint16_t *src2, ptrdiff_t stride2);
+uint64_t xvcb200_compare_short_sample(int metric, int bitdepth, int width, int height,
+                                      const int16_t *src1, ptrdiff_t stride1,
+                                      const uint16_t *src2, ptrdiff_t stride2);
+
+/* InterPrediction::SimdFunc (xvc_common_lib/inter_prediction.h:176-216); C defaults
+ * inter_prediction.cc:1207-1385 (filters), :1462 (copy bipred), :1675 (add_avg).
+ * `src` points at the centre sample; the callee backs up taps/2-1 (cc:1215,1275).
+ * chroma = 0: 8-tap luma, 1: 4-tap chroma (table index kLC). */
+void xvcb200_filter_h_sample_sample(int chroma, int width, int height, int bitdepth,
+                                    const int16_t *filter, const uint16_t *src, ptrdiff_t src_stride,
+                                    uint16_t *dst, ptrdiff_t dst_stride);
+void xvcb200_filter_h_sample_short(int chroma, int width, int height, int bitdepth,
+                                   const int16_t *filter, const uint16_t *src, ptrdiff_t src_stride,
+                                   int16_t *dst, ptrdiff_t dst_stride);
+void xvcb200_filter_v_sample_sample(int chroma, int width, int height, int bitdepth,
+                                    const int16_t *filter, const uint16_t *src, ptrdiff_t src_stride,
+                                    uint16_t *dst, ptrdiff_t dst_stride);
+void xvcb200_filter_v_sample_short(int chroma, int width, int height, int bitdepth,
+                                   const int16_t *filter, const uint16_t *src, ptrdiff_t src_stride,
+                                   int16_t *dst, ptrdiff_t dst_stride);
+void xvcb200_filter_v_short_sample(int chroma, int width, int height, int bitdepth,
+                                   const int16_t *filter, const int16_t *src, ptrdiff_t src_stride,
+                                   uint16_t *dst, ptrdiff_t dst_stride);
+void xvcb200_filter_v_short_short(int chroma, int width, int height, int bitdepth,
+                                  const int16_t *filter, const int16_t *src, ptrdiff_t src_stride,
+                                  int16_t *dst, ptrdiff_t dst_stride);
+void xvcb200_add_avg(int width, int height, int offset, int shift, int bitdepth,
+                     const int16_t *src1, intptr_t stride1, const int16_t *src2, intptr_t stride2,
+                     uint16_t *dst, intptr_t dst_stride);
+void xvcb200_filter_copy_bipred(int width, int height, int16_t offset, int shift,
+                                const uint16_t *ref, ptrdiff_t ref_stride,
+                                int16_t *pred, ptrdiff_t pred_stride);
+
+/* InterPrediction::FilterLuma / FilterChroma (inter_prediction.cc:1387-1448) and the
+ * bi-pred variants (:1475-1538): fractional position in 1/16 (luma) or 1/32 (chroma). */
+void xvcb200_interp_block(int chroma, int width, int height, int bitdepth, int frac_x, int frac_y,
+                          const uint16_t *ref, ptrdiff_t ref_stride, uint16_t *pred, ptrdiff_t pred_stride);
+void xvcb200_interp_block_bipred(int chroma, int width, int height, int bitdepth, int frac_x, int frac_y,
+                                 const uint16_t *ref, ptrdiff_t ref_stride, int16_t *pred, ptrdiff_t pred_stride);
+
+/* The reference's table structs, same member order, so a maintainer can memcpy/assign
+ * (see INTEGRATION.md).  Indices: [0] width<=2 / luma, [1] width>=4 / chroma. */
+typedef struct {
+  void (*add_avg[2])(int, int, int, int, int, const int16_t *, intptr_t, const int16_t *, intptr_t,
+                     uint16_t *, intptr_t);
+  void (*filter_copy_bipred[2])(int, int, int16_t, int, const uint16_t *, ptrdiff_t, int16_t *, ptrdiff_t);
+  void (*filter_h_sample_sample[2])(int, int, int, const int16_t *, const uint16_t *, ptrdiff_t, uint16_t *, ptrdiff_t);
+  void (*filter_h_sample_short[2])(int, int, int, const int16_t *, const uint16_t *, ptrdiff_t, int16_t *, ptrdiff_t);
+  void (*filter_v_sample_sample[2])(int, int, int, const int16_t *, const uint16_t *, ptrdiff_t, uint16_t *, ptrdiff_t);
+  void (*filter_v_sample_short[2])(int, int, int, const int16_t *, const uint16_t *, ptrdiff_t, int16_t *, ptrdiff_t);
+  void (*filter_v_short_sample[2])(int, int, int, const int16_t *, const int16_t *, ptrdiff_t, uint16_t *, ptrdiff_t);
+  void (*filter_v_short_short[2])(int, int, int, const int16_t *, const int16_t *, ptrdiff_t, int16_t *, ptrdiff_t);
+} xvcb200_inter_prediction_simd_func;   /* == InterPrediction::SimdFunc, inter_prediction.h:176-216 */
+
+typedef struct {
+  int (*sad_sample_sample[7])(int, int, const uint16_t *, ptrdiff_t, const uint16_t *, ptrdiff_t);
+  int (*sad_short_sample[7])(int, int, const int16_t *, ptrdiff_t, const uint16_t *, ptrdiff_t);
+  uint64_t (*ssd_sample_sample[7])(int, int, const uint16_t *, ptrdiff_t, const uint16_t *, ptrdiff_t);
+  uint64_t (*ssd_short_sample[7])(int, int, const int16_t *, ptrdiff_t, const uint16_t *, ptrdiff_t);
+  uint64_t (*ssd_short_short[7])(int, int, const int16_t *, ptrdiff_t, const int16_t *, ptrdiff_t);
+} xvcb200_sample_metric_simd_func;      /* == SampleMetric::SimdFunc, sample_metric.h:166-191 */
+
+/* simd::InterPredictionSimd::Register / simd::SampleMetricSimd::Register equivalents
+ * (simd/inter_prediction_simd.h:36-39, simd/sample_metric_simd.h:36-40). */
+void xvcb200_register_inter_prediction(xvcb200_inter_prediction_simd_func *table);
+void xvcb200_register_sample_metric(int bitdepth, xvcb200_sample_metric_simd_func *table);
+
+/* Transform types, numbering of TransformType (xvc_common_lib/cu_types.h). */
+enum { XVCB200_TX_DEFAULT = 0, XVCB200_TX_DCT2 = 1, XVCB200_TX_DCT5 = 2, XVCB200_TX_DCT8 = 3,
+       XVCB200_TX_DST1 = 4, XVCB200_TX_DST7 = 5 };
+
+/* ForwardTransform::Transform (transform.cc:869-961) / TransformSkip (:963-995).
+ * tx_hor/tx_ver = cu.GetTransformType(comp,1)/(comp,0); dst4x4 = can_dst_4x4 (:874-876). */
+void xvcb200_fwd_transform(int width, int height, int bitdepth, int tx_hor, int tx_ver, int dst4x4,
+                           const int16_t *resi, ptrdiff_t resi_stride, int16_t *coeff, ptrdiff_t coeff_stride);
+void xvcb200_fwd_transform_skip(int width, int height, int bitdepth,
+                                const int16_t *resi, ptrdiff_t resi_stride, int16_t *coeff, ptrdiff_t coeff_stride);
+/* InverseTransform::Transform (transform.cc:83-182), TransformSkip (:184-215). */
+void xvcb200_inv_transform(int width, int height, int bitdepth, int tx_hor, int tx_ver, int dst4x4, int dc_only,
+                           const int16_t *coeff, ptrdiff_t coeff_stride, int16_t *resi, ptrdiff_t resi_stride);
+void xvcb200_inv_transform_skip(int width, int height, int bitdepth,
+                                const int16_t *coeff, ptrdiff_t coeff_stride, int16_t *resi, ptrdiff_t resi_stride);
+
+/* Qp (quantize.cc:48-92): per-component derived values. */
+typedef struct {
+  int32_t qp_raw[3];       /* after chroma table/offset */
+  int32_t qp_bitdepth[3];  /* qp_raw + 6*(bitdepth-8), >= 0 */
+  double distortion_weight[3];
+  double lambda[3];
+  double lambda_sqrt;
+} xvcb200_qp;
+void xvcb200_qp_init(xvcb200_qp *out, int qp, int chroma_format /*0:400 1:420 2:422 3:444*/, int bitdepth,
+                     double lambda, int chroma_offset_table, int chroma_offset_u, int chroma_offset_v);
+
+/* RdoQuant::QuantFast (rdo_quant.cc:156-201) incl. CoeffSignHideFast (:448-573).
+ * qp_bitdepth = Qp::qp_bitdepth_[comp]; scan_order 0 diagonal, 1 horizontal, 2 vertical
+ * (TransformHelper::DetermineScanOrder, transform.cc:1614-1636).  Returns num_non_zero. */
+int xvcb200_quant_fast(int width, int height, int bitdepth, int qp_bitdepth, int intra_picture,
+                       int sign_hiding, int scan_order,
+                       const int16_t *in, ptrdiff_t in_stride, int16_t *out, ptrdiff_t out_stride);
+/* Quantize::Inverse (quantize.cc:94-125). */
+void xvcb200_dequant(int width, int height, int bitdepth, int qp_bitdepth,
+                     const int16_t *in, ptrdiff_t in_stride, int16_t *out, ptrdiff_t out_stride);
+
+/* ------------------------------------------------------------------------------------
+ * (B) batched, device-resident
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct xvcb200_ctx xvcb200_ctx;
+
+/* Geometry of a device picture slot.  Planes are padded like YuvPicture(padding=true)
+ * (yuv_pic.cc:32-68: 80 luma / 40 chroma samples on every side are addressable), with a
+ * 128-byte aligned pitch and x=0 on a 128-byte boundary. */
+typedef struct {
+  int32_t width[3], height[3];
+  int32_t pitch[3];        /* elements */
+  int32_t margin_x[3];     /* allocated columns left of x=0 (>= 80 / 40) */
+  int32_t margin_y[3];     /* allocated rows above y=0 (80 / 40) */
+} xvcb200_plane_geom;
+
+/* One coding unit (leaf of the CU tree).  What CodingUnit carries for this path
+ * (coding_unit.h:62-74, cu_types.h). */
+typedef struct {
+  int16_t x, y;            /* luma position */
+  uint8_t w, h;            /* luma size, 4..64 */
+  uint8_t depth;           /* cu.GetDepth() (quad depth); 0 disables prev-MV start (inter_tz_search.cc:115) */
+  uint8_t flags;           /* XVCB200_CU_* */
+  int8_t qp;               /* raw luma QP of the CU (cu.GetQp(kY)) */
+  int8_t ref_idx[2];       /* -1: list unused */
+  uint8_t tx_select;       /* reserved (0 = DCT-2 both directions) */
+  int32_t mv[2][2];        /* [list][x,y], 1/16 pel */
+} xvcb200_cu;
+enum { XVCB200_CU_INTRA = 1, XVCB200_CU_FULLPEL_MV = 2, XVCB200_CU_CBF_Y = 4, XVCB200_CU_CBF_U = 8,
+       XVCB200_CU_CBF_V = 16, XVCB200_CU_SKIP_ME = 32 };
+
+/* Motion estimation job: InterSearch::MotionEstNormal (inter_search.cc:606-662) for one
+ * (CU, reference picture): TzSearch::Search (inter_tz_search.cc:84-171) then SubpelSearch
+ * (inter_search.cc:893-949). */
+typedef struct {
+  int32_t cu;              /* index into the CU array */
+  int32_t ref_slot;        /* picture slot of the (padded) reference */
+  int32_t search_range;    /* InterSearch::GetSearchRangeUniPred (inter_search.cc:1050-1057) */
+  int32_t mvp[2];          /* predictor, 1/16 pel */
+  int32_t prev[2];         /* previous full-pel search result (previous_fullpel_, inter_search.cc:636) */
+  int32_t list;            /* 0/1: which ref list this job belongs to (for the picture pipeline) */
+} xvcb200_me_job;
+
+typedef struct {
+  int32_t mv_fullpel[2];   /* TzSearch::Search result */
+  int32_t mv[2];           /* after SubpelSearch, 1/16 pel */
+  uint32_t cost_fullpel;   /* state.cost_best */
+  uint32_t dist;           /* *out_dist (SATD of the best sub-pel candidate) */
+  uint32_t cost;           /* best_cost of the sub-pel search */
+  uint32_t num_sad;        /* candidates evaluated (statistics; not in the reference) */
+} xvcb200_me_result;
+
+/* InterSearch::FullSearch (inter_search.cc:853-891): +-range around the clipped window on
+ * the weighted original 2*orig - pred_other (sample_buffer.h:147-161). */
+typedef struct {
+  int32_t cu, ref_slot, other_pred_slot;
+  int32_t mvp[2];
+  int32_t center[2];       /* mv_bootstrap / mvp used for DetermineMinMaxMv, 1/16 pel */
+  int32_t range;
+} xvcb200_fullsearch_job;
+
+/* One transform unit = one component of one CU: TransformEncoder::TransformAndReconstruct
+ * (transform_encoder.cc:203-285) with QuantFast.  Output levels are written to a
+ * picture-shaped int16 plane set ("coefficient slot"). */
+typedef struct {
+  uint32_t ssd;            /* Sum d^2 >> 2(bd-8), before chroma weight */
+  int32_t num_non_zero;
+} xvcb200_tu_result;
+
+/* Per-4x4 metadata for deblocking (what GetBoundaryStrength reads through
+ * PictureData::GetCuAt, deblocking_filter.cc:154-241).  Built on device from the CU array. */
+
+int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int bitdepth,
+                       int chroma_format, int num_slots);
+void xvcb200_ctx_destroy(xvcb200_ctx *ctx);
+/* run on a caller-owned stream (cudaStream_t as void*); 0 = the context's own stream */
+int xvcb200_ctx_set_stream(xvcb200_ctx *ctx, void *cuda_stream);
+int xvcb200_sync(xvcb200_ctx *ctx);                 /* waits, returns sticky status */
+const char *xvcb200_ctx_error_string(xvcb200_ctx *ctx);
+int xvcb200_get_geometry(xvcb200_ctx *ctx, xvcb200_plane_geom *geom);
+/* device address of sample (0,0) of a plane of a slot (uint16_t*); coefficient slots: int16_t* */
+int xvcb200_slot_ptr(xvcb200_ctx *ctx, int slot, int comp, void **dev_ptr);
+
+/* host <-> device picture transfer; host planes are tight or strided (elements). */
+int xvcb200_upload_picture(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]);
+int xvcb200_download_picture(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]);
+int xvcb200_download_coeff(xvcb200_ctx *ctx, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]);
+/* YuvPicture::PadBorder (yuv_pic.cc:118-150) */
+int xvcb200_pad_border(xvcb200_ctx *ctx, int slot);
+
+/* CU array upload (host -> device list owned by the context). */
+int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n);
+int xvcb200_get_cus(xvcb200_ctx *ctx, xvcb200_cu *cus, int n);
+
+/* lambda_sqrt = Qp::GetLambdaSqrt(); lambda_me = floor(65536*lambda_sqrt) is derived inside. */
+int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *jobs, int n,
+                      double lambda_sqrt, xvcb200_me_result *results);
+int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearch_job *jobs, int n,
+                        double lambda_sqrt, xvcb200_me_result *results);
+
+/* InterPrediction::MotionCompensation (inter_prediction.cc:710-738) for every CU in the
+ * context's CU array, all three components, into pred_slot.  ref_slots[list][ref_idx]. */
+int xvcb200_motion_compensate(xvcb200_ctx *ctx, const int32_t ref_slots[2][5], int pred_slot);
+
+/* TransformAndReconstruct for every CU x component: residual = orig - pred, forward
+ * transform, QuantFast, dequant, inverse transform, AddClip into rec_slot; levels into
+ * coeff_slot; per-TU results[3*n_cus] (order: cu-major, component-minor); cbf flags are
+ * written back into the device CU array. */
+int xvcb200_tq_reconstruct(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slot, int coeff_slot,
+                           int pic_qp_unused, int intra_picture, int chroma_offset_table,
+                           int chroma_offset_u, int chroma_offset_v, xvcb200_tu_result *results);
+/* decoder side: CuDecoder::DecompressComponent (cu_decoder.cc:102-138) from levels */
+int xvcb200_dequant_reconstruct(xvcb200_ctx *ctx, int pred_slot, int rec_slot, int coeff_slot,
+                                int chroma_offset_table, int chroma_offset_u, int chroma_offset_v);
+
+/* DeblockingFilter::DeblockPicture (deblocking_filter.cc:56-77) on rec_slot in place,
+ * using the context's CU array.  pic_type: 0 bi, 1 uni (PicturePredictionType).
+ * ref_poc[list][ref_idx]: POC of each reference (CodingUnit::GetRefPoc). */
+int xvcb200_deblock_picture(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_offset, int tc_offset,
+                            const int64_t ref_poc[2][5]);
+
+/* ------------------------------------------------------------------------------------
+ * (C) picture-level hot path
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t orig_slot, pred_slot, rec_slot, coeff_slot;
+  int32_t ref_slots[2][5];
+  int64_t ref_poc[2][5];
+  int32_t num_ref[2];
+  int32_t pic_type;                  /* 0 bi, 1 uni */
+  int32_t search_range[2][5];
+  double lambda_sqrt;
+  int32_t chroma_offset_table, chroma_offset_u, chroma_offset_v;
+  int32_t beta_offset, tc_offset;
+  int32_t deblock, pad;
+} xvcb200_picture_params;
+
+/* ME for every (CU, list 0/1 ref_idx 0) with the CU's mv[list] as predictor -> best list
+ * by cost -> MC -> T/Q/recon -> deblock -> pad.  Results: per-CU chosen mv/ref written back
+ * into the CU array, me_results[2*n] (may be NULL), tu_results[3*n] (may be NULL). */
+int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *params,
+                           xvcb200_me_result *me_results, xvcb200_tu_result *tu_results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* XVC_B200_H_ */

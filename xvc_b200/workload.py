@@ -1,0 +1,126 @@
+"""Synthetic workloads for tests and bench.py: YUV 4:2:0 content and CU partitions.
+
+Content generator = the one BASELINE.md section 2 records for the reference probes
+(seed 1234): 8x8-block uniform noise in [0,255], 5x5 box filter, + N(0,6) per-pixel noise,
+clipped to 8 bit; frame i is the (W x H) crop at offset (2i mod 32, i mod 32);
+U = 128 + 0.25*(Y_sub - 128), V = 128 - 0.25*(Y_sub - 128).  Samples are returned at the
+encoder's internal bit depth (8-bit input shifted left by bitdepth-8, as
+Resampler::ConvertFrom does for the default 10-bit internal pipeline, encoder.cc:445-480).
+"""
+import numpy as np
+
+from . import abi
+
+
+def synth_canvas(width, height, seed=1234):
+    rng = np.random.default_rng(seed)
+    cw, ch = width + 64, height + 64
+    blocks = rng.integers(0, 256, size=((ch + 7) // 8, (cw + 7) // 8)).astype(np.float64)
+    img = np.kron(blocks, np.ones((8, 8)))[:ch, :cw]
+    pad = np.pad(img, 2, mode="edge")
+    box = np.zeros_like(img)
+    for dy in range(5):
+        for dx in range(5):
+            box += pad[dy:dy + ch, dx:dx + cw]
+    box /= 25.0
+    box += rng.normal(0.0, 6.0, size=box.shape)
+    return np.clip(np.rint(box), 0, 255).astype(np.uint16)
+
+
+def synth_frame(canvas, width, height, index, bitdepth=10):
+    """Returns (Y, U, V) uint16 planes (tight) of frame `index`."""
+    ox, oy = (2 * index) % 32, index % 32
+    y8 = canvas[oy:oy + height, ox:ox + width].astype(np.int32)
+    sub = (y8[0::2, 0::2] + y8[0::2, 1::2] + y8[1::2, 0::2] + y8[1::2, 1::2] + 2) >> 2
+    u8 = np.clip(np.rint(128 + 0.25 * (sub - 128)), 0, 255).astype(np.int32)
+    v8 = np.clip(np.rint(128 - 0.25 * (sub - 128)), 0, 255).astype(np.int32)
+    sh = bitdepth - 8
+    return tuple(np.ascontiguousarray((p << sh).astype(np.uint16)) for p in (y8, u8, v8))
+
+
+def random_frame(width, height, bitdepth, rng):
+    """Uniform random samples over the full legal range (worst case for arithmetic)."""
+    hi = 1 << bitdepth
+    return (rng.integers(0, hi, size=(height, width), dtype=np.uint16),
+            rng.integers(0, hi, size=(height // 2, width // 2), dtype=np.uint16),
+            rng.integers(0, hi, size=(height // 2, width // 2), dtype=np.uint16))
+
+
+def make_partition(width, height, seed=7, min_size=8, max_size=64, qp=32, uniform=None):
+    """Leaf CUs covering the picture, as an abi.cu_dtype array.
+
+    Every 64x64 CTU is split recursively (quad / horizontal / vertical binary / none) by a
+    seeded RNG; CUs that cross the picture edge are always split (the reference forces
+    those splits too, cu_encoder.cc:123-273).  `uniform=N` gives an N x N grid instead.
+    CU dimensions are powers of two in [min_size, max_size]; width/height must be
+    multiples of 8 (SegmentHeader internal size, segment_header.h:51-62).
+    """
+    assert width % 8 == 0 and height % 8 == 0
+    rng = np.random.default_rng(seed)
+    out = []
+
+    def emit(x, y, w, h, depth):
+        out.append((x, y, w, h, depth))
+
+    def split(x, y, w, h, depth):
+        if x >= width or y >= height:
+            return
+        over_x, over_y = x + w > width, y + h > height
+        if uniform is not None:
+            want = "quad" if (w > uniform or h > uniform) else "none"
+            if want == "none" and (over_x or over_y):
+                want = "quad"
+        elif over_x or over_y or w > max_size or h > max_size:
+            want = "quad" if w == h and w > 8 else ("ver" if over_x or w > h else "hor")
+        else:
+            opts, probs = ["none"], [0.30 + 0.5 * (w * h <= 256)]
+            if w == h and w > 8 and w // 2 >= min_size:
+                opts.append("quad"); probs.append(0.40)
+            if h // 2 >= min_size:
+                opts.append("hor"); probs.append(0.15)
+            if w // 2 >= min_size:
+                opts.append("ver"); probs.append(0.15)
+            p = np.array(probs) / sum(probs)
+            want = opts[int(rng.choice(len(opts), p=p))]
+        if want == "none":
+            emit(x, y, w, h, depth)
+        elif want == "quad":
+            hw, hh = w // 2, h // 2
+            for (sx, sy) in ((x, y), (x + hw, y), (x, y + hh), (x + hw, y + hh)):
+                split(sx, sy, hw, hh, depth + 1)
+        elif want == "hor":
+            split(x, y, w, h // 2, depth + 1)
+            split(x, y + h // 2, w, h // 2, depth + 1)
+        else:
+            split(x, y, w // 2, h, depth + 1)
+            split(x + w // 2, y, w // 2, h, depth + 1)
+
+    for cy in range(0, height, 64):
+        for cx in range(0, width, 64):
+            split(cx, cy, 64, 64, 0)
+    cus = np.zeros(len(out), dtype=abi.cu_dtype)
+    for i, (x, y, w, h, d) in enumerate(out):
+        cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"], cus[i]["depth"] = x, y, w, h, d
+    cus["qp"] = qp
+    cus["ref_idx"] = -1
+    return cus
+
+
+def check_partition(cus, width, height):
+    """True when the CUs tile the picture exactly once."""
+    cover = np.zeros((height // 4, width // 4), dtype=np.int32)
+    for c in cus:
+        cover[c["y"] // 4:(c["y"] + c["h"]) // 4, c["x"] // 4:(c["x"] + c["w"]) // 4] += 1
+    return bool((cover == 1).all())
+
+
+def lambda_for_qp(qp, pic_type_factor=0.68):
+    """PictureEncoder::CalculateLambda (picture_encoder.cc:313-354) for a non-hierarchical
+    inter picture with sub-GOP length 1: 0.68 * 2^((qp-12)/3)."""
+    return pic_type_factor * 2.0 ** ((qp - 12) / 3.0)
+
+
+def search_range_uni(poc, ref_poc, sub_gop_length=16, rmin=96, rmax=256):
+    """InterSearch::GetSearchRangeUniPred, inter_search.cc:1050-1057."""
+    r = (rmax * abs(poc - ref_poc) + sub_gop_length // 2) // sub_gop_length
+    return max(rmin, min(rmax, r))
