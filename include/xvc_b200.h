@@ -51,6 +51,9 @@ void xvcb200_clear_error(void);
 /* number of kernels this library has launched since load (bench.py gpu_launches) */
 uint64_t xvcb200_launch_count(void);
 const char *xvcb200_version(void);
+/* sizeof() of the structs below as compiled (0 cu, 1 me_job, 2 me_result, 3 fullsearch_job,
+ * 4 tu_result, 5 picture_params, 6 plane_geom, 7 qp) -- lets bindings verify their layout */
+int xvcb200_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------
  * (A) table-shaped entry points, host pointers
@@ -216,7 +219,7 @@ enum { XVCB200_CU_INTRA = 1, XVCB200_CU_FULLPEL_MV = 2, XVCB200_CU_CBF_Y = 4, XV
  * (inter_search.cc:893-949). */
 typedef struct {
   int32_t cu;              /* index into the CU array */
-  int32_t ref_slot;        /* picture slot of the (padded) reference */
+  int32_t ref_slot;        /* picture slot of the (padded) reference picture */
   int32_t search_range;    /* InterSearch::GetSearchRangeUniPred (inter_search.cc:1050-1057) */
   int32_t mvp[2];          /* predictor, 1/16 pel */
   int32_t prev[2];         /* previous full-pel search result (previous_fullpel_, inter_search.cc:636) */
@@ -257,6 +260,7 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
 void xvcb200_ctx_destroy(xvcb200_ctx *ctx);
 /* run on a caller-owned stream (cudaStream_t as void*); 0 = the context's own stream */
 int xvcb200_ctx_set_stream(xvcb200_ctx *ctx, void *cuda_stream);
+void *xvcb200_stream(xvcb200_ctx *ctx);              /* the cudaStream_t work is enqueued on */
 int xvcb200_sync(xvcb200_ctx *ctx);                 /* waits, returns sticky status */
 const char *xvcb200_ctx_error_string(xvcb200_ctx *ctx);
 int xvcb200_get_geometry(xvcb200_ctx *ctx, xvcb200_plane_geom *geom);
@@ -267,6 +271,9 @@ int xvcb200_slot_ptr(xvcb200_ctx *ctx, int slot, int comp, void **dev_ptr);
 int xvcb200_upload_picture(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]);
 int xvcb200_download_picture(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]);
 int xvcb200_download_coeff(xvcb200_ctx *ctx, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]);
+int xvcb200_upload_coeff(xvcb200_ctx *ctx, int slot, const int16_t *const planes[3], const ptrdiff_t strides[3]);
+/* one plane incl. its 80 / 40 sample border, tight (h + 2*pad) x (w + 2*pad) */
+int xvcb200_download_padded(xvcb200_ctx *ctx, int slot, int comp, uint16_t *dst);
 /* YuvPicture::PadBorder (yuv_pic.cc:118-150) */
 int xvcb200_pad_border(xvcb200_ctx *ctx, int slot);
 
@@ -300,6 +307,11 @@ int xvcb200_dequant_reconstruct(xvcb200_ctx *ctx, int pred_slot, int rec_slot, i
  * ref_poc[list][ref_idx]: POC of each reference (CodingUnit::GetRefPoc). */
 int xvcb200_deblock_picture(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_offset, int tc_offset,
                             const int64_t ref_poc[2][5]);
+/* same with the segment's chroma QP mapping (SegmentHeader chroma_qp_offset_table / _u / _v); the
+ * short form uses table 1, offsets 0 (encoder defaults, encoder_settings.h:93-95) */
+int xvcb200_deblock_picture_ex(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_offset, int tc_offset,
+                               int chroma_offset_table, int chroma_offset_u, int chroma_offset_v,
+                               const int64_t ref_poc[2][5]);
 
 /* ------------------------------------------------------------------------------------
  * (C) picture-level hot path

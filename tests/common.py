@@ -1,0 +1,111 @@
+"""Shared input builders for the parity tests (seeded; no reference access at run time)."""
+import numpy as np
+
+from oracle.bindings import Picture
+from xvc_b200 import abi, workload
+
+SIZES = [4, 8, 16, 32, 64]
+CSIZES = [2, 4, 8, 16, 32]
+
+
+def rnd_samples(rng, h, w, bd):
+    return rng.integers(0, 1 << bd, size=(h, w), dtype=np.uint16)
+
+
+def rnd_resi(rng, h, w, bd):
+    return rng.integers(-(1 << bd) + 1, 1 << bd, size=(h, w)).astype(np.int16)
+
+
+def frames(width, height, bd, seed, content="synth"):
+    """(current, ref L0, ref L1) frame triples."""
+    rng = np.random.default_rng(seed)
+    if content == "synth":
+        canvas = workload.synth_canvas(width, height, seed)
+        return [workload.synth_frame(canvas, width, height, i, bd) for i in (8, 0, 16)]
+    return [workload.random_frame(width, height, bd, rng) for _ in range(3)]
+
+
+def me_jobs(cus, rng, nl, ranges, spread, slots=(0, 0)):
+    jobs = np.zeros(len(cus) * nl, dtype=abi.me_job_dtype)
+    for i in range(len(cus)):
+        for l in range(nl):
+            j = jobs[i * nl + l]
+            j["cu"], j["list"], j["ref_slot"] = i, l, slots[l]
+            j["search_range"] = ranges[l]
+            j["mvp"] = rng.integers(-spread, spread + 1, size=2)
+            j["prev"] = rng.integers(-spread // 16 - 1, spread // 16 + 2, size=2)
+    return jobs
+
+
+def mc_cus(width, height, rng, seed, min_size=4):
+    cus = workload.make_partition(width, height, seed=seed, min_size=min_size)
+    for i in range(len(cus)):
+        mode = i % 3
+        cus[i]["ref_idx"] = [(0, -1), (-1, 0), (0, 0)][mode]
+        cus[i]["mv"] = rng.integers(-3000, 3001, size=(2, 2))
+        if i % 5 == 0:
+            cus[i]["mv"] = (rng.integers(-20, 21, size=(2, 2)) * 16)
+        if mode == 0:
+            cus[i]["mv"][1] = 0
+        if mode == 1:
+            cus[i]["mv"][0] = 0
+    return cus
+
+
+def deblock_cus(width, height, rng, seed, min_size, pic_type):
+    cus = workload.make_partition(width, height, seed=seed, min_size=min_size)
+    n = len(cus)
+    cus["qp"] = rng.integers(25, 45, size=n)
+    flags = np.zeros(n, dtype=np.uint8)
+    flags[rng.random(n) < 0.15] |= abi.CU_INTRA
+    flags[rng.random(n) < 0.4] |= abi.CU_CBF_Y
+    cus["flags"] = flags
+    for i in range(n):
+        if flags[i] & abi.CU_INTRA:
+            cus[i]["ref_idx"] = (-1, -1)
+            continue
+        mode = rng.integers(0, 3) if pic_type == 0 else 0
+        cus[i]["ref_idx"] = [(0, -1), (-1, 0), (0, 0)][mode]
+        base = rng.integers(-2, 3, size=(2, 2)) * 16
+        cus[i]["mv"] = base + rng.integers(-10, 11, size=(2, 2))
+        if mode == 0:
+            cus[i]["mv"][1] = 0
+        if mode == 1:
+            cus[i]["mv"][0] = 0
+    return cus
+
+
+def blocky_recon(cur, cus, rng, bd):
+    """A reconstruction with real block edges: per-CU DC offsets on top of the source."""
+    recp = [p.astype(np.int32) for p in cur]
+    for cu in cus:
+        off = int(rng.integers(-6, 7)) << (bd - 8)
+        recp[0][cu["y"]:cu["y"] + cu["h"], cu["x"]:cu["x"] + cu["w"]] += off
+        for c in (1, 2):
+            recp[c][cu["y"] // 2:(cu["y"] + cu["h"]) // 2, cu["x"] // 2:(cu["x"] + cu["w"]) // 2] += off
+    return [np.clip(p, 0, (1 << bd) - 1).astype(np.uint16) for p in recp]
+
+
+def picture_params(pic_type, lam, ranges=(128, 128), pocs=(0, 16), slots=None, deblock=1, pad=1):
+    prm = np.zeros(1, dtype=abi.picture_params_dtype)
+    prm["pic_type"] = pic_type
+    prm["search_range"][0, 0, 0], prm["search_range"][0, 1, 0] = ranges
+    prm["lambda_sqrt"] = np.sqrt(lam)
+    prm["chroma_offset_table"] = 1
+    prm["ref_poc"][0, 0, 0], prm["ref_poc"][0, 1, 0] = pocs
+    prm["num_ref"] = 1
+    prm["deblock"], prm["pad"] = deblock, pad
+    prm["ref_slots"] = -1
+    if slots is not None:
+        prm["orig_slot"], prm["pred_slot"], prm["rec_slot"], prm["coeff_slot"] = slots["orig"], slots["pred"], slots["rec"], slots["coeff"]
+        prm["ref_slots"][0, 0, 0], prm["ref_slots"][0, 1, 0] = slots["ref0"], slots["ref1"]
+    return prm
+
+
+def oracle_refs(oracle, width, height, r0, r1=None):
+    refs = {(0, 0): Picture(width, height, 80, r0)}
+    oracle.pad_border(refs[(0, 0)])
+    if r1 is not None:
+        refs[(1, 0)] = Picture(width, height, 80, r1)
+        oracle.pad_border(refs[(1, 0)])
+    return refs

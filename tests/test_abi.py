@@ -1,0 +1,56 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol
+include/xvc_b200.h declares, the struct layouts match the Python mirrors, and the product
+fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from xvc_b200 import abi, lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = lib.load()
+    header = open(os.path.join(ROOT, "include", "xvc_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(xvcb200_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) > 50
+    for name in declared:
+        assert hasattr(L, name), "libxvc_b200.so does not export %s" % name
+    assert sorted(set(lib.EXPORTS)) == declared
+    assert b"sm_100a" in L.xvcb200_version()
+
+
+def test_struct_layouts_match_header():
+    L = lib.load()
+    for which, (name, dt) in abi.ABI_STRUCTS.items():
+        assert L.xvcb200_abi_sizeof(which) == dt.itemsize, name
+    assert abi.cu_dtype.fields["mv"][1] == 12 and abi.cu_dtype.fields["flags"][1] == 7
+
+
+def test_qp_init_host_side():
+    # pure host arithmetic (Qp::Qp, quantize.cc:48-92): 4:2:0 chroma table at qp 32 / 10 bit
+    q = lib.qp_init(32, 10, lam=57.9)
+    assert list(q["qp_raw"]) == [32, 31, 31] and list(q["qp_bitdepth"]) == [44, 43, 43]
+    assert q["distortion_weight"][0] == 1.0 and abs(q["distortion_weight"][1] - 2 ** (1 / 3.0)) < 1e-12
+    assert q["lambda_sqrt"] == np.sqrt(57.9)
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(lib.XvcB200Error):
+        lib.Context(64, 64)
+    a = np.zeros((8, 8), dtype=np.uint16)
+    with pytest.raises(lib.XvcB200Error):
+        lib.sad(a, a, 8, 8)

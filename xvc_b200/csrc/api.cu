@@ -1,0 +1,708 @@
+// C-ABI layer of libxvc_b200.so (include/xvc_b200.h): context and picture-slot management,
+// host<->device staging for the table-shaped entry points, and the per-picture pipeline.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "xvcb_internal.h"
+
+namespace xvcb {
+
+cudaError_t launch_tq_reconstruct_classes(cudaStream_t s, xvcb200_cu *d_cus, const int *d_tu_list,
+                                          const int class_count[7][7], const int class_offset[7][7],
+                                          const TqParams &p, Pic3 orig, Pic3 pred, Pic3 rec, int16_t *const lev[3],
+                                          const int lev_pitch[3], xvcb200_tu_result *d_res);
+
+static thread_local int t_last_error = XVCB200_OK;
+static thread_local char t_last_error_str[256] = "";
+
+void set_last_error(int code, const char *what) {
+  if (t_last_error == XVCB200_OK) {
+    t_last_error = code;
+    snprintf(t_last_error_str, sizeof(t_last_error_str), "%s", what);
+  }
+}
+
+void *xvcb_ctx_impl::scratch(size_t bytes) {
+  if (bytes > scratch_bytes) {
+    if (d_scratch) { cudaStreamSynchronize(stream); cudaFree(d_scratch); d_scratch = nullptr; }
+    size_t want = bytes + bytes / 4 + 4096;
+    if (!check(cudaMalloc(&d_scratch, want), "cudaMalloc(scratch)")) { scratch_bytes = 0; return nullptr; }
+    scratch_bytes = want;
+  }
+  return d_scratch;
+}
+void *xvcb_ctx_impl::scratch2(size_t bytes) {
+  if (bytes > scratch2_bytes) {
+    if (d_scratch2) { cudaStreamSynchronize(stream); cudaFree(d_scratch2); d_scratch2 = nullptr; }
+    size_t want = bytes + bytes / 4 + 4096;
+    if (!check(cudaMalloc(&d_scratch2, want), "cudaMalloc(scratch2)")) { scratch2_bytes = 0; return nullptr; }
+    scratch2_bytes = want;
+  }
+  return d_scratch2;
+}
+void *xvcb_ctx_impl::pinned(size_t bytes) {
+  if (bytes > pinned_bytes) {
+    if (h_pinned) { cudaStreamSynchronize(stream); cudaFreeHost(h_pinned); h_pinned = nullptr; }
+    size_t want = bytes + bytes / 4 + 4096;
+    if (!check(cudaMallocHost(&h_pinned, want), "cudaMallocHost")) { pinned_bytes = 0; return nullptr; }
+    pinned_bytes = want;
+  }
+  return h_pinned;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread staging context for the table-shaped (host pointer, one block) entry points
+// ------------------------------------------------------------------------------------------
+struct Leaf {
+  cudaStream_t stream = nullptr;
+  uint8_t *d = nullptr;       // device staging
+  uint8_t *h = nullptr;       // pinned host staging
+  static constexpr size_t kBytes = 1 << 20;
+  bool ok = false;
+  bool init() {
+    if (ok) return true;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      set_last_error(XVCB200_NO_DEVICE, "no CUDA device: xvc_b200 has no CPU fallback");
+      return false;
+    }
+    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&d, kBytes) != cudaSuccess || cudaMallocHost(&h, kBytes) != cudaSuccess) {
+      set_last_error(XVCB200_CUDA_ERROR, cudaGetErrorString(cudaGetLastError()));
+      return false;
+    }
+    ok = true;
+    return true;
+  }
+  bool done(cudaError_t e) {
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_last_error(XVCB200_CUDA_ERROR, cudaGetErrorString(e)); return false; }
+    return true;
+  }
+};
+static thread_local Leaf t_leaf;
+
+// copies a strided host block (rows x cols elements of esz bytes) into pinned staging at byte
+// offset `off`, tightly packed, and returns the offset after it (16-byte aligned)
+static size_t stage_in(Leaf &L, size_t off, const void *src, ptrdiff_t stride, int rows, int cols, int esz) {
+  const uint8_t *s = static_cast<const uint8_t *>(src);
+  for (int y = 0; y < rows; y++) memcpy(L.h + off + (size_t)y * cols * esz, s + (ptrdiff_t)y * stride * esz, (size_t)cols * esz);
+  return (off + (size_t)rows * cols * esz + 15) & ~(size_t)15;
+}
+static void stage_out(Leaf &L, size_t off, void *dst, ptrdiff_t stride, int rows, int cols, int esz) {
+  uint8_t *d = static_cast<uint8_t *>(dst);
+  for (int y = 0; y < rows; y++) memcpy(d + (ptrdiff_t)y * stride * esz, L.h + off + (size_t)y * cols * esz, (size_t)cols * esz);
+}
+
+static uint64_t leaf_metric(int metric, int bitdepth, int w, int h, int a_short, int b_short, const void *a,
+                            ptrdiff_t sa, const void *b, ptrdiff_t sb, int rows_used_step) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return ~0ull;
+  (void)rows_used_step;
+  size_t off_a = 0;
+  size_t off_b = stage_in(L, off_a, a, sa, h, w, 2);
+  size_t off_o = stage_in(L, off_b, b, sb, h, w, 2);
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t e = launch_block_metric(L.stream, metric, bitdepth, w, h, a_short, b_short, L.d + off_a, w, L.d + off_b, w,
+                                      reinterpret_cast<unsigned long long *>(L.d + off_o));
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, 8, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return ~0ull;
+  uint64_t r;
+  memcpy(&r, L.h + off_o, 8);
+  return r;
+}
+
+}  // namespace xvcb
+
+using namespace xvcb;  // NOLINT
+
+extern "C" {
+
+int xvcb200_last_error(void) { return t_last_error; }
+const char *xvcb200_last_error_string(void) { return t_last_error_str; }
+void xvcb200_clear_error(void) { t_last_error = XVCB200_OK; t_last_error_str[0] = 0; }
+uint64_t xvcb200_launch_count(void) { return g_launch_count.load(); }
+const char *xvcb200_version(void) { return "xvc_b200 0.1 (sm_100a)"; }
+
+int xvcb200_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(xvcb200_cu);
+    case 1: return (int)sizeof(xvcb200_me_job);
+    case 2: return (int)sizeof(xvcb200_me_result);
+    case 3: return (int)sizeof(xvcb200_fullsearch_job);
+    case 4: return (int)sizeof(xvcb200_tu_result);
+    case 5: return (int)sizeof(xvcb200_picture_params);
+    case 6: return (int)sizeof(xvcb200_plane_geom);
+    case 7: return (int)sizeof(xvcb200_qp);
+    default: return -1;
+  }
+}
+
+// ---------------------------------------------------------------- (A) metrics
+int xvcb200_sad_sample_sample(int w, int h, const uint16_t *a, ptrdiff_t sa, const uint16_t *b, ptrdiff_t sb) {
+  return (int)leaf_metric(-1, 8, w, h, 0, 0, a, sa, b, sb, 1);
+}
+int xvcb200_sad_short_sample(int w, int h, const int16_t *a, ptrdiff_t sa, const uint16_t *b, ptrdiff_t sb) {
+  return (int)leaf_metric(-1, 8, w, h, 1, 0, a, sa, b, sb, 1);
+}
+uint64_t xvcb200_ssd_sample_sample(int w, int h, const uint16_t *a, ptrdiff_t sa, const uint16_t *b, ptrdiff_t sb) {
+  return leaf_metric(-2, 8, w, h, 0, 0, a, sa, b, sb, 1);
+}
+uint64_t xvcb200_ssd_short_sample(int w, int h, const int16_t *a, ptrdiff_t sa, const uint16_t *b, ptrdiff_t sb) {
+  return leaf_metric(-2, 8, w, h, 1, 0, a, sa, b, sb, 1);
+}
+uint64_t xvcb200_ssd_short_short(int w, int h, const int16_t *a, ptrdiff_t sa, const int16_t *b, ptrdiff_t sb) {
+  return leaf_metric(-2, 8, w, h, 1, 1, a, sa, b, sb, 1);
+}
+uint64_t xvcb200_compare_sample_sample(int metric, int bitdepth, int w, int h, const uint16_t *a, ptrdiff_t sa,
+                                       const uint16_t *b, ptrdiff_t sb) {
+  return leaf_metric(metric, bitdepth, w, h, 0, 0, a, sa, b, sb, 1);
+}
+uint64_t xvcb200_compare_short_sample(int metric, int bitdepth, int w, int h, const int16_t *a, ptrdiff_t sa,
+                                      const uint16_t *b, ptrdiff_t sb) {
+  return leaf_metric(metric, bitdepth, w, h, 1, 0, a, sa, b, sb, 1);
+}
+
+// ---------------------------------------------------------------- (A) filters
+static void leaf_filter(int kind, int chroma, int w, int h, int bitdepth, const int16_t *filter, const void *src,
+                        ptrdiff_t ss, void *dst, ptrdiff_t ds) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  const int n = chroma ? 4 : 8, before = n / 2 - 1, after = n / 2;
+  const bool hor = kind <= 1;
+  // stage exactly the apron the reference kernel reads
+  const int x0 = hor ? -before : 0, y0 = hor ? 0 : -before;
+  const int cols = w + (hor ? before + after : 0), rows = h + (hor ? 0 : before + after);
+  const uint8_t *s = static_cast<const uint8_t *>(src) + ((ptrdiff_t)y0 * ss + x0) * 2;
+  size_t off_out = stage_in(L, 0, s, ss, rows, cols, 2);
+  cudaMemcpyAsync(L.d, L.h, off_out, cudaMemcpyHostToDevice, L.stream);
+  const uint8_t *dsrc = L.d + ((size_t)(-y0) * cols + (-x0)) * 2;
+  cudaError_t e = launch_block_filter(L.stream, kind, chroma, w, h, bitdepth, filter, dsrc, cols, L.d + off_out, w);
+  cudaMemcpyAsync(L.h + off_out, L.d + off_out, (size_t)w * h * 2, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return;
+  stage_out(L, off_out, dst, ds, h, w, 2);
+}
+void xvcb200_filter_h_sample_sample(int chroma, int w, int h, int bd, const int16_t *f, const uint16_t *s, ptrdiff_t ss, uint16_t *d, ptrdiff_t ds) { leaf_filter(0, chroma, w, h, bd, f, s, ss, d, ds); }
+void xvcb200_filter_h_sample_short(int chroma, int w, int h, int bd, const int16_t *f, const uint16_t *s, ptrdiff_t ss, int16_t *d, ptrdiff_t ds) { leaf_filter(1, chroma, w, h, bd, f, s, ss, d, ds); }
+void xvcb200_filter_v_sample_sample(int chroma, int w, int h, int bd, const int16_t *f, const uint16_t *s, ptrdiff_t ss, uint16_t *d, ptrdiff_t ds) { leaf_filter(2, chroma, w, h, bd, f, s, ss, d, ds); }
+void xvcb200_filter_v_sample_short(int chroma, int w, int h, int bd, const int16_t *f, const uint16_t *s, ptrdiff_t ss, int16_t *d, ptrdiff_t ds) { leaf_filter(3, chroma, w, h, bd, f, s, ss, d, ds); }
+void xvcb200_filter_v_short_sample(int chroma, int w, int h, int bd, const int16_t *f, const int16_t *s, ptrdiff_t ss, uint16_t *d, ptrdiff_t ds) { leaf_filter(4, chroma, w, h, bd, f, s, ss, d, ds); }
+void xvcb200_filter_v_short_short(int chroma, int w, int h, int bd, const int16_t *f, const int16_t *s, ptrdiff_t ss, int16_t *d, ptrdiff_t ds) { leaf_filter(5, chroma, w, h, bd, f, s, ss, d, ds); }
+
+void xvcb200_add_avg(int w, int h, int offset, int shift, int bitdepth, const int16_t *a, intptr_t sa, const int16_t *b,
+                     intptr_t sb, uint16_t *dst, intptr_t ds) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  size_t off_b = stage_in(L, 0, a, sa, h, w, 2);
+  size_t off_o = stage_in(L, off_b, b, sb, h, w, 2);
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t e = launch_block_add_avg(L.stream, w, h, offset, shift, bitdepth, (const int16_t *)L.d, w,
+                                       (const int16_t *)(L.d + off_b), w, (Sample *)(L.d + off_o), w);
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, (size_t)w * h * 2, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return;
+  stage_out(L, off_o, dst, ds, h, w, 2);
+}
+
+void xvcb200_filter_copy_bipred(int w, int h, int16_t offset, int shift, const uint16_t *ref, ptrdiff_t rs, int16_t *pred,
+                                ptrdiff_t ps) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  size_t off_o = stage_in(L, 0, ref, rs, h, w, 2);
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t e = launch_block_copy_bipred(L.stream, w, h, offset, shift, (const Sample *)L.d, w, (int16_t *)(L.d + off_o), w);
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, (size_t)w * h * 2, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return;
+  stage_out(L, off_o, pred, ps, h, w, 2);
+}
+
+static void leaf_interp(int chroma, int bipred, int w, int h, int bitdepth, int fx, int fy, const uint16_t *ref,
+                        ptrdiff_t rs, void *pred, ptrdiff_t ps) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  const int n = chroma ? 4 : 8, before = n / 2 - 1, after = n / 2;
+  const int x0 = fx ? -before : 0, y0 = fy ? -before : 0;
+  const int cols = w + (fx ? before + after : 0), rows = h + (fy ? before + after : 0);
+  size_t off_o = stage_in(L, 0, ref + (ptrdiff_t)y0 * rs + x0, rs, rows, cols, 2);
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  const Sample *dref = (const Sample *)L.d + (size_t)(-y0) * cols + (-x0);
+  cudaError_t e = launch_block_interp(L.stream, chroma, bipred, w, h, bitdepth, fx, fy, dref, cols, L.d + off_o, w);
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, (size_t)w * h * 2, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return;
+  stage_out(L, off_o, pred, ps, h, w, 2);
+}
+void xvcb200_interp_block(int chroma, int w, int h, int bd, int fx, int fy, const uint16_t *ref, ptrdiff_t rs, uint16_t *pred, ptrdiff_t ps) { leaf_interp(chroma, 0, w, h, bd, fx, fy, ref, rs, pred, ps); }
+void xvcb200_interp_block_bipred(int chroma, int w, int h, int bd, int fx, int fy, const uint16_t *ref, ptrdiff_t rs, int16_t *pred, ptrdiff_t ps) { leaf_interp(chroma, 1, w, h, bd, fx, fy, ref, rs, pred, ps); }
+
+// table registration: the reference's tables carry one pointer per [size class] / [luma, chroma];
+// thin adaptors bind the `chroma` argument
+#define XVCB_ADAPT(name, ST, DT)                                                                                         \
+  static void name##_luma(int w, int h, int bd, const int16_t *f, const ST *s, ptrdiff_t ss, DT *d, ptrdiff_t ds) { xvcb200_##name(0, w, h, bd, f, s, ss, d, ds); } \
+  static void name##_chroma(int w, int h, int bd, const int16_t *f, const ST *s, ptrdiff_t ss, DT *d, ptrdiff_t ds) { xvcb200_##name(1, w, h, bd, f, s, ss, d, ds); }
+XVCB_ADAPT(filter_h_sample_sample, uint16_t, uint16_t)
+XVCB_ADAPT(filter_h_sample_short, uint16_t, int16_t)
+XVCB_ADAPT(filter_v_sample_sample, uint16_t, uint16_t)
+XVCB_ADAPT(filter_v_sample_short, uint16_t, int16_t)
+XVCB_ADAPT(filter_v_short_sample, int16_t, uint16_t)
+XVCB_ADAPT(filter_v_short_short, int16_t, int16_t)
+#undef XVCB_ADAPT
+
+void xvcb200_register_inter_prediction(xvcb200_inter_prediction_simd_func *t) {
+  for (int i = 0; i < 2; i++) { t->add_avg[i] = &xvcb200_add_avg; t->filter_copy_bipred[i] = &xvcb200_filter_copy_bipred; }
+#define XVCB_SET(name) t->name[0] = &name##_luma; t->name[1] = &name##_chroma;
+  XVCB_SET(filter_h_sample_sample) XVCB_SET(filter_h_sample_short) XVCB_SET(filter_v_sample_sample)
+  XVCB_SET(filter_v_sample_short) XVCB_SET(filter_v_short_sample) XVCB_SET(filter_v_short_short)
+#undef XVCB_SET
+}
+
+void xvcb200_register_sample_metric(int bitdepth, xvcb200_sample_metric_simd_func *t) {
+  (void)bitdepth;
+  for (int i = 0; i < 7; i++) {   // index = log2(width); the reference leaves [0] null (sample_metric.cc:785-823)
+    t->sad_sample_sample[i] = i ? &xvcb200_sad_sample_sample : nullptr;
+    t->sad_short_sample[i] = i ? &xvcb200_sad_short_sample : nullptr;
+    t->ssd_sample_sample[i] = i ? &xvcb200_ssd_sample_sample : nullptr;
+    t->ssd_short_sample[i] = i ? &xvcb200_ssd_short_sample : nullptr;
+    t->ssd_short_short[i] = i ? &xvcb200_ssd_short_short : nullptr;
+  }
+}
+
+// ---------------------------------------------------------------- (A) transform / quant
+static void leaf_transform(int forward, int w, int h, int bitdepth, int tx_hor, int tx_ver, int dst4x4, int dc_only,
+                           int skip, const int16_t *in, ptrdiff_t is, int16_t *out, ptrdiff_t os) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  size_t off_o = stage_in(L, 0, in, is, h, w, 2);
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t e = launch_block_transform(L.stream, forward, w, h, bitdepth, tx_hor, tx_ver, dst4x4, dc_only, skip,
+                                         (const int16_t *)L.d, w, (int16_t *)(L.d + off_o), w);
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, (size_t)w * h * 2, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return;
+  stage_out(L, off_o, out, os, h, w, 2);
+}
+void xvcb200_fwd_transform(int w, int h, int bd, int tx_hor, int tx_ver, int dst4x4, const int16_t *resi, ptrdiff_t rs, int16_t *coeff, ptrdiff_t cs) { leaf_transform(1, w, h, bd, tx_hor, tx_ver, dst4x4, 0, 0, resi, rs, coeff, cs); }
+void xvcb200_fwd_transform_skip(int w, int h, int bd, const int16_t *resi, ptrdiff_t rs, int16_t *coeff, ptrdiff_t cs) { leaf_transform(1, w, h, bd, 0, 0, 0, 0, 1, resi, rs, coeff, cs); }
+void xvcb200_inv_transform(int w, int h, int bd, int tx_hor, int tx_ver, int dst4x4, int dc_only, const int16_t *coeff, ptrdiff_t cs, int16_t *resi, ptrdiff_t rs) { leaf_transform(0, w, h, bd, tx_hor, tx_ver, dst4x4, dc_only, 0, coeff, cs, resi, rs); }
+void xvcb200_inv_transform_skip(int w, int h, int bd, const int16_t *coeff, ptrdiff_t cs, int16_t *resi, ptrdiff_t rs) { leaf_transform(0, w, h, bd, 0, 0, 0, 0, 1, coeff, cs, resi, rs); }
+
+// Qp::Qp (quantize.cc:48-92): host-side scalar set-up, no device work
+void xvcb200_qp_init(xvcb200_qp *out, int qp, int chroma_format, int bitdepth, double lambda, int table, int off_u, int off_v) {
+  static const uint8_t chroma_scale[58] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19,
+                                           20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 33, 33, 34, 34, 35, 35,
+                                           36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51};
+  const int offs[3] = {0, off_u, off_v};
+  out->lambda_sqrt = std::sqrt(lambda);
+  for (int c = 0; c < 3; c++) {
+    int raw = qp;
+    double weight = 1.0;
+    if (c > 0) {
+      const int base = qp < 0 ? 0 : (qp > 57 ? 57 : qp);
+      int with_off = qp + offs[c];
+      with_off = with_off < 0 ? 0 : (with_off > 57 ? 57 : with_off);
+      raw = with_off;
+      int delta = with_off - base;
+      if (chroma_format == 1 && table == 1) { raw = chroma_scale[with_off]; delta = chroma_scale[with_off] - base; }
+      weight = std::pow(2.0, -delta / 3.0);
+    }
+    out->qp_raw[c] = raw;
+    const int qbd = raw + 6 * (bitdepth - 8);
+    out->qp_bitdepth[c] = qbd < 0 ? 0 : qbd;
+    out->distortion_weight[c] = weight;
+    out->lambda[c] = c == 0 ? lambda : lambda / weight;
+  }
+}
+
+int xvcb200_quant_fast(int w, int h, int bitdepth, int qp_bitdepth, int intra_picture, int sign_hiding, int scan_order,
+                       const int16_t *in, ptrdiff_t is, int16_t *out, ptrdiff_t os) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return -1;
+  size_t off_o = stage_in(L, 0, in, is, h, w, 2);
+  size_t off_n = (off_o + (size_t)w * h * 2 + 15) & ~(size_t)15;
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t e = launch_block_quant(L.stream, w, h, bitdepth, qp_bitdepth, intra_picture, sign_hiding, scan_order,
+                                     (const int16_t *)L.d, w, (int16_t *)(L.d + off_o), w, (int *)(L.d + off_n));
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, off_n + 4 - off_o, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return -1;
+  stage_out(L, off_o, out, os, h, w, 2);
+  int nnz;
+  memcpy(&nnz, L.h + off_n, 4);
+  return nnz;
+}
+
+void xvcb200_dequant(int w, int h, int bitdepth, int qp_bitdepth, const int16_t *in, ptrdiff_t is, int16_t *out, ptrdiff_t os) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  size_t off_o = stage_in(L, 0, in, is, h, w, 2);
+  cudaMemcpyAsync(L.d, L.h, off_o, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t e = launch_block_dequant(L.stream, w, h, bitdepth, qp_bitdepth, (const int16_t *)L.d, w, (int16_t *)(L.d + off_o), w);
+  cudaMemcpyAsync(L.h + off_o, L.d + off_o, (size_t)w * h * 2, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(e)) return;
+  stage_out(L, off_o, out, os, h, w, 2);
+}
+
+// ---------------------------------------------------------------- (B) context
+struct CtxExtra {           // host-side state that is not needed by kernels
+  PlaneView *d_luma_views = nullptr;          // luma PlaneView of every slot
+  int *d_tu_list = nullptr;                   // TU ids (3*cu + comp) grouped by shape class
+  int tu_cap = 0;
+  int class_count[7][7];
+  int class_offset[7][7];
+  xvcb200_me_job *d_jobs = nullptr; xvcb200_me_result *d_me = nullptr; xvcb200_tu_result *d_tu = nullptr;
+  int jobs_cap = 0, me_cap = 0, tu_res_cap = 0;
+};
+
+}  // extern "C"
+
+struct CtxFull : public xvcb200_ctx { CtxExtra ex; };
+static CtxFull *full(xvcb200_ctx *c) { return static_cast<CtxFull *>(c); }
+
+template <typename T> static bool ensure(xvcb200_ctx *c, T **ptr, int *cap, int n) {
+  if (n <= *cap) return true;
+  if (*ptr) { cudaStreamSynchronize(c->stream); cudaFree(*ptr); *ptr = nullptr; }
+  const int want = n + n / 4 + 64;
+  if (!c->check(cudaMalloc(ptr, sizeof(T) * (size_t)want), "cudaMalloc")) { *cap = 0; return false; }
+  *cap = want;
+  return true;
+}
+
+extern "C" {
+
+int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int bitdepth, int chroma_format,
+                       int num_slots) {
+  if (!out) return XVCB200_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (width <= 0 || height <= 0 || width >= 65536 || height >= 65536 || (width & 7) || (height & 7) || bitdepth < 8 ||
+      bitdepth > 12 || num_slots < 1 || num_slots > 64)
+    return XVCB200_INVALID_ARGUMENT;
+  if (chroma_format != 1) return XVCB200_UNSUPPORTED;    // 4:2:0 only on the batched path
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    set_last_error(XVCB200_NO_DEVICE, "no CUDA device: xvc_b200 has no CPU fallback");
+    return XVCB200_NO_DEVICE;
+  }
+  CtxFull *c = new CtxFull();
+  memset(c->ex.class_count, 0, sizeof(c->ex.class_count));
+  memset(c->ex.class_offset, 0, sizeof(c->ex.class_offset));
+  c->device = device; c->width = width; c->height = height; c->bitdepth = bitdepth; c->chroma_format = chroma_format;
+  if (!c->check(cudaSetDevice(device), "cudaSetDevice") ||
+      !c->check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+    int st = c->status; delete c; return st;
+  }
+  c->own_stream = true;
+  size_t plane_bytes[3], total = 0;
+  for (int p = 0; p < 3; p++) {
+    const int cs = p ? 1 : 0;
+    c->geom.width[p] = width >> cs; c->geom.height[p] = height >> cs;
+    c->geom.margin_x[p] = 128 >> cs;            // >= 80/40 (yuv_pic.cc:39-41) and keeps x = 0 on a 128-byte boundary
+    c->geom.margin_y[p] = 80 >> cs;
+    c->geom.pitch[p] = ((c->geom.width[p] + 2 * c->geom.margin_x[p]) + 63) & ~63;
+    plane_bytes[p] = ((size_t)c->geom.pitch[p] * (c->geom.height[p] + 2 * c->geom.margin_y[p]) * 2 + 255) & ~(size_t)255;
+    total += plane_bytes[p];
+  }
+  c->slots.resize(num_slots);
+  std::vector<PlaneView> views(num_slots);
+  for (int s = 0; s < num_slots; s++) {
+    DevPicture &d = c->slots[s];
+    if (!c->check(cudaMalloc(&d.alloc, total), "cudaMalloc(slot)")) { xvcb200_ctx_destroy(c); return XVCB200_OUT_OF_MEMORY; }
+    d.bytes = total;
+    cudaMemsetAsync(d.alloc, 0, total, c->stream);
+    size_t off = 0;
+    for (int p = 0; p < 3; p++) {
+      d.base[p] = reinterpret_cast<Sample *>(d.alloc + off) + (size_t)c->geom.margin_y[p] * c->geom.pitch[p] + c->geom.margin_x[p];
+      off += plane_bytes[p];
+    }
+    views[s] = c->plane(s, 0);
+  }
+  c->map_w = width >> 2; c->map_h = height >> 2;
+  const size_t cells = (size_t)c->map_w * c->map_h;
+  if (!c->check(cudaMalloc(&c->ex.d_luma_views, sizeof(PlaneView) * num_slots), "cudaMalloc(views)") ||
+      !c->check(cudaMemcpyAsync(c->ex.d_luma_views, views.data(), sizeof(PlaneView) * num_slots, cudaMemcpyHostToDevice, c->stream), "memcpy(views)") ||
+      !c->check(cudaMalloc(&c->d_cu_map, sizeof(int32_t) * cells), "cudaMalloc(map)") ||
+      !c->check(cudaMalloc(&c->d_edge_bs[0], cells), "cudaMalloc(bs)") ||
+      !c->check(cudaMalloc(&c->d_edge_bs[1], cells), "cudaMalloc(bs)") ||
+      !c->check(cudaStreamSynchronize(c->stream), "sync")) {
+    int st = c->status; xvcb200_ctx_destroy(c); return st;
+  }
+  *out = c;
+  return XVCB200_OK;
+}
+
+void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
+  if (!ctx) return;
+  CtxFull *c = full(ctx);
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto &s : c->slots) if (s.alloc) cudaFree(s.alloc);
+  cudaFree(c->d_cus); cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
+  cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int xvcb200_ctx_set_stream(xvcb200_ctx *c, void *cuda_stream) {
+  if (!c) return XVCB200_INVALID_ARGUMENT;
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+  if (cuda_stream == nullptr) {
+    if (!c->check(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return c->status;
+    c->own_stream = true;
+  } else {
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+  }
+  return XVCB200_OK;
+}
+
+int xvcb200_sync(xvcb200_ctx *c) {
+  if (!c) return XVCB200_INVALID_ARGUMENT;
+  c->check(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+  return c->status;
+}
+const char *xvcb200_ctx_error_string(xvcb200_ctx *c) { return c ? c->error.c_str() : "null context"; }
+
+int xvcb200_get_geometry(xvcb200_ctx *c, xvcb200_plane_geom *g) {
+  if (!c || !g) return XVCB200_INVALID_ARGUMENT;
+  *g = c->geom;
+  return XVCB200_OK;
+}
+int xvcb200_slot_ptr(xvcb200_ctx *c, int slot, int comp, void **p) {
+  if (!c || !p || slot < 0 || slot >= (int)c->slots.size() || comp < 0 || comp > 2) return XVCB200_INVALID_ARGUMENT;
+  *p = c->slots[slot].base[comp];
+  return XVCB200_OK;
+}
+void *xvcb200_stream(xvcb200_ctx *c) { return c ? c->stream : nullptr; }
+
+static bool slot_ok(xvcb200_ctx *c, int slot) { return c && slot >= 0 && slot < (int)c->slots.size(); }
+
+int xvcb200_upload_picture(xvcb200_ctx *c, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
+  for (int p = 0; p < 3; p++)
+    if (!c->check(cudaMemcpy2DAsync(c->slots[slot].base[p], (size_t)c->geom.pitch[p] * 2, planes[p], (size_t)strides[p] * 2,
+                                    (size_t)c->geom.width[p] * 2, c->geom.height[p], cudaMemcpyHostToDevice, c->stream),
+                  "upload_picture"))
+      return c->status;
+  return XVCB200_OK;
+}
+static int download_planes(xvcb200_ctx *c, int slot, void *const planes[3], const ptrdiff_t strides[3]) {
+  if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
+  for (int p = 0; p < 3; p++)
+    if (!c->check(cudaMemcpy2DAsync(planes[p], (size_t)strides[p] * 2, c->slots[slot].base[p], (size_t)c->geom.pitch[p] * 2,
+                                    (size_t)c->geom.width[p] * 2, c->geom.height[p], cudaMemcpyDeviceToHost, c->stream),
+                  "download_picture"))
+      return c->status;
+  return xvcb200_sync(c);
+}
+int xvcb200_download_picture(xvcb200_ctx *c, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  return download_planes(c, slot, reinterpret_cast<void *const *>(planes), strides);
+}
+int xvcb200_download_coeff(xvcb200_ctx *c, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]) {
+  return download_planes(c, slot, reinterpret_cast<void *const *>(planes), strides);
+}
+// full padded allocation of one plane (tests of PadBorder): rows x cols = (h+2*pad) x (w+2*pad), pad = 80 / 40
+int xvcb200_download_padded(xvcb200_ctx *c, int slot, int comp, uint16_t *dst) {
+  if (!slot_ok(c, slot) || comp < 0 || comp > 2 || !dst) return XVCB200_INVALID_ARGUMENT;
+  const int pad = 80 >> (comp ? 1 : 0), w = c->geom.width[comp] + 2 * pad, h = c->geom.height[comp] + 2 * pad;
+  const Sample *src = c->slots[slot].base[comp] - (ptrdiff_t)pad * c->geom.pitch[comp] - pad;
+  if (!c->check(cudaMemcpy2DAsync(dst, (size_t)w * 2, src, (size_t)c->geom.pitch[comp] * 2, (size_t)w * 2, h,
+                                  cudaMemcpyDeviceToHost, c->stream), "download_padded"))
+    return c->status;
+  return xvcb200_sync(c);
+}
+
+int xvcb200_pad_border(xvcb200_ctx *c, int slot) {
+  if (!slot_ok(c, slot)) return XVCB200_INVALID_ARGUMENT;
+  const int pad[3] = {80, 40, 40};
+  c->check(launch_pad_border(c->stream, pic3(c, slot), pad), "pad_border");
+  return c->status;
+}
+
+// CU array -> device, plus the shape-class lists of the transform units (host bucketing:
+// shapes are fixed for the picture, only mv / flags change on the device afterwards)
+int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
+  if (!ctx || (!cus && n > 0) || n < 0) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  for (int i = 0; i < n; i++) {
+    const xvcb200_cu &u = cus[i];
+    const bool pow2 = (u.w & (u.w - 1)) == 0 && (u.h & (u.h - 1)) == 0;
+    if (!pow2 || u.w < 4 || u.h < 4 || u.w > 64 || u.h > 64 || u.x < 0 || u.y < 0 || u.x + u.w > c->width ||
+        u.y + u.h > c->height || (u.x & 3) || (u.y & 3))
+      return XVCB200_INVALID_ARGUMENT;
+  }
+  if (!ensure(c, &c->d_cus, &c->cap_cus, n) || !ensure(c, &c->ex.d_tu_list, &c->ex.tu_cap, 3 * n)) return c->status;
+  c->n_cus = n;
+  if (n == 0) return XVCB200_OK;
+  int *list = static_cast<int *>(c->pinned(sizeof(int) * 3 * (size_t)n + sizeof(xvcb200_cu) * (size_t)n));
+  if (!list) return c->status;
+  xvcb200_cu *hc = reinterpret_cast<xvcb200_cu *>(list + 3 * (size_t)n);
+  cudaStreamSynchronize(c->stream);          // pinned buffer may still feed an earlier copy
+  memcpy(hc, cus, sizeof(xvcb200_cu) * (size_t)n);
+  auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
+  memset(c->ex.class_count, 0, sizeof(c->ex.class_count));
+  for (int i = 0; i < n; i++)
+    for (int comp = 0; comp < 3; comp++) c->ex.class_count[lg(cus[i].w >> (comp ? 1 : 0))][lg(cus[i].h >> (comp ? 1 : 0))]++;
+  int off = 0, fill[7][7];
+  for (int a = 0; a < 7; a++)
+    for (int b = 0; b < 7; b++) { c->ex.class_offset[a][b] = off; fill[a][b] = off; off += c->ex.class_count[a][b]; }
+  for (int i = 0; i < n; i++)
+    for (int comp = 0; comp < 3; comp++) list[fill[lg(cus[i].w >> (comp ? 1 : 0))][lg(cus[i].h >> (comp ? 1 : 0))]++] = 3 * i + comp;
+  if (!c->check(cudaMemcpyAsync(c->d_cus, hc, sizeof(xvcb200_cu) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "set_cus") ||
+      !c->check(cudaMemcpyAsync(c->ex.d_tu_list, list, sizeof(int) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream), "set_cus"))
+    return c->status;
+  return XVCB200_OK;
+}
+
+int xvcb200_get_cus(xvcb200_ctx *c, xvcb200_cu *cus, int n) {
+  if (!c || !cus || n < 0 || n > c->n_cus) return XVCB200_INVALID_ARGUMENT;
+  if (!c->check(cudaMemcpyAsync(cus, c->d_cus, sizeof(xvcb200_cu) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "get_cus"))
+    return c->status;
+  return xvcb200_sync(c);
+}
+
+static uint32_t lambda_me_of(double lambda_sqrt) { return (uint32_t)std::floor(65536.0 * lambda_sqrt); }
+
+int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *jobs, int n, double lambda_sqrt,
+                      xvcb200_me_result *results) {
+  if (!slot_ok(ctx, orig_slot) || !jobs || !results || n < 0) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  for (int i = 0; i < n; i++)
+    if (jobs[i].cu < 0 || jobs[i].cu >= c->n_cus || !slot_ok(c, jobs[i].ref_slot) || jobs[i].search_range < 1 ||
+        jobs[i].search_range > 256)
+      return XVCB200_INVALID_ARGUMENT;
+  if (n == 0) return XVCB200_OK;
+  if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
+  c->check(cudaMemcpyAsync(c->ex.d_jobs, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "me jobs");
+  c->check(launch_me_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
+                            c->plane(orig_slot, 0), c->ex.d_luma_views, (int)c->slots.size(), c->ex.d_me), "me_search");
+  c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "me results");
+  return xvcb200_sync(c);
+}
+
+int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearch_job *jobs, int n, double lambda_sqrt,
+                        xvcb200_me_result *results) {
+  if (!slot_ok(ctx, orig_slot) || !jobs || !results || n < 0) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  for (int i = 0; i < n; i++)
+    if (jobs[i].cu < 0 || jobs[i].cu >= c->n_cus || !slot_ok(c, jobs[i].ref_slot) || !slot_ok(c, jobs[i].other_pred_slot) ||
+        jobs[i].range < 0 || jobs[i].range > 64)
+      return XVCB200_INVALID_ARGUMENT;
+  if (n == 0) return XVCB200_OK;
+  xvcb200_fullsearch_job *dj = static_cast<xvcb200_fullsearch_job *>(c->scratch(sizeof(*jobs) * (size_t)n));
+  if (!dj || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
+  c->check(cudaMemcpyAsync(dj, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "fs jobs");
+  c->check(launch_full_search(c->stream, c->d_cus, dj, n, c->bitdepth, lambda_me_of(lambda_sqrt), c->plane(orig_slot, 0),
+                              c->ex.d_luma_views, c->ex.d_me), "full_search");
+  c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "fs results");
+  return xvcb200_sync(c);
+}
+
+static bool refs_from_slots(xvcb200_ctx *c, const int32_t ref_slots[2][5], Pic3 refs[2][5]) {
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) {
+      int s = ref_slots[l][i];
+      if (s < 0 || s >= (int)c->slots.size()) s = 0;   // unused entries: any valid view (never dereferenced)
+      refs[l][i] = pic3(c, s);
+    }
+  return true;
+}
+
+int xvcb200_motion_compensate(xvcb200_ctx *c, const int32_t ref_slots[2][5], int pred_slot) {
+  if (!slot_ok(c, pred_slot) || !ref_slots) return XVCB200_INVALID_ARGUMENT;
+  Pic3 refs[2][5];
+  refs_from_slots(c, ref_slots, refs);
+  c->check(launch_motion_compensate(c->stream, c->d_cus, c->n_cus, c->bitdepth, refs, pic3(c, pred_slot)), "motion_compensate");
+  return c->status;
+}
+
+static int tq_common(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slot, int coeff_slot, int intra_picture,
+                     int table, int off_u, int off_v, int decode_only, xvcb200_tu_result *results) {
+  if (!slot_ok(ctx, pred_slot) || !slot_ok(ctx, rec_slot) || !slot_ok(ctx, coeff_slot) || (!decode_only && !slot_ok(ctx, orig_slot)))
+    return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  const int n = c->n_cus;
+  if (n == 0) return XVCB200_OK;
+  if (!ensure(c, &c->ex.d_tu, &c->ex.tu_res_cap, 3 * n)) return c->status;
+  TqParams p;
+  p.bitdepth = c->bitdepth; p.intra_picture = intra_picture; p.table = table; p.off_u = off_u; p.off_v = off_v;
+  p.decode_only = decode_only;
+  int16_t *lev[3]; int pitch[3];
+  for (int k = 0; k < 3; k++) { lev[k] = reinterpret_cast<int16_t *>(c->slots[coeff_slot].base[k]); pitch[k] = c->geom.pitch[k]; }
+  c->check(launch_tq_reconstruct_classes(c->stream, c->d_cus, c->ex.d_tu_list, c->ex.class_count, c->ex.class_offset, p,
+                                         pic3(c, decode_only ? pred_slot : orig_slot), pic3(c, pred_slot), pic3(c, rec_slot),
+                                         lev, pitch, decode_only ? nullptr : c->ex.d_tu), "tq_reconstruct");
+  if (results && !decode_only) {
+    c->check(cudaMemcpyAsync(results, c->ex.d_tu, sizeof(*results) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "tu results");
+    return xvcb200_sync(c);
+  }
+  return c->status;
+}
+
+int xvcb200_tq_reconstruct(xvcb200_ctx *c, int orig_slot, int pred_slot, int rec_slot, int coeff_slot, int pic_qp_unused,
+                           int intra_picture, int table, int off_u, int off_v, xvcb200_tu_result *results) {
+  (void)pic_qp_unused;
+  return tq_common(c, orig_slot, pred_slot, rec_slot, coeff_slot, intra_picture, table, off_u, off_v, 0, results);
+}
+int xvcb200_dequant_reconstruct(xvcb200_ctx *c, int pred_slot, int rec_slot, int coeff_slot, int table, int off_u, int off_v) {
+  return tq_common(c, 0, pred_slot, rec_slot, coeff_slot, 0, table, off_u, off_v, 1, nullptr);
+}
+// levels into a coefficient slot (decoder side input)
+int xvcb200_upload_coeff(xvcb200_ctx *c, int slot, const int16_t *const planes[3], const ptrdiff_t strides[3]) {
+  return xvcb200_upload_picture(c, slot, reinterpret_cast<const uint16_t *const *>(planes), strides);
+}
+
+int xvcb200_deblock_picture(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset,
+                            const int64_t ref_poc[2][5]) {
+  return xvcb200_deblock_picture_ex(c, rec_slot, pic_type, beta_offset, tc_offset, 1, 0, 0, ref_poc);
+}
+int xvcb200_deblock_picture_ex(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table,
+                               int off_u, int off_v, const int64_t ref_poc[2][5]) {
+  if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1) return XVCB200_INVALID_ARGUMENT;
+  DeblockParams p;
+  p.bitdepth = c->bitdepth; p.pic_type = pic_type; p.beta_offset = beta_offset; p.tc_offset = tc_offset;
+  p.table = table; p.off_u = off_u; p.off_v = off_v;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) p.ref_poc[l][i] = ref_poc[l][i];
+  c->check(launch_deblock(c->stream, c->d_cus, c->n_cus, p, pic3(c, rec_slot), c->d_cu_map, c->d_edge_bs[0], c->d_edge_bs[1],
+                          c->map_w, c->map_h), "deblock");
+  return c->status;
+}
+
+// ---------------------------------------------------------------- (C) picture pipeline
+int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, xvcb200_me_result *me_results,
+                           xvcb200_tu_result *tu_results) {
+  if (!ctx || !prm) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  const int n = c->n_cus;
+  const int nl = prm->pic_type == 0 ? 2 : 1;
+  if (!slot_ok(c, prm->orig_slot) || !slot_ok(c, prm->pred_slot) || !slot_ok(c, prm->rec_slot) || !slot_ok(c, prm->coeff_slot) ||
+      prm->pic_type < 0 || prm->pic_type > 1 || !slot_ok(c, prm->ref_slots[0][0]) || (nl == 2 && !slot_ok(c, prm->ref_slots[1][0])))
+    return XVCB200_INVALID_ARGUMENT;
+  if (n == 0) return XVCB200_OK;
+  if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n * nl) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n * nl) ||
+      !ensure(c, &c->ex.d_tu, &c->ex.tu_res_cap, 3 * n))
+    return c->status;
+  const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
+  const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
+  c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
+  c->check(launch_me_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
+                            c->plane(prm->orig_slot, 0), c->ex.d_luma_views, (int)c->slots.size(), c->ex.d_me), "me_search");
+  c->check(launch_me_decide(c->stream, c->d_cus, n, nl, c->ex.d_me), "me_decide");
+  Pic3 refs[2][5];
+  refs_from_slots(c, prm->ref_slots, refs);
+  c->check(launch_motion_compensate(c->stream, c->d_cus, n, c->bitdepth, refs, pic3(c, prm->pred_slot)), "motion_compensate");
+  int st = tq_common(c, prm->orig_slot, prm->pred_slot, prm->rec_slot, prm->coeff_slot, 0, prm->chroma_offset_table,
+                     prm->chroma_offset_u, prm->chroma_offset_v, 0, nullptr);
+  if (st != XVCB200_OK) return st;
+  if (prm->deblock) {
+    st = xvcb200_deblock_picture_ex(c, prm->rec_slot, prm->pic_type, prm->beta_offset, prm->tc_offset, prm->chroma_offset_table,
+                                    prm->chroma_offset_u, prm->chroma_offset_v, prm->ref_poc);
+    if (st != XVCB200_OK) return st;
+  }
+  if (prm->pad) xvcb200_pad_border(c, prm->rec_slot);
+  if (me_results)
+    c->check(cudaMemcpyAsync(me_results, c->ex.d_me, sizeof(*me_results) * (size_t)n * nl, cudaMemcpyDeviceToHost, c->stream), "me results");
+  if (tu_results)
+    c->check(cudaMemcpyAsync(tu_results, c->ex.d_tu, sizeof(*tu_results) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "tu results");
+  return c->status;   // asynchronous: xvcb200_sync() completes it
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+// In-loop deblocking (DeblockingFilter, deblocking_filter.cc) and border padding
+// (YuvPicture::PadBorder, yuv_pic.cc:118-150) for a whole device-resident picture.
+//
+// Parallel decomposition.  The reference visits every 4x4 grid position of every CTU in
+// raster order, all vertical edges first, then all horizontal edges (:56-77).  A vertical
+// edge segment (4 rows) reads 4 and writes up to 3 samples on each side, so two edges 4
+// samples apart in the same 4-row group are order dependent (left one first); edges in
+// different 4-row groups, and edges 8 or more apart, touch disjoint samples.  The unit of
+// parallel work is therefore a CHAIN: a maximal run of consecutive active edges (boundary
+// strength > 0) 4 samples apart inside one 4-row group (vertical pass) or one 4-column group
+// (horizontal pass).  The thread whose edge starts a chain filters the whole chain in the
+// reference's order; every other thread of that chain does nothing.  Chroma edges sit on an
+// 8-sample chroma grid and only touch one sample each side, so they are independent.
+#include "xvcb_device.cuh"
+
+namespace xvcb {
+
+__constant__ uint8_t c_tc[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  0,  0,  0,  0,  0,  0,  0,  0,
+                                 1, 1, 1, 1, 1, 1, 1, 1, 1, 2,  2,  2,  2,  3,  3,  3,  3,  4,
+                                 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};   // kTcTable, :34-38
+__constant__ uint8_t c_beta[64] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,
+                                   6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24,
+                                   26, 28, 30, 32, 34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56,
+                                   58, 60, 62, 64, 66, 68, 70, 72, 74, 76, 78, 80, 82, 84, 86, 88};  // kBetaTable, :40-45
+__constant__ uint8_t c_db_chroma_scale[58] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 19,
+                                              20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 33, 33, 34, 34, 35, 35,
+                                              36, 36, 37, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51};
+
+// ---------------------------------------------------------------- CU map (PictureData::MarkUsedInPic, picture_data.cc:196-210)
+__global__ void cu_map_kernel(const xvcb200_cu *__restrict__ cus, int n, int32_t *__restrict__ map, int map_w, int map_h) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const xvcb200_cu cu = cus[i];
+  const int bw = cu.w >> 2, bh = cu.h >> 2, bx = cu.x >> 2, by = cu.y >> 2;
+  for (int e = threadIdx.x; e < bw * bh; e += blockDim.x) {
+    const int x = bx + e % bw, y = by + e / bw;
+    if (x < map_w && y < map_h) map[y * map_w + x] = i;
+  }
+}
+
+struct DbRefPoc { long long poc[2][5]; };
+
+__device__ __forceinline__ long long ref_poc_of(const xvcb200_cu &cu, int list, const DbRefPoc &rp) {
+  return cu.ref_idx[list] < 0 ? -1 : rp.poc[list][cu.ref_idx[list]];   // CodingUnit::GetRefPoc, coding_unit.cc:166-172
+}
+__device__ __forceinline__ bool mv_far(const int32_t a[2], const int32_t b[2]) {
+  return abs(a[0] - b[0]) >= 16 || abs(a[1] - b[1]) >= 16;               // one integer sample at 1/16 pel
+}
+
+// DeblockingFilter::GetBoundaryStrength, deblocking_filter.cc:154-241.  Without affine motion the
+// four corner MVs of a CU are equal, so the corner selection (:166-176) reads the same value.
+__device__ int boundary_strength(const xvcb200_cu &p, const xvcb200_cu &q, int pic_type, const DbRefPoc &rp) {
+  if ((p.flags | q.flags) & XVCB200_CU_INTRA) return 2;
+  if ((p.flags | q.flags) & XVCB200_CU_CBF_Y) return 1;
+  if (pic_type == 0) {
+    const long long p0 = ref_poc_of(p, 0, rp), p1 = ref_poc_of(p, 1, rp), q0 = ref_poc_of(q, 0, rp), q1 = ref_poc_of(q, 1, rp);
+    if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
+    const bool straight = mv_far(p.mv[0], q.mv[0]) || mv_far(p.mv[1], q.mv[1]);
+    const bool crossed = mv_far(p.mv[0], q.mv[1]) || mv_far(p.mv[1], q.mv[0]);
+    if (p0 != p1) return (p0 == q0) ? straight : crossed;
+    return straight && crossed;
+  }
+  if (p.ref_idx[0] != q.ref_idx[0]) return 1;
+  return mv_far(p.mv[0], q.mv[0]);
+}
+
+// boundary strength of the left (bs_v) and top (bs_h) edge of every 4x4 block; 0 = no edge
+__global__ void edge_bs_kernel(const xvcb200_cu *__restrict__ cus, const int32_t *__restrict__ map, int map_w, int map_h,
+                               int pic_type, const __grid_constant__ DbRefPoc rp, uint8_t *__restrict__ bs_v,
+                               uint8_t *__restrict__ bs_h) {
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= map_w * map_h) return;
+  const int cx = cell % map_w, cy = cell / map_w;
+  const int iq = map[cell];
+  uint8_t v = 0, h = 0;
+  if (iq >= 0) {
+    const xvcb200_cu q = cus[iq];
+    if (cx > 0) {
+      const int ip = map[cell - 1];
+      if (ip >= 0 && ip != iq) v = (uint8_t)boundary_strength(cus[ip], q, pic_type, rp);
+    }
+    if (cy > 0) {
+      const int ip = map[cell - map_w];
+      if (ip >= 0 && ip != iq) h = (uint8_t)boundary_strength(cus[ip], q, pic_type, rp);
+    }
+  }
+  bs_v[cell] = v;
+  bs_h[cell] = h;
+}
+
+// FilterEdgeLuma + CheckStrongFilter + FilterLumaWeak + FilterLumaStrong (:243-401) for one
+// 4-line edge segment.  `across` steps over the edge, `along` steps along it.
+__device__ void luma_segment(Sample *s, int across, int along, int bitdepth, int bs, int qp, int beta_off, int tc_off) {
+  const int bd_shift = bitdepth - 8, maxv = (1 << bitdepth) - 1;
+  // the reference clips the beta index to size() = 64, one past the table (:270-271); unreachable
+  // for qp <= 51 with zero offsets -- defined here as the last entry
+  const int beta = c_beta[min(clip3i(qp + beta_off, 0, 64), 63)] << bd_shift;
+  int px[4][4], qx[4][4];   // [line][distance from the edge]
+#pragma unroll
+  for (int l = 0; l < 4; l++)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      px[l][i] = s[l * along - (i + 1) * across];
+      qx[l][i] = s[l * along + i * across];
+    }
+  const int dp0 = abs(px[0][2] - 2 * px[0][1] + px[0][0]), dq0 = abs(qx[0][0] - 2 * qx[0][1] + qx[0][2]);
+  const int dp3 = abs(px[3][2] - 2 * px[3][1] + px[3][0]), dq3 = abs(qx[3][0] - 2 * qx[3][1] + qx[3][2]);
+  const int d0 = dp0 + dq0, d3 = dp3 + dq3;
+  if (d0 + d3 >= beta) return;
+  const int tc = c_tc[clip3i(qp + tc_off + 2 * (bs - 1), 0, 53)] << bd_shift;
+  bool strong = (d0 << 1) < (beta >> 2) && (d3 << 1) < (beta >> 2);
+#pragma unroll
+  for (int l = 0; l < 4; l += 3)
+    strong = strong && (abs(px[l][3] - px[l][0]) + abs(qx[l][0] - qx[l][3])) < (beta >> 3) &&
+             abs(px[l][0] - qx[l][0]) < ((tc * 5 + 1) >> 1);
+  if (strong) {
+    const int t2 = 2 * tc;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const int p3 = px[l][3], p2 = px[l][2], p1 = px[l][1], p0 = px[l][0];
+      const int q0 = qx[l][0], q1 = qx[l][1], q2 = qx[l][2], q3 = qx[l][3];
+      // delta clipped to +-2tc, narrowed to Sample, added with no final clip (:392-397)
+#define XVCB_PUT(off, old, nv) s[l * along + (off) * across] = (Sample)((old) + (Sample)clip3i((nv) - (old), -t2, t2))
+      XVCB_PUT(-3, p2, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+      XVCB_PUT(-2, p1, (p2 + p1 + p0 + q0 + 2) >> 2);
+      XVCB_PUT(-1, p0, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+      XVCB_PUT(0, q0, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+      XVCB_PUT(1, q1, (p0 + q0 + q1 + q2 + 2) >> 2);
+      XVCB_PUT(2, q2, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+#undef XVCB_PUT
+    }
+    return;
+  }
+  const int side = (beta + (beta >> 1)) >> 3;
+  const bool do_p1 = (dp0 + dp3) < side, do_q1 = (dq0 + dq3) < side;
+  const int half = tc >> 1;
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const int p2 = px[l][2], p1 = px[l][1], p0 = px[l][0], q0 = qx[l][0], q1 = qx[l][1], q2 = qx[l][2];
+    int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+    if (abs(delta) >= tc * 10) continue;
+    delta = clip3i(delta, -tc, tc);
+    s[l * along - across] = (Sample)clip3i(p0 + delta, 0, maxv);
+    s[l * along] = (Sample)clip3i(q0 - delta, 0, maxv);
+    if (do_p1) s[l * along - 2 * across] = (Sample)clip3i(p1 + clip3i((((p2 + p0 + 1) >> 1) - p1 + delta) >> 1, -half, half), 0, maxv);
+    if (do_q1) s[l * along + across] = (Sample)clip3i(q1 + clip3i((((q2 + q0 + 1) >> 1) - q1 - delta) >> 1, -half, half), 0, maxv);
+  }
+}
+
+// FilterEdgeChroma + FilterChroma<2> (:403-450): 2 chroma lines per 4-sample luma segment in 4:2:0
+__device__ void chroma_segment(Sample *s, int across, int along, int bitdepth, int qp, int tc_off) {
+  const int tc = c_tc[min(clip3i(qp + tc_off + 2, 0, 54), 53)] << (bitdepth - 8);   // index clip as in luma
+  const int maxv = (1 << bitdepth) - 1;
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    const int p1 = s[l * along - 2 * across], p0 = s[l * along - across], q0 = s[l * along], q1 = s[l * along + across];
+    const int delta = clip3i((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
+    s[l * along - across] = (Sample)clip3i(p0 + delta, 0, maxv);
+    s[l * along] = (Sample)clip3i(q0 - delta, 0, maxv);
+  }
+}
+
+template <int DIR>   // 0: vertical edges, 1: horizontal edges
+__global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restrict__ cus, const int32_t *__restrict__ map,
+                                                      const uint8_t *__restrict__ bs_arr, int map_w, int map_h,
+                                                      DeblockParams prm, Pic3 rec) {
+  // thread -> 4x4 block; for DIR 1 consecutive threads still walk along x so loads coalesce
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= map_w * map_h) return;
+  const int cx = cell % map_w, cy = cell / map_w;
+  const int bs0 = bs_arr[cell];
+  if (bs0 == 0) return;
+  const int step = DIR == 0 ? 1 : map_w;                 // next edge of the chain
+  const int pos = DIR == 0 ? cx : cy, lim = DIR == 0 ? map_w : map_h;
+  const PlaneView ly = rec.p[0];
+  const int across = DIR == 0 ? 1 : ly.pitch, along = DIR == 0 ? ly.pitch : 1;
+
+  // chroma: bs == 2 edges whose chroma coordinate is a multiple of 8 (:131-149)
+  if (bs0 == 2 && ((DIR == 0 ? cx : cy) & 3) == 0) {
+    const int iq = map[cell], ip = map[cell - step];
+    const int qpp = chroma_qp_raw(cus[ip].qp, prm.off_u, prm.table, c_db_chroma_scale);   // cu.GetQp(kU) for both planes (:127)
+    const int qpq = chroma_qp_raw(cus[iq].qp, prm.off_u, prm.table, c_db_chroma_scale);
+    const int cqp = (qpp + qpq + 1) >> 1;
+    for (int c = 1; c < 3; c++) {
+      const PlaneView pc = rec.p[c];
+      Sample *s = pc.base + (cy * 2) * pc.pitch + cx * 2;
+      chroma_segment(s, DIR == 0 ? 1 : pc.pitch, DIR == 0 ? pc.pitch : 1, prm.bitdepth, cqp, prm.tc_offset);
+    }
+  }
+
+  // luma: only the head of a chain works
+  if (pos > 0 && bs_arr[cell - step] != 0) return;
+  int e = cell;
+  for (int k = pos; k < lim; k++, e += step) {
+    const int bs = bs_arr[e];
+    if (bs == 0) break;
+    const int iq = map[e], ip = map[e - step];
+    const int qp = (cus[ip].qp + cus[iq].qp + 1) >> 1;
+    const int ex = DIR == 0 ? k : cx, ey = DIR == 0 ? cy : k;
+    Sample *s = ly.base + (ey * 4) * ly.pitch + ex * 4;
+    luma_segment(s, across, along, prm.bitdepth, bs, qp, prm.beta_offset, prm.tc_offset);
+  }
+}
+
+cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
+                           int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h) {
+  if (n <= 0) return cudaSuccess;
+  const int cells = map_w * map_h;
+  cudaError_t e = cudaMemsetAsync(d_map, 0xff, sizeof(int32_t) * cells, s);
+  if (e != cudaSuccess) return e;
+  DbRefPoc rp;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) rp.poc[l][i] = p.ref_poc[l][i];
+  g_launch_count += 4;
+  cu_map_kernel<<<n, 64, 0, s>>>(d_cus, n, d_map, map_w, map_h);
+  edge_bs_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, map_w, map_h, p.pic_type, rp, d_bs_v, d_bs_h);
+  deblock_kernel<0><<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_v, map_w, map_h, p, rec);
+  deblock_kernel<1><<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_h, map_w, map_h, p, rec);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- PadBorder
+// Every sample outside the picture takes the value of the nearest picture sample (rows are
+// replicated first, then columns over all rows incl. the new ones: corners = corner samples).
+__global__ void pad_border_kernel(PlaneView pl, int pad) {
+  const int fw = pl.width + 2 * pad, fh = pl.height + 2 * pad;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= fw * fh) return;
+  const int x = idx % fw - pad, y = idx / fw - pad;
+  if (x >= 0 && x < pl.width && y >= 0 && y < pl.height) return;
+  const int sx = clip3i(x, 0, pl.width - 1), sy = clip3i(y, 0, pl.height - 1);
+  pl.base[y * pl.pitch + x] = pl.base[sy * pl.pitch + sx];
+}
+
+cudaError_t launch_pad_border(cudaStream_t s, Pic3 pic, const int pad[3]) {
+  for (int c = 0; c < 3; c++) {
+    const int total = (pic.p[c].width + 2 * pad[c]) * (pic.p[c].height + 2 * pad[c]);
+    g_launch_count++;
+    pad_border_kernel<<<(total + 255) / 256, 256, 0, s>>>(pic.p[c], pad[c]);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace xvcb

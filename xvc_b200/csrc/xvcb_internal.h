@@ -1,0 +1,139 @@
+// Internal declarations shared by the kernels and the C-ABI layer of libxvc_b200.so.
+#ifndef XVCB_INTERNAL_H_
+#define XVCB_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/xvc_b200.h"
+
+namespace xvcb {
+
+typedef uint16_t Sample;
+
+extern std::atomic<uint64_t> g_launch_count;
+void set_last_error(int code, const char *what);
+
+// One device picture: three padded planes in a single allocation.
+struct DevPicture {
+  uint8_t *alloc = nullptr;
+  size_t bytes = 0;
+  Sample *base[3] = {nullptr, nullptr, nullptr};   // sample (0,0)
+};
+
+struct PlaneView {           // what kernels receive
+  Sample *base;
+  int pitch;                 // elements
+  int width, height;
+};
+
+struct xvcb_ctx_impl {
+  int device = 0;
+  int width = 0, height = 0, bitdepth = 10, chroma_format = 1;
+  xvcb200_plane_geom geom{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int status = XVCB200_OK;
+  std::string error;
+  std::vector<DevPicture> slots;
+
+  // CU array (device) and derived per-picture maps
+  xvcb200_cu *d_cus = nullptr;
+  int n_cus = 0, cap_cus = 0;
+  int32_t *d_cu_map = nullptr;       // CU index per 4x4 block
+  uint8_t *d_edge_bs[2] = {nullptr, nullptr};   // boundary strength per 4x4 block: [0] left edge, [1] top edge
+  int map_w = 0, map_h = 0;
+
+  // scratch (device), grown on demand
+  void *d_scratch = nullptr;  size_t scratch_bytes = 0;
+  void *d_scratch2 = nullptr; size_t scratch2_bytes = 0;
+  void *h_pinned = nullptr;   size_t pinned_bytes = 0;
+
+  bool fail(int code, const std::string &what) {
+    if (status == XVCB200_OK) { status = code; error = what; }
+    set_last_error(code, what.c_str());
+    return false;
+  }
+  bool check(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    return fail(e == cudaErrorMemoryAllocation ? XVCB200_OUT_OF_MEMORY : XVCB200_CUDA_ERROR,
+                std::string(what) + ": " + cudaGetErrorString(e));
+  }
+  PlaneView plane(int slot, int comp) const {
+    PlaneView v;
+    v.base = slots[slot].base[comp];
+    v.pitch = geom.pitch[comp];
+    v.width = geom.width[comp];
+    v.height = geom.height[comp];
+    return v;
+  }
+  void *scratch(size_t bytes);
+  void *scratch2(size_t bytes);
+  void *pinned(size_t bytes);
+};
+
+struct Pic3 { PlaneView p[3]; };
+inline Pic3 pic3(const xvcb_ctx_impl *c, int slot) {
+  Pic3 r; for (int i = 0; i < 3; i++) r.p[i] = c->plane(slot, i); return r;
+}
+
+// ---- launchers (each enqueues on `stream`, bumps g_launch_count, returns cudaGetLastError) ----
+
+// metrics.cu: one block, result into *d_out (uint64).  kind: see xo_sad/xo_ssd; metric >= 0 applies
+// SampleMetric::Compare scaling (XVCB200_METRIC_*), metric < 0: raw sad (-1) / raw ssd (-2).
+cudaError_t launch_block_metric(cudaStream_t s, int metric, int bitdepth, int w, int h, int a_short, int b_short,
+                                const void *a, int sa, const void *b, int sb, unsigned long long *d_out);
+
+// interp.cu
+cudaError_t launch_block_filter(cudaStream_t s, int kind, int chroma, int w, int h, int bitdepth, const int16_t taps[8],
+                                const void *src, int ss, void *dst, int ds);
+cudaError_t launch_block_add_avg(cudaStream_t s, int w, int h, int offset, int shift, int bitdepth, const int16_t *a,
+                                 int sa, const int16_t *b, int sb, Sample *dst, int ds);
+cudaError_t launch_block_copy_bipred(cudaStream_t s, int w, int h, int offset, int shift, const Sample *ref, int rs,
+                                     int16_t *pred, int ps);
+cudaError_t launch_block_interp(cudaStream_t s, int chroma, int bipred, int w, int h, int bitdepth, int fx, int fy,
+                                const Sample *ref, int rs, void *pred, int ps);
+cudaError_t launch_motion_compensate(cudaStream_t s, const xvcb200_cu *d_cus, int n, int bitdepth,
+                                     const Pic3 refs[2][5], Pic3 pred);
+
+// transform.cu
+cudaError_t launch_block_transform(cudaStream_t s, int forward, int w, int h, int bitdepth, int tx_hor, int tx_ver,
+                                   int dst4x4, int dc_only, int skip, const int16_t *in, int is, int16_t *out, int os);
+cudaError_t launch_block_quant(cudaStream_t s, int w, int h, int bitdepth, int qp_bd, int intra_pic, int sign_hiding,
+                               int scan, const int16_t *in, int is, int16_t *out, int os, int *d_nnz);
+cudaError_t launch_block_dequant(cudaStream_t s, int w, int h, int bitdepth, int qp_bd, const int16_t *in, int is,
+                                 int16_t *out, int os);
+struct TqParams {
+  int bitdepth, intra_picture, table, off_u, off_v;
+  int decode_only;        // 1: dequant + inverse + reconstruct from levels (CuDecoder::DecompressComponent)
+};
+
+// me.cu
+cudaError_t launch_me_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
+                             uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, int n_slots,
+                             xvcb200_me_result *d_res);
+cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_fullsearch_job *d_jobs, int n,
+                               int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_planes,
+                               xvcb200_me_result *d_res);
+cudaError_t launch_me_decide(cudaStream_t s, xvcb200_cu *d_cus, int n, int nl, const xvcb200_me_result *d_res);
+cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, int n, int nl, const int ref_slot[2],
+                                const int range[2], xvcb200_me_job *d_jobs);
+
+// deblock.cu
+cudaError_t launch_pad_border(cudaStream_t s, Pic3 pic, const int pad[3]);
+struct DeblockParams {
+  int bitdepth, pic_type, beta_offset, tc_offset, table, off_u, off_v;
+  long long ref_poc[2][5];
+};
+cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
+                           int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h);
+
+}  // namespace xvcb
+
+struct xvcb200_ctx : public xvcb::xvcb_ctx_impl {};
+
+#endif

@@ -1,0 +1,369 @@
+"""ctypes binding of libxvc_b200.so (include/xvc_b200.h).
+
+The Python side only marshals numpy arrays into the C ABI; every sample is produced by
+the CUDA kernels.  There is no CPU fallback: loading fails loudly when the shared library
+has not been built, and every call fails loudly when no CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxvc_b200.so")
+
+c_int, c_void_p, c_double, c_u64 = ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64
+c_ssize = ctypes.c_ssize_t
+
+# every symbol include/xvc_b200.h declares (tests/test_abi.py checks they are all exported)
+EXPORTS = [
+    "xvcb200_last_error", "xvcb200_last_error_string", "xvcb200_clear_error", "xvcb200_launch_count",
+    "xvcb200_version", "xvcb200_abi_sizeof",
+    "xvcb200_sad_sample_sample", "xvcb200_sad_short_sample", "xvcb200_ssd_sample_sample",
+    "xvcb200_ssd_short_sample", "xvcb200_ssd_short_short", "xvcb200_compare_sample_sample",
+    "xvcb200_compare_short_sample",
+    "xvcb200_filter_h_sample_sample", "xvcb200_filter_h_sample_short", "xvcb200_filter_v_sample_sample",
+    "xvcb200_filter_v_sample_short", "xvcb200_filter_v_short_sample", "xvcb200_filter_v_short_short",
+    "xvcb200_add_avg", "xvcb200_filter_copy_bipred", "xvcb200_interp_block", "xvcb200_interp_block_bipred",
+    "xvcb200_register_inter_prediction", "xvcb200_register_sample_metric",
+    "xvcb200_fwd_transform", "xvcb200_fwd_transform_skip", "xvcb200_inv_transform", "xvcb200_inv_transform_skip",
+    "xvcb200_qp_init", "xvcb200_quant_fast", "xvcb200_dequant",
+    "xvcb200_ctx_create", "xvcb200_ctx_destroy", "xvcb200_ctx_set_stream", "xvcb200_stream", "xvcb200_sync",
+    "xvcb200_ctx_error_string", "xvcb200_get_geometry", "xvcb200_slot_ptr",
+    "xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff",
+    "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus",
+    "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_tq_reconstruct",
+    "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex",
+    "xvcb200_encode_picture",
+]
+
+
+class XvcB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XvcB200Error("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(xvc_b200 has no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.xvcb200_last_error_string.restype = ctypes.c_char_p
+    L.xvcb200_version.restype = ctypes.c_char_p
+    L.xvcb200_ctx_error_string.restype = ctypes.c_char_p
+    L.xvcb200_ctx_error_string.argtypes = [c_void_p]
+    L.xvcb200_launch_count.restype = c_u64
+    L.xvcb200_stream.restype = c_void_p
+    L.xvcb200_stream.argtypes = [c_void_p]
+    blk = [c_int, c_int, c_void_p, c_ssize, c_void_p, c_ssize]
+    for name in ("xvcb200_sad_sample_sample", "xvcb200_sad_short_sample"):
+        getattr(L, name).argtypes = blk
+    for name in ("xvcb200_ssd_sample_sample", "xvcb200_ssd_short_sample", "xvcb200_ssd_short_short"):
+        getattr(L, name).argtypes = blk
+        getattr(L, name).restype = c_u64
+    for name in ("xvcb200_compare_sample_sample", "xvcb200_compare_short_sample"):
+        getattr(L, name).argtypes = [c_int, c_int] + blk
+        getattr(L, name).restype = c_u64
+    for name in ("h_sample_sample", "h_sample_short", "v_sample_sample", "v_sample_short", "v_short_sample", "v_short_short"):
+        getattr(L, "xvcb200_filter_" + name).argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_add_avg.argtypes = [c_int] * 5 + [c_void_p, c_ssize, c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_filter_copy_bipred.argtypes = [c_int, c_int, ctypes.c_int16, c_int, c_void_p, c_ssize, c_void_p, c_ssize]
+    for name in ("xvcb200_interp_block", "xvcb200_interp_block_bipred"):
+        getattr(L, name).argtypes = [c_int] * 6 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_fwd_transform.argtypes = [c_int] * 6 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_inv_transform.argtypes = [c_int] * 7 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    for name in ("xvcb200_fwd_transform_skip", "xvcb200_inv_transform_skip"):
+        getattr(L, name).argtypes = [c_int] * 3 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_qp_init.argtypes = [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_int]
+    L.xvcb200_quant_fast.argtypes = [c_int] * 7 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_dequant.argtypes = [c_int] * 4 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_ctx_create.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]
+    L.xvcb200_ctx_destroy.argtypes = [c_void_p]
+    L.xvcb200_ctx_set_stream.argtypes = [c_void_p, c_void_p]
+    L.xvcb200_sync.argtypes = [c_void_p]
+    L.xvcb200_get_geometry.argtypes = [c_void_p, c_void_p]
+    L.xvcb200_slot_ptr.argtypes = [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)]
+    for name in ("xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff"):
+        getattr(L, name).argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+    L.xvcb200_download_padded.argtypes = [c_void_p, c_int, c_int, c_void_p]
+    L.xvcb200_pad_border.argtypes = [c_void_p, c_int]
+    L.xvcb200_set_cus.argtypes = [c_void_p, c_void_p, c_int]
+    L.xvcb200_get_cus.argtypes = [c_void_p, c_void_p, c_int]
+    L.xvcb200_me_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
+    L.xvcb200_full_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
+    L.xvcb200_motion_compensate.argtypes = [c_void_p, c_void_p, c_int]
+    L.xvcb200_tq_reconstruct.argtypes = [c_void_p] + [c_int] * 9 + [c_void_p]
+    L.xvcb200_dequant_reconstruct.argtypes = [c_void_p] + [c_int] * 6
+    L.xvcb200_deblock_picture.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    L.xvcb200_deblock_picture_ex.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p]
+    L.xvcb200_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    _lib = L
+    return L
+
+
+def _check_leaf(L):
+    if L.xvcb200_last_error() != 0:
+        msg = L.xvcb200_last_error_string().decode()
+        L.xvcb200_clear_error()
+        raise XvcB200Error(msg)
+
+
+def _off(arr, row, col):
+    return c_void_p(arr.ctypes.data + arr.dtype.itemsize * (row * arr.shape[1] + col))
+
+
+# ---------------------------------------------------------------------- table-shaped calls
+def sad(a, b, w, h):
+    L = load()
+    fn = L.xvcb200_sad_short_sample if a.dtype == np.int16 else L.xvcb200_sad_sample_sample
+    r = fn(w, h, abi.ptr(a), a.shape[1], abi.ptr(b), b.shape[1])
+    _check_leaf(L)
+    return r
+
+
+def ssd(a, b, w, h):
+    L = load()
+    if a.dtype == np.int16 and b.dtype == np.int16:
+        fn = L.xvcb200_ssd_short_short
+    elif a.dtype == np.int16:
+        fn = L.xvcb200_ssd_short_sample
+    else:
+        fn = L.xvcb200_ssd_sample_sample
+    r = fn(w, h, abi.ptr(a), a.shape[1], abi.ptr(b), b.shape[1])
+    _check_leaf(L)
+    return r
+
+
+def compare(metric, bitdepth, a, b, w, h):
+    L = load()
+    fn = L.xvcb200_compare_short_sample if a.dtype == np.int16 else L.xvcb200_compare_sample_sample
+    r = fn(metric, bitdepth, w, h, abi.ptr(a), a.shape[1], abi.ptr(b), b.shape[1])
+    _check_leaf(L)
+    return r
+
+
+_FILTER_NAMES = ["h_sample_sample", "h_sample_short", "v_sample_sample", "v_sample_short", "v_short_sample", "v_short_short"]
+
+
+def filter_block(kind, chroma, w, h, bitdepth, taps, src, src_off, dst):
+    L = load()
+    fn = getattr(L, "xvcb200_filter_" + _FILTER_NAMES[kind])
+    fn(chroma, w, h, bitdepth, abi.ptr(np.ascontiguousarray(taps, dtype=np.int16)), _off(src, *src_off), src.shape[1],
+       abi.ptr(dst), dst.shape[1])
+    _check_leaf(L)
+
+
+def interp_block(chroma, bipred, w, h, bitdepth, fx, fy, ref, ref_off, pred):
+    L = load()
+    fn = L.xvcb200_interp_block_bipred if bipred else L.xvcb200_interp_block
+    fn(chroma, w, h, bitdepth, fx, fy, _off(ref, *ref_off), ref.shape[1], abi.ptr(pred), pred.shape[1])
+    _check_leaf(L)
+
+
+def add_avg(w, h, offset, shift, bitdepth, a, b, dst):
+    L = load()
+    L.xvcb200_add_avg(w, h, offset, shift, bitdepth, abi.ptr(a), a.shape[1], abi.ptr(b), b.shape[1], abi.ptr(dst), dst.shape[1])
+    _check_leaf(L)
+
+
+def filter_copy_bipred(w, h, offset, shift, ref, pred):
+    L = load()
+    L.xvcb200_filter_copy_bipred(w, h, offset, shift, abi.ptr(ref), ref.shape[1], abi.ptr(pred), pred.shape[1])
+    _check_leaf(L)
+
+
+def fwd_transform(w, h, bitdepth, tx_hor, tx_ver, dst4x4, resi):
+    L = load()
+    out = np.zeros((h, w), dtype=np.int16)
+    L.xvcb200_fwd_transform(w, h, bitdepth, tx_hor, tx_ver, dst4x4, abi.ptr(resi), resi.shape[1], abi.ptr(out), w)
+    _check_leaf(L)
+    return out
+
+
+def inv_transform(w, h, bitdepth, tx_hor, tx_ver, dst4x4, dc_only, coeff):
+    L = load()
+    out = np.zeros((h, w), dtype=np.int16)
+    L.xvcb200_inv_transform(w, h, bitdepth, tx_hor, tx_ver, dst4x4, dc_only, abi.ptr(coeff), coeff.shape[1], abi.ptr(out), w)
+    _check_leaf(L)
+    return out
+
+
+def transform_skip(forward, w, h, bitdepth, inp):
+    L = load()
+    out = np.zeros((h, w), dtype=np.int16)
+    fn = L.xvcb200_fwd_transform_skip if forward else L.xvcb200_inv_transform_skip
+    fn(w, h, bitdepth, abi.ptr(inp), inp.shape[1], abi.ptr(out), w)
+    _check_leaf(L)
+    return out
+
+
+def qp_init(qp, bitdepth, lam=1.0, table=1, off_u=0, off_v=0, chroma_format=1):
+    L = load()
+    q = np.zeros(1, dtype=abi.qp_dtype)
+    L.xvcb200_qp_init(abi.ptr(q), qp, chroma_format, bitdepth, lam, table, off_u, off_v)
+    return q[0]
+
+
+def quant_fast(w, h, bitdepth, qp_bd, intra_pic, sign_hiding, scan, coeff):
+    L = load()
+    out = np.zeros((h, w), dtype=np.int16)
+    nz = L.xvcb200_quant_fast(w, h, bitdepth, qp_bd, intra_pic, sign_hiding, scan, abi.ptr(coeff), coeff.shape[1], abi.ptr(out), w)
+    _check_leaf(L)
+    return out, nz
+
+
+def dequant(w, h, bitdepth, qp_bd, lev):
+    L = load()
+    out = np.zeros((h, w), dtype=np.int16)
+    L.xvcb200_dequant(w, h, bitdepth, qp_bd, abi.ptr(lev), lev.shape[1], abi.ptr(out), w)
+    _check_leaf(L)
+    return out
+
+
+def launch_count():
+    return int(load().xvcb200_launch_count())
+
+
+# ---------------------------------------------------------------------- batched context
+class Context:
+    """xvcb200_ctx: device-resident picture slots + the per-picture hot path."""
+
+    def __init__(self, width, height, bitdepth=10, num_slots=8, device=0):
+        self.L = load()
+        self.h = c_void_p()
+        st = self.L.xvcb200_ctx_create(ctypes.byref(self.h), device, width, height, bitdepth, 1, num_slots)
+        if st != 0:
+            msg = self.L.xvcb200_last_error_string().decode()
+            self.L.xvcb200_clear_error()
+            self.h = None
+            raise XvcB200Error("xvcb200_ctx_create failed (%d): %s" % (st, msg))
+        self.width, self.height, self.bitdepth, self.num_slots = width, height, bitdepth, num_slots
+        self.shapes = [(height, width), (height // 2, width // 2), (height // 2, width // 2)]
+        g = np.zeros(1, dtype=abi.plane_geom_dtype)
+        self.L.xvcb200_get_geometry(self.h, abi.ptr(g))
+        self.geom = g[0]
+        self.n_cus = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xvcb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ok(self, st):
+        if st != 0:
+            raise XvcB200Error("xvc_b200 call failed (%d): %s" % (st, self.L.xvcb200_ctx_error_string(self.h).decode()))
+
+    def sync(self):
+        self._ok(self.L.xvcb200_sync(self.h))
+
+    def stream(self):
+        return self.L.xvcb200_stream(self.h)
+
+    def set_stream(self, cuda_stream):
+        self._ok(self.L.xvcb200_ctx_set_stream(self.h, c_void_p(cuda_stream)))
+
+    def slot_ptr(self, slot, comp):
+        p = c_void_p()
+        self._ok(self.L.xvcb200_slot_ptr(self.h, slot, comp, ctypes.byref(p)))
+        return p.value
+
+    @staticmethod
+    def _strides(planes):
+        return (c_ssize * 3)(*[p.strides[0] // p.itemsize for p in planes])
+
+    def upload(self, slot, planes):
+        planes = [p if p.flags["C_CONTIGUOUS"] or p.strides[1] == p.itemsize else np.ascontiguousarray(p) for p in planes]
+        self._keep = planes
+        self._ok(self.L.xvcb200_upload_picture(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+
+    def upload_coeff(self, slot, planes):
+        planes = [np.ascontiguousarray(p, dtype=np.int16) for p in planes]
+        self._keep = planes
+        self._ok(self.L.xvcb200_upload_coeff(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+
+    def download(self, slot, out=None):
+        planes = out if out is not None else [np.zeros(s, dtype=np.uint16) for s in self.shapes]
+        self._ok(self.L.xvcb200_download_picture(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+        return planes
+
+    def download_coeff(self, slot):
+        planes = [np.zeros(s, dtype=np.int16) for s in self.shapes]
+        self._ok(self.L.xvcb200_download_coeff(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+        return planes
+
+    def download_padded(self, slot, comp):
+        pad = 80 if comp == 0 else 40
+        h, w = self.shapes[comp]
+        out = np.zeros((h + 2 * pad, w + 2 * pad), dtype=np.uint16)
+        self._ok(self.L.xvcb200_download_padded(self.h, slot, comp, abi.ptr(out)))
+        return out
+
+    def pad_border(self, slot):
+        self._ok(self.L.xvcb200_pad_border(self.h, slot))
+
+    def set_cus(self, cus):
+        cus = np.ascontiguousarray(cus, dtype=abi.cu_dtype)
+        self._ok(self.L.xvcb200_set_cus(self.h, abi.ptr(cus), len(cus)))
+        self.n_cus = len(cus)
+
+    def get_cus(self):
+        out = np.zeros(self.n_cus, dtype=abi.cu_dtype)
+        self._ok(self.L.xvcb200_get_cus(self.h, abi.ptr(out), self.n_cus))
+        return out
+
+    def me_search(self, orig_slot, jobs, lambda_sqrt):
+        jobs = np.ascontiguousarray(jobs, dtype=abi.me_job_dtype)
+        res = np.zeros(len(jobs), dtype=abi.me_result_dtype)
+        self._ok(self.L.xvcb200_me_search(self.h, orig_slot, abi.ptr(jobs), len(jobs), lambda_sqrt, abi.ptr(res)))
+        return res
+
+    def full_search(self, orig_slot, jobs, lambda_sqrt):
+        jobs = np.ascontiguousarray(jobs, dtype=abi.fullsearch_job_dtype)
+        res = np.zeros(len(jobs), dtype=abi.me_result_dtype)
+        self._ok(self.L.xvcb200_full_search(self.h, orig_slot, abi.ptr(jobs), len(jobs), lambda_sqrt, abi.ptr(res)))
+        return res
+
+    @staticmethod
+    def _ref_slots(ref_slots):
+        arr = np.full((2, 5), -1, dtype=np.int32)
+        for (l, i), s in ref_slots.items():
+            arr[l, i] = s
+        return arr
+
+    def motion_compensate(self, ref_slots, pred_slot):
+        arr = self._ref_slots(ref_slots)
+        self._ok(self.L.xvcb200_motion_compensate(self.h, abi.ptr(arr), pred_slot))
+
+    def tq_reconstruct(self, orig_slot, pred_slot, rec_slot, coeff_slot, intra_picture=0, table=1, off_u=0, off_v=0):
+        res = np.zeros(3 * self.n_cus, dtype=abi.tu_result_dtype)
+        self._ok(self.L.xvcb200_tq_reconstruct(self.h, orig_slot, pred_slot, rec_slot, coeff_slot, 0, intra_picture, table,
+                                               off_u, off_v, abi.ptr(res)))
+        return res
+
+    def dequant_reconstruct(self, pred_slot, rec_slot, coeff_slot, table=1, off_u=0, off_v=0):
+        self._ok(self.L.xvcb200_dequant_reconstruct(self.h, pred_slot, rec_slot, coeff_slot, table, off_u, off_v))
+
+    def deblock_picture(self, rec_slot, pic_type, ref_poc, beta_offset=0, tc_offset=0, table=1, off_u=0, off_v=0):
+        poc = np.zeros((2, 5), dtype=np.int64)
+        for (l, i), p in ref_poc.items():
+            poc[l, i] = p
+        self._ok(self.L.xvcb200_deblock_picture_ex(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
+                                                   abi.ptr(poc)))
+
+    def encode_picture(self, params, want_results=True):
+        prm = params if isinstance(params, np.ndarray) else np.array([params], dtype=abi.picture_params_dtype)
+        nl = 2 if int(prm["pic_type"][0]) == 0 else 1
+        me = np.zeros(nl * self.n_cus, dtype=abi.me_result_dtype) if want_results else None
+        tu = np.zeros(3 * self.n_cus, dtype=abi.tu_result_dtype) if want_results else None
+        self._ok(self.L.xvcb200_encode_picture(self.h, abi.ptr(prm), abi.ptr(me), abi.ptr(tu)))
+        return me, tu
