@@ -1,0 +1,371 @@
+#!/usr/bin/env python3
+"""bench.py -- the xvc hot path on B200: encoded Mpixels/s at 1080p qp32.
+
+A step = one inter (bi-predicted) picture through the whole hot path
+    ME (TZ full-pel + sub-pel, 2 reference pictures) -> list decision -> motion compensation
+    -> residual / forward transform / QuantFast / dequant / inverse transform / reconstruction
+    -> deblocking -> border padding
+on a seeded CU partition of a synthetic 1920x1080 4:2:0 picture, 10-bit internal, qp 32.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]      our arm (CUDA through the C ABI)
+  python bench.py --impl reference ...                      the reference's own CPU code on the
+                                                            host cores (oracle/_ref), same step
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM),
+`e2e` the same step through the C ABI with host buffers (H2D of the picture + CU array, D2H of
+reconstruction, levels and CU decisions inside the timed region).
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from xvc_b200 import abi, workload  # noqa: E402
+
+WIDTH, HEIGHT, BITDEPTH, QP = 1920, 1080, 10, 32
+POC, REF_POCS, SUB_GOP = 8, (0, 16), 16
+METRIC = "encoded Mpixels/sec at 1080p qp32; bit-exact recon vs reference"
+
+
+def picture_inputs(index_offset=0, seed=1234, partition_seed=7):
+    """(current, ref L0, ref L1) planes + CU partition + picture parameters of one step."""
+    canvas = workload.synth_canvas(WIDTH, HEIGHT, seed)
+    frames = [workload.synth_frame(canvas, WIDTH, HEIGHT, i + index_offset, BITDEPTH) for i in (POC, REF_POCS[0], REF_POCS[1])]
+    cus = workload.make_partition(WIDTH, HEIGHT, seed=partition_seed, min_size=8, qp=QP)
+    lam = workload.lambda_for_qp(QP)
+    prm = np.zeros(1, dtype=abi.picture_params_dtype)
+    prm["pic_type"] = 0
+    for l in range(2):
+        prm["search_range"][0, l, 0] = workload.search_range_uni(POC, REF_POCS[l], SUB_GOP)
+        prm["ref_poc"][0, l, 0] = REF_POCS[l]
+    prm["lambda_sqrt"] = np.sqrt(lam)
+    prm["chroma_offset_table"] = 1
+    prm["num_ref"] = 1
+    prm["deblock"], prm["pad"] = 1, 1
+    prm["ref_slots"] = -1
+    return frames, cus, prm, lam
+
+
+def recon_digest(planes):
+    h = hashlib.md5()
+    for p in planes:
+        h.update(np.ascontiguousarray(p).tobytes())
+    return h.hexdigest()
+
+
+def config_dict(n_cus, extra=None):
+    cfg = {"workload": "1920x1080 synthetic YUV420 qp32, ME+transform+deblock (configs[1])",
+           "width": WIDTH, "height": HEIGHT, "bitdepth_internal": BITDEPTH, "qp": QP,
+           "picture": "bi-predicted, 2 reference pictures (POC %d, refs %d/%d), search range %d" % (
+               POC, REF_POCS[0], REF_POCS[1], workload.search_range_uni(POC, REF_POCS[0], SUB_GOP)),
+           "partition": "seeded random quad/binary CU tree, 8..64, %d CUs; predictor mvp = 0 for every CU" % n_cus,
+           "l2": "flushed between timed iterations (256 MiB write)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the same step
+# ------------------------------------------------------------------------------------------
+class CpuArm:
+    """oracle/_ref (the unmodified reference compiled by oracle/Makefile) when it was built,
+    else the C restatement.  Test infrastructure used as a timed baseline only."""
+
+    def __init__(self):
+        from oracle import bindings
+        self.b = bindings
+        self.kind = "reference" if bindings.have_ref() else "port"
+        if self.kind == "reference":
+            self.ref = bindings.Ref()
+            self.cores = int(self.ref.L.xref_num_threads())
+        else:
+            self.oracle = bindings.Oracle()
+            self.cores = 1
+
+    def run(self, frames, cus, prm, lam):
+        """One step; returns (seconds, reconstruction planes)."""
+        if self.kind == "reference":
+            s = self.ref.session(WIDTH, HEIGHT, BITDEPTH, 0, QP, lam, simd=1, poc=POC, sub_gop=SUB_GOP)
+            s.set_orig(frames[0])
+            s.add_ref(0, 0, REF_POCS[0], frames[1])
+            s.add_ref(1, 0, REF_POCS[1], frames[2])
+            t0 = time.perf_counter()
+            s.encode_picture(prm, cus, threads=self.cores)
+            dt = time.perf_counter() - t0
+            rec = s.get_rec()
+            s.close()
+            return dt, rec
+        P = self.b.Picture
+        orig = P(WIDTH, HEIGHT, 0, frames[0])
+        refs = {(0, 0): P(WIDTH, HEIGHT, 80, frames[1]), (1, 0): P(WIDTH, HEIGHT, 80, frames[2])}
+        for r in refs.values():
+            self.oracle.pad_border(r)
+        pred, rec = P(WIDTH, HEIGHT, 80), P(WIDTH, HEIGHT, 80)
+        t0 = time.perf_counter()
+        self.oracle.encode_picture(orig, refs, pred, rec, BITDEPTH, cus.copy(), prm)
+        dt = time.perf_counter() - t0
+        return dt, rec.planes()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames, cus, prm, lam = picture_inputs()
+    arm = CpuArm()
+    for _ in range(args.warmup):
+        arm.run(frames, cus, prm, lam)
+    times = [arm.run(frames, cus, prm, lam)[0] for _ in range(args.steps)]
+    sec = float(np.mean(times))
+    mpx = WIDTH * HEIGHT / sec / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpx, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16 samples / int32 arithmetic", "data": "synthetic", "config": config_dict(len(cus)),
+        "cpu_baseline": {"value": mpx, "unit": "Mpixels/s", "cores": arm.cores, "kind": arm.kind,
+                         "sample": "one full 1920x1080 picture per step, %d steps, all host threads over CUs" % args.steps},
+        "e2e": {"value": mpx, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], False
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, reasons))
+                time.sleep(0.02)
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: %s" % getattr(self, "error", "no samples")]}
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+                 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        seen = set()
+        for _, r in self.samples:
+            for bit, name in names.items():
+                if r & bit:
+                    seen.add(name)
+        return {"sm_mhz": float(np.median([s for s, _ in self.samples])), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(seen), "samples": len(self.samples)}
+
+
+def run_ours(args):
+    import torch
+    from xvc_b200 import lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- xvc_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # frame-parallel sharding: every rank encodes its own picture of the sequence (weak scaling)
+    frames, cus, prm, lam = picture_inputs(index_offset=rank)
+    n = len(cus)
+    ctx = lib.Context(WIDTH, HEIGHT, BITDEPTH, num_slots=6, device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    SL = dict(orig=0, ref0=1, ref1=2, pred=3, rec=4, coeff=5)
+    prm["orig_slot"], prm["pred_slot"], prm["rec_slot"], prm["coeff_slot"] = SL["orig"], SL["pred"], SL["rec"], SL["coeff"]
+    prm["ref_slots"][0, 0, 0], prm["ref_slots"][0, 1, 0] = SL["ref0"], SL["ref1"]
+    ctx.upload(SL["orig"], frames[0])
+    for slot, f in ((SL["ref0"], frames[1]), (SL["ref1"], frames[2])):
+        ctx.upload(slot, f)
+        ctx.pad_border(slot)
+    ctx.set_cus(cus)
+    ctx.sync()
+    ctx.set_profiling(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        ctx.set_cus(cus)          # restores predictors / flags the previous step overwrote (device copy)
+        ctx.encode_picture(prm, want_results=False)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.launch_count()
+    step_ms, stage_ms = [], {k: [] for k in lib.Context.STAGES}
+    for _ in range(args.steps):
+        ctx.set_cus(cus)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.encode_picture(prm, want_results=False)
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        for k, v in ctx.stage_times_ms().items():
+            stage_ms[k].append(v)
+    launches = lib.launch_count() - launches0
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    total_ms = float(np.sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * WIDTH * HEIGHT / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # noqa: E731
+    h_orig = [pin(p) for p in frames[0]]
+    h_rec = [pin(np.zeros_like(p)) for p in frames[0]]
+    h_lev = [pin(np.zeros(p.shape, dtype=np.int16)) for p in frames[0]]
+    h2d = sum(p.nbytes for p in h_orig) + cus.nbytes
+    d2h = sum(p.nbytes for p in h_rec) + sum(p.nbytes for p in h_lev) + cus.nbytes
+
+    def e2e_step():
+        ctx.upload(SL["orig"], h_orig)
+        ctx.set_cus(cus)
+        ctx.encode_picture(prm, want_results=False)
+        ctx.L.xvcb200_download_picture(ctx.h, SL["rec"], abi.plane_ptr_array(h_rec), ctx._strides(h_rec))
+        ctx.L.xvcb200_download_coeff(ctx.h, SL["coeff"], abi.plane_ptr_array(h_lev), ctx._strides(h_lev))
+        return ctx.get_cus()
+
+    ctx.set_profiling(False)
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        cus_out = e2e_step()
+    torch.cuda.synchronize()
+    e2e_sec = (time.perf_counter() - t0)
+    # the flush is not part of the step: time it alone and subtract
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+    torch.cuda.synchronize()
+    e2e_sec -= (time.perf_counter() - t1)
+    if dist is not None:
+        t = torch.tensor([e2e_sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e_value = world * WIDTH * HEIGHT * args.steps / e2e_sec / 1e6
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel, from the live per-stage CUDA events
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    P = WIDTH * HEIGHT
+    alg_bytes = {   # SURVEY.md section 8(d), S = 2 bytes/sample, 2 reference pictures
+        "tz_search": P * 2 * (1 + 2) + 16 * n * 2,
+        "subpel_search": P * 2 * (1 + 2) + 32 * n * 2,
+        "motion_compensate": int(1.5 * P * 2 * 2),
+        "tq_reconstruct": int(4 * 1.5 * P * 2),
+        "deblock": int(2 * 1.5 * P * 2) + 2 * P,
+        "pad_border": int(0.2 * 1.5 * P * 2),
+        "me_jobs": 60 * n,
+    }
+    stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    dom = max(stage_avg, key=stage_avg.get)
+    achieved = alg_bytes[dom] / (stage_avg[dom] * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes[dom], "avg_ms": stage_avg[dom],
+                "note": "integer SAD search: ALU/L1-bound, not HBM-bound; see DESIGN.md for op counts",
+                "stages_ms": stage_avg,
+                "stages_frac_of_hbm": {k: alg_bytes[k] / (v * 1e-3) / 1e9 / peak for k, v in stage_avg.items() if v > 0}}
+
+    # ---- CPU baseline beside it (bounded sample) + bit-exact reconstruction check
+    cpu = None
+    bitexact = None
+    try:
+        arm = CpuArm()
+        frames0, cus0, prm0, lam0 = picture_inputs(index_offset=0)
+        t_first, rec_cpu = arm.run(frames0, cus0, prm0, lam0)
+        reps = int(min(20, max(1, 8.0 / max(t_first, 1e-3)))) if arm.kind == "reference" else 1
+        times = [t_first] + [arm.run(frames0, cus0, prm0, lam0)[0] for _ in range(reps - 1)]
+        sec = float(np.mean(times[1:])) if len(times) > 1 else t_first
+        cpu = {"value": WIDTH * HEIGHT / sec / 1e6, "unit": "Mpixels/s", "cores": arm.cores, "kind": arm.kind,
+               "sample": "%d full 1920x1080 pictures of the same step (first one untimed warm-up)" % len(times)}
+        bitexact = recon_digest(rec_cpu) == recon_digest(h_rec)
+    except Exception as e:  # noqa: BLE001
+        cpu = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "port", "sample": "unavailable: %r" % (e,)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16 samples / int32 arithmetic", "data": "synthetic",
+        "config": config_dict(n, {"parallelism": "frame-parallel: one picture per GPU" if world > 1 else "single GPU"}),
+        "frames_per_s": value * 1e6 / (WIDTH * HEIGHT),
+        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "recon_bitexact_vs_cpu_baseline": bitexact,
+        "me_sad_candidates_per_step": None,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -335,6 +335,12 @@ typedef struct {
 int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *params,
                            xvcb200_me_result *me_results, xvcb200_tu_result *tu_results);
 
+/* Optional per-stage device timing of xvcb200_encode_picture (CUDA events on the context
+ * stream): ms[0..6] = job set-up, full-pel TZ search, sub-pel search + list decision, motion
+ * compensation, T/Q/recon, deblocking, padding -- of the last call. */
+int xvcb200_set_profiling(xvcb200_ctx *ctx, int enable);
+int xvcb200_get_stage_times(xvcb200_ctx *ctx, float ms[7]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,7 +275,7 @@ def test_tq_reconstruct(oracle, bd, qp, min_size):
     cus["qp"][::3] = qp + 3
     cus["ref_idx"][:, 0] = 0
     rng = np.random.default_rng(121)
-    predp = [np.clip(p.astype(np.int32) + rng.integers(-40, 41, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16) for p in cur]
+    predp = [np.clip(p.astype(np.int32) + rng.integers(-(60 << (bd - 8)), (60 << (bd - 8)) + 1, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16) for p in cur]
     ctx = lib.Context(width, height, bd, 6)
     ctx.upload(0, cur)
     ctx.upload(3, predp)

@@ -354,7 +354,7 @@ def test_tq_reconstruct(oracle, ref, bd, qp):
     cus["qp"][::3] = qp + 3
     cus["ref_idx"][:, 0] = 0
     rng = np.random.default_rng(21)
-    predp = [np.clip(p.astype(np.int32) + rng.integers(-40, 41, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16)
+    predp = [np.clip(p.astype(np.int32) + rng.integers(-(60 << (bd - 8)), (60 << (bd - 8)) + 1, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16)
              for p in orig.planes()]
     s.set_cus(cus)
     s.set_pred(predp)
@@ -364,6 +364,7 @@ def test_tq_reconstruct(oracle, ref, bd, qp):
     levels, to = oracle.tq_reconstruct(orig, pred, rec, bd, cus_o)
     assert np.array_equal(tr["num_non_zero"], to["num_non_zero"])
     assert np.array_equal(tr["ssd"], to["ssd"])
+    assert (to["num_non_zero"] > 1).sum() > len(cus) // 4   # the quantiser and sign hiding had real work
     for c in range(3):
         assert np.array_equal(s.get_rec()[c], rec.plane(c)), c
         assert np.array_equal(s.get_coeff()[c], levels[c]), c

@@ -348,6 +348,10 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int class_offset[7][7];
   xvcb200_me_job *d_jobs = nullptr; xvcb200_me_result *d_me = nullptr; xvcb200_tu_result *d_tu = nullptr;
   int jobs_cap = 0, me_cap = 0, tu_res_cap = 0;
+  // optional per-stage timing of xvcb200_encode_picture (CUDA events on the context stream)
+  bool profile = false;
+  cudaEvent_t ev[9] = {nullptr};
+  bool ev_valid = false;
 };
 
 }  // extern "C"
@@ -436,6 +440,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
+  for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -571,8 +576,10 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
   if (n == 0) return XVCB200_OK;
   if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
   c->check(cudaMemcpyAsync(c->ex.d_jobs, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "me jobs");
-  c->check(launch_me_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
-                            c->plane(orig_slot, 0), c->ex.d_luma_views, (int)c->slots.size(), c->ex.d_me), "me_search");
+  c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
+                            c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "tz_search");
+  c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
+                                c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");
   c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "me results");
   return xvcb200_sync(c);
 }
@@ -666,6 +673,28 @@ int xvcb200_deblock_picture_ex(xvcb200_ctx *c, int rec_slot, int pic_type, int b
   return c->status;
 }
 
+// per-stage device times of the last xvcb200_encode_picture: ms[0..6] = make jobs, full-pel TZ
+// search, sub-pel search + list decision, motion compensation, T/Q/recon, deblocking, padding
+int xvcb200_set_profiling(xvcb200_ctx *ctx, int enable) {
+  if (!ctx) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (enable && !c->ex.ev[0])
+    for (auto &e : c->ex.ev)
+      if (!c->check(cudaEventCreate(&e), "cudaEventCreate")) return c->status;
+  c->ex.profile = enable != 0;
+  c->ex.ev_valid = false;
+  return XVCB200_OK;
+}
+int xvcb200_get_stage_times(xvcb200_ctx *ctx, float ms[7]) {
+  if (!ctx || !ms) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (!c->ex.ev_valid) return XVCB200_INVALID_ARGUMENT;
+  if (!c->check(cudaEventSynchronize(c->ex.ev[7]), "cudaEventSynchronize")) return c->status;
+  for (int i = 0; i < 7; i++)
+    if (!c->check(cudaEventElapsedTime(&ms[i], c->ex.ev[i], c->ex.ev[i + 1]), "cudaEventElapsedTime")) return c->status;
+  return XVCB200_OK;
+}
+
 // ---------------------------------------------------------------- (C) picture pipeline
 int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, xvcb200_me_result *me_results,
                            xvcb200_tu_result *tu_results) {
@@ -682,22 +711,35 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     return c->status;
   const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
   const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
+  int stage = 0;
+  auto mark = [&]() { if (c->ex.profile) cudaEventRecord(c->ex.ev[stage], c->stream); stage++; };
+  mark();   // 0: start
   c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
-  c->check(launch_me_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                            c->plane(prm->orig_slot, 0), c->ex.d_luma_views, (int)c->slots.size(), c->ex.d_me), "me_search");
+  mark();   // 1: jobs built
+  c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
+                            c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "tz_search");
+  mark();   // 2: full-pel search done
+  c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
+                                c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");
   c->check(launch_me_decide(c->stream, c->d_cus, n, nl, c->ex.d_me), "me_decide");
+  mark();   // 3: sub-pel search + list decision done
   Pic3 refs[2][5];
   refs_from_slots(c, prm->ref_slots, refs);
   c->check(launch_motion_compensate(c->stream, c->d_cus, n, c->bitdepth, refs, pic3(c, prm->pred_slot)), "motion_compensate");
+  mark();   // 4: prediction done
   int st = tq_common(c, prm->orig_slot, prm->pred_slot, prm->rec_slot, prm->coeff_slot, 0, prm->chroma_offset_table,
                      prm->chroma_offset_u, prm->chroma_offset_v, 0, nullptr);
   if (st != XVCB200_OK) return st;
+  mark();   // 5: T/Q/recon done
   if (prm->deblock) {
     st = xvcb200_deblock_picture_ex(c, prm->rec_slot, prm->pic_type, prm->beta_offset, prm->tc_offset, prm->chroma_offset_table,
                                     prm->chroma_offset_u, prm->chroma_offset_v, prm->ref_poc);
     if (st != XVCB200_OK) return st;
   }
+  mark();   // 6: deblocking done
   if (prm->pad) xvcb200_pad_border(c, prm->rec_slot);
+  mark();   // 7: padding done
+  c->ex.ev_valid = c->ex.profile;
   if (me_results)
     c->check(cudaMemcpyAsync(me_results, c->ex.d_me, sizeof(*me_results) * (size_t)n * nl, cudaMemcpyDeviceToHost, c->stream), "me results");
   if (tu_results)

@@ -396,12 +396,19 @@ __global__ void __launch_bounds__(128) subpel_kernel(const xvcb200_cu *__restric
   }
 }
 
-cudaError_t launch_me_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
-                             uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, int n_slots,
-                             xvcb200_me_result *d_res) {
+cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
+                             uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res) {
   if (n <= 0) return cudaSuccess;
-  g_launch_count += 2;
+  g_launch_count++;
   tz_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
+                                 int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
+                                 xvcb200_me_result *d_res) {
+  if (n <= 0) return cudaSuccess;
+  g_launch_count++;
   subpel_kernel<<<n, 128, 0, s>>>(d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res);
   return cudaGetLastError();
 }

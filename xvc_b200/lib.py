@@ -36,7 +36,7 @@ EXPORTS = [
     "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_tq_reconstruct",
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex",
-    "xvcb200_encode_picture",
+    "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
 ]
 
 
@@ -104,6 +104,8 @@ def load():
     L.xvcb200_deblock_picture.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.xvcb200_deblock_picture_ex.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p]
     L.xvcb200_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    L.xvcb200_set_profiling.argtypes = [c_void_p, c_int]
+    L.xvcb200_get_stage_times.argtypes = [c_void_p, c_void_p]
     _lib = L
     return L
 
@@ -359,6 +361,16 @@ class Context:
             poc[l, i] = p
         self._ok(self.L.xvcb200_deblock_picture_ex(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
                                                    abi.ptr(poc)))
+
+    STAGES = ("me_jobs", "tz_search", "subpel_search", "motion_compensate", "tq_reconstruct", "deblock", "pad_border")
+
+    def set_profiling(self, on=True):
+        self._ok(self.L.xvcb200_set_profiling(self.h, int(on)))
+
+    def stage_times_ms(self):
+        ms = np.zeros(7, dtype=np.float32)
+        self._ok(self.L.xvcb200_get_stage_times(self.h, abi.ptr(ms)))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
 
     def encode_picture(self, params, want_results=True):
         prm = params if isinstance(params, np.ndarray) else np.array([params], dtype=abi.picture_params_dtype)
