@@ -179,7 +179,7 @@ class ClockSampler(threading.Thread):
 
 def run_ours(args):
     import torch
-    from xvc_b200 import lib
+    from xvc_b200 import lib, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,10 +195,14 @@ def run_ours(args):
     # frame-parallel sharding: every rank encodes its own picture of the sequence (weak scaling)
     frames, cus, prm, lam = picture_inputs(index_offset=rank)
     n = len(cus)
-    ctx = lib.Context(WIDTH, HEIGHT, BITDEPTH, num_slots=6, device=local_rank)
-    stream = torch.cuda.current_stream()
+    # slots: 0 orig, 1/2 references, 3 prediction, 4 levels, 5.. one reconstruction slot per rank
+    # (contiguous: the frame-parallel all-gather lands every rank's reconstruction in place)
+    ctx = lib.Context(WIDTH, HEIGHT, BITDEPTH, num_slots=5 + world, device=local_rank)
+    # a dedicated (non-default) torch stream: the library enqueues on it, torch events time it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    SL = dict(orig=0, ref0=1, ref1=2, pred=3, rec=4, coeff=5)
+    SL = dict(orig=0, ref0=1, ref1=2, pred=3, coeff=4, rec=5 + rank)
     prm["orig_slot"], prm["pred_slot"], prm["rec_slot"], prm["coeff_slot"] = SL["orig"], SL["pred"], SL["rec"], SL["coeff"]
     prm["ref_slots"][0, 0, 0], prm["ref_slots"][0, 1, 0] = SL["ref0"], SL["ref1"]
     ctx.upload(SL["orig"], frames[0])
@@ -218,6 +222,8 @@ def run_ours(args):
     def device_step():
         ctx.set_cus(cus)          # restores predictors / flags the previous step overwrote (device copy)
         ctx.encode_picture(prm, want_results=False)
+        if dist is not None:
+            sharding.frame_parallel_exchange(ctx, dist, rank, world, 5)
 
     for _ in range(args.warmup):
         device_step()
@@ -232,6 +238,8 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ctx.encode_picture(prm, want_results=False)
+        if dist is not None:   # finished, padded reconstructions to every GPU that will reference them
+            sharding.frame_parallel_exchange(ctx, dist, rank, world, 5)
         e1.record(stream)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
@@ -261,6 +269,8 @@ def run_ours(args):
         ctx.upload(SL["orig"], h_orig)
         ctx.set_cus(cus)
         ctx.encode_picture(prm, want_results=False)
+        if dist is not None:
+            sharding.frame_parallel_exchange(ctx, dist, rank, world, 5)
         ctx.L.xvcb200_download_picture(ctx.h, SL["rec"], abi.plane_ptr_array(h_rec), ctx._strides(h_rec))
         ctx.L.xvcb200_download_coeff(ctx.h, SL["coeff"], abi.plane_ptr_array(h_lev), ctx._strides(h_lev))
         return ctx.get_cus()
@@ -338,7 +348,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16 samples / int32 arithmetic", "data": "synthetic",
-        "config": config_dict(n, {"parallelism": "frame-parallel: one picture per GPU" if world > 1 else "single GPU"}),
+        "config": config_dict(n, {"parallelism": ("frame-parallel: one picture per GPU + NCCL all-gather of the padded reconstructions (%d x %.1f MB) inside the step" % (world, ctx.slot_region(0)[1] / 1e6)) if world > 1 else "single GPU"}),
         "frames_per_s": value * 1e6 / (WIDTH * HEIGHT),
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

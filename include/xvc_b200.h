@@ -267,6 +267,11 @@ int xvcb200_get_geometry(xvcb200_ctx *ctx, xvcb200_plane_geom *geom);
 /* device address of sample (0,0) of a plane of a slot (uint16_t*); coefficient slots: int16_t* */
 int xvcb200_slot_ptr(xvcb200_ctx *ctx, int slot, int comp, void **dev_ptr);
 
+/* the whole device allocation of a slot (three padded planes).  All slots of a context live
+ * back to back in one arena, so slots [s, s+n) form one contiguous buffer of n * bytes --
+ * e.g. the destination of an NCCL all-gather of reconstructed pictures. */
+int xvcb200_slot_region(xvcb200_ctx *ctx, int slot, void **base, uint64_t *bytes);
+
 /* host <-> device picture transfer; host planes are tight or strided (elements). */
 int xvcb200_upload_picture(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]);
 int xvcb200_download_picture(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]);
@@ -312,6 +317,15 @@ int xvcb200_deblock_picture(xvcb200_ctx *ctx, int rec_slot, int pic_type, int be
 int xvcb200_deblock_picture_ex(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_offset, int tc_offset,
                                int chroma_offset_table, int chroma_offset_u, int chroma_offset_v,
                                const int64_t ref_poc[2][5]);
+
+/* One band of the picture for CTB-row sharding across GPUs.  pass_mask: 1 = vertical edges of
+ * rows [y_begin, y_end), 2 = horizontal edges whose q side lies in [y_begin, y_end) (the edge
+ * ON y_begin belongs to this band and reads/writes up to 4/3 rows above it: the caller
+ * exchanges those halo rows, see xvc_b200/sharding.py).  The context's CU array must describe
+ * the whole picture. */
+int xvcb200_deblock_band(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_offset, int tc_offset,
+                         int chroma_offset_table, int chroma_offset_u, int chroma_offset_v,
+                         const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end);
 
 /* ------------------------------------------------------------------------------------
  * (C) picture-level hot path

@@ -123,6 +123,7 @@ class Oracle:
         L.xo_tq_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         L.xo_dequant_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]
         L.xo_deblock_picture.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+        L.xo_deblock_band.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int]
         L.xo_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
 
     # ---- leaf
@@ -235,6 +236,13 @@ class Oracle:
         poc = _poc_array(ref_poc)
         self.L.xo_deblock_picture(ctypes.byref(r), bitdepth, abi.ptr(cus), len(cus), pic_type, beta_offset, tc_offset,
                                   table, off_u, off_v, poc)
+
+    def deblock_band(self, rec, bitdepth, cus, pic_type, ref_poc, pass_mask, y_begin, y_end, beta_offset=0, tc_offset=0,
+                     table=1, off_u=0, off_v=0):
+        r = rec.c_struct()
+        poc = _poc_array(ref_poc)
+        self.L.xo_deblock_band(ctypes.byref(r), bitdepth, abi.ptr(cus), len(cus), pic_type, beta_offset, tc_offset,
+                               table, off_u, off_v, poc, pass_mask, y_begin, y_end)
 
     def encode_picture(self, orig, refs, pred, rec, bitdepth, cus, params):
         levels = [np.zeros((orig.height[c], orig.width[c]), dtype=np.int16) for c in range(3)]

@@ -1080,6 +1080,16 @@ static void db_chroma_segment(uint16_t *s, ptrdiff_t across, ptrdiff_t along, in
  * horizontal edges; 4x4 grid; chroma only for bs == 2 on the 8-sample chroma grid. */
 void xo_deblock_picture(xo_picture *rec, int bitdepth, const xvcb200_cu *cus, int n, int pic_type, int beta_offset,
                         int tc_offset, int table, int off_u, int off_v, const int64_t ref_poc[2][5]) {
+  xo_deblock_band(rec, bitdepth, cus, n, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, 3, 0,
+                  rec->height[0]);
+}
+
+/* The same walk restricted to one band of rows and to the selected passes (1 = vertical edges,
+ * 2 = horizontal edges): the unit a CTB-row shard executes.  Whole-picture order is recovered
+ * when the bands run top to bottom with their halo rows exchanged. */
+void xo_deblock_band(xo_picture *rec, int bitdepth, const xvcb200_cu *cus, int n, int pic_type, int beta_offset,
+                     int tc_offset, int table, int off_u, int off_v, const int64_t ref_poc[2][5], int pass_mask,
+                     int y_begin, int y_end) {
   const int W = rec->width[0], H = rec->height[0];
   db_ctx d;
   d.cus = cus; d.pic_type = pic_type;
@@ -1100,6 +1110,7 @@ void xo_deblock_picture(xo_picture *rec, int bitdepth, const xvcb200_cu *cus, in
       for (int dy = 0; dy < 64; dy += 4)
         for (int dx = 0; dx < 64; dx += 4) {
           const int x = (ctu % ctus_x) * 64 + dx, y = (ctu / ctus_x) * 64 + dy;
+          if (!(pass_mask & (1 << dir)) || y < y_begin || y >= y_end) continue;
           const int iq = db_cu_at(&d, x, y);
           if (iq < 0) continue;
           const int ip = dir == 0 ? db_cu_at(&d, x - 1, y) : db_cu_at(&d, x, y - 1);

@@ -97,6 +97,9 @@ void xo_dequant_reconstruct(const xo_picture *pred, xo_picture *rec, int16_t *co
                             const xvcb200_cu *cus, int n, int table, int off_u, int off_v);
 void xo_deblock_picture(xo_picture *rec, int bitdepth, const xvcb200_cu *cus, int n, int pic_type, int beta_offset,
                         int tc_offset, int table, int off_u, int off_v, const int64_t ref_poc[2][5]);
+void xo_deblock_band(xo_picture *rec, int bitdepth, const xvcb200_cu *cus, int n, int pic_type, int beta_offset,
+                     int tc_offset, int table, int off_u, int off_v, const int64_t ref_poc[2][5], int pass_mask,
+                     int y_begin, int y_end);
 void xo_encode_picture(const xo_picture *orig, const xo_picture *const refs[2][5], xo_picture *pred, xo_picture *rec,
                        int16_t *const levels[3], int bitdepth, xvcb200_cu *cus, int n,
                        const xvcb200_picture_params *params, xvcb200_me_result *me_results,

@@ -1,0 +1,77 @@
+"""world_size-2 (and 3) gloo runs on CPU of the N>1 host logic: CTU-row banded encode with the
+deblocking halo exchange must reproduce the single-process result bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import common
+from oracle.bindings import Oracle, Picture
+from xvc_b200 import sharding, workload
+
+W, H, BD, QP = 200, 136, 10, 32
+
+
+def _inputs():
+    cur, r0, r1 = common.frames(W, H, BD, 301)
+    cus = workload.make_partition(W, H, seed=31, min_size=4, qp=QP)
+    prm = common.picture_params(0, workload.lambda_for_qp(QP), ranges=(96, 96))
+    prm["pad"] = 0
+    return cur, r0, r1, cus, prm
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    cur, r0, r1, cus, prm = _inputs()
+    eng = OracleEngine(W, H, BD, cur, {(0, 0): r0, (1, 0): r1}, {(0, 0): 0, (1, 0): 16})
+    enc = sharding.BandedPictureEncoder(eng, dist, rank, world, H)
+    full = enc.encode(cus, prm)
+    y0, y1 = enc.bands[rank]
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), cus=full.view(np.uint8), y0=y0, y1=y1,
+             **{"p%d" % c: enc.gather_band_rows(c).numpy() for c in range(3)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_banded_encode_matches_single_process(tmp_path, world):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    cur, r0, r1, cus, prm = _inputs()
+    o = Oracle()
+    pred, rec = Picture(W, H, 80), Picture(W, H, 80)
+    cus_ref = cus.copy()
+    o.encode_picture(Picture(W, H, 0, cur), common.oracle_refs(o, W, H, r0, r1), pred, rec, BD, cus_ref, prm)
+    planes = [np.zeros((H >> (1 if c else 0), W >> (1 if c else 0)), dtype=np.uint16) for c in range(3)]
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        y0, y1 = int(z["y0"]), int(z["y1"])
+        for c in range(3):
+            s = 1 if c else 0
+            planes[c][y0 >> s:y1 >> s] = z["p%d" % c].astype(np.uint16)
+        got = z["cus"].view(cus.dtype)
+        for f in ("flags", "ref_idx", "mv"):
+            assert np.array_equal(got[f], cus_ref[f]), (r, f)
+    for c in range(3):
+        assert np.array_equal(planes[c], rec.plane(c)), c
+
+
+def test_band_rows_cover_picture():
+    for h in (64, 72, 136, 1080, 2160):
+        for world in (1, 2, 3, 4, 8):
+            bands = sharding.band_rows(h, world)
+            assert bands[0][0] == 0 and bands[-1][1] == h
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            assert all(y0 % 64 == 0 or y0 == h for y0, _ in bands)

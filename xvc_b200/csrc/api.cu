@@ -402,13 +402,18 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
     plane_bytes[p] = ((size_t)c->geom.pitch[p] * (c->geom.height[p] + 2 * c->geom.margin_y[p]) * 2 + 255) & ~(size_t)255;
     total += plane_bytes[p];
   }
+  // all slots in ONE allocation, back to back: a run of slots is a contiguous buffer, so a
+  // collective (NCCL all-gather of finished reconstructions) can land directly in reference slots
   c->slots.resize(num_slots);
   std::vector<PlaneView> views(num_slots);
+  uint8_t *arena = nullptr;
+  if (!c->check(cudaMalloc(&arena, total * num_slots), "cudaMalloc(slots)")) { int st = c->status; delete c; return st; }
+  cudaMemsetAsync(arena, 0, total * num_slots, c->stream);
+  c->slot_stride = total;
   for (int s = 0; s < num_slots; s++) {
     DevPicture &d = c->slots[s];
-    if (!c->check(cudaMalloc(&d.alloc, total), "cudaMalloc(slot)")) { xvcb200_ctx_destroy(c); return XVCB200_OUT_OF_MEMORY; }
+    d.alloc = arena + (size_t)s * total;
     d.bytes = total;
-    cudaMemsetAsync(d.alloc, 0, total, c->stream);
     size_t off = 0;
     for (int p = 0; p < 3; p++) {
       d.base[p] = reinterpret_cast<Sample *>(d.alloc + off) + (size_t)c->geom.margin_y[p] * c->geom.pitch[p] + c->geom.margin_x[p];
@@ -435,7 +440,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   CtxFull *c = full(ctx);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (auto &s : c->slots) if (s.alloc) cudaFree(s.alloc);
+  if (!c->slots.empty() && c->slots[0].alloc) cudaFree(c->slots[0].alloc);   // one arena for all slots
   cudaFree(c->d_cus); cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
   cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -476,6 +481,13 @@ int xvcb200_slot_ptr(xvcb200_ctx *c, int slot, int comp, void **p) {
   return XVCB200_OK;
 }
 void *xvcb200_stream(xvcb200_ctx *c) { return c ? c->stream : nullptr; }
+// whole allocation of a slot (three padded planes); consecutive slots are contiguous
+int xvcb200_slot_region(xvcb200_ctx *c, int slot, void **base, uint64_t *bytes) {
+  if (!c || !base || !bytes || slot < 0 || slot >= (int)c->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  *base = c->slots[slot].alloc;
+  *bytes = c->slot_stride;
+  return XVCB200_OK;
+}
 
 static bool slot_ok(xvcb200_ctx *c, int slot) { return c && slot >= 0 && slot < (int)c->slots.size(); }
 
@@ -656,20 +668,29 @@ int xvcb200_upload_coeff(xvcb200_ctx *c, int slot, const int16_t *const planes[3
   return xvcb200_upload_picture(c, slot, reinterpret_cast<const uint16_t *const *>(planes), strides);
 }
 
+int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
+                         int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end);
 int xvcb200_deblock_picture(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset,
                             const int64_t ref_poc[2][5]) {
   return xvcb200_deblock_picture_ex(c, rec_slot, pic_type, beta_offset, tc_offset, 1, 0, 0, ref_poc);
 }
 int xvcb200_deblock_picture_ex(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table,
                                int off_u, int off_v, const int64_t ref_poc[2][5]) {
-  if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1) return XVCB200_INVALID_ARGUMENT;
+  if (!c) return XVCB200_INVALID_ARGUMENT;
+  return xvcb200_deblock_band(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, 3, 0, c->height);
+}
+int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
+                         int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end) {
+  if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1 || y_begin < 0 || y_end > c->height ||
+      y_begin > y_end || (y_begin & 3) || (y_end & 3) || (pass_mask & ~3))
+    return XVCB200_INVALID_ARGUMENT;
   DeblockParams p;
   p.bitdepth = c->bitdepth; p.pic_type = pic_type; p.beta_offset = beta_offset; p.tc_offset = tc_offset;
   p.table = table; p.off_u = off_u; p.off_v = off_v;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) p.ref_poc[l][i] = ref_poc[l][i];
   c->check(launch_deblock(c->stream, c->d_cus, c->n_cus, p, pic3(c, rec_slot), c->d_cu_map, c->d_edge_bs[0], c->d_edge_bs[1],
-                          c->map_w, c->map_h), "deblock");
+                          c->map_w, c->map_h, pass_mask, y_begin, y_end), "deblock");
   return c->status;
 }
 

@@ -163,15 +163,18 @@ __device__ void chroma_segment(Sample *s, int across, int along, int bitdepth, i
 template <int DIR>   // 0: vertical edges, 1: horizontal edges
 __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restrict__ cus, const int32_t *__restrict__ map,
                                                       const uint8_t *__restrict__ bs_arr, int map_w, int map_h,
-                                                      DeblockParams prm, Pic3 rec) {
-  // thread -> 4x4 block; for DIR 1 consecutive threads still walk along x so loads coalesce
-  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cell >= map_w * map_h) return;
+                                                      DeblockParams prm, Pic3 rec, int cy_begin, int cy_end) {
+  // thread -> 4x4 block; for DIR 1 consecutive threads still walk along x so loads coalesce.
+  // [cy_begin, cy_end): band of 4-row groups this launch owns (CTB-row sharding); an edge row
+  // belongs to the band that holds its q side.
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x + cy_begin * map_w;
+  if (cell >= map_w * cy_end) return;
   const int cx = cell % map_w, cy = cell / map_w;
   const int bs0 = bs_arr[cell];
   if (bs0 == 0) return;
   const int step = DIR == 0 ? 1 : map_w;                 // next edge of the chain
-  const int pos = DIR == 0 ? cx : cy, lim = DIR == 0 ? map_w : map_h;
+  const int pos = DIR == 0 ? cx : cy, lim = DIR == 0 ? map_w : cy_end;
+  const int first = DIR == 0 ? 0 : cy_begin;             // chains restart at the top of a band
   const PlaneView ly = rec.p[0];
   const int across = DIR == 0 ? 1 : ly.pitch, along = DIR == 0 ? ly.pitch : 1;
 
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restri
   }
 
   // luma: only the head of a chain works
-  if (pos > 0 && bs_arr[cell - step] != 0) return;
+  if (pos > first && bs_arr[cell - step] != 0) return;
   int e = cell;
   for (int k = pos; k < lim; k++, e += step) {
     const int bs = bs_arr[e];
@@ -203,19 +206,29 @@ __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restri
 }
 
 cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
-                           int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h) {
+                           int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h, int pass_mask,
+                           int y_begin, int y_end) {
   if (n <= 0) return cudaSuccess;
   const int cells = map_w * map_h;
+  const int cy0 = y_begin >> 2, cy1 = y_end >> 2;
+  const int band_cells = map_w * (cy1 - cy0);
+  if (band_cells <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_map, 0xff, sizeof(int32_t) * cells, s);
   if (e != cudaSuccess) return e;
   DbRefPoc rp;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) rp.poc[l][i] = p.ref_poc[l][i];
-  g_launch_count += 4;
+  g_launch_count += 2;
   cu_map_kernel<<<n, 64, 0, s>>>(d_cus, n, d_map, map_w, map_h);
   edge_bs_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, map_w, map_h, p.pic_type, rp, d_bs_v, d_bs_h);
-  deblock_kernel<0><<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_v, map_w, map_h, p, rec);
-  deblock_kernel<1><<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_h, map_w, map_h, p, rec);
+  if (pass_mask & 1) {
+    g_launch_count++;
+    deblock_kernel<0><<<(band_cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_v, map_w, map_h, p, rec, cy0, cy1);
+  }
+  if (pass_mask & 2) {
+    g_launch_count++;
+    deblock_kernel<1><<<(band_cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_h, map_w, map_h, p, rec, cy0, cy1);
+  }
   return cudaGetLastError();
 }
 

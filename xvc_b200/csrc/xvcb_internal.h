@@ -40,6 +40,7 @@ struct xvcb_ctx_impl {
   int status = XVCB200_OK;
   std::string error;
   std::vector<DevPicture> slots;
+  size_t slot_stride = 0;            // bytes between consecutive slots (one arena)
 
   // CU array (device) and derived per-picture maps
   xvcb200_cu *d_cus = nullptr;
@@ -132,7 +133,8 @@ struct DeblockParams {
   long long ref_poc[2][5];
 };
 cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
-                           int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h);
+                           int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h, int pass_mask,
+                           int y_begin, int y_end);
 
 }  // namespace xvcb
 

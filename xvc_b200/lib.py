@@ -31,11 +31,11 @@ EXPORTS = [
     "xvcb200_fwd_transform", "xvcb200_fwd_transform_skip", "xvcb200_inv_transform", "xvcb200_inv_transform_skip",
     "xvcb200_qp_init", "xvcb200_quant_fast", "xvcb200_dequant",
     "xvcb200_ctx_create", "xvcb200_ctx_destroy", "xvcb200_ctx_set_stream", "xvcb200_stream", "xvcb200_sync",
-    "xvcb200_ctx_error_string", "xvcb200_get_geometry", "xvcb200_slot_ptr",
+    "xvcb200_ctx_error_string", "xvcb200_get_geometry", "xvcb200_slot_ptr", "xvcb200_slot_region",
     "xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff",
     "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_tq_reconstruct",
-    "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex",
+    "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
 ]
 
@@ -90,6 +90,7 @@ def load():
     L.xvcb200_sync.argtypes = [c_void_p]
     L.xvcb200_get_geometry.argtypes = [c_void_p, c_void_p]
     L.xvcb200_slot_ptr.argtypes = [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)]
+    L.xvcb200_slot_region.argtypes = [c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_u64)]
     for name in ("xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff"):
         getattr(L, name).argtypes = [c_void_p, c_int, c_void_p, c_void_p]
     L.xvcb200_download_padded.argtypes = [c_void_p, c_int, c_int, c_void_p]
@@ -103,6 +104,7 @@ def load():
     L.xvcb200_dequant_reconstruct.argtypes = [c_void_p] + [c_int] * 6
     L.xvcb200_deblock_picture.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.xvcb200_deblock_picture_ex.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p]
+    L.xvcb200_deblock_band.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 3
     L.xvcb200_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.xvcb200_set_profiling.argtypes = [c_void_p, c_int]
     L.xvcb200_get_stage_times.argtypes = [c_void_p, c_void_p]
@@ -279,6 +281,34 @@ class Context:
         self._ok(self.L.xvcb200_slot_ptr(self.h, slot, comp, ctypes.byref(p)))
         return p.value
 
+    def slot_region(self, slot):
+        """(device address, bytes) of the whole allocation of a slot; slots are contiguous."""
+        p, n = c_void_p(), c_u64()
+        self._ok(self.L.xvcb200_slot_region(self.h, slot, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def slots_tensor(self, first, count=1):
+        """torch uint8 CUDA tensor aliasing slots [first, first+count) (no copy)."""
+        import torch
+        base, nbytes = self.slot_region(first)
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (count * nbytes,), "typestr": "|u1", "data": (base, False), "version": 3}
+        return torch.as_tensor(_Mem(), device="cuda")
+
+    def plane_tensor(self, slot, comp):
+        """torch int16/uint16-as-int16 view [rows, pitch] of one plane incl. margins (no copy)."""
+        import torch
+        g = self.geom
+        rows = int(g["height"][comp] + 2 * g["margin_y"][comp])
+        pitch = int(g["pitch"][comp])
+        p00 = self.slot_ptr(slot, comp)
+        base = p00 - 2 * (int(g["margin_y"][comp]) * pitch + int(g["margin_x"][comp]))
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (rows, pitch), "typestr": "<i2", "data": (base, False), "version": 3}
+        return torch.as_tensor(_Mem(), device="cuda")
+
     @staticmethod
     def _strides(planes):
         return (c_ssize * 3)(*[p.strides[0] // p.itemsize for p in planes])
@@ -361,6 +391,14 @@ class Context:
             poc[l, i] = p
         self._ok(self.L.xvcb200_deblock_picture_ex(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
                                                    abi.ptr(poc)))
+
+    def deblock_band(self, rec_slot, pic_type, ref_poc, pass_mask, y_begin, y_end, beta_offset=0, tc_offset=0, table=1,
+                     off_u=0, off_v=0):
+        poc = np.zeros((2, 5), dtype=np.int64)
+        for (l, i), p in ref_poc.items():
+            poc[l, i] = p
+        self._ok(self.L.xvcb200_deblock_band(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
+                                             abi.ptr(poc), pass_mask, y_begin, y_end))
 
     STAGES = ("me_jobs", "tz_search", "subpel_search", "motion_compensate", "tq_reconstruct", "deblock", "pad_border")
 

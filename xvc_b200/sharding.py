@@ -1,0 +1,175 @@
+"""Multi-GPU decomposition of the hot path (one process per GPU, torch.distributed).
+
+xvc itself has exactly one parallel mechanism: picture-level worker threads, a picture being
+runnable once its reference pictures are finished (thread_encoder.cc:99-159).  Two
+decompositions follow from the data flow of the hot path:
+
+* frame_parallel_exchange(): every rank encodes its own picture; the only data-path exchange
+  is the finished, padded reconstruction that later pictures reference -- one NCCL all-gather
+  straight into reference slots (slots of a context are contiguous in memory).
+
+* BandedPictureEncoder: ONE picture split into bands of CTU rows.  ME / MC / T-Q-recon of a
+  band need nothing from other bands (reference pictures are replicated).  Deblocking needs
+  one exchange: vertical edges are row-local; the horizontal edge ON a band boundary belongs to
+  the lower band (its q side), reads 4 and writes 3 luma rows (2 / 1 chroma rows) of the upper
+  band, and must run after the upper band finished its own edges (order dependence of edges 4
+  rows apart, deblocking_filter.cc:56-77).  Protocol per boundary: upper -> lower 4 luma + 2x2
+  chroma rows after the upper band's passes; lower filters, returns 3 luma + 2x1 chroma rows.
+  CU metadata (cbf flags, chosen MVs) of all bands is all-gathered first because boundary
+  strength looks at both sides of an edge.
+
+The classes take an `engine` (the compute backend) so the host logic can be exercised on CPU
+with gloo in tests; GpuEngine below is the product engine (libxvc_b200 through lib.Context).
+"""
+import numpy as np
+
+from . import abi
+
+
+def band_rows(height, world):
+    """Contiguous bands of 64-row CTU rows, as even as possible: [(y0, y1), ...]."""
+    ctu_rows = (height + 63) // 64
+    out, start = [], 0
+    for r in range(world):
+        n = ctu_rows // world + (1 if r < ctu_rows % world else 0)
+        out.append((min(height, 64 * start), min(height, 64 * (start + n))))
+        start += n
+    return out
+
+
+def cus_in_band(cus, y0, y1):
+    return cus[(cus["y"] >= y0) & (cus["y"] < y1)]
+
+
+class GpuEngine:
+    """Compute backend on one B200: a lib.Context whose stream is torch's current stream."""
+
+    def __init__(self, ctx, slots, bitdepth, ref_poc):
+        import torch
+        self.torch = torch
+        self.ctx, self.slots, self.bitdepth, self.ref_poc = ctx, slots, bitdepth, ref_poc
+        # one non-default stream for the library's kernels, torch copies and the NCCL p2p ops
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        ctx.set_stream(self.stream.cuda_stream)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def encode_band(self, cus_band, prm):
+        p = prm.copy()
+        p["deblock"], p["pad"] = 0, 0
+        self.ctx.set_cus(cus_band)
+        self.ctx.encode_picture(p, want_results=False)
+        return self.ctx.get_cus()
+
+    def set_cus(self, cus):
+        self.ctx.set_cus(cus)
+
+    def deblock(self, pic_type, pass_mask, y0, y1):
+        self.ctx.deblock_band(self.slots["rec"], pic_type, self.ref_poc, pass_mask, y0, y1)
+
+    def _rows(self, comp, y0, y1):
+        g = self.ctx.geom
+        t = self.ctx.plane_tensor(self.slots["rec"], comp)
+        my, mx, w = int(g["margin_y"][comp]), int(g["margin_x"][comp]), int(g["width"][comp])
+        return t[my + y0:my + y1, mx:mx + w]
+
+    def get_rows(self, comp, y0, y1):
+        return self._rows(comp, y0, y1).contiguous()
+
+    def put_rows(self, comp, y0, rows):
+        self._rows(comp, y0, y0 + rows.shape[0]).copy_(rows)
+
+    def empty_rows(self, comp, n):
+        return self.torch.empty((n, int(self.ctx.geom["width"][comp])), dtype=self.torch.int16, device=self.device)
+
+    def to_comm(self, arr_u8):
+        return self.torch.from_numpy(arr_u8).to(self.device)
+
+    def from_comm(self, t):
+        return t.cpu().numpy()
+
+    def finish(self):
+        self.ctx.sync()
+
+
+class BandedPictureEncoder:
+    """One picture across `world` ranks by CTU-row bands (see module docstring)."""
+
+    def __init__(self, engine, dist, rank, world, height):
+        self.e, self.dist, self.rank, self.world = engine, dist, rank, world
+        self.bands = band_rows(height, world)
+
+    def _gather_cus(self, mine):
+        """all-gather of variable-length CU arrays -> the full CU list in picture order."""
+        if self.world == 1:
+            return mine
+        torch = __import__("torch")
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+        n_local = self.e.to_comm(np.array([len(mine)], dtype=np.int64).view(np.uint8))
+        all_n = [self.e.to_comm(np.zeros(8, dtype=np.uint8)) for _ in range(self.world)]
+        self.dist.all_gather(all_n, n_local)
+        lens = [int(self.e.from_comm(t).view(np.int64)[0]) for t in all_n]
+        cap = max(lens) * abi.cu_dtype.itemsize
+        buf = np.zeros(cap, dtype=np.uint8)
+        buf[:mine.nbytes] = mine.view(np.uint8)
+        outs = [self.e.to_comm(np.zeros(cap, dtype=np.uint8)) for _ in range(self.world)]
+        self.dist.all_gather(outs, self.e.to_comm(buf))
+        parts = [self.e.from_comm(t)[:n * abi.cu_dtype.itemsize].view(abi.cu_dtype) for t, n in zip(outs, lens)]
+        del counts
+        return np.concatenate(parts)
+
+    def encode(self, cus, prm):
+        """cus: the CU list of the WHOLE picture (every rank passes the same); returns the full
+        CU list after the decisions of all bands.  The rank's band of the reconstruction (plus
+        the rows its neighbours returned) is final when this returns."""
+        e, r = self.e, self.rank
+        y0, y1 = self.bands[r]
+        pic_type = int(prm["pic_type"][0])
+        mine = e.encode_band(cus_in_band(cus, y0, y1), prm) if y1 > y0 else cus[:0].copy()
+        full = self._gather_cus(mine)
+        if not int(prm["deblock"][0]):
+            e.finish()
+            return full
+        e.set_cus(full)
+        if y1 > y0:
+            e.deblock(pic_type, 1, y0, y1)                   # vertical edges: row-local
+        up = r - 1 if r > 0 and y1 > y0 and y0 > 0 else None
+        down = r + 1 if r + 1 < self.world and self.bands[r + 1][1] > self.bands[r + 1][0] and y1 > y0 else None
+        if up is not None:                                    # halo from the band above (its passes are done)
+            for comp, n in ((0, 4), (1, 2), (2, 2)):
+                t = e.empty_rows(comp, n)
+                self.dist.recv(t, src=up)
+                e.put_rows(comp, (y0 >> (1 if comp else 0)) - n, t)
+        if y1 > y0:
+            e.deblock(pic_type, 2, y0, y1)                   # horizontal edges incl. the one ON y0
+        if up is not None:                                    # rows the boundary edge modified go back
+            for comp, n in ((0, 3), (1, 1), (2, 1)):
+                yb = y0 >> (1 if comp else 0)
+                self.dist.send(e.get_rows(comp, yb - n, yb), dst=up)
+        if down is not None:
+            for comp, n in ((0, 4), (1, 2), (2, 2)):
+                yb = y1 >> (1 if comp else 0)
+                self.dist.send(e.get_rows(comp, yb - n, yb), dst=down)
+            for comp, n in ((0, 3), (1, 1), (2, 1)):
+                t = e.empty_rows(comp, n)
+                self.dist.recv(t, src=down)
+                e.put_rows(comp, (y1 >> (1 if comp else 0)) - n, t)
+        e.finish()
+        return full
+
+    def gather_band_rows(self, comp):
+        """Final reconstruction rows of this rank's band (for assembling the picture)."""
+        y0, y1 = self.bands[self.rank]
+        s = 1 if comp else 0
+        return self.e.get_rows(comp, y0 >> s, y1 >> s)
+
+
+def frame_parallel_exchange(ctx, dist, rank, world, first_slot):
+    """After every rank reconstructed (and padded) its own picture into slot first_slot+rank:
+    one in-place all-gather makes slots [first_slot, first_slot+world) hold all of them on every
+    rank, ready to be used as reference slots."""
+    if world == 1:
+        return
+    whole = ctx.slots_tensor(first_slot, world)
+    mine = ctx.slots_tensor(first_slot + rank, 1)
+    dist.all_gather_into_tensor(whole, mine)
