@@ -32,13 +32,13 @@ class OracleEngine:
         self.o.deblock_band(self.rec, self.bd, self.cus, pic_type, self.ref_poc, pass_mask, y0, y1)
 
     def get_rows(self, comp, y0, y1):
-        return torch.from_numpy(self.rec.plane(comp)[y0:y1].astype(np.int16, copy=True))
+        return torch.from_numpy(np.ascontiguousarray(self.rec.plane(comp)[y0:y1]).view(np.uint8).copy())
 
     def put_rows(self, comp, y0, rows):
-        self.rec.plane(comp)[y0:y0 + rows.shape[0]] = rows.numpy().astype(np.uint16)
+        self.rec.plane(comp)[y0:y0 + rows.shape[0]] = rows.numpy().view(np.uint16)
 
     def empty_rows(self, comp, n):
-        return torch.empty((n, self.rec.width[comp]), dtype=torch.int16)
+        return torch.empty((n, 2 * self.rec.width[comp]), dtype=torch.uint8)
 
     def to_comm(self, arr_u8):
         return torch.from_numpy(np.ascontiguousarray(arr_u8).copy())

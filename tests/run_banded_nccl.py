@@ -33,7 +33,7 @@ def main():
     eng = sharding.GpuEngine(ctx, dict(rec=4), BD, {(0, 0): 0, (1, 0): 16})
     enc = sharding.BandedPictureEncoder(eng, dist, rank, world, H)
     full = enc.encode(cus, prm)
-    bands = [enc.gather_band_rows(c).cpu().numpy().astype(np.uint16) for c in range(3)]
+    bands = [enc.gather_band_rows(c).cpu().numpy().view(np.uint16) for c in range(3)]
     # single-GPU truth on every rank (second context)
     ctx2 = lib.Context(W, H, BD, 6, device=local)
     ctx2.upload(0, cur)

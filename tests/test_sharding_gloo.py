@@ -35,7 +35,7 @@ def _worker(rank, world, port, out_dir):
     full = enc.encode(cus, prm)
     y0, y1 = enc.bands[rank]
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), cus=full.view(np.uint8), y0=y0, y1=y1,
-             **{"p%d" % c: enc.gather_band_rows(c).numpy() for c in range(3)})
+             **{"p%d" % c: enc.gather_band_rows(c).numpy().view(np.uint16) for c in range(3)})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,7 +60,7 @@ def test_banded_encode_matches_single_process(tmp_path, world):
         y0, y1 = int(z["y0"]), int(z["y1"])
         for c in range(3):
             s = 1 if c else 0
-            planes[c][y0 >> s:y1 >> s] = z["p%d" % c].astype(np.uint16)
+            planes[c][y0 >> s:y1 >> s] = z["p%d" % c]
         got = z["cus"].view(cus.dtype)
         for f in ("flags", "ref_idx", "mv"):
             assert np.array_equal(got[f], cus_ref[f]), (r, f)

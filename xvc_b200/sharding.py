@@ -73,14 +73,15 @@ class GpuEngine:
         my, mx, w = int(g["margin_y"][comp]), int(g["margin_x"][comp]), int(g["width"][comp])
         return t[my + y0:my + y1, mx:mx + w]
 
+    # rows travel as bytes: NCCL has no 16-bit integer type
     def get_rows(self, comp, y0, y1):
-        return self._rows(comp, y0, y1).contiguous()
+        return self._rows(comp, y0, y1).contiguous().view(self.torch.uint8)
 
     def put_rows(self, comp, y0, rows):
-        self._rows(comp, y0, y0 + rows.shape[0]).copy_(rows)
+        self._rows(comp, y0, y0 + rows.shape[0]).copy_(rows.view(self.torch.int16))
 
     def empty_rows(self, comp, n):
-        return self.torch.empty((n, int(self.ctx.geom["width"][comp])), dtype=self.torch.int16, device=self.device)
+        return self.torch.empty((n, 2 * int(self.ctx.geom["width"][comp])), dtype=self.torch.uint8, device=self.device)
 
     def to_comm(self, arr_u8):
         return self.torch.from_numpy(arr_u8).to(self.device)
