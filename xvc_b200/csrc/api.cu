@@ -1,8 +1,10 @@
 // C-ABI layer of libxvc_b200.so (include/xvc_b200.h): context and picture-slot management,
 // host<->device staging for the table-shaped entry points, and the per-picture pipeline.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 #include "xvcb_internal.h"
 
@@ -348,6 +350,13 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int class_offset[7][7];
   xvcb200_me_job *d_jobs = nullptr; xvcb200_me_result *d_me = nullptr; xvcb200_tu_result *d_tu = nullptr;
   int jobs_cap = 0, me_cap = 0, tu_res_cap = 0;
+  // TZ search job groups (jobs sharing a reference picture and a CTU share one staged window)
+  std::vector<xvcb200_cu> h_cus;              // host copy of the CU array (set_cus)
+  int *d_job_index = nullptr; int job_index_cap = 0;
+  int *d_groups = nullptr; int groups_cap = 0;       // pairs {first, count}
+  uint8_t *d_tz_states = nullptr; int tz_states_cap = 0;
+  int *d_counter = nullptr;
+  int pipeline_groups_nl = 0, pipeline_n_groups = 0;   // cached grouping of the picture pipeline's job list
   // optional per-stage timing of xvcb200_encode_picture (CUDA events on the context stream)
   bool profile = false;
   cudaEvent_t ev[9] = {nullptr};
@@ -444,6 +453,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->d_cus); cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
   cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -547,12 +557,14 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   }
   if (!ensure(c, &c->d_cus, &c->cap_cus, n) || !ensure(c, &c->ex.d_tu_list, &c->ex.tu_cap, 3 * n)) return c->status;
   c->n_cus = n;
-  if (n == 0) return XVCB200_OK;
+  if (n == 0) { c->ex.h_cus.clear(); c->ex.pipeline_groups_nl = 0; return XVCB200_OK; }
   int *list = static_cast<int *>(c->pinned(sizeof(int) * 3 * (size_t)n + sizeof(xvcb200_cu) * (size_t)n));
   if (!list) return c->status;
   xvcb200_cu *hc = reinterpret_cast<xvcb200_cu *>(list + 3 * (size_t)n);
   cudaStreamSynchronize(c->stream);          // pinned buffer may still feed an earlier copy
   memcpy(hc, cus, sizeof(xvcb200_cu) * (size_t)n);
+  c->ex.h_cus.assign(cus, cus + n);
+  c->ex.pipeline_groups_nl = 0;
   auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
   memset(c->ex.class_count, 0, sizeof(c->ex.class_count));
   for (int i = 0; i < n; i++)
@@ -575,6 +587,40 @@ int xvcb200_get_cus(xvcb200_ctx *c, xvcb200_cu *cus, int n) {
   return xvcb200_sync(c);
 }
 
+}  // extern "C"
+
+namespace xvcb { size_t tz_state_bytes(); }
+
+// Groups search jobs by (reference slot, CTU of the CU) and uploads the index + group arrays.
+// key(i) must be cheap; jobs of one group end up adjacent in job_index, in their original order.
+template <class KeyOf, class JobOf>
+static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of) {
+  std::vector<std::pair<long long, int>> order((size_t)n_jobs);
+  for (int i = 0; i < n_jobs; i++) order[(size_t)i] = std::make_pair(key_of(i), job_of(i));
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<long long, int> &a, const std::pair<long long, int> &b) { return a.first < b.first; });
+  std::vector<int> index((size_t)n_jobs), groups;
+  for (int i = 0; i < n_jobs; i++) {
+    index[(size_t)i] = order[(size_t)i].second;
+    if (i == 0 || order[(size_t)i].first != order[(size_t)i - 1].first) { groups.push_back(i); groups.push_back(0); }
+    groups.back()++;
+  }
+  const int n_groups = (int)groups.size() / 2;
+  if (!ensure(c, &c->ex.d_job_index, &c->ex.job_index_cap, n_jobs) || !ensure(c, &c->ex.d_groups, &c->ex.groups_cap, 2 * n_groups))
+    return -1;
+  int st_cap_elems = c->ex.tz_states_cap;
+  if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return -1;
+  c->ex.tz_states_cap = st_cap_elems;
+  if (!c->ex.d_counter && !c->check(cudaMalloc(&c->ex.d_counter, sizeof(int)), "cudaMalloc(counter)")) return -1;
+  // synchronous copies: the vectors die at return
+  if (!c->check(cudaMemcpyAsync(c->ex.d_job_index, index.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz index") ||
+      !c->check(cudaMemcpyAsync(c->ex.d_groups, groups.data(), sizeof(int) * groups.size(), cudaMemcpyHostToDevice, c->stream), "tz groups") ||
+      !c->check(cudaStreamSynchronize(c->stream), "tz groups sync"))
+    return -1;
+  return n_groups;
+}
+
+extern "C" {
+
 static uint32_t lambda_me_of(double lambda_sqrt) { return (uint32_t)std::floor(65536.0 * lambda_sqrt); }
 
 int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *jobs, int n, double lambda_sqrt,
@@ -588,8 +634,19 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
   if (n == 0) return XVCB200_OK;
   if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
   c->check(cudaMemcpyAsync(c->ex.d_jobs, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "me jobs");
+  const int ctus_x = (c->width + 63) >> 6;
+  const int n_groups = upload_tz_groups(
+      c, n,
+      [&](int i) {
+        const xvcb200_cu &u = c->ex.h_cus[(size_t)jobs[i].cu];
+        return ((long long)jobs[i].ref_slot << 40) | ((long long)jobs[i].search_range << 28) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
+      },
+      [](int i) { return i; });
+  if (n_groups < 0) return c->status;
+  c->ex.pipeline_groups_nl = 0;
   c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
-                            c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "tz_search");
+                            c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
+                            n_groups, c->ex.d_tz_states, c->ex.d_counter), "tz_search");
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
                                 c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");
   c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "me results");
@@ -732,13 +789,27 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     return c->status;
   const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
   const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
+  if (c->ex.pipeline_groups_nl != nl) {      // job (cu, list) = cu * nl + list, grouped by (list, CTU); cached until set_cus
+    const int ctus_x = (c->width + 63) >> 6;
+    const int ng = upload_tz_groups(
+        c, n * nl,
+        [&](int i) {
+          const xvcb200_cu &u = c->ex.h_cus[(size_t)(i / nl)];
+          return ((long long)(i % nl) << 40) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
+        },
+        [](int i) { return i; });
+    if (ng < 0) return c->status;
+    c->ex.pipeline_groups_nl = nl;
+    c->ex.pipeline_n_groups = ng;
+  }
   int stage = 0;
   auto mark = [&]() { if (c->ex.profile) cudaEventRecord(c->ex.ev[stage], c->stream); stage++; };
   mark();   // 0: start
   c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
   mark();   // 1: jobs built
   c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                            c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "tz_search");
+                            c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
+                            c->ex.pipeline_n_groups, c->ex.d_tz_states, c->ex.d_counter), "tz_search");
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
                                 c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");

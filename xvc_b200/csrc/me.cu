@@ -41,11 +41,27 @@ __device__ __forceinline__ uint32_t ld_pair(const Sample *p) {
 // Sum of |a - b| over two packed 16-bit lanes: max - min per lane, native VIMNMX.U16x2.
 __device__ __forceinline__ uint32_t absdiff2(uint32_t a, uint32_t b) { return __vmaxu2(a, b) - __vminu2(a, b); }
 
+// Where reference samples come from: the padded reference plane in global memory and, when the
+// search windows of a job group fit, a copy of their bounding box staged in shared memory
+// (rows of `spw` 32-bit words, two samples per word; spw is odd so that lanes reading rows
+// 5*k apart -- the raster grid -- fall into distinct banks).
+struct RefSrc {
+  const Sample *plane; int gpitch;      // sample (0,0) of the reference luma plane
+  const uint32_t *sm; int spw;          // staged box, null when not staged
+  int rx0, ry0, rx1, ry1;               // staged box in picture coordinates, [rx0,rx1) x [ry0,ry1), rx0 even
+};
+
+__device__ __forceinline__ bool block_staged(const RefSrc &src, const MeGeom &g, int cx, int cy) {
+  const int X = g.x + cx, Y = g.y + cy;
+  return src.sm != nullptr && X >= src.rx0 && X + g.w <= src.rx1 && Y >= src.ry0 && Y + g.h <= src.ry1;
+}
+
 // Lane j holds candidate j (cx, cy, valid) of a list of K <= 32 candidates; returns in lane j
 // the metric value (SampleMetric::Compare kSad / kSadFast incl. the bit-depth shift) of candidate j.
+// G lanes share one candidate (G = min(32, pairs)), 32/G candidates per pass.
 template <int P>
-__device__ __forceinline__ uint32_t eval_candidates(const MeGeom &g, const uint32_t (&o)[P], const Sample *ref0,
-                                                    int pitch, int cx, int cy, bool valid, int K, int lane) {
+__device__ __forceinline__ uint32_t eval_candidates(const MeGeom &g, const uint32_t (&o)[P], const RefSrc &src,
+                                                    int cx, int cy, bool valid, int K, int lane) {
   const int NG = 32 >> g.lG;                 // candidates per pass
   const int gl = lane & (g.G - 1), grp = lane >> g.lG;
   uint32_t mine = 0xffffffffu;
@@ -56,17 +72,34 @@ __device__ __forceinline__ uint32_t eval_candidates(const MeGeom &g, const uint3
     const bool sv = __shfl_sync(XVCB_FULL, (int)valid, c & 31) && c < K;
     uint32_t acc = 0;
     if (sv) {
-      const Sample *r = ref0 + sy * pitch + sx;
+      if (block_staged(src, g, sx, sy)) {
+        const int ox = g.x + sx - src.rx0, oy = g.y + sy - src.ry0;
 #pragma unroll
-      for (int k0 = 0; k0 < P; k0 += 8) {
-        uint32_t packed = 0;   // up to 8 x 4095 per 16-bit lane: no carry between the lanes
+        for (int k0 = 0; k0 < P; k0 += 8) {
+          uint32_t packed = 0;   // up to 8 x 4095 per 16-bit lane: no carry between the lanes
 #pragma unroll
-        for (int k = k0; k < (k0 + 8 < P ? k0 + 8 : P); k++) {
-          const int q = gl + (k << g.lG);
-          const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
-          packed += absdiff2(o[k], ld_pair(r + row * g.rstep * pitch + col * 2));
+          for (int k = k0; k < (k0 + 8 < P ? k0 + 8 : P); k++) {
+            const int q = gl + (k << g.lG);
+            const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
+            const int sxo = ox + col * 2;
+            const uint32_t *wp = src.sm + (oy + row * g.rstep) * src.spw + (sxo >> 1);
+            packed += absdiff2(o[k], __funnelshift_r(wp[0], wp[1], (sxo & 1) << 4));
+          }
+          acc += (packed & 0xffff) + (packed >> 16);
         }
-        acc += (packed & 0xffff) + (packed >> 16);
+      } else {
+        const Sample *r = src.plane + (g.y + sy) * src.gpitch + g.x + sx;
+#pragma unroll
+        for (int k0 = 0; k0 < P; k0 += 8) {
+          uint32_t packed = 0;
+#pragma unroll
+          for (int k = k0; k < (k0 + 8 < P ? k0 + 8 : P); k++) {
+            const int q = gl + (k << g.lG);
+            const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
+            packed += absdiff2(o[k], ld_pair(r + row * g.rstep * src.gpitch + col * 2));
+          }
+          acc += (packed & 0xffff) + (packed >> 16);
+        }
       }
     }
 #pragma unroll
@@ -115,8 +148,11 @@ __device__ __forceinline__ bool inside(int x, int y, int pos, const int lo[2], c
 __device__ __forceinline__ int diamond_point(int r, int lane, int &dx, int &dy, int &pos, int &rep) {
   dx = dy = pos = 0; rep = r;
   if (r == 1) {
-    const int px[4] = {0, -1, 1, 0}, py[4] = {-1, 0, 0, 1}, pp[4] = {-3, -1, 1, 3};
-    if (lane < 4) { dx = px[lane]; dy = py[lane]; pos = pp[lane]; }
+    if (lane < 4) {
+      dx = lane == 1 ? -1 : (lane == 2 ? 1 : 0);
+      dy = lane == 0 ? -1 : (lane == 3 ? 1 : 0);
+      pos = lane == 0 ? -3 : (lane == 1 ? -1 : (lane == 2 ? 1 : 3));
+    }
     return 4;
   }
   if (r <= 8) {
@@ -156,62 +192,82 @@ __device__ __forceinline__ int diamond_point(int r, int lane, int &dx, int &dy, 
 // Lane -> point of FullpelNeighborPointSearch (inter_tz_search.cc:212-259).
 __device__ __forceinline__ int two_point(int last_pos, int lane, int &dx, int &dy, int &pos) {
   // {dx0,dy0,pos0, dx1,dy1,pos1} per last_position -4..4
-  int t[6] = {0, 0, 0, 0, 0, 0};
+  int t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
   switch (last_pos) {
-    case -4: t[0] = -1; t[2] = -1; t[4] = -1; t[5] = -3; break;
-    case -3: t[0] = -1; t[1] = -1; t[2] = -4; t[3] = 1; t[4] = -1; t[5] = -2; break;
-    case -2: t[1] = -1; t[2] = -3; t[3] = 1; t[5] = 1; break;
-    case -1: t[0] = -1; t[1] = 1; t[2] = 2; t[3] = -1; t[4] = -1; t[5] = -4; break;
-    case 1: t[0] = 1; t[1] = -1; t[2] = -2; t[3] = 1; t[4] = 1; t[5] = 4; break;
-    case 2: t[0] = -1; t[2] = -1; t[4] = 1; t[5] = 3; break;
-    case 3: t[0] = -1; t[1] = 1; t[2] = 2; t[3] = 1; t[4] = 1; t[5] = 4; break;
-    case 4: t[0] = 1; t[2] = 1; t[4] = 1; t[5] = 3; break;
+    case -4: t0 = -1; t2 = -1; t4 = -1; t5 = -3; break;
+    case -3: t0 = -1; t1 = -1; t2 = -4; t3 = 1; t4 = -1; t5 = -2; break;
+    case -2: t1 = -1; t2 = -3; t3 = 1; t5 = 1; break;
+    case -1: t0 = -1; t1 = 1; t2 = 2; t3 = -1; t4 = -1; t5 = -4; break;
+    case 1: t0 = 1; t1 = -1; t2 = -2; t3 = 1; t4 = 1; t5 = 4; break;
+    case 2: t0 = -1; t2 = -1; t4 = 1; t5 = 3; break;
+    case 3: t0 = -1; t1 = 1; t2 = 2; t3 = 1; t4 = 1; t5 = 4; break;
+    case 4: t0 = 1; t2 = 1; t4 = 1; t5 = 3; break;
     default: return 0;
   }
-  const int s = lane == 1 ? 3 : 0;
-  dx = t[s]; dy = t[s + 1]; pos = t[s + 2];
+  dx = lane == 1 ? t3 : t0; dy = lane == 1 ? t4 : t1; pos = lane == 1 ? t5 : t2;
   return 2;
 }
 
+// State of one search between its phases (kept in global scratch, L2 resident).
+struct TzJobState {
+  int bx, by; uint32_t cost; int last_pos, last_range;
+  int lo[2], hi[2], slo[2], shi[2];
+  uint32_t evals;
+  int need_raster;
+};
+
 template <int P>
-__device__ void tz_search_warp(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job, PlaneView orig,
-                               PlaneView ref, int lane, xvcb200_me_result *out) {
-  // original block -> registers (packed pairs), distributed like the reference reads
-  uint32_t o[P];
-  {
-    const int gl = lane & (g.G - 1);
-    const Sample *ob = orig.base + g.y * orig.pitch + g.x;
+__device__ __forceinline__ void load_orig_regs(const MeGeom &g, PlaneView orig, int lane, uint32_t (&o)[P]) {
+  const int gl = lane & (g.G - 1);
+  const Sample *ob = orig.base + g.y * orig.pitch + g.x;
 #pragma unroll
-    for (int k = 0; k < P; k++) {
-      const int q = gl + (k << g.lG);
-      const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
-      o[k] = ld_pair(ob + row * g.rstep * orig.pitch + col * 2);
-    }
+  for (int k = 0; k < P; k++) {
+    const int q = gl + (k << g.lG);
+    const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
+    o[k] = ld_pair(ob + row * g.rstep * orig.pitch + col * 2);
   }
-  const Sample *ref0 = ref.base + g.y * ref.pitch + g.x;
-  const int pitch = ref.pitch;
+}
+
+template <int P>
+__device__ __forceinline__ void neighbour_points(const MeGeom &g, const uint32_t (&o)[P], const RefSrc &src, TzBest &b,
+                                                 const int lo[2], const int hi[2], uint32_t &evals, int lane) {
+  if (b.last_range != 1) return;
+  b.last_range = 0;
+  int dx = 0, dy = 0, pos = 0;
+  const int K = two_point(b.last_pos, lane, dx, dy, pos);
+  if (K == 0) return;
+  const int cx = b.x + dx, cy = b.y + dy;
+  const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
+  evals += __popc(__ballot_sync(XVCB_FULL, valid));
+  const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, K, lane);
+  apply_candidates(b, d, cx, cy, pos, 1, g, lane);
+}
+
+// Phase 1 of TzSearch::Search: start points, first diamond pass, 2-point refinement
+// (inter_tz_search.cc:102-144).
+template <int P>
+__device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job, int pic_w, int pic_h,
+                          const uint32_t (&o)[P], const RefSrc &src, int lane, TzJobState &st) {
   const int range = job.search_range;
   int lo[2], hi[2], slo[2], shi[2];
-  min_max_mv(g.x, g.y, ref.width, ref.height, g.mvpx, g.mvpy, range, lo, hi);
+  min_max_mv(g.x, g.y, pic_w, pic_h, g.mvpx, g.mvpy, range, lo, hi);
   slo[0] = lo[0]; slo[1] = lo[1]; shi[0] = hi[0]; shi[1] = hi[1];
   TzBest b;
   b.x = 0; b.y = 0; b.cost = 0xffffffffu; b.last_pos = 0; b.last_range = 0;
   uint32_t evals = 0;
-
-  // start points: predictor, zero, previous search result (inter_tz_search.cc:102-131)
-  {
+  {   // predictor, zero, previous search result (:102-131)
     int px = g.mvpx, py = g.mvpy;
-    clip_mv(g.x, g.y, ref.width, ref.height, px, py);
+    clip_mv(g.x, g.y, pic_w, pic_h, px, py);
     px >>= 4; py >>= 4;
     int qx = job.prev[0] * 16, qy = job.prev[1] * 16;
-    clip_mv(g.x, g.y, ref.width, ref.height, qx, qy);
+    clip_mv(g.x, g.y, pic_w, pic_h, qx, qy);
     qx >>= 4; qy >>= 4;
     const bool use_zero = (px != 0 || py != 0);
     const bool use_prev = cu.depth != 0;
     const int cx = lane == 0 ? px : (lane == 1 ? 0 : qx);
     const int cy = lane == 0 ? py : (lane == 1 ? 0 : qy);
     const bool valid = lane == 0 || (lane == 1 && use_zero) || (lane == 2 && use_prev);
-    const uint32_t d = eval_candidates<P>(g, o, ref0, pitch, cx, cy, valid, 3, lane);
+    const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, 3, lane);
     evals += 1 + use_zero + use_prev;
     uint32_t cost = 0xffffffffu;
     if (d != 0xffffffffu) cost = d + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
@@ -222,13 +278,11 @@ __device__ void tz_search_warp(const MeGeom &g, const xvcb200_cu &cu, const xvcb
     if (use_zero && c1 < b.cost) { b.cost = c1; b.x = 0; b.y = 0; moved = true; }
     if (use_prev) {
       if (c2 < b.cost) { b.cost = c2; b.x = qx; b.y = qy; moved = true; }
-      if (moved) min_max_mv(g.x, g.y, ref.width, ref.height, b.x * 16, b.y * 16, range, slo, shi);
+      if (moved) min_max_mv(g.x, g.y, pic_w, pic_h, b.x * 16, b.y * 16, range, slo, shi);
     }
     b.last_range = 0;
   }
-
-  // first diamond pass around the start point, stops after three rounds without a hit (:133-143)
-  {
+  {   // first diamond pass around the start point, stops after three rounds without a hit (:133-143)
     const int bx = b.x, by = b.y;
     int misses = 0;
     for (int r = 1; r <= range; r *= 2) {
@@ -237,46 +291,48 @@ __device__ void tz_search_warp(const MeGeom &g, const xvcb200_cu &cu, const xvcb
       const int cx = bx + dx, cy = by + dy;
       const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
       evals += __popc(__ballot_sync(XVCB_FULL, valid));
-      const uint32_t d = eval_candidates<P>(g, o, ref0, pitch, cx, cy, valid, K, lane);
+      const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, K, lane);
       if (apply_candidates(b, d, cx, cy, pos, rep, g, lane)) misses = 0;
       else if (++misses >= 3) break;
     }
   }
-  auto neighbours = [&]() {
-    if (b.last_range != 1) return;
-    b.last_range = 0;
-    int dx = 0, dy = 0, pos = 0;
-    const int K = two_point(b.last_pos, lane, dx, dy, pos);
-    if (K == 0) return;
-    const int cx = b.x + dx, cy = b.y + dy;
-    const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
-    evals += __popc(__ballot_sync(XVCB_FULL, valid));
-    const uint32_t d = eval_candidates<P>(g, o, ref0, pitch, cx, cy, valid, K, lane);
-    apply_candidates(b, d, cx, cy, pos, 1, g, lane);
-  };
-  neighbours();
+  neighbour_points<P>(g, o, src, b, lo, hi, evals, lane);
+  st.bx = b.x; st.by = b.y; st.cost = b.cost; st.last_pos = b.last_pos; st.last_range = b.last_range;
+  st.lo[0] = lo[0]; st.lo[1] = lo[1]; st.hi[0] = hi[0]; st.hi[1] = hi[1];
+  st.slo[0] = slo[0]; st.slo[1] = slo[1]; st.shi[0] = shi[0]; st.shi[1] = shi[1];
+  st.evals = evals;
+  st.need_raster = b.last_range > 5;       // kFullSearchGranularity (:91, :146)
+}
 
-  // raster scan of the window on a 5-sample grid (:145-155)
-  if (b.last_range > 5) {
-    b.last_range = 5;
-    const int nx = (shi[0] - slo[0]) / 5 + 1, ny = (shi[1] - slo[1]) / 5 + 1;
-    if (shi[0] >= slo[0] && shi[1] >= slo[1]) {
-      const int total = nx * ny;
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
-        const int j = t / nx, i = t - j * nx;
-        const int cx = slo[0] + 5 * i, cy = slo[1] + 5 * j;
-        const bool valid = t < total;
-        const int K = min(32, total - t0);
-        const uint32_t d = eval_candidates<P>(g, o, ref0, pitch, cx, cy, valid, K, lane);
-        const int keep_pos = b.last_pos, keep_range = b.last_range;   // CheckCostBest alone leaves these untouched
-        apply_candidates(b, d, cx, cy, keep_pos, keep_range, g, lane);
-      }
-      evals += total;
+// Raster scan of the window on a 5-sample grid by ONE warp (:145-155); used when the window
+// is not staged in shared memory.
+template <int P>
+__device__ void tz_raster_warp(const MeGeom &g, const uint32_t (&o)[P], const RefSrc &src, int lane, TzJobState &st) {
+  TzBest b;
+  b.x = st.bx; b.y = st.by; b.cost = st.cost; b.last_pos = st.last_pos; b.last_range = 5;
+  const int nx = (st.shi[0] - st.slo[0]) / 5 + 1, ny = (st.shi[1] - st.slo[1]) / 5 + 1;
+  if (st.shi[0] >= st.slo[0] && st.shi[1] >= st.slo[1]) {
+    const int total = nx * ny;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int t = t0 + lane;
+      const int j = t / nx, i = t - j * nx;
+      const int cx = st.slo[0] + 5 * i, cy = st.slo[1] + 5 * j;
+      const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, t < total, min(32, total - t0), lane);
+      apply_candidates(b, d, cx, cy, b.last_pos, b.last_range, g, lane);   // CheckCostBest alone keeps last_*
     }
+    st.evals += total;
   }
+  st.bx = b.x; st.by = b.y; st.cost = b.cost; st.last_range = 5;
+  st.need_raster = 0;
+}
 
-  // re-centre until the centre wins (:157-168)
+// Phase 3: re-centre until the centre wins (:157-168), then the result.
+template <int P>
+__device__ void tz_phase3(const MeGeom &g, int range, const uint32_t (&o)[P], const RefSrc &src, int lane,
+                          const TzJobState &st, xvcb200_me_result *out) {
+  TzBest b;
+  b.x = st.bx; b.y = st.by; b.cost = st.cost; b.last_pos = st.last_pos; b.last_range = st.last_range;
+  uint32_t evals = st.evals;
   while (b.last_range > 0) {
     const int bx = b.x, by = b.y;
     b.last_range = 0;
@@ -284,12 +340,12 @@ __device__ void tz_search_warp(const MeGeom &g, const xvcb200_cu &cu, const xvcb
       int dx, dy, pos, rep;
       const int K = diamond_point(r, lane, dx, dy, pos, rep);
       const int cx = bx + dx, cy = by + dy;
-      const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
+      const bool valid = lane < K && inside(cx, cy, pos, st.lo, st.hi);
       evals += __popc(__ballot_sync(XVCB_FULL, valid));
-      const uint32_t d = eval_candidates<P>(g, o, ref0, pitch, cx, cy, valid, K, lane);
+      const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, K, lane);
       apply_candidates(b, d, cx, cy, pos, rep, g, lane);
     }
-    neighbours();
+    neighbour_points<P>(g, o, src, b, st.lo, st.hi, evals, lane);
   }
   if (lane == 0) {
     out->mv_fullpel[0] = b.x; out->mv_fullpel[1] = b.y;
@@ -315,26 +371,256 @@ __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, ui
   return g;
 }
 
-__global__ void __launch_bounds__(128) tz_search_kernel(const xvcb200_cu *__restrict__ cus,
-                                                        const xvcb200_me_job *__restrict__ jobs, int n, int bitdepth,
-                                                        uint32_t lambda, PlaneView orig,
-                                                        const PlaneView *__restrict__ ref_planes,
-                                                        xvcb200_me_result *__restrict__ res) {
-  const int lane = threadIdx.x & 31;
-  const int ji = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (ji >= n) return;
-  const xvcb200_me_job job = jobs[ji];
-  const xvcb200_cu cu = cus[job.cu];
-  const PlaneView ref = ref_planes[job.ref_slot];
-  const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+// which: 1 = phase 1 (+ raster and phase 3 when `through`), 3 = phase 3
+template <int P>
+__device__ void tz_job_phase(int which, bool through, const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job,
+                             PlaneView orig, int pic_w, int pic_h, const RefSrc &src, int lane, TzJobState *st_g,
+                             xvcb200_me_result *out) {
+  uint32_t o[P];
+  load_orig_regs<P>(g, orig, lane, o);
+  TzJobState st;
+  if (which == 1) {
+    tz_phase1<P>(g, cu, job, pic_w, pic_h, o, src, lane, st);
+    if (through) {
+      if (st.need_raster) tz_raster_warp<P>(g, o, src, lane, st);
+      tz_phase3<P>(g, job.search_range, o, src, lane, st, out);
+    } else if (lane == 0) {
+      *st_g = st;
+    }
+  } else {
+    st = *st_g;
+    tz_phase3<P>(g, job.search_range, o, src, lane, st, out);
+  }
+}
+
+__device__ void tz_job_dispatch(int which, bool through, const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job,
+                                PlaneView orig, int pic_w, int pic_h, const RefSrc &src, int lane, TzJobState *st_g,
+                                xvcb200_me_result *out) {
   const int pairs = g.rows << g.lpw;
   switch (pairs >> 5) {
-    case 0: case 1: tz_search_warp<1>(g, cu, job, orig, ref, lane, &res[ji]); break;
-    case 2: tz_search_warp<2>(g, cu, job, orig, ref, lane, &res[ji]); break;
-    case 4: tz_search_warp<4>(g, cu, job, orig, ref, lane, &res[ji]); break;
-    case 8: tz_search_warp<8>(g, cu, job, orig, ref, lane, &res[ji]); break;
-    case 16: tz_search_warp<16>(g, cu, job, orig, ref, lane, &res[ji]); break;
-    default: tz_search_warp<32>(g, cu, job, orig, ref, lane, &res[ji]); break;
+    case 0: case 1: tz_job_phase<1>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
+    case 2: tz_job_phase<2>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
+    case 4: tz_job_phase<4>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
+    case 8: tz_job_phase<8>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
+    case 16: tz_job_phase<16>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
+    default: tz_job_phase<32>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
+  }
+}
+
+// One raster candidate column for 32 candidate rows (lane = row): sum of |orig - ref| over the
+// block rows the metric visits.  `rp` = this lane's first reference word, `so` = the original
+// block as packed pairs in shared memory (broadcast reads), shift = 0 / 16 for even / odd x.
+template <int LPW>
+__device__ __forceinline__ uint32_t raster_sad(const uint32_t *rp, int row_words, const uint32_t *so, int rows,
+                                               int shift) {
+  constexpr int PW = 1 << LPW;
+  uint32_t total = 0;
+  for (int r = 0; r < rows; r++) {
+    uint32_t prev = rp[0];
+#pragma unroll
+    for (int c0 = 0; c0 < PW; c0 += 16) {
+      uint32_t acc = 0;       // <= 16 x 4095 per 16-bit lane
+#pragma unroll
+      for (int c = c0; c < (c0 + 16 < PW ? c0 + 16 : PW); c++) {
+        const uint32_t nxt = rp[c + 1];
+        acc += absdiff2(so[c], __funnelshift_r(prev, nxt, shift));
+        prev = nxt;
+      }
+      total += (acc & 0xffff) + (acc >> 16);
+    }
+    rp += row_words;
+    so += PW;
+  }
+  return total;
+}
+
+constexpr int kTzThreads = 256;
+constexpr int kTzWarps = kTzThreads / 32;
+
+struct TzGroup { int first, count; };    // run of entries in job_index: jobs sharing a reference picture and a CTU
+
+// TzSearch::Search for job groups.  One persistent CTA per SM; per group: bounding box of the
+// search windows -> shared memory, phase 1 per warp, raster scans CTA-wide (one candidate per
+// lane, no reductions in the inner loop), phase 3 per warp.
+__global__ void __launch_bounds__(kTzThreads, 1)
+tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
+                 const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
+                 int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
+                 const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res,
+                 TzJobState *__restrict__ states, int region_budget_words) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t *s_orig = smem;                       // 1024 words: original block of the job being raster-scanned
+  uint32_t *s_region = smem + 1024;
+  __shared__ int s_group, s_next, s_box[4];
+  __shared__ unsigned long long s_red[kTzWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (;;) {
+    __syncthreads();                             // previous group is completely done with shared memory
+    if (tid == 0) {
+      s_group = atomicAdd(counter, 1);
+      s_next = 0;
+      s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
+    }
+    __syncthreads();
+    const int grp = s_group;
+    if (grp >= n_groups) break;
+    const TzGroup G = groups[grp];
+    const PlaneView ref = ref_planes[jobs[job_index[G.first]].ref_slot];
+
+    // bounding box of the jobs' search windows (block extent included)
+    for (int k = tid; k < G.count; k += kTzThreads) {
+      const xvcb200_me_job job = jobs[job_index[G.first + k]];
+      const xvcb200_cu cu = cus[job.cu];
+      int lo[2], hi[2];
+      min_max_mv(cu.x, cu.y, ref.width, ref.height, job.mvp[0], job.mvp[1], job.search_range, lo, hi);
+      atomicMin(&s_box[0], cu.x + lo[0]); atomicMin(&s_box[1], cu.y + lo[1]);
+      atomicMax(&s_box[2], cu.x + hi[0] + cu.w); atomicMax(&s_box[3], cu.y + hi[1] + cu.h);
+    }
+    __syncthreads();
+    RefSrc src;
+    src.plane = ref.base; src.gpitch = ref.pitch;
+    src.rx0 = s_box[0] & ~7; src.ry0 = s_box[1]; src.rx1 = s_box[2]; src.ry1 = s_box[3];
+    const int bw = src.rx1 - src.rx0, bh = src.ry1 - src.ry0;
+    src.spw = ((bw + 1) / 2 + 1) | 1;
+    const bool staged = (long long)src.spw * bh <= region_budget_words;
+    src.sm = staged ? s_region : nullptr;
+    if (staged) {     // 16-byte global loads (rx0 is a multiple of 8 samples), 4-byte shared stores
+      const int cpr = (bw + 7) >> 3;
+      for (int idx = tid; idx < bh * cpr; idx += kTzThreads) {
+        const int row = idx / cpr, ch = idx - row * cpr;
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ref.base + (src.ry0 + row) * ref.pitch + src.rx0) + ch);
+        uint32_t *d = s_region + row * src.spw + ch * 4;
+        const int left = src.spw - ch * 4;
+        d[0] = v.x;
+        if (left > 1) d[1] = v.y;
+        if (left > 2) d[2] = v.z;
+        if (left > 3) d[3] = v.w;
+      }
+    }
+    __syncthreads();
+
+    // phase 1 (and everything else when the windows are not staged): one warp per job
+    for (;;) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&s_next, 1);
+      k = __shfl_sync(XVCB_FULL, k, 0);
+      if (k >= G.count) break;
+      const int ji = job_index[G.first + k];
+      const xvcb200_me_job job = jobs[ji];
+      const xvcb200_cu cu = cus[job.cu];
+      const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+      tz_job_dispatch(1, !staged, g, cu, job, orig, ref.width, ref.height, src, lane, &states[ji], &res[ji]);
+    }
+    if (!staged) continue;
+    __threadfence_block();
+    __syncthreads();
+
+    // raster scans, CTA-wide, one job after the other
+    for (int k = 0; k < G.count; k++) {
+      const int ji = job_index[G.first + k];
+      TzJobState *stp = &states[ji];
+      if (!stp->need_raster) continue;           // uniform: every thread reads the same word
+      const xvcb200_me_job job = jobs[ji];
+      const xvcb200_cu cu = cus[job.cu];
+      const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+      const int slox = stp->slo[0], sloy = stp->slo[1], shix = stp->shi[0], shiy = stp->shi[1];
+      const uint32_t cost_in = stp->cost;
+      const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
+      const bool nonempty = shix >= slox && shiy >= sloy;
+      const bool fits = nonempty && g.x + slox >= src.rx0 && g.x + shix + g.w <= src.rx1 && g.y + sloy >= src.ry0 &&
+                        g.y + shiy + g.h <= src.ry1;
+      if (!fits) {       // window moved by the start points: one warp scans it from global memory
+        if (warp == 0) {
+          TzJobState st = *stp;
+          // (registers for the largest block class; the scan is the rare path)
+          const int pairs = g.rows << g.lpw;
+#define XVCB_RW(PP) { uint32_t o[PP]; load_orig_regs<PP>(g, orig, lane, o); tz_raster_warp<PP>(g, o, src, lane, st); }
+          switch (pairs >> 5) {
+            case 0: case 1: XVCB_RW(1) break;
+            case 2: XVCB_RW(2) break;
+            case 4: XVCB_RW(4) break;
+            case 8: XVCB_RW(8) break;
+            case 16: XVCB_RW(16) break;
+            default: XVCB_RW(32) break;
+          }
+#undef XVCB_RW
+          if (lane == 0) *stp = st;
+        }
+        __threadfence_block();
+        __syncthreads();
+        continue;
+      }
+      // original block -> shared memory as packed pairs [row][pair]
+      const int pw = 1 << g.lpw;
+      for (int q = tid; q < (g.rows << g.lpw); q += kTzThreads) {
+        const int row = q >> g.lpw, col = q & (pw - 1);
+        s_orig[q] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
+      }
+      __syncthreads();
+      const int passes = (ny + 31) >> 5;
+      uint32_t best_cost = 0xffffffffu, best_t = 0;
+      for (int task = warp; task < nx * passes; task += kTzWarps) {
+        const int i = task % nx, j = (task / nx) * 32 + lane;
+        const int jj = min(j, ny - 1);             // idle lanes recompute the last row (no stray reads)
+        const int cx = slox + 5 * i, cy = sloy + 5 * jj;
+        const int ox = g.x + cx - src.rx0, oy = g.y + cy - src.ry0;
+        const uint32_t *rp = s_region + oy * src.spw + (ox >> 1);
+        const int shift = (ox & 1) << 4, rw = g.rstep * src.spw;
+        uint32_t sad;
+        switch (g.lpw) {
+          case 1: sad = raster_sad<1>(rp, rw, s_orig, g.rows, shift); break;
+          case 2: sad = raster_sad<2>(rp, rw, s_orig, g.rows, shift); break;
+          case 3: sad = raster_sad<3>(rp, rw, s_orig, g.rows, shift); break;
+          case 4: sad = raster_sad<4>(rp, rw, s_orig, g.rows, shift); break;
+          default: sad = raster_sad<5>(rp, rw, s_orig, g.rows, shift); break;
+        }
+        if (j < ny) {
+          const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
+          const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+          const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
+          if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+        }
+      }
+      unsigned long long key = ((unsigned long long)best_cost << 32) | best_t;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(XVCB_FULL, key, off);
+        key = other < key ? other : key;
+      }
+      if (lane == 0) s_red[warp] = key;
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long m = s_red[0];
+        for (int w2 = 1; w2 < kTzWarps; w2++) m = s_red[w2] < m ? s_red[w2] : m;
+        const uint32_t c = (uint32_t)(m >> 32), t = (uint32_t)m;
+        if (c < cost_in) {                         // strict: ties keep the earlier best (:266-268)
+          stp->cost = c;
+          stp->bx = slox + 5 * (int)(t % nx);
+          stp->by = sloy + 5 * (int)(t / nx);
+        }
+        stp->last_range = 5;
+        stp->evals += nx * ny;
+        stp->need_raster = 0;
+      }
+      __threadfence_block();
+      __syncthreads();
+    }
+
+    // phase 3: one warp per job
+    if (tid == 0) s_next = 0;
+    __syncthreads();
+    for (;;) {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&s_next, 1);
+      k = __shfl_sync(XVCB_FULL, k, 0);
+      if (k >= G.count) break;
+      const int ji = job_index[G.first + k];
+      const xvcb200_me_job job = jobs[ji];
+      const xvcb200_cu cu = cus[job.cu];
+      const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+      tz_job_dispatch(3, false, g, cu, job, orig, ref.width, ref.height, src, lane, &states[ji], &res[ji]);
+    }
   }
 }
 
@@ -397,12 +683,31 @@ __global__ void __launch_bounds__(128) subpel_kernel(const xvcb200_cu *__restric
 }
 
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
-                             uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res) {
-  if (n <= 0) return cudaSuccess;
+                             uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
+                             const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter) {
+  if (n <= 0 || n_groups <= 0) return cudaSuccess;
+  static int smem_bytes = 0, num_sms = 0;
+  if (!smem_bytes) {
+    int dev = 0, max_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, tz_search_kernel);
+    smem_bytes = max_optin - (int)fa.sharedSizeBytes - 1024;
+    cudaError_t e = cudaFuncSetAttribute(tz_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { smem_bytes = 0; return e; }
+  }
+  cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
   g_launch_count++;
-  tz_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  const int grid = n_groups < num_sms ? n_groups : num_sms;
+  tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups),
+                                                        n_groups, d_counter, bitdepth, lambda_me, orig, d_ref_planes, d_res,
+                                                        static_cast<TzJobState *>(d_states), smem_bytes / 4 - 1024);
   return cudaGetLastError();
 }
+size_t tz_state_bytes() { return sizeof(TzJobState); }
 
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
