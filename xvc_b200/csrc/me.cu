@@ -13,6 +13,10 @@
 // candidate; "changed" = that minimum is below the incoming best.  The kernels evaluate a
 // whole list at once (one candidate per lane, lane index = list position) and take the
 // minimum of (cost << 5 | lane) -- the same winner, found in parallel.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
 #include "xvcb_interp.cuh"
 #include "xvcb_satd.cuh"
 
@@ -41,77 +45,81 @@ __device__ __forceinline__ uint32_t ld_pair(const Sample *p) {
 // Sum of |a - b| over two packed 16-bit lanes: max - min per lane, native VIMNMX.U16x2.
 __device__ __forceinline__ uint32_t absdiff2(uint32_t a, uint32_t b) { return __vmaxu2(a, b) - __vminu2(a, b); }
 
-// Where reference samples come from: the padded reference plane in global memory and, when the
-// search windows of a job group fit, a copy of their bounding box staged in shared memory
-// (rows of `spw` 32-bit words, two samples per word; spw is odd so that lanes reading rows
-// 5*k apart -- the raster grid -- fall into distinct banks).
-struct RefSrc {
-  const Sample *plane; int gpitch;      // sample (0,0) of the reference luma plane
-  const uint32_t *sm; int spw;          // staged box, null when not staged
-  int rx0, ry0, rx1, ry1;               // staged box in picture coordinates, [rx0,rx1) x [ry0,ry1), rx0 even
-};
-
-__device__ __forceinline__ bool block_staged(const RefSrc &src, const MeGeom &g, int cx, int cy) {
-  const int X = g.x + cx, Y = g.y + cy;
-  return src.sm != nullptr && X >= src.rx0 && X + g.w <= src.rx1 && Y >= src.ry0 && Y + g.h <= src.ry1;
+// Sum of |orig - ref| over `nrows` rows of PW = 2^LPW sample pairs.  rp: first (4-byte aligned)
+// reference word of the first row; a row of pairs starting at an odd sample is assembled from
+// two neighbouring words with a funnel shift (shift = 16), at an even sample shift = 0.
+// so: the original block as packed pairs.  GLOBAL: rp is global memory (read-only path).
+template <int LPW, bool GLOBAL>
+__device__ __forceinline__ uint32_t sad_rows(const uint32_t *rp, int ref_row_words, const uint32_t *so, int so_row_words,
+                                             int nrows, int shift) {
+  constexpr int PW = 1 << LPW;
+  uint32_t total = 0;
+  for (int r = 0; r < nrows; r++) {
+    uint32_t prev = GLOBAL ? __ldg(rp) : rp[0];
+#pragma unroll
+    for (int c0 = 0; c0 < PW; c0 += 16) {
+      uint32_t acc = 0;       // <= 16 x 4095 per 16-bit lane: no carry between the lanes
+#pragma unroll
+      for (int c = c0; c < (c0 + 16 < PW ? c0 + 16 : PW); c++) {
+        const uint32_t nxt = GLOBAL ? __ldg(rp + c + 1) : rp[c + 1];
+        acc += absdiff2(so[c], __funnelshift_r(prev, nxt, shift));
+        prev = nxt;
+      }
+      total += (acc & 0xffff) + (acc >> 16);
+    }
+    rp += ref_row_words;
+    so += so_row_words;
+  }
+  return total;
 }
 
-// Lane j holds candidate j (cx, cy, valid) of a list of K <= 32 candidates; returns in lane j
-// the metric value (SampleMetric::Compare kSad / kSadFast incl. the bit-depth shift) of candidate j.
-// G lanes share one candidate (G = min(32, pairs)), 32/G candidates per pass.
-template <int P>
-__device__ __forceinline__ uint32_t eval_candidates(const MeGeom &g, const uint32_t (&o)[P], const RefSrc &src,
-                                                    int cx, int cy, bool valid, int K, int lane) {
-  const int NG = 32 >> g.lG;                 // candidates per pass
-  const int gl = lane & (g.G - 1), grp = lane >> g.lG;
-  uint32_t mine = 0xffffffffu;
-  for (int c0 = 0; c0 < K; c0 += NG) {
-    const int c = c0 + grp;
-    const int sx = __shfl_sync(XVCB_FULL, cx, c & 31);
-    const int sy = __shfl_sync(XVCB_FULL, cy, c & 31);
-    const bool sv = __shfl_sync(XVCB_FULL, (int)valid, c & 31) && c < K;
+template <bool GLOBAL>
+__device__ __forceinline__ uint32_t sad_rows_lpw(int lpw, const uint32_t *rp, int ref_row_words, const uint32_t *so,
+                                                 int so_row_words, int nrows, int shift) {
+  switch (lpw) {
+    case 1: return sad_rows<1, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 2: return sad_rows<2, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 3: return sad_rows<3, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 4: return sad_rows<4, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    default: return sad_rows<5, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
+  }
+}
+
+// Evaluates the K <= 32 candidates of one search round for one warp.  Lane j holds candidate j
+// (cx, cy, valid) and receives its metric value (SampleMetric::Compare kSad / kSadFast incl. the
+// bit-depth shift).  The 32 lanes are split into K' = pow2(K) sub-groups of G = 32/K' lanes (not
+// more than the block has rows); each lane sums whole block rows r = sub, sub+G, ... of its
+// candidate, the G partial sums meet in log2(G) shuffles.  Original block: shared memory, rows
+// padded by one word so that the G row-interleaved lanes hit distinct banks.
+struct RoundEval {
+  const MeGeom &g;
+  const uint32_t *so;        // [rows][PW + 1] packed pairs
+  const Sample *plane;       // sample (0,0) of the reference luma plane (4-byte aligned, even pitch)
+  int gpitch;
+  int lane;
+
+  __device__ __forceinline__ uint32_t operator()(int cx, int cy, bool valid, int K) const {
+    int lg = K <= 4 ? 3 : (K <= 8 ? 2 : (K <= 16 ? 1 : 0));
+    while ((1 << lg) > g.rows) lg--;
+    const int cand = lane >> lg, sub = lane & ((1 << lg) - 1);
+    const int sx = __shfl_sync(XVCB_FULL, cx, cand);
+    const int sy = __shfl_sync(XVCB_FULL, cy, cand);
+    const bool sv = __shfl_sync(XVCB_FULL, (int)valid, cand) && cand < K;
     uint32_t acc = 0;
     if (sv) {
-      if (block_staged(src, g, sx, sy)) {
-        const int ox = g.x + sx - src.rx0, oy = g.y + sy - src.ry0;
-#pragma unroll
-        for (int k0 = 0; k0 < P; k0 += 8) {
-          uint32_t packed = 0;   // up to 8 x 4095 per 16-bit lane: no carry between the lanes
-#pragma unroll
-          for (int k = k0; k < (k0 + 8 < P ? k0 + 8 : P); k++) {
-            const int q = gl + (k << g.lG);
-            const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
-            const int sxo = ox + col * 2;
-            const uint32_t *wp = src.sm + (oy + row * g.rstep) * src.spw + (sxo >> 1);
-            packed += absdiff2(o[k], __funnelshift_r(wp[0], wp[1], (sxo & 1) << 4));
-          }
-          acc += (packed & 0xffff) + (packed >> 16);
-        }
-      } else {
-        const Sample *r = src.plane + (g.y + sy) * src.gpitch + g.x + sx;
-#pragma unroll
-        for (int k0 = 0; k0 < P; k0 += 8) {
-          uint32_t packed = 0;
-#pragma unroll
-          for (int k = k0; k < (k0 + 8 < P ? k0 + 8 : P); k++) {
-            const int q = gl + (k << g.lG);
-            const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
-            packed += absdiff2(o[k], ld_pair(r + row * g.rstep * src.gpitch + col * 2));
-          }
-          acc += (packed & 0xffff) + (packed >> 16);
-        }
-      }
+      const int X = g.x + sx;
+      const Sample *row0 = plane + (g.y + sy + sub * g.rstep) * gpitch + (X & ~1);
+      acc = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * gpitch << lg) >> 1,
+                               so + sub * ((1 << g.lpw) + 1), ((1 << g.lpw) + 1) << lg, g.rows >> lg, (X & 1) << 4);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-      if (off < g.G) acc += __shfl_xor_sync(XVCB_FULL, acc, off);
-    // candidate j was computed in pass j / NG by group j % NG
-    const uint32_t got = __shfl_sync(XVCB_FULL, acc, (lane & (NG - 1)) << g.lG);
-    if ((lane & ~(NG - 1)) == c0) mine = got;
+    for (int off = 4; off > 0; off >>= 1)
+      if (off < (1 << lg)) acc += __shfl_xor_sync(XVCB_FULL, acc, off);
+    const uint32_t mine = __shfl_sync(XVCB_FULL, acc, (lane << lg) & 31);
+    if (!valid || lane >= K) return 0xffffffffu;
+    return g.fast ? (mine * 2) >> g.bd_shift : mine >> g.bd_shift;
   }
-  if (!valid || lane >= K) return 0xffffffffu;
-  return g.fast ? (mine * 2) >> g.bd_shift : mine >> g.bd_shift;
-}
+};
 
 // Applies an evaluated candidate list to the running best (see the file comment).
 __device__ __forceinline__ bool apply_candidates(TzBest &b, uint32_t dist, int cx, int cy, int pos, int range,
@@ -208,7 +216,7 @@ __device__ __forceinline__ int two_point(int last_pos, int lane, int &dx, int &d
   return 2;
 }
 
-// State of one search between its phases (kept in global scratch, L2 resident).
+// State of one search between its phases (global scratch, L2 resident).
 struct TzJobState {
   int bx, by; uint32_t cost; int last_pos, last_range;
   int lo[2], hi[2], slo[2], shi[2];
@@ -216,21 +224,8 @@ struct TzJobState {
   int need_raster;
 };
 
-template <int P>
-__device__ __forceinline__ void load_orig_regs(const MeGeom &g, PlaneView orig, int lane, uint32_t (&o)[P]) {
-  const int gl = lane & (g.G - 1);
-  const Sample *ob = orig.base + g.y * orig.pitch + g.x;
-#pragma unroll
-  for (int k = 0; k < P; k++) {
-    const int q = gl + (k << g.lG);
-    const int row = q >> g.lpw, col = q & ((1 << g.lpw) - 1);
-    o[k] = ld_pair(ob + row * g.rstep * orig.pitch + col * 2);
-  }
-}
-
-template <int P>
-__device__ __forceinline__ void neighbour_points(const MeGeom &g, const uint32_t (&o)[P], const RefSrc &src, TzBest &b,
-                                                 const int lo[2], const int hi[2], uint32_t &evals, int lane) {
+__device__ __forceinline__ void neighbour_points(const MeGeom &g, const RoundEval &ev, TzBest &b, const int lo[2],
+                                                 const int hi[2], uint32_t &evals, int lane) {
   if (b.last_range != 1) return;
   b.last_range = 0;
   int dx = 0, dy = 0, pos = 0;
@@ -239,15 +234,14 @@ __device__ __forceinline__ void neighbour_points(const MeGeom &g, const uint32_t
   const int cx = b.x + dx, cy = b.y + dy;
   const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
   evals += __popc(__ballot_sync(XVCB_FULL, valid));
-  const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, K, lane);
+  const uint32_t d = ev(cx, cy, valid, K);
   apply_candidates(b, d, cx, cy, pos, 1, g, lane);
 }
 
 // Phase 1 of TzSearch::Search: start points, first diamond pass, 2-point refinement
 // (inter_tz_search.cc:102-144).
-template <int P>
 __device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job, int pic_w, int pic_h,
-                          const uint32_t (&o)[P], const RefSrc &src, int lane, TzJobState &st) {
+                          const RoundEval &ev, int lane, TzJobState &st) {
   const int range = job.search_range;
   int lo[2], hi[2], slo[2], shi[2];
   min_max_mv(g.x, g.y, pic_w, pic_h, g.mvpx, g.mvpy, range, lo, hi);
@@ -267,7 +261,7 @@ __device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_m
     const int cx = lane == 0 ? px : (lane == 1 ? 0 : qx);
     const int cy = lane == 0 ? py : (lane == 1 ? 0 : qy);
     const bool valid = lane == 0 || (lane == 1 && use_zero) || (lane == 2 && use_prev);
-    const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, 3, lane);
+    const uint32_t d = ev(cx, cy, valid, 3);
     evals += 1 + use_zero + use_prev;
     uint32_t cost = 0xffffffffu;
     if (d != 0xffffffffu) cost = d + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
@@ -291,12 +285,12 @@ __device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_m
       const int cx = bx + dx, cy = by + dy;
       const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
       evals += __popc(__ballot_sync(XVCB_FULL, valid));
-      const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, K, lane);
+      const uint32_t d = ev(cx, cy, valid, K);
       if (apply_candidates(b, d, cx, cy, pos, rep, g, lane)) misses = 0;
       else if (++misses >= 3) break;
     }
   }
-  neighbour_points<P>(g, o, src, b, lo, hi, evals, lane);
+  neighbour_points(g, ev, b, lo, hi, evals, lane);
   st.bx = b.x; st.by = b.y; st.cost = b.cost; st.last_pos = b.last_pos; st.last_range = b.last_range;
   st.lo[0] = lo[0]; st.lo[1] = lo[1]; st.hi[0] = hi[0]; st.hi[1] = hi[1];
   st.slo[0] = slo[0]; st.slo[1] = slo[1]; st.shi[0] = shi[0]; st.shi[1] = shi[1];
@@ -304,32 +298,9 @@ __device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_m
   st.need_raster = b.last_range > 5;       // kFullSearchGranularity (:91, :146)
 }
 
-// Raster scan of the window on a 5-sample grid by ONE warp (:145-155); used when the window
-// is not staged in shared memory.
-template <int P>
-__device__ void tz_raster_warp(const MeGeom &g, const uint32_t (&o)[P], const RefSrc &src, int lane, TzJobState &st) {
-  TzBest b;
-  b.x = st.bx; b.y = st.by; b.cost = st.cost; b.last_pos = st.last_pos; b.last_range = 5;
-  const int nx = (st.shi[0] - st.slo[0]) / 5 + 1, ny = (st.shi[1] - st.slo[1]) / 5 + 1;
-  if (st.shi[0] >= st.slo[0] && st.shi[1] >= st.slo[1]) {
-    const int total = nx * ny;
-    for (int t0 = 0; t0 < total; t0 += 32) {
-      const int t = t0 + lane;
-      const int j = t / nx, i = t - j * nx;
-      const int cx = st.slo[0] + 5 * i, cy = st.slo[1] + 5 * j;
-      const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, t < total, min(32, total - t0), lane);
-      apply_candidates(b, d, cx, cy, b.last_pos, b.last_range, g, lane);   // CheckCostBest alone keeps last_*
-    }
-    st.evals += total;
-  }
-  st.bx = b.x; st.by = b.y; st.cost = b.cost; st.last_range = 5;
-  st.need_raster = 0;
-}
-
 // Phase 3: re-centre until the centre wins (:157-168), then the result.
-template <int P>
-__device__ void tz_phase3(const MeGeom &g, int range, const uint32_t (&o)[P], const RefSrc &src, int lane,
-                          const TzJobState &st, xvcb200_me_result *out) {
+__device__ void tz_phase3(const MeGeom &g, int range, const RoundEval &ev, int lane, const TzJobState &st,
+                          xvcb200_me_result *out) {
   TzBest b;
   b.x = st.bx; b.y = st.by; b.cost = st.cost; b.last_pos = st.last_pos; b.last_range = st.last_range;
   uint32_t evals = st.evals;
@@ -342,10 +313,10 @@ __device__ void tz_phase3(const MeGeom &g, int range, const uint32_t (&o)[P], co
       const int cx = bx + dx, cy = by + dy;
       const bool valid = lane < K && inside(cx, cy, pos, st.lo, st.hi);
       evals += __popc(__ballot_sync(XVCB_FULL, valid));
-      const uint32_t d = eval_candidates<P>(g, o, src, cx, cy, valid, K, lane);
+      const uint32_t d = ev(cx, cy, valid, K);
       apply_candidates(b, d, cx, cy, pos, rep, g, lane);
     }
-    neighbour_points<P>(g, o, src, b, st.lo, st.hi, evals, lane);
+    neighbour_points(g, ev, b, st.lo, st.hi, evals, lane);
   }
   if (lane == 0) {
     out->mv_fullpel[0] = b.x; out->mv_fullpel[1] = b.y;
@@ -371,87 +342,66 @@ __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, ui
   return g;
 }
 
-// which: 1 = phase 1 (+ raster and phase 3 when `through`), 3 = phase 3
-template <int P>
-__device__ void tz_job_phase(int which, bool through, const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job,
-                             PlaneView orig, int pic_w, int pic_h, const RefSrc &src, int lane, TzJobState *st_g,
-                             xvcb200_me_result *out) {
-  uint32_t o[P];
-  load_orig_regs<P>(g, orig, lane, o);
-  TzJobState st;
+// Phase 1 (which = 1) or phase 3 (which = 3) of every job: one warp per job.
+constexpr int kRoundWarps = 4;
+__global__ void __launch_bounds__(kRoundWarps * 32)
+tz_rounds_kernel(int which, const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
+                 int bitdepth, uint32_t lambda, PlaneView orig, const PlaneView *__restrict__ ref_planes,
+                 xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states) {
+  __shared__ uint32_t s_orig[kRoundWarps][32 * 33];     // up to 32 rows x (32 pairs + 1 pad word)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ji = blockIdx.x * kRoundWarps + warp;
+  if (ji >= n) return;
+  const xvcb200_me_job job = jobs[ji];
+  const xvcb200_cu cu = cus[job.cu];
+  const PlaneView ref = ref_planes[job.ref_slot];
+  const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+  if (which == 3 && states[ji].last_range <= 0) {       // nothing to refine: result = state
+    if (lane == 0) {
+      res[ji].mv_fullpel[0] = states[ji].bx; res[ji].mv_fullpel[1] = states[ji].by;
+      res[ji].cost_fullpel = states[ji].cost; res[ji].num_sad = states[ji].evals;
+    }
+    return;
+  }
+  uint32_t *so = s_orig[warp];
+  const int pw = 1 << g.lpw;
+  for (int q = lane; q < (g.rows << g.lpw); q += 32) {
+    const int row = q >> g.lpw, col = q & (pw - 1);
+    so[row * (pw + 1) + col] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
+  }
+  __syncwarp();
+  const RoundEval ev{g, so, ref.base, ref.pitch, lane};
   if (which == 1) {
-    tz_phase1<P>(g, cu, job, pic_w, pic_h, o, src, lane, st);
-    if (through) {
-      if (st.need_raster) tz_raster_warp<P>(g, o, src, lane, st);
-      tz_phase3<P>(g, job.search_range, o, src, lane, st, out);
-    } else if (lane == 0) {
-      *st_g = st;
-    }
+    TzJobState st;
+    tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
+    if (lane == 0) states[ji] = st;
   } else {
-    st = *st_g;
-    tz_phase3<P>(g, job.search_range, o, src, lane, st, out);
+    const TzJobState st = states[ji];
+    tz_phase3(g, job.search_range, ev, lane, st, &res[ji]);
   }
 }
 
-__device__ void tz_job_dispatch(int which, bool through, const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job,
-                                PlaneView orig, int pic_w, int pic_h, const RefSrc &src, int lane, TzJobState *st_g,
-                                xvcb200_me_result *out) {
-  const int pairs = g.rows << g.lpw;
-  switch (pairs >> 5) {
-    case 0: case 1: tz_job_phase<1>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
-    case 2: tz_job_phase<2>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
-    case 4: tz_job_phase<4>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
-    case 8: tz_job_phase<8>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
-    case 16: tz_job_phase<16>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
-    default: tz_job_phase<32>(which, through, g, cu, job, orig, pic_w, pic_h, src, lane, st_g, out); break;
-  }
-}
-
-// One raster candidate column for 32 candidate rows (lane = row): sum of |orig - ref| over the
-// block rows the metric visits.  `rp` = this lane's first reference word, `so` = the original
-// block as packed pairs in shared memory (broadcast reads), shift = 0 / 16 for even / odd x.
-template <int LPW>
-__device__ __forceinline__ uint32_t raster_sad(const uint32_t *rp, int row_words, const uint32_t *so, int rows,
-                                               int shift) {
-  constexpr int PW = 1 << LPW;
-  uint32_t total = 0;
-  for (int r = 0; r < rows; r++) {
-    uint32_t prev = rp[0];
-#pragma unroll
-    for (int c0 = 0; c0 < PW; c0 += 16) {
-      uint32_t acc = 0;       // <= 16 x 4095 per 16-bit lane
-#pragma unroll
-      for (int c = c0; c < (c0 + 16 < PW ? c0 + 16 : PW); c++) {
-        const uint32_t nxt = rp[c + 1];
-        acc += absdiff2(so[c], __funnelshift_r(prev, nxt, shift));
-        prev = nxt;
-      }
-      total += (acc & 0xffff) + (acc >> 16);
-    }
-    rp += row_words;
-    so += PW;
-  }
-  return total;
-}
-
-constexpr int kTzThreads = 256;
+constexpr int kTzThreads = 512;
 constexpr int kTzWarps = kTzThreads / 32;
 
 struct TzGroup { int first, count; };    // run of entries in job_index: jobs sharing a reference picture and a CTU
 
-// TzSearch::Search for job groups.  One persistent CTA per SM; per group: bounding box of the
-// search windows -> shared memory, phase 1 per warp, raster scans CTA-wide (one candidate per
-// lane, no reductions in the inner loop), phase 3 per warp.
+// Raster scan of TzSearch::Search (inter_tz_search.cc:145-155) for every job that needs it.
+// One persistent CTA per SM.  Per job group (jobs of one CTU on one reference picture): the
+// bounding box of the jobs' scan windows is staged in shared memory once; then every job is
+// scanned CTA-wide with ONE CANDIDATE PER LANE: a warp takes one grid column (fixed x, so the
+// alignment shift is warp-uniform) and 32 grid rows (5 picture rows apart; the odd row pitch of
+// the staged box makes those 32 rows fall into 32 distinct banks).  No shuffles or reductions in
+// the inner loop; the per-lane winners meet once per job.
 __global__ void __launch_bounds__(kTzThreads, 1)
-tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
+tz_raster_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
                  const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
                  int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
-                 const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res,
-                 TzJobState *__restrict__ states, int region_budget_words) {
+                 const PlaneView *__restrict__ ref_planes, TzJobState *__restrict__ states, int region_budget_words) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t *s_orig = smem;                       // 1024 words: original block of the job being raster-scanned
+  uint32_t *s_orig = smem;                       // 1024 words: original block of the job being scanned
   uint32_t *s_region = smem + 1024;
-  __shared__ int s_group, s_next, s_box[4];
+  __shared__ int s_group, s_box[4];
   __shared__ unsigned long long s_red[kTzWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -459,7 +409,6 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     __syncthreads();                             // previous group is completely done with shared memory
     if (tid == 0) {
       s_group = atomicAdd(counter, 1);
-      s_next = 0;
       s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
     }
     __syncthreads();
@@ -468,55 +417,50 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     const TzGroup G = groups[grp];
     const PlaneView ref = ref_planes[jobs[job_index[G.first]].ref_slot];
 
-    // bounding box of the jobs' search windows (block extent included)
+    // bounding box of the scan windows (block extent included) of the jobs that scan
     for (int k = tid; k < G.count; k += kTzThreads) {
-      const xvcb200_me_job job = jobs[job_index[G.first + k]];
-      const xvcb200_cu cu = cus[job.cu];
-      int lo[2], hi[2];
-      min_max_mv(cu.x, cu.y, ref.width, ref.height, job.mvp[0], job.mvp[1], job.search_range, lo, hi);
-      atomicMin(&s_box[0], cu.x + lo[0]); atomicMin(&s_box[1], cu.y + lo[1]);
-      atomicMax(&s_box[2], cu.x + hi[0] + cu.w); atomicMax(&s_box[3], cu.y + hi[1] + cu.h);
+      const int ji = job_index[G.first + k];
+      const TzJobState *st = &states[ji];
+      if (!st->need_raster || st->shi[0] < st->slo[0] || st->shi[1] < st->slo[1]) continue;
+      const xvcb200_cu cu = cus[jobs[ji].cu];
+      atomicMin(&s_box[0], cu.x + st->slo[0]); atomicMin(&s_box[1], cu.y + st->slo[1]);
+      atomicMax(&s_box[2], cu.x + st->shi[0] + cu.w); atomicMax(&s_box[3], cu.y + st->shi[1] + cu.h);
     }
     __syncthreads();
-    RefSrc src;
-    src.plane = ref.base; src.gpitch = ref.pitch;
-    src.rx0 = s_box[0] & ~7; src.ry0 = s_box[1]; src.rx1 = s_box[2]; src.ry1 = s_box[3];
-    const int bw = src.rx1 - src.rx0, bh = src.ry1 - src.ry0;
-    src.spw = ((bw + 1) / 2 + 1) | 1;
-    const bool staged = (long long)src.spw * bh <= region_budget_words;
-    src.sm = staged ? s_region : nullptr;
+    if (s_box[2] < s_box[0]) continue;           // no job of this group scans
+    const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
+    const int bw = rx1 - rx0, bh = ry1 - ry0;
+    const int spw = ((bw + 1) / 2 + 1) | 1;
+    const bool staged = (long long)spw * bh <= region_budget_words;
     if (staged) {     // 16-byte global loads (rx0 is a multiple of 8 samples), 4-byte shared stores
-      const int cpr = (bw + 7) >> 3;
-      for (int idx = tid; idx < bh * cpr; idx += kTzThreads) {
-        const int row = idx / cpr, ch = idx - row * cpr;
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ref.base + (src.ry0 + row) * ref.pitch + src.rx0) + ch);
-        uint32_t *d = s_region + row * src.spw + ch * 4;
-        const int left = src.spw - ch * 4;
-        d[0] = v.x;
-        if (left > 1) d[1] = v.y;
-        if (left > 2) d[2] = v.z;
-        if (left > 3) d[3] = v.w;
+      const int cpr = (bw + 7) >> 3, total = bh * cpr;
+      for (int idx0 = tid; idx0 < total; idx0 += 4 * kTzThreads) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {            // four independent loads in flight per thread
+          const int idx = idx0 + u * kTzThreads;
+          if (idx < total) {
+            const int row = idx / cpr, ch = idx - row * cpr;
+            v[u] = __ldg(reinterpret_cast<const uint4 *>(ref.base + (ry0 + row) * ref.pitch + rx0) + ch);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int idx = idx0 + u * kTzThreads;
+          if (idx < total) {
+            const int row = idx / cpr, ch = idx - row * cpr;
+            uint32_t *d = s_region + row * spw + ch * 4;
+            const int left = spw - ch * 4;
+            d[0] = v[u].x;
+            if (left > 1) d[1] = v[u].y;
+            if (left > 2) d[2] = v[u].z;
+            if (left > 3) d[3] = v[u].w;
+          }
+        }
       }
     }
     __syncthreads();
 
-    // phase 1 (and everything else when the windows are not staged): one warp per job
-    for (;;) {
-      int k = 0;
-      if (lane == 0) k = atomicAdd(&s_next, 1);
-      k = __shfl_sync(XVCB_FULL, k, 0);
-      if (k >= G.count) break;
-      const int ji = job_index[G.first + k];
-      const xvcb200_me_job job = jobs[ji];
-      const xvcb200_cu cu = cus[job.cu];
-      const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
-      tz_job_dispatch(1, !staged, g, cu, job, orig, ref.width, ref.height, src, lane, &states[ji], &res[ji]);
-    }
-    if (!staged) continue;
-    __threadfence_block();
-    __syncthreads();
-
-    // raster scans, CTA-wide, one job after the other
     for (int k = 0; k < G.count; k++) {
       const int ji = job_index[G.first + k];
       TzJobState *stp = &states[ji];
@@ -528,29 +472,6 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       const uint32_t cost_in = stp->cost;
       const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
       const bool nonempty = shix >= slox && shiy >= sloy;
-      const bool fits = nonempty && g.x + slox >= src.rx0 && g.x + shix + g.w <= src.rx1 && g.y + sloy >= src.ry0 &&
-                        g.y + shiy + g.h <= src.ry1;
-      if (!fits) {       // window moved by the start points: one warp scans it from global memory
-        if (warp == 0) {
-          TzJobState st = *stp;
-          // (registers for the largest block class; the scan is the rare path)
-          const int pairs = g.rows << g.lpw;
-#define XVCB_RW(PP) { uint32_t o[PP]; load_orig_regs<PP>(g, orig, lane, o); tz_raster_warp<PP>(g, o, src, lane, st); }
-          switch (pairs >> 5) {
-            case 0: case 1: XVCB_RW(1) break;
-            case 2: XVCB_RW(2) break;
-            case 4: XVCB_RW(4) break;
-            case 8: XVCB_RW(8) break;
-            case 16: XVCB_RW(16) break;
-            default: XVCB_RW(32) break;
-          }
-#undef XVCB_RW
-          if (lane == 0) *stp = st;
-        }
-        __threadfence_block();
-        __syncthreads();
-        continue;
-      }
       // original block -> shared memory as packed pairs [row][pair]
       const int pw = 1 << g.lpw;
       for (int q = tid; q < (g.rows << g.lpw); q += kTzThreads) {
@@ -558,28 +479,29 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         s_orig[q] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
       }
       __syncthreads();
-      const int passes = (ny + 31) >> 5;
       uint32_t best_cost = 0xffffffffu, best_t = 0;
-      for (int task = warp; task < nx * passes; task += kTzWarps) {
-        const int i = task % nx, j = (task / nx) * 32 + lane;
-        const int jj = min(j, ny - 1);             // idle lanes recompute the last row (no stray reads)
-        const int cx = slox + 5 * i, cy = sloy + 5 * jj;
-        const int ox = g.x + cx - src.rx0, oy = g.y + cy - src.ry0;
-        const uint32_t *rp = s_region + oy * src.spw + (ox >> 1);
-        const int shift = (ox & 1) << 4, rw = g.rstep * src.spw;
-        uint32_t sad;
-        switch (g.lpw) {
-          case 1: sad = raster_sad<1>(rp, rw, s_orig, g.rows, shift); break;
-          case 2: sad = raster_sad<2>(rp, rw, s_orig, g.rows, shift); break;
-          case 3: sad = raster_sad<3>(rp, rw, s_orig, g.rows, shift); break;
-          case 4: sad = raster_sad<4>(rp, rw, s_orig, g.rows, shift); break;
-          default: sad = raster_sad<5>(rp, rw, s_orig, g.rows, shift); break;
-        }
-        if (j < ny) {
-          const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
-          const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-          const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
-          if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+      if (nonempty) {
+        const int passes = (ny + 31) >> 5;
+        for (int task = warp; task < nx * passes; task += kTzWarps) {
+          const int i = task % nx, j = (task / nx) * 32 + lane;
+          const int jj = min(j, ny - 1);             // idle lanes recompute the last row (no stray reads)
+          const int cx = slox + 5 * i, cy = sloy + 5 * jj;
+          uint32_t sad;
+          if (staged) {
+            const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
+            sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, s_orig, pw, g.rows, (ox & 1) << 4);
+          } else {                                    // window too large for shared memory: same walk from global memory
+            const int X = g.x + cx;
+            const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
+            sad = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, s_orig, pw,
+                                     g.rows, (X & 1) << 4);
+          }
+          if (j < ny) {
+            const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
+            const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+            const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
+            if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+          }
         }
       }
       unsigned long long key = ((unsigned long long)best_cost << 32) | best_t;
@@ -594,32 +516,16 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         unsigned long long m = s_red[0];
         for (int w2 = 1; w2 < kTzWarps; w2++) m = s_red[w2] < m ? s_red[w2] : m;
         const uint32_t c = (uint32_t)(m >> 32), t = (uint32_t)m;
-        if (c < cost_in) {                         // strict: ties keep the earlier best (:266-268)
+        if (nonempty && c < cost_in) {             // strict: ties keep the earlier best (:266-268)
           stp->cost = c;
           stp->bx = slox + 5 * (int)(t % nx);
           stp->by = sloy + 5 * (int)(t / nx);
         }
         stp->last_range = 5;
-        stp->evals += nx * ny;
+        if (nonempty) stp->evals += nx * ny;
         stp->need_raster = 0;
       }
-      __threadfence_block();
       __syncthreads();
-    }
-
-    // phase 3: one warp per job
-    if (tid == 0) s_next = 0;
-    __syncthreads();
-    for (;;) {
-      int k = 0;
-      if (lane == 0) k = atomicAdd(&s_next, 1);
-      k = __shfl_sync(XVCB_FULL, k, 0);
-      if (k >= G.count) break;
-      const int ji = job_index[G.first + k];
-      const xvcb200_me_job job = jobs[ji];
-      const xvcb200_cu cu = cus[job.cu];
-      const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
-      tz_job_dispatch(3, false, g, cu, job, orig, ref.width, ref.height, src, lane, &states[ji], &res[ji]);
     }
   }
 }
@@ -693,18 +599,21 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, tz_search_kernel);
+    cudaFuncGetAttributes(&fa, tz_raster_kernel);
     smem_bytes = max_optin - (int)fa.sharedSizeBytes - 1024;
-    cudaError_t e = cudaFuncSetAttribute(tz_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(tz_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { smem_bytes = 0; return e; }
   }
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  g_launch_count++;
-  const int grid = n_groups < num_sms ? n_groups : num_sms;
-  tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups),
-                                                        n_groups, d_counter, bitdepth, lambda_me, orig, d_ref_planes, d_res,
-                                                        static_cast<TzJobState *>(d_states), smem_bytes / 4 - 1024);
+  TzJobState *st = static_cast<TzJobState *>(d_states);
+  const int blocks = (n + kRoundWarps - 1) / kRoundWarps;
+  g_launch_count += 3;
+  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(1, d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
+  tz_raster_kernel<<<n_groups < num_sms ? n_groups : num_sms, kTzThreads, smem_bytes, s>>>(
+      d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
+      d_ref_planes, st, smem_bytes / 4 - 1024);
+  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(3, d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
   return cudaGetLastError();
 }
 size_t tz_state_bytes() { return sizeof(TzJobState); }
