@@ -13,7 +13,8 @@ namespace xvcb {
 cudaError_t launch_tq_reconstruct_classes(cudaStream_t s, xvcb200_cu *d_cus, const int *d_tu_list,
                                           const int class_count[7][7], const int class_offset[7][7],
                                           const TqParams &p, Pic3 orig, Pic3 pred, Pic3 rec, int16_t *const lev[3],
-                                          const int lev_pitch[3], xvcb200_tu_result *d_res);
+                                          const int lev_pitch[3], xvcb200_tu_result *d_res, cudaStream_t *side,
+                                          cudaEvent_t *side_ev, int n_side, cudaEvent_t fork_ev);
 
 static thread_local int t_last_error = XVCB200_OK;
 static thread_local char t_last_error_str[256] = "";
@@ -357,6 +358,12 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   uint8_t *d_tz_states = nullptr; int tz_states_cap = 0;
   int *d_counter = nullptr;
   int pipeline_groups_nl = 0, pipeline_n_groups = 0;   // cached grouping of the picture pipeline's job list
+  // side streams for independent launches inside one stage (T/Q shape classes)
+  static constexpr int kSide = 6;
+  cudaStream_t side[kSide] = {nullptr};
+  cudaEvent_t side_ev[kSide] = {nullptr};
+  cudaEvent_t fork_ev = nullptr;
+  int n_side = 0;
   // optional per-stage timing of xvcb200_encode_picture (CUDA events on the context stream)
   bool profile = false;
   cudaEvent_t ev[9] = {nullptr};
@@ -430,6 +437,13 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
     }
     views[s] = c->plane(s, 0);
   }
+  if (cudaEventCreateWithFlags(&c->ex.fork_ev, cudaEventDisableTiming) == cudaSuccess) {
+    for (int i = 0; i < CtxExtra::kSide; i++) {
+      if (cudaStreamCreateWithFlags(&c->ex.side[i], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ex.side_ev[i], cudaEventDisableTiming) != cudaSuccess) break;
+      c->ex.n_side = i + 1;
+    }
+  }
   c->map_w = width >> 2; c->map_h = height >> 2;
   const size_t cells = (size_t)c->map_w * c->map_h;
   if (!c->check(cudaMalloc(&c->ex.d_luma_views, sizeof(PlaneView) * num_slots), "cudaMalloc(views)") ||
@@ -456,6 +470,8 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
+  if (c->ex.fork_ev) cudaEventDestroy(c->ex.fork_ev);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -704,7 +720,8 @@ static int tq_common(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slo
   for (int k = 0; k < 3; k++) { lev[k] = reinterpret_cast<int16_t *>(c->slots[coeff_slot].base[k]); pitch[k] = c->geom.pitch[k]; }
   c->check(launch_tq_reconstruct_classes(c->stream, c->d_cus, c->ex.d_tu_list, c->ex.class_count, c->ex.class_offset, p,
                                          pic3(c, decode_only ? pred_slot : orig_slot), pic3(c, pred_slot), pic3(c, rec_slot),
-                                         lev, pitch, decode_only ? nullptr : c->ex.d_tu), "tq_reconstruct");
+                                         lev, pitch, decode_only ? nullptr : c->ex.d_tu, c->ex.side, c->ex.side_ev,
+                                         c->ex.n_side, c->ex.fork_ev), "tq_reconstruct");
   if (results && !decode_only) {
     c->check(cudaMemcpyAsync(results, c->ex.d_tu, sizeof(*results) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "tu results");
     return xvcb200_sync(c);

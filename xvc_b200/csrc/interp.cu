@@ -125,8 +125,9 @@ __device__ __forceinline__ void mc_cu(const xvcb200_cu &cu, int comp, int bitdep
     const int shift = (head > 2 ? head : 2) + 1;
     const int offset = (1 << (shift - 1)) + 2 * 8192;
     const int maxv = (1 << bitdepth) - 1;
+    const int lw = 31 - __clz(w);
     for (int i = tid; i < w * h; i += 128) {
-      const int yy = i / w, xx = i - yy * w;
+      const int yy = i >> lw, xx = i & (w - 1);
       dst[yy * pred.pitch + xx] = add_avg_one(bi0[yy * 64 + xx], bi1[yy * 64 + xx], offset, shift, maxv);
     }
   } else {

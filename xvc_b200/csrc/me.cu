@@ -546,8 +546,9 @@ __global__ void __launch_bounds__(128) subpel_kernel(const xvcb200_cu *__restric
   const xvcb200_cu cu = cus[job.cu];
   const PlaneView ref = ref_planes[job.ref_slot];
   const int w = cu.w, h = cu.h;
+  const int lw = 31 - __clz(w);
   for (int i = tid; i < w * h; i += 128) {
-    const int y = i / w, x = i - y * w;
+    const int y = i >> lw, x = i & (w - 1);
     org[y * 64 + x] = orig.base[(cu.y + y) * orig.pitch + cu.x + x];
   }
   const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;

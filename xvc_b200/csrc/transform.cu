@@ -539,23 +539,39 @@ static void launch_tq_class(cudaStream_t s, xvcb200_cu *d_cus, const int *d_list
 
 // h_class_count / h_class_offset: per shape class [lw][lh] (1..6) counts and offsets into
 // d_tu_list, prepared on the host when the CU array is set.
+// The shape classes are independent of each other: their launches are spread round-robin over
+// `n_side` side streams that fork from / join into `s` through events, so the many small grids
+// overlap on the GPU instead of running back to back.
 cudaError_t launch_tq_reconstruct_classes(cudaStream_t s, xvcb200_cu *d_cus, const int *d_tu_list,
                                           const int class_count[7][7], const int class_offset[7][7],
                                           const TqParams &p, Pic3 orig, Pic3 pred, Pic3 rec, int16_t *const lev[3],
-                                          const int lev_pitch[3], xvcb200_tu_result *d_res) {
+                                          const int lev_pitch[3], xvcb200_tu_result *d_res, cudaStream_t *side,
+                                          cudaEvent_t *side_ev, int n_side, cudaEvent_t fork_ev) {
   cudaError_t e = ensure_dct2_constant();
   if (e != cudaSuccess) return e;
+  if (n_side > 0) {
+    cudaEventRecord(fork_ev, s);
+    for (int i = 0; i < n_side; i++) cudaStreamWaitEvent(side[i], fork_ev, 0);
+  }
+  int rr = 0;
   TqPlanes pl;
   for (int c = 0; c < 3; c++) {
     pl.orig[c] = orig.p[c]; pl.pred[c] = pred.p[c]; pl.rec[c] = rec.p[c];
     pl.lev[c] = lev[c]; pl.lev_pitch[c] = lev_pitch[c];
   }
-#define XVCB_TQ(LW, LH) \
-  if (class_count[LW][LH] > 0) launch_tq_class<LW, LH>(s, d_cus, d_tu_list + class_offset[LW][LH], class_count[LW][LH], p, pl, d_res);
+#define XVCB_TQ(LW, LH)                                                                                              \
+  if (class_count[LW][LH] > 0)                                                                                     \
+    launch_tq_class<LW, LH>(n_side > 0 ? side[rr++ % n_side] : s, d_cus, d_tu_list + class_offset[LW][LH],          \
+                            class_count[LW][LH], p, pl, d_res);
 #define XVCB_TQ_ROW(LW) XVCB_TQ(LW, 1) XVCB_TQ(LW, 2) XVCB_TQ(LW, 3) XVCB_TQ(LW, 4) XVCB_TQ(LW, 5) XVCB_TQ(LW, 6)
-  XVCB_TQ_ROW(1) XVCB_TQ_ROW(2) XVCB_TQ_ROW(3) XVCB_TQ_ROW(4) XVCB_TQ_ROW(5) XVCB_TQ_ROW(6)
+  // largest transforms first: they have the longest critical path
+  XVCB_TQ_ROW(6) XVCB_TQ_ROW(5) XVCB_TQ_ROW(4) XVCB_TQ_ROW(3) XVCB_TQ_ROW(2) XVCB_TQ_ROW(1)
 #undef XVCB_TQ_ROW
 #undef XVCB_TQ
+  for (int i = 0; i < n_side; i++) {
+    cudaEventRecord(side_ev[i], side[i]);
+    cudaStreamWaitEvent(s, side_ev[i], 0);
+  }
   return cudaGetLastError();
 }
 

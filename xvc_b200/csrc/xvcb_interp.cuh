@@ -54,8 +54,9 @@ __device__ __forceinline__ void fir_pass(int w, int h, int bitdepth, const Taps 
   int shift, offset;
   filter_shift_offset(kSrcShort, kDstSample, bitdepth, shift, offset);
   const int maxv = (1 << bitdepth) - 1;
+  const int lw = 31 - __clz(w);                      // block widths are powers of two
   for (int i = tid; i < w * h; i += nthreads) {
-    const int y = i / w, x = i - y * w;
+    const int y = i >> lw, x = i & (w - 1);
     const ST *p = src + y * ss + x - (NTAPS / 2 - 1) * step;
     int sum = 0;
 #pragma unroll
@@ -81,8 +82,9 @@ __device__ __forceinline__ void interp_cta(int w, int h, int bitdepth, int fx, i
   const int chroma = NTAPS == 4;
   if (fx == 0 && fy == 0) {
     const int shift = 14 - bitdepth;
+    const int lw = 31 - __clz(w);
     for (int i = tid; i < w * h; i += nthreads) {
-      const int y = i / w, x = i - y * w;
+      const int y = i >> lw, x = i & (w - 1);
       const Sample s = ref[y * rs + x];
       if (BIPRED) pred[y * ps + x] = (PT)(int16_t)((int16_t)(s << shift) - (int16_t)8192);   // FilterCopyBipred_c, cc:1462-1473
       else pred[y * ps + x] = (PT)s;

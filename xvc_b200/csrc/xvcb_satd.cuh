@@ -28,15 +28,15 @@ template <int TW, int TH> __device__ __forceinline__ int satd_norm(int s) {
 // SATD (before the >> (bitdepth-8)); the caller reduces over threads.
 template <int TW, int TH, class Diff>
 __device__ __forceinline__ unsigned satd_partial(Diff diff, int w, int h, int tid, int nthreads) {
-  const int tiles_x = w / TW;
-  const int total = tiles_x * h;   // tile rows in the block
+  const int ltx = 31 - __clz(w / TW);   // log2(tiles per block row); all dimensions are powers of two
+  const int total = (w / TW) * h;       // tile rows in the block
   const int lane = tid & 31;
   unsigned acc = 0;
   for (int g0 = 0; g0 < total; g0 += nthreads) {
     const int g = g0 + tid;
     const bool active = g < total;
-    const int tile = g / TH, r = g % TH;
-    const int tx = (tile % tiles_x) * TW, ty = (tile / tiles_x) * TH + r;
+    const int tile = g / TH, r = g % TH;   // TH is a compile-time power of two
+    const int tx = (tile & ((1 << ltx) - 1)) * TW, ty = (tile >> ltx) * TH + r;
     int v[TW];
 #pragma unroll
     for (int i = 0; i < TW; i++) v[i] = active ? diff(tx + i, ty) : 0;
