@@ -357,7 +357,15 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int *d_groups = nullptr; int groups_cap = 0;       // pairs {first, count}
   uint8_t *d_tz_states = nullptr; int tz_states_cap = 0;
   int *d_counter = nullptr;
+  int *d_order = nullptr; int order_cap = 0;          // job indices, largest blocks first
   int pipeline_groups_nl = 0, pipeline_n_groups = 0;   // cached grouping of the picture pipeline's job list
+  // successive-elimination support: 8-sample segment sums of every slot's luma plane, survivor pool
+  std::vector<PlaneView> h_luma_views;
+  std::vector<Sample *> h_s8_base;
+  uint8_t *d_s8_arena = nullptr;
+  PlaneView *d_s8_views = nullptr;
+  uint16_t *d_pool = nullptr;
+  int pool_cap = 1 << 16, pool_ctas = 0;
   // side streams for independent launches inside one stage (T/Q shape classes)
   static constexpr int kSide = 6;
   cudaStream_t side[kSide] = {nullptr};
@@ -444,6 +452,23 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
       c->ex.n_side = i + 1;
     }
   }
+  {   // 8-sample segment sums of every slot's luma plane (same geometry as the plane itself)
+    std::vector<PlaneView> s8v(num_slots);
+    c->ex.h_luma_views = views;
+    c->ex.h_s8_base.resize(num_slots);
+    if (!c->check(cudaMalloc(&c->ex.d_s8_arena, plane_bytes[0] * num_slots), "cudaMalloc(s8)") ||
+        !c->check(cudaMalloc(&c->ex.d_s8_views, sizeof(PlaneView) * num_slots), "cudaMalloc(s8 views)")) {
+      int st = c->status; xvcb200_ctx_destroy(c); return st;
+    }
+    for (int s = 0; s < num_slots; s++) {
+      s8v[s] = views[s];
+      s8v[s].base = reinterpret_cast<Sample *>(c->ex.d_s8_arena + (size_t)s * plane_bytes[0]) +
+                    (size_t)c->geom.margin_y[0] * c->geom.pitch[0] + c->geom.margin_x[0];
+      c->ex.h_s8_base[s] = s8v[s].base;
+    }
+    cudaMemcpyAsync(c->ex.d_s8_views, s8v.data(), sizeof(PlaneView) * num_slots, cudaMemcpyHostToDevice, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
   c->map_w = width >> 2; c->map_h = height >> 2;
   const size_t cells = (size_t)c->map_w * c->map_h;
   if (!c->check(cudaMalloc(&c->ex.d_luma_views, sizeof(PlaneView) * num_slots), "cudaMalloc(views)") ||
@@ -467,6 +492,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->d_cus); cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
   cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  cudaFree(c->ex.d_order); cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
@@ -605,12 +631,12 @@ int xvcb200_get_cus(xvcb200_ctx *c, xvcb200_cu *cus, int n) {
 
 }  // extern "C"
 
-namespace xvcb { size_t tz_state_bytes(); }
+namespace xvcb { size_t tz_state_bytes(); int tz_max_ctas(); }
 
 // Groups search jobs by (reference slot, CTU of the CU) and uploads the index + group arrays.
 // key(i) must be cheap; jobs of one group end up adjacent in job_index, in their original order.
-template <class KeyOf, class JobOf>
-static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of) {
+template <class KeyOf, class JobOf, class AreaOf>
+static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of, AreaOf area_of) {
   std::vector<std::pair<long long, int>> order((size_t)n_jobs);
   for (int i = 0; i < n_jobs; i++) order[(size_t)i] = std::make_pair(key_of(i), job_of(i));
   std::stable_sort(order.begin(), order.end(), [](const std::pair<long long, int> &a, const std::pair<long long, int> &b) { return a.first < b.first; });
@@ -621,14 +647,23 @@ static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of) 
     groups.back()++;
   }
   const int n_groups = (int)groups.size() / 2;
-  if (!ensure(c, &c->ex.d_job_index, &c->ex.job_index_cap, n_jobs) || !ensure(c, &c->ex.d_groups, &c->ex.groups_cap, 2 * n_groups))
+  std::vector<int> by_size((size_t)n_jobs);
+  for (int i = 0; i < n_jobs; i++) by_size[(size_t)i] = i;
+  std::stable_sort(by_size.begin(), by_size.end(), [&](int x, int y) { return area_of(x) > area_of(y); });
+  if (!ensure(c, &c->ex.d_job_index, &c->ex.job_index_cap, n_jobs) || !ensure(c, &c->ex.d_groups, &c->ex.groups_cap, 2 * n_groups) ||
+      !ensure(c, &c->ex.d_order, &c->ex.order_cap, n_jobs))
     return -1;
+  if (!c->ex.d_pool) {
+    c->ex.pool_ctas = xvcb::tz_max_ctas();
+    if (!c->check(cudaMalloc(&c->ex.d_pool, sizeof(uint16_t) * (size_t)c->ex.pool_cap * c->ex.pool_ctas), "cudaMalloc(pool)")) return -1;
+  }
   int st_cap_elems = c->ex.tz_states_cap;
   if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return -1;
   c->ex.tz_states_cap = st_cap_elems;
   if (!c->ex.d_counter && !c->check(cudaMalloc(&c->ex.d_counter, sizeof(int)), "cudaMalloc(counter)")) return -1;
   // synchronous copies: the vectors die at return
-  if (!c->check(cudaMemcpyAsync(c->ex.d_job_index, index.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz index") ||
+  if (!c->check(cudaMemcpyAsync(c->ex.d_order, by_size.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz order") ||
+      !c->check(cudaMemcpyAsync(c->ex.d_job_index, index.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz index") ||
       !c->check(cudaMemcpyAsync(c->ex.d_groups, groups.data(), sizeof(int) * groups.size(), cudaMemcpyHostToDevice, c->stream), "tz groups") ||
       !c->check(cudaStreamSynchronize(c->stream), "tz groups sync"))
     return -1;
@@ -657,12 +692,19 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
         const xvcb200_cu &u = c->ex.h_cus[(size_t)jobs[i].cu];
         return ((long long)jobs[i].ref_slot << 40) | ((long long)jobs[i].search_range << 28) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
       },
-      [](int i) { return i; });
+      [](int i) { return i; },
+      [&](int i) { const xvcb200_cu &u = c->ex.h_cus[(size_t)jobs[i].cu]; return (int)u.w * u.h; });
   if (n_groups < 0) return c->status;
   c->ex.pipeline_groups_nl = 0;
+  std::vector<int> ref_list;
+  for (int i = 0; i < n; i++)
+    if (std::find(ref_list.begin(), ref_list.end(), jobs[i].ref_slot) == ref_list.end()) ref_list.push_back(jobs[i].ref_slot);
+  const int margin[2] = {c->geom.margin_x[0], c->geom.margin_y[0]};
   c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
                             c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
-                            n_groups, c->ex.d_tz_states, c->ex.d_counter), "tz_search");
+                            n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_order, c->ex.d_s8_views,
+                            c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), ref_list.data(), (int)ref_list.size(), margin,
+                            c->ex.d_pool, c->ex.pool_cap), "tz_search");
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
                                 c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");
   c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "me results");
@@ -814,7 +856,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
           const xvcb200_cu &u = c->ex.h_cus[(size_t)(i / nl)];
           return ((long long)(i % nl) << 40) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
         },
-        [](int i) { return i; });
+        [](int i) { return i; },
+        [&](int i) { const xvcb200_cu &u = c->ex.h_cus[(size_t)(i / nl)]; return (int)u.w * u.h; });
     if (ng < 0) return c->status;
     c->ex.pipeline_groups_nl = nl;
     c->ex.pipeline_n_groups = ng;
@@ -824,9 +867,15 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   mark();   // 0: start
   c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
   mark();   // 1: jobs built
-  c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                            c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
-                            c->ex.pipeline_n_groups, c->ex.d_tz_states, c->ex.d_counter), "tz_search");
+  {
+    const int margin[2] = {c->geom.margin_x[0], c->geom.margin_y[0]};
+    const int n_ref = (nl == 2 && slots[1] != slots[0]) ? 2 : 1;
+    c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
+                              c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
+                              c->ex.pipeline_n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_order, c->ex.d_s8_views,
+                              c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), slots, n_ref, margin, c->ex.d_pool,
+                              c->ex.pool_cap), "tz_search");
+  }
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
                                 c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");

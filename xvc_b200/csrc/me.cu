@@ -54,6 +54,7 @@ __device__ __forceinline__ uint32_t sad_rows(const uint32_t *rp, int ref_row_wor
                                              int nrows, int shift) {
   constexpr int PW = 1 << LPW;
   uint32_t total = 0;
+#pragma unroll 4
   for (int r = 0; r < nrows; r++) {
     uint32_t prev = GLOBAL ? __ldg(rp) : rp[0];
 #pragma unroll
@@ -345,13 +346,15 @@ __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, ui
 // Phase 1 (which = 1) or phase 3 (which = 3) of every job: one warp per job.
 constexpr int kRoundWarps = 4;
 __global__ void __launch_bounds__(kRoundWarps * 32)
-tz_rounds_kernel(int which, const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
-                 int bitdepth, uint32_t lambda, PlaneView orig, const PlaneView *__restrict__ ref_planes,
-                 xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states) {
+tz_rounds_kernel(int which, const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
+                 const int *__restrict__ order, int n, int bitdepth, uint32_t lambda, PlaneView orig,
+                 const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res,
+                 TzJobState *__restrict__ states) {
   __shared__ uint32_t s_orig[kRoundWarps][32 * 33];     // up to 32 rows x (32 pairs + 1 pad word)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ji = blockIdx.x * kRoundWarps + warp;
-  if (ji >= n) return;
+  const int slot = blockIdx.x * kRoundWarps + warp;
+  if (slot >= n) return;
+  const int ji = order[slot];                           // largest blocks first (longest jobs start first)
   const xvcb200_me_job job = jobs[ji];
   const xvcb200_cu cu = cus[job.cu];
   const PlaneView ref = ref_planes[job.ref_slot];
@@ -381,151 +384,310 @@ tz_rounds_kernel(int which, const xvcb200_cu *__restrict__ cus, const xvcb200_me
   }
 }
 
+// S8[y][x] = sum of the 8 reference samples x..x+7 of row y, for every position of the padded
+// plane: the segment sums of the successive-elimination bound below.  <= 8 * 4095: fits uint16.
+__global__ void segment_sum_kernel(PlaneView src, Sample *__restrict__ dst00, int x_begin, int x_end, int y_begin,
+                                   int y_end) {
+  const int x = x_begin + (blockIdx.x * blockDim.x + threadIdx.x) * 8;   // 8 outputs per thread, sliding window
+  const int y = y_begin + blockIdx.y;
+  if (x >= x_end || y >= y_end) return;
+  const Sample *p = src.base + y * src.pitch + x;
+  Sample *d = dst00 + y * src.pitch + x;
+  int win = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) win += p[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (x + i < x_end) d[i] = (Sample)win;
+    win += (int)p[i + 8] - (int)p[i];
+  }
+}
+
+// stages the box [rx0, rx0 + 8*cpr) x [ry0, ry0 + bh) of a plane into shared memory rows of `spw` words
+__device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int rx0, int ry0, int bh, int cpr, int spw,
+                                          uint32_t *s_region, int tid, int nthreads) {
+  const int total = bh * cpr;
+  for (int idx0 = tid; idx0 < total; idx0 += 4 * nthreads) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {            // four independent 16-byte loads in flight per thread
+      const int idx = idx0 + u * nthreads;
+      if (idx < total) {
+        const int row = idx / cpr, ch = idx - row * cpr;
+        v[u] = __ldg(reinterpret_cast<const uint4 *>(plane00 + (ry0 + row) * pitch + rx0) + ch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int idx = idx0 + u * nthreads;
+      if (idx < total) {
+        const int row = idx / cpr, ch = idx - row * cpr;
+        uint32_t *d = s_region + row * spw + ch * 4;
+        const int left = spw - ch * 4;
+        d[0] = v[u].x;
+        if (left > 1) d[1] = v[u].y;
+        if (left > 2) d[2] = v[u].z;
+        if (left > 3) d[3] = v[u].w;
+      }
+    }
+  }
+}
+
+// Lower bound of the SAD of one candidate from 8-sample segment sums: NSEG segments per row,
+// `rp` = S8 at the candidate's first row/column (uint16), seg = segment sums of the original
+// block, two per word for NSEG >= 2.  VABSDIFF.U32 does |a - b| + c in one instruction.
+template <int NSEG>
+__device__ __forceinline__ uint32_t seg_bound(const uint16_t *rp, int row_stride, const uint32_t *seg, int rows) {
+  uint32_t lb = 0;
+  if (NSEG == 1) {
+    const uint16_t *s16 = reinterpret_cast<const uint16_t *>(seg);
+#pragma unroll 4
+    for (int r = 0; r < rows; r++) lb = __usad((unsigned)rp[r * row_stride], (unsigned)s16[r], lb);
+  } else {
+#pragma unroll 2
+    for (int r = 0; r < rows; r++) {
+#pragma unroll
+      for (int k = 0; k < NSEG; k += 2) {
+        const uint32_t a2 = seg[(r * NSEG + k) >> 1];
+        lb = __usad((unsigned)rp[k * 8], a2 & 0xffffu, lb);
+        lb = __usad((unsigned)rp[k * 8 + 8], a2 >> 16, lb);
+      }
+      rp += row_stride;
+    }
+  }
+  return lb;
+}
+
 constexpr int kTzThreads = 512;
 constexpr int kTzWarps = kTzThreads / 32;
+constexpr int kMaxGroupJobs = 256;       // jobs handled per pass over a group
 
 struct TzGroup { int first, count; };    // run of entries in job_index: jobs sharing a reference picture and a CTU
 
 // Raster scan of TzSearch::Search (inter_tz_search.cc:145-155) for every job that needs it.
-// One persistent CTA per SM.  Per job group (jobs of one CTU on one reference picture): the
-// bounding box of the jobs' scan windows is staged in shared memory once; then every job is
-// scanned CTA-wide with ONE CANDIDATE PER LANE: a warp takes one grid column (fixed x, so the
-// alignment shift is warp-uniform) and 32 grid rows (5 picture rows apart; the odd row pitch of
-// the staged box makes those 32 rows fall into 32 distinct banks).  No shuffles or reductions in
-// the inner loop; the per-lane winners meet once per job.
+// One persistent CTA per SM.  Per job group (jobs of one CTU on one reference picture) the
+// bounding box of the jobs' scan windows is staged in shared memory, and jobs are scanned
+// CTA-wide with ONE CANDIDATE PER LANE: a warp takes one grid column (fixed x, so the alignment
+// is warp-uniform) and 32 grid rows (5 picture rows apart; the odd row pitch of the staged box
+// makes those 32 rows fall into 32 distinct banks).  No shuffles in the inner loops.
+//
+// Successive elimination (exact).  For every candidate a lower bound of its SAD is computed
+// first from 8-sample segment sums:  sum_rows sum_k | A8[r][k] - S8[y + r][x + 8k] |  <=  SAD
+// (triangle inequality per segment), hence bound_cost = scale(bound) + rate <= cost.  A
+// candidate can only replace the incoming best if cost < cost_in (strict compare of
+// CheckCostBest, :266), so candidates with bound_cost >= cost_in are dropped without changing
+// the result.  Pass 1 stages the S8 box and writes the surviving candidate indices of every
+// job to a per-CTA pool; pass 2 stages the sample box and evaluates the survivors exactly.
 __global__ void __launch_bounds__(kTzThreads, 1)
 tz_raster_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
                  const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
                  int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
-                 const PlaneView *__restrict__ ref_planes, TzJobState *__restrict__ states, int region_budget_words) {
+                 const PlaneView *__restrict__ ref_planes, const PlaneView *__restrict__ s8_planes,
+                 TzJobState *__restrict__ states, int region_budget_words, uint16_t *__restrict__ pool_all,
+                 int pool_cap, unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t *s_orig = smem;                       // 1024 words: original block of the job being scanned
+  long long t_mark = prof ? clock64() : 0;
+  auto lap = [&](int slot) {     // optional phase timing (XVCB_TZ_PROF=1): cycles of thread 0, summed over CTAs
+    if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&prof[slot], (unsigned long long)(now - t_mark)); t_mark = now; }
+  };
+  uint32_t *s_orig = smem;                       // 1024 words: original block (pairs) / its segment sums
   uint32_t *s_region = smem + 1024;
-  __shared__ int s_group, s_box[4];
+  __shared__ int s_group, s_box[4], s_count, s_pool_used;
+  __shared__ int s_list_off[kMaxGroupJobs], s_list_cnt[kMaxGroupJobs];   // -1: dense scan (no list)
   __shared__ unsigned long long s_red[kTzWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint16_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
 
   for (;;) {
     __syncthreads();                             // previous group is completely done with shared memory
-    if (tid == 0) {
-      s_group = atomicAdd(counter, 1);
-      s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
-    }
+    if (tid == 0) s_group = atomicAdd(counter, 1);
     __syncthreads();
     const int grp = s_group;
     if (grp >= n_groups) break;
     const TzGroup G = groups[grp];
-    const PlaneView ref = ref_planes[jobs[job_index[G.first]].ref_slot];
+    const int ref_slot = jobs[job_index[G.first]].ref_slot;
+    const PlaneView ref = ref_planes[ref_slot];
+    const PlaneView s8 = s8_planes[ref_slot];
 
-    // bounding box of the scan windows (block extent included) of the jobs that scan
-    for (int k = tid; k < G.count; k += kTzThreads) {
-      const int ji = job_index[G.first + k];
-      const TzJobState *st = &states[ji];
-      if (!st->need_raster || st->shi[0] < st->slo[0] || st->shi[1] < st->slo[1]) continue;
-      const xvcb200_cu cu = cus[jobs[ji].cu];
-      atomicMin(&s_box[0], cu.x + st->slo[0]); atomicMin(&s_box[1], cu.y + st->slo[1]);
-      atomicMax(&s_box[2], cu.x + st->shi[0] + cu.w); atomicMax(&s_box[3], cu.y + st->shi[1] + cu.h);
-    }
-    __syncthreads();
-    if (s_box[2] < s_box[0]) continue;           // no job of this group scans
-    const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
-    const int bw = rx1 - rx0, bh = ry1 - ry0;
-    const int spw = ((bw + 1) / 2 + 1) | 1;
-    const bool staged = (long long)spw * bh <= region_budget_words;
-    if (staged) {     // 16-byte global loads (rx0 is a multiple of 8 samples), 4-byte shared stores
-      const int cpr = (bw + 7) >> 3, total = bh * cpr;
-      for (int idx0 = tid; idx0 < total; idx0 += 4 * kTzThreads) {
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {            // four independent loads in flight per thread
-          const int idx = idx0 + u * kTzThreads;
-          if (idx < total) {
-            const int row = idx / cpr, ch = idx - row * cpr;
-            v[u] = __ldg(reinterpret_cast<const uint4 *>(ref.base + (ry0 + row) * ref.pitch + rx0) + ch);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int idx = idx0 + u * kTzThreads;
-          if (idx < total) {
-            const int row = idx / cpr, ch = idx - row * cpr;
-            uint32_t *d = s_region + row * spw + ch * 4;
-            const int left = spw - ch * 4;
-            d[0] = v[u].x;
-            if (left > 1) d[1] = v[u].y;
-            if (left > 2) d[2] = v[u].z;
-            if (left > 3) d[3] = v[u].w;
-          }
-        }
-      }
-    }
-    __syncthreads();
-
-    for (int k = 0; k < G.count; k++) {
-      const int ji = job_index[G.first + k];
-      TzJobState *stp = &states[ji];
-      if (!stp->need_raster) continue;           // uniform: every thread reads the same word
-      const xvcb200_me_job job = jobs[ji];
-      const xvcb200_cu cu = cus[job.cu];
-      const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
-      const int slox = stp->slo[0], sloy = stp->slo[1], shix = stp->shi[0], shiy = stp->shi[1];
-      const uint32_t cost_in = stp->cost;
-      const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
-      const bool nonempty = shix >= slox && shiy >= sloy;
-      // original block -> shared memory as packed pairs [row][pair]
-      const int pw = 1 << g.lpw;
-      for (int q = tid; q < (g.rows << g.lpw); q += kTzThreads) {
-        const int row = q >> g.lpw, col = q & (pw - 1);
-        s_orig[q] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
+    for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
+      const int kn = min(kMaxGroupJobs, G.count - k0);
+      __syncthreads();
+      if (tid == 0) { s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30); s_pool_used = 0; }
+      __syncthreads();
+      // bounding box of the scan windows (block extent included) of the jobs that scan
+      for (int k = tid; k < kn; k += kTzThreads) {
+        const int ji = job_index[G.first + k0 + k];
+        const TzJobState *st = &states[ji];
+        s_list_off[k] = -1; s_list_cnt[k] = 0;
+        if (!st->need_raster || st->shi[0] < st->slo[0] || st->shi[1] < st->slo[1]) continue;
+        const xvcb200_cu cu = cus[jobs[ji].cu];
+        atomicMin(&s_box[0], cu.x + st->slo[0]); atomicMin(&s_box[1], cu.y + st->slo[1]);
+        atomicMax(&s_box[2], cu.x + st->shi[0] + cu.w); atomicMax(&s_box[3], cu.y + st->shi[1] + cu.h);
       }
       __syncthreads();
-      uint32_t best_cost = 0xffffffffu, best_t = 0;
-      if (nonempty) {
-        const int passes = (ny + 31) >> 5;
-        for (int task = warp; task < nx * passes; task += kTzWarps) {
-          const int i = task % nx, j = (task / nx) * 32 + lane;
-          const int jj = min(j, ny - 1);             // idle lanes recompute the last row (no stray reads)
-          const int cx = slox + 5 * i, cy = sloy + 5 * jj;
-          uint32_t sad;
-          if (staged) {
-            const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
-            sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, s_orig, pw, g.rows, (ox & 1) << 4);
-          } else {                                    // window too large for shared memory: same walk from global memory
-            const int X = g.x + cx;
-            const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
-            sad = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, s_orig, pw,
-                                     g.rows, (X & 1) << 4);
+      if (s_box[2] < s_box[0]) continue;           // no job of this chunk scans
+      const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
+      const int bw = rx1 - rx0, bh = ry1 - ry0;
+      const int spw = ((bw + 1) / 2 + 1) | 1;
+      const int cpr = (bw + 7) >> 3;
+      const bool staged = (long long)spw * bh <= region_budget_words;
+
+      // ---------------- pass 1: segment-sum bound, survivors -> pool
+      lap(0);
+      if (staged && s8.base != nullptr) {
+        stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+        __syncthreads();
+        lap(1);
+        const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
+        uint16_t *s_seg = reinterpret_cast<uint16_t *>(s_orig);      // [rows][w/8]
+        for (int k = 0; k < kn; k++) {
+          const int ji = job_index[G.first + k0 + k];
+          const TzJobState *stp = &states[ji];
+          if (!stp->need_raster) continue;           // uniform
+          const xvcb200_me_job job = jobs[ji];
+          const xvcb200_cu cu = cus[job.cu];
+          if (cu.w < 8) continue;                    // no 8-sample segments: dense scan in pass 2
+          const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+          const int slox = stp->slo[0], sloy = stp->slo[1], shix = stp->shi[0], shiy = stp->shi[1];
+          const uint32_t cost_in = stp->cost;
+          const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
+          const int lsg = g.lpw - 2, nseg = 1 << lsg;                // segments per row
+          for (int q = tid; q < (g.rows << lsg); q += kTzThreads) {
+            const int row = q >> lsg, sg = q & (nseg - 1);
+            const Sample *p = orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + sg * 8;
+            int sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sum += p[i];
+            s_seg[q] = (uint16_t)sum;
           }
-          if (j < ny) {
+          if (tid == 0) s_count = 0;
+          __syncthreads();
+          const int base = s_pool_used;
+          const int room = pool_cap - base;
+          const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
+          const int rstride = g.rstep * 2 * spw;
+          for (int j0 = 0; j0 < ny; j0 += 32) {
+            const int j = j0 + lane, jj = min(j, ny - 1);
+            const int cy = sloy + 5 * jj, oy = g.y + cy - ry0;
+            const uint32_t bits_y = exp_golomb_bits((cy * 16 - g.mvpy) >> (g.down + 2));
+            for (int i = warp; i < nx; i += kTzWarps) {
+              const int cx = slox + 5 * i, ox = g.x + cx - rx0;
+              const uint16_t *rp = s8reg + oy * (2 * spw) + ox;
+              uint32_t lb = 0;
+              switch (lsg) {
+                case 0: lb = seg_bound<1>(rp, rstride, seg32, g.rows); break;
+                case 1: lb = seg_bound<2>(rp, rstride, seg32, g.rows); break;
+                case 2: lb = seg_bound<4>(rp, rstride, seg32, g.rows); break;
+                default: lb = seg_bound<8>(rp, rstride, seg32, g.rows); break;
+              }
+              const uint32_t lbd = g.fast ? (lb * 2) >> g.bd_shift : lb >> g.bd_shift;
+              const uint32_t bits = bits_y + exp_golomb_bits((cx * 16 - g.mvpx) >> (g.down + 2));
+              const bool keep = j < ny && lbd + ((g.lambda * bits) >> 16) < cost_in;
+              const unsigned mask = __ballot_sync(XVCB_FULL, keep);
+              if (mask) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
+                wbase = __shfl_sync(XVCB_FULL, wbase, 0);
+                const int slot = wbase + __popc(mask & ((1u << lane) - 1));
+                if (keep && slot < room) pool[base + slot] = (uint16_t)(j * nx + i);
+              }
+            }
+          }
+          __syncthreads();
+          if (tid == 0) {
+            if (s_count <= room && nx * ny <= 65536) { s_list_off[k] = base; s_list_cnt[k] = s_count; s_pool_used = base + s_count; }
+            if (prof) { atomicAdd(&prof[6], (unsigned long long)(nx * ny)); atomicAdd(&prof[7], (unsigned long long)s_count); }
+          }
+          __syncthreads();
+        }
+      }
+
+      // ---------------- pass 2: exact SAD of the survivors (or of every candidate: dense scan)
+      __syncthreads();
+      lap(2);
+      if (staged) stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+      __syncthreads();
+      lap(3);
+      for (int k = 0; k < kn; k++) {
+        const int ji = job_index[G.first + k0 + k];
+        TzJobState *stp = &states[ji];
+        if (!stp->need_raster) continue;           // uniform: every thread reads the same word
+        const xvcb200_me_job job = jobs[ji];
+        const xvcb200_cu cu = cus[job.cu];
+        const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
+        const int slox = stp->slo[0], sloy = stp->slo[1], shix = stp->shi[0], shiy = stp->shi[1];
+        const uint32_t cost_in = stp->cost;
+        const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
+        const bool nonempty = shix >= slox && shiy >= sloy;
+        const int list_off = s_list_off[k], list_cnt = s_list_cnt[k];
+        // original block -> shared memory as packed pairs [row][pair]
+        const int pw = 1 << g.lpw;
+        for (int q = tid; q < (g.rows << g.lpw); q += kTzThreads) {
+          const int row = q >> g.lpw, col = q & (pw - 1);
+          s_orig[q] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
+        }
+        __syncthreads();
+        uint32_t best_cost = 0xffffffffu, best_t = 0;
+        if (nonempty && list_off >= 0) {             // survivors: arbitrary grid positions per lane
+          for (int e = tid; e < list_cnt; e += kTzThreads) {
+            const uint32_t t = pool[list_off + e];
+            const int j = (int)t / nx, i = (int)t - j * nx;
+            const int cx = slox + 5 * i, cy = sloy + 5 * j;
+            const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
+            const uint32_t sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, s_orig, pw,
+                                                     g.rows, (ox & 1) << 4);
             const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
             const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-            const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
             if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
           }
+        } else if (nonempty) {                       // dense scan
+          const int passes = (ny + 31) >> 5;
+          for (int task = warp; task < nx * passes; task += kTzWarps) {
+            const int i = task % nx, j = (task / nx) * 32 + lane;
+            const int jj = min(j, ny - 1);             // idle lanes recompute the last row (no stray reads)
+            const int cx = slox + 5 * i, cy = sloy + 5 * jj;
+            uint32_t sad;
+            if (staged) {
+              const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
+              sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, s_orig, pw, g.rows, (ox & 1) << 4);
+            } else {                                    // window too large for shared memory: same walk from global memory
+              const int X = g.x + cx;
+              const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
+              sad = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, s_orig, pw,
+                                       g.rows, (X & 1) << 4);
+            }
+            if (j < ny) {
+              const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
+              const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+              const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
+              if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+            }
+          }
         }
-      }
-      unsigned long long key = ((unsigned long long)best_cost << 32) | best_t;
+        unsigned long long key = ((unsigned long long)best_cost << 32) | best_t;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(XVCB_FULL, key, off);
-        key = other < key ? other : key;
-      }
-      if (lane == 0) s_red[warp] = key;
-      __syncthreads();
-      if (tid == 0) {
-        unsigned long long m = s_red[0];
-        for (int w2 = 1; w2 < kTzWarps; w2++) m = s_red[w2] < m ? s_red[w2] : m;
-        const uint32_t c = (uint32_t)(m >> 32), t = (uint32_t)m;
-        if (nonempty && c < cost_in) {             // strict: ties keep the earlier best (:266-268)
-          stp->cost = c;
-          stp->bx = slox + 5 * (int)(t % nx);
-          stp->by = sloy + 5 * (int)(t / nx);
+        for (int off = 16; off > 0; off >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(XVCB_FULL, key, off);
+          key = other < key ? other : key;
         }
-        stp->last_range = 5;
-        if (nonempty) stp->evals += nx * ny;
-        stp->need_raster = 0;
+        if (lane == 0) s_red[warp] = key;
+        __syncthreads();
+        if (tid == 0) {
+          unsigned long long m = s_red[0];
+          for (int w2 = 1; w2 < kTzWarps; w2++) m = s_red[w2] < m ? s_red[w2] : m;
+          const uint32_t c = (uint32_t)(m >> 32), t = (uint32_t)m;
+          if (nonempty && c < cost_in) {             // strict: ties keep the earlier best (:266-268)
+            stp->cost = c;
+            stp->bx = slox + 5 * (int)(t % nx);
+            stp->by = sloy + 5 * (int)(t / nx);
+          }
+          stp->last_range = 5;
+          if (nonempty) stp->evals += nx * ny;
+          stp->need_raster = 0;
+        }
+        __syncthreads();
       }
-      __syncthreads();
+      lap(4);
     }
   }
 }
@@ -591,7 +753,10 @@ __global__ void __launch_bounds__(128) subpel_kernel(const xvcb200_cu *__restric
 
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
-                             const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter) {
+                             const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
+                             const int *d_order, const PlaneView *d_s8_planes, const PlaneView *h_ref_planes,
+                             Sample *const *h_s8_base, const int *ref_slots, int n_ref_slots, const int margin[2],
+                             uint16_t *d_pool, int pool_cap) {
   if (n <= 0 || n_groups <= 0) return cudaSuccess;
   static int smem_bytes = 0, num_sms = 0;
   if (!smem_bytes) {
@@ -610,14 +775,34 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   TzJobState *st = static_cast<TzJobState *>(d_states);
   const int blocks = (n + kRoundWarps - 1) / kRoundWarps;
   g_launch_count += 3;
-  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(1, d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
-  tz_raster_kernel<<<n_groups < num_sms ? n_groups : num_sms, kTzThreads, smem_bytes, s>>>(
+  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(1, d_cus, d_jobs, d_order, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
+  // segment sums of the reference pictures this launch searches (rows/columns the windows can touch)
+  for (int i = 0; i < n_ref_slots; i++) {
+    const PlaneView rv = h_ref_planes[ref_slots[i]];
+    const int x0 = -margin[0], x1 = rv.width + margin[0] - 8, y0 = -margin[1], y1 = rv.height + margin[1];
+    dim3 grid(((x1 - x0 + 7) / 8 + 127) / 128, y1 - y0);
+    g_launch_count++;
+    segment_sum_kernel<<<grid, 128, 0, s>>>(rv, h_s8_base[ref_slots[i]], x0, x1, y0, y1);
+  }
+  static unsigned long long *prof = nullptr;
+  static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
+  if (want_prof && !prof) cudaMallocManaged(&prof, 8 * sizeof(*prof));
+  if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 8 * sizeof(*prof)); }
+  const int grid = n_groups < num_sms ? n_groups : num_sms;
+  tz_raster_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
       d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
-      d_ref_planes, st, smem_bytes / 4 - 1024);
-  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(3, d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
+      d_ref_planes, d_s8_planes, st, smem_bytes / 4 - 1024, d_pool, pool_cap, want_prof ? prof : nullptr);
+  if (want_prof) {
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[tz raster prof] cycles/CTA: box %.0f stageS8 %.0f bound %.0f stageRef %.0f exact %.0f | candidates %llu survivors %llu (%.2f%%)\n",
+            (double)prof[0] / grid, (double)prof[1] / grid, (double)prof[2] / grid, (double)prof[3] / grid, (double)prof[4] / grid,
+            prof[6], prof[7], 100.0 * (double)prof[7] / (double)(prof[6] ? prof[6] : 1));
+  }
+  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(3, d_cus, d_jobs, d_order, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
   return cudaGetLastError();
 }
 size_t tz_state_bytes() { return sizeof(TzJobState); }
+int tz_max_ctas() { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
 
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
