@@ -364,7 +364,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   std::vector<Sample *> h_s8_base;
   uint8_t *d_s8_arena = nullptr;
   PlaneView *d_s8_views = nullptr;
-  uint16_t *d_pool = nullptr;
+  uint32_t *d_pool = nullptr;
   int pool_cap = 1 << 16, pool_ctas = 0;
   // side streams for independent launches inside one stage (T/Q shape classes)
   static constexpr int kSide = 6;
@@ -655,7 +655,7 @@ static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of, 
     return -1;
   if (!c->ex.d_pool) {
     c->ex.pool_ctas = xvcb::tz_max_ctas();
-    if (!c->check(cudaMalloc(&c->ex.d_pool, sizeof(uint16_t) * (size_t)c->ex.pool_cap * c->ex.pool_ctas), "cudaMalloc(pool)")) return -1;
+    if (!c->check(cudaMalloc(&c->ex.d_pool, sizeof(uint32_t) * (size_t)c->ex.pool_cap * c->ex.pool_ctas), "cudaMalloc(pool)")) return -1;
   }
   int st_cap_elems = c->ex.tz_states_cap;
   if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return -1;
@@ -702,7 +702,7 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
   const int margin[2] = {c->geom.margin_x[0], c->geom.margin_y[0]};
   c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
                             c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
-                            n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_order, c->ex.d_s8_views,
+                            n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
                             c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), ref_list.data(), (int)ref_list.size(), margin,
                             c->ex.d_pool, c->ex.pool_cap), "tz_search");
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
@@ -872,7 +872,7 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     const int n_ref = (nl == 2 && slots[1] != slots[0]) ? 2 : 1;
     c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
                               c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
-                              c->ex.pipeline_n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_order, c->ex.d_s8_views,
+                              c->ex.pipeline_n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
                               c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), slots, n_ref, margin, c->ex.d_pool,
                               c->ex.pool_cap), "tz_search");
   }

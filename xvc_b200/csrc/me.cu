@@ -94,9 +94,12 @@ __device__ __forceinline__ uint32_t sad_rows_lpw(int lpw, const uint32_t *rp, in
 // padded by one word so that the G row-interleaved lanes hit distinct banks.
 struct RoundEval {
   const MeGeom &g;
-  const uint32_t *so;        // [rows][PW + 1] packed pairs
+  const uint32_t *so;        // original block as packed pairs; rows visited by the metric are so_row_words apart
+  int so_row_words;
   const Sample *plane;       // sample (0,0) of the reference luma plane (4-byte aligned, even pitch)
   int gpitch;
+  const uint32_t *sm;        // reference box staged in shared memory (rows of spw words), or null
+  int spw, rx0, ry0, rx1, ry1;
   int lane;
 
   __device__ __forceinline__ uint32_t operator()(int cx, int cy, bool valid, int K) const {
@@ -108,10 +111,17 @@ struct RoundEval {
     const bool sv = __shfl_sync(XVCB_FULL, (int)valid, cand) && cand < K;
     uint32_t acc = 0;
     if (sv) {
-      const int X = g.x + sx;
-      const Sample *row0 = plane + (g.y + sy + sub * g.rstep) * gpitch + (X & ~1);
-      acc = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * gpitch << lg) >> 1,
-                               so + sub * ((1 << g.lpw) + 1), ((1 << g.lpw) + 1) << lg, g.rows >> lg, (X & 1) << 4);
+      const int X = g.x + sx, Y = g.y + sy;
+      const uint32_t *op = so + sub * so_row_words;
+      if (sm != nullptr && X >= rx0 && X + g.w <= rx1 && Y >= ry0 && Y + g.h <= ry1) {
+        const int ox = X - rx0, oy = Y - ry0 + sub * g.rstep;
+        acc = sad_rows_lpw<false>(g.lpw, sm + oy * spw + (ox >> 1), (g.rstep * spw) << lg, op, so_row_words << lg,
+                                  g.rows >> lg, (ox & 1) << 4);
+      } else {
+        const Sample *row0 = plane + (Y + sub * g.rstep) * gpitch + (X & ~1);
+        acc = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * gpitch << lg) >> 1, op,
+                                 so_row_words << lg, g.rows >> lg, (X & 1) << 4);
+      }
     }
 #pragma unroll
     for (int off = 4; off > 0; off >>= 1)
@@ -343,47 +353,6 @@ __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, ui
   return g;
 }
 
-// Phase 1 (which = 1) or phase 3 (which = 3) of every job: one warp per job.
-constexpr int kRoundWarps = 4;
-__global__ void __launch_bounds__(kRoundWarps * 32)
-tz_rounds_kernel(int which, const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
-                 const int *__restrict__ order, int n, int bitdepth, uint32_t lambda, PlaneView orig,
-                 const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res,
-                 TzJobState *__restrict__ states) {
-  __shared__ uint32_t s_orig[kRoundWarps][32 * 33];     // up to 32 rows x (32 pairs + 1 pad word)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slot = blockIdx.x * kRoundWarps + warp;
-  if (slot >= n) return;
-  const int ji = order[slot];                           // largest blocks first (longest jobs start first)
-  const xvcb200_me_job job = jobs[ji];
-  const xvcb200_cu cu = cus[job.cu];
-  const PlaneView ref = ref_planes[job.ref_slot];
-  const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
-  if (which == 3 && states[ji].last_range <= 0) {       // nothing to refine: result = state
-    if (lane == 0) {
-      res[ji].mv_fullpel[0] = states[ji].bx; res[ji].mv_fullpel[1] = states[ji].by;
-      res[ji].cost_fullpel = states[ji].cost; res[ji].num_sad = states[ji].evals;
-    }
-    return;
-  }
-  uint32_t *so = s_orig[warp];
-  const int pw = 1 << g.lpw;
-  for (int q = lane; q < (g.rows << g.lpw); q += 32) {
-    const int row = q >> g.lpw, col = q & (pw - 1);
-    so[row * (pw + 1) + col] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
-  }
-  __syncwarp();
-  const RoundEval ev{g, so, ref.base, ref.pitch, lane};
-  if (which == 1) {
-    TzJobState st;
-    tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
-    if (lane == 0) states[ji] = st;
-  } else {
-    const TzJobState st = states[ji];
-    tz_phase3(g, job.search_range, ev, lane, st, &res[ji]);
-  }
-}
-
 // S8[y][x] = sum of the 8 reference samples x..x+7 of row y, for every position of the padded
 // plane: the segment sums of the successive-elimination bound below.  <= 8 * 4095: fits uint16.
 __global__ void segment_sum_kernel(PlaneView src, Sample *__restrict__ dst00, int x_begin, int x_end, int y_begin,
@@ -460,43 +429,69 @@ __device__ __forceinline__ uint32_t seg_bound(const uint16_t *rp, int row_stride
 
 constexpr int kTzThreads = 512;
 constexpr int kTzWarps = kTzThreads / 32;
-constexpr int kMaxGroupJobs = 256;       // jobs handled per pass over a group
+constexpr int kMaxGroupJobs = 128;       // jobs handled per pass over a group
+constexpr int kTileWords = 64 * 33;      // original CTU as packed pairs, rows padded to 33 words
+constexpr int kSegWords = 128;           // segment sums of the block being bounded (<= 32 rows x 8)
 
 struct TzGroup { int first, count; };    // run of entries in job_index: jobs sharing a reference picture and a CTU
 
-// Raster scan of TzSearch::Search (inter_tz_search.cc:145-155) for every job that needs it.
-// One persistent CTA per SM.  Per job group (jobs of one CTU on one reference picture) the
-// bounding box of the jobs' scan windows is staged in shared memory, and jobs are scanned
-// CTA-wide with ONE CANDIDATE PER LANE: a warp takes one grid column (fixed x, so the alignment
-// is warp-uniform) and 32 grid rows (5 picture rows apart; the odd row pitch of the staged box
-// makes those 32 rows fall into 32 distinct banks).  No shuffles in the inner loops.
+struct SJob {                            // one job of the current group, in shared memory
+  int ji;
+  short x, y; unsigned char w, h, depth, fullpel;
+  int mvpx, mvpy, prevx, prevy, range;
+  int slox, sloy, nx, ny;                // raster grid (valid when need != 0)
+  uint32_t cost_in;
+  int need;                              // 0: no raster; 1: raster, box staged; 2: raster, window outside the staged box
+  int list_off, list_cnt;                // survivors in the pool; list_off < 0: dense scan
+  unsigned long long key;                // best (cost << 32 | scan position) of the exact pass
+};
+
+__device__ __forceinline__ MeGeom sjob_geom(const SJob &j, int bitdepth, uint32_t lambda) {
+  xvcb200_cu cu;
+  cu.x = j.x; cu.y = j.y; cu.w = j.w; cu.h = j.h; cu.depth = j.depth;
+  cu.flags = j.fullpel ? XVCB200_CU_FULLPEL_MV : 0;
+  return me_geom(cu, bitdepth, lambda, j.mvpx, j.mvpy);
+}
+
+// TzSearch::Search (inter_tz_search.cc:84-171) for job groups.  One persistent CTA per SM takes
+// groups from a counter.  A group = the jobs of one CTU on one reference picture: the bounding
+// box of their search windows and the original CTU are staged in shared memory once and shared
+// by all phases of all its jobs.
 //
-// Successive elimination (exact).  For every candidate a lower bound of its SAD is computed
-// first from 8-sample segment sums:  sum_rows sum_k | A8[r][k] - S8[y + r][x + 8k] |  <=  SAD
-// (triangle inequality per segment), hence bound_cost = scale(bound) + rate <= cost.  A
-// candidate can only replace the incoming best if cost < cost_in (strict compare of
-// CheckCostBest, :266), so candidates with bound_cost >= cost_in are dropped without changing
-// the result.  Pass 1 stages the S8 box and writes the surviving candidate indices of every
-// job to a per-CTA pool; pass 2 stages the sample box and evaluates the survivors exactly.
+//   phase 1   start points + first diamond pass + 2-point step, one warp per job (sub-group
+//             evaluation, see RoundEval), reading the staged box
+//   raster    jobs whose first pass ended far out (last_range > 5) scan the window on the
+//             5-sample grid (:145-155), CTA-wide, ONE CANDIDATE PER LANE: a warp takes one grid
+//             column (fixed x: warp-uniform alignment) and 32 grid rows (5 picture rows apart; the
+//             odd row pitch of the box puts them in 32 distinct banks).
+//             Successive elimination (exact): first a lower bound of every candidate's SAD from
+//             8-sample segment sums,  sum_rows sum_k |A8[r][k] - S8[y+r][x+8k]| <= SAD  (triangle
+//             inequality per segment), hence bound_cost <= cost.  A candidate can only replace
+//             the incoming best if cost < cost_in (strict compare of CheckCostBest, :266), so
+//             candidates with bound_cost >= cost_in are dropped without changing the result.  The
+//             S8 box is staged for the bound pass, survivors go to a per-CTA pool, then the
+//             sample box is staged again and the survivors of all jobs are evaluated exactly in
+//             one flat loop (per-job winners through a 64-bit shared-memory atomicMin).
+//   phase 3   re-centre until the centre wins, one warp per job.
 __global__ void __launch_bounds__(kTzThreads, 1)
-tz_raster_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
+tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
                  const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
                  int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
                  const PlaneView *__restrict__ ref_planes, const PlaneView *__restrict__ s8_planes,
-                 TzJobState *__restrict__ states, int region_budget_words, uint16_t *__restrict__ pool_all,
-                 int pool_cap, unsigned long long *__restrict__ prof) {
+                 xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states, int region_budget_words,
+                 uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t *s_tile = smem;                                   // original CTU, packed pairs, 33 words per row
+  uint16_t *s_seg = reinterpret_cast<uint16_t *>(smem + kTileWords);
+  SJob *s_job = reinterpret_cast<SJob *>(smem + kTileWords + kSegWords);
+  uint32_t *s_region = smem + kTileWords + kSegWords + kMaxGroupJobs * (sizeof(SJob) / 4);
+  __shared__ int s_group, s_box[4], s_next, s_count, s_pool_used, s_any_raster;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
   long long t_mark = prof ? clock64() : 0;
   auto lap = [&](int slot) {     // optional phase timing (XVCB_TZ_PROF=1): cycles of thread 0, summed over CTAs
     if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&prof[slot], (unsigned long long)(now - t_mark)); t_mark = now; }
   };
-  uint32_t *s_orig = smem;                       // 1024 words: original block (pairs) / its segment sums
-  uint32_t *s_region = smem + 1024;
-  __shared__ int s_group, s_box[4], s_count, s_pool_used;
-  __shared__ int s_list_off[kMaxGroupJobs], s_list_cnt[kMaxGroupJobs];   // -1: dense scan (no list)
-  __shared__ unsigned long long s_red[kTzWarps];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint16_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
 
   for (;;) {
     __syncthreads();                             // previous group is completely done with shared memory
@@ -512,182 +507,235 @@ tz_raster_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
       const int kn = min(kMaxGroupJobs, G.count - k0);
       __syncthreads();
-      if (tid == 0) { s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30); s_pool_used = 0; }
-      __syncthreads();
-      // bounding box of the scan windows (block extent included) of the jobs that scan
-      for (int k = tid; k < kn; k += kTzThreads) {
-        const int ji = job_index[G.first + k0 + k];
-        const TzJobState *st = &states[ji];
-        s_list_off[k] = -1; s_list_cnt[k] = 0;
-        if (!st->need_raster || st->shi[0] < st->slo[0] || st->shi[1] < st->slo[1]) continue;
-        const xvcb200_cu cu = cus[jobs[ji].cu];
-        atomicMin(&s_box[0], cu.x + st->slo[0]); atomicMin(&s_box[1], cu.y + st->slo[1]);
-        atomicMax(&s_box[2], cu.x + st->shi[0] + cu.w); atomicMax(&s_box[3], cu.y + st->shi[1] + cu.h);
+      if (tid == 0) {
+        s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
+        s_pool_used = 0; s_next = 0; s_any_raster = 0;
       }
       __syncthreads();
-      if (s_box[2] < s_box[0]) continue;           // no job of this chunk scans
+      // job descriptors -> shared memory; bounding box of the search windows (block extent included)
+      for (int k = tid; k < kn; k += kTzThreads) {
+        const int ji = job_index[G.first + k0 + k];
+        const xvcb200_me_job job = jobs[ji];
+        const xvcb200_cu cu = cus[job.cu];
+        SJob &sj = s_job[k];
+        sj.ji = ji; sj.x = cu.x; sj.y = cu.y; sj.w = cu.w; sj.h = cu.h; sj.depth = cu.depth;
+        sj.fullpel = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 1 : 0;
+        sj.mvpx = job.mvp[0]; sj.mvpy = job.mvp[1]; sj.prevx = job.prev[0]; sj.prevy = job.prev[1];
+        sj.range = job.search_range; sj.need = 0; sj.list_off = -1; sj.list_cnt = 0;
+        sj.key = ~0ull;
+        int lo[2], hi[2];
+        min_max_mv(cu.x, cu.y, ref.width, ref.height, job.mvp[0], job.mvp[1], job.search_range, lo, hi);
+        atomicMin(&s_box[0], cu.x + lo[0]); atomicMin(&s_box[1], cu.y + lo[1]);
+        atomicMax(&s_box[2], cu.x + hi[0] + cu.w); atomicMax(&s_box[3], cu.y + hi[1] + cu.h);
+      }
+      __syncthreads();
       const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
       const int bw = rx1 - rx0, bh = ry1 - ry0;
       const int spw = ((bw + 1) / 2 + 1) | 1;
       const int cpr = (bw + 7) >> 3;
       const bool staged = (long long)spw * bh <= region_budget_words;
-
-      // ---------------- pass 1: segment-sum bound, survivors -> pool
+      const int ctu_x = s_job[0].x & ~63, ctu_y = s_job[0].y & ~63;
       lap(0);
-      if (staged && s8.base != nullptr) {
-        stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
-        __syncthreads();
-        lap(1);
-        const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
-        uint16_t *s_seg = reinterpret_cast<uint16_t *>(s_orig);      // [rows][w/8]
-        for (int k = 0; k < kn; k++) {
-          const int ji = job_index[G.first + k0 + k];
-          const TzJobState *stp = &states[ji];
-          if (!stp->need_raster) continue;           // uniform
-          const xvcb200_me_job job = jobs[ji];
-          const xvcb200_cu cu = cus[job.cu];
-          if (cu.w < 8) continue;                    // no 8-sample segments: dense scan in pass 2
-          const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
-          const int slox = stp->slo[0], sloy = stp->slo[1], shix = stp->shi[0], shiy = stp->shi[1];
-          const uint32_t cost_in = stp->cost;
-          const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
-          const int lsg = g.lpw - 2, nseg = 1 << lsg;                // segments per row
-          for (int q = tid; q < (g.rows << lsg); q += kTzThreads) {
-            const int row = q >> lsg, sg = q & (nseg - 1);
-            const Sample *p = orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + sg * 8;
-            int sum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) sum += p[i];
-            s_seg[q] = (uint16_t)sum;
-          }
-          if (tid == 0) s_count = 0;
-          __syncthreads();
-          const int base = s_pool_used;
-          const int room = pool_cap - base;
-          const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
-          const int rstride = g.rstep * 2 * spw;
-          for (int j0 = 0; j0 < ny; j0 += 32) {
-            const int j = j0 + lane, jj = min(j, ny - 1);
-            const int cy = sloy + 5 * jj, oy = g.y + cy - ry0;
-            const uint32_t bits_y = exp_golomb_bits((cy * 16 - g.mvpy) >> (g.down + 2));
-            for (int i = warp; i < nx; i += kTzWarps) {
-              const int cx = slox + 5 * i, ox = g.x + cx - rx0;
-              const uint16_t *rp = s8reg + oy * (2 * spw) + ox;
-              uint32_t lb = 0;
-              switch (lsg) {
-                case 0: lb = seg_bound<1>(rp, rstride, seg32, g.rows); break;
-                case 1: lb = seg_bound<2>(rp, rstride, seg32, g.rows); break;
-                case 2: lb = seg_bound<4>(rp, rstride, seg32, g.rows); break;
-                default: lb = seg_bound<8>(rp, rstride, seg32, g.rows); break;
-              }
-              const uint32_t lbd = g.fast ? (lb * 2) >> g.bd_shift : lb >> g.bd_shift;
-              const uint32_t bits = bits_y + exp_golomb_bits((cx * 16 - g.mvpx) >> (g.down + 2));
-              const bool keep = j < ny && lbd + ((g.lambda * bits) >> 16) < cost_in;
-              const unsigned mask = __ballot_sync(XVCB_FULL, keep);
-              if (mask) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
-                wbase = __shfl_sync(XVCB_FULL, wbase, 0);
-                const int slot = wbase + __popc(mask & ((1u << lane) - 1));
-                if (keep && slot < room) pool[base + slot] = (uint16_t)(j * nx + i);
-              }
-            }
-          }
-          __syncthreads();
-          if (tid == 0) {
-            if (s_count <= room && nx * ny <= 65536) { s_list_off[k] = base; s_list_cnt[k] = s_count; s_pool_used = base + s_count; }
-            if (prof) { atomicAdd(&prof[6], (unsigned long long)(nx * ny)); atomicAdd(&prof[7], (unsigned long long)s_count); }
-          }
-          __syncthreads();
-        }
+      // original CTU -> shared memory (all jobs of a group lie in one CTU)
+      for (int q = tid; q < 64 * 32; q += kTzThreads) {
+        const int row = q >> 5, col = q & 31;
+        s_tile[row * 33 + col] = ld_pair(orig.base + (ctu_y + row) * orig.pitch + ctu_x + col * 2);
       }
-
-      // ---------------- pass 2: exact SAD of the survivors (or of every candidate: dense scan)
-      __syncthreads();
-      lap(2);
       if (staged) stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
       __syncthreads();
-      lap(3);
-      for (int k = 0; k < kn; k++) {
-        const int ji = job_index[G.first + k0 + k];
-        TzJobState *stp = &states[ji];
-        if (!stp->need_raster) continue;           // uniform: every thread reads the same word
-        const xvcb200_me_job job = jobs[ji];
-        const xvcb200_cu cu = cus[job.cu];
-        const MeGeom g = me_geom(cu, bitdepth, lambda, job.mvp[0], job.mvp[1]);
-        const int slox = stp->slo[0], sloy = stp->slo[1], shix = stp->shi[0], shiy = stp->shi[1];
-        const uint32_t cost_in = stp->cost;
-        const int nx = (shix - slox) / 5 + 1, ny = (shiy - sloy) / 5 + 1;
-        const bool nonempty = shix >= slox && shiy >= sloy;
-        const int list_off = s_list_off[k], list_cnt = s_list_cnt[k];
-        // original block -> shared memory as packed pairs [row][pair]
-        const int pw = 1 << g.lpw;
-        for (int q = tid; q < (g.rows << g.lpw); q += kTzThreads) {
-          const int row = q >> g.lpw, col = q & (pw - 1);
-          s_orig[q] = ld_pair(orig.base + (g.y + row * g.rstep) * orig.pitch + g.x + col * 2);
+      lap(1);
+
+      // ---------------- phase 1: one warp per job
+      for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&s_next, 1);
+        k = __shfl_sync(XVCB_FULL, k, 0);
+        if (k >= kn) break;
+        SJob &sj = s_job[k];
+        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
+        xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
+        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
+        TzJobState st;
+        tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
+        if (lane == 0) {
+          states[sj.ji] = st;
+          if (st.need_raster && st.shi[0] >= st.slo[0] && st.shi[1] >= st.slo[1]) {
+            sj.slox = st.slo[0]; sj.sloy = st.slo[1];
+            sj.nx = (st.shi[0] - st.slo[0]) / 5 + 1; sj.ny = (st.shi[1] - st.slo[1]) / 5 + 1;
+            sj.cost_in = st.cost;
+            const bool fits = staged && g.x + st.slo[0] >= rx0 && g.x + st.shi[0] + g.w <= rx1 && g.y + st.slo[1] >= ry0 &&
+                              g.y + st.shi[1] + g.h <= ry1;
+            sj.need = fits ? 1 : 2;
+            s_any_raster = 1;
+          }
         }
-        __syncthreads();
-        uint32_t best_cost = 0xffffffffu, best_t = 0;
-        if (nonempty && list_off >= 0) {             // survivors: arbitrary grid positions per lane
-          for (int e = tid; e < list_cnt; e += kTzThreads) {
-            const uint32_t t = pool[list_off + e];
-            const int j = (int)t / nx, i = (int)t - j * nx;
-            const int cx = slox + 5 * i, cy = sloy + 5 * j;
+      }
+      __threadfence_block();
+      __syncthreads();
+      lap(2);
+
+      if (s_any_raster) {
+        // ---------------- raster pass 1: segment-sum bound, survivors -> pool
+        if (staged && s8.base != nullptr) {
+          stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+          __syncthreads();
+          lap(3);
+          const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
+          for (int k = 0; k < kn; k++) {
+            const SJob &sj = s_job[k];
+            if (sj.need != 1 || sj.w < 8 || sj.nx * sj.ny > 65535) continue;      // uniform
+            const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+            const int slox = sj.slox, sloy = sj.sloy, nx = sj.nx, ny = sj.ny;
+            const uint32_t cost_in = sj.cost_in;
+            const int lsg = g.lpw - 2, nseg = 1 << lsg;                // segments per row
+            const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
+            for (int q = tid; q < (g.rows << lsg); q += kTzThreads) {
+              const int row = q >> lsg, sg = q & (nseg - 1);
+              const uint32_t *p = tp + row * g.rstep * 33 + sg * 4;
+              const uint32_t s2 = p[0] + p[1] + p[2] + p[3];            // two 16-bit partial sums, no carry (<= 4 x 4095)
+              s_seg[q] = (uint16_t)((s2 & 0xffff) + (s2 >> 16));
+            }
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            const int base = s_pool_used;
+            const int room = pool_cap - base;
+            const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
+            const int rstride = g.rstep * 2 * spw;
+            for (int j0 = 0; j0 < ny; j0 += 32) {
+              const int j = j0 + lane, jj = min(j, ny - 1);
+              const int cy = sloy + 5 * jj, oy = g.y + cy - ry0;
+              const uint32_t bits_y = exp_golomb_bits((cy * 16 - g.mvpy) >> (g.down + 2));
+              for (int i = warp; i < nx; i += kTzWarps) {
+                const int cx = slox + 5 * i, ox = g.x + cx - rx0;
+                const uint16_t *rp = s8reg + oy * (2 * spw) + ox;
+                uint32_t lb = 0;
+                switch (lsg) {
+                  case 0: lb = seg_bound<1>(rp, rstride, seg32, g.rows); break;
+                  case 1: lb = seg_bound<2>(rp, rstride, seg32, g.rows); break;
+                  case 2: lb = seg_bound<4>(rp, rstride, seg32, g.rows); break;
+                  default: lb = seg_bound<8>(rp, rstride, seg32, g.rows); break;
+                }
+                const uint32_t lbd = g.fast ? (lb * 2) >> g.bd_shift : lb >> g.bd_shift;
+                const uint32_t bits = bits_y + exp_golomb_bits((cx * 16 - g.mvpx) >> (g.down + 2));
+                const bool keep = j < ny && lbd + ((g.lambda * bits) >> 16) < cost_in;
+                const unsigned mask = __ballot_sync(XVCB_FULL, keep);
+                if (mask) {
+                  int wbase = 0;
+                  if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
+                  wbase = __shfl_sync(XVCB_FULL, wbase, 0);
+                  const int slot = wbase + __popc(mask & ((1u << lane) - 1));
+                  if (keep && slot < room) pool[base + slot] = ((uint32_t)k << 16) | (uint32_t)(j * nx + i);
+                }
+              }
+            }
+            __syncthreads();
+            if (tid == 0) {
+              if (s_count <= room) { s_job[k].list_off = base; s_job[k].list_cnt = s_count; s_pool_used = base + s_count; }
+              if (prof) { atomicAdd(&prof[8], (unsigned long long)(nx * ny)); atomicAdd(&prof[9], (unsigned long long)s_count); }
+            }
+            __syncthreads();
+          }
+          lap(4);
+          stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+          __syncthreads();
+          lap(5);
+        }
+
+        // ---------------- raster pass 2a: survivors of all jobs, one flat loop, one candidate per lane
+        {
+          const int total = s_pool_used;
+          for (int e = tid; e < total; e += kTzThreads) {
+            const uint32_t ent = pool[e];
+            const int k = (int)(ent >> 16);
+            const uint32_t t = ent & 0xffffu;
+            SJob &sj = s_job[k];
+            if (sj.list_off < 0 || e < sj.list_off || e >= sj.list_off + sj.list_cnt) continue;   // list of an overflowed job
+            const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+            const int j = (int)t / sj.nx, i = (int)t - j * sj.nx;
+            const int cx = sj.slox + 5 * i, cy = sj.sloy + 5 * j;
             const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
-            const uint32_t sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, s_orig, pw,
-                                                     g.rows, (ox & 1) << 4);
+            const uint32_t sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw,
+                                                     s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, g.rows,
+                                                     (ox & 1) << 4);
             const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
             const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-            if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
-          }
-        } else if (nonempty) {                       // dense scan
-          const int passes = (ny + 31) >> 5;
-          for (int task = warp; task < nx * passes; task += kTzWarps) {
-            const int i = task % nx, j = (task / nx) * 32 + lane;
-            const int jj = min(j, ny - 1);             // idle lanes recompute the last row (no stray reads)
-            const int cx = slox + 5 * i, cy = sloy + 5 * jj;
-            uint32_t sad;
-            if (staged) {
-              const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
-              sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, s_orig, pw, g.rows, (ox & 1) << 4);
-            } else {                                    // window too large for shared memory: same walk from global memory
-              const int X = g.x + cx;
-              const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
-              sad = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, s_orig, pw,
-                                       g.rows, (X & 1) << 4);
-            }
-            if (j < ny) {
-              const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
-              const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-              const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
-              if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
-            }
+            atomicMin(&sj.key, ((unsigned long long)cost << 32) | t);
           }
         }
-        unsigned long long key = ((unsigned long long)best_cost << 32) | best_t;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(XVCB_FULL, key, off);
-          key = other < key ? other : key;
+        // ---------------- raster pass 2b: dense scans (no survivor list), CTA-wide per job
+        for (int k = 0; k < kn; k++) {
+          SJob &sj = s_job[k];
+          if (sj.need == 0 || sj.list_off >= 0) continue;      // uniform
+          const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+          const int slox = sj.slox, sloy = sj.sloy, nx = sj.nx, ny = sj.ny;
+          const bool in_box = sj.need == 1;
+          const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
+          uint32_t best_cost = 0xffffffffu, best_t = 0;
+          for (int j0 = 0; j0 < ny; j0 += 32) {
+            const int j = j0 + lane, jj = min(j, ny - 1);     // idle lanes recompute the last row (no stray reads)
+            const int cy = sloy + 5 * jj;
+            for (int i = warp; i < nx; i += kTzWarps) {
+              const int cx = slox + 5 * i;
+              uint32_t sad;
+              if (in_box) {
+                const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
+                sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, tp, 33 * g.rstep, g.rows, (ox & 1) << 4);
+              } else {                                  // window outside / larger than the staged box: same walk from global memory
+                const int X = g.x + cx;
+                const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
+                sad = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, tp,
+                                         33 * g.rstep, g.rows, (X & 1) << 4);
+              }
+              if (j < ny) {
+                const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
+                const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+                const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
+                if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+              }
+            }
+          }
+          if (best_cost != 0xffffffffu) atomicMin(&sj.key, ((unsigned long long)best_cost << 32) | best_t);
         }
-        if (lane == 0) s_red[warp] = key;
         __syncthreads();
-        if (tid == 0) {
-          unsigned long long m = s_red[0];
-          for (int w2 = 1; w2 < kTzWarps; w2++) m = s_red[w2] < m ? s_red[w2] : m;
-          const uint32_t c = (uint32_t)(m >> 32), t = (uint32_t)m;
-          if (nonempty && c < cost_in) {             // strict: ties keep the earlier best (:266-268)
+        // winners -> job state (strict compare: ties keep the earlier best, :266-268)
+        for (int k = tid; k < kn; k += kTzThreads) {
+          SJob &sj = s_job[k];
+          if (sj.need == 0) continue;
+          TzJobState *stp = &states[sj.ji];
+          const uint32_t c = (uint32_t)(sj.key >> 32), t = (uint32_t)sj.key;
+          if (sj.key != ~0ull && c < sj.cost_in) {
             stp->cost = c;
-            stp->bx = slox + 5 * (int)(t % nx);
-            stp->by = sloy + 5 * (int)(t / nx);
+            stp->bx = sj.slox + 5 * (int)(t % sj.nx);
+            stp->by = sj.sloy + 5 * (int)(t / sj.nx);
           }
           stp->last_range = 5;
-          if (nonempty) stp->evals += nx * ny;
+          stp->evals += sj.nx * sj.ny;
           stp->need_raster = 0;
         }
-        __syncthreads();
+        __threadfence_block();
       }
-      lap(4);
+      if (tid == 0) s_next = 0;
+      __syncthreads();
+      lap(6);
+
+      // ---------------- phase 3: one warp per job
+      for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&s_next, 1);
+        k = __shfl_sync(XVCB_FULL, k, 0);
+        if (k >= kn) break;
+        const SJob &sj = s_job[k];
+        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
+        TzJobState st = states[sj.ji];
+        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }     // empty scan window (:146-147)
+        tz_phase3(g, sj.range, ev, lane, st, &res[sj.ji]);
+      }
+      __syncthreads();
+      lap(7);
     }
   }
 }
@@ -754,9 +802,8 @@ __global__ void __launch_bounds__(128) subpel_kernel(const xvcb200_cu *__restric
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
-                             const int *d_order, const PlaneView *d_s8_planes, const PlaneView *h_ref_planes,
-                             Sample *const *h_s8_base, const int *ref_slots, int n_ref_slots, const int margin[2],
-                             uint16_t *d_pool, int pool_cap) {
+                             const PlaneView *d_s8_planes, const PlaneView *h_ref_planes, Sample *const *h_s8_base,
+                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap) {
   if (n <= 0 || n_groups <= 0) return cudaSuccess;
   static int smem_bytes = 0, num_sms = 0;
   if (!smem_bytes) {
@@ -765,18 +812,14 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, tz_raster_kernel);
-    smem_bytes = max_optin - (int)fa.sharedSizeBytes - 1024;
-    cudaError_t e = cudaFuncSetAttribute(tz_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaFuncGetAttributes(&fa, tz_search_kernel);
+    smem_bytes = max_optin - (int)fa.sharedSizeBytes - 512;
+    cudaError_t e = cudaFuncSetAttribute(tz_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { smem_bytes = 0; return e; }
   }
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  TzJobState *st = static_cast<TzJobState *>(d_states);
-  const int blocks = (n + kRoundWarps - 1) / kRoundWarps;
-  g_launch_count += 3;
-  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(1, d_cus, d_jobs, d_order, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
-  // segment sums of the reference pictures this launch searches (rows/columns the windows can touch)
+  // 8-sample segment sums of the reference pictures this launch searches
   for (int i = 0; i < n_ref_slots; i++) {
     const PlaneView rv = h_ref_planes[ref_slots[i]];
     const int x0 = -margin[0], x1 = rv.width + margin[0] - 8, y0 = -margin[1], y1 = rv.height + margin[1];
@@ -786,19 +829,22 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   }
   static unsigned long long *prof = nullptr;
   static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
-  if (want_prof && !prof) cudaMallocManaged(&prof, 8 * sizeof(*prof));
-  if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 8 * sizeof(*prof)); }
+  if (want_prof && !prof) cudaMallocManaged(&prof, 16 * sizeof(*prof));
+  if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 16 * sizeof(*prof)); }
   const int grid = n_groups < num_sms ? n_groups : num_sms;
-  tz_raster_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
+  const int fixed_words = kTileWords + kSegWords + kMaxGroupJobs * (int)(sizeof(SJob) / 4);
+  g_launch_count++;
+  tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
       d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
-      d_ref_planes, d_s8_planes, st, smem_bytes / 4 - 1024, d_pool, pool_cap, want_prof ? prof : nullptr);
+      d_ref_planes, d_s8_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
+      want_prof ? prof : nullptr);
   if (want_prof) {
     cudaStreamSynchronize(s);
-    fprintf(stderr, "[tz raster prof] cycles/CTA: box %.0f stageS8 %.0f bound %.0f stageRef %.0f exact %.0f | candidates %llu survivors %llu (%.2f%%)\n",
+    fprintf(stderr, "[tz prof] cycles/CTA: box %.0f stage %.0f phase1 %.0f stageS8 %.0f bound %.0f stageRef %.0f exact %.0f phase3 %.0f | raster candidates %llu survivors %llu (%.2f%%)\n",
             (double)prof[0] / grid, (double)prof[1] / grid, (double)prof[2] / grid, (double)prof[3] / grid, (double)prof[4] / grid,
-            prof[6], prof[7], 100.0 * (double)prof[7] / (double)(prof[6] ? prof[6] : 1));
+            (double)prof[5] / grid, (double)prof[6] / grid, (double)prof[7] / grid, prof[8], prof[9],
+            100.0 * (double)prof[9] / (double)(prof[8] ? prof[8] : 1));
   }
-  tz_rounds_kernel<<<blocks, kRoundWarps * 32, 0, s>>>(3, d_cus, d_jobs, d_order, n, bitdepth, lambda_me, orig, d_ref_planes, d_res, st);
   return cudaGetLastError();
 }
 size_t tz_state_bytes() { return sizeof(TzJobState); }
