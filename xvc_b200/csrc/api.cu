@@ -357,8 +357,12 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int *d_groups = nullptr; int groups_cap = 0;       // pairs {first, count}
   uint8_t *d_tz_states = nullptr; int tz_states_cap = 0;
   int *d_counter = nullptr;
-  int *d_order = nullptr; int order_cap = 0;          // job indices, largest blocks first
-  int pipeline_groups_nl = 0, pipeline_n_groups = 0;   // cached grouping of the picture pipeline's job list
+  // the picture pipeline's own grouping (job = cu * nl + list), built by set_cus for nl = 1 and 2
+  int *d_pipe_index[2] = {nullptr, nullptr}; int pipe_index_cap[2] = {0, 0};
+  int *d_pipe_groups[2] = {nullptr, nullptr}; int pipe_groups_cap[2] = {0, 0};
+  int pipe_n_groups[2] = {0, 0};
+  void *h_setcus = nullptr; size_t h_setcus_cap = 0;   // pinned staging of set_cus, guarded by setcus_ev
+  cudaEvent_t setcus_ev = nullptr;
   // successive-elimination support: 8-sample segment sums of every slot's luma plane, survivor pool
   std::vector<PlaneView> h_luma_views;
   std::vector<Sample *> h_s8_base;
@@ -492,7 +496,10 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->d_cus); cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
   cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  cudaFree(c->ex.d_order); cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
+  for (int i = 0; i < 2; i++) { cudaFree(c->ex.d_pipe_index[i]); cudaFree(c->ex.d_pipe_groups[i]); }
+  if (c->ex.h_setcus) cudaFreeHost(c->ex.h_setcus);
+  if (c->ex.setcus_ev) cudaEventDestroy(c->ex.setcus_ev);
+  cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
@@ -599,14 +606,47 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   }
   if (!ensure(c, &c->d_cus, &c->cap_cus, n) || !ensure(c, &c->ex.d_tu_list, &c->ex.tu_cap, 3 * n)) return c->status;
   c->n_cus = n;
-  if (n == 0) { c->ex.h_cus.clear(); c->ex.pipeline_groups_nl = 0; return XVCB200_OK; }
-  int *list = static_cast<int *>(c->pinned(sizeof(int) * 3 * (size_t)n + sizeof(xvcb200_cu) * (size_t)n));
-  if (!list) return c->status;
-  xvcb200_cu *hc = reinterpret_cast<xvcb200_cu *>(list + 3 * (size_t)n);
-  cudaStreamSynchronize(c->stream);          // pinned buffer may still feed an earlier copy
+  if (n == 0) { c->ex.h_cus.clear(); return XVCB200_OK; }
+  // CU groups by CTU (counting sort: coding order inside a CTU is kept)
+  const int ctus_x = (c->width + 63) >> 6, n_ctus = ctus_x * ((c->height + 63) >> 6);
+  std::vector<int> ctu_first((size_t)n_ctus + 1, 0), by_ctu((size_t)n);
+  for (int i = 0; i < n; i++) ctu_first[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6)) + 1]++;
+  int n_groups = 0;
+  for (int t = 0; t < n_ctus; t++) { n_groups += ctu_first[(size_t)t + 1] != 0; ctu_first[(size_t)t + 1] += ctu_first[(size_t)t]; }
+  {
+    std::vector<int> fill(ctu_first.begin(), ctu_first.end() - 1);
+    for (int i = 0; i < n; i++) by_ctu[(size_t)fill[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6))]++] = i;
+  }
+  for (int v = 0; v < 2; v++)
+    if (!ensure(c, &c->ex.d_pipe_index[v], &c->ex.pipe_index_cap[v], (v + 1) * n) ||
+        !ensure(c, &c->ex.d_pipe_groups[v], &c->ex.pipe_groups_cap[v], 2 * (v + 1) * n_groups))
+      return c->status;
+  // pinned staging: [cus][tu list 3n][index nl=1: n][index nl=2: 2n][groups nl=1: 2g][groups nl=2: 4g]
+  const size_t ints = 3 * (size_t)n + 3 * (size_t)n + 6 * (size_t)n_groups;
+  const size_t need = sizeof(xvcb200_cu) * (size_t)n + sizeof(int) * ints;
+  if (!c->ex.setcus_ev && !c->check(cudaEventCreateWithFlags(&c->ex.setcus_ev, cudaEventDisableTiming), "cudaEventCreate")) return c->status;
+  if (!c->check(cudaEventSynchronize(c->ex.setcus_ev), "set_cus staging")) return c->status;   // earlier copies out of the buffer
+  if (need > c->ex.h_setcus_cap) {
+    if (c->ex.h_setcus) cudaFreeHost(c->ex.h_setcus);
+    c->ex.h_setcus = nullptr; c->ex.h_setcus_cap = 0;
+    if (!c->check(cudaHostAlloc(&c->ex.h_setcus, need + need / 4, cudaHostAllocDefault), "cudaHostAlloc")) return c->status;
+    c->ex.h_setcus_cap = need + need / 4;
+  }
+  xvcb200_cu *hc = static_cast<xvcb200_cu *>(c->ex.h_setcus);
+  int *list = reinterpret_cast<int *>(hc + n);
+  int *idx1 = list + 3 * (size_t)n, *idx2 = idx1 + n, *grp1 = idx2 + 2 * (size_t)n, *grp2 = grp1 + 2 * (size_t)n_groups;
   memcpy(hc, cus, sizeof(xvcb200_cu) * (size_t)n);
   c->ex.h_cus.assign(cus, cus + n);
-  c->ex.pipeline_groups_nl = 0;
+  for (int i = 0; i < n; i++) { idx1[i] = by_ctu[(size_t)i]; idx2[i] = 2 * by_ctu[(size_t)i]; idx2[n + i] = 2 * by_ctu[(size_t)i] + 1; }
+  for (int t = 0, g = 0; t < n_ctus; t++) {
+    const int first = ctu_first[(size_t)t], cnt = ctu_first[(size_t)t + 1] - first;
+    if (cnt == 0) continue;
+    grp1[2 * g] = first; grp1[2 * g + 1] = cnt;
+    grp2[2 * g] = first; grp2[2 * g + 1] = cnt;
+    grp2[2 * (n_groups + g)] = n + first; grp2[2 * (n_groups + g) + 1] = cnt;
+    g++;
+  }
+  c->ex.pipe_n_groups[0] = n_groups; c->ex.pipe_n_groups[1] = 2 * n_groups;
   auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
   memset(c->ex.class_count, 0, sizeof(c->ex.class_count));
   for (int i = 0; i < n; i++)
@@ -616,8 +656,14 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
     for (int b = 0; b < 7; b++) { c->ex.class_offset[a][b] = off; fill[a][b] = off; off += c->ex.class_count[a][b]; }
   for (int i = 0; i < n; i++)
     for (int comp = 0; comp < 3; comp++) list[fill[lg(cus[i].w >> (comp ? 1 : 0))][lg(cus[i].h >> (comp ? 1 : 0))]++] = 3 * i + comp;
-  if (!c->check(cudaMemcpyAsync(c->d_cus, hc, sizeof(xvcb200_cu) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "set_cus") ||
-      !c->check(cudaMemcpyAsync(c->ex.d_tu_list, list, sizeof(int) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream), "set_cus"))
+  auto up = [&](void *d, const void *h, size_t bytes) {
+    return c->check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream), "set_cus");
+  };
+  if (!up(c->d_cus, hc, sizeof(xvcb200_cu) * (size_t)n) || !up(c->ex.d_tu_list, list, sizeof(int) * 3 * (size_t)n) ||
+      !up(c->ex.d_pipe_index[0], idx1, sizeof(int) * (size_t)n) || !up(c->ex.d_pipe_index[1], idx2, sizeof(int) * 2 * (size_t)n) ||
+      !up(c->ex.d_pipe_groups[0], grp1, sizeof(int) * 2 * (size_t)n_groups) ||
+      !up(c->ex.d_pipe_groups[1], grp2, sizeof(int) * 4 * (size_t)n_groups) ||
+      !c->check(cudaEventRecord(c->ex.setcus_ev, c->stream), "set_cus"))
     return c->status;
   return XVCB200_OK;
 }
@@ -633,12 +679,25 @@ int xvcb200_get_cus(xvcb200_ctx *c, xvcb200_cu *cus, int n) {
 
 namespace xvcb { size_t tz_state_bytes(); int tz_max_ctas(); }
 
+// Per-job search state, the survivor pools and the group counter of tz_search_kernel.
+static bool ensure_tz_scratch(CtxFull *c, int n_jobs) {
+  if (!c->ex.d_pool) {
+    c->ex.pool_ctas = xvcb::tz_max_ctas();
+    if (!c->check(cudaMalloc(&c->ex.d_pool, sizeof(uint32_t) * (size_t)c->ex.pool_cap * c->ex.pool_ctas), "cudaMalloc(pool)")) return false;
+  }
+  int st_cap_elems = c->ex.tz_states_cap;
+  if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return false;
+  c->ex.tz_states_cap = st_cap_elems;
+  if (!c->ex.d_counter && !c->check(cudaMalloc(&c->ex.d_counter, sizeof(int)), "cudaMalloc(counter)")) return false;
+  return true;
+}
+
 // Groups search jobs by (reference slot, CTU of the CU) and uploads the index + group arrays.
 // key(i) must be cheap; jobs of one group end up adjacent in job_index, in their original order.
-template <class KeyOf, class JobOf, class AreaOf>
-static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of, AreaOf area_of) {
+template <class KeyOf>
+static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of) {
   std::vector<std::pair<long long, int>> order((size_t)n_jobs);
-  for (int i = 0; i < n_jobs; i++) order[(size_t)i] = std::make_pair(key_of(i), job_of(i));
+  for (int i = 0; i < n_jobs; i++) order[(size_t)i] = std::make_pair(key_of(i), i);
   std::stable_sort(order.begin(), order.end(), [](const std::pair<long long, int> &a, const std::pair<long long, int> &b) { return a.first < b.first; });
   std::vector<int> index((size_t)n_jobs), groups;
   for (int i = 0; i < n_jobs; i++) {
@@ -647,23 +706,11 @@ static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of, JobOf job_of, 
     groups.back()++;
   }
   const int n_groups = (int)groups.size() / 2;
-  std::vector<int> by_size((size_t)n_jobs);
-  for (int i = 0; i < n_jobs; i++) by_size[(size_t)i] = i;
-  std::stable_sort(by_size.begin(), by_size.end(), [&](int x, int y) { return area_of(x) > area_of(y); });
-  if (!ensure(c, &c->ex.d_job_index, &c->ex.job_index_cap, n_jobs) || !ensure(c, &c->ex.d_groups, &c->ex.groups_cap, 2 * n_groups) ||
-      !ensure(c, &c->ex.d_order, &c->ex.order_cap, n_jobs))
+  if (!ensure(c, &c->ex.d_job_index, &c->ex.job_index_cap, n_jobs) || !ensure(c, &c->ex.d_groups, &c->ex.groups_cap, 2 * n_groups))
     return -1;
-  if (!c->ex.d_pool) {
-    c->ex.pool_ctas = xvcb::tz_max_ctas();
-    if (!c->check(cudaMalloc(&c->ex.d_pool, sizeof(uint32_t) * (size_t)c->ex.pool_cap * c->ex.pool_ctas), "cudaMalloc(pool)")) return -1;
-  }
-  int st_cap_elems = c->ex.tz_states_cap;
-  if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return -1;
-  c->ex.tz_states_cap = st_cap_elems;
-  if (!c->ex.d_counter && !c->check(cudaMalloc(&c->ex.d_counter, sizeof(int)), "cudaMalloc(counter)")) return -1;
+  if (!ensure_tz_scratch(c, n_jobs)) return -1;
   // synchronous copies: the vectors die at return
-  if (!c->check(cudaMemcpyAsync(c->ex.d_order, by_size.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz order") ||
-      !c->check(cudaMemcpyAsync(c->ex.d_job_index, index.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz index") ||
+  if (!c->check(cudaMemcpyAsync(c->ex.d_job_index, index.data(), sizeof(int) * (size_t)n_jobs, cudaMemcpyHostToDevice, c->stream), "tz index") ||
       !c->check(cudaMemcpyAsync(c->ex.d_groups, groups.data(), sizeof(int) * groups.size(), cudaMemcpyHostToDevice, c->stream), "tz groups") ||
       !c->check(cudaStreamSynchronize(c->stream), "tz groups sync"))
     return -1;
@@ -686,16 +733,11 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
   if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
   c->check(cudaMemcpyAsync(c->ex.d_jobs, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "me jobs");
   const int ctus_x = (c->width + 63) >> 6;
-  const int n_groups = upload_tz_groups(
-      c, n,
-      [&](int i) {
-        const xvcb200_cu &u = c->ex.h_cus[(size_t)jobs[i].cu];
-        return ((long long)jobs[i].ref_slot << 40) | ((long long)jobs[i].search_range << 28) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
-      },
-      [](int i) { return i; },
-      [&](int i) { const xvcb200_cu &u = c->ex.h_cus[(size_t)jobs[i].cu]; return (int)u.w * u.h; });
+  const int n_groups = upload_tz_groups(c, n, [&](int i) {
+    const xvcb200_cu &u = c->ex.h_cus[(size_t)jobs[i].cu];
+    return ((long long)jobs[i].ref_slot << 40) | ((long long)jobs[i].search_range << 28) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
+  });
   if (n_groups < 0) return c->status;
-  c->ex.pipeline_groups_nl = 0;
   std::vector<int> ref_list;
   for (int i = 0; i < n; i++)
     if (std::find(ref_list.begin(), ref_list.end(), jobs[i].ref_slot) == ref_list.end()) ref_list.push_back(jobs[i].ref_slot);
@@ -848,20 +890,7 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     return c->status;
   const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
   const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
-  if (c->ex.pipeline_groups_nl != nl) {      // job (cu, list) = cu * nl + list, grouped by (list, CTU); cached until set_cus
-    const int ctus_x = (c->width + 63) >> 6;
-    const int ng = upload_tz_groups(
-        c, n * nl,
-        [&](int i) {
-          const xvcb200_cu &u = c->ex.h_cus[(size_t)(i / nl)];
-          return ((long long)(i % nl) << 40) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
-        },
-        [](int i) { return i; },
-        [&](int i) { const xvcb200_cu &u = c->ex.h_cus[(size_t)(i / nl)]; return (int)u.w * u.h; });
-    if (ng < 0) return c->status;
-    c->ex.pipeline_groups_nl = nl;
-    c->ex.pipeline_n_groups = ng;
-  }
+  if (!ensure_tz_scratch(c, n * nl)) return c->status;
   int stage = 0;
   auto mark = [&]() { if (c->ex.profile) cudaEventRecord(c->ex.ev[stage], c->stream); stage++; };
   mark();   // 0: start
@@ -871,8 +900,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     const int margin[2] = {c->geom.margin_x[0], c->geom.margin_y[0]};
     const int n_ref = (nl == 2 && slots[1] != slots[0]) ? 2 : 1;
     c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                              c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
-                              c->ex.pipeline_n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
+                              c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_pipe_index[nl - 1],
+                              c->ex.d_pipe_groups[nl - 1], c->ex.pipe_n_groups[nl - 1], c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
                               c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), slots, n_ref, margin, c->ex.d_pool,
                               c->ex.pool_cap), "tz_search");
   }

@@ -132,6 +132,49 @@ struct RoundEval {
   }
 };
 
+// The same for ONE large block handled by the whole CTA: every warp runs the search control flow
+// redundantly (identical state in every warp); a round's candidates are dealt to the warps, the
+// 32 lanes of a warp split one candidate's rows (and row halves), per-candidate sums meet in
+// shared memory.  Contains __syncthreads(): all threads of the CTA must call it together.
+struct CtaEval {
+  const MeGeom &g;
+  const uint32_t *so; int so_row_words;
+  const Sample *plane; int gpitch;
+  const uint32_t *sm; int spw, rx0, ry0, rx1, ry1;
+  uint32_t *s_dist;          // 32 words of shared memory
+  int lane, warp, nwarps;
+
+  __device__ __forceinline__ uint32_t operator()(int cx, int cy, bool valid, int K) const {
+    const int lrows = 31 - __clz(g.rows);               // rows is a power of two <= 32
+    const int row = lane & (g.rows - 1), part = lane >> lrows, lparts = 5 - lrows;
+    const int lpl = g.lpw - lparts;                      // log2(pairs per lane) of one row
+    for (int c = warp; c < K; c += nwarps) {
+      const int sx = __shfl_sync(XVCB_FULL, cx, c);
+      const int sy = __shfl_sync(XVCB_FULL, cy, c);
+      const bool sv = __shfl_sync(XVCB_FULL, (int)valid, c);
+      uint32_t acc = 0;
+      if (sv) {
+        const int X = g.x + sx + (part << (lpl + 1)), Y = g.y + sy + row * g.rstep;
+        const uint32_t *op = so + row * so_row_words + (part << lpl);
+        if (sm != nullptr && g.x + sx >= rx0 && g.x + sx + g.w <= rx1 && g.y + sy >= ry0 && g.y + sy + g.h <= ry1) {
+          const int ox = X - rx0;
+          acc = sad_rows_lpw<false>(lpl, sm + (Y - ry0) * spw + (ox >> 1), 0, op, 0, 1, (ox & 1) << 4);
+        } else {
+          const Sample *row0 = plane + Y * gpitch + (X & ~1);
+          acc = sad_rows_lpw<true>(lpl, reinterpret_cast<const uint32_t *>(row0), 0, op, 0, 1, (X & 1) << 4);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) s_dist[c] = acc;
+    }
+    __syncthreads();
+    const uint32_t mine = s_dist[lane];
+    __syncthreads();
+    if (!valid || lane >= K) return 0xffffffffu;
+    return g.fast ? (mine * 2) >> g.bd_shift : mine >> g.bd_shift;
+  }
+};
+
 // Applies an evaluated candidate list to the running best (see the file comment).
 __device__ __forceinline__ bool apply_candidates(TzBest &b, uint32_t dist, int cx, int cy, int pos, int range,
                                                  const MeGeom &g, int lane) {
@@ -235,7 +278,8 @@ struct TzJobState {
   int need_raster;
 };
 
-__device__ __forceinline__ void neighbour_points(const MeGeom &g, const RoundEval &ev, TzBest &b, const int lo[2],
+template <class Eval>
+__device__ __forceinline__ void neighbour_points(const MeGeom &g, const Eval &ev, TzBest &b, const int lo[2],
                                                  const int hi[2], uint32_t &evals, int lane) {
   if (b.last_range != 1) return;
   b.last_range = 0;
@@ -251,8 +295,9 @@ __device__ __forceinline__ void neighbour_points(const MeGeom &g, const RoundEva
 
 // Phase 1 of TzSearch::Search: start points, first diamond pass, 2-point refinement
 // (inter_tz_search.cc:102-144).
+template <class Eval>
 __device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job, int pic_w, int pic_h,
-                          const RoundEval &ev, int lane, TzJobState &st) {
+                          const Eval &ev, int lane, TzJobState &st) {
   const int range = job.search_range;
   int lo[2], hi[2], slo[2], shi[2];
   min_max_mv(g.x, g.y, pic_w, pic_h, g.mvpx, g.mvpy, range, lo, hi);
@@ -310,7 +355,8 @@ __device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_m
 }
 
 // Phase 3: re-centre until the centre wins (:157-168), then the result.
-__device__ void tz_phase3(const MeGeom &g, int range, const RoundEval &ev, int lane, const TzJobState &st,
+template <class Eval>
+__device__ void tz_phase3(const MeGeom &g, int range, const Eval &ev, int lane, const TzJobState &st,
                           xvcb200_me_result *out) {
   TzBest b;
   b.x = st.bx; b.y = st.by; b.cost = st.cost; b.last_pos = st.last_pos; b.last_range = st.last_range;
@@ -329,7 +375,7 @@ __device__ void tz_phase3(const MeGeom &g, int range, const RoundEval &ev, int l
     }
     neighbour_points(g, ev, b, st.lo, st.hi, evals, lane);
   }
-  if (lane == 0) {
+  if (lane == 0 && out != nullptr) {
     out->mv_fullpel[0] = b.x; out->mv_fullpel[1] = b.y;
     out->cost_fullpel = b.cost;
     out->num_sad = evals;
@@ -486,6 +532,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   SJob *s_job = reinterpret_cast<SJob *>(smem + kTileWords + kSegWords);
   uint32_t *s_region = smem + kTileWords + kSegWords + kMaxGroupJobs * (sizeof(SJob) / 4);
   __shared__ int s_group, s_box[4], s_next, s_count, s_pool_used, s_any_raster;
+  __shared__ uint32_t s_dist[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
   long long t_mark = prof ? clock64() : 0;
@@ -545,7 +592,19 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       __syncthreads();
       lap(1);
 
-      // ---------------- phase 1: one warp per job
+      // ---------------- phase 1: small blocks one warp per job, large blocks (>= 512 pairs) CTA-wide
+      auto finish_phase1 = [&](SJob &sj, const MeGeom &g, const TzJobState &st) {
+        states[sj.ji] = st;
+        if (st.need_raster && st.shi[0] >= st.slo[0] && st.shi[1] >= st.slo[1]) {
+          sj.slox = st.slo[0]; sj.sloy = st.slo[1];
+          sj.nx = (st.shi[0] - st.slo[0]) / 5 + 1; sj.ny = (st.shi[1] - st.slo[1]) / 5 + 1;
+          sj.cost_in = st.cost;
+          const bool fits = staged && g.x + st.slo[0] >= rx0 && g.x + st.shi[0] + g.w <= rx1 && g.y + st.slo[1] >= ry0 &&
+                            g.y + st.shi[1] + g.h <= ry1;
+          sj.need = fits ? 1 : 2;
+          s_any_raster = 1;
+        }
+      };
       for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&s_next, 1);
@@ -553,24 +612,27 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         if (k >= kn) break;
         SJob &sj = s_job[k];
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        if ((g.rows << g.lpw) >= 512) continue;
         xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
         xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
         const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
                            staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
         TzJobState st;
         tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
-        if (lane == 0) {
-          states[sj.ji] = st;
-          if (st.need_raster && st.shi[0] >= st.slo[0] && st.shi[1] >= st.slo[1]) {
-            sj.slox = st.slo[0]; sj.sloy = st.slo[1];
-            sj.nx = (st.shi[0] - st.slo[0]) / 5 + 1; sj.ny = (st.shi[1] - st.slo[1]) / 5 + 1;
-            sj.cost_in = st.cost;
-            const bool fits = staged && g.x + st.slo[0] >= rx0 && g.x + st.shi[0] + g.w <= rx1 && g.y + st.slo[1] >= ry0 &&
-                              g.y + st.shi[1] + g.h <= ry1;
-            sj.need = fits ? 1 : 2;
-            s_any_raster = 1;
-          }
-        }
+        if (lane == 0) finish_phase1(sj, g, st);
+      }
+      __syncthreads();
+      for (int k = 0; k < kn; k++) {
+        SJob &sj = s_job[k];
+        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        if ((g.rows << g.lpw) < 512) continue;      // uniform
+        xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
+        xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
+        const CtaEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                         staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, s_dist, lane, warp, kTzWarps};
+        TzJobState st;
+        tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
+        if (tid == 0) finish_phase1(sj, g, st);
       }
       __threadfence_block();
       __syncthreads();
@@ -603,31 +665,29 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             const int room = pool_cap - base;
             const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
             const int rstride = g.rstep * 2 * spw;
-            for (int j0 = 0; j0 < ny; j0 += 32) {
-              const int j = j0 + lane, jj = min(j, ny - 1);
+            const int passes = (ny + 31) >> 5;
+            for (int task = warp; task < nx * passes; task += kTzWarps) {
+              const int pass = task / nx, i = task - pass * nx;
+              const int j = pass * 32 + lane, jj = min(j, ny - 1);
               const int cy = sloy + 5 * jj, oy = g.y + cy - ry0;
-              const uint32_t bits_y = exp_golomb_bits((cy * 16 - g.mvpy) >> (g.down + 2));
-              for (int i = warp; i < nx; i += kTzWarps) {
-                const int cx = slox + 5 * i, ox = g.x + cx - rx0;
-                const uint16_t *rp = s8reg + oy * (2 * spw) + ox;
-                uint32_t lb = 0;
-                switch (lsg) {
-                  case 0: lb = seg_bound<1>(rp, rstride, seg32, g.rows); break;
-                  case 1: lb = seg_bound<2>(rp, rstride, seg32, g.rows); break;
-                  case 2: lb = seg_bound<4>(rp, rstride, seg32, g.rows); break;
-                  default: lb = seg_bound<8>(rp, rstride, seg32, g.rows); break;
-                }
-                const uint32_t lbd = g.fast ? (lb * 2) >> g.bd_shift : lb >> g.bd_shift;
-                const uint32_t bits = bits_y + exp_golomb_bits((cx * 16 - g.mvpx) >> (g.down + 2));
-                const bool keep = j < ny && lbd + ((g.lambda * bits) >> 16) < cost_in;
-                const unsigned mask = __ballot_sync(XVCB_FULL, keep);
-                if (mask) {
-                  int wbase = 0;
-                  if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
-                  wbase = __shfl_sync(XVCB_FULL, wbase, 0);
-                  const int slot = wbase + __popc(mask & ((1u << lane) - 1));
-                  if (keep && slot < room) pool[base + slot] = ((uint32_t)k << 16) | (uint32_t)(j * nx + i);
-                }
+              const int cx = slox + 5 * i, ox = g.x + cx - rx0;
+              const uint16_t *rp = s8reg + oy * (2 * spw) + ox;
+              uint32_t lb = 0;
+              switch (lsg) {
+                case 0: lb = seg_bound<1>(rp, rstride, seg32, g.rows); break;
+                case 1: lb = seg_bound<2>(rp, rstride, seg32, g.rows); break;
+                case 2: lb = seg_bound<4>(rp, rstride, seg32, g.rows); break;
+                default: lb = seg_bound<8>(rp, rstride, seg32, g.rows); break;
+              }
+              const uint32_t lbd = g.fast ? (lb * 2) >> g.bd_shift : lb >> g.bd_shift;
+              const bool keep = j < ny && lbd + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16) < cost_in;
+              const unsigned mask = __ballot_sync(XVCB_FULL, keep);
+              if (mask) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
+                wbase = __shfl_sync(XVCB_FULL, wbase, 0);
+                const int slot = wbase + __popc(mask & ((1u << lane) - 1));
+                if (keep && slot < room) pool[base + slot] = ((uint32_t)k << 16) | (uint32_t)(j * nx + i);
               }
             }
             __syncthreads();
@@ -720,7 +780,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       __syncthreads();
       lap(6);
 
-      // ---------------- phase 3: one warp per job
+      // ---------------- phase 3: small blocks one warp per job, large blocks CTA-wide
       for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&s_next, 1);
@@ -728,11 +788,23 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         if (k >= kn) break;
         const SJob &sj = s_job[k];
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        if ((g.rows << g.lpw) >= 512) continue;
         const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
                            staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
         TzJobState st = states[sj.ji];
         if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }     // empty scan window (:146-147)
         tz_phase3(g, sj.range, ev, lane, st, &res[sj.ji]);
+      }
+      __syncthreads();
+      for (int k = 0; k < kn; k++) {
+        const SJob &sj = s_job[k];
+        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        if ((g.rows << g.lpw) < 512) continue;      // uniform
+        const CtaEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                         staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, s_dist, lane, warp, kTzWarps};
+        TzJobState st = states[sj.ji];
+        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }
+        tz_phase3(g, sj.range, ev, lane, st, tid == 0 ? &res[sj.ji] : nullptr);
       }
       __syncthreads();
       lap(7);
