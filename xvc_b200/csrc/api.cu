@@ -357,6 +357,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int *d_groups = nullptr; int groups_cap = 0;       // pairs {first, count}
   uint8_t *d_tz_states = nullptr; int tz_states_cap = 0;
   int *d_counter = nullptr;
+  int *d_subpel_lists = nullptr; int subpel_lists_cap = 0;   // job lists by block-size class + their counters
   // the picture pipeline's own grouping (job = cu * nl + list), built by set_cus for nl = 1 and 2
   int *d_pipe_index[2] = {nullptr, nullptr}; int pipe_index_cap[2] = {0, 0};
   int *d_pipe_groups[2] = {nullptr, nullptr}; int pipe_groups_cap[2] = {0, 0};
@@ -499,7 +500,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   for (int i = 0; i < 2; i++) { cudaFree(c->ex.d_pipe_index[i]); cudaFree(c->ex.d_pipe_groups[i]); }
   if (c->ex.h_setcus) cudaFreeHost(c->ex.h_setcus);
   if (c->ex.setcus_ev) cudaEventDestroy(c->ex.setcus_ev);
-  cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
+  cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
@@ -689,6 +690,7 @@ static bool ensure_tz_scratch(CtxFull *c, int n_jobs) {
   if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return false;
   c->ex.tz_states_cap = st_cap_elems;
   if (!c->ex.d_counter && !c->check(cudaMalloc(&c->ex.d_counter, sizeof(int)), "cudaMalloc(counter)")) return false;
+  if (!ensure(c, &c->ex.d_subpel_lists, &c->ex.subpel_lists_cap, 4 * n_jobs + 4)) return false;
   return true;
 }
 
@@ -748,7 +750,7 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
                             c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), ref_list.data(), (int)ref_list.size(), margin,
                             c->ex.d_pool, c->ex.pool_cap), "tz_search");
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
-                                c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");
+                                c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists), "subpel_search");
   c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "me results");
   return xvcb200_sync(c);
 }
@@ -907,7 +909,7 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   }
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                                c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me), "subpel_search");
+                                c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists), "subpel_search");
   c->check(launch_me_decide(c->stream, c->d_cus, n, nl, c->ex.d_me), "me_decide");
   mark();   // 3: sub-pel search + list decision done
   Pic3 refs[2][5];

@@ -2,7 +2,7 @@
 // (CU, reference picture) jobs.
 //
 //   tz_search_kernel   TzSearch::Search (inter_tz_search.cc:84-171), one WARP per job.
-//   subpel_kernel      InterSearch::SubpelSearch / GetSubpelDist (inter_search.cc:893-964), one CTA per job.
+//   (sub-pel search: subpel.cu)
 //   full_search_kernel InterSearch::FullSearch (inter_search.cc:853-891), one warp per job.
 //
 // Exactness of the parallel search.  The reference walks its candidate list in order and
@@ -812,65 +812,6 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   }
 }
 
-// ---------------------------------------------------------------- sub-pel search
-__global__ void __launch_bounds__(128) subpel_kernel(const xvcb200_cu *__restrict__ cus,
-                                                     const xvcb200_me_job *__restrict__ jobs, int n, int bitdepth,
-                                                     uint32_t lambda, PlaneView orig,
-                                                     const PlaneView *__restrict__ ref_planes,
-                                                     xvcb200_me_result *__restrict__ res) {
-  __shared__ int16_t tmp[64 * 71];
-  __shared__ Sample pred[64 * 64];
-  __shared__ Sample org[64 * 64];
-  __shared__ unsigned part[4];
-  const int tid = threadIdx.x;
-  const int ji = blockIdx.x;
-  const xvcb200_me_job job = jobs[ji];
-  const xvcb200_cu cu = cus[job.cu];
-  const PlaneView ref = ref_planes[job.ref_slot];
-  const int w = cu.w, h = cu.h;
-  const int lw = 31 - __clz(w);
-  for (int i = tid; i < w * h; i += 128) {
-    const int y = i >> lw, x = i & (w - 1);
-    org[y * 64 + x] = orig.base[(cu.y + y) * orig.pitch + cu.x + x];
-  }
-  const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;
-  const bool fullpel_only = (cu.flags & XVCB200_CU_FULLPEL_MV) != 0;
-  uint32_t best_cost = 0xffffffffu, best_dist = 0xffffffffu;
-  int best_x = fx0, best_y = fy0;
-  const int8_t half[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
-  const int8_t qpel[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
-  auto diff = [&](int x, int y) { return (int)org[y * 64 + x] - (int)pred[y * 64 + x]; };
-  for (int pass = 0; pass < 2; pass++) {
-    const int bx = best_x, by = best_y;
-    const int step = pass == 0 ? 8 : 4;      // MvDelta(.., 1) / MvDelta(.., 2) in 1/16 units
-    for (int i = pass; i < 9; i++) {
-      const int mvx = bx + (pass == 0 ? half[i][0] : qpel[i][0]) * step;
-      const int mvy = by + (pass == 0 ? half[i][1] : qpel[i][1]) * step;
-      int cx = mvx, cy = mvy;                // MotionCompensationMv clips a copy (inter_prediction.cc:747-748)
-      clip_mv(cu.x, cu.y, ref.width, ref.height, cx, cy);
-      const Sample *r = ref.base + (cu.y + (cy >> 4)) * ref.pitch + cu.x + (cx >> 4);
-      __syncthreads();                       // previous candidate's SATD reads are done
-      interp_cta<false, 8>(w, h, bitdepth, cx & 15, cy & 15, r, ref.pitch, pred, 64, tmp, tid, 128);
-      __syncthreads();
-      unsigned s = satd_block_partial(diff, w, h, tid, 128);
-      s = warp_sum(s);
-      if ((tid & 31) == 0) part[tid >> 5] = s;
-      __syncthreads();
-      const uint32_t dist = (part[0] + part[1] + part[2] + part[3]) >> (bitdepth - 8);
-      if (fullpel_only) { best_dist = dist; best_cost = dist; break; }
-      if (dist < best_cost) {
-        const uint32_t cost = dist + ((lambda * mvd_bits(job.mvp[0], job.mvp[1], mvx, mvy)) >> 16);
-        if (cost < best_cost) { best_cost = cost; best_dist = dist; best_x = mvx; best_y = mvy; }
-      }
-    }
-    if (fullpel_only) break;
-  }
-  if (tid == 0) {
-    res[ji].mv[0] = best_x; res[ji].mv[1] = best_y;
-    res[ji].dist = best_dist; res[ji].cost = best_cost;
-  }
-}
-
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
@@ -921,15 +862,6 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
 }
 size_t tz_state_bytes() { return sizeof(TzJobState); }
 int tz_max_ctas() { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
-
-cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
-                                 int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
-                                 xvcb200_me_result *d_res) {
-  if (n <= 0) return cudaSuccess;
-  g_launch_count++;
-  subpel_kernel<<<n, 128, 0, s>>>(d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  return cudaGetLastError();
-}
 
 // ---------------------------------------------------------------- bi-prediction full search
 // InterSearch::FullSearch (inter_search.cc:853-891): every full-pel position of the clipped

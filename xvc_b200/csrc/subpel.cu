@@ -1,0 +1,486 @@
+// Sub-pel motion search: InterSearch::SubpelSearch / GetSubpelDist (inter_search.cc:893-964) for a
+// batch of (CU, reference picture) jobs, after the full-pel search wrote mv_fullpel.
+//
+// The reference evaluates 1 + 8 half-pel and 8 quarter-pel candidates one after the other, each
+// by a full motion compensation (FilterLuma, inter_prediction.cc:1387-1430) and a SATD.  The
+// candidates of one pass share almost all of their filter work:
+//
+//   half-pel pass   the 8 neighbours use one horizontal half-pel plane of (w+1) x (h+8) raw
+//                   filter sums (integer columns X0-1 .. X0+w-1): its rows give the two
+//                   horizontal-only candidates, one vertical half-pel pass over it gives a
+//                   (w+1) x (h+1) plane holding all four diagonal candidates, one vertical pass
+//                   over the reference gives the two vertical-only ones.  3 filter passes
+//                   instead of 12.
+//   quarter-pel     the 8 neighbours have three x coordinates; per x one horizontal pass over
+//                   h+8 rows, then one vertical pass per candidate.  <= 3 + 8 instead of 16.
+//
+// Each filter pass is a register sliding window: a thread produces a run of 8 (9) outputs along
+// the filter direction from 15 (16) inputs, all operands in shared memory.  SATD runs on up to
+// four candidates of one plane at once (warp-cooperative Hadamard, xvcb_satd.cuh).  The arithmetic
+// (shifts, offsets, int16 narrowing, clipping) is that of xvcb_interp.cuh, i.e. bit-exact to the
+// reference; candidates are then replayed in the reference's order with its strict `<` tests.
+//
+// Teams: blocks of <= 256 samples are searched by one warp (four jobs per CTA), larger ones by
+// a CTA of 128 or 256 threads; each class is one persistent launch that strides over a
+// device-built job list.  Jobs whose candidates would be moved by InterPrediction::ClipMv
+// (inter_prediction.cc:769-782) or with a 4-sample side go to the generic kernel, which
+// interpolates every candidate on its own exactly as the reference does.
+#include "xvcb_interp.cuh"
+#include "xvcb_satd.cuh"
+
+namespace xvcb {
+
+// ---------------------------------------------------------------- generic path (one candidate at a time)
+__global__ void __launch_bounds__(128) subpel_generic_kernel(const xvcb200_cu *__restrict__ cus,
+                                                             const xvcb200_me_job *__restrict__ jobs,
+                                                             const int *__restrict__ list, const int *__restrict__ count,
+                                                             int bitdepth, uint32_t lambda, PlaneView orig,
+                                                             const PlaneView *__restrict__ ref_planes,
+                                                             xvcb200_me_result *__restrict__ res) {
+  __shared__ int16_t tmp[64 * 71];
+  __shared__ Sample pred[64 * 64];
+  __shared__ Sample org[64 * 64];
+  __shared__ unsigned part[4];
+  const int tid = threadIdx.x;
+  const int n_list = *count;
+  for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+    const int ji = list[li];
+    const xvcb200_me_job job = jobs[ji];
+    const xvcb200_cu cu = cus[job.cu];
+    const PlaneView ref = ref_planes[job.ref_slot];
+    const int w = cu.w, h = cu.h;
+    const int lw = 31 - __clz(w);
+    __syncthreads();
+    for (int i = tid; i < w * h; i += 128) {
+      const int y = i >> lw, x = i & (w - 1);
+      org[y * 64 + x] = orig.base[(cu.y + y) * orig.pitch + cu.x + x];
+    }
+    const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;
+    const bool fullpel_only = (cu.flags & XVCB200_CU_FULLPEL_MV) != 0;
+    uint32_t best_cost = 0xffffffffu, best_dist = 0xffffffffu;
+    int best_x = fx0, best_y = fy0;
+    const int8_t half[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, -1}, {-1, 1}, {1, 1}};
+    const int8_t qpel[9][2] = {{0, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {1, 1}};
+    auto diff = [&](int x, int y) { return (int)org[y * 64 + x] - (int)pred[y * 64 + x]; };
+    for (int pass = 0; pass < 2; pass++) {
+      const int bx = best_x, by = best_y;
+      const int step = pass == 0 ? 8 : 4;      // MvDelta(.., 1) / MvDelta(.., 2) in 1/16 units
+      for (int i = pass; i < 9; i++) {
+        const int mvx = bx + (pass == 0 ? half[i][0] : qpel[i][0]) * step;
+        const int mvy = by + (pass == 0 ? half[i][1] : qpel[i][1]) * step;
+        int cx = mvx, cy = mvy;                // MotionCompensationMv clips a copy (inter_prediction.cc:747-748)
+        clip_mv(cu.x, cu.y, ref.width, ref.height, cx, cy);
+        const Sample *r = ref.base + (cu.y + (cy >> 4)) * ref.pitch + cu.x + (cx >> 4);
+        __syncthreads();                       // previous candidate's SATD reads are done
+        interp_cta<false, 8>(w, h, bitdepth, cx & 15, cy & 15, r, ref.pitch, pred, 64, tmp, tid, 128);
+        __syncthreads();
+        unsigned s = satd_block_partial(diff, w, h, tid, 128);
+        s = warp_sum(s);
+        if ((tid & 31) == 0) part[tid >> 5] = s;
+        __syncthreads();
+        const uint32_t dist = (part[0] + part[1] + part[2] + part[3]) >> (bitdepth - 8);
+        if (fullpel_only) { best_dist = dist; best_cost = dist; break; }
+        if (dist < best_cost) {
+          const uint32_t cost = dist + ((lambda * mvd_bits(job.mvp[0], job.mvp[1], mvx, mvy)) >> 16);
+          if (cost < best_cost) { best_cost = cost; best_dist = dist; best_x = mvx; best_y = mvy; }
+        }
+      }
+      if (fullpel_only) break;
+    }
+    if (tid == 0) {
+      res[ji].mv[0] = best_x; res[ji].mv[1] = best_y;
+      res[ji].dist = best_dist; res[ji].cost = best_cost;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- job classes
+// lists: 4 segments of n ints; counts[4].  Class 0: <= 256 samples, 1: <= 1024, 2: larger, 3: generic.
+__global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
+                                       int *__restrict__ lists, int *__restrict__ counts) {
+  const int ji = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ji >= n) return;
+  const xvcb200_cu cu = cus[jobs[ji].cu];
+  const int area = (int)cu.w * cu.h;
+  const int cls = (cu.w < 8 || cu.h < 8) ? 3 : (area <= 256 ? 0 : (area <= 1024 ? 1 : 2));
+  lists[(size_t)cls * n + atomicAdd(&counts[cls], 1)] = ji;
+}
+
+// shared memory of one team (bytes): reference window, horizontal plane, prediction plane, original.
+// Row pitches are chosen odd in 32-bit words so that threads working on consecutive rows hit
+// distinct banks.
+__host__ __device__ inline int subpel_team_bytes(int w, int h) {
+  const int samples = (h + 9) * (w + 10) + (h + 9) * (w + 2) + (h + 1) * (w + 2) + h * (w + 2);
+  return (2 * samples + 15) & ~15;
+}
+
+struct Taps8 { int t[8]; };
+__device__ __forceinline__ Taps8 luma_taps(int frac) {
+  Taps8 r;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r.t[k] = (int)c_luma_taps[frac][k];
+  return r;
+}
+
+// Up to 9 FIR outputs spaced `step` elements apart along the filter direction: out(r) =
+// sum_k taps[k] * in[(r + k) * step].  Reads 16 inputs (the last one only matters for count 9).
+template <typename ST, class Emit>
+__device__ __forceinline__ void fir_run(const ST *in, int step, int count, const Taps8 &taps, Emit emit) {
+  int win[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) win[k] = (int)in[k * step];
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    if (r < count) {
+      int sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += win[r + k] * taps.t[k];
+      emit(r, sum);
+    }
+  }
+}
+
+template <int T> __device__ __forceinline__ void team_sync() {
+  if (T == 32) __syncwarp(); else __syncthreads();
+}
+
+// SATD of up to four candidates that live in one prediction plane at offsets (ox, oy) in {0,1}^2
+// (packed two bits per candidate in `offs`).  The candidates are stacked into one list of tile
+// rows so that small blocks still fill the team.
+template <int TW, int TH>
+__device__ __forceinline__ void satd_stacked(const Sample *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
+                                             int w, int h, int tid, int nthreads, unsigned (&acc)[4]) {
+  const int ltx = 31 - __clz(w / TW);
+  const int lper = ltx + (31 - __clz(h));      // log2(tile rows per candidate)
+  const int total = nc << lper;
+  const int lane = tid & 31;
+  for (int g0 = 0; g0 < total; g0 += nthreads) {
+    const int g = g0 + tid;
+    const bool active = g < total;
+    const int c = active ? g >> lper : 0, gi = g & ((1 << lper) - 1);
+    const int tile = gi / TH, r = gi % TH;
+    const int tx = (tile & ((1 << ltx) - 1)) * TW, ty = (tile >> ltx) * TH + r;
+    const int ox = (offs >> (2 * c)) & 1, oy = (offs >> (2 * c + 1)) & 1;
+    const Sample *po = org + ty * op + tx, *pq = pred + (ty + oy) * pp + tx + ox;
+    int v[TW];
+#pragma unroll
+    for (int i = 0; i < TW; i++) v[i] = active ? (int)po[i] - (int)pq[i] : 0;
+#pragma unroll
+    for (int len = 1; len < TW; len <<= 1)
+#pragma unroll
+      for (int i = 0; i < TW; i += 2 * len)
+#pragma unroll
+        for (int j = i; j < i + len; j++) {
+          const int p = v[j], q = v[j + len];
+          v[j] = p + q;
+          v[j + len] = p - q;
+        }
+#pragma unroll
+    for (int o = 1; o < TH; o <<= 1) {
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < TW; i++) {
+        const int pv = __shfl_xor_sync(XVCB_FULL, v[i], o);
+        v[i] = upper ? pv - v[i] : v[i] + pv;
+      }
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < TW; i++) s += abs(v[i]);
+#pragma unroll
+    for (int o = 1; o < TH; o <<= 1) s += __shfl_xor_sync(XVCB_FULL, s, o);
+    if (active && r == 0) {
+      const unsigned t = (unsigned)satd_norm<TW, TH>(s);
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) acc[cc] += c == cc ? t : 0u;
+    }
+  }
+}
+
+// Tile choice by block shape (sample_metric.cc:322-387) for sides >= 8, then the team-wide sums.
+template <int T>
+__device__ __forceinline__ void satd_candidates(const Sample *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
+                                                int w, int h, int tid, unsigned *s_part, unsigned (&sum)[4]) {
+  unsigned acc[4] = {0, 0, 0, 0};
+  if (w > h) satd_stacked<16, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
+  else if (w < h) satd_stacked<8, 16>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
+  else satd_stacked<8, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
+#pragma unroll
+  for (int c = 0; c < 4; c++) acc[c] = warp_sum(acc[c]);
+  if (T == 32) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) sum[c] = acc[c];
+    __syncwarp();
+  } else {
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) s_part[(tid >> 5) * 4 + c] = acc[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      unsigned t = 0;
+      for (int wi = 0; wi < T / 32; wi++) t += s_part[wi * 4 + c];
+      sum[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_team_kernel(
+    const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, const int *__restrict__ list,
+    const int *__restrict__ count, int *__restrict__ slow_list, int *__restrict__ slow_count, int team_bytes, int bitdepth,
+    uint32_t lambda, PlaneView orig, const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res) {
+  extern __shared__ __align__(16) unsigned char subpel_smem[];
+  __shared__ unsigned s_part[T == 32 ? 4 : (T / 32) * 4];
+  __shared__ unsigned s_sd[T == 32 ? 4 : 1][20];
+  unsigned *sd = s_sd[T == 32 ? (threadIdx.x >> 5) : 0];
+  const int tid = T == 32 ? (threadIdx.x & 31) : threadIdx.x;
+  const int teams = T == 32 ? gridDim.x * 4 : gridDim.x;
+  const int team0 = T == 32 ? blockIdx.x * 4 + (threadIdx.x >> 5) : blockIdx.x;
+  unsigned char *base = subpel_smem + (T == 32 ? (threadIdx.x >> 5) * team_bytes : 0);
+  const int n_list = *count;
+  const int maxv = (1 << bitdepth) - 1;
+  int sh1, off1, sh2, off2;
+  filter_shift_offset(false, false, bitdepth, sh1, off1);     // horizontal stage of the 2-D filter
+  filter_shift_offset(true, true, bitdepth, sh2, off2);       // vertical stage on the intermediate
+  for (int li = team0; li < n_list; li += teams) {
+    const int ji = list[li];
+    const xvcb200_me_job job = jobs[ji];
+    const xvcb200_cu cu = cus[job.cu];
+    const PlaneView ref = ref_planes[job.ref_slot];
+    const int w = cu.w, h = cu.h;
+    const int mfx = res[ji].mv_fullpel[0], mfy = res[ji].mv_fullpel[1];
+    const int fx0 = mfx * 16, fy0 = mfy * 16;
+    {   // every candidate lies within +-12/16 of the full-pel vector: ClipMv must leave that range alone
+      int ax = fx0 - 12, ay = fy0 - 12, bx = fx0 + 12, by = fy0 + 12;
+      clip_mv(cu.x, cu.y, ref.width, ref.height, ax, ay);
+      clip_mv(cu.x, cu.y, ref.width, ref.height, bx, by);
+      if (ax != fx0 - 12 || ay != fy0 - 12 || bx != fx0 + 12 || by != fy0 + 12) {
+        if (tid == 0) slow_list[atomicAdd(slow_count, 1)] = ji;
+        continue;
+      }
+    }
+    const bool fullpel_only = (cu.flags & XVCB200_CU_FULLPEL_MV) != 0;
+    const int RP = w + 10, TP = w + 2, PP = w + 2, OP = w + 2;
+    Sample *sref = reinterpret_cast<Sample *>(base);
+    int16_t *tmp = reinterpret_cast<int16_t *>(sref + (h + 9) * RP);
+    Sample *pred = reinterpret_cast<Sample *>(tmp + (h + 9) * TP);
+    Sample *org = pred + (h + 1) * PP;
+    team_sync<T>();                      // the previous job of this team is done with the buffers
+    // reference window: rows Y0-4 .. Y0+h+3, columns from the even sample at or left of X0-4
+    // (aligned 32-bit loads; `co` = 0/1 is where X0-4 sits in the staged row), original block.
+    const int co = (cu.x + mfx - 4) & 1;
+    {
+      const Sample *src = ref.base + (cu.y + mfy - 4) * ref.pitch + (cu.x + mfx - 4 - co);
+      const int wr = RP >> 1, total = (h + 8) * wr;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(sref);
+      for (int i0 = tid; i0 < total; i0 += 8 * T) {
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {          // eight independent loads in flight per thread
+          const int i = i0 + u * T;
+          if (i < total) {
+            const int y = i / wr, x = i - y * wr;
+            v[u] = __ldg(reinterpret_cast<const uint32_t *>(src + y * ref.pitch) + x);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int i = i0 + u * T;
+          if (i < total) dst[i] = v[u];
+        }
+      }
+      const int lw2 = 30 - __clz(w);          // log2(w / 2)
+      const Sample *so = orig.base + cu.y * orig.pitch + cu.x;
+      uint32_t *od = reinterpret_cast<uint32_t *>(org);
+      for (int i0 = tid; i0 < (w * h) >> 1; i0 += 4 * T) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * T;
+          if (i < (w * h) >> 1) v[u] = __ldg(reinterpret_cast<const uint32_t *>(so + (i >> lw2) * orig.pitch) + (i & ((w >> 1) - 1)));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * T;
+          if (i < (w * h) >> 1) od[(i >> lw2) * (OP >> 1) + (i & ((w >> 1) - 1))] = v[u];
+        }
+      }
+    }
+    team_sync<T>();
+
+    // H pass: tmp[row][c] for all h+8 rows, c in [0, ncols); raw sums of rows [prow0, prow0+h)
+    // also give the horizontal-only prediction.
+    auto h_product = [&](int frac, int col0, int ncols, bool want_pred, int prow0) {
+      const Taps8 taps = luma_taps(frac);
+      const int rows_n = h + 8, runs = w >> 3;
+      for (int task = tid; task < rows_n * runs; task += T) {
+        const int run = task / rows_n, row = task - run * rows_n;
+        const int c0 = run * 8;
+        const int cnt = run == runs - 1 ? ncols - c0 : 8;
+        const bool to_pred = want_pred && row >= prow0 && row < prow0 + h;
+        int16_t *tp = tmp + row * TP + c0;
+        Sample *pp = pred + (row - prow0) * PP + c0;
+        fir_run(sref + row * RP + co + col0 + c0, 1, cnt, taps, [&](int r, int sum) {
+          tp[r] = (int16_t)((sum + off1) >> sh1);
+          if (to_pred) pp[r] = (Sample)clip3i((sum + 32) >> 6, 0, maxv);
+        });
+      }
+    };
+    // V pass over the intermediate (FROM_TMP) or over the reference window: pred[r][c], r in
+    // [0, nrows), c in [0, ncols); the taps of output row 0 start at source row row0.
+    auto v_product = [&](bool from_tmp, int frac, int src_col0, int row0, int nrows, int ncols) {
+      const Taps8 taps = luma_taps(frac);
+      const int runs = h >> 3;
+      for (int task = tid; task < ncols * runs; task += T) {
+        const int run = task / ncols, col = task - run * ncols;
+        const int r0 = run * 8;
+        const int cnt = run == runs - 1 ? nrows - r0 : 8;
+        Sample *pp = pred + r0 * PP + col;
+        if (from_tmp) {
+          fir_run(tmp + (row0 + r0) * TP + col, TP, cnt, taps, [&](int r, int sum) {
+            pp[r * PP] = (Sample)clip3i((int)(int16_t)((sum + off2) >> sh2), 0, maxv);
+          });
+        } else {
+          fir_run(sref + (row0 + r0) * RP + co + src_col0 + col, RP, cnt, taps, [&](int r, int sum) {
+            pp[r * PP] = (Sample)clip3i((int)(int16_t)((sum + 32) >> 6), 0, maxv);
+          });
+        }
+      }
+    };
+
+    uint32_t best_cost = 0xffffffffu, best_dist = 0xffffffffu;
+    int best_x = fx0, best_y = fy0;
+    auto consider = [&](uint32_t satd, int mvx, int mvy) {      // inter_search.cc:925-934
+      const uint32_t dist = satd >> (bitdepth - 8);
+      if (dist < best_cost) {
+        const uint32_t cost = dist + ((lambda * mvd_bits(job.mvp[0], job.mvp[1], mvx, mvy)) >> 16);
+        if (cost < best_cost) { best_cost = cost; best_dist = dist; best_x = mvx; best_y = mvy; }
+      }
+    };
+    // The search as a list of steps, each = [one filter pass] + SATD of the 1..4 candidates its
+    // plane holds, executed by ONE loop so that every routine exists once in the code (the
+    // kernel has to stay inside the instruction cache: warps of different teams run different
+    // steps at the same time).  SATD sums land in sd[]: 0 = full-pel, 1..8 = half-pel list,
+    // 9 + 3j + k = quarter-pel candidate (x index j, y index k).
+    int bx = fx0, by = fy0;
+#pragma unroll 1
+    for (int s = 0; s < 16; s++) {
+      int kind = 0;            // 0 none, 1 horizontal, 2 vertical from the reference, 3 vertical from the intermediate
+      int frac = 8, col0 = 0, row0 = 0, nrows = h, ncols = w, want_pred = 0, nc = 1, dst = 0;
+      unsigned offs = 0;
+      const Sample *pq = pred;
+      int ppitch = PP;
+      if (s == 0) { pq = sref + 4 * RP + 4 + co; ppitch = RP; }
+      else if (s == 1) { kind = 2; col0 = 4; nrows = h + 1; nc = 2; offs = 2u << 2; dst = 1; }             // (0,-1) (0,1)
+      else if (s == 2) { kind = 1; ncols = w + 1; want_pred = 1; row0 = 4; nc = 2; offs = 1u << 2; dst = 3; }  // (-1,0) (1,0)
+      else if (s == 3) { kind = 3; nrows = h + 1; ncols = w + 1; nc = 4; offs = (1u << 2) | (2u << 4) | (3u << 6); dst = 5; }
+      else {
+        if (s == 4) {          // half-pel decisions in list order, then the quarter-pel pass around the winner
+          team_sync<T>();
+          consider(sd[0], fx0, fy0);
+          const int hx[8] = {0, 0, -1, 1, -1, 1, -1, 1}, hy[8] = {-1, 1, 0, 0, -1, -1, 1, 1};
+#pragma unroll
+          for (int i = 0; i < 8; i++) consider(sd[1 + i], fx0 + hx[i] * 8, fy0 + hy[i] * 8);
+          bx = best_x; by = best_y;
+        }
+        const int q = s - 4, j = q >> 2, kk = q & 3;
+        const int xv = bx + (j - 1) * 4;
+        const int ixr = (xv >> 4) - mfx, fxj = xv & 15;
+        if (kk == 0) {         // horizontal plane of x index j (+ the candidate on an integer row, if any)
+          if (fxj == 0) continue;
+          int k0 = -1;
+          for (int k = 0; k < 3; k++)
+            if (((by + (k - 1) * 4) & 15) == 0 && !(j == 1 && k == 1)) k0 = k;
+          kind = 1; frac = fxj; col0 = ixr + 1; want_pred = k0 >= 0;
+          row0 = 4 + (k0 >= 0 ? ((by + (k0 - 1) * 4) >> 4) - mfy : 0);
+          nc = k0 >= 0 ? 1 : 0; dst = 9 + 3 * j + (k0 >= 0 ? k0 : 0);
+        } else {
+          const int k = kk - 1;
+          const int yv = by + (k - 1) * 4;
+          const int iyr = (yv >> 4) - mfy, fyk = yv & 15;
+          if (fyk == 0 || (j == 1 && k == 1)) continue;
+          kind = fxj != 0 ? 3 : 2; frac = fyk; col0 = 4 + ixr; row0 = iyr + 1; dst = 9 + 3 * j + k;
+        }
+      }
+      if (kind == 1) h_product(frac, col0, ncols, want_pred != 0, row0);
+      else if (kind != 0) v_product(kind == 3, frac, col0, row0, nrows, ncols);
+      team_sync<T>();
+      if (nc > 0) {
+        unsigned sum[4];
+        satd_candidates<T>(org, OP, pq, ppitch, offs, nc, w, h, tid, s_part, sum);
+        if (tid == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            if (c < nc) sd[dst + c] = sum[c];
+        }
+      }
+      if (fullpel_only) break;
+    }
+    team_sync<T>();
+    if (fullpel_only) {
+      best_dist = best_cost = sd[0] >> (bitdepth - 8);
+    } else {
+      // order: (0,-1) (0,1) (-1,-1) (1,-1) (-1,0) (1,0) (-1,1) (1,1)
+      const int qx[8] = {0, 0, -1, 1, -1, 1, -1, 1}, qy[8] = {-1, 1, -1, -1, 0, 0, 1, 1};
+#pragma unroll
+      for (int i = 0; i < 8; i++) consider(sd[9 + 3 * (qx[i] + 1) + qy[i] + 1], bx + qx[i] * 4, by + qy[i] * 4);
+    }
+    if (tid == 0) {
+      res[ji].mv[0] = best_x; res[ji].mv[1] = best_y;
+      res[ji].dist = best_dist; res[ji].cost = best_cost;
+    }
+  }
+}
+
+static int max_team_bytes(int max_area, int min_area) {
+  int best = 0;
+  for (int w = 8; w <= 64; w <<= 1)
+    for (int h = 8; h <= 64; h <<= 1)
+      if (w * h <= max_area && w * h > min_area && subpel_team_bytes(w, h) > best) best = subpel_team_bytes(w, h);
+  return best;
+}
+
+cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
+                                 int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
+                                 xvcb200_me_result *d_res, int *d_lists) {
+  if (n <= 0) return cudaSuccess;
+  static int num_sms = 0, bytes0 = 0, bytes1 = 0, bytes2 = 0, occ0 = 1, occ1 = 1, occ2 = 1;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    bytes0 = max_team_bytes(256, 0);
+    bytes1 = max_team_bytes(1024, 256);
+    bytes2 = max_team_bytes(4096, 1024);
+    cudaError_t e = cudaFuncSetAttribute(subpel_team_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * bytes0);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes2);
+    if (e != cudaSuccess) { num_sms = 0; return e; }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, subpel_team_kernel<32>, 128, 4 * bytes0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, subpel_team_kernel<128>, 128, bytes1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, subpel_team_kernel<256>, 256, bytes2);
+    if (occ0 < 1) occ0 = 1;
+    if (occ1 < 1) occ1 = 1;
+    if (occ2 < 1) occ2 = 1;
+  }
+  int *counts = d_lists + 4 * (size_t)n;
+  cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  g_launch_count += 5;
+  subpel_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, d_jobs, n, d_lists, counts);
+  int *slow = d_lists + 3 * (size_t)n;
+  // persistent grids: as many CTAs as fit, each strides over its class list (largest blocks first)
+  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + 2 * (size_t)n, counts + 2, slow, counts + 3,
+                                                         bytes2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s>>>(d_cus, d_jobs, d_lists + (size_t)n, counts + 1, slow, counts + 3,
+                                                          bytes1, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s>>>(d_cus, d_jobs, d_lists, counts, slow, counts + 3, bytes0,
+                                                             bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_generic_kernel<<<num_sms * 4, 128, 0, s>>>(d_cus, d_jobs, slow, counts + 3, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  return cudaGetLastError();
+}
+
+}  // namespace xvcb
