@@ -388,10 +388,10 @@ __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, ui
   g.fast = cu.h > 8;                       // InterSearch::GetFullpelMetric, inter_search.cc:1059-1069
   g.rows = g.fast ? cu.h >> 1 : cu.h;
   g.rstep = g.fast ? 2 : 1;
-  g.lpw = ilog2i(cu.w) - 1;
+  g.lpw = 30 - __clz((int)cu.w);
   const int pairs = g.rows << g.lpw;
   g.G = pairs < 32 ? pairs : 32;
-  g.lG = ilog2i(g.G);
+  g.lG = 31 - __clz(g.G);
   g.bd_shift = bitdepth - 8;
   g.mvpx = mvpx; g.mvpy = mvpy;
   g.down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
@@ -422,13 +422,14 @@ __global__ void segment_sum_kernel(PlaneView src, Sample *__restrict__ dst00, in
 __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int rx0, int ry0, int bh, int cpr, int spw,
                                           uint32_t *s_region, int tid, int nthreads) {
   const int total = bh * cpr;
+  const uint32_t magic = 0xffffffffu / (uint32_t)cpr + 1u;    // idx / cpr == umulhi(idx, magic) for idx * cpr < 2^32
   for (int idx0 = tid; idx0 < total; idx0 += 4 * nthreads) {
     uint4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {            // four independent 16-byte loads in flight per thread
       const int idx = idx0 + u * nthreads;
       if (idx < total) {
-        const int row = idx / cpr, ch = idx - row * cpr;
+        const int row = (int)__umulhi((uint32_t)idx, magic), ch = idx - row * cpr;
         v[u] = __ldg(reinterpret_cast<const uint4 *>(plane00 + (ry0 + row) * pitch + rx0) + ch);
       }
     }
@@ -436,7 +437,7 @@ __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int 
     for (int u = 0; u < 4; u++) {
       const int idx = idx0 + u * nthreads;
       if (idx < total) {
-        const int row = idx / cpr, ch = idx - row * cpr;
+        const int row = (int)__umulhi((uint32_t)idx, magic), ch = idx - row * cpr;
         uint32_t *d = s_region + row * spw + ch * 4;
         const int left = spw - ch * 4;
         d[0] = v[u].x;
@@ -456,18 +457,22 @@ __device__ __forceinline__ uint32_t seg_bound(const uint16_t *rp, int row_stride
   uint32_t lb = 0;
   if (NSEG == 1) {
     const uint16_t *s16 = reinterpret_cast<const uint16_t *>(seg);
-#pragma unroll 4
-    for (int r = 0; r < rows; r++) lb = __usad((unsigned)rp[r * row_stride], (unsigned)s16[r], lb);
-  } else {
-#pragma unroll 2
-    for (int r = 0; r < rows; r++) {
+    for (int r = 0; r < rows; r += 4) {       // rows is a multiple of 4
 #pragma unroll
-      for (int k = 0; k < NSEG; k += 2) {
-        const uint32_t a2 = seg[(r * NSEG + k) >> 1];
-        lb = __usad((unsigned)rp[k * 8], a2 & 0xffffu, lb);
-        lb = __usad((unsigned)rp[k * 8 + 8], a2 >> 16, lb);
+      for (int u = 0; u < 4; u++) lb = __usad((unsigned)rp[(r + u) * row_stride], (unsigned)s16[r + u], lb);
+    }
+  } else {
+    for (int r = 0; r < rows; r += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+#pragma unroll
+        for (int k = 0; k < NSEG; k += 2) {
+          const uint32_t a2 = seg[((r + u) * NSEG + k) >> 1];
+          lb = __usad((unsigned)rp[k * 8], a2 & 0xffffu, lb);
+          lb = __usad((unsigned)rp[k * 8 + 8], a2 >> 16, lb);
+        }
+        rp += row_stride;
       }
-      rp += row_stride;
     }
   }
   return lb;
@@ -475,9 +480,9 @@ __device__ __forceinline__ uint32_t seg_bound(const uint16_t *rp, int row_stride
 
 constexpr int kTzThreads = 512;
 constexpr int kTzWarps = kTzThreads / 32;
-constexpr int kMaxGroupJobs = 128;       // jobs handled per pass over a group
+constexpr int kMaxGroupJobs = 64;        // jobs handled per pass over a group
 constexpr int kTileWords = 64 * 33;      // original CTU as packed pairs, rows padded to 33 words
-constexpr int kSegWords = 128;           // segment sums of the block being bounded (<= 32 rows x 8)
+constexpr int kSegWords = 256;           // segment sums of the blocks being bounded: 512 x uint16 (a tiled CTU needs <= 512)
 
 struct TzGroup { int first, count; };    // run of entries in job_index: jobs sharing a reference picture and a CTU
 
@@ -488,7 +493,9 @@ struct SJob {                            // one job of the current group, in sha
   int slox, sloy, nx, ny;                // raster grid (valid when need != 0)
   uint32_t cost_in;
   int need;                              // 0: no raster; 1: raster, box staged; 2: raster, window outside the staged box
-  int list_off, list_cnt;                // survivors in the pool; list_off < 0: dense scan
+  int list_off, list_cnt;                // survivors in the pool (shared by the jobs of one bound batch); list_off < 0: dense scan
+  int task0;                             // first bound task of the job in its batch, -1: not in the batch
+  int seg_off;                           // its segment sums in s_seg
   unsigned long long key;                // best (cost << 32 | scan position) of the exact pass
 };
 
@@ -531,8 +538,10 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   uint16_t *s_seg = reinterpret_cast<uint16_t *>(smem + kTileWords);
   SJob *s_job = reinterpret_cast<SJob *>(smem + kTileWords + kSegWords);
   uint32_t *s_region = smem + kTileWords + kSegWords + kMaxGroupJobs * (sizeof(SJob) / 4);
-  __shared__ int s_group, s_box[4], s_next, s_count, s_pool_used, s_any_raster;
+  __shared__ int s_group, s_box[4], s_next, s_count, s_pool_used, s_any_raster, s_batch_end, s_batch_tasks;
   __shared__ uint32_t s_dist[32];
+  __shared__ int s_cls[10], s_ncoop;
+  __shared__ unsigned char s_order[kMaxGroupJobs];    // jobs of the group, largest block first
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
   long long t_mark = prof ? clock64() : 0;
@@ -558,6 +567,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
         s_pool_used = 0; s_next = 0; s_any_raster = 0;
       }
+      if (tid < 10) s_cls[tid] = 0;
       __syncthreads();
       // job descriptors -> shared memory; bounding box of the search windows (block extent included)
       for (int k = tid; k < kn; k += kTzThreads) {
@@ -574,8 +584,20 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         min_max_mv(cu.x, cu.y, ref.width, ref.height, job.mvp[0], job.mvp[1], job.search_range, lo, hi);
         atomicMin(&s_box[0], cu.x + lo[0]); atomicMin(&s_box[1], cu.y + lo[1]);
         atomicMax(&s_box[2], cu.x + hi[0] + cu.w); atomicMax(&s_box[3], cu.y + hi[1] + cu.h);
+        atomicAdd(&s_cls[__clz((int)cu.w * cu.h) - 19], 1);       // area 4096 -> class 0 ... 16 -> class 8
       }
       __syncthreads();
+      if (tid == 0) {          // class counts -> first slot of each class; blocks of >= 2048 samples are searched CTA-wide
+        s_ncoop = s_cls[0] + s_cls[1];
+        int off = 0;
+        for (int c = 0; c < 10; c++) { const int n = s_cls[c]; s_cls[c] = off; off += n; }
+        s_next = s_ncoop;
+      }
+      __syncthreads();
+      for (int k = tid; k < kn; k += kTzThreads)
+        s_order[atomicAdd(&s_cls[__clz((int)s_job[k].w * s_job[k].h) - 19], 1)] = (unsigned char)k;
+      __syncthreads();
+      const int n_coop = s_ncoop;
       const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
       const int bw = rx1 - rx0, bh = ry1 - ry0;
       const int spw = ((bw + 1) / 2 + 1) | 1;
@@ -586,7 +608,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       // original CTU -> shared memory (all jobs of a group lie in one CTU)
       for (int q = tid; q < 64 * 32; q += kTzThreads) {
         const int row = q >> 5, col = q & 31;
-        s_tile[row * 33 + col] = ld_pair(orig.base + (ctu_y + row) * orig.pitch + ctu_x + col * 2);
+        s_tile[row * 33 + col] = __ldg(reinterpret_cast<const uint32_t *>(orig.base + (ctu_y + row) * orig.pitch + ctu_x) + col);
       }
       if (staged) stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
       __syncthreads();
@@ -605,27 +627,9 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
           s_any_raster = 1;
         }
       };
-      for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&s_next, 1);
-        k = __shfl_sync(XVCB_FULL, k, 0);
-        if (k >= kn) break;
-        SJob &sj = s_job[k];
+      for (int o = 0; o < n_coop; o++) {
+        SJob &sj = s_job[s_order[o]];
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        if ((g.rows << g.lpw) >= 512) continue;
-        xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
-        xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
-        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
-        TzJobState st;
-        tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
-        if (lane == 0) finish_phase1(sj, g, st);
-      }
-      __syncthreads();
-      for (int k = 0; k < kn; k++) {
-        SJob &sj = s_job[k];
-        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        if ((g.rows << g.lpw) < 512) continue;      // uniform
         xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
         xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
         const CtaEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
@@ -633,6 +637,21 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         TzJobState st;
         tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
         if (tid == 0) finish_phase1(sj, g, st);
+      }
+      for (;;) {
+        int o = 0;
+        if (lane == 0) o = atomicAdd(&s_next, 1);
+        o = __shfl_sync(XVCB_FULL, o, 0);
+        if (o >= kn) break;
+        SJob &sj = s_job[s_order[o]];
+        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
+        xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
+        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
+        TzJobState st;
+        tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
+        if (lane == 0) finish_phase1(sj, g, st);
       }
       __threadfence_block();
       __syncthreads();
@@ -645,57 +664,108 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
           __syncthreads();
           lap(3);
           const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
-          for (int k = 0; k < kn; k++) {
-            const SJob &sj = s_job[k];
-            if (sj.need != 1 || sj.w < 8 || sj.nx * sj.ny > 65535) continue;      // uniform
-            const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-            const int slox = sj.slox, sloy = sj.sloy, nx = sj.nx, ny = sj.ny;
-            const uint32_t cost_in = sj.cost_in;
-            const int lsg = g.lpw - 2, nseg = 1 << lsg;                // segments per row
-            const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
-            for (int q = tid; q < (g.rows << lsg); q += kTzThreads) {
-              const int row = q >> lsg, sg = q & (nseg - 1);
-              const uint32_t *p = tp + row * g.rstep * 33 + sg * 4;
-              const uint32_t s2 = p[0] + p[1] + p[2] + p[3];            // two 16-bit partial sums, no carry (<= 4 x 4095)
-              s_seg[q] = (uint16_t)((s2 & 0xffff) + (s2 >> 16));
+          const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
+          // Jobs are bounded in batches (as many as have room for their segment sums); inside a
+          // batch the (grid column, 32 grid rows) tasks of ALL jobs form one list that the warps
+          // take dynamically.
+          for (int kb = 0; kb < kn;) {                         // uniform
+            if (tid == 0) {
+              int used = 0, tasks = 0, k = kb;
+              for (; k < kn; k++) {
+                SJob &sj = s_job[k];
+                sj.task0 = -1;
+                if (sj.need != 1 || sj.w < 8 || sj.nx * sj.ny > 65535) continue;
+                const int segs = (sj.h > 8 ? sj.h >> 1 : sj.h) * (sj.w >> 3);
+                if (used + segs > 2 * kSegWords) break;
+                sj.seg_off = used; sj.task0 = tasks;
+                used += (segs + 1) & ~1;
+                tasks += sj.nx * ((sj.ny + 31) >> 5);
+              }
+              s_batch_end = k; s_batch_tasks = tasks; s_next = 0; s_count = 0;
             }
-            if (tid == 0) s_count = 0;
+            __syncthreads();
+            const int ke = s_batch_end, ntasks = s_batch_tasks;
+            for (int k = kb + warp; k < ke; k += kTzWarps) {    // segment sums of the original blocks, a warp per job
+              const SJob &sj = s_job[k];
+              if (sj.task0 < 0) continue;
+              const int rstep = sj.h > 8 ? 2 : 1, rows = sj.h > 8 ? sj.h >> 1 : sj.h;
+              const int lsg = 28 - __clz((int)sj.w);            // log2(w / 8)
+              const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
+              for (int q = lane; q < (rows << lsg); q += 32) {
+                const int row = q >> lsg, sg = q & ((1 << lsg) - 1);
+                const uint32_t *p = tp + row * rstep * 33 + sg * 4;
+                const uint32_t s2 = p[0] + p[1] + p[2] + p[3];            // two 16-bit partial sums, no carry (<= 4 x 4095)
+                s_seg[sj.seg_off + q] = (uint16_t)((s2 & 0xffff) + (s2 >> 16));
+              }
+            }
             __syncthreads();
             const int base = s_pool_used;
             const int room = pool_cap - base;
-            const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
-            const int rstride = g.rstep * 2 * spw;
-            const int passes = (ny + 31) >> 5;
-            for (int task = warp; task < nx * passes; task += kTzWarps) {
-              const int pass = task / nx, i = task - pass * nx;
-              const int j = pass * 32 + lane, jj = min(j, ny - 1);
-              const int cy = sloy + 5 * jj, oy = g.y + cy - ry0;
-              const int cx = slox + 5 * i, ox = g.x + cx - rx0;
-              const uint16_t *rp = s8reg + oy * (2 * spw) + ox;
-              uint32_t lb = 0;
-              switch (lsg) {
-                case 0: lb = seg_bound<1>(rp, rstride, seg32, g.rows); break;
-                case 1: lb = seg_bound<2>(rp, rstride, seg32, g.rows); break;
-                case 2: lb = seg_bound<4>(rp, rstride, seg32, g.rows); break;
-                default: lb = seg_bound<8>(rp, rstride, seg32, g.rows); break;
-              }
-              const uint32_t lbd = g.fast ? (lb * 2) >> g.bd_shift : lb >> g.bd_shift;
-              const bool keep = j < ny && lbd + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16) < cost_in;
-              const unsigned mask = __ballot_sync(XVCB_FULL, keep);
-              if (mask) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
-                wbase = __shfl_sync(XVCB_FULL, wbase, 0);
-                const int slot = wbase + __popc(mask & ((1u << lane) - 1));
-                if (keep && slot < room) pool[base + slot] = ((uint32_t)k << 16) | (uint32_t)(j * nx + i);
+            {
+              int kcur = kb - 1, tend = 0, tbeg = 0;           // the job the warp's current task belongs to
+              int nx = 1, ny = 1, slox = 0, sloy = 0, lsg = 0, rstride = 0, rows = 0, gx = 0, gy = 0, fast = 0, down = 0;
+              int mvpx = 0, mvpy = 0;
+              uint32_t cost_in = 0;
+              const uint32_t *segp = seg32;
+              for (int task = warp; task < ntasks; task += kTzWarps) {
+                while (task >= tend) {                           // tasks arrive in increasing order
+                  kcur++;
+                  const SJob &sj = s_job[kcur];
+                  if (sj.task0 < 0) continue;
+                  nx = sj.nx; ny = sj.ny; slox = sj.slox; sloy = sj.sloy; cost_in = sj.cost_in;
+                  tbeg = sj.task0; tend = tbeg + nx * ((ny + 31) >> 5);
+                  fast = sj.h > 8; rows = fast ? sj.h >> 1 : sj.h;
+                  lsg = 28 - __clz((int)sj.w);
+                  rstride = (fast ? 2 : 1) * 2 * spw;
+                  gx = sj.x - rx0; gy = sj.y - ry0;
+                  mvpx = sj.mvpx; mvpy = sj.mvpy; down = sj.fullpel ? 2 : 0;
+                  segp = seg32 + (sj.seg_off >> 1);
+                }
+                const int local = task - tbeg;
+                const int pass = local / nx, i = local - pass * nx;
+                const int j = pass * 32 + lane, jj = min(j, ny - 1);
+                const int cx = slox + 5 * i, cy = sloy + 5 * jj;
+                const uint32_t rate = (lambda * (exp_golomb_bits((cx * 16 - mvpx) >> (down + 2)) +
+                                                 exp_golomb_bits((cy * 16 - mvpy) >> (down + 2)))) >> 16;
+                // dropped iff dist_bound + rate >= cost_in, in raw SAD units: lb >= thr
+                uint32_t thr = 0;
+                if (j < ny && rate < cost_in) {
+                  const uint32_t need = (cost_in - rate) << (bitdepth - 8);
+                  thr = fast ? (need + 1) >> 1 : need;
+                }
+                const uint16_t *rp = s8reg + (gy + cy) * (2 * spw) + gx + cx;
+                uint32_t lb = 0;
+                switch (lsg) {
+                  case 0: lb = seg_bound<1>(rp, rstride, segp, rows); break;
+                  case 1: lb = seg_bound<2>(rp, rstride, segp, rows); break;
+                  case 2: lb = seg_bound<4>(rp, rstride, segp, rows); break;
+                  default: lb = seg_bound<8>(rp, rstride, segp, rows); break;
+                }
+                const bool keep = lb < thr;
+                const unsigned mask = __ballot_sync(XVCB_FULL, keep);
+                if (mask) {
+                  int wbase = 0;
+                  if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
+                  wbase = __shfl_sync(XVCB_FULL, wbase, 0);
+                  const int slot = wbase + __popc(mask & ((1u << lane) - 1));
+                  if (keep && slot < room) pool[base + slot] = ((uint32_t)kcur << 16) | (uint32_t)(j * nx + i);
+                }
               }
             }
             __syncthreads();
             if (tid == 0) {
-              if (s_count <= room) { s_job[k].list_off = base; s_job[k].list_cnt = s_count; s_pool_used = base + s_count; }
-              if (prof) { atomicAdd(&prof[8], (unsigned long long)(nx * ny)); atomicAdd(&prof[9], (unsigned long long)s_count); }
+              unsigned long long cands = 0;
+              for (int k = kb; k < ke; k++) {
+                SJob &sj = s_job[k];
+                if (sj.task0 < 0) continue;
+                cands += (unsigned long long)(sj.nx * sj.ny);
+                if (s_count <= room) { sj.list_off = base; sj.list_cnt = s_count; }
+              }
+              if (s_count <= room) s_pool_used = base + s_count;
+              if (prof) { atomicAdd(&prof[8], cands); atomicAdd(&prof[9], (unsigned long long)s_count); }
             }
             __syncthreads();
+            kb = ke;
           }
           lap(4);
           stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
@@ -776,35 +846,32 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         }
         __threadfence_block();
       }
-      if (tid == 0) s_next = 0;
+      if (tid == 0) s_next = n_coop;
       __syncthreads();
       lap(6);
 
       // ---------------- phase 3: small blocks one warp per job, large blocks CTA-wide
-      for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&s_next, 1);
-        k = __shfl_sync(XVCB_FULL, k, 0);
-        if (k >= kn) break;
-        const SJob &sj = s_job[k];
+      for (int o = 0; o < n_coop; o++) {
+        const SJob &sj = s_job[s_order[o]];
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        if ((g.rows << g.lpw) >= 512) continue;
-        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
-        TzJobState st = states[sj.ji];
-        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }     // empty scan window (:146-147)
-        tz_phase3(g, sj.range, ev, lane, st, &res[sj.ji]);
-      }
-      __syncthreads();
-      for (int k = 0; k < kn; k++) {
-        const SJob &sj = s_job[k];
-        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        if ((g.rows << g.lpw) < 512) continue;      // uniform
         const CtaEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
                          staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, s_dist, lane, warp, kTzWarps};
         TzJobState st = states[sj.ji];
-        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }
+        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }     // empty scan window (:146-147)
         tz_phase3(g, sj.range, ev, lane, st, tid == 0 ? &res[sj.ji] : nullptr);
+      }
+      for (;;) {
+        int o = 0;
+        if (lane == 0) o = atomicAdd(&s_next, 1);
+        o = __shfl_sync(XVCB_FULL, o, 0);
+        if (o >= kn) break;
+        const SJob &sj = s_job[s_order[o]];
+        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
+        TzJobState st = states[sj.ji];
+        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }
+        tz_phase3(g, sj.range, ev, lane, st, &res[sj.ji]);
       }
       __syncthreads();
       lap(7);
