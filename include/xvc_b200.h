@@ -277,6 +277,20 @@ int xvcb200_upload_picture(xvcb200_ctx *ctx, int slot, const uint16_t *const pla
 int xvcb200_download_picture(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]);
 int xvcb200_download_coeff(xvcb200_ctx *ctx, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]);
 int xvcb200_upload_coeff(xvcb200_ctx *ctx, int slot, const int16_t *const planes[3], const ptrdiff_t strides[3]);
+/* The same transfers on a second (copy) stream owned by the context, so that they overlap the
+ * kernels of another picture.  Ordering is kept by events inside the library: an upload starts
+ * once the work enqueued BEFORE the call is done and is awaited by work enqueued after it; a
+ * download starts once the work enqueued before the call is done, and later work that writes
+ * the same slot (or the CU array) waits for it.  To overlap, alternate between two slots and
+ * enqueue the upload of picture n+1 before xvcb200_encode_picture of picture n.  Host buffers
+ * should be page-locked.  xvcb200_sync_copies() waits for the copy stream, xvcb200_wait_download()
+ * for the transfers of one slot (the copy stream runs them in call order). */
+int xvcb200_upload_picture_async(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]);
+int xvcb200_download_picture_async(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]);
+int xvcb200_download_coeff_async(xvcb200_ctx *ctx, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]);
+int xvcb200_get_cus_async(xvcb200_ctx *ctx, xvcb200_cu *cus, int n);
+int xvcb200_wait_download(xvcb200_ctx *ctx, int slot);   /* host waits for the last async download of a slot; slot < 0: the CU array */
+int xvcb200_sync_copies(xvcb200_ctx *ctx);
 /* one plane incl. its 80 / 40 sample border, tight (h + 2*pad) x (w + 2*pad) */
 int xvcb200_download_padded(xvcb200_ctx *ctx, int slot, int comp, uint16_t *dst);
 /* YuvPicture::PadBorder (yuv_pic.cc:118-150) */

@@ -361,3 +361,61 @@ def test_encode_picture(oracle, pic_type, bd):
     for c in range(3):
         assert np.array_equal(ctx.download_padded(4, c), rec.full[c]), c
         assert np.array_equal(levg[c], levels[c]), c
+
+
+def test_async_transfers_pipeline(oracle):
+    """Two pictures in flight on alternating slot sets (uploads / downloads on the copy stream)
+    give the same levels, reconstruction and CU decisions as the synchronous calls, picture by
+    picture -- the events inside the library keep every transfer ordered against the kernels."""
+    width, height, bd, qp = 200, 104, 10, 32
+    lam = workload.lambda_for_qp(qp)
+    pics = [common.frames(width, height, bd, 500 + i) for i in range(4)]
+    cus = workload.make_partition(width, height, seed=19, min_size=8, qp=qp)
+    ctx = lib.Context(width, height, bd, num_slots=9)
+    # slots: 1/2 references (shared), 3 prediction; set A = (0 orig, 4 rec, 5 levels), set B = (6, 7, 8)
+    _, r0, r1 = pics[0]
+    for s, f in ((1, r0), (2, r1)):
+        ctx.upload(s, f)
+        ctx.pad_border(s)
+    sets = [dict(orig=0, rec=4, coeff=5), dict(orig=6, rec=7, coeff=8)]
+    prms = [common.picture_params(0, lam, slots=dict(orig=st["orig"], ref0=1, ref1=2, pred=3, rec=st["rec"], coeff=st["coeff"]))
+            for st in sets]
+    # synchronous truth
+    truth = []
+    for cur, _, _ in pics:
+        ctx.upload(0, cur)
+        ctx.set_cus(cus)
+        ctx.encode_picture(prms[0], want_results=False)
+        truth.append((ctx.download(4), ctx.download_coeff(5), ctx.get_cus()))
+    # pipelined
+    host = [dict(rec=[np.zeros_like(p) for p in pics[0][0]], lev=[np.zeros(p.shape, dtype=np.int16) for p in pics[0][0]],
+                 cus=np.zeros(len(cus), dtype=abi.cu_dtype)) for _ in range(2)]
+    got = []
+
+    def collect(i):
+        s = i & 1
+        ctx.wait_download(sets[s]["rec"])
+        got.append(([p.copy() for p in host[s]["rec"]], [p.copy() for p in host[s]["lev"]], host[s]["cus"].copy()))
+
+    ctx.upload_async(sets[0]["orig"], pics[0][0])
+    for i in range(len(pics)):
+        s = i & 1
+        if i + 1 < len(pics):
+            ctx.upload_async(sets[1 - s]["orig"], pics[i + 1][0])
+        ctx.set_cus(cus)
+        ctx.encode_picture(prms[s], want_results=False)
+        ctx.get_cus_async(host[s]["cus"])
+        ctx.download_coeff_async(sets[s]["coeff"], host[s]["lev"])
+        ctx.download_async(sets[s]["rec"], host[s]["rec"])
+        if i >= 1:
+            collect(i - 1)
+    collect(len(pics) - 1)
+    ctx.sync_copies()
+    ctx.sync()
+    for i, ((rec_t, lev_t, cus_t), (rec_g, lev_g, cus_g)) in enumerate(zip(truth, got)):
+        for c in range(3):
+            assert np.array_equal(rec_t[c], rec_g[c]), (i, c)
+            assert np.array_equal(lev_t[c], lev_g[c]), (i, c)
+        for f in ("flags", "ref_idx", "mv"):
+            assert np.array_equal(cus_t[f], cus_g[f]), (i, f)
+    assert any(np.any(l[0]) for _, l, _ in got)      # the pictures have non-zero levels

@@ -359,11 +359,21 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int *d_counter = nullptr;
   int *d_subpel_lists = nullptr; int subpel_lists_cap = 0;   // job lists by block-size class + their counters
   // the picture pipeline's own grouping (job = cu * nl + list), built by set_cus for nl = 1 and 2
-  int *d_pipe_index[2] = {nullptr, nullptr}; int pipe_index_cap[2] = {0, 0};
-  int *d_pipe_groups[2] = {nullptr, nullptr}; int pipe_groups_cap[2] = {0, 0};
+  int *d_pipe_index[2] = {nullptr, nullptr};
+  int *d_pipe_groups[2] = {nullptr, nullptr};
   int pipe_n_groups[2] = {0, 0};
-  void *h_setcus = nullptr; size_t h_setcus_cap = 0;   // pinned staging of set_cus, guarded by setcus_ev
-  cudaEvent_t setcus_ev = nullptr;
+  // Everything set_cus sends ([cus][tu list][index nl=1][index nl=2][groups nl=1][groups nl=2]) is ONE blob,
+  // double-buffered: the upload for the next picture goes to the other blob on the upload stream
+  // while the kernels of the current picture still use theirs.  d_cus / d_tu_list / d_pipe_* point
+  // into the current blob.
+  struct CuBlob {
+    uint8_t *d = nullptr; size_t cap = 0;       // device
+    void *h = nullptr; size_t hcap = 0;         // page-locked host image
+    cudaEvent_t up_ev = nullptr;                // upload done (also: host image free again)
+    cudaEvent_t free_ev = nullptr;              // compute enqueued while it was current is done
+    cudaEvent_t dl_ev = nullptr; bool dl_pending = false;   // xvcb200_get_cus_async reading it
+  } blob[2];
+  int cur_blob = -1;
   // successive-elimination support: 8-sample segment sums of every slot's luma plane, survivor pool
   std::vector<PlaneView> h_luma_views;
   std::vector<Sample *> h_s8_base;
@@ -377,6 +387,22 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   cudaEvent_t side_ev[kSide] = {nullptr};
   cudaEvent_t fork_ev = nullptr;
   int n_side = 0;
+  // tight device staging of whole pictures for PCIe transfers: [stream set 0 = context stream, 1 = copy stream][0 up, 1 down]
+  uint16_t *d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  // second stream for transfers that overlap compute (xvcb200_*_async)
+  cudaStream_t copy_stream = nullptr;         // device -> host
+  cudaStream_t up_stream = nullptr;           // host -> device (own stream: uploads never queue behind downloads)
+  cudaEvent_t mark_ev = nullptr;              // "compute enqueued so far", re-recorded per transfer
+  std::vector<cudaEvent_t> up_ev; std::vector<char> up_pending;   // per slot; pending = 1 + staging index (tight) or 1 (direct)
+  // staging rings of the async transfers: the copy streams only run DMA, the pack / unpack
+  // kernels run on the context stream in program order (a small kernel on another stream would
+  // wait for the persistent search kernels to leave the SMs)
+  static constexpr int kUpRing = 2, kDownRing = 4;
+  uint16_t *d_up_ring[kUpRing] = {nullptr}; cudaEvent_t up_ring_ev[kUpRing] = {nullptr};     // event: unpacked, buffer free
+  uint16_t *d_down_ring[kDownRing] = {nullptr}; cudaEvent_t down_ring_ev[kDownRing] = {nullptr}; // event: copied out, buffer free
+  unsigned up_ring_next = 0, down_ring_next = 0;
+  std::vector<char> up_tight;                 // per slot: staging index of the pending upload, -1 = written directly
+  std::vector<cudaEvent_t> dl_ev; std::vector<char> dl_pending;   // per slot, last entry = the CU array
   // optional per-stage timing of xvcb200_encode_picture (CUDA events on the context stream)
   bool profile = false;
   cudaEvent_t ev[9] = {nullptr};
@@ -387,6 +413,9 @@ struct CtxExtra {           // host-side state that is not needed by kernels
 
 struct CtxFull : public xvcb200_ctx { CtxExtra ex; };
 static CtxFull *full(xvcb200_ctx *c) { return static_cast<CtxFull *>(c); }
+static void join_uploads(CtxFull *c);
+static void join_upload_slot(CtxFull *c, int slot);
+static void join_downloads(CtxFull *c, int slot);
 
 template <typename T> static bool ensure(xvcb200_ctx *c, T **ptr, int *cap, int n) {
   if (n <= *cap) return true;
@@ -494,15 +523,27 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (!c->slots.empty() && c->slots[0].alloc) cudaFree(c->slots[0].alloc);   // one arena for all slots
-  cudaFree(c->d_cus); cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
+  cudaFree(c->d_cu_map); cudaFree(c->d_edge_bs[0]); cudaFree(c->d_edge_bs[1]);
   cudaFree(c->d_scratch); cudaFree(c->d_scratch2);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  for (int i = 0; i < 2; i++) { cudaFree(c->ex.d_pipe_index[i]); cudaFree(c->ex.d_pipe_groups[i]); }
-  if (c->ex.h_setcus) cudaFreeHost(c->ex.h_setcus);
-  if (c->ex.setcus_ev) cudaEventDestroy(c->ex.setcus_ev);
+  for (auto &b : c->ex.blob) {
+    cudaFree(b.d);
+    if (b.h) cudaFreeHost(b.h);
+    if (b.up_ev) cudaEventDestroy(b.up_ev);
+    if (b.free_ev) cudaEventDestroy(b.free_ev);
+    if (b.dl_ev) cudaEventDestroy(b.dl_ev);
+  }
+  if (c->ex.copy_stream) { cudaStreamSynchronize(c->ex.copy_stream); cudaStreamDestroy(c->ex.copy_stream); }
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) cudaFree(c->ex.d_stage[a][b]);
+  if (c->ex.up_stream) { cudaStreamSynchronize(c->ex.up_stream); cudaStreamDestroy(c->ex.up_stream); }
+  if (c->ex.mark_ev) cudaEventDestroy(c->ex.mark_ev);
+  for (cudaEvent_t e : c->ex.up_ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < CtxExtra::kUpRing; i++) { cudaFree(c->ex.d_up_ring[i]); if (c->ex.up_ring_ev[i]) cudaEventDestroy(c->ex.up_ring_ev[i]); }
+  for (int i = 0; i < CtxExtra::kDownRing; i++) { cudaFree(c->ex.d_down_ring[i]); if (c->ex.down_ring_ev[i]) cudaEventDestroy(c->ex.down_ring_ev[i]); }
+  for (cudaEvent_t e : c->ex.dl_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
-  cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_tu_list); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
+  cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
   if (c->ex.fork_ev) cudaEventDestroy(c->ex.fork_ev);
@@ -551,22 +592,60 @@ int xvcb200_slot_region(xvcb200_ctx *c, int slot, void **base, uint64_t *bytes) 
 
 static bool slot_ok(xvcb200_ctx *c, int slot) { return c && slot >= 0 && slot < (int)c->slots.size(); }
 
+// One picture between host planes and a slot, enqueued on `st`.  Tight host planes (stride ==
+// width) travel as one contiguous copy per plane through a tight device staging buffer plus a
+// pack / unpack kernel; a row-by-row 2-D copy of a padded plane runs at a fraction of the PCIe
+// rate.  Strided host planes take the 2-D copy.  set: 0 = context stream, 1 = copy stream.
+static int transfer_picture(xvcb200_ctx *ctx, int slot, void *const planes[3], const ptrdiff_t strides[3], bool to_device,
+                            cudaStream_t st, int set) {
+  CtxFull *c = full(ctx);
+  bool tight = (c->geom.width[0] & 7) == 0;
+  size_t samples = 0, off[3];
+  for (int p = 0; p < 3; p++) {
+    tight = tight && strides[p] == c->geom.width[p];
+    off[p] = samples;
+    samples += (size_t)c->geom.width[p] * c->geom.height[p];
+  }
+  if (tight) {
+    uint16_t *&stage = c->ex.d_stage[set][to_device ? 0 : 1];
+    if (!stage && !c->check(cudaMalloc(&stage, samples * 2), "cudaMalloc(staging)")) return c->status;
+    if (to_device) {
+      for (int p = 0; p < 3; p++)
+        if (!c->check(cudaMemcpyAsync(stage + off[p], planes[p], (size_t)c->geom.width[p] * c->geom.height[p] * 2,
+                                      cudaMemcpyHostToDevice, st), "upload_picture"))
+          return c->status;
+      c->check(launch_plane_pack(st, pic3(c, slot), stage, 0), "plane_unpack");
+    } else {
+      if (!c->check(launch_plane_pack(st, pic3(c, slot), stage, 1), "plane_pack")) return c->status;
+      for (int p = 0; p < 3; p++)
+        if (!c->check(cudaMemcpyAsync(planes[p], stage + off[p], (size_t)c->geom.width[p] * c->geom.height[p] * 2,
+                                      cudaMemcpyDeviceToHost, st), "download_picture"))
+          return c->status;
+    }
+    return c->status;
+  }
+  for (int p = 0; p < 3; p++) {
+    const cudaError_t e = to_device
+        ? cudaMemcpy2DAsync(c->slots[slot].base[p], (size_t)c->geom.pitch[p] * 2, planes[p], (size_t)strides[p] * 2,
+                            (size_t)c->geom.width[p] * 2, c->geom.height[p], cudaMemcpyHostToDevice, st)
+        : cudaMemcpy2DAsync(planes[p], (size_t)strides[p] * 2, c->slots[slot].base[p], (size_t)c->geom.pitch[p] * 2,
+                            (size_t)c->geom.width[p] * 2, c->geom.height[p], cudaMemcpyDeviceToHost, st);
+    if (!c->check(e, to_device ? "upload_picture" : "download_picture")) return c->status;
+  }
+  return c->status;
+}
+
 int xvcb200_upload_picture(xvcb200_ctx *c, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]) {
   if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
-  for (int p = 0; p < 3; p++)
-    if (!c->check(cudaMemcpy2DAsync(c->slots[slot].base[p], (size_t)c->geom.pitch[p] * 2, planes[p], (size_t)strides[p] * 2,
-                                    (size_t)c->geom.width[p] * 2, c->geom.height[p], cudaMemcpyHostToDevice, c->stream),
-                  "upload_picture"))
-      return c->status;
-  return XVCB200_OK;
+  join_upload_slot(full(c), slot);          // an async upload nobody consumed must not land on top of this one
+  join_downloads(full(c), slot);
+  // pageable host memory is consumed before cudaMemcpyAsync returns; page-locked memory must stay valid until the stream reaches the copy
+  return transfer_picture(c, slot, reinterpret_cast<void *const *>(const_cast<uint16_t *const *>(planes)), strides, true, c->stream, 0);
 }
 static int download_planes(xvcb200_ctx *c, int slot, void *const planes[3], const ptrdiff_t strides[3]) {
   if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
-  for (int p = 0; p < 3; p++)
-    if (!c->check(cudaMemcpy2DAsync(planes[p], (size_t)strides[p] * 2, c->slots[slot].base[p], (size_t)c->geom.pitch[p] * 2,
-                                    (size_t)c->geom.width[p] * 2, c->geom.height[p], cudaMemcpyDeviceToHost, c->stream),
-                  "download_picture"))
-      return c->status;
+  const int st = transfer_picture(c, slot, planes, strides, false, c->stream, 0);
+  if (st != XVCB200_OK) return st;
   return xvcb200_sync(c);
 }
 int xvcb200_download_picture(xvcb200_ctx *c, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]) {
@@ -586,8 +665,191 @@ int xvcb200_download_padded(xvcb200_ctx *c, int slot, int comp, uint16_t *dst) {
   return xvcb200_sync(c);
 }
 
+}  // extern "C"
+
+// ---- transfers on the copy stream.  Ordering is enforced with events, never by the host:
+//  * an async upload starts after all compute enqueued BEFORE the call (nobody still reads the
+//    slot) and compute enqueued after it waits for it (join_uploads);
+//  * an async download starts after all compute enqueued before the call; compute that later
+//    WRITES the same slot waits for it (join_downloads).
+static bool copy_setup(CtxFull *c) {
+  if (c->ex.copy_stream) return true;
+  if (!c->check(cudaStreamCreateWithFlags(&c->ex.copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)") ||
+      !c->check(cudaStreamCreateWithFlags(&c->ex.up_stream, cudaStreamNonBlocking), "cudaStreamCreate(upload)") ||
+      !c->check(cudaEventCreateWithFlags(&c->ex.mark_ev, cudaEventDisableTiming), "cudaEventCreate"))
+    return false;
+  c->ex.dl_ev.assign(c->slots.size() + 1, nullptr);
+  c->ex.dl_pending.assign(c->slots.size() + 1, 0);
+  c->ex.up_ev.assign(c->slots.size(), nullptr);
+  c->ex.up_pending.assign(c->slots.size(), 0);
+  c->ex.up_tight.assign(c->slots.size(), -1);
+  size_t samples = 0;
+  for (int p = 0; p < 3; p++) samples += (size_t)c->geom.width[p] * c->geom.height[p];
+  for (int i = 0; i < CtxExtra::kUpRing; i++)
+    if (!c->check(cudaMalloc(&c->ex.d_up_ring[i], samples * 2), "cudaMalloc(staging)") ||
+        !c->check(cudaEventCreateWithFlags(&c->ex.up_ring_ev[i], cudaEventDisableTiming), "cudaEventCreate"))
+      return false;
+  for (int i = 0; i < CtxExtra::kDownRing; i++)
+    if (!c->check(cudaMalloc(&c->ex.d_down_ring[i], samples * 2), "cudaMalloc(staging)") ||
+        !c->check(cudaEventCreateWithFlags(&c->ex.down_ring_ev[i], cudaEventDisableTiming), "cudaEventCreate"))
+      return false;
+  for (auto &e : c->ex.dl_ev)
+    if (!c->check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return false;
+  for (auto &e : c->ex.up_ev)
+    if (!c->check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate")) return false;
+  return true;
+}
+static bool copy_after_compute(CtxFull *c, cudaStream_t st) {
+  return c->check(cudaEventRecord(c->ex.mark_ev, c->stream), "cudaEventRecord") &&
+         c->check(cudaStreamWaitEvent(st, c->ex.mark_ev, 0), "cudaStreamWaitEvent");
+}
+// Compute waits only for pending uploads of the slots it reads (join_upload_slot): an upload
+// made ahead for the next picture must not hold back the kernels of the current one.
+static void join_upload_slot(CtxFull *c, int slot) {
+  if (c->ex.up_pending.empty() || slot < 0 || slot >= (int)c->ex.up_pending.size() || !c->ex.up_pending[slot]) return;
+  c->check(cudaStreamWaitEvent(c->stream, c->ex.up_ev[slot], 0), "cudaStreamWaitEvent");
+  c->ex.up_pending[slot] = 0;
+  const int k = c->ex.up_tight[slot];
+  if (k >= 0) {                 // the picture sits in a tight staging buffer: unpack it into the slot, here, in program order
+    c->check(launch_plane_pack(c->stream, pic3(c, slot), c->ex.d_up_ring[k], 0), "plane_unpack");
+    c->check(cudaEventRecord(c->ex.up_ring_ev[k], c->stream), "cudaEventRecord");
+    c->ex.up_tight[slot] = -1;
+  }
+}
+static void join_uploads(CtxFull *c) {          // entry points without an explicit read set: all pending uploads
+  for (int s = 0; s < (int)c->ex.up_pending.size(); s++) join_upload_slot(c, s);
+}
+static void join_downloads(CtxFull *c, int slot) {     // slot == -1: the CU array
+  if (slot < 0) {
+    if (c->ex.cur_blob >= 0 && c->ex.blob[c->ex.cur_blob].dl_pending) {
+      c->check(cudaStreamWaitEvent(c->stream, c->ex.blob[c->ex.cur_blob].dl_ev, 0), "cudaStreamWaitEvent");
+      c->ex.blob[c->ex.cur_blob].dl_pending = false;
+    }
+    return;
+  }
+  if (c->ex.dl_pending.empty()) return;
+  const size_t i = (size_t)slot;
+  if (!c->ex.dl_pending[i]) return;
+  c->check(cudaStreamWaitEvent(c->stream, c->ex.dl_ev[i], 0), "cudaStreamWaitEvent");
+  c->ex.dl_pending[i] = 0;
+}
+static bool host_planes_tight(const CtxFull *c, const ptrdiff_t strides[3]) {
+  bool tight = (c->geom.width[0] & 7) == 0;
+  for (int p = 0; p < 3; p++) tight = tight && strides[p] == c->geom.width[p];
+  return tight;
+}
+static int download_planes_async(CtxFull *c, int slot, void *const planes[3], const ptrdiff_t strides[3]) {
+  if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
+  if (!copy_setup(c)) return c->status;
+  if (host_planes_tight(c, strides)) {
+    // pack on the context stream (program order: the slot may be rewritten right after), DMA on the copy stream
+    const int k = (int)(c->ex.down_ring_next++ % CtxExtra::kDownRing);
+    c->check(cudaStreamWaitEvent(c->stream, c->ex.down_ring_ev[k], 0), "cudaStreamWaitEvent");
+    if (!c->check(launch_plane_pack(c->stream, pic3(c, slot), c->ex.d_down_ring[k], 1), "plane_pack") ||
+        !copy_after_compute(c, c->ex.copy_stream))
+      return c->status;
+    size_t off = 0;
+    for (int p = 0; p < 3; p++) {
+      const size_t cnt = (size_t)c->geom.width[p] * c->geom.height[p];
+      if (!c->check(cudaMemcpyAsync(planes[p], c->ex.d_down_ring[k] + off, cnt * 2, cudaMemcpyDeviceToHost, c->ex.copy_stream),
+                    "download_async"))
+        return c->status;
+      off += cnt;
+    }
+    c->check(cudaEventRecord(c->ex.down_ring_ev[k], c->ex.copy_stream), "cudaEventRecord");
+    c->check(cudaEventRecord(c->ex.dl_ev[slot], c->ex.copy_stream), "cudaEventRecord");   // for xvcb200_wait_download only
+    return c->status;
+  }
+  if (!copy_after_compute(c, c->ex.copy_stream)) return c->status;
+  if (transfer_picture(c, slot, planes, strides, false, c->ex.copy_stream, 1) != XVCB200_OK) return c->status;
+  c->check(cudaEventRecord(c->ex.dl_ev[slot], c->ex.copy_stream), "cudaEventRecord");
+  c->ex.dl_pending[slot] = 1;
+  return c->status;
+}
+
+extern "C" {
+
+int xvcb200_upload_picture_async(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  if (!slot_ok(ctx, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (!copy_setup(c)) return c->status;
+  if (host_planes_tight(c, strides)) {
+    // DMA into a tight staging buffer now; the unpack kernel runs on the context stream when the
+    // first call that reads the slot is enqueued (join_upload_slot), so the slot itself is only
+    // ever written in program order
+    if (c->ex.up_pending[slot]) join_upload_slot(c, slot);      // an earlier upload of this slot nobody consumed
+    const int k = (int)(c->ex.up_ring_next++ % CtxExtra::kUpRing);
+    for (size_t s = 0; s < c->ex.up_tight.size(); s++)          // a pending upload still owns this staging buffer
+      if (c->ex.up_pending[s] && c->ex.up_tight[s] == k) join_upload_slot(c, (int)s);
+    c->check(cudaStreamWaitEvent(c->ex.up_stream, c->ex.up_ring_ev[k], 0), "cudaStreamWaitEvent");
+    size_t off = 0;
+    for (int p = 0; p < 3; p++) {
+      const size_t cnt = (size_t)c->geom.width[p] * c->geom.height[p];
+      if (!c->check(cudaMemcpyAsync(c->ex.d_up_ring[k] + off, planes[p], cnt * 2, cudaMemcpyHostToDevice, c->ex.up_stream),
+                    "upload_picture_async"))
+        return c->status;
+      off += cnt;
+    }
+    c->check(cudaEventRecord(c->ex.up_ev[slot], c->ex.up_stream), "cudaEventRecord");
+    c->ex.up_pending[slot] = 1;
+    c->ex.up_tight[slot] = (char)k;
+    return c->status;
+  }
+  if (!copy_after_compute(c, c->ex.up_stream)) return c->status;
+  // a download of the same slot still in flight reads what this upload overwrites
+  if (c->ex.dl_pending[slot]) c->check(cudaStreamWaitEvent(c->ex.up_stream, c->ex.dl_ev[slot], 0), "cudaStreamWaitEvent");
+  if (transfer_picture(c, slot, reinterpret_cast<void *const *>(const_cast<uint16_t *const *>(planes)), strides, true,
+                       c->ex.up_stream, 1) != XVCB200_OK)
+    return c->status;
+  c->check(cudaEventRecord(c->ex.up_ev[slot], c->ex.up_stream), "cudaEventRecord");
+  c->ex.up_pending[slot] = 1;
+  return c->status;
+}
+int xvcb200_download_picture_async(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  if (!ctx) return XVCB200_INVALID_ARGUMENT;
+  return download_planes_async(full(ctx), slot, reinterpret_cast<void *const *>(planes), strides);
+}
+int xvcb200_download_coeff_async(xvcb200_ctx *ctx, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]) {
+  if (!ctx) return XVCB200_INVALID_ARGUMENT;
+  return download_planes_async(full(ctx), slot, reinterpret_cast<void *const *>(planes), strides);
+}
+int xvcb200_get_cus_async(xvcb200_ctx *ctx, xvcb200_cu *cus, int n) {
+  if (!ctx || !cus || n < 0 || n > ctx->n_cus) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (!copy_setup(c) || !copy_after_compute(c, c->ex.copy_stream)) return c->status;
+  if (!c->check(cudaMemcpyAsync(cus, c->d_cus, sizeof(xvcb200_cu) * (size_t)n, cudaMemcpyDeviceToHost, c->ex.copy_stream), "get_cus_async"))
+    return c->status;
+  if (c->ex.cur_blob >= 0) {
+    c->check(cudaEventRecord(c->ex.blob[c->ex.cur_blob].dl_ev, c->ex.copy_stream), "cudaEventRecord");
+    c->ex.blob[c->ex.cur_blob].dl_pending = true;
+  }
+  return c->status;
+}
+// host waits for the last async download of one slot (slot < 0: the CU array)
+int xvcb200_wait_download(xvcb200_ctx *ctx, int slot) {
+  if (!ctx || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (slot < 0) {
+    for (auto &b : c->ex.blob)
+      if (b.dl_ev) c->check(cudaEventSynchronize(b.dl_ev), "cudaEventSynchronize");
+    return c->status;
+  }
+  if (c->ex.dl_ev.empty()) return c->status;
+  c->check(cudaEventSynchronize(c->ex.dl_ev[(size_t)slot]), "cudaEventSynchronize");
+  return c->status;
+}
+int xvcb200_sync_copies(xvcb200_ctx *ctx) {
+  if (!ctx) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (c->ex.copy_stream) c->check(cudaStreamSynchronize(c->ex.copy_stream), "cudaStreamSynchronize(copy)");
+  if (c->ex.up_stream) c->check(cudaStreamSynchronize(c->ex.up_stream), "cudaStreamSynchronize(upload)");
+  return c->status;
+}
+
 int xvcb200_pad_border(xvcb200_ctx *c, int slot) {
   if (!slot_ok(c, slot)) return XVCB200_INVALID_ARGUMENT;
+  join_upload_slot(full(c), slot);
+  join_downloads(full(c), slot);
   const int pad[3] = {80, 40, 40};
   c->check(launch_pad_border(c->stream, pic3(c, slot), pad), "pad_border");
   return c->status;
@@ -605,9 +867,9 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
         u.y + u.h > c->height || (u.x & 3) || (u.y & 3))
       return XVCB200_INVALID_ARGUMENT;
   }
-  if (!ensure(c, &c->d_cus, &c->cap_cus, n) || !ensure(c, &c->ex.d_tu_list, &c->ex.tu_cap, 3 * n)) return c->status;
   c->n_cus = n;
   if (n == 0) { c->ex.h_cus.clear(); return XVCB200_OK; }
+  if (!copy_setup(c)) return c->status;
   // CU groups by CTU (counting sort: coding order inside a CTU is kept)
   const int ctus_x = (c->width + 63) >> 6, n_ctus = ctus_x * ((c->height + 63) >> 6);
   std::vector<int> ctu_first((size_t)n_ctus + 1, 0), by_ctu((size_t)n);
@@ -618,22 +880,30 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
     std::vector<int> fill(ctu_first.begin(), ctu_first.end() - 1);
     for (int i = 0; i < n; i++) by_ctu[(size_t)fill[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6))]++] = i;
   }
-  for (int v = 0; v < 2; v++)
-    if (!ensure(c, &c->ex.d_pipe_index[v], &c->ex.pipe_index_cap[v], (v + 1) * n) ||
-        !ensure(c, &c->ex.d_pipe_groups[v], &c->ex.pipe_groups_cap[v], 2 * (v + 1) * n_groups))
-      return c->status;
-  // pinned staging: [cus][tu list 3n][index nl=1: n][index nl=2: 2n][groups nl=1: 2g][groups nl=2: 4g]
+  // blob layout: [cus][tu list 3n][index nl=1: n][index nl=2: 2n][groups nl=1: 2g][groups nl=2: 4g]
   const size_t ints = 3 * (size_t)n + 3 * (size_t)n + 6 * (size_t)n_groups;
   const size_t need = sizeof(xvcb200_cu) * (size_t)n + sizeof(int) * ints;
-  if (!c->ex.setcus_ev && !c->check(cudaEventCreateWithFlags(&c->ex.setcus_ev, cudaEventDisableTiming), "cudaEventCreate")) return c->status;
-  if (!c->check(cudaEventSynchronize(c->ex.setcus_ev), "set_cus staging")) return c->status;   // earlier copies out of the buffer
-  if (need > c->ex.h_setcus_cap) {
-    if (c->ex.h_setcus) cudaFreeHost(c->ex.h_setcus);
-    c->ex.h_setcus = nullptr; c->ex.h_setcus_cap = 0;
-    if (!c->check(cudaHostAlloc(&c->ex.h_setcus, need + need / 4, cudaHostAllocDefault), "cudaHostAlloc")) return c->status;
-    c->ex.h_setcus_cap = need + need / 4;
+  const int nb = c->ex.cur_blob < 0 ? 0 : c->ex.cur_blob ^ 1;
+  CtxExtra::CuBlob &B = c->ex.blob[nb];
+  if (!B.up_ev && (!c->check(cudaEventCreateWithFlags(&B.up_ev, cudaEventDisableTiming), "cudaEventCreate") ||
+                   !c->check(cudaEventCreateWithFlags(&B.free_ev, cudaEventDisableTiming), "cudaEventCreate") ||
+                   !c->check(cudaEventCreateWithFlags(&B.dl_ev, cudaEventDisableTiming), "cudaEventCreate")))
+    return c->status;
+  if (!c->check(cudaEventSynchronize(B.up_ev), "set_cus staging")) return c->status;   // earlier copy out of its host image
+  if (need > B.hcap) {
+    if (B.h) cudaFreeHost(B.h);
+    B.h = nullptr; B.hcap = 0;
+    if (!c->check(cudaHostAlloc(&B.h, need + need / 4, cudaHostAllocDefault), "cudaHostAlloc")) return c->status;
+    B.hcap = need + need / 4;
   }
-  xvcb200_cu *hc = static_cast<xvcb200_cu *>(c->ex.h_setcus);
+  if (need > B.cap) {                       // rare: the picture before the current one may still be running on it
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->ex.copy_stream);
+    cudaFree(B.d); B.d = nullptr; B.cap = 0;
+    if (!c->check(cudaMalloc(&B.d, need + need / 4), "cudaMalloc(cu blob)")) return c->status;
+    B.cap = need + need / 4;
+  }
+  xvcb200_cu *hc = static_cast<xvcb200_cu *>(B.h);
   int *list = reinterpret_cast<int *>(hc + n);
   int *idx1 = list + 3 * (size_t)n, *idx2 = idx1 + n, *grp1 = idx2 + 2 * (size_t)n, *grp2 = grp1 + 2 * (size_t)n_groups;
   memcpy(hc, cus, sizeof(xvcb200_cu) * (size_t)n);
@@ -657,15 +927,23 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
     for (int b = 0; b < 7; b++) { c->ex.class_offset[a][b] = off; fill[a][b] = off; off += c->ex.class_count[a][b]; }
   for (int i = 0; i < n; i++)
     for (int comp = 0; comp < 3; comp++) list[fill[lg(cus[i].w >> (comp ? 1 : 0))][lg(cus[i].h >> (comp ? 1 : 0))]++] = 3 * i + comp;
-  auto up = [&](void *d, const void *h, size_t bytes) {
-    return c->check(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream), "set_cus");
-  };
-  if (!up(c->d_cus, hc, sizeof(xvcb200_cu) * (size_t)n) || !up(c->ex.d_tu_list, list, sizeof(int) * 3 * (size_t)n) ||
-      !up(c->ex.d_pipe_index[0], idx1, sizeof(int) * (size_t)n) || !up(c->ex.d_pipe_index[1], idx2, sizeof(int) * 2 * (size_t)n) ||
-      !up(c->ex.d_pipe_groups[0], grp1, sizeof(int) * 2 * (size_t)n_groups) ||
-      !up(c->ex.d_pipe_groups[1], grp2, sizeof(int) * 4 * (size_t)n_groups) ||
-      !c->check(cudaEventRecord(c->ex.setcus_ev, c->stream), "set_cus"))
+  // the blob being left: free once the work enqueued so far is done
+  if (c->ex.cur_blob >= 0) c->check(cudaEventRecord(c->ex.blob[c->ex.cur_blob].free_ev, c->stream), "cudaEventRecord");
+  // upload on the upload stream, after the last users of this blob; the context stream waits for it
+  c->check(cudaStreamWaitEvent(c->ex.up_stream, B.free_ev, 0), "cudaStreamWaitEvent");
+  if (B.dl_pending) { c->check(cudaStreamWaitEvent(c->ex.up_stream, B.dl_ev, 0), "cudaStreamWaitEvent"); B.dl_pending = false; }
+  if (!c->check(cudaMemcpyAsync(B.d, B.h, need, cudaMemcpyHostToDevice, c->ex.up_stream), "set_cus") ||
+      !c->check(cudaEventRecord(B.up_ev, c->ex.up_stream), "set_cus") ||
+      !c->check(cudaStreamWaitEvent(c->stream, B.up_ev, 0), "set_cus"))
     return c->status;
+  c->ex.cur_blob = nb;
+  c->d_cus = reinterpret_cast<xvcb200_cu *>(B.d);
+  int *dl = reinterpret_cast<int *>(c->d_cus + n);
+  c->ex.d_tu_list = dl;
+  c->ex.d_pipe_index[0] = dl + 3 * (size_t)n;
+  c->ex.d_pipe_index[1] = c->ex.d_pipe_index[0] + n;
+  c->ex.d_pipe_groups[0] = c->ex.d_pipe_index[1] + 2 * (size_t)n;
+  c->ex.d_pipe_groups[1] = c->ex.d_pipe_groups[0] + 2 * (size_t)n_groups;
   return XVCB200_OK;
 }
 
@@ -733,6 +1011,8 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
       return XVCB200_INVALID_ARGUMENT;
   if (n == 0) return XVCB200_OK;
   if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
+  join_upload_slot(c, orig_slot);
+  for (int i = 0; i < n; i++) join_upload_slot(c, jobs[i].ref_slot);
   c->check(cudaMemcpyAsync(c->ex.d_jobs, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "me jobs");
   const int ctus_x = (c->width + 63) >> 6;
   const int n_groups = upload_tz_groups(c, n, [&](int i) {
@@ -766,6 +1046,7 @@ int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearc
   if (n == 0) return XVCB200_OK;
   xvcb200_fullsearch_job *dj = static_cast<xvcb200_fullsearch_job *>(c->scratch(sizeof(*jobs) * (size_t)n));
   if (!dj || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n)) return c->status;
+  join_uploads(c);
   c->check(cudaMemcpyAsync(dj, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "fs jobs");
   c->check(launch_full_search(c->stream, c->d_cus, dj, n, c->bitdepth, lambda_me_of(lambda_sqrt), c->plane(orig_slot, 0),
                               c->ex.d_luma_views, c->ex.d_me), "full_search");
@@ -785,6 +1066,9 @@ static bool refs_from_slots(xvcb200_ctx *c, const int32_t ref_slots[2][5], Pic3 
 
 int xvcb200_motion_compensate(xvcb200_ctx *c, const int32_t ref_slots[2][5], int pred_slot) {
   if (!slot_ok(c, pred_slot) || !ref_slots) return XVCB200_INVALID_ARGUMENT;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) join_upload_slot(full(c), ref_slots[l][i]);
+  join_downloads(full(c), pred_slot);
   Pic3 refs[2][5];
   refs_from_slots(c, ref_slots, refs);
   c->check(launch_motion_compensate(c->stream, c->d_cus, c->n_cus, c->bitdepth, refs, pic3(c, pred_slot)), "motion_compensate");
@@ -800,6 +1084,12 @@ static int tq_common(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slo
   if (n == 0) return XVCB200_OK;
   if (!ensure(c, &c->ex.d_tu, &c->ex.tu_res_cap, 3 * n)) return c->status;
   TqParams p;
+  join_upload_slot(c, orig_slot);
+  join_upload_slot(c, pred_slot);
+  join_upload_slot(c, coeff_slot);
+  join_downloads(c, rec_slot);
+  join_downloads(c, coeff_slot);
+  join_downloads(c, -1);
   p.bitdepth = c->bitdepth; p.intra_picture = intra_picture; p.table = table; p.off_u = off_u; p.off_v = off_v;
   p.decode_only = decode_only;
   int16_t *lev[3]; int pitch[3];
@@ -844,6 +1134,8 @@ int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_of
   if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1 || y_begin < 0 || y_end > c->height ||
       y_begin > y_end || (y_begin & 3) || (y_end & 3) || (pass_mask & ~3))
     return XVCB200_INVALID_ARGUMENT;
+  join_upload_slot(full(c), rec_slot);
+  join_downloads(full(c), rec_slot);
   DeblockParams p;
   p.bitdepth = c->bitdepth; p.pic_type = pic_type; p.beta_offset = beta_offset; p.tc_offset = tc_offset;
   p.table = table; p.off_u = off_u; p.off_v = off_v;
@@ -893,6 +1185,12 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
   const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
   if (!ensure_tz_scratch(c, n * nl)) return c->status;
+  join_upload_slot(c, prm->orig_slot);           // explicit read set: an upload made ahead for the NEXT picture is not waited for
+  for (int l = 0; l < nl; l++) join_upload_slot(c, prm->ref_slots[l][0]);
+  join_downloads(c, prm->pred_slot);
+  join_downloads(c, prm->rec_slot);
+  join_downloads(c, prm->coeff_slot);
+  join_downloads(c, -1);
   int stage = 0;
   auto mark = [&]() { if (c->ex.profile) cudaEventRecord(c->ex.ev[stage], c->stream); stage++; };
   mark();   // 0: start

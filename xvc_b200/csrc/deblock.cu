@@ -254,4 +254,29 @@ cudaError_t launch_pad_border(cudaStream_t s, Pic3 pic, const int pad[3]) {
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- picture <-> tight staging
+// The three planes of a picture between the padded slot layout and one tight buffer (planes
+// back to back, row pitch = width), so that the PCIe transfer is one contiguous copy per plane
+// instead of one DMA descriptor per row.  Widths are multiples of 4 samples (8-byte vectors).
+__global__ void plane_pack_kernel(Pic3 pic, uint16_t *__restrict__ tight, int to_tight) {
+  const int comp = blockIdx.y;
+  const PlaneView pl = pic.p[comp];
+  size_t off = 0;
+  for (int c = 0; c < comp; c++) off += (size_t)pic.p[c].width * pic.p[c].height;
+  const int vw = pl.width >> 2;                       // 8-byte vectors per row
+  const int total = vw * pl.height;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int y = i / vw, x = (i - y * vw) * 4;
+    uint2 *t = reinterpret_cast<uint2 *>(tight + off + (size_t)y * pl.width + x);
+    uint2 *s = reinterpret_cast<uint2 *>(pl.base + y * pl.pitch + x);
+    if (to_tight) *t = *s; else *s = *t;
+  }
+}
+
+cudaError_t launch_plane_pack(cudaStream_t s, Pic3 pic, uint16_t *tight, int to_tight) {
+  g_launch_count++;
+  plane_pack_kernel<<<dim3(296, 3), 256, 0, s>>>(pic, tight, to_tight);
+  return cudaGetLastError();
+}
+
 }  // namespace xvcb

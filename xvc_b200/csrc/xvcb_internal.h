@@ -132,6 +132,8 @@ cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, int n, 
 
 // deblock.cu
 cudaError_t launch_pad_border(cudaStream_t s, Pic3 pic, const int pad[3]);
+// slot planes <-> one tight buffer (planes back to back); widths must be multiples of 4 samples, 8-byte aligned rows
+cudaError_t launch_plane_pack(cudaStream_t s, Pic3 pic, uint16_t *tight, int to_tight);
 struct DeblockParams {
   int bitdepth, pic_type, beta_offset, tc_offset, table, off_u, off_v;
   long long ref_poc[2][5];

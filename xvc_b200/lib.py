@@ -34,6 +34,8 @@ EXPORTS = [
     "xvcb200_ctx_error_string", "xvcb200_get_geometry", "xvcb200_slot_ptr", "xvcb200_slot_region",
     "xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff",
     "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus",
+    "xvcb200_upload_picture_async", "xvcb200_download_picture_async", "xvcb200_download_coeff_async",
+    "xvcb200_get_cus_async", "xvcb200_sync_copies", "xvcb200_wait_download",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_tq_reconstruct",
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
@@ -91,8 +93,12 @@ def load():
     L.xvcb200_get_geometry.argtypes = [c_void_p, c_void_p]
     L.xvcb200_slot_ptr.argtypes = [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)]
     L.xvcb200_slot_region.argtypes = [c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_u64)]
-    for name in ("xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff"):
+    for name in ("xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff",
+                 "xvcb200_upload_picture_async", "xvcb200_download_picture_async", "xvcb200_download_coeff_async"):
         getattr(L, name).argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+    L.xvcb200_get_cus_async.argtypes = [c_void_p, c_void_p, c_int]
+    L.xvcb200_sync_copies.argtypes = [c_void_p]
+    L.xvcb200_wait_download.argtypes = [c_void_p, c_int]
     L.xvcb200_download_padded.argtypes = [c_void_p, c_int, c_int, c_void_p]
     L.xvcb200_pad_border.argtypes = [c_void_p, c_int]
     L.xvcb200_set_cus.argtypes = [c_void_p, c_void_p, c_int]
@@ -332,6 +338,26 @@ class Context:
         planes = [np.zeros(s, dtype=np.int16) for s in self.shapes]
         self._ok(self.L.xvcb200_download_coeff(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
         return planes
+
+    # transfers on the context's copy stream (see include/xvc_b200.h); the caller keeps the
+    # (page-locked) host arrays alive and unchanged until sync_copies()
+    def upload_async(self, slot, planes):
+        self._ok(self.L.xvcb200_upload_picture_async(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+
+    def download_async(self, slot, planes):
+        self._ok(self.L.xvcb200_download_picture_async(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+
+    def download_coeff_async(self, slot, planes):
+        self._ok(self.L.xvcb200_download_coeff_async(self.h, slot, abi.plane_ptr_array(planes), self._strides(planes)))
+
+    def get_cus_async(self, out):
+        self._ok(self.L.xvcb200_get_cus_async(self.h, abi.ptr(out), self.n_cus))
+
+    def wait_download(self, slot):
+        self._ok(self.L.xvcb200_wait_download(self.h, slot))
+
+    def sync_copies(self):
+        self._ok(self.L.xvcb200_sync_copies(self.h))
 
     def download_padded(self, slot, comp):
         pad = 80 if comp == 0 else 40
