@@ -95,15 +95,39 @@ __global__ void __launch_bounds__(128) subpel_generic_kernel(const xvcb200_cu *_
 }
 
 // ---------------------------------------------------------------- job classes
-// lists: 4 segments of n ints; counts[4].  Class 0: <= 256 samples, 1: <= 1024, 2: larger, 3: generic.
+// lists: 11 segments of n ints + counts[11].  Segment 0: blocks of <= 1024 samples (CTA of 128),
+// 1: larger (CTA of 256), 2: generic kernel, 3..9: blocks of <= 256 samples (one warp each) by
+// shape -- the warp teams walk these seven lists as one, so that the four warps of a CTA (and
+// neighbouring CTAs) work on the same shape and run the same instructions at about the same
+// time: the kernel is instruction-fetch bound when every warp is somewhere else in the code.
+constexpr int kSubpelLists = 11;
 __global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
                                        int *__restrict__ lists, int *__restrict__ counts) {
   const int ji = blockIdx.x * blockDim.x + threadIdx.x;
   if (ji >= n) return;
   const xvcb200_cu cu = cus[jobs[ji].cu];
   const int area = (int)cu.w * cu.h;
-  const int cls = (cu.w < 8 || cu.h < 8) ? 3 : (area <= 256 ? 0 : (area <= 1024 ? 1 : 2));
-  lists[(size_t)cls * n + atomicAdd(&counts[cls], 1)] = ji;
+  int seg;
+  if (cu.w < 8 || cu.h < 8) seg = 2;
+  else if (area > 1024) seg = 1;
+  else if (area > 256) seg = 0;
+  else seg = 3 + (28 - __clz((int)cu.w)) * 3 + (28 - __clz((int)cu.h));     // (log2 w - 3) * 3 + (log2 h - 3): 0,1,2,3,4,6
+  lists[(size_t)seg * n + atomicAdd(&counts[seg], 1)] = ji;
+}
+
+// The seven shape lists of the small blocks -> one list (segment 10), its length -> counts[10].
+__global__ void subpel_concat_kernel(int n, int *__restrict__ lists, int *__restrict__ counts) {
+  int end[7], total = 0;
+#pragma unroll
+  for (int q = 0; q < 7; q++) { total += counts[3 + q]; end[q] = total; }
+  const int li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li == 0) counts[10] = total;
+  if (li >= total) return;
+  int q = 0, first = 0;
+#pragma unroll
+  for (int t = 0; t < 6; t++)
+    if (li >= end[t]) { q = t + 1; first = end[t]; }
+  lists[(size_t)10 * n + li] = lists[(size_t)(3 + q) * n + (li - first)];
 }
 
 // shared memory of one team (bytes): reference window, horizontal plane, prediction plane, original.
@@ -466,20 +490,21 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
     if (occ1 < 1) occ1 = 1;
     if (occ2 < 1) occ2 = 1;
   }
-  int *counts = d_lists + 4 * (size_t)n;
-  cudaError_t e = cudaMemsetAsync(counts, 0, 4 * sizeof(int), s);
+  int *counts = d_lists + kSubpelLists * (size_t)n;
+  cudaError_t e = cudaMemsetAsync(counts, 0, kSubpelLists * sizeof(int), s);
   if (e != cudaSuccess) return e;
-  g_launch_count += 5;
+  g_launch_count += 6;
   subpel_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, d_jobs, n, d_lists, counts);
-  int *slow = d_lists + 3 * (size_t)n;
+  subpel_concat_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_lists, counts);
+  int *slow = d_lists + 2 * (size_t)n;
   // persistent grids: as many CTAs as fit, each strides over its class list (largest blocks first)
-  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + 2 * (size_t)n, counts + 2, slow, counts + 3,
+  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + (size_t)n, counts + 1, slow, counts + 2,
                                                          bytes2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s>>>(d_cus, d_jobs, d_lists + (size_t)n, counts + 1, slow, counts + 3,
-                                                          bytes1, bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s>>>(d_cus, d_jobs, d_lists, counts, slow, counts + 3, bytes0,
-                                                             bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  subpel_generic_kernel<<<num_sms * 4, 128, 0, s>>>(d_cus, d_jobs, slow, counts + 3, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s>>>(d_cus, d_jobs, d_lists, counts, slow, counts + 2, bytes1, bitdepth,
+                                                          lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, slow,
+                                                             counts + 2, bytes0, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_generic_kernel<<<num_sms * 4, 128, 0, s>>>(d_cus, d_jobs, slow, counts + 2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
   return cudaGetLastError();
 }
 
