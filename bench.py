@@ -344,8 +344,14 @@ def run_ours(args):
     stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     dom = max(stage_avg, key=stage_avg.get)
     achieved = alg_bytes[dom] / (stage_avg[dom] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_final_traffic.json")     # ncu --set full capture of the dominant kernel
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("kernel", "").startswith(dom):
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes[dom], "avg_ms": stage_avg[dom],
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": alg_bytes[dom], "avg_ms": stage_avg[dom],
                 "note": "integer SAD search: ALU/L1-bound, not HBM-bound; see DESIGN.md for op counts",
                 "stages_ms": stage_avg,
                 "stages_frac_of_hbm": {k: alg_bytes[k] / (v * 1e-3) / 1e9 / peak for k, v in stage_avg.items() if v > 0}}
