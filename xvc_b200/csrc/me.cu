@@ -101,14 +101,22 @@ struct RoundEval {
   const uint32_t *sm;        // reference box staged in shared memory (rows of spw words), or null
   int spw, rx0, ry0, rx1, ry1;
   int lane;
+  // Warp team: 2^lt warps run the same search redundantly (identical state) and split the
+  // candidates of every round; the per-candidate sums meet in t_dist (2 x 32 words, one half per
+  // round parity so that ONE named barrier per round suffices: a warp can only reach the second
+  // write of a half after every team mate has passed the barrier in between, i.e. has read it).
+  int tw, lt;                // rank in the team, log2(team size)
+  uint32_t *t_dist;
+  int bar_id;
+  mutable int parity;
 
   __device__ __forceinline__ uint32_t operator()(int cx, int cy, bool valid, int K) const {
-    int lg = K <= 4 ? 3 : (K <= 8 ? 2 : (K <= 16 ? 1 : 0));
+    int lg = (K <= 4 ? 3 : (K <= 8 ? 2 : (K <= 16 ? 1 : 0))) + lt;
     while ((1 << lg) > g.rows) lg--;
-    const int cand = lane >> lg, sub = lane & ((1 << lg) - 1);
-    const int sx = __shfl_sync(XVCB_FULL, cx, cand);
-    const int sy = __shfl_sync(XVCB_FULL, cy, cand);
-    const bool sv = __shfl_sync(XVCB_FULL, (int)valid, cand) && cand < K;
+    const int cand = (tw << (5 - lg)) + (lane >> lg), sub = lane & ((1 << lg) - 1);
+    const int sx = __shfl_sync(XVCB_FULL, cx, cand & 31);
+    const int sy = __shfl_sync(XVCB_FULL, cy, cand & 31);
+    const bool sv = __shfl_sync(XVCB_FULL, (int)valid, cand & 31) && cand < K;
     uint32_t acc = 0;
     if (sv) {
       const int X = g.x + sx, Y = g.y + sy;
@@ -124,9 +132,18 @@ struct RoundEval {
       }
     }
 #pragma unroll
-    for (int off = 4; off > 0; off >>= 1)
+    for (int off = 16; off > 0; off >>= 1)
       if (off < (1 << lg)) acc += __shfl_xor_sync(XVCB_FULL, acc, off);
-    const uint32_t mine = __shfl_sync(XVCB_FULL, acc, (lane << lg) & 31);
+    uint32_t mine;
+    if (lt == 0) {
+      mine = __shfl_sync(XVCB_FULL, acc, (lane << lg) & 31);
+    } else {
+      uint32_t *d = t_dist + (parity << 5);
+      parity ^= 1;
+      if (sub == 0 && cand < 32) d[cand] = acc;
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 << lt) : "memory");
+      mine = d[lane];
+    }
     if (!valid || lane >= K) return 0xffffffffu;
     return g.fast ? (mine * 2) >> g.bd_shift : mine >> g.bd_shift;
   }
@@ -449,6 +466,24 @@ __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int 
   }
 }
 
+// The same box through cp.async (LDGSTS), one 32-bit word per copy: no register staging, so a
+// thread keeps all of its ~100 copies in flight at once instead of four 16-byte loads.  (Rows
+// have an odd pitch in words, so wider asynchronous copies would be misaligned.)
+__device__ __forceinline__ void stage_box_async(const Sample *plane00, int pitch, int rx0, int ry0, int bh, int spw,
+                                                uint32_t *s_region, int tid, int nthreads) {
+  const int total = bh * spw;
+  const uint32_t magic = 0xffffffffu / (uint32_t)spw + 1u;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_region);
+  const uint32_t *g0 = reinterpret_cast<const uint32_t *>(plane00 + (size_t)ry0 * pitch + rx0);
+  const int pw = pitch >> 1;
+  for (int idx = tid; idx < total; idx += nthreads) {
+    const int row = (int)__umulhi((uint32_t)idx, magic), c = idx - row * spw;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * (uint32_t)idx), "l"(g0 + row * pw + c) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // Lower bound of the SAD of one candidate from 8-sample segment sums: NSEG segments per row,
 // `rp` = S8 at the candidate's first row/column (uint16), seg = segment sums of the original
 // block, two per word for NSEG >= 2.  VABSDIFF.U32 does |a - b| + c in one instruction.
@@ -476,6 +511,41 @@ __device__ __forceinline__ uint32_t seg_bound(const uint16_t *rp, int row_stride
     }
   }
   return lb;
+}
+
+// The same bound for CH neighbouring grid columns (candidates 5 samples apart in x) of one grid
+// row per lane at once: a segment sum of the original block is fetched once and used for CH
+// candidates, whose S8 operands sit at compile-time offsets from one row pointer -- two
+// instructions (LDS.U16 + VABSDIFF) per segment difference.
+constexpr int kBoundCols = 8;
+template <int NSEG>
+__device__ __forceinline__ void seg_bound_cols(const uint16_t *rp, int row_stride, const uint32_t *seg, int rows,
+                                               uint32_t (&lb)[kBoundCols]) {
+  if (NSEG == 1) {
+    for (int r = 0; r < rows; r += 2) {          // rows is a multiple of 4; a word of seg = two rows
+      const uint32_t a2 = seg[r >> 1];
+      const uint32_t s0 = a2 & 0xffffu, s1 = a2 >> 16;
+      const uint16_t *rq = rp + row_stride;
+#pragma unroll
+      for (int u = 0; u < kBoundCols; u++) lb[u] = __usad((unsigned)rp[5 * u], s0, lb[u]);
+#pragma unroll
+      for (int u = 0; u < kBoundCols; u++) lb[u] = __usad((unsigned)rq[5 * u], s1, lb[u]);
+      rp = rq + row_stride;
+    }
+  } else {
+    for (int r = 0; r < rows; r++) {
+#pragma unroll
+      for (int k = 0; k < NSEG; k += 2) {
+        const uint32_t a2 = seg[(r * NSEG + k) >> 1];
+        const uint32_t s0 = a2 & 0xffffu, s1 = a2 >> 16;
+#pragma unroll
+        for (int u = 0; u < kBoundCols; u++) lb[u] = __usad((unsigned)rp[k * 8 + 5 * u], s0, lb[u]);
+#pragma unroll
+        for (int u = 0; u < kBoundCols; u++) lb[u] = __usad((unsigned)rp[k * 8 + 8 + 5 * u], s1, lb[u]);
+      }
+      rp += row_stride;
+    }
+  }
 }
 
 constexpr int kTzThreads = 512;
@@ -532,7 +602,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
                  int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
                  const PlaneView *__restrict__ ref_planes, const PlaneView *__restrict__ s8_planes,
                  xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states, int region_budget_words,
-                 uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof) {
+                 uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof, int stage_mode) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *s_tile = smem;                                   // original CTU, packed pairs, 33 words per row
   uint16_t *s_seg = reinterpret_cast<uint16_t *>(smem + kTileWords);
@@ -542,11 +612,49 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   __shared__ uint32_t s_dist[32];
   __shared__ int s_cls[10], s_ncoop;
   __shared__ unsigned char s_order[kMaxGroupJobs];    // jobs of the group, largest block first
+  __shared__ uint32_t s_tdist[kTzWarps / 2][64];      // per warp team: candidate sums of a round (two parities)
+  __shared__ int s_fetch[kTzWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
   long long t_mark = prof ? clock64() : 0;
   auto lap = [&](int slot) {     // optional phase timing (XVCB_TZ_PROF=1): cycles of thread 0, summed over CTAs
     if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&prof[slot], (unsigned long long)(now - t_mark)); t_mark = now; }
+  };
+
+  // Warp teams for phases 1 and 3.  A group has only ~10 jobs, so one warp per job leaves warps
+  // idle and the largest block sets the phase time.  Jobs are fetched largest first (s_order) by
+  // teams of 4 warps; blocks of 1024 samples are searched by the whole team, at the first block
+  // of 512 a team splits into two pairs, at the first smaller block into single warps (team
+  // sizes only shrink: the order is by area).  Teams synchronise on named barriers
+  // (id 1 + first warp / 2), single warps not at all.
+  int kn_cur = 0;
+  auto team_jobs = [&](auto body) {
+    int tsize = 4;
+    for (;;) {
+      const int tfirst = warp & ~(tsize - 1);
+      int o = 0;
+      if (tsize == 1) {
+        if (lane == 0) o = atomicAdd(&s_next, 1);
+        o = __shfl_sync(XVCB_FULL, o, 0);
+      } else {
+        const int bar = 1 + (tfirst >> 1);
+        if (warp == tfirst && lane == 0) s_fetch[tfirst] = atomicAdd(&s_next, 1);
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * tsize) : "memory");
+        o = s_fetch[tfirst];
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * tsize) : "memory");
+      }
+      if (o >= kn_cur) break;
+      SJob &sj = s_job[s_order[o]];
+      const int area = (int)sj.w * sj.h;
+      const int want = area >= 1024 ? 4 : (area >= 512 ? 2 : 1);
+      if (want < tsize) {
+        const bool first_sub = (warp & (tsize - 1)) < want;    // the sub-team that keeps this job
+        tsize = want;
+        if (!first_sub) continue;
+      }
+      const int tf = warp & ~(tsize - 1);
+      body(sj, warp - tf, tsize == 4 ? 2 : (tsize == 2 ? 1 : 0), 1 + (tf >> 1), s_tdist[tf >> 1]);
+    }
   };
 
   for (;;) {
@@ -562,6 +670,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
 
     for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
       const int kn = min(kMaxGroupJobs, G.count - k0);
+      kn_cur = kn;
       __syncthreads();
       if (tid == 0) {
         s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
@@ -610,7 +719,10 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         const int row = q >> 5, col = q & 31;
         s_tile[row * 33 + col] = __ldg(reinterpret_cast<const uint32_t *>(orig.base + (ctu_y + row) * orig.pitch + ctu_x) + col);
       }
-      if (staged) stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+      if (staged) {
+        if (stage_mode & 1) stage_box_async(ref.base, ref.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
+        else stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+      }
       __syncthreads();
       lap(1);
 
@@ -627,6 +739,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
           s_any_raster = 1;
         }
       };
+      long long t_c0 = prof ? clock64() : 0;
       for (int o = 0; o < n_coop; o++) {
         SJob &sj = s_job[s_order[o]];
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
@@ -638,21 +751,19 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
         if (tid == 0) finish_phase1(sj, g, st);
       }
-      for (;;) {
-        int o = 0;
-        if (lane == 0) o = atomicAdd(&s_next, 1);
-        o = __shfl_sync(XVCB_FULL, o, 0);
-        if (o >= kn) break;
-        SJob &sj = s_job[s_order[o]];
+      if (prof && tid == 0) { atomicAdd(&prof[10], (unsigned long long)(clock64() - t_c0)); atomicAdd(&prof[14], (unsigned long long)n_coop); atomicAdd(&prof[15], (unsigned long long)kn); }
+      team_jobs([&](SJob &sj, int tw, int lt, int bar, uint32_t *td) {
+        const long long t_j0 = prof ? clock64() : 0;
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
         xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
         xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
         const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
+                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane, tw, lt, td, bar, 0};
         TzJobState st;
         tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
-        if (lane == 0) finish_phase1(sj, g, st);
-      }
+        if (tw == 0 && lane == 0) finish_phase1(sj, g, st);
+        if (prof && lane == 0) atomicAdd(&prof[11], (unsigned long long)(clock64() - t_j0));
+      });
       __threadfence_block();
       __syncthreads();
       lap(2);
@@ -660,26 +771,28 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       if (s_any_raster) {
         // ---------------- raster pass 1: segment-sum bound, survivors -> pool
         if (staged && s8.base != nullptr) {
-          stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+          if (stage_mode & 2) stage_box_async(s8.base, s8.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
+          else stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
           __syncthreads();
           lap(3);
           const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
           const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
           // Jobs are bounded in batches (as many as have room for their segment sums); inside a
-          // batch the (grid column, 32 grid rows) tasks of ALL jobs form one list that the warps
-          // take dynamically.
+          // batch the (kBoundCols grid columns, 32 grid rows) tasks of ALL jobs form one list that
+          // is dealt to the warps.  The last column chunk of a job is shifted left to stay inside
+          // the window; the columns it shares with its neighbour are not reported twice.
           for (int kb = 0; kb < kn;) {                         // uniform
             if (tid == 0) {
               int used = 0, tasks = 0, k = kb;
               for (; k < kn; k++) {
                 SJob &sj = s_job[k];
                 sj.task0 = -1;
-                if (sj.need != 1 || sj.w < 8 || sj.nx * sj.ny > 65535) continue;
+                if (sj.need != 1 || sj.w < 8 || sj.nx < kBoundCols || sj.nx * sj.ny > 65535) continue;
                 const int segs = (sj.h > 8 ? sj.h >> 1 : sj.h) * (sj.w >> 3);
                 if (used + segs > 2 * kSegWords) break;
                 sj.seg_off = used; sj.task0 = tasks;
                 used += (segs + 1) & ~1;
-                tasks += sj.nx * ((sj.ny + 31) >> 5);
+                tasks += ((sj.nx + kBoundCols - 1) / kBoundCols) * ((sj.ny + 31) >> 5);
               }
               s_batch_end = k; s_batch_tasks = tasks; s_next = 0; s_count = 0;
             }
@@ -703,7 +816,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             const int room = pool_cap - base;
             {
               int kcur = kb - 1, tend = 0, tbeg = 0;           // the job the warp's current task belongs to
-              int nx = 1, ny = 1, slox = 0, sloy = 0, lsg = 0, rstride = 0, rows = 0, gx = 0, gy = 0, fast = 0, down = 0;
+              int nx = 1, ny = 1, nch = 1, slox = 0, sloy = 0, lsg = 0, rstride = 0, rows = 0, gx = 0, gy = 0, fast = 0, sh = 2;
               int mvpx = 0, mvpy = 0;
               uint32_t cost_in = 0;
               const uint32_t *segp = seg32;
@@ -713,42 +826,51 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
                   const SJob &sj = s_job[kcur];
                   if (sj.task0 < 0) continue;
                   nx = sj.nx; ny = sj.ny; slox = sj.slox; sloy = sj.sloy; cost_in = sj.cost_in;
-                  tbeg = sj.task0; tend = tbeg + nx * ((ny + 31) >> 5);
+                  nch = (nx + kBoundCols - 1) / kBoundCols;
+                  tbeg = sj.task0; tend = tbeg + nch * ((ny + 31) >> 5);
                   fast = sj.h > 8; rows = fast ? sj.h >> 1 : sj.h;
                   lsg = 28 - __clz((int)sj.w);
                   rstride = (fast ? 2 : 1) * 2 * spw;
                   gx = sj.x - rx0; gy = sj.y - ry0;
-                  mvpx = sj.mvpx; mvpy = sj.mvpy; down = sj.fullpel ? 2 : 0;
+                  mvpx = sj.mvpx; mvpy = sj.mvpy; sh = sj.fullpel ? 4 : 2;
                   segp = seg32 + (sj.seg_off >> 1);
                 }
                 const int local = task - tbeg;
-                const int pass = local / nx, i = local - pass * nx;
-                const int j = pass * 32 + lane, jj = min(j, ny - 1);
-                const int cx = slox + 5 * i, cy = sloy + 5 * jj;
-                const uint32_t rate = (lambda * (exp_golomb_bits((cx * 16 - mvpx) >> (down + 2)) +
-                                                 exp_golomb_bits((cy * 16 - mvpy) >> (down + 2)))) >> 16;
-                // dropped iff dist_bound + rate >= cost_in, in raw SAD units: lb >= thr
-                uint32_t thr = 0;
-                if (j < ny && rate < cost_in) {
-                  const uint32_t need = (cost_in - rate) << (bitdepth - 8);
-                  thr = fast ? (need + 1) >> 1 : need;
-                }
-                const uint16_t *rp = s8reg + (gy + cy) * (2 * spw) + gx + cx;
-                uint32_t lb = 0;
+                const int pass = local / nch, ch = local - pass * nch;
+                const int skip = max(0, (ch + 1) * kBoundCols - nx);       // leading columns owned by the previous chunk
+                const int i0 = ch * kBoundCols - skip;
+                const int j = pass * 32 + lane, jj = min(j, ny - 1);      // idle lanes recompute the last row (no stray reads)
+                const int cy = sloy + 5 * jj;
+                const uint32_t bits_y = exp_golomb_bits((cy * 16 - mvpy) >> sh);
+                const uint16_t *rp = s8reg + (gy + cy) * (2 * spw) + gx + slox + 5 * i0;
+                uint32_t lb[kBoundCols];
+#pragma unroll
+                for (int u = 0; u < kBoundCols; u++) lb[u] = 0;
                 switch (lsg) {
-                  case 0: lb = seg_bound<1>(rp, rstride, segp, rows); break;
-                  case 1: lb = seg_bound<2>(rp, rstride, segp, rows); break;
-                  case 2: lb = seg_bound<4>(rp, rstride, segp, rows); break;
-                  default: lb = seg_bound<8>(rp, rstride, segp, rows); break;
+                  case 0: seg_bound_cols<1>(rp, rstride, segp, rows, lb); break;
+                  case 1: seg_bound_cols<2>(rp, rstride, segp, rows, lb); break;
+                  case 2: seg_bound_cols<4>(rp, rstride, segp, rows, lb); break;
+                  default: seg_bound_cols<8>(rp, rstride, segp, rows, lb); break;
                 }
-                const bool keep = lb < thr;
-                const unsigned mask = __ballot_sync(XVCB_FULL, keep);
-                if (mask) {
-                  int wbase = 0;
-                  if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
-                  wbase = __shfl_sync(XVCB_FULL, wbase, 0);
-                  const int slot = wbase + __popc(mask & ((1u << lane) - 1));
-                  if (keep && slot < room) pool[base + slot] = ((uint32_t)kcur << 16) | (uint32_t)(j * nx + i);
+#pragma unroll
+                for (int u = 0; u < kBoundCols; u++) {
+                  const int i = i0 + u, cx = slox + 5 * i;
+                  const uint32_t rate = (lambda * (exp_golomb_bits((cx * 16 - mvpx) >> sh) + bits_y)) >> 16;
+                  // dropped iff dist_bound + rate >= cost_in, in raw SAD units: lb >= thr
+                  uint32_t thr = 0;
+                  if (j < ny && u >= skip && rate < cost_in) {
+                    const uint32_t need = (cost_in - rate) << (bitdepth - 8);
+                    thr = fast ? (need + 1) >> 1 : need;
+                  }
+                  const bool keep = lb[u] < thr;
+                  const unsigned mask = __ballot_sync(XVCB_FULL, keep);
+                  if (mask) {
+                    int wbase = 0;
+                    if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
+                    wbase = __shfl_sync(XVCB_FULL, wbase, 0);
+                    const int slot = wbase + __popc(mask & ((1u << lane) - 1));
+                    if (keep && slot < room) pool[base + slot] = ((uint32_t)kcur << 16) | (uint32_t)(j * nx + i);
+                  }
                 }
               }
             }
@@ -768,7 +890,8 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             kb = ke;
           }
           lap(4);
-          stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+          if (stage_mode & 2) stage_box_async(ref.base, ref.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
+          else stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
           __syncthreads();
           lap(5);
         }
@@ -851,6 +974,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       lap(6);
 
       // ---------------- phase 3: small blocks one warp per job, large blocks CTA-wide
+      t_c0 = prof ? clock64() : 0;
       for (int o = 0; o < n_coop; o++) {
         const SJob &sj = s_job[s_order[o]];
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
@@ -860,19 +984,17 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }     // empty scan window (:146-147)
         tz_phase3(g, sj.range, ev, lane, st, tid == 0 ? &res[sj.ji] : nullptr);
       }
-      for (;;) {
-        int o = 0;
-        if (lane == 0) o = atomicAdd(&s_next, 1);
-        o = __shfl_sync(XVCB_FULL, o, 0);
-        if (o >= kn) break;
-        const SJob &sj = s_job[s_order[o]];
+      if (prof && tid == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - t_c0));
+      team_jobs([&](SJob &sj, int tw, int lt, int bar, uint32_t *td) {
+        const long long t_j0 = prof ? clock64() : 0;
         const MeGeom g = sjob_geom(sj, bitdepth, lambda);
         const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane};
+                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane, tw, lt, td, bar, 0};
         TzJobState st = states[sj.ji];
         if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }
-        tz_phase3(g, sj.range, ev, lane, st, &res[sj.ji]);
-      }
+        tz_phase3(g, sj.range, ev, lane, st, tw == 0 ? &res[sj.ji] : nullptr);
+        if (prof && lane == 0) atomicAdd(&prof[13], (unsigned long long)(clock64() - t_j0));
+      });
       __syncthreads();
       lap(7);
     }
@@ -911,19 +1033,22 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
   if (want_prof && !prof) cudaMallocManaged(&prof, 16 * sizeof(*prof));
   if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 16 * sizeof(*prof)); }
+  static const int stage_mode = getenv("XVCB_TZ_STAGE") ? atoi(getenv("XVCB_TZ_STAGE")) : 0;
   const int grid = n_groups < num_sms ? n_groups : num_sms;
   const int fixed_words = kTileWords + kSegWords + kMaxGroupJobs * (int)(sizeof(SJob) / 4);
   g_launch_count++;
   tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
       d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
       d_ref_planes, d_s8_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
-      want_prof ? prof : nullptr);
+      want_prof ? prof : nullptr, stage_mode);
   if (want_prof) {
     cudaStreamSynchronize(s);
     fprintf(stderr, "[tz prof] cycles/CTA: box %.0f stage %.0f phase1 %.0f stageS8 %.0f bound %.0f stageRef %.0f exact %.0f phase3 %.0f | raster candidates %llu survivors %llu (%.2f%%)\n",
             (double)prof[0] / grid, (double)prof[1] / grid, (double)prof[2] / grid, (double)prof[3] / grid, (double)prof[4] / grid,
             (double)prof[5] / grid, (double)prof[6] / grid, (double)prof[7] / grid, prof[8], prof[9],
             100.0 * (double)prof[9] / (double)(prof[8] ? prof[8] : 1));
+    fprintf(stderr, "[tz prof2] cycles/CTA: coop1 %.0f teamwarp-busy1 %.0f coop3 %.0f teamwarp-busy3 %.0f | coop jobs %llu jobs %llu\n",
+            (double)prof[10] / grid, (double)prof[11] / grid, (double)prof[12] / grid, (double)prof[13] / grid, prof[14], prof[15]);
   }
   return cudaGetLastError();
 }
