@@ -74,141 +74,35 @@ __device__ __forceinline__ uint32_t sad_rows(const uint32_t *rp, int ref_row_wor
   return total;
 }
 
-template <bool GLOBAL>
+// The same from global memory (read-only path) for candidates outside the staged box: rare, so
+// one compact out-of-line routine for all shapes.
+__device__ __noinline__ uint32_t sad_rows_global(const uint32_t *rp, int ref_row_words, const uint32_t *so,
+                                                 int so_row_words, int nrows, int shift, int pw) {
+  uint32_t total = 0;
+  for (int r = 0; r < nrows; r++) {
+    uint32_t prev = __ldg(rp), acc = 0;
+    for (int c = 0; c < pw; c++) {
+      const uint32_t nxt = __ldg(rp + c + 1);
+      acc += absdiff2(so[c], __funnelshift_r(prev, nxt, shift));
+      prev = nxt;
+      if ((c & 15) == 15) { total += (acc & 0xffff) + (acc >> 16); acc = 0; }
+    }
+    total += (acc & 0xffff) + (acc >> 16);
+    rp += ref_row_words;
+    so += so_row_words;
+  }
+  return total;
+}
+
 __device__ __forceinline__ uint32_t sad_rows_lpw(int lpw, const uint32_t *rp, int ref_row_words, const uint32_t *so,
                                                  int so_row_words, int nrows, int shift) {
   switch (lpw) {
-    case 1: return sad_rows<1, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
-    case 2: return sad_rows<2, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
-    case 3: return sad_rows<3, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
-    case 4: return sad_rows<4, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
-    default: return sad_rows<5, GLOBAL>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 1: return sad_rows<1, false>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 2: return sad_rows<2, false>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 3: return sad_rows<3, false>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    case 4: return sad_rows<4, false>(rp, ref_row_words, so, so_row_words, nrows, shift);
+    default: return sad_rows<5, false>(rp, ref_row_words, so, so_row_words, nrows, shift);
   }
-}
-
-// Evaluates the K <= 32 candidates of one search round for one warp.  Lane j holds candidate j
-// (cx, cy, valid) and receives its metric value (SampleMetric::Compare kSad / kSadFast incl. the
-// bit-depth shift).  The 32 lanes are split into K' = pow2(K) sub-groups of G = 32/K' lanes (not
-// more than the block has rows); each lane sums whole block rows r = sub, sub+G, ... of its
-// candidate, the G partial sums meet in log2(G) shuffles.  Original block: shared memory, rows
-// padded by one word so that the G row-interleaved lanes hit distinct banks.
-struct RoundEval {
-  const MeGeom &g;
-  const uint32_t *so;        // original block as packed pairs; rows visited by the metric are so_row_words apart
-  int so_row_words;
-  const Sample *plane;       // sample (0,0) of the reference luma plane (4-byte aligned, even pitch)
-  int gpitch;
-  const uint32_t *sm;        // reference box staged in shared memory (rows of spw words), or null
-  int spw, rx0, ry0, rx1, ry1;
-  int lane;
-  // Warp team: 2^lt warps run the same search redundantly (identical state) and split the
-  // candidates of every round; the per-candidate sums meet in t_dist (2 x 32 words, one half per
-  // round parity so that ONE named barrier per round suffices: a warp can only reach the second
-  // write of a half after every team mate has passed the barrier in between, i.e. has read it).
-  int tw, lt;                // rank in the team, log2(team size)
-  uint32_t *t_dist;
-  int bar_id;
-  mutable int parity;
-
-  __device__ __forceinline__ uint32_t operator()(int cx, int cy, bool valid, int K) const {
-    int lg = (K <= 4 ? 3 : (K <= 8 ? 2 : (K <= 16 ? 1 : 0))) + lt;
-    while ((1 << lg) > g.rows) lg--;
-    const int cand = (tw << (5 - lg)) + (lane >> lg), sub = lane & ((1 << lg) - 1);
-    const int sx = __shfl_sync(XVCB_FULL, cx, cand & 31);
-    const int sy = __shfl_sync(XVCB_FULL, cy, cand & 31);
-    const bool sv = __shfl_sync(XVCB_FULL, (int)valid, cand & 31) && cand < K;
-    uint32_t acc = 0;
-    if (sv) {
-      const int X = g.x + sx, Y = g.y + sy;
-      const uint32_t *op = so + sub * so_row_words;
-      if (sm != nullptr && X >= rx0 && X + g.w <= rx1 && Y >= ry0 && Y + g.h <= ry1) {
-        const int ox = X - rx0, oy = Y - ry0 + sub * g.rstep;
-        acc = sad_rows_lpw<false>(g.lpw, sm + oy * spw + (ox >> 1), (g.rstep * spw) << lg, op, so_row_words << lg,
-                                  g.rows >> lg, (ox & 1) << 4);
-      } else {
-        const Sample *row0 = plane + (Y + sub * g.rstep) * gpitch + (X & ~1);
-        acc = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * gpitch << lg) >> 1, op,
-                                 so_row_words << lg, g.rows >> lg, (X & 1) << 4);
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-      if (off < (1 << lg)) acc += __shfl_xor_sync(XVCB_FULL, acc, off);
-    uint32_t mine;
-    if (lt == 0) {
-      mine = __shfl_sync(XVCB_FULL, acc, (lane << lg) & 31);
-    } else {
-      uint32_t *d = t_dist + (parity << 5);
-      parity ^= 1;
-      if (sub == 0 && cand < 32) d[cand] = acc;
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 << lt) : "memory");
-      mine = d[lane];
-    }
-    if (!valid || lane >= K) return 0xffffffffu;
-    return g.fast ? (mine * 2) >> g.bd_shift : mine >> g.bd_shift;
-  }
-};
-
-// The same for ONE large block handled by the whole CTA: every warp runs the search control flow
-// redundantly (identical state in every warp); a round's candidates are dealt to the warps, the
-// 32 lanes of a warp split one candidate's rows (and row halves), per-candidate sums meet in
-// shared memory.  Contains __syncthreads(): all threads of the CTA must call it together.
-struct CtaEval {
-  const MeGeom &g;
-  const uint32_t *so; int so_row_words;
-  const Sample *plane; int gpitch;
-  const uint32_t *sm; int spw, rx0, ry0, rx1, ry1;
-  uint32_t *s_dist;          // 32 words of shared memory
-  int lane, warp, nwarps;
-
-  __device__ __forceinline__ uint32_t operator()(int cx, int cy, bool valid, int K) const {
-    const int lrows = 31 - __clz(g.rows);               // rows is a power of two <= 32
-    const int row = lane & (g.rows - 1), part = lane >> lrows, lparts = 5 - lrows;
-    const int lpl = g.lpw - lparts;                      // log2(pairs per lane) of one row
-    for (int c = warp; c < K; c += nwarps) {
-      const int sx = __shfl_sync(XVCB_FULL, cx, c);
-      const int sy = __shfl_sync(XVCB_FULL, cy, c);
-      const bool sv = __shfl_sync(XVCB_FULL, (int)valid, c);
-      uint32_t acc = 0;
-      if (sv) {
-        const int X = g.x + sx + (part << (lpl + 1)), Y = g.y + sy + row * g.rstep;
-        const uint32_t *op = so + row * so_row_words + (part << lpl);
-        if (sm != nullptr && g.x + sx >= rx0 && g.x + sx + g.w <= rx1 && g.y + sy >= ry0 && g.y + sy + g.h <= ry1) {
-          const int ox = X - rx0;
-          acc = sad_rows_lpw<false>(lpl, sm + (Y - ry0) * spw + (ox >> 1), 0, op, 0, 1, (ox & 1) << 4);
-        } else {
-          const Sample *row0 = plane + Y * gpitch + (X & ~1);
-          acc = sad_rows_lpw<true>(lpl, reinterpret_cast<const uint32_t *>(row0), 0, op, 0, 1, (X & 1) << 4);
-        }
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) s_dist[c] = acc;
-    }
-    __syncthreads();
-    const uint32_t mine = s_dist[lane];
-    __syncthreads();
-    if (!valid || lane >= K) return 0xffffffffu;
-    return g.fast ? (mine * 2) >> g.bd_shift : mine >> g.bd_shift;
-  }
-};
-
-// Applies an evaluated candidate list to the running best (see the file comment).
-__device__ __forceinline__ bool apply_candidates(TzBest &b, uint32_t dist, int cx, int cy, int pos, int range,
-                                                 const MeGeom &g, int lane) {
-  uint32_t key = 0xffffffffu;
-  if (dist != 0xffffffffu) {
-    const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-    key = (cost << 5) | (uint32_t)lane;
-  }
-  const uint32_t win = __reduce_min_sync(XVCB_FULL, key);
-  if (win == 0xffffffffu || (win >> 5) >= b.cost) return false;
-  const int wl = win & 31;
-  b.cost = win >> 5;
-  b.x = __shfl_sync(XVCB_FULL, cx, wl);
-  b.y = __shfl_sync(XVCB_FULL, cy, wl);
-  b.last_pos = __shfl_sync(XVCB_FULL, pos, wl);
-  b.last_range = __shfl_sync(XVCB_FULL, range, wl);
-  return true;
 }
 
 // IsInside<Dir> (inter_tz_search.cc:278-301): the direction of a pattern point selects which
@@ -295,109 +189,126 @@ struct TzJobState {
   int need_raster;
 };
 
-template <class Eval>
-__device__ __forceinline__ void neighbour_points(const MeGeom &g, const Eval &ev, TzBest &b, const int lo[2],
-                                                 const int hi[2], uint32_t &evals, int lane) {
-  if (b.last_range != 1) return;
-  b.last_range = 0;
-  int dx = 0, dy = 0, pos = 0;
-  const int K = two_point(b.last_pos, lane, dx, dy, pos);
-  if (K == 0) return;
-  const int cx = b.x + dx, cy = b.y + dy;
-  const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
-  evals += __popc(__ballot_sync(XVCB_FULL, valid));
-  const uint32_t d = ev(cx, cy, valid, K);
-  apply_candidates(b, d, cx, cy, pos, 1, g, lane);
+// Search pattern of FullpelDiamondSearch as a table: for the three pattern classes (radius 1:
+// 4 points, 2..8: 8 points, >= 16: 16 points) point k in units of 1, r/2, r/4, its direction
+// index and whether its recorded range is r/2 (the diagonal points of the 8-point pattern) --
+// packed (ux + 8) | (uy + 8) << 4 | (pos + 8) << 8 | half << 12.
+__device__ __forceinline__ int pack_pattern_point(int cls, int k) {
+  const int r = cls == 0 ? 1 : (cls == 1 ? 2 : 16), unit = cls == 2 ? 4 : 1;
+  int dx, dy, pos, rep;
+  diamond_point(r, k, dx, dy, pos, rep);
+  return (dx / unit + 8) | ((dy / unit + 8) << 4) | ((pos + 8) << 8) | ((rep != r ? 1 : 0) << 12);
+}
+// point k of the round with radius 2^ri around (ax, ay)
+__device__ __forceinline__ void pattern_point(const int *s_pat, int ri, int k, int ax, int ay, int &cx, int &cy, int &pos,
+                                              int &rep) {
+  const int cls = ri == 0 ? 0 : (ri <= 3 ? 1 : 2);
+  const int pk = s_pat[cls * 16 + k];
+  const int r = 1 << ri, unit = cls == 0 ? 1 : (cls == 1 ? r >> 1 : r >> 2);
+  cx = ax + ((pk & 15) - 8) * unit;
+  cy = ay + (((pk >> 4) & 15) - 8) * unit;
+  pos = ((pk >> 8) & 15) - 8;
+  rep = (pk >> 12) ? r >> 1 : r;
 }
 
-// Phase 1 of TzSearch::Search: start points, first diamond pass, 2-point refinement
-// (inter_tz_search.cc:102-144).
-template <class Eval>
-__device__ void tz_phase1(const MeGeom &g, const xvcb200_cu &cu, const xvcb200_me_job &job, int pic_w, int pic_h,
-                          const Eval &ev, int lane, TzJobState &st) {
-  const int range = job.search_range;
-  int lo[2], hi[2], slo[2], shi[2];
-  min_max_mv(g.x, g.y, pic_w, pic_h, g.mvpx, g.mvpy, range, lo, hi);
-  slo[0] = lo[0]; slo[1] = lo[1]; shi[0] = hi[0]; shi[1] = hi[1];
-  TzBest b;
-  b.x = 0; b.y = 0; b.cost = 0xffffffffu; b.last_pos = 0; b.last_range = 0;
-  uint32_t evals = 0;
-  {   // predictor, zero, previous search result (:102-131)
-    int px = g.mvpx, py = g.mvpy;
-    clip_mv(g.x, g.y, pic_w, pic_h, px, py);
-    px >>= 4; py >>= 4;
-    int qx = job.prev[0] * 16, qy = job.prev[1] * 16;
-    clip_mv(g.x, g.y, pic_w, pic_h, qx, qy);
-    qx >>= 4; qy >>= 4;
-    const bool use_zero = (px != 0 || py != 0);
-    const bool use_prev = cu.depth != 0;
-    const int cx = lane == 0 ? px : (lane == 1 ? 0 : qx);
-    const int cy = lane == 0 ? py : (lane == 1 ? 0 : qy);
-    const bool valid = lane == 0 || (lane == 1 && use_zero) || (lane == 2 && use_prev);
-    const uint32_t d = ev(cx, cy, valid, 3);
-    evals += 1 + use_zero + use_prev;
-    uint32_t cost = 0xffffffffu;
-    if (d != 0xffffffffu) cost = d + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-    const uint32_t c0 = __shfl_sync(XVCB_FULL, cost, 0), c1 = __shfl_sync(XVCB_FULL, cost, 1),
-                   c2 = __shfl_sync(XVCB_FULL, cost, 2);
-    b.cost = c0; b.x = px; b.y = py;
-    bool moved = false;
-    if (use_zero && c1 < b.cost) { b.cost = c1; b.x = 0; b.y = 0; moved = true; }
-    if (use_prev) {
-      if (c2 < b.cost) { b.cost = c2; b.x = qx; b.y = qy; moved = true; }
-      if (moved) min_max_mv(g.x, g.y, pic_w, pic_h, b.x * 16, b.y * 16, range, slo, shi);
-    }
-    b.last_range = 0;
-  }
-  {   // first diamond pass around the start point, stops after three rounds without a hit (:133-143)
-    const int bx = b.x, by = b.y;
-    int misses = 0;
-    for (int r = 1; r <= range; r *= 2) {
-      int dx, dy, pos, rep;
-      const int K = diamond_point(r, lane, dx, dy, pos, rep);
-      const int cx = bx + dx, cy = by + dy;
-      const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
-      evals += __popc(__ballot_sync(XVCB_FULL, valid));
-      const uint32_t d = ev(cx, cy, valid, K);
-      if (apply_candidates(b, d, cx, cy, pos, rep, g, lane)) misses = 0;
-      else if (++misses >= 3) break;
-    }
-  }
-  neighbour_points(g, ev, b, lo, hi, evals, lane);
-  st.bx = b.x; st.by = b.y; st.cost = b.cost; st.last_pos = b.last_pos; st.last_range = b.last_range;
-  st.lo[0] = lo[0]; st.lo[1] = lo[1]; st.hi[0] = hi[0]; st.hi[1] = hi[1];
-  st.slo[0] = slo[0]; st.slo[1] = slo[1]; st.shi[0] = shi[0]; st.shi[1] = shi[1];
-  st.evals = evals;
-  st.need_raster = b.last_range > 5;       // kFullSearchGranularity (:91, :146)
-}
+// The candidate evaluator of the search.  All rounds of a diamond pass share their centre, so
+// their candidates do not depend on each other: the whole pass (4 + 8 + 8 + 8 + 16 + ... points,
+// "slots" in the reference's order) is evaluated at once and the reference's sequential
+// decisions (strict compares, three-miss rule, evaluation counts) are then replayed on the stored
+// costs -- one long dependent chain per pass instead of one per round.
+// A job is searched by a TEAM of 2^lt warps that run the control flow redundantly (identical
+// state) and split the evaluation passes; a pass = 32 >> lg slots, 2^lg lanes per candidate
+// (each lane sums whole block rows r = sub, sub + 2^lg, ..., the partial sums meet in lg
+// shuffles).  Costs return to "holder" lanes: slot s lives in lane s & 31, register s >> 5 --
+// through one shuffle per pass for a single warp, through the team's scratch (128 words of
+// shared memory) for a team.
+enum { kEvalDiamond, kEvalList };
+struct SearchEval {
+  const MeGeom &g;
+  const uint32_t *so;        // original block as packed pairs; rows visited by the metric are so_row_words apart
+  int so_row_words;
+  const Sample *plane;       // sample (0,0) of the reference luma plane (4-byte aligned, even pitch)
+  int gpitch;
+  const uint32_t *sm;        // reference box staged in shared memory (rows of spw words), or null
+  int spw, rx0, ry0, rx1, ry1;
+  const int *s_pat;
+  int lane;
+  int tw, lt;                // rank of this warp in the team, log2(team size)
+  uint32_t *t_cost;
+  int bar_id;
 
-// Phase 3: re-centre until the centre wins (:157-168), then the result.
-template <class Eval>
-__device__ void tz_phase3(const MeGeom &g, int range, const Eval &ev, int lane, const TzJobState &st,
-                          xvcb200_me_result *out) {
-  TzBest b;
-  b.x = st.bx; b.y = st.by; b.cost = st.cost; b.last_pos = st.last_pos; b.last_range = st.last_range;
-  uint32_t evals = st.evals;
-  while (b.last_range > 0) {
-    const int bx = b.x, by = b.y;
-    b.last_range = 0;
-    for (int r = 1; r <= range; r *= 2) {
-      int dx, dy, pos, rep;
-      const int K = diamond_point(r, lane, dx, dy, pos, rep);
-      const int cx = bx + dx, cy = by + dy;
-      const bool valid = lane < K && inside(cx, cy, pos, st.lo, st.hi);
-      evals += __popc(__ballot_sync(XVCB_FULL, valid));
-      const uint32_t d = ev(cx, cy, valid, K);
-      apply_candidates(b, d, cx, cy, pos, rep, g, lane);
+  // kEvalDiamond: slots = the points of rounds 0..nrounds-1 around (ax, ay), valid if inside the
+  // window [lo, hi].  kEvalList: slot k < nslots = the candidate held by lane k (ex, ey, evalid).
+  // cost[q] of lane l = cost of slot 32 q + l, 0xffffffff for invalid / non-existent slots.
+  __device__ __forceinline__ void run(int mode, int lg, int nslots, int ax, int ay, const int lo[2], const int hi[2], int ex,
+                                      int ey, bool evalid, uint32_t (&cost)[4]) {
+    const int spp = 32 >> lg;
+    const int npass = (nslots + spp - 1) >> (5 - lg);
+#pragma unroll
+    for (int q = 0; q < 4; q++) cost[q] = 0xffffffffu;
+    for (int p = tw; p < npass; p += 1 << lt) {
+      const int s0 = p << (5 - lg);
+      const int s = s0 + (lane >> lg), sub = lane & ((1 << lg) - 1);
+      int cx, cy;
+      bool valid;
+      if (mode == kEvalDiamond) {
+        int ri, k, pos, rep;
+        if (s < 4) { ri = 0; k = s; }
+        else if (s < 28) { ri = 1 + ((s - 4) >> 3); k = (s - 4) & 7; }
+        else { ri = 4 + ((s - 28) >> 4); k = (s - 28) & 15; }
+        pattern_point(s_pat, ri, k, ax, ay, cx, cy, pos, rep);
+        valid = s < nslots && inside(cx, cy, pos, lo, hi);
+      } else {
+        cx = __shfl_sync(XVCB_FULL, ex, s & 31);
+        cy = __shfl_sync(XVCB_FULL, ey, s & 31);
+        valid = __shfl_sync(XVCB_FULL, (int)evalid, s & 31) && s < nslots;
+      }
+      uint32_t c = 0xffffffffu;
+      if (__ballot_sync(XVCB_FULL, valid)) {
+        uint32_t acc = 0;
+        if (valid) {
+          const int X = g.x + cx, Y = g.y + cy;
+          const uint32_t *op = so + sub * so_row_words;
+          if (sm != nullptr && X >= rx0 && X + g.w <= rx1 && Y >= ry0 && Y + g.h <= ry1) {
+            const int ox = X - rx0, oy = Y - ry0 + sub * g.rstep;
+            acc = sad_rows_lpw(g.lpw, sm + oy * spw + (ox >> 1), (g.rstep * spw) << lg, op, so_row_words << lg,
+                               g.rows >> lg, (ox & 1) << 4);
+          } else {
+            const Sample *row0 = plane + (Y + sub * g.rstep) * gpitch + (X & ~1);
+            acc = sad_rows_global(reinterpret_cast<const uint32_t *>(row0), (g.rstep * gpitch << lg) >> 1, op,
+                                  so_row_words << lg, g.rows >> lg, (X & 1) << 4, 1 << g.lpw);
+          }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+          if (off < (1 << lg)) acc += __shfl_xor_sync(XVCB_FULL, acc, off);
+        if (valid) {
+          const uint32_t dist = g.fast ? (acc * 2) >> g.bd_shift : acc >> g.bd_shift;
+          c = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+        }
+      }
+      if (lt == 0) {
+        const int base = s0 & 31, q = s0 >> 5;
+        const uint32_t v = __shfl_sync(XVCB_FULL, c, ((lane - base) << lg) & 31);
+        if (lane >= base && lane < base + spp) {
+          if (q == 0) cost[0] = v;
+          else if (q == 1) cost[1] = v;
+          else if (q == 2) cost[2] = v;
+          else cost[3] = v;
+        }
+      } else if (sub == 0) {
+        t_cost[s] = c;
+      }
     }
-    neighbour_points(g, ev, b, st.lo, st.hi, evals, lane);
+    if (lt > 0) {
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 << lt) : "memory");
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        if (32 * q + lane < (npass << (5 - lg))) cost[q] = t_cost[32 * q + lane];
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 << lt) : "memory");
+    }
   }
-  if (lane == 0 && out != nullptr) {
-    out->mv_fullpel[0] = b.x; out->mv_fullpel[1] = b.y;
-    out->cost_fullpel = b.cost;
-    out->num_sad = evals;
-  }
-}
+};
 
 __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, uint32_t lambda, int mvpx, int mvpy) {
   MeGeom g;
@@ -609,10 +520,10 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   SJob *s_job = reinterpret_cast<SJob *>(smem + kTileWords + kSegWords);
   uint32_t *s_region = smem + kTileWords + kSegWords + kMaxGroupJobs * (sizeof(SJob) / 4);
   __shared__ int s_group, s_box[4], s_next, s_count, s_pool_used, s_any_raster, s_batch_end, s_batch_tasks;
-  __shared__ uint32_t s_dist[32];
   __shared__ int s_cls[10], s_ncoop;
   __shared__ unsigned char s_order[kMaxGroupJobs];    // jobs of the group, largest block first
-  __shared__ uint32_t s_tdist[kTzWarps / 2][64];      // per warp team: candidate sums of a round (two parities)
+  __shared__ uint32_t s_tcost[kTzWarps / 4][128];     // per warp team: the costs of one evaluation
+  __shared__ int s_pat[48];
   __shared__ int s_fetch[kTzWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
@@ -621,41 +532,8 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&prof[slot], (unsigned long long)(now - t_mark)); t_mark = now; }
   };
 
-  // Warp teams for phases 1 and 3.  A group has only ~10 jobs, so one warp per job leaves warps
-  // idle and the largest block sets the phase time.  Jobs are fetched largest first (s_order) by
-  // teams of 4 warps; blocks of 1024 samples are searched by the whole team, at the first block
-  // of 512 a team splits into two pairs, at the first smaller block into single warps (team
-  // sizes only shrink: the order is by area).  Teams synchronise on named barriers
-  // (id 1 + first warp / 2), single warps not at all.
-  int kn_cur = 0;
-  auto team_jobs = [&](auto body) {
-    int tsize = 4;
-    for (;;) {
-      const int tfirst = warp & ~(tsize - 1);
-      int o = 0;
-      if (tsize == 1) {
-        if (lane == 0) o = atomicAdd(&s_next, 1);
-        o = __shfl_sync(XVCB_FULL, o, 0);
-      } else {
-        const int bar = 1 + (tfirst >> 1);
-        if (warp == tfirst && lane == 0) s_fetch[tfirst] = atomicAdd(&s_next, 1);
-        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * tsize) : "memory");
-        o = s_fetch[tfirst];
-        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * tsize) : "memory");
-      }
-      if (o >= kn_cur) break;
-      SJob &sj = s_job[s_order[o]];
-      const int area = (int)sj.w * sj.h;
-      const int want = area >= 1024 ? 4 : (area >= 512 ? 2 : 1);
-      if (want < tsize) {
-        const bool first_sub = (warp & (tsize - 1)) < want;    // the sub-team that keeps this job
-        tsize = want;
-        if (!first_sub) continue;
-      }
-      const int tf = warp & ~(tsize - 1);
-      body(sj, warp - tf, tsize == 4 ? 2 : (tsize == 2 ? 1 : 0), 1 + (tf >> 1), s_tdist[tf >> 1]);
-    }
-  };
+  if (tid < 48) s_pat[tid] = pack_pattern_point(tid >> 4, tid & 15);
+  __syncthreads();
 
   for (;;) {
     __syncthreads();                             // previous group is completely done with shared memory
@@ -670,7 +548,6 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
 
     for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
       const int kn = min(kMaxGroupJobs, G.count - k0);
-      kn_cur = kn;
       __syncthreads();
       if (tid == 0) {
         s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
@@ -700,13 +577,12 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         s_ncoop = s_cls[0] + s_cls[1];
         int off = 0;
         for (int c = 0; c < 10; c++) { const int n = s_cls[c]; s_cls[c] = off; off += n; }
-        s_next = s_ncoop;
+        s_next = 0;
       }
       __syncthreads();
       for (int k = tid; k < kn; k += kTzThreads)
         s_order[atomicAdd(&s_cls[__clz((int)s_job[k].w * s_job[k].h) - 19], 1)] = (unsigned char)k;
       __syncthreads();
-      const int n_coop = s_ncoop;
       const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
       const int bw = rx1 - rx0, bh = ry1 - ry0;
       const int spw = ((bw + 1) / 2 + 1) | 1;
@@ -726,277 +602,400 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       __syncthreads();
       lap(1);
 
-      // ---------------- phase 1: small blocks one warp per job, large blocks (>= 512 pairs) CTA-wide
-      auto finish_phase1 = [&](SJob &sj, const MeGeom &g, const TzJobState &st) {
-        states[sj.ji] = st;
-        if (st.need_raster && st.shi[0] >= st.slo[0] && st.shi[1] >= st.slo[1]) {
-          sj.slox = st.slo[0]; sj.sloy = st.slo[1];
-          sj.nx = (st.shi[0] - st.slo[0]) / 5 + 1; sj.ny = (st.shi[1] - st.slo[1]) / 5 + 1;
-          sj.cost_in = st.cost;
-          const bool fits = staged && g.x + st.slo[0] >= rx0 && g.x + st.shi[0] + g.w <= rx1 && g.y + st.slo[1] >= ry0 &&
-                            g.y + st.shi[1] + g.h <= ry1;
-          sj.need = fits ? 1 : 2;
-          s_any_raster = 1;
-        }
-      };
-      long long t_c0 = prof ? clock64() : 0;
-      for (int o = 0; o < n_coop; o++) {
-        SJob &sj = s_job[s_order[o]];
-        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
-        xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
-        const CtaEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                         staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, s_dist, lane, warp, kTzWarps};
-        TzJobState st;
-        tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
-        if (tid == 0) finish_phase1(sj, g, st);
-      }
-      if (prof && tid == 0) { atomicAdd(&prof[10], (unsigned long long)(clock64() - t_c0)); atomicAdd(&prof[14], (unsigned long long)n_coop); atomicAdd(&prof[15], (unsigned long long)kn); }
-      team_jobs([&](SJob &sj, int tw, int lt, int bar, uint32_t *td) {
-        const long long t_j0 = prof ? clock64() : 0;
-        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        xvcb200_cu cu; cu.x = sj.x; cu.y = sj.y; cu.w = sj.w; cu.h = sj.h; cu.depth = sj.depth; cu.flags = 0;
-        xvcb200_me_job job; job.search_range = sj.range; job.prev[0] = sj.prevx; job.prev[1] = sj.prevy;
-        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane, tw, lt, td, bar, 0};
-        TzJobState st;
-        tz_phase1(g, cu, job, ref.width, ref.height, ev, lane, st);
-        if (tw == 0 && lane == 0) finish_phase1(sj, g, st);
-        if (prof && lane == 0) atomicAdd(&prof[11], (unsigned long long)(clock64() - t_j0));
-      });
-      __threadfence_block();
-      __syncthreads();
-      lap(2);
-
-      if (s_any_raster) {
-        // ---------------- raster pass 1: segment-sum bound, survivors -> pool
-        if (staged && s8.base != nullptr) {
-          if (stage_mode & 2) stage_box_async(s8.base, s8.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
-          else stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
-          __syncthreads();
-          lap(3);
-          const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
-          const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
-          // Jobs are bounded in batches (as many as have room for their segment sums); inside a
-          // batch the (kBoundCols grid columns, 32 grid rows) tasks of ALL jobs form one list that
-          // is dealt to the warps.  The last column chunk of a job is shifted left to stay inside
-          // the window; the columns it shares with its neighbour are not reported twice.
-          for (int kb = 0; kb < kn;) {                         // uniform
-            if (tid == 0) {
-              int used = 0, tasks = 0, k = kb;
-              for (; k < kn; k++) {
-                SJob &sj = s_job[k];
-                sj.task0 = -1;
-                if (sj.need != 1 || sj.w < 8 || sj.nx < kBoundCols || sj.nx * sj.ny > 65535) continue;
-                const int segs = (sj.h > 8 ? sj.h >> 1 : sj.h) * (sj.w >> 3);
-                if (used + segs > 2 * kSegWords) break;
-                sj.seg_off = used; sj.task0 = tasks;
-                used += (segs + 1) & ~1;
-                tasks += ((sj.nx + kBoundCols - 1) / kBoundCols) * ((sj.ny + 31) >> 5);
-              }
-              s_batch_end = k; s_batch_tasks = tasks; s_next = 0; s_count = 0;
-            }
-            __syncthreads();
-            const int ke = s_batch_end, ntasks = s_batch_tasks;
-            for (int k = kb + warp; k < ke; k += kTzWarps) {    // segment sums of the original blocks, a warp per job
-              const SJob &sj = s_job[k];
-              if (sj.task0 < 0) continue;
-              const int rstep = sj.h > 8 ? 2 : 1, rows = sj.h > 8 ? sj.h >> 1 : sj.h;
-              const int lsg = 28 - __clz((int)sj.w);            // log2(w / 8)
-              const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
-              for (int q = lane; q < (rows << lsg); q += 32) {
-                const int row = q >> lsg, sg = q & ((1 << lsg) - 1);
-                const uint32_t *p = tp + row * rstep * 33 + sg * 4;
-                const uint32_t s2 = p[0] + p[1] + p[2] + p[3];            // two 16-bit partial sums, no carry (<= 4 x 4095)
-                s_seg[sj.seg_off + q] = (uint16_t)((s2 & 0xffff) + (s2 >> 16));
-              }
-            }
-            __syncthreads();
-            const int base = s_pool_used;
-            const int room = pool_cap - base;
-            {
-              int kcur = kb - 1, tend = 0, tbeg = 0;           // the job the warp's current task belongs to
-              int nx = 1, ny = 1, nch = 1, slox = 0, sloy = 0, lsg = 0, rstride = 0, rows = 0, gx = 0, gy = 0, fast = 0, sh = 2;
-              int mvpx = 0, mvpy = 0;
-              uint32_t cost_in = 0;
-              const uint32_t *segp = seg32;
-              for (int task = warp; task < ntasks; task += kTzWarps) {
-                while (task >= tend) {                           // tasks arrive in increasing order
-                  kcur++;
-                  const SJob &sj = s_job[kcur];
+      // ---------------- phase 1 (ph = 0: start points, first diamond pass, 2-point step), the raster
+      // scan of the jobs that ended far out, phase 3 (ph = 1: re-centre until the centre wins).
+      // Both phases are ONE loop with ONE evaluation site driven by a small state machine, so the
+      // SAD routines exist once in the code: the search is issue-bound and every warp of the CTA
+      // is somewhere else in it, the kernel has to stay inside the instruction cache.
+      // Jobs are fetched largest first.  Blocks of >= 2048 samples (groups of one or two jobs) are
+      // searched by all 16 warps as one team; at the first smaller block the team splits into
+      // single warps, one job each.  The team synchronises on named barrier 1.
+#pragma unroll 1
+      for (int ph = 0; ph < 2; ph++) {
+        if (ph == 1) {
+          if (s_any_raster) {
+            // ---------------- raster pass 1: segment-sum bound, survivors -> pool
+            if (staged && s8.base != nullptr) {
+              if (stage_mode & 2) stage_box_async(s8.base, s8.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
+              else stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+              __syncthreads();
+              lap(3);
+              const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
+              const uint32_t *seg32 = reinterpret_cast<const uint32_t *>(s_seg);
+              // Jobs are bounded in batches (as many as have room for their segment sums); inside a
+              // batch the (kBoundCols grid columns, 32 grid rows) tasks of ALL jobs form one list that
+              // is dealt to the warps.  The last column chunk of a job is shifted left to stay inside
+              // the window; the columns it shares with its neighbour are not reported twice.
+              for (int kb = 0; kb < kn;) {                         // uniform
+                if (tid == 0) {
+                  int used = 0, tasks = 0, k = kb;
+                  for (; k < kn; k++) {
+                    SJob &sj = s_job[k];
+                    sj.task0 = -1;
+                    if (sj.need != 1 || sj.w < 8 || sj.nx < kBoundCols || sj.nx * sj.ny > 65535) continue;
+                    const int segs = (sj.h > 8 ? sj.h >> 1 : sj.h) * (sj.w >> 3);
+                    if (used + segs > 2 * kSegWords) break;
+                    sj.seg_off = used; sj.task0 = tasks;
+                    used += (segs + 1) & ~1;
+                    tasks += ((sj.nx + kBoundCols - 1) / kBoundCols) * ((sj.ny + 31) >> 5);
+                  }
+                  s_batch_end = k; s_batch_tasks = tasks; s_next = 0; s_count = 0;
+                }
+                __syncthreads();
+                const int ke = s_batch_end, ntasks = s_batch_tasks;
+                for (int k = kb + warp; k < ke; k += kTzWarps) {    // segment sums of the original blocks, a warp per job
+                  const SJob &sj = s_job[k];
                   if (sj.task0 < 0) continue;
-                  nx = sj.nx; ny = sj.ny; slox = sj.slox; sloy = sj.sloy; cost_in = sj.cost_in;
-                  nch = (nx + kBoundCols - 1) / kBoundCols;
-                  tbeg = sj.task0; tend = tbeg + nch * ((ny + 31) >> 5);
-                  fast = sj.h > 8; rows = fast ? sj.h >> 1 : sj.h;
-                  lsg = 28 - __clz((int)sj.w);
-                  rstride = (fast ? 2 : 1) * 2 * spw;
-                  gx = sj.x - rx0; gy = sj.y - ry0;
-                  mvpx = sj.mvpx; mvpy = sj.mvpy; sh = sj.fullpel ? 4 : 2;
-                  segp = seg32 + (sj.seg_off >> 1);
-                }
-                const int local = task - tbeg;
-                const int pass = local / nch, ch = local - pass * nch;
-                const int skip = max(0, (ch + 1) * kBoundCols - nx);       // leading columns owned by the previous chunk
-                const int i0 = ch * kBoundCols - skip;
-                const int j = pass * 32 + lane, jj = min(j, ny - 1);      // idle lanes recompute the last row (no stray reads)
-                const int cy = sloy + 5 * jj;
-                const uint32_t bits_y = exp_golomb_bits((cy * 16 - mvpy) >> sh);
-                const uint16_t *rp = s8reg + (gy + cy) * (2 * spw) + gx + slox + 5 * i0;
-                uint32_t lb[kBoundCols];
-#pragma unroll
-                for (int u = 0; u < kBoundCols; u++) lb[u] = 0;
-                switch (lsg) {
-                  case 0: seg_bound_cols<1>(rp, rstride, segp, rows, lb); break;
-                  case 1: seg_bound_cols<2>(rp, rstride, segp, rows, lb); break;
-                  case 2: seg_bound_cols<4>(rp, rstride, segp, rows, lb); break;
-                  default: seg_bound_cols<8>(rp, rstride, segp, rows, lb); break;
-                }
-#pragma unroll
-                for (int u = 0; u < kBoundCols; u++) {
-                  const int i = i0 + u, cx = slox + 5 * i;
-                  const uint32_t rate = (lambda * (exp_golomb_bits((cx * 16 - mvpx) >> sh) + bits_y)) >> 16;
-                  // dropped iff dist_bound + rate >= cost_in, in raw SAD units: lb >= thr
-                  uint32_t thr = 0;
-                  if (j < ny && u >= skip && rate < cost_in) {
-                    const uint32_t need = (cost_in - rate) << (bitdepth - 8);
-                    thr = fast ? (need + 1) >> 1 : need;
-                  }
-                  const bool keep = lb[u] < thr;
-                  const unsigned mask = __ballot_sync(XVCB_FULL, keep);
-                  if (mask) {
-                    int wbase = 0;
-                    if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
-                    wbase = __shfl_sync(XVCB_FULL, wbase, 0);
-                    const int slot = wbase + __popc(mask & ((1u << lane) - 1));
-                    if (keep && slot < room) pool[base + slot] = ((uint32_t)kcur << 16) | (uint32_t)(j * nx + i);
+                  const int rstep = sj.h > 8 ? 2 : 1, rows = sj.h > 8 ? sj.h >> 1 : sj.h;
+                  const int lsg = 28 - __clz((int)sj.w);            // log2(w / 8)
+                  const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
+                  for (int q = lane; q < (rows << lsg); q += 32) {
+                    const int row = q >> lsg, sg = q & ((1 << lsg) - 1);
+                    const uint32_t *p = tp + row * rstep * 33 + sg * 4;
+                    const uint32_t s2 = p[0] + p[1] + p[2] + p[3];            // two 16-bit partial sums, no carry (<= 4 x 4095)
+                    s_seg[sj.seg_off + q] = (uint16_t)((s2 & 0xffff) + (s2 >> 16));
                   }
                 }
+                __syncthreads();
+                const int base = s_pool_used;
+                const int room = pool_cap - base;
+                {
+                  int kcur = kb - 1, tend = 0, tbeg = 0;           // the job the warp's current task belongs to
+                  int nx = 1, ny = 1, nch = 1, slox = 0, sloy = 0, lsg = 0, rstride = 0, rows = 0, gx = 0, gy = 0, fast = 0, sh = 2;
+                  int mvpx = 0, mvpy = 0;
+                  uint32_t cost_in = 0;
+                  const uint32_t *segp = seg32;
+                  for (int task = warp; task < ntasks; task += kTzWarps) {
+                    while (task >= tend) {                           // tasks arrive in increasing order
+                      kcur++;
+                      const SJob &sj = s_job[kcur];
+                      if (sj.task0 < 0) continue;
+                      nx = sj.nx; ny = sj.ny; slox = sj.slox; sloy = sj.sloy; cost_in = sj.cost_in;
+                      nch = (nx + kBoundCols - 1) / kBoundCols;
+                      tbeg = sj.task0; tend = tbeg + nch * ((ny + 31) >> 5);
+                      fast = sj.h > 8; rows = fast ? sj.h >> 1 : sj.h;
+                      lsg = 28 - __clz((int)sj.w);
+                      rstride = (fast ? 2 : 1) * 2 * spw;
+                      gx = sj.x - rx0; gy = sj.y - ry0;
+                      mvpx = sj.mvpx; mvpy = sj.mvpy; sh = sj.fullpel ? 4 : 2;
+                      segp = seg32 + (sj.seg_off >> 1);
+                    }
+                    const int local = task - tbeg;
+                    const int pass = local / nch, ch = local - pass * nch;
+                    const int skip = max(0, (ch + 1) * kBoundCols - nx);       // leading columns owned by the previous chunk
+                    const int i0 = ch * kBoundCols - skip;
+                    const int j = pass * 32 + lane, jj = min(j, ny - 1);      // idle lanes recompute the last row (no stray reads)
+                    const int cy = sloy + 5 * jj;
+                    const uint32_t bits_y = exp_golomb_bits((cy * 16 - mvpy) >> sh);
+                    const uint16_t *rp = s8reg + (gy + cy) * (2 * spw) + gx + slox + 5 * i0;
+                    uint32_t lb[kBoundCols];
+    #pragma unroll
+                    for (int u = 0; u < kBoundCols; u++) lb[u] = 0;
+                    switch (lsg) {
+                      case 0: seg_bound_cols<1>(rp, rstride, segp, rows, lb); break;
+                      case 1: seg_bound_cols<2>(rp, rstride, segp, rows, lb); break;
+                      case 2: seg_bound_cols<4>(rp, rstride, segp, rows, lb); break;
+                      default: seg_bound_cols<8>(rp, rstride, segp, rows, lb); break;
+                    }
+    #pragma unroll
+                    for (int u = 0; u < kBoundCols; u++) {
+                      const int i = i0 + u, cx = slox + 5 * i;
+                      const uint32_t rate = (lambda * (exp_golomb_bits((cx * 16 - mvpx) >> sh) + bits_y)) >> 16;
+                      // dropped iff dist_bound + rate >= cost_in, in raw SAD units: lb >= thr
+                      uint32_t thr = 0;
+                      if (j < ny && u >= skip && rate < cost_in) {
+                        const uint32_t need = (cost_in - rate) << (bitdepth - 8);
+                        thr = fast ? (need + 1) >> 1 : need;
+                      }
+                      const bool keep = lb[u] < thr;
+                      const unsigned mask = __ballot_sync(XVCB_FULL, keep);
+                      if (mask) {
+                        int wbase = 0;
+                        if (lane == 0) wbase = atomicAdd(&s_count, __popc(mask));
+                        wbase = __shfl_sync(XVCB_FULL, wbase, 0);
+                        const int slot = wbase + __popc(mask & ((1u << lane) - 1));
+                        if (keep && slot < room) pool[base + slot] = ((uint32_t)kcur << 16) | (uint32_t)(j * nx + i);
+                      }
+                    }
+                  }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                  unsigned long long cands = 0;
+                  for (int k = kb; k < ke; k++) {
+                    SJob &sj = s_job[k];
+                    if (sj.task0 < 0) continue;
+                    cands += (unsigned long long)(sj.nx * sj.ny);
+                    if (s_count <= room) { sj.list_off = base; sj.list_cnt = s_count; }
+                  }
+                  if (s_count <= room) s_pool_used = base + s_count;
+                  if (prof) { atomicAdd(&prof[8], cands); atomicAdd(&prof[9], (unsigned long long)s_count); }
+                }
+                __syncthreads();
+                kb = ke;
               }
+              lap(4);
+              if (stage_mode & 2) stage_box_async(ref.base, ref.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
+              else stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+              __syncthreads();
+              lap(5);
             }
-            __syncthreads();
-            if (tid == 0) {
-              unsigned long long cands = 0;
-              for (int k = kb; k < ke; k++) {
-                SJob &sj = s_job[k];
-                if (sj.task0 < 0) continue;
-                cands += (unsigned long long)(sj.nx * sj.ny);
-                if (s_count <= room) { sj.list_off = base; sj.list_cnt = s_count; }
-              }
-              if (s_count <= room) s_pool_used = base + s_count;
-              if (prof) { atomicAdd(&prof[8], cands); atomicAdd(&prof[9], (unsigned long long)s_count); }
-            }
-            __syncthreads();
-            kb = ke;
-          }
-          lap(4);
-          if (stage_mode & 2) stage_box_async(ref.base, ref.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
-          else stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
-          __syncthreads();
-          lap(5);
-        }
 
-        // ---------------- raster pass 2a: survivors of all jobs, one flat loop, one candidate per lane
-        {
-          const int total = s_pool_used;
-          for (int e = tid; e < total; e += kTzThreads) {
-            const uint32_t ent = pool[e];
-            const int k = (int)(ent >> 16);
-            const uint32_t t = ent & 0xffffu;
-            SJob &sj = s_job[k];
-            if (sj.list_off < 0 || e < sj.list_off || e >= sj.list_off + sj.list_cnt) continue;   // list of an overflowed job
-            const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-            const int j = (int)t / sj.nx, i = (int)t - j * sj.nx;
-            const int cx = sj.slox + 5 * i, cy = sj.sloy + 5 * j;
-            const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
-            const uint32_t sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw,
-                                                     s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, g.rows,
-                                                     (ox & 1) << 4);
-            const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
-            const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-            atomicMin(&sj.key, ((unsigned long long)cost << 32) | t);
-          }
-        }
-        // ---------------- raster pass 2b: dense scans (no survivor list), CTA-wide per job
-        for (int k = 0; k < kn; k++) {
-          SJob &sj = s_job[k];
-          if (sj.need == 0 || sj.list_off >= 0) continue;      // uniform
-          const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-          const int slox = sj.slox, sloy = sj.sloy, nx = sj.nx, ny = sj.ny;
-          const bool in_box = sj.need == 1;
-          const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
-          uint32_t best_cost = 0xffffffffu, best_t = 0;
-          for (int j0 = 0; j0 < ny; j0 += 32) {
-            const int j = j0 + lane, jj = min(j, ny - 1);     // idle lanes recompute the last row (no stray reads)
-            const int cy = sloy + 5 * jj;
-            for (int i = warp; i < nx; i += kTzWarps) {
-              const int cx = slox + 5 * i;
-              uint32_t sad;
-              if (in_box) {
+            // ---------------- raster pass 2a: survivors of all jobs, one flat loop, one candidate per lane
+            {
+              const int total = s_pool_used;
+              for (int e = tid; e < total; e += kTzThreads) {
+                const uint32_t ent = pool[e];
+                const int k = (int)(ent >> 16);
+                const uint32_t t = ent & 0xffffu;
+                SJob &sj = s_job[k];
+                if (sj.list_off < 0 || e < sj.list_off || e >= sj.list_off + sj.list_cnt) continue;   // list of an overflowed job
+                const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+                const int j = (int)t / sj.nx, i = (int)t - j * sj.nx;
+                const int cx = sj.slox + 5 * i, cy = sj.sloy + 5 * j;
                 const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
-                sad = sad_rows_lpw<false>(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, tp, 33 * g.rstep, g.rows, (ox & 1) << 4);
-              } else {                                  // window outside / larger than the staged box: same walk from global memory
-                const int X = g.x + cx;
-                const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
-                sad = sad_rows_lpw<true>(g.lpw, reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, tp,
-                                         33 * g.rstep, g.rows, (X & 1) << 4);
-              }
-              if (j < ny) {
+                const uint32_t sad = sad_rows_lpw(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw,
+                                                         s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, g.rows,
+                                                         (ox & 1) << 4);
                 const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
                 const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-                const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
-                if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+                atomicMin(&sj.key, ((unsigned long long)cost << 32) | t);
               }
             }
+            // ---------------- raster pass 2b: dense scans (no survivor list), CTA-wide per job
+            for (int k = 0; k < kn; k++) {
+              SJob &sj = s_job[k];
+              if (sj.need == 0 || sj.list_off >= 0) continue;      // uniform
+              const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+              const int slox = sj.slox, sloy = sj.sloy, nx = sj.nx, ny = sj.ny;
+              const bool in_box = sj.need == 1;
+              const uint32_t *tp = s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1);
+              uint32_t best_cost = 0xffffffffu, best_t = 0;
+              for (int j0 = 0; j0 < ny; j0 += 32) {
+                const int j = j0 + lane, jj = min(j, ny - 1);     // idle lanes recompute the last row (no stray reads)
+                const int cy = sloy + 5 * jj;
+                for (int i = warp; i < nx; i += kTzWarps) {
+                  const int cx = slox + 5 * i;
+                  uint32_t sad;
+                  if (in_box) {
+                    const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
+                    sad = sad_rows_lpw(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw, tp, 33 * g.rstep, g.rows, (ox & 1) << 4);
+                  } else {                                  // window outside / larger than the staged box: same walk from global memory
+                    const int X = g.x + cx;
+                    const Sample *row0 = ref.base + (g.y + cy) * ref.pitch + (X & ~1);
+                    sad = sad_rows_global(reinterpret_cast<const uint32_t *>(row0), (g.rstep * ref.pitch) >> 1, tp, 33 * g.rstep,
+                                          g.rows, (X & 1) << 4, 1 << g.lpw);
+                  }
+                  if (j < ny) {
+                    const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
+                    const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+                    const uint32_t t = (uint32_t)(j * nx + i);                      // position in the reference's scan order
+                    if (cost < best_cost || (cost == best_cost && t < best_t)) { best_cost = cost; best_t = t; }
+                  }
+                }
+              }
+              if (best_cost != 0xffffffffu) atomicMin(&sj.key, ((unsigned long long)best_cost << 32) | best_t);
+            }
+            __syncthreads();
+            // winners -> job state (strict compare: ties keep the earlier best, :266-268)
+            for (int k = tid; k < kn; k += kTzThreads) {
+              SJob &sj = s_job[k];
+              if (sj.need == 0) continue;
+              TzJobState *stp = &states[sj.ji];
+              const uint32_t c = (uint32_t)(sj.key >> 32), t = (uint32_t)sj.key;
+              if (sj.key != ~0ull && c < sj.cost_in) {
+                stp->cost = c;
+                stp->bx = sj.slox + 5 * (int)(t % sj.nx);
+                stp->by = sj.sloy + 5 * (int)(t / sj.nx);
+              }
+              stp->last_range = 5;
+              stp->evals += sj.nx * sj.ny;
+              stp->need_raster = 0;
+            }
+            __threadfence_block();
           }
-          if (best_cost != 0xffffffffu) atomicMin(&sj.key, ((unsigned long long)best_cost << 32) | best_t);
+          if (tid == 0) s_next = 0;
+          __syncthreads();
+          lap(6);
         }
-        __syncthreads();
-        // winners -> job state (strict compare: ties keep the earlier best, :266-268)
-        for (int k = tid; k < kn; k += kTzThreads) {
-          SJob &sj = s_job[k];
-          if (sj.need == 0) continue;
-          TzJobState *stp = &states[sj.ji];
-          const uint32_t c = (uint32_t)(sj.key >> 32), t = (uint32_t)sj.key;
-          if (sj.key != ~0ull && c < sj.cost_in) {
-            stp->cost = c;
-            stp->bx = sj.slox + 5 * (int)(t % sj.nx);
-            stp->by = sj.sloy + 5 * (int)(t / sj.nx);
+        int tsize = kTzWarps;
+        long long t_w = prof ? clock64() : 0;
+        auto tick = [&](int slot) { if (prof) { const long long now = clock64(); if (lane == 0) atomicAdd(&prof[slot], (unsigned long long)(now - t_w)); t_w = now; } };
+        for (;;) {
+          tick(16);                                   // end-of-job / idle
+          const int tfirst = warp & ~(tsize - 1);
+          int o = 0;
+          if (tsize == 1) {
+            if (lane == 0) o = atomicAdd(&s_next, 1);
+            o = __shfl_sync(XVCB_FULL, o, 0);
+          } else {
+            const int bar = 1 + (tfirst >> 2);
+            if (warp == tfirst && lane == 0) s_fetch[tfirst] = atomicAdd(&s_next, 1);
+            asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * tsize) : "memory");
+            o = s_fetch[tfirst];
+            asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(32 * tsize) : "memory");
           }
-          stp->last_range = 5;
-          stp->evals += sj.nx * sj.ny;
-          stp->need_raster = 0;
+          if (o >= kn) break;
+          SJob &sj = s_job[s_order[o]];
+          const int area = (int)sj.w * sj.h;
+          const int want = area >= 2048 ? kTzWarps : (area >= 512 ? 4 : 1);
+          if (want < tsize) {
+            const bool first_sub = (warp & (tsize - 1)) < want;    // the sub-team that keeps this job
+            tsize = want;
+            if (!first_sub) continue;
+          }
+          const int tf = warp & ~(tsize - 1), tw = warp - tf;
+          tick(10);                                   // fetch
+          const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+          SearchEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
+                        staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, s_pat, lane, tw, 31 - __clz(tsize),
+                        s_tcost[tf >> 2], 1 + (tf >> 2)};
+          const int lrows = 31 - __clz(g.rows);
+          // lanes per candidate: diamond passes / the 2-3 point lists
+          const int lg_d = min(lrows, tsize == kTzWarps ? 4 : (tsize == 4 ? 2 : ((g.rows << g.lpw) >= 64 ? 1 : 0)));
+          const int lg_l = min(lrows, tsize == kTzWarps ? 4 : 3);
+          const int range = sj.range;
+          const int nrounds = 32 - __clz(range);                       // radii 1, 2, 4, ... <= range
+          const int nslots = nrounds <= 1 ? 4 * nrounds : (nrounds <= 4 ? 8 * nrounds - 4 : 16 * nrounds - 36);
+          TzJobState *stp = &states[sj.ji];
+          int lo[2], hi[2], slo[2], shi[2];
+          TzBest b;
+          uint32_t evals;
+          uint32_t cost[4];
+          if (ph == 0) {      // inter_tz_search.cc:92-131: predictor, zero, previous search result
+            min_max_mv(g.x, g.y, ref.width, ref.height, g.mvpx, g.mvpy, range, lo, hi);
+            slo[0] = lo[0]; slo[1] = lo[1]; shi[0] = hi[0]; shi[1] = hi[1];
+            int px = g.mvpx, py = g.mvpy;
+            clip_mv(g.x, g.y, ref.width, ref.height, px, py);
+            px >>= 4; py >>= 4;
+            int qx = sj.prevx * 16, qy = sj.prevy * 16;
+            clip_mv(g.x, g.y, ref.width, ref.height, qx, qy);
+            qx >>= 4; qy >>= 4;
+            const bool use_zero = px != 0 || py != 0, use_prev = sj.depth != 0;
+            const int ex = lane == 0 ? px : (lane == 1 ? 0 : qx), ey = lane == 0 ? py : (lane == 1 ? 0 : qy);
+            tick(11);                                 // setup
+            ev.run(kEvalList, lg_l, 3, 0, 0, lo, hi, ex, ey, lane == 0 || (lane == 1 && use_zero) || (lane == 2 && use_prev), cost);
+            tick(12);                                 // start eval
+            evals = 1 + use_zero + use_prev;
+            const uint32_t c0 = __shfl_sync(XVCB_FULL, cost[0], 0), c1 = __shfl_sync(XVCB_FULL, cost[0], 1),
+                           c2 = __shfl_sync(XVCB_FULL, cost[0], 2);
+            b.cost = c0; b.x = px; b.y = py;
+            bool moved = false;
+            if (use_zero && c1 < b.cost) { b.cost = c1; b.x = 0; b.y = 0; moved = true; }
+            if (use_prev) {
+              if (c2 < b.cost) { b.cost = c2; b.x = qx; b.y = qy; moved = true; }
+              if (moved) min_max_mv(g.x, g.y, ref.width, ref.height, b.x * 16, b.y * 16, range, slo, shi);
+            }
+            b.last_pos = 0; b.last_range = 1 << 30;     // enters the loop below exactly once
+          } else {
+            b.x = stp->bx; b.y = stp->by; b.cost = stp->cost; b.last_pos = stp->last_pos; b.last_range = stp->last_range;
+            lo[0] = stp->lo[0]; lo[1] = stp->lo[1]; hi[0] = stp->hi[0]; hi[1] = stp->hi[1];
+            slo[0] = slo[1] = shi[0] = shi[1] = 0;
+            evals = stp->evals;
+            if (stp->need_raster) b.last_range = 5;        // empty scan window (:146-147)
+            tick(11);
+          }
+          // ph 0: the first diamond pass around the start point, stops after three rounds without
+          // a hit (:133-143), then the 2-point step.  ph 1: re-centre until the centre wins (:157-168).
+          while (b.last_range > 0) {
+            const int ax = b.x, ay = b.y;
+            b.last_range = 0;
+            tick(11);
+            ev.run(kEvalDiamond, lg_d, nslots, ax, ay, lo, hi, 0, 0, false, cost);
+            tick(13);                                 // diamond eval
+            if (prof && lane == 0) atomicAdd(&prof[17], 1ull);
+            // FullpelDiamondSearch replayed (:173-210).  The winner of every round (first minimum in
+            // the reference's candidate order) and its number of evaluated points do not depend on
+            // the running best: ten independent warp reductions, then the sequential decisions
+            // (strict compare, three-miss rule of the first pass) on uniform values.
+            uint32_t win[10];
+            uint32_t nv_lo = 0, nv_hi = 0;                   // evaluated points per round, 5 bits each
+#pragma unroll
+            for (int ri = 0; ri < 10; ri++) {
+              constexpr int kBeg[10] = {0, 4, 12, 20, 28, 44, 60, 76, 92, 108};
+              const int K = ri == 0 ? 4 : (ri <= 3 ? 8 : 16);
+              const int sbeg = kBeg[ri], q0 = sbeg >> 5, q1 = (sbeg + K - 1) >> 5;
+              win[ri] = 0xffffffffu;
+              if (ri < nrounds) {
+                uint32_t key = 0xffffffffu;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                  if (q != q0 && q != q1) continue;
+                  const int rel = 32 * q + lane - sbeg;
+                  if ((unsigned)rel < (unsigned)K && cost[q] != 0xffffffffu) key = min(key, (cost[q] << 5) | (uint32_t)rel);
+                }
+                win[ri] = __reduce_min_sync(XVCB_FULL, key);
+                const uint32_t nv = __popc(__ballot_sync(XVCB_FULL, key != 0xffffffffu));
+                if (ri < 6) nv_lo |= nv << (5 * ri); else nv_hi |= nv << (5 * (ri - 6));
+              }
+            }
+            int misses = 0, wri = -1, wk = 0;
+            bool stopped = false;
+#pragma unroll
+            for (int ri = 0; ri < 10; ri++) {
+              if (ri < nrounds && !stopped) {
+                evals += ((ri < 6 ? nv_lo >> (5 * ri) : nv_hi >> (5 * (ri - 6))) & 31u);
+                if (win[ri] != 0xffffffffu && (win[ri] >> 5) < b.cost) {
+                  b.cost = win[ri] >> 5; wri = ri; wk = win[ri] & 31; misses = 0;
+                } else if (ph == 0 && ++misses >= 3) {
+                  stopped = true;
+                }
+              }
+            }
+            if (wri >= 0) pattern_point(s_pat, wri, wk, ax, ay, b.x, b.y, b.last_pos, b.last_range);
+            tick(14);                                 // replay
+            if (b.last_range == 1) {                         // FullpelNeighborPointSearch, :212-259
+              b.last_range = 0;
+              int dx = 0, dy = 0, pos = 0;
+              const int K = two_point(b.last_pos, lane, dx, dy, pos);
+              const int cx = b.x + dx, cy = b.y + dy;
+              const bool valid = lane < K && inside(cx, cy, pos, lo, hi);
+              const unsigned vm = __ballot_sync(XVCB_FULL, valid);
+              if (vm) {
+                evals += __popc(vm);
+                ev.run(kEvalList, lg_l, 2, 0, 0, lo, hi, cx, cy, valid, cost);
+                const uint32_t key = lane < 2 && cost[0] != 0xffffffffu ? (cost[0] << 5) | (uint32_t)lane : 0xffffffffu;
+                const uint32_t win = __reduce_min_sync(XVCB_FULL, key);
+                if (win != 0xffffffffu && (win >> 5) < b.cost) {
+                  b.cost = win >> 5;
+                  int wx = 0, wy = 0, wpos = 0;
+                  two_point(b.last_pos, win & 31, wx, wy, wpos);
+                  b.x += wx; b.y += wy; b.last_pos = wpos; b.last_range = 1;
+                }
+              }
+            }
+            tick(15);                                 // neighbour
+            if (ph == 0) break;
+          }
+          if (tw == 0 && lane == 0) {
+            if (ph == 0) {
+              stp->bx = b.x; stp->by = b.y; stp->cost = b.cost; stp->last_pos = b.last_pos; stp->last_range = b.last_range;
+              stp->lo[0] = lo[0]; stp->lo[1] = lo[1]; stp->hi[0] = hi[0]; stp->hi[1] = hi[1];
+              stp->slo[0] = slo[0]; stp->slo[1] = slo[1]; stp->shi[0] = shi[0]; stp->shi[1] = shi[1];
+              stp->evals = evals;
+              const int need_raster = b.last_range > 5;       // kFullSearchGranularity (:91, :146)
+              stp->need_raster = need_raster;
+              if (need_raster && shi[0] >= slo[0] && shi[1] >= slo[1]) {
+                sj.slox = slo[0]; sj.sloy = slo[1];
+                sj.nx = (shi[0] - slo[0]) / 5 + 1; sj.ny = (shi[1] - slo[1]) / 5 + 1;
+                sj.cost_in = b.cost;
+                const bool fits = staged && g.x + slo[0] >= rx0 && g.x + shi[0] + g.w <= rx1 && g.y + slo[1] >= ry0 &&
+                                  g.y + shi[1] + g.h <= ry1;
+                sj.need = fits ? 1 : 2;
+                s_any_raster = 1;
+              }
+            } else {
+              xvcb200_me_result *out = &res[sj.ji];
+              out->mv_fullpel[0] = b.x; out->mv_fullpel[1] = b.y;
+              out->cost_fullpel = b.cost;
+              out->num_sad = evals;
+            }
+          }
         }
         __threadfence_block();
+        __syncthreads();
+        lap(ph == 0 ? 2 : 7);
       }
-      if (tid == 0) s_next = n_coop;
-      __syncthreads();
-      lap(6);
-
-      // ---------------- phase 3: small blocks one warp per job, large blocks CTA-wide
-      t_c0 = prof ? clock64() : 0;
-      for (int o = 0; o < n_coop; o++) {
-        const SJob &sj = s_job[s_order[o]];
-        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        const CtaEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                         staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, s_dist, lane, warp, kTzWarps};
-        TzJobState st = states[sj.ji];
-        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }     // empty scan window (:146-147)
-        tz_phase3(g, sj.range, ev, lane, st, tid == 0 ? &res[sj.ji] : nullptr);
-      }
-      if (prof && tid == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - t_c0));
-      team_jobs([&](SJob &sj, int tw, int lt, int bar, uint32_t *td) {
-        const long long t_j0 = prof ? clock64() : 0;
-        const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-        const RoundEval ev{g, s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, ref.base, ref.pitch,
-                           staged ? s_region : nullptr, spw, rx0, ry0, rx1, ry1, lane, tw, lt, td, bar, 0};
-        TzJobState st = states[sj.ji];
-        if (st.need_raster) { st.last_range = 5; st.need_raster = 0; }
-        tz_phase3(g, sj.range, ev, lane, st, tw == 0 ? &res[sj.ji] : nullptr);
-        if (prof && lane == 0) atomicAdd(&prof[13], (unsigned long long)(clock64() - t_j0));
-      });
-      __syncthreads();
-      lap(7);
     }
   }
 }
@@ -1031,8 +1030,8 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   }
   static unsigned long long *prof = nullptr;
   static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
-  if (want_prof && !prof) cudaMallocManaged(&prof, 16 * sizeof(*prof));
-  if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 16 * sizeof(*prof)); }
+  if (want_prof && !prof) cudaMallocManaged(&prof, 24 * sizeof(*prof));
+  if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 24 * sizeof(*prof)); }
   static const int stage_mode = getenv("XVCB_TZ_STAGE") ? atoi(getenv("XVCB_TZ_STAGE")) : 0;
   const int grid = n_groups < num_sms ? n_groups : num_sms;
   const int fixed_words = kTileWords + kSegWords + kMaxGroupJobs * (int)(sizeof(SJob) / 4);
@@ -1047,8 +1046,9 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
             (double)prof[0] / grid, (double)prof[1] / grid, (double)prof[2] / grid, (double)prof[3] / grid, (double)prof[4] / grid,
             (double)prof[5] / grid, (double)prof[6] / grid, (double)prof[7] / grid, prof[8], prof[9],
             100.0 * (double)prof[9] / (double)(prof[8] ? prof[8] : 1));
-    fprintf(stderr, "[tz prof2] cycles/CTA: coop1 %.0f teamwarp-busy1 %.0f coop3 %.0f teamwarp-busy3 %.0f | coop jobs %llu jobs %llu\n",
-            (double)prof[10] / grid, (double)prof[11] / grid, (double)prof[12] / grid, (double)prof[13] / grid, prof[14], prof[15]);
+    fprintf(stderr, "[tz prof2] warp-cycles/CTA: fetch %.0f setup %.0f start %.0f diamond %.0f replay %.0f neighbour %.0f tail/idle %.0f | diamond passes (warp level) %llu\n",
+            (double)prof[10] / grid, (double)prof[11] / grid, (double)prof[12] / grid, (double)prof[13] / grid, (double)prof[14] / grid,
+            (double)prof[15] / grid, (double)prof[16] / grid, prof[17]);
   }
   return cudaGetLastError();
 }
