@@ -24,13 +24,34 @@ static const int16_t h_mats[XVCB_MAT_TOTAL] = {XVCB_MAT_VALUES};
 __constant__ int c_dct2[XVCB_MAT_DCT2_TOTAL];
 static bool g_dct2_loaded[16] = {false};
 
+// The same matrices for the fused kernel, int32 in global memory (L1 resident; every thread of a
+// warp reads the same 16 bytes).  Per size N (offset = offset of the N x N matrix above), with
+// R = min(N, 32) the number of coefficients a 64-point transform keeps (kTransformZeroOutMinSize):
+//   g_tq_fwdT[j * R + k] = m[k][j]   forward: the R outputs of one input sample are contiguous
+//   g_tq_inv [k * N + j] = m[k][j]   inverse: the N outputs of one coefficient are contiguous
+constexpr int kTqTableInts = 3412;
+__device__ __align__(16) int g_tq_fwdT[kTqTableInts];
+__device__ __align__(16) int g_tq_inv[kTqTableInts];
+
 static cudaError_t ensure_dct2_constant() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 16 && g_dct2_loaded[dev]) return cudaSuccess;
-  static int h_dct2[XVCB_MAT_DCT2_TOTAL];
+  static int h_dct2[XVCB_MAT_DCT2_TOTAL], h_fwdT[kTqTableInts], h_inv[kTqTableInts];
   for (int i = 0; i < XVCB_MAT_DCT2_TOTAL; i++) h_dct2[i] = h_mats[i];
+  int off = 0;
+  for (int n = 2; n <= 64; n <<= 1) {
+    const int r = n > 32 ? 32 : n;
+    for (int k = 0; k < r; k++)
+      for (int j = 0; j < n; j++) {
+        h_fwdT[off + j * r + k] = h_mats[off + k * n + j];
+        h_inv[off + k * n + j] = h_mats[off + k * n + j];
+      }
+    off += (n / 2) * (n / 2) * 4;       // = n * n: the matrices lie back to back
+  }
   cudaError_t e = cudaMemcpyToSymbol(c_dct2, h_dct2, sizeof(h_dct2));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tq_fwdT, h_fwdT, sizeof(h_fwdT));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tq_inv, h_inv, sizeof(h_inv));
   if (e == cudaSuccess && dev < 16) g_dct2_loaded[dev] = true;
   return e;
 }
@@ -297,70 +318,97 @@ cudaError_t launch_block_dequant(cudaStream_t s, int w, int h, int bitdepth, int
 
 // ================================================================ fused T/Q/recon, DCT-2
 //
-// One thread per transform LINE.  A thread loads its line of N int16 into registers once and
-// forms every output as a dot product with a matrix row taken from constant memory; the row
-// index is warp-uniform, so the coefficient is a uniform operand of the IMAD (no load
-// instruction per MAC).  Small blocks share a warp: L = max(W,H) threads per TU, NT/L TUs per
+// A transform stage is a set of LINES (rows or columns of the block); a line of a long transform
+// is shared by SPLIT threads, each producing a contiguous run of its outputs.  A thread loads its
+// line of N int16 into registers once and accumulates all of its outputs together: for every
+// input sample the matrix coefficients of its outputs are contiguous in the int32 tables above,
+// fetched with 16-byte loads whose address is uniform across the lines of a warp (one L1
+// transaction), so the inner loop is IMADs on independent accumulators.  Small blocks share a
 // CTA.  Shared-memory rows are padded by one 32-bit word so that the per-thread line reads
 // (stride = pitch) are bank-conflict free.
 
 template <int N> struct Dct2 { static constexpr int kOff = Dct2<N / 2>::kOff + (N / 2) * (N / 2); };
 template <> struct Dct2<2> { static constexpr int kOff = 0; };
 
-// forward line: in = N contiguous int16 (4-byte aligned); out[k*os] for k < N
+// threads sharing one line of an N-point transform
+template <int N> struct Split { static constexpr int kS = N >= 64 ? 4 : (N >= 32 ? 2 : 1); };
+
+// forward line: in = N contiguous int16 (4-byte aligned); out[k*os] for k < N.  This thread: outputs
+// [split * KPT, (split + 1) * KPT) of the R = min(N, 32) computed ones (+ its share of the zeros).
 template <int N>
-__device__ __forceinline__ void fwd_line(const int16_t *in, int16_t *out, int os, int shift, bool zero_line) {
-  constexpr int R = N > 32 ? 32 : N;
-  if (zero_line) {
-#pragma unroll 4
-    for (int k = 0; k < N; k++) out[k * os] = 0;
-    return;
-  }
-  int v[N];
-  if (N >= 2) {
+__device__ __forceinline__ void fwd_line(const int16_t *in, int split, int16_t *out, int os, int shift, bool zero_line) {
+  constexpr int R = N > 32 ? 32 : N, S = Split<N>::kS, KPT = R / S;
+  const int k0 = split * KPT;
+  if (!zero_line) {
+    int v[N];
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
       const uint32_t p = *reinterpret_cast<const uint32_t *>(in + j);
       v[j] = (int)(int16_t)(p & 0xffff);
       v[j + 1] = (int)(int16_t)(p >> 16);
     }
-  }
-  const int add = 1 << (shift - 1);
-  const int *m = c_dct2 + Dct2<N>::kOff;
-#pragma unroll 2
-  for (int k = 0; k < R; k++) {
-    int sum = add;
+    int acc[KPT];
 #pragma unroll
-    for (int j = 0; j < N; j++) sum += m[k * N + j] * v[j];
-    out[k * os] = (int16_t)(sum >> shift);
-  }
-  if (N > R) {
+    for (int i = 0; i < KPT; i++) acc[i] = 1 << (shift - 1);
+    const int *mt = g_tq_fwdT + Dct2<N>::kOff + k0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      if (KPT >= 4) {
+#pragma unroll
+        for (int i = 0; i < KPT; i += 4) {
+          const int4 c = __ldg(reinterpret_cast<const int4 *>(mt + j * R + i));
+          acc[i] += c.x * v[j]; acc[i + 1] += c.y * v[j]; acc[i + 2] += c.z * v[j]; acc[i + 3] += c.w * v[j];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < KPT; i++) acc[i] += __ldg(mt + j * R + i) * v[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KPT; i++) out[(k0 + i) * os] = (int16_t)(acc[i] >> shift);
+  } else {
 #pragma unroll 4
-    for (int k = R; k < N; k++) out[k * os] = 0;
+    for (int i = 0; i < KPT; i++) out[(k0 + i) * os] = 0;
+  }
+  if (N > R) {      // coefficients 32..63 of a 64-point transform are zero
+#pragma unroll 4
+    for (int i = 0; i < KPT; i++) out[(R + k0 + i) * os] = 0;
   }
 }
 
-// inverse line: in[k*is] for k < min(N,32); out = N contiguous int16, clipped
+// inverse line: in[k*is] for k < min(N,32); out = N contiguous int16, clipped.  This thread:
+// outputs [split * JPT, (split + 1) * JPT).
 template <int N>
-__device__ __forceinline__ void inv_line(const int16_t *in, int is, int16_t *out, int shift, bool zero_line) {
-  constexpr int R = N > 32 ? 32 : N;
+__device__ __forceinline__ void inv_line(const int16_t *in, int is, int split, int16_t *out, int shift, bool zero_line) {
+  constexpr int R = N > 32 ? 32 : N, S = Split<N>::kS, JPT = N / S;
+  const int j0 = split * JPT;
   if (zero_line) {
 #pragma unroll 4
-    for (int j = 0; j < N; j++) out[j] = 0;
+    for (int i = 0; i < JPT; i++) out[j0 + i] = 0;
     return;
   }
   int v[R];
 #pragma unroll
   for (int k = 0; k < R; k++) v[k] = in[k * is];
-  const int add = 1 << (shift - 1);
-  const int *m = c_dct2 + Dct2<N>::kOff;
-#pragma unroll 2
-  for (int j = 0; j < N; j++) {
-    int sum = add;
+  int acc[JPT];
 #pragma unroll
-    for (int k = 0; k < R; k++) sum += m[k * N + j] * v[k];
-    out[j] = (int16_t)clip16(sum >> shift);
+  for (int i = 0; i < JPT; i++) acc[i] = 1 << (shift - 1);
+  const int *m = g_tq_inv + Dct2<N>::kOff + j0;
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    if (JPT >= 4) {
+#pragma unroll
+      for (int i = 0; i < JPT; i += 4) {
+        const int4 c = __ldg(reinterpret_cast<const int4 *>(m + k * N + i));
+        acc[i] += c.x * v[k]; acc[i + 1] += c.y * v[k]; acc[i + 2] += c.z * v[k]; acc[i + 3] += c.w * v[k];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < JPT; i++) acc[i] += __ldg(m + k * N + i) * v[k];
+    }
   }
+#pragma unroll
+  for (int i = 0; i < JPT; i++) out[j0 + i] = (int16_t)clip16(acc[i] >> shift);
 }
 
 struct TqPlanes {
@@ -369,24 +417,31 @@ struct TqPlanes {
   int lev_pitch[3];
 };
 
+template <int LW, int LH> struct TqShape {
+  static constexpr int W = 1 << LW, H = 1 << LH;
+  static constexpr int T1 = H * Split<W>::kS;            // threads of a stage along the rows (N = W, H lines)
+  static constexpr int T2 = W * Split<H>::kS;            // ... along the columns (N = H, W lines)
+  static constexpr int TT = T1 > T2 ? T1 : T2;           // threads per transform unit
+  static constexpr int NT = TT < 32 ? 32 : TT;           // threads per CTA
+  static constexpr int TPB = NT / TT;                    // transform units per CTA
+};
+
 template <int LW, int LH>
-__global__ void __launch_bounds__((1 << (LW > LH ? LW : LH)) < 32 ? 32 : (1 << (LW > LH ? LW : LH)))
+__global__ void __launch_bounds__(TqShape<LW, LH>::NT)
 tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_tu, TqParams prm,
           const __grid_constant__ TqPlanes pl, xvcb200_tu_result *__restrict__ results) {
-  constexpr int W = 1 << LW, H = 1 << LH;
-  constexpr int L = W > H ? W : H;
-  constexpr int NT = L < 32 ? 32 : L;
-  constexpr int TPB = NT / L;
+  using Sh = TqShape<LW, LH>;
+  constexpr int W = Sh::W, H = Sh::H, TT = Sh::TT, TPB = Sh::TPB, T1 = Sh::T1, T2 = Sh::T2;
   constexpr int PA = W + 2, PB = H + 2;          // row pitches (int16) of the [H][W] and [W][H] buffers
+  constexpr int SZB = W * PB > H * PA ? W * PB : H * PA;
   __shared__ __align__(16) int16_t s_a[TPB][H * PA];   // residual -> delta -> reconstructed residual
-  __shared__ __align__(16) int16_t s_b[TPB][W * PB];   // transposed intermediate
+  __shared__ __align__(16) int16_t s_b[TPB][SZB];      // transposed intermediate of both transforms; the levels in between
   __shared__ __align__(16) int16_t s_c[TPB][H * PA];   // coefficients / dequantised coefficients
-  __shared__ __align__(16) int16_t s_d[TPB][H * PA];   // levels
   __shared__ int s_nnz[TPB], s_last[TPB];
   __shared__ unsigned long long s_ssd[TPB];
 
   const int tid = threadIdx.x;
-  const int t = tid / L, line = tid % L;            // TU slot in this CTA, line in the TU
+  const int t = tid / TT, ti = tid % TT;            // TU slot in this CTA, thread in the TU
   const int tu = blockIdx.x * TPB + t;
   const bool valid = tu < n_tu;
   const int id = valid ? tu_list[tu] : 0;
@@ -395,7 +450,7 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
   const int cs = comp ? 1 : 0;
   const int x0 = cu.x >> cs, y0 = cu.y >> cs;
   const int bd = prm.bitdepth;
-  int16_t *A = s_a[t], *B = s_b[t], *C = s_c[t], *D = s_d[t];
+  int16_t *A = s_a[t], *B = s_b[t], *C = s_c[t], *D = s_b[t];   // D (levels, [H][PA]) lives in B between the transforms
 
   int qp_raw = cu.qp;
   if (comp) qp_raw = chroma_qp_raw(cu.qp, comp == 1 ? prm.off_u : prm.off_v, prm.table, c_chroma_scale);
@@ -407,28 +462,28 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
   Sample *rec = pr.base + y0 * pr.pitch + x0;
   int16_t *lev = pl.lev[comp] + y0 * pl.lev_pitch[comp] + x0;
 
-  if (line == 0) { s_nnz[t] = 0; s_last[t] = -1; s_ssd[t] = 0; }
+  if (ti == 0) { s_nnz[t] = 0; s_last[t] = -1; s_ssd[t] = 0; }
   __syncthreads();
 
   bool cbf;
   if (!prm.decode_only) {
     // residual = orig - pred (ResidualBuffer::Subtract, sample_buffer.h:130-145)
     if (valid)
-      for (int e = line; e < W * H; e += L) {
+      for (int e = ti; e < W * H; e += TT) {
         const int y = e / W, x = e % W;
         A[y * PA + x] = (int16_t)((int)orig[y * po.pitch + x] - (int)pred[y * pp.pitch + x]);
       }
     __syncthreads();
     // forward: rows (N = W, lines = H) into B[k][y]; columns (N = H, lines = W) into C[x][y']
-    if (valid && line < H) fwd_line<W>(A + line * PA, B + line, PB, LW + bd - 9 + 2, false);
+    if (valid && ti < T1) fwd_line<W>(A + (ti % H) * PA, ti / H, B + (ti % H), PB, LW + bd - 9 + 2, false);
     __syncthreads();
-    if (valid && line < W) fwd_line<H>(B + line * PB, C + line, PA, LH + 6 + 2, line >= 32);
+    if (valid && ti < T2) fwd_line<H>(B + (ti % W) * PB, ti / W, C + (ti % W), PA, LH + 6 + 2, (ti % W) >= 32);
     __syncthreads();
     // QuantFast (rdo_quant.cc:156-201)
     const QuantParams q = quant_params(LW, LH, bd, qp_bd, prm.intra_picture);
     int mine = 0;
     if (valid)
-      for (int e = line; e < W * H; e += L) {
+      for (int e = ti; e < W * H; e += TT) {
         const int y = e / W, x = e % W;
         int16_t lv, dl;
         quant_one(C[y * PA + x], q, lv, dl);
@@ -442,7 +497,7 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
       constexpr int BW = W >= 4 ? W / 4 : 1, BH = H >= 4 ? H / 4 : 1;
       const bool run = valid && s_nnz[t] > 1;
       if (run)
-        for (int sb = line; sb < BW * BH; sb += L) {
+        for (int sb = ti; sb < BW * BH; sb += TT) {
           const int sx = sb % BW, sy = sb / BW;
           bool any = false;
 #pragma unroll
@@ -451,24 +506,24 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
         }
       __syncthreads();
       if (run)
-        for (int sb = line; sb < BW * BH; sb += L) {
+        for (int sb = ti; sb < BW * BH; sb += TT) {
           const int sx = sb % BW, sy = sb / BW;
           sign_hide_subblock(0, subblock_scan_index(0, BW, BH, sx, sy) == s_last[t], C + sy * 4 * PA + sx * 4, PA,
                              A + sy * 4 * PA + sx * 4, PA, D + sy * 4 * PA + sx * 4, PA);
         }
       __syncthreads();
-      if (run && line == 0) s_nnz[t] = 0;
+      if (run && ti == 0) s_nnz[t] = 0;
       __syncthreads();
       if (run) {
         mine = 0;
-        for (int e = line; e < W * H; e += L) mine += D[(e / W) * PA + e % W] != 0;
+        for (int e = ti; e < W * H; e += TT) mine += D[(e / W) * PA + e % W] != 0;
         if (mine) atomicAdd(&s_nnz[t], mine);
       }
       __syncthreads();
     }
     cbf = s_nnz[t] != 0;
     if (valid)   // levels out (zero block when cbf == 0)
-      for (int e = line; e < W * H; e += L) {
+      for (int e = ti; e < W * H; e += TT) {
         const int y = e / W, x = e % W;
         lev[y * pl.lev_pitch[comp] + x] = cbf ? D[y * PA + x] : (int16_t)0;
       }
@@ -476,7 +531,7 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
     const int bit = comp == 0 ? XVCB200_CU_CBF_Y : (comp == 1 ? XVCB200_CU_CBF_U : XVCB200_CU_CBF_V);
     cbf = (cu.flags & bit) != 0;
     if (valid && cbf)
-      for (int e = line; e < W * H; e += L) {
+      for (int e = ti; e < W * H; e += TT) {
         const int y = e / W, x = e % W;
         D[y * PA + x] = lev[y * pl.lev_pitch[comp] + x];
       }
@@ -486,22 +541,22 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
   // dequant (Quantize::Inverse) -> C
   const DequantParams dq = dequant_params(LW, LH, bd, qp_bd);
   if (valid && cbf)
-    for (int e = line; e < W * H; e += L) {
+    for (int e = ti; e < W * H; e += TT) {
       const int y = e / W, x = e % W;
       C[y * PA + x] = dequant_one(D[y * PA + x], dq);
     }
   __syncthreads();
   // inverse: columns (N = H, lines = W) into B[x][j]; rows (N = W, lines = H) into A[y][x]
-  if (valid && cbf && line < W) inv_line<H>(C + line, PA, B + line * PB, 7 + 2, line >= 32);
+  if (valid && cbf && ti < T2) inv_line<H>(C + (ti % W), PA, ti / W, B + (ti % W) * PB, 7 + 2, (ti % W) >= 32);
   __syncthreads();
-  if (valid && cbf && line < H) inv_line<W>(B + line, PB, A + line * PA, 20 - bd + 2, false);
+  if (valid && cbf && ti < T1) inv_line<W>(B + (ti % H), PB, ti / H, A + (ti % H) * PA, 20 - bd + 2, false);
   __syncthreads();
 
   // reconstruct (SampleBuffer::AddClip, sample_buffer.h:72-87; cbf == 0: copy of the prediction)
   const int maxv = (1 << bd) - 1;
   unsigned long long ssd = 0;
   if (valid)
-    for (int e = line; e < W * H; e += L) {
+    for (int e = ti; e < W * H; e += TT) {
       const int y = e / W, x = e % W;
       const int p = pred[y * pp.pitch + x];
       const int r = cbf ? clip3i(p + A[y * PA + x], 0, maxv) : p;
@@ -514,7 +569,7 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
   if (!prm.decode_only) {
     if (ssd) atomicAdd(&s_ssd[t], ssd);
     __syncthreads();
-    if (valid && line == 0) {
+    if (valid && ti == 0) {
       if (results) {
         results[id].ssd = (uint32_t)(s_ssd[t] >> (2 * (bd - 8)));
         results[id].num_non_zero = s_nnz[t];
@@ -530,9 +585,7 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
 template <int LW, int LH>
 static void launch_tq_class(cudaStream_t s, xvcb200_cu *d_cus, const int *d_list, int count, const TqParams &p,
                             const TqPlanes &pl, xvcb200_tu_result *d_res) {
-  constexpr int L = 1 << (LW > LH ? LW : LH);
-  constexpr int NT = L < 32 ? 32 : L;
-  constexpr int TPB = NT / L;
+  constexpr int NT = TqShape<LW, LH>::NT, TPB = TqShape<LW, LH>::TPB;
   g_launch_count++;
   tq_kernel<LW, LH><<<(count + TPB - 1) / TPB, NT, 0, s>>>(d_cus, d_list, count, p, pl, d_res);
 }
