@@ -377,24 +377,6 @@ __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int 
   }
 }
 
-// The same box through cp.async (LDGSTS), one 32-bit word per copy: no register staging, so a
-// thread keeps all of its ~100 copies in flight at once instead of four 16-byte loads.  (Rows
-// have an odd pitch in words, so wider asynchronous copies would be misaligned.)
-__device__ __forceinline__ void stage_box_async(const Sample *plane00, int pitch, int rx0, int ry0, int bh, int spw,
-                                                uint32_t *s_region, int tid, int nthreads) {
-  const int total = bh * spw;
-  const uint32_t magic = 0xffffffffu / (uint32_t)spw + 1u;
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_region);
-  const uint32_t *g0 = reinterpret_cast<const uint32_t *>(plane00 + (size_t)ry0 * pitch + rx0);
-  const int pw = pitch >> 1;
-  for (int idx = tid; idx < total; idx += nthreads) {
-    const int row = (int)__umulhi((uint32_t)idx, magic), c = idx - row * spw;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sbase + 4u * (uint32_t)idx), "l"(g0 + row * pw + c) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
 // Lower bound of the SAD of one candidate from 8-sample segment sums: NSEG segments per row,
 // `rp` = S8 at the candidate's first row/column (uint16), seg = segment sums of the original
 // block, two per word for NSEG >= 2.  VABSDIFF.U32 does |a - b| + c in one instruction.
@@ -513,7 +495,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
                  int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
                  const PlaneView *__restrict__ ref_planes, const PlaneView *__restrict__ s8_planes,
                  xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states, int region_budget_words,
-                 uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof, int stage_mode) {
+                 uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *s_tile = smem;                                   // original CTU, packed pairs, 33 words per row
   uint16_t *s_seg = reinterpret_cast<uint16_t *>(smem + kTileWords);
@@ -595,10 +577,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         const int row = q >> 5, col = q & 31;
         s_tile[row * 33 + col] = __ldg(reinterpret_cast<const uint32_t *>(orig.base + (ctu_y + row) * orig.pitch + ctu_x) + col);
       }
-      if (staged) {
-        if (stage_mode & 1) stage_box_async(ref.base, ref.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
-        else stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
-      }
+      if (staged) stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
       __syncthreads();
       lap(1);
 
@@ -616,8 +595,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
           if (s_any_raster) {
             // ---------------- raster pass 1: segment-sum bound, survivors -> pool
             if (staged && s8.base != nullptr) {
-              if (stage_mode & 2) stage_box_async(s8.base, s8.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
-              else stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+              stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
               __syncthreads();
               lap(3);
               const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
@@ -735,8 +713,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
                 kb = ke;
               }
               lap(4);
-              if (stage_mode & 2) stage_box_async(ref.base, ref.pitch, rx0, ry0, bh, spw, s_region, tid, kTzThreads);
-              else stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+              stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
               __syncthreads();
               lap(5);
             }
@@ -1032,14 +1009,13 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
   if (want_prof && !prof) cudaMallocManaged(&prof, 24 * sizeof(*prof));
   if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 24 * sizeof(*prof)); }
-  static const int stage_mode = getenv("XVCB_TZ_STAGE") ? atoi(getenv("XVCB_TZ_STAGE")) : 0;
   const int grid = n_groups < num_sms ? n_groups : num_sms;
   const int fixed_words = kTileWords + kSegWords + kMaxGroupJobs * (int)(sizeof(SJob) / 4);
   g_launch_count++;
   tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
       d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
       d_ref_planes, d_s8_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
-      want_prof ? prof : nullptr, stage_mode);
+      want_prof ? prof : nullptr);
   if (want_prof) {
     cudaStreamSynchronize(s);
     fprintf(stderr, "[tz prof] cycles/CTA: box %.0f stage %.0f phase1 %.0f stageS8 %.0f bound %.0f stageRef %.0f exact %.0f phase3 %.0f | raster candidates %llu survivors %llu (%.2f%%)\n",
