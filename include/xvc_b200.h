@@ -342,6 +342,47 @@ int xvcb200_deblock_band(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_
                          const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end);
 
 /* ------------------------------------------------------------------------------------
+ * (B') intra prediction -- SURVEY section 8(f) rank 3, the first component after the hot path.
+ * Unrestricted configuration (67 modes: 0 planar, 1 DC, 2..66 angular; 18 horizontal,
+ * 50 vertical).  LM chroma and the MPM derivation stay with the caller.
+ * ---------------------------------------------------------------------------------- */
+#define XVCB200_INTRA_REF_STRIDE 129   /* IntraPrediction::kRefSampleStride_ = 2 * 64 + 1, intra_prediction.h:40 */
+#define XVCB200_INTRA_NUM_MODES 67     /* kNbrIntraModesExt, cu_types.h:86 */
+
+/* IntraPrediction::FillReferenceState (intra_prediction.cc:128-147) with the neighbour
+ * availability (DetermineNeighbors :688-707) given explicitly: ComputeRefSamples (:709-851)
+ * into ref_samples and, if ref_filtered != NULL, FilterRefSamples (:853-876) into ref_filtered.
+ * Both arrays: 2 x XVCB200_INTRA_REF_STRIDE samples laid out like IntraPrediction::RefState
+ * ([0] above-left, [1 .. w+h] above, [stride + y] left; unused entries are written as 0).
+ * `block` = HOST pointer to the block's top-left sample inside the reconstructed plane; only
+ * neighbours declared available are read.  above_right / below_left = number of available
+ * samples beyond the block (CodingUnit::GetCuSizeAboveRight / GetCuSizeBelowLeft), 0 = none. */
+void xvcb200_intra_ref_samples(int width, int height, int bitdepth, int has_above_left, int has_above, int above_right,
+                               int has_left, int below_left, const uint16_t *block, ptrdiff_t stride,
+                               uint16_t *ref_samples, uint16_t *ref_filtered);
+/* IntraPrediction::Predict (intra_prediction.cc:81-126) for planar / DC / angular modes.
+ * is_luma selects reference smoothing (UseFilteredRefSamples :342-364; width/height are then
+ * the CU's luma size) and the edge filters of blocks up to 16x16.  Host pointers. */
+void xvcb200_intra_predict(int mode, int width, int height, int bitdepth, int is_luma, const uint16_t *ref_samples,
+                           const uint16_t *ref_filtered, uint16_t *pred, ptrdiff_t stride);
+
+typedef struct {
+  int32_t x, y;                      /* luma position of the block */
+  uint8_t w, h;
+  uint8_t has_above_left, has_above, has_left;
+  uint8_t above_right, below_left;   /* available samples beyond the block */
+  uint8_t reserved;
+} xvcb200_intra_job;
+/* First loop of IntraSearch::DetermineSlowIntraModes (xvc_enc_lib/intra_search.cc:185-216) for
+ * n luma blocks at once: for every mode the SATD (SampleMetric kSatd incl. the bit-depth shift)
+ * of its prediction against the original block in orig_slot.  Reference samples are taken from
+ * the luma plane of src_slot (the reconstruction of the blocks coded so far, or any picture for
+ * a pre-analysis).  satd: HOST array n x XVCB200_INTRA_NUM_MODES; the mode bits and the sort
+ * stay with the caller (they depend on the entropy coder's state). */
+int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const xvcb200_intra_job *jobs, int n,
+                            uint32_t *satd);
+
+/* ------------------------------------------------------------------------------------
  * (C) picture-level hot path
  * ---------------------------------------------------------------------------------- */
 typedef struct {

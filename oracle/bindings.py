@@ -125,6 +125,10 @@ class Oracle:
         L.xo_deblock_picture.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
         L.xo_deblock_band.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int]
         L.xo_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+        L.xo_intra_ref_samples.argtypes = [c_int] * 8 + [c_void_p, c_ssize, c_void_p]
+        L.xo_intra_filter_ref.argtypes = [c_int, c_int, c_void_p, c_void_p]
+        L.xo_intra_predict.argtypes = [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_ssize]
+        L.xo_intra_satd_scan.argtypes = [c_int, c_int, c_int, c_void_p, c_ssize, c_void_p, c_void_p, c_void_p]
 
     # ---- leaf
     def sad(self, kind, a, b, w, h, sa=None, sb=None):
@@ -195,6 +199,31 @@ class Oracle:
     def pad_border(self, pic):
         s = pic.c_struct()
         self.L.xo_pad_border(ctypes.byref(s))
+
+    # ---- intra prediction (xvc_oracle_intra.c)
+    def intra_ref_samples(self, w, h, bitdepth, nb, plane, x, y):
+        plane = np.ascontiguousarray(plane, dtype=np.uint16)
+        ref = np.zeros(2 * abi.INTRA_REF_STRIDE, dtype=np.uint16)
+        filt = np.zeros(2 * abi.INTRA_REF_STRIDE, dtype=np.uint16)
+        blk = ctypes.c_void_p(plane.ctypes.data + (y * plane.shape[1] + x) * 2)
+        self.L.xo_intra_ref_samples(w, h, bitdepth, int(nb[0]), int(nb[1]), int(nb[2]), int(nb[3]), int(nb[4]), blk,
+                                    ctypes.c_ssize_t(plane.shape[1]), abi.ptr(ref))
+        self.L.xo_intra_filter_ref(w, h, abi.ptr(ref), abi.ptr(filt))
+        return ref, filt
+
+    def intra_predict(self, mode, w, h, bitdepth, is_luma, ref, filt):
+        pred = np.zeros((h, w), dtype=np.uint16)
+        self.L.xo_intra_predict(mode, w, h, bitdepth, int(is_luma), abi.ptr(np.ascontiguousarray(ref, dtype=np.uint16)),
+                                abi.ptr(None if filt is None else np.ascontiguousarray(filt, dtype=np.uint16)), abi.ptr(pred),
+                                ctypes.c_ssize_t(w))
+        return pred
+
+    def intra_satd_scan(self, w, h, bitdepth, orig_plane, x, y, ref, filt):
+        orig_plane = np.ascontiguousarray(orig_plane, dtype=np.uint16)
+        out = np.zeros(abi.INTRA_NUM_MODES, dtype=np.uint32)
+        blk = ctypes.c_void_p(orig_plane.ctypes.data + (y * orig_plane.shape[1] + x) * 2)
+        self.L.xo_intra_satd_scan(w, h, bitdepth, blk, ctypes.c_ssize_t(orig_plane.shape[1]), abi.ptr(ref), abi.ptr(filt), abi.ptr(out))
+        return out
 
     def me_search(self, orig, refs, bitdepth, cus, jobs, lambda_sqrt):
         res = np.zeros(len(jobs), dtype=abi.me_result_dtype)
@@ -272,6 +301,7 @@ class Ref:
         L.xref_transform_matrix.restype = ctypes.POINTER(ctypes.c_int16)
         L.xref_session_create.restype = c_void_p
         L.xref_session_create.argtypes = [c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_i64, c_int, c_int, c_int, c_int]
+        L.xref_intra_scan.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.xref_qp_info.argtypes = [c_int, c_int, c_double, c_int, c_int, c_int, c_void_p]
         L.xref_sad.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ssize, c_void_p, c_ssize]
         L.xref_ssd.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ssize, c_void_p, c_ssize]
@@ -450,6 +480,26 @@ class RefSession:
 
     def deblock_picture(self, beta_offset=0, tc_offset=0):
         self.L.xref_deblock_picture(self.h, beta_offset, tc_offset)
+
+    def intra_scan(self, cus, comp=0, want_pred=True):
+        """CUs in coding order -> (jobs, ref_samples, ref_filtered, predictions per CU [67][h][w], satd [n][67])."""
+        n = len(cus)
+        sh = 1 if comp else 0
+        jobs = np.zeros(n, dtype=abi.intra_job_dtype)
+        ref = np.zeros((n, 2 * abi.INTRA_REF_STRIDE), dtype=np.uint16)
+        filt = np.zeros((n, 2 * abi.INTRA_REF_STRIDE), dtype=np.uint16)
+        sizes = [abi.INTRA_NUM_MODES * int(c["w"] >> sh) * int(c["h"] >> sh) for c in cus]
+        pred = np.zeros(sum(sizes), dtype=np.uint16) if want_pred else None
+        satd = np.zeros((n, abi.INTRA_NUM_MODES), dtype=np.uint32)
+        self.L.xref_intra_scan(self.h, abi.ptr(np.ascontiguousarray(cus)), n, comp, abi.ptr(jobs), abi.ptr(ref), abi.ptr(filt),
+                               abi.ptr(pred), abi.ptr(satd))
+        preds = None
+        if want_pred:
+            preds, off = [], 0
+            for c, sz in zip(cus, sizes):
+                preds.append(pred[off:off + sz].reshape(abi.INTRA_NUM_MODES, int(c["h"] >> sh), int(c["w"] >> sh)))
+                off += sz
+        return jobs, ref, filt, preds, satd
 
     def pad_border_rec(self):
         self.L.xref_pad_border_rec(self.h)

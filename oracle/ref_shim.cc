@@ -27,6 +27,7 @@
 #include "xvc_common_lib/coding_unit.h"
 #include "xvc_common_lib/deblocking_filter.h"
 #include "xvc_common_lib/inter_prediction.h"
+#include "xvc_common_lib/intra_prediction.h"
 #include "xvc_common_lib/picture_data.h"
 #include "xvc_common_lib/quantize.h"
 #include "xvc_common_lib/segment_header.h"
@@ -711,6 +712,63 @@ void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const
   if (cus_out) {
     std::memcpy(cus_out, cus_in, sizeof(xvcb200_cu) * n);
     xref_session_get_cus(s, cus_out, n);
+  }
+}
+
+// ---------------------------------------------------------------- intra prediction
+// For the CUs of `cus` in coding order (each one sees only the CUs before it, like the encoder
+// while it walks the picture): the neighbour availability, the reference samples as
+// IntraPrediction::FillReferenceState leaves them (from the session's reconstruction picture),
+// the prediction of every mode (planar, DC, 65 angular) and, for luma, its SATD against the
+// session's original picture.  comp: 0 luma, 1/2 chroma.
+//   ref_out / filt_out : n x 2 x 129 samples (entries the block does not use are zeroed)
+//   pred_out           : for CU i, 67 blocks of (w x h) tight samples, CUs back to back (or null)
+//   satd_out           : n x 67 (luma only, or null)
+void xref_intra_scan(xref_session *s, const xvcb200_cu *cus, int n, int comp_i, xvcb200_intra_job *jobs_out,
+                     uint16_t *ref_out, uint16_t *filt_out, uint16_t *pred_out, uint32_t *satd_out) {
+  EnsureInit(s);
+  const YuvComponent comp = static_cast<YuvComponent>(comp_i);
+  IntraPrediction ip(s->bitdepth);
+  SampleMetric satd(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth, MetricType::kSatd);
+  Qp qp(s->pic_qp, ChromaFormat::k420, s->bitdepth, 1.0, 1, 0, 0);
+  const ptrdiff_t rs = IntraPrediction::kRefSampleStride_;
+  std::vector<Sample> tmp(64 * 64 * 2);
+  size_t pred_off = 0;
+  for (int i = 0; i < n; i++) {
+    const xvcb200_cu &d = cus[i];
+    CodingUnit *cu = s->pic_data->CreateCu(CuTree::Primary, d.depth, d.x, d.y, d.w, d.h);
+    cu->SetPredMode(PredictionMode::kIntra);
+    cu->SetQp(d.qp);
+    const int w = cu->GetWidth(comp), h = cu->GetHeight(comp), x = cu->GetPosX(comp), y = cu->GetPosY(comp);
+    xvcb200_intra_job &j = jobs_out[i];
+    std::memset(&j, 0, sizeof(j));
+    j.x = x; j.y = y; j.w = static_cast<uint8_t>(w); j.h = static_cast<uint8_t>(h);
+    j.has_left = x > 0; j.has_above = y > 0; j.has_above_left = x > 0 && y > 0;          // DetermineNeighbors, :688-707
+    j.below_left = x > 0 ? static_cast<uint8_t>(cu->GetCuSizeBelowLeft(comp)) : 0;
+    j.above_right = y > 0 ? static_cast<uint8_t>(cu->GetCuSizeAboveRight(comp)) : 0;
+    IntraPrediction::RefState state;
+    state.ref_samples.fill(0);
+    state.ref_filtered.fill(0);
+    ip.FillReferenceState(*cu, comp, *s->rec, &state);
+    for (int k = 0; k < 2 * rs; k++) {
+      const bool used = k <= w + h || (k >= rs && k < rs + w + h);
+      ref_out[static_cast<size_t>(i) * 2 * rs + k] = used ? state.ref_samples[k] : 0;
+      filt_out[static_cast<size_t>(i) * 2 * rs + k] = (used && comp_i == 0) ? state.ref_filtered[k] : 0;
+    }
+    for (int mode = 0; mode < kNbrIntraModesExt; mode++) {
+      // horizontal modes of non-square blocks write the transposed block first: 64-sample stride, 128 rows
+      SampleBuffer out(tmp.data(), 64);
+      ip.Predict(static_cast<IntraMode>(mode), *cu, comp, state, *s->rec, &out);
+      if (pred_out) {
+        for (int r = 0; r < h; r++) std::memcpy(pred_out + pred_off + static_cast<size_t>(r) * w, tmp.data() + r * 64, sizeof(Sample) * w);
+        pred_off += static_cast<size_t>(w) * h;
+      }
+      if (satd_out && comp_i == 0)
+        satd_out[static_cast<size_t>(i) * kNbrIntraModesExt + mode] = static_cast<uint32_t>(
+            satd.Compare(qp, comp, w, h, s->orig->GetSamplePtr(comp, x, y), s->orig->GetStride(comp), tmp.data(), 64));
+    }
+    s->pic_data->MarkUsedInPic(cu);
+    s->cus.push_back(cu);
   }
 }
 

@@ -105,6 +105,16 @@ void xo_encode_picture(const xo_picture *orig, const xo_picture *const refs[2][5
                        const xvcb200_picture_params *params, xvcb200_me_result *me_results,
                        xvcb200_tu_result *tu_results);
 
+/* ---- intra prediction (intra_prediction.cc, xvc_oracle_intra.c); ref arrays: 2 x XVCB200_INTRA_REF_STRIDE ---- */
+void xo_intra_ref_samples(int w, int h, int bitdepth, int has_above_left, int has_above, int above_right, int has_left,
+                          int below_left, const uint16_t *block, ptrdiff_t stride, uint16_t *ref);
+void xo_intra_filter_ref(int w, int h, const uint16_t *src, uint16_t *dst);
+int xo_intra_use_filtered_ref(int mode, int w, int h);
+void xo_intra_predict(int mode, int w, int h, int bitdepth, int luma, const uint16_t *ref_samples,
+                      const uint16_t *ref_filtered, uint16_t *out, ptrdiff_t os);
+void xo_intra_satd_scan(int w, int h, int bitdepth, const uint16_t *orig, ptrdiff_t ostride, const uint16_t *ref_samples,
+                        const uint16_t *ref_filtered, uint32_t *satd);
+
 #ifdef __cplusplus
 }
 #endif

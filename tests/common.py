@@ -109,3 +109,36 @@ def oracle_refs(oracle, width, height, r0, r1=None):
         refs[(1, 0)] = Picture(width, height, 80, r1)
         oracle.pad_border(refs[(1, 0)])
     return refs
+
+
+def intra_jobs_in_coding_order(cus, width, height, comp=0):
+    """xvcb200_intra_job per CU when the CUs are coded in array order: a neighbour is available once
+    its CU has been coded.  Mirrors IntraPrediction::DetermineNeighbors (intra_prediction.cc:688-707)
+    with CodingUnit::GetCuSizeAboveRight / GetCuSizeBelowLeft (coding_unit.cc:304-336) on a 4x4 map;
+    checked against the reference in tests/test_intra_oracle.py."""
+    coded = np.zeros((height // 4 + 1, width // 4 + 1), dtype=bool)
+    sh = 1 if comp else 0
+    jobs = np.zeros(len(cus), dtype=abi.intra_job_dtype)
+
+    def at(x, y):
+        return 0 <= x < width and 0 <= y < height and coded[y // 4, x // 4]
+
+    for k, c in enumerate(cus):
+        x, y, w, h = int(c["x"]), int(c["y"]), int(c["w"]), int(c["h"])
+        ar = bl = 0
+        if y > 0:
+            for i in range(h, -1, -4):
+                if at(x + w - 4 + i, y - 4):
+                    ar = i
+                    break
+        if x > 0:
+            for i in range(w, -1, -4):
+                if at(x - 4, y + h - 4 + i):
+                    bl = i
+                    break
+        j = jobs[k]
+        j["x"], j["y"], j["w"], j["h"] = x >> sh, y >> sh, w >> sh, h >> sh
+        j["has_left"], j["has_above"], j["has_above_left"] = x > 0, y > 0, x > 0 and y > 0
+        j["above_right"], j["below_left"] = ar >> sh, bl >> sh
+        coded[y // 4:(y + h) // 4, x // 4:(x + w) // 4] = True
+    return jobs

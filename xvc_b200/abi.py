@@ -54,6 +54,13 @@ qp_dtype = np.dtype([
     ("lambda", "<f8", (3,)), ("lambda_sqrt", "<f8"),
 ], align=True)
 
+# intra prediction (IntraPrediction::RefState: 2 x 129 samples; 67 modes)
+INTRA_REF_STRIDE, INTRA_NUM_MODES = 129, 67
+intra_job_dtype = np.dtype([
+    ("x", "<i4"), ("y", "<i4"), ("w", "u1"), ("h", "u1"), ("has_above_left", "u1"), ("has_above", "u1"),
+    ("has_left", "u1"), ("above_right", "u1"), ("below_left", "u1"), ("reserved", "u1"),
+], align=True)
+
 ABI_STRUCTS = {
     0: ("xvcb200_cu", cu_dtype),
     1: ("xvcb200_me_job", me_job_dtype),
@@ -63,6 +70,7 @@ ABI_STRUCTS = {
     5: ("xvcb200_picture_params", picture_params_dtype),
     6: ("xvcb200_plane_geom", plane_geom_dtype),
     7: ("xvcb200_qp", qp_dtype),
+    8: ("xvcb200_intra_job", intra_job_dtype),
 }
 
 

@@ -138,6 +138,7 @@ int xvcb200_abi_sizeof(int which) {
     case 5: return (int)sizeof(xvcb200_picture_params);
     case 6: return (int)sizeof(xvcb200_plane_geom);
     case 7: return (int)sizeof(xvcb200_qp);
+    case 8: return (int)sizeof(xvcb200_intra_job);
     default: return -1;
   }
 }
@@ -286,6 +287,53 @@ void xvcb200_fwd_transform(int w, int h, int bd, int tx_hor, int tx_ver, int dst
 void xvcb200_fwd_transform_skip(int w, int h, int bd, const int16_t *resi, ptrdiff_t rs, int16_t *coeff, ptrdiff_t cs) { leaf_transform(1, w, h, bd, 0, 0, 0, 0, 1, resi, rs, coeff, cs); }
 void xvcb200_inv_transform(int w, int h, int bd, int tx_hor, int tx_ver, int dst4x4, int dc_only, const int16_t *coeff, ptrdiff_t cs, int16_t *resi, ptrdiff_t rs) { leaf_transform(0, w, h, bd, tx_hor, tx_ver, dst4x4, dc_only, 0, coeff, cs, resi, rs); }
 void xvcb200_inv_transform_skip(int w, int h, int bd, const int16_t *coeff, ptrdiff_t cs, int16_t *resi, ptrdiff_t rs) { leaf_transform(0, w, h, bd, 0, 0, 0, 0, 1, coeff, cs, resi, rs); }
+
+// ---------------------------------------------------------------- (A) intra prediction, one block
+void xvcb200_intra_ref_samples(int w, int h, int bitdepth, int has_above_left, int has_above, int above_right, int has_left,
+                               int below_left, const uint16_t *block, ptrdiff_t stride, uint16_t *ref_samples,
+                               uint16_t *ref_filtered) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  // the available neighbours, tightly: [0] corner, [1 .. w+h] row above, then the column to the left
+  const int n = w + h;
+  uint16_t *e = reinterpret_cast<uint16_t *>(L.h);
+  memset(e, 0, sizeof(uint16_t) * (2 * n + 1));
+  if (has_above_left) e[0] = block[-stride - 1];
+  if (has_above) {
+    memcpy(e + 1, block - stride, sizeof(uint16_t) * w);
+    if (above_right > 0) memcpy(e + 1 + w, block - stride + w, sizeof(uint16_t) * above_right);
+  }
+  if (has_left)
+    for (int y = 0; y < h + (below_left > 0 ? below_left : 0); y++) e[n + 1 + y] = block[y * stride - 1];
+  const size_t off_ref = (sizeof(uint16_t) * (2 * n + 1) + 15) & ~(size_t)15, ref_bytes = sizeof(uint16_t) * 2 * XVCB200_INTRA_REF_STRIDE;
+  const size_t off_filt = (off_ref + ref_bytes + 15) & ~(size_t)15;
+  cudaMemcpyAsync(L.d, L.h, off_ref, cudaMemcpyHostToDevice, L.stream);
+  const int nb[5] = {has_above_left, has_above, above_right, has_left, below_left};
+  cudaError_t err = launch_intra_ref(L.stream, w, h, bitdepth, nb, reinterpret_cast<const Sample *>(L.d),
+                                     reinterpret_cast<Sample *>(L.d + off_ref),
+                                     ref_filtered ? reinterpret_cast<Sample *>(L.d + off_filt) : nullptr);
+  cudaMemcpyAsync(L.h + off_ref, L.d + off_ref, off_filt + ref_bytes - off_ref, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(err)) return;
+  memcpy(ref_samples, L.h + off_ref, ref_bytes);
+  if (ref_filtered) memcpy(ref_filtered, L.h + off_filt, ref_bytes);
+}
+
+void xvcb200_intra_predict(int mode, int w, int h, int bitdepth, int is_luma, const uint16_t *ref_samples,
+                           const uint16_t *ref_filtered, uint16_t *pred, ptrdiff_t stride) {
+  Leaf &L = t_leaf;
+  if (!L.init()) return;
+  const size_t ref_bytes = sizeof(uint16_t) * 2 * XVCB200_INTRA_REF_STRIDE;
+  const size_t off_filt = (ref_bytes + 15) & ~(size_t)15, off_out = (off_filt + ref_bytes + 15) & ~(size_t)15;
+  memcpy(L.h, ref_samples, ref_bytes);
+  if (ref_filtered) memcpy(L.h + off_filt, ref_filtered, ref_bytes);
+  cudaMemcpyAsync(L.d, L.h, off_out, cudaMemcpyHostToDevice, L.stream);
+  cudaError_t err = launch_intra_predict(L.stream, mode, w, h, bitdepth, is_luma, reinterpret_cast<const Sample *>(L.d),
+                                         ref_filtered ? reinterpret_cast<const Sample *>(L.d + off_filt) : nullptr,
+                                         reinterpret_cast<Sample *>(L.d + off_out), w);
+  cudaMemcpyAsync(L.h + off_out, L.d + off_out, sizeof(uint16_t) * (size_t)w * h, cudaMemcpyDeviceToHost, L.stream);
+  if (!L.done(err)) return;
+  stage_out(L, off_out, pred, stride, h, w, 2);
+}
 
 // Qp::Qp (quantize.cc:48-92): host-side scalar set-up, no device work
 void xvcb200_qp_init(xvcb200_qp *out, int qp, int chroma_format, int bitdepth, double lambda, int table, int off_u, int off_v) {
@@ -1051,6 +1099,31 @@ int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearc
   c->check(launch_full_search(c->stream, c->d_cus, dj, n, c->bitdepth, lambda_me_of(lambda_sqrt), c->plane(orig_slot, 0),
                               c->ex.d_luma_views, c->ex.d_me), "full_search");
   c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "fs results");
+  return xvcb200_sync(c);
+}
+
+int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const xvcb200_intra_job *jobs, int n,
+                            uint32_t *satd) {
+  if (!slot_ok(ctx, orig_slot) || !slot_ok(ctx, src_slot) || !jobs || !satd || n < 0) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  for (int i = 0; i < n; i++) {
+    const xvcb200_intra_job &j = jobs[i];
+    const bool pow2 = j.w >= 4 && j.w <= 64 && j.h >= 4 && j.h <= 64 && !(j.w & (j.w - 1)) && !(j.h & (j.h - 1));
+    if (!pow2 || j.x < 0 || j.y < 0 || j.x + j.w > c->width || j.y + j.h > c->height || j.above_right > j.h || j.below_left > j.w ||
+        ((j.has_above_left || j.has_left || j.below_left) && j.x == 0) || ((j.has_above_left || j.has_above || j.above_right) && j.y == 0) ||
+        j.x + j.w + j.above_right > c->width || j.y + j.h + j.below_left > c->height)
+      return XVCB200_INVALID_ARGUMENT;
+  }
+  if (n == 0) return XVCB200_OK;
+  const size_t job_bytes = (sizeof(*jobs) * (size_t)n + 15) & ~(size_t)15, out_bytes = sizeof(uint32_t) * XVCB200_INTRA_NUM_MODES * (size_t)n;
+  uint8_t *d = static_cast<uint8_t *>(c->scratch(job_bytes + out_bytes));
+  if (!d) return c->status;
+  join_upload_slot(c, orig_slot);
+  join_upload_slot(c, src_slot);
+  c->check(cudaMemcpyAsync(d, jobs, sizeof(*jobs) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "intra jobs");
+  c->check(launch_intra_satd_scan(c->stream, reinterpret_cast<const xvcb200_intra_job *>(d), n, c->bitdepth, c->plane(orig_slot, 0),
+                                  c->plane(src_slot, 0), reinterpret_cast<uint32_t *>(d + job_bytes)), "intra_satd_scan");
+  c->check(cudaMemcpyAsync(satd, d + job_bytes, out_bytes, cudaMemcpyDeviceToHost, c->stream), "intra satd");
   return xvcb200_sync(c);
 }
 

@@ -130,6 +130,13 @@ cudaError_t launch_me_decide(cudaStream_t s, xvcb200_cu *d_cus, int n, int nl, c
 cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, int n, int nl, const int ref_slot[2],
                                 const int range[2], xvcb200_me_job *d_jobs);
 
+// intra.cu
+cudaError_t launch_intra_ref(cudaStream_t s, int w, int h, int bitdepth, const int nb[5], const Sample *d_edges, Sample *d_ref,
+                             Sample *d_filt);
+cudaError_t launch_intra_predict(cudaStream_t s, int mode, int w, int h, int bitdepth, int luma, const Sample *d_ref,
+                                 const Sample *d_filt, Sample *d_out, int os);
+cudaError_t launch_intra_satd_scan(cudaStream_t s, const xvcb200_intra_job *d_jobs, int n, int bitdepth, PlaneView orig,
+                                   PlaneView src, uint32_t *d_satd);
 // deblock.cu
 cudaError_t launch_pad_border(cudaStream_t s, Pic3 pic, const int pad[3]);
 // slot planes <-> one tight buffer (planes back to back); widths must be multiples of 4 samples, 8-byte aligned rows

@@ -39,6 +39,7 @@ EXPORTS = [
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_tq_reconstruct",
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
+    "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan",
 ]
 
 
@@ -86,6 +87,9 @@ def load():
     L.xvcb200_qp_init.argtypes = [c_void_p, c_int, c_int, c_int, c_double, c_int, c_int, c_int]
     L.xvcb200_quant_fast.argtypes = [c_int] * 7 + [c_void_p, c_ssize, c_void_p, c_ssize]
     L.xvcb200_dequant.argtypes = [c_int] * 4 + [c_void_p, c_ssize, c_void_p, c_ssize]
+    L.xvcb200_intra_ref_samples.argtypes = [c_int] * 8 + [c_void_p, c_ssize, c_void_p, c_void_p]
+    L.xvcb200_intra_predict.argtypes = [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_ssize]
+    L.xvcb200_intra_satd_scan.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
     L.xvcb200_ctx_create.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]
     L.xvcb200_ctx_destroy.argtypes = [c_void_p]
     L.xvcb200_ctx_set_stream.argtypes = [c_void_p, c_void_p]
@@ -235,6 +239,28 @@ def dequant(w, h, bitdepth, qp_bd, lev):
     L.xvcb200_dequant(w, h, bitdepth, qp_bd, abi.ptr(lev), lev.shape[1], abi.ptr(out), w)
     _check_leaf(L)
     return out
+
+
+def intra_ref_samples(w, h, bitdepth, nb, plane, x, y, want_filtered=True):
+    """IntraPrediction::FillReferenceState for the block at (x, y) of a host plane; nb = (has_above_left,
+    has_above, above_right, has_left, below_left).  Returns (ref_samples, ref_filtered) of 2 x 129 samples."""
+    L = load()
+    plane = np.ascontiguousarray(plane, dtype=np.uint16)
+    ref = np.zeros(2 * abi.INTRA_REF_STRIDE, dtype=np.uint16)
+    filt = np.zeros(2 * abi.INTRA_REF_STRIDE, dtype=np.uint16) if want_filtered else None
+    L.xvcb200_intra_ref_samples(w, h, bitdepth, int(nb[0]), int(nb[1]), int(nb[2]), int(nb[3]), int(nb[4]),
+                                _off(plane, y, x), plane.strides[0] // 2, abi.ptr(ref), abi.ptr(filt))
+    _check_leaf(L)
+    return ref, filt
+
+
+def intra_predict(mode, w, h, bitdepth, is_luma, ref, filt):
+    L = load()
+    pred = np.zeros((h, w), dtype=np.uint16)
+    L.xvcb200_intra_predict(mode, w, h, bitdepth, int(is_luma), abi.ptr(np.ascontiguousarray(ref, dtype=np.uint16)),
+                            abi.ptr(None if filt is None else np.ascontiguousarray(filt, dtype=np.uint16)), abi.ptr(pred), w)
+    _check_leaf(L)
+    return pred
 
 
 def launch_count():
@@ -425,6 +451,12 @@ class Context:
             poc[l, i] = p
         self._ok(self.L.xvcb200_deblock_band(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
                                              abi.ptr(poc), pass_mask, y_begin, y_end))
+
+    def intra_satd_scan(self, orig_slot, src_slot, jobs):
+        jobs = np.ascontiguousarray(jobs, dtype=abi.intra_job_dtype)
+        out = np.zeros((len(jobs), abi.INTRA_NUM_MODES), dtype=np.uint32)
+        self._ok(self.L.xvcb200_intra_satd_scan(self.h, orig_slot, src_slot, abi.ptr(jobs), len(jobs), abi.ptr(out)))
+        return out
 
     STAGES = ("me_jobs", "tz_search", "subpel_search", "motion_compensate", "tq_reconstruct", "deblock", "pad_border")
 
