@@ -1,7 +1,8 @@
 // Motion estimation: InterSearch::MotionEstNormal (inter_search.cc:606-662) for a batch of
 // (CU, reference picture) jobs.
 //
-//   tz_search_kernel   TzSearch::Search (inter_tz_search.cc:84-171), one WARP per job.
+//   tz_search_kernel   TzSearch::Search (inter_tz_search.cc:84-171): persistent CTAs, a CTU's jobs
+//                      per step, searched by warp teams (16 / 4 / 1 warps by block size).
 //   (sub-pel search: subpel.cu)
 //   full_search_kernel InterSearch::FullSearch (inter_search.cc:853-891), one warp per job.
 //
@@ -11,8 +12,10 @@
 // state equals: best = first candidate attaining the minimum cost over the list, kept only if
 // that minimum is below the incoming best; last_position / last_range are those of that
 // candidate; "changed" = that minimum is below the incoming best.  The kernels evaluate a
-// whole list at once (one candidate per lane, lane index = list position) and take the
-// minimum of (cost << 5 | lane) -- the same winner, found in parallel.
+// whole list at once and take the minimum of (cost << 5 | list position) -- the same winner,
+// found in parallel.  The rounds of one diamond pass share their centre, so their lists do not
+// depend on each other either: a whole pass is evaluated at once and the reference's
+// round-by-round decisions are replayed on the stored costs (see SearchEval).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -377,39 +380,14 @@ __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int 
   }
 }
 
-// Lower bound of the SAD of one candidate from 8-sample segment sums: NSEG segments per row,
-// `rp` = S8 at the candidate's first row/column (uint16), seg = segment sums of the original
-// block, two per word for NSEG >= 2.  VABSDIFF.U32 does |a - b| + c in one instruction.
-template <int NSEG>
-__device__ __forceinline__ uint32_t seg_bound(const uint16_t *rp, int row_stride, const uint32_t *seg, int rows) {
-  uint32_t lb = 0;
-  if (NSEG == 1) {
-    const uint16_t *s16 = reinterpret_cast<const uint16_t *>(seg);
-    for (int r = 0; r < rows; r += 4) {       // rows is a multiple of 4
-#pragma unroll
-      for (int u = 0; u < 4; u++) lb = __usad((unsigned)rp[(r + u) * row_stride], (unsigned)s16[r + u], lb);
-    }
-  } else {
-    for (int r = 0; r < rows; r += 2) {
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-#pragma unroll
-        for (int k = 0; k < NSEG; k += 2) {
-          const uint32_t a2 = seg[((r + u) * NSEG + k) >> 1];
-          lb = __usad((unsigned)rp[k * 8], a2 & 0xffffu, lb);
-          lb = __usad((unsigned)rp[k * 8 + 8], a2 >> 16, lb);
-        }
-        rp += row_stride;
-      }
-    }
-  }
-  return lb;
-}
-
-// The same bound for CH neighbouring grid columns (candidates 5 samples apart in x) of one grid
-// row per lane at once: a segment sum of the original block is fetched once and used for CH
-// candidates, whose S8 operands sit at compile-time offsets from one row pointer -- two
-// instructions (LDS.U16 + VABSDIFF) per segment difference.
+// Lower bound of the SAD of a candidate from 8-sample segment sums (successive elimination):
+// sum_rows sum_k |A8[r][k] - S8[y+r][x+8k]| <= SAD (triangle inequality per segment), with S8 =
+// segment sums of the reference at every position (segment_sum_kernel) and A8 = segment sums of
+// the original block, two per word.  VABSDIFF.U32 does |a - b| + c in one instruction.
+// Evaluated for CH neighbouring grid columns (candidates 5 samples apart in x) of one grid row per
+// lane at once: a segment sum of the original block is fetched once and used for CH candidates,
+// whose S8 operands sit at compile-time offsets from one row pointer -- two instructions
+// (LDS.U16 + VABSDIFF) per segment difference.
 constexpr int kBoundCols = 8;
 template <int NSEG>
 __device__ __forceinline__ void seg_bound_cols(const uint16_t *rp, int row_stride, const uint32_t *seg, int rows,

@@ -165,12 +165,15 @@ class BandedPictureEncoder:
         return self.e.get_rows(comp, y0 >> s, y1 >> s)
 
 
-def frame_parallel_exchange(ctx, dist, rank, world, first_slot):
+def frame_parallel_exchange(ctx, dist, rank, world, first_slot, async_op=False):
     """After every rank reconstructed (and padded) its own picture into slot first_slot+rank:
     one in-place all-gather makes slots [first_slot, first_slot+world) hold all of them on every
-    rank, ready to be used as reference slots."""
+    rank, ready to be used as reference slots.  async_op=True: the collective runs on NCCL's own
+    stream behind the kernels enqueued so far and the returned work's wait() orders a later
+    consumer (or the reuse of these slots) behind it -- the picture encoded next does not
+    depend on it (pictures of one temporal layer, thread_encoder.cc:99-131)."""
     if world == 1:
-        return
+        return None
     whole = ctx.slots_tensor(first_slot, world)
     mine = ctx.slots_tensor(first_slot + rank, 1)
-    dist.all_gather_into_tensor(whole, mine)
+    return dist.all_gather_into_tensor(whole, mine, async_op=async_op)
