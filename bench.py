@@ -383,7 +383,7 @@ def run_ours(args):
     dom = max(stage_avg, key=stage_avg.get)
     achieved = alg_bytes[dom] / (stage_avg[dom] * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_final_traffic.json")     # ncu --set full capture of the dominant kernel
+    tpath = os.path.join(ROOT, "profiles", "r1s2_traffic.json")     # ncu --set full capture of the dominant kernel
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("kernel", "").startswith(dom):

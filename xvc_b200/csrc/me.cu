@@ -350,14 +350,15 @@ __global__ void segment_sum_kernel(PlaneView src, Sample *__restrict__ dst00, in
 }
 
 // stages the box [rx0, rx0 + 8*cpr) x [ry0, ry0 + bh) of a plane into shared memory rows of `spw` words
+constexpr int kStageDepth = 4;
 __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int rx0, int ry0, int bh, int cpr, int spw,
                                           uint32_t *s_region, int tid, int nthreads) {
   const int total = bh * cpr;
   const uint32_t magic = 0xffffffffu / (uint32_t)cpr + 1u;    // idx / cpr == umulhi(idx, magic) for idx * cpr < 2^32
-  for (int idx0 = tid; idx0 < total; idx0 += 4 * nthreads) {
-    uint4 v[4];
+  for (int idx0 = tid; idx0 < total; idx0 += kStageDepth * nthreads) {
+    uint4 v[kStageDepth];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {            // four independent 16-byte loads in flight per thread
+    for (int u = 0; u < kStageDepth; u++) {            // independent 16-byte loads in flight per thread
       const int idx = idx0 + u * nthreads;
       if (idx < total) {
         const int row = (int)__umulhi((uint32_t)idx, magic), ch = idx - row * cpr;
@@ -365,7 +366,7 @@ __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int 
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < kStageDepth; u++) {
       const int idx = idx0 + u * nthreads;
       if (idx < total) {
         const int row = (int)__umulhi((uint32_t)idx, magic), ch = idx - row * cpr;
