@@ -211,6 +211,31 @@ def test_me_search(oracle, content, bd, min_size):
         assert np.median(mv0[:, 0]) == 16 * 16 and np.median(mv0[:, 1]) == 8 * 16
 
 
+@pytest.mark.parametrize("ranges", [(1, 2), (3, 5), (8, 16), (40, 64), (200, 256)])
+def test_me_search_ranges(oracle, ranges):
+    """Every number of diamond rounds a pass can have (1 .. 9: radii 1, 2, 4, ... <= range), incl.
+    ranges that are not powers of two and windows narrower than a column chunk of the raster bound."""
+    width, height, bd = 208, 120, 10
+    cur, r0, r1 = common.frames(width, height, bd, 212, "synth")
+    lam = workload.lambda_for_qp(30)
+    ctx = _ctx(width, height, bd, cur, r0, r1)
+    rng = np.random.default_rng(214 + ranges[0])
+    cus = workload.make_partition(width, height, seed=5, min_size=4)
+    ctx.set_cus(cus)
+    jobs = common.me_jobs(cus, rng, 2, ranges, 60, slots=(1, 2))
+    rg = ctx.me_search(0, jobs, np.sqrt(lam))
+    ojobs = jobs.copy()
+    ojobs["ref_slot"] = 0
+    ro = oracle.me_search(Picture(width, height, 0, cur), common.oracle_refs(oracle, width, height, r0, r1), bd, cus,
+                          ojobs, np.sqrt(lam))
+    for f in ("mv_fullpel", "cost_fullpel", "num_sad", "mv", "dist", "cost"):
+        assert np.array_equal(rg[f], ro[f]), f
+    bad = jobs[:1].copy()
+    bad["search_range"] = 257
+    with pytest.raises(lib.XvcB200Error):
+        ctx.me_search(0, bad, np.sqrt(lam))
+
+
 def test_me_search_far_predictors(oracle):
     """Predictors far outside the picture: ClipMv, window clipping and reads from the border."""
     width, height, bd = 136, 72, 10

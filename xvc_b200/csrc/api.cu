@@ -1257,6 +1257,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     return c->status;
   const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
   const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
+  for (int l = 0; l < nl; l++)      // GetSearchRangeUniPred yields 96..256; the search kernel holds a pass of <= 9 rounds
+    if (ranges[l] < 1 || ranges[l] > 256) return XVCB200_INVALID_ARGUMENT;
   if (!ensure_tz_scratch(c, n * nl)) return c->status;
   join_upload_slot(c, prm->orig_slot);           // explicit read set: an upload made ahead for the NEXT picture is not waited for
   for (int l = 0; l < nl; l++) join_upload_slot(c, prm->ref_slots[l][0]);
