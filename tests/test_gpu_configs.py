@@ -128,3 +128,48 @@ def test_full_size_picture(oracle, width, height, bd, qp):
     for c in range(3):
         assert np.array_equal(ctx.download_padded(6, c), rec_b[c]), c
     ctx.close()
+
+
+def test_hierarchical_gop_chain(oracle):
+    """Reconstructions stay on the GPU and become reference pictures of later pictures
+    (picture_encoder.cc:149-151: deblock, PadBorder, then the picture is referenced): key picture
+    POC 0 -> uni-predicted POC 16 -> bi-predicted POC 8 (refs 0 / 16) -> bi-predicted POC 4
+    (refs 0 / 8), in the coding order of a hierarchical-B sub-GOP.  Every picture is compared with
+    the oracle running the same chain on its own reconstructions."""
+    width, height, bd, qp = 264, 136, 10, 30
+    canvas = workload.synth_canvas(width, height, 77)
+    frame = lambda poc: workload.synth_frame(canvas, width, height, poc, bd)   # noqa: E731
+    lam = workload.lambda_for_qp(qp)
+    # slots: 0 orig, 1 pred, 2 levels, 3.. reconstructions by coding order
+    ctx = lib.Context(width, height, bd, num_slots=7)
+    ctx.upload(3, frame(0))
+    ctx.pad_border(3)
+    rec_o = {0: Picture(width, height, 80, frame(0))}
+    oracle.pad_border(rec_o[0])
+    slot_of = {0: 3}
+    chain = [(16, 1, (0,)), (8, 0, (0, 16)), (4, 0, (0, 8))]       # (poc, pic_type, reference POCs L0 / L1)
+    for k, (poc, pic_type, ref_pocs) in enumerate(chain):
+        cur = frame(poc)
+        cus = workload.make_partition(width, height, seed=40 + k, min_size=8, qp=qp)
+        ranges = tuple(workload.search_range_uni(poc, p) for p in ref_pocs) + ((96,) if len(ref_pocs) == 1 else ())
+        rec_slot = 4 + k
+        slots = dict(orig=0, ref0=slot_of[ref_pocs[0]], ref1=slot_of[ref_pocs[1]] if len(ref_pocs) > 1 else -1, pred=1, rec=rec_slot, coeff=2)
+        prm = common.picture_params(pic_type, lam, ranges=ranges[:2], pocs=(ref_pocs + (0,))[:2], slots=slots)
+        ctx.upload(0, cur)
+        ctx.set_cus(cus)
+        me_g, tu_g = ctx.encode_picture(prm)
+        ctx.sync()
+        refs = {(0, 0): rec_o[ref_pocs[0]]}
+        if len(ref_pocs) > 1:
+            refs[(1, 0)] = rec_o[ref_pocs[1]]
+        pred, rec = Picture(width, height, 80), Picture(width, height, 80)
+        cus_o = cus.copy()
+        levels, me_o, tu_o = oracle.encode_picture(Picture(width, height, 0, cur), refs, pred, rec, bd, cus_o, prm)
+        assert np.array_equal(me_g, me_o) and np.array_equal(tu_g, tu_o), poc
+        lev_g = ctx.download_coeff(2)
+        for c in range(3):
+            assert np.array_equal(ctx.download_padded(rec_slot, c), rec.full[c]), (poc, c)
+            assert np.array_equal(lev_g[c], levels[c]), (poc, c)
+        rec_o[poc] = rec
+        slot_of[poc] = rec_slot
+    ctx.close()
