@@ -382,15 +382,25 @@ def run_ours(args):
     stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     dom = max(stage_avg, key=stage_avg.get)
     achieved = alg_bytes[dom] / (stage_avg[dom] * 1e-3) / 1e9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, issue = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r1s2_traffic.json")     # ncu --set full capture of the dominant kernel
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("kernel", "").startswith(dom):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            if "warp_instructions_per_launch" in tj:
+                # the ceilings that actually bound the integer search: warp-instruction issue (SMs x 4 schedulers x
+                # clock) and the shared-memory pipe (one wavefront per SM per clock); counts from the same ncu capture
+                sm_clock = 148 * 1.965e9
+                issue = {"warp_instructions_per_launch": tj["warp_instructions_per_launch"],
+                         "issue_frac_of_peak": tj["warp_instructions_per_launch"] / (stage_avg[dom] * 1e-3) / (4 * sm_clock),
+                         "shared_wavefronts_per_launch": tj.get("shared_wavefronts_per_launch"),
+                         "shared_pipe_frac_of_peak": (tj["shared_wavefronts_per_launch"] / (stage_avg[dom] * 1e-3) / sm_clock) if tj.get("shared_wavefronts_per_launch") else None,
+                         "peak": "148 SMs x 4 schedulers (issue) / x 1 wavefront (shared memory) x 1.965 GHz"}
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": alg_bytes[dom], "avg_ms": stage_avg[dom],
                 "note": "integer SAD search: ALU/L1-bound, not HBM-bound; see DESIGN.md for op counts",
+                "compute_ceilings": issue,
                 "stages_ms": stage_avg,
                 "stages_frac_of_hbm": {k: alg_bytes[k] / (v * 1e-3) / 1e9 / peak for k, v in stage_avg.items() if v > 0}}
 

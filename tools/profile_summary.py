@@ -92,6 +92,8 @@ def full(tag, rep, cmd):
     traffic = sum(float(dom[hdr.index(m)].replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}[units[hdr.index(m)]]
                   for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     json.dump({"kernel": short(dom[ik]).replace("_kernel", ""), "dram_bytes_per_launch": traffic,
+               "warp_instructions_per_launch": float(dom[hdr.index("smsp__inst_executed.sum")].replace(",", "")),
+               "shared_wavefronts_per_launch": float(dom[hdr.index("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")].replace(",", "")),
                "source": "profiles/%s_kernels_full.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" % tag},
               open(os.path.join(PROF, tag + "_traffic.json"), "w"))
 
