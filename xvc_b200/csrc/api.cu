@@ -430,7 +430,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   uint32_t *d_pool = nullptr;
   int pool_cap = 1 << 16, pool_ctas = 0;
   // side streams for independent launches inside one stage (T/Q shape classes)
-  static constexpr int kSide = 6;
+  static constexpr int kSide = 16;
   cudaStream_t side[kSide] = {nullptr};
   cudaEvent_t side_ev[kSide] = {nullptr};
   cudaEvent_t fork_ev = nullptr;
@@ -1078,7 +1078,8 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
                             c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), ref_list.data(), (int)ref_list.size(), margin,
                             c->ex.d_pool, c->ex.pool_cap), "tz_search");
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
-                                c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists), "subpel_search");
+                                c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev,
+                                c->ex.n_side, c->ex.fork_ev), "subpel_search");
   c->check(cudaMemcpyAsync(results, c->ex.d_me, sizeof(*results) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "me results");
   return xvcb200_sync(c);
 }
@@ -1282,7 +1283,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   }
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                                c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists), "subpel_search");
+                                c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists, c->ex.side,
+                                c->ex.side_ev, c->ex.n_side, c->ex.fork_ev), "subpel_search");
   c->check(launch_me_decide(c->stream, c->d_cus, n, nl, c->ex.d_me), "me_decide");
   mark();   // 3: sub-pel search + list decision done
   Pic3 refs[2][5];

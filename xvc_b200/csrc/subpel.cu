@@ -469,7 +469,8 @@ static int max_team_bytes(int max_area, int min_area) {
 
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
-                                 xvcb200_me_result *d_res, int *d_lists) {
+                                 xvcb200_me_result *d_res, int *d_lists, cudaStream_t *side, cudaEvent_t *side_ev,
+                                 int n_side, cudaEvent_t fork_ev) {
   if (n <= 0) return cudaSuccess;
   static int num_sms = 0, bytes0 = 0, bytes1 = 0, bytes2 = 0, occ0 = 1, occ1 = 1, occ2 = 1;
   if (!num_sms) {
@@ -497,13 +498,30 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
   subpel_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, d_jobs, n, d_lists, counts);
   subpel_concat_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_lists, counts);
   int *slow = d_lists + 2 * (size_t)n;
+  // The three size classes are independent persistent grids, each sized to fill the register
+  // file on its own; on separate streams the next class's CTAs move in as soon as CTAs of the
+  // previous one retire (its tail) instead of after its last CTA.  The generic kernel consumes
+  // the list of jobs all three hand over, so it joins them.
+  const bool fork = n_side >= 2;
+  cudaStream_t s1 = fork ? side[0] : s, s2 = fork ? side[1] : s;
+  if (fork) {
+    cudaEventRecord(fork_ev, s);
+    cudaStreamWaitEvent(s1, fork_ev, 0);
+    cudaStreamWaitEvent(s2, fork_ev, 0);
+  }
   // persistent grids: as many CTAs as fit, each strides over its class list (largest blocks first)
   subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + (size_t)n, counts + 1, slow, counts + 2,
                                                          bytes2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s>>>(d_cus, d_jobs, d_lists, counts, slow, counts + 2, bytes1, bitdepth,
-                                                          lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, slow,
-                                                             counts + 2, bytes0, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s1>>>(d_cus, d_jobs, d_lists, counts, slow, counts + 2, bytes1, bitdepth,
+                                                           lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s2>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, slow,
+                                                              counts + 2, bytes0, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  if (fork) {
+    cudaEventRecord(side_ev[0], s1);
+    cudaEventRecord(side_ev[1], s2);
+    cudaStreamWaitEvent(s, side_ev[0], 0);
+    cudaStreamWaitEvent(s, side_ev[1], 0);
+  }
   subpel_generic_kernel<<<num_sms * 4, 128, 0, s>>>(d_cus, d_jobs, slow, counts + 2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
   return cudaGetLastError();
 }
