@@ -1203,8 +1203,14 @@ int xvcb200_deblock_picture_ex(xvcb200_ctx *c, int rec_slot, int pic_type, int b
   if (!c) return XVCB200_INVALID_ARGUMENT;
   return xvcb200_deblock_band(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, 3, 0, c->height);
 }
+static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
+                        int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready);
 int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
                          int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end) {
+  return deblock_impl(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, pass_mask, y_begin, y_end, false);
+}
+static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
+                        int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready) {
   if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1 || y_begin < 0 || y_end > c->height ||
       y_begin > y_end || (y_begin & 3) || (y_end & 3) || (pass_mask & ~3))
     return XVCB200_INVALID_ARGUMENT;
@@ -1216,7 +1222,7 @@ int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_of
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) p.ref_poc[l][i] = ref_poc[l][i];
   c->check(launch_deblock(c->stream, c->d_cus, c->n_cus, p, pic3(c, rec_slot), c->d_cu_map, c->d_edge_bs[0], c->d_edge_bs[1],
-                          c->map_w, c->map_h, pass_mask, y_begin, y_end), "deblock");
+                          c->map_w, c->map_h, pass_mask, y_begin, y_end, map_ready), "deblock");
   return c->status;
 }
 
@@ -1270,6 +1276,14 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   int stage = 0;
   auto mark = [&]() { if (c->ex.profile) cudaEventRecord(c->ex.ev[stage], c->stream); stage++; };
   mark();   // 0: start
+  // the deblocking stage's CU map depends on the CU geometry only: built on a side stream behind the
+  // search (the T/Q stage's join over all side streams orders it before the deblocking kernels)
+  const bool map_ahead = prm->deblock && c->ex.n_side >= 3;
+  if (map_ahead) {
+    cudaEventRecord(c->ex.fork_ev, c->stream);
+    cudaStreamWaitEvent(c->ex.side[2], c->ex.fork_ev, 0);
+    c->check(launch_cu_map(c->ex.side[2], c->d_cus, n, c->d_cu_map, c->map_w, c->map_h), "cu_map");
+  }
   c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
   mark();   // 1: jobs built
   {
@@ -1279,7 +1293,7 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
                               c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_pipe_index[nl - 1],
                               c->ex.d_pipe_groups[nl - 1], c->ex.pipe_n_groups[nl - 1], c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
                               c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), slots, n_ref, margin, c->ex.d_pool,
-                              c->ex.pool_cap), "tz_search");
+                              c->ex.pool_cap, c->ex.n_side >= 4 ? c->ex.side[3] : nullptr, c->ex.fork_ev, c->ex.side_ev[3]), "tz_search");
   }
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
@@ -1296,8 +1310,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   if (st != XVCB200_OK) return st;
   mark();   // 5: T/Q/recon done
   if (prm->deblock) {
-    st = xvcb200_deblock_picture_ex(c, prm->rec_slot, prm->pic_type, prm->beta_offset, prm->tc_offset, prm->chroma_offset_table,
-                                    prm->chroma_offset_u, prm->chroma_offset_v, prm->ref_poc);
+    st = deblock_impl(c, prm->rec_slot, prm->pic_type, prm->beta_offset, prm->tc_offset, prm->chroma_offset_table,
+                      prm->chroma_offset_u, prm->chroma_offset_v, prm->ref_poc, 3, 0, c->height, map_ahead);
     if (st != XVCB200_OK) return st;
   }
   mark();   // 6: deblocking done

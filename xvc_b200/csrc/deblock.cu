@@ -205,21 +205,33 @@ __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restri
   }
 }
 
+// CU index of every 4x4 block: depends on the CU geometry only, so the picture pipeline builds it
+// on a side stream while the search runs.
+cudaError_t launch_cu_map(cudaStream_t s, const xvcb200_cu *d_cus, int n, int32_t *d_map, int map_w, int map_h) {
+  if (n <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(d_map, 0xff, sizeof(int32_t) * map_w * map_h, s);
+  if (e != cudaSuccess) return e;
+  g_launch_count++;
+  cu_map_kernel<<<n, 64, 0, s>>>(d_cus, n, d_map, map_w, map_h);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
                            int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h, int pass_mask,
-                           int y_begin, int y_end) {
+                           int y_begin, int y_end, bool map_ready) {
   if (n <= 0) return cudaSuccess;
   const int cells = map_w * map_h;
   const int cy0 = y_begin >> 2, cy1 = y_end >> 2;
   const int band_cells = map_w * (cy1 - cy0);
   if (band_cells <= 0) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(d_map, 0xff, sizeof(int32_t) * cells, s);
-  if (e != cudaSuccess) return e;
+  if (!map_ready) {
+    cudaError_t e = launch_cu_map(s, d_cus, n, d_map, map_w, map_h);
+    if (e != cudaSuccess) return e;
+  }
   DbRefPoc rp;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) rp.poc[l][i] = p.ref_poc[l][i];
-  g_launch_count += 2;
-  cu_map_kernel<<<n, 64, 0, s>>>(d_cus, n, d_map, map_w, map_h);
+  g_launch_count++;
   edge_bs_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, map_w, map_h, p.pic_type, rp, d_bs_v, d_bs_h);
   if (pass_mask & 1) {
     g_launch_count++;
@@ -235,22 +247,42 @@ cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const
 // ---------------------------------------------------------------- PadBorder
 // Every sample outside the picture takes the value of the nearest picture sample (rows are
 // replicated first, then columns over all rows incl. the new ones: corners = corner samples).
-__global__ void pad_border_kernel(PlaneView pl, int pad) {
-  const int fw = pl.width + 2 * pad, fh = pl.height + 2 * pad;
+// One thread per BORDER sample of the three planes (blockIdx.y = plane): the two bands of `pad`
+// rows above / below over the full padded width, then the two side bands of the picture rows.
+struct PadPlanes { PlaneView p[3]; int pad[3]; };
+__global__ void pad_border_kernel(const __grid_constant__ PadPlanes pp) {
+  const PlaneView pl = pp.p[blockIdx.y];
+  const int pad = pp.pad[blockIdx.y];
+  const int fw = pl.width + 2 * pad, band = pad * fw;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= fw * fh) return;
-  const int x = idx % fw - pad, y = idx / fw - pad;
-  if (x >= 0 && x < pl.width && y >= 0 && y < pl.height) return;
+  int x, y;
+  if (idx < 2 * band) {
+    const int i = idx < band ? idx : idx - band;
+    const int r = i / fw;
+    x = i - r * fw - pad;
+    y = idx < band ? r - pad : pl.height + r;
+  } else {
+    const int i = idx - 2 * band;
+    if (i >= 2 * pad * pl.height) return;
+    y = i / (2 * pad);
+    const int c = i - y * 2 * pad;
+    x = c < pad ? c - pad : pl.width + c - pad;
+  }
   const int sx = clip3i(x, 0, pl.width - 1), sy = clip3i(y, 0, pl.height - 1);
   pl.base[y * pl.pitch + x] = pl.base[sy * pl.pitch + sx];
 }
 
 cudaError_t launch_pad_border(cudaStream_t s, Pic3 pic, const int pad[3]) {
+  PadPlanes pp;
+  int most = 0;
   for (int c = 0; c < 3; c++) {
-    const int total = (pic.p[c].width + 2 * pad[c]) * (pic.p[c].height + 2 * pad[c]);
-    g_launch_count++;
-    pad_border_kernel<<<(total + 255) / 256, 256, 0, s>>>(pic.p[c], pad[c]);
+    pp.p[c] = pic.p[c];
+    pp.pad[c] = pad[c];
+    const int total = 2 * pad[c] * (pic.p[c].width + 2 * pad[c]) + 2 * pad[c] * pic.p[c].height;
+    most = total > most ? total : most;
   }
+  g_launch_count++;
+  pad_border_kernel<<<dim3((most + 255) / 256, 3), 256, 0, s>>>(pp);
   return cudaGetLastError();
 }
 

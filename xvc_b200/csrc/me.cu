@@ -960,7 +960,8 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
                              const PlaneView *d_s8_planes, const PlaneView *h_ref_planes, Sample *const *h_s8_base,
-                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap) {
+                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap,
+                             cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev) {
   if (n <= 0 || n_groups <= 0) return cudaSuccess;
   static int smem_bytes = 0, num_sms = 0;
   if (!smem_bytes) {
@@ -976,13 +977,22 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   }
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  // 8-sample segment sums of the reference pictures this launch searches
+  // 8-sample segment sums of the reference pictures this launch searches (two pictures: side by side)
+  const bool fork = side != nullptr && n_ref_slots == 2;
+  if (fork) {
+    cudaEventRecord(fork_ev, s);
+    cudaStreamWaitEvent(side, fork_ev, 0);
+  }
   for (int i = 0; i < n_ref_slots; i++) {
     const PlaneView rv = h_ref_planes[ref_slots[i]];
     const int x0 = -margin[0], x1 = rv.width + margin[0] - 8, y0 = -margin[1], y1 = rv.height + margin[1];
     dim3 grid(((x1 - x0 + 7) / 8 + 127) / 128, y1 - y0);
     g_launch_count++;
-    segment_sum_kernel<<<grid, 128, 0, s>>>(rv, h_s8_base[ref_slots[i]], x0, x1, y0, y1);
+    segment_sum_kernel<<<grid, 128, 0, (fork && i == 1) ? side : s>>>(rv, h_s8_base[ref_slots[i]], x0, x1, y0, y1);
+  }
+  if (fork) {
+    cudaEventRecord(join_ev, side);
+    cudaStreamWaitEvent(s, join_ev, 0);
   }
   static unsigned long long *prof = nullptr;
   static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;

@@ -118,7 +118,8 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
                              const PlaneView *d_s8_planes, const PlaneView *h_ref_planes, Sample *const *h_s8_base,
-                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap);
+                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap,
+                             cudaStream_t side = nullptr, cudaEvent_t fork_ev = nullptr, cudaEvent_t join_ev = nullptr);
 // subpel.cu
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
@@ -148,7 +149,8 @@ struct DeblockParams {
 };
 cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
                            int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h, int pass_mask,
-                           int y_begin, int y_end);
+                           int y_begin, int y_end, bool map_ready = false);
+cudaError_t launch_cu_map(cudaStream_t s, const xvcb200_cu *d_cus, int n, int32_t *d_map, int map_w, int map_h);
 
 }  // namespace xvcb
 
