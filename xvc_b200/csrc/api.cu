@@ -957,13 +957,21 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   memcpy(hc, cus, sizeof(xvcb200_cu) * (size_t)n);
   c->ex.h_cus.assign(cus, cus + n);
   for (int i = 0; i < n; i++) { idx1[i] = by_ctu[(size_t)i]; idx2[i] = 2 * by_ctu[(size_t)i]; idx2[n + i] = 2 * by_ctu[(size_t)i] + 1; }
-  for (int t = 0, g = 0; t < n_ctus; t++) {
+  // Groups are handed to the persistent search CTAs in this order: longest first (cost grows with
+  // the number of jobs), so that the groups still running when the counter runs out are the short ones.
+  std::vector<int> ctu_order;
+  ctu_order.reserve((size_t)n_groups);
+  for (int t = 0; t < n_ctus; t++)
+    if (ctu_first[(size_t)t + 1] > ctu_first[(size_t)t]) ctu_order.push_back(t);
+  std::stable_sort(ctu_order.begin(), ctu_order.end(), [&](int a, int b) {
+    return ctu_first[(size_t)a + 1] - ctu_first[(size_t)a] > ctu_first[(size_t)b + 1] - ctu_first[(size_t)b];
+  });
+  for (int g = 0; g < n_groups; g++) {
+    const int t = ctu_order[(size_t)g];
     const int first = ctu_first[(size_t)t], cnt = ctu_first[(size_t)t + 1] - first;
-    if (cnt == 0) continue;
     grp1[2 * g] = first; grp1[2 * g + 1] = cnt;
-    grp2[2 * g] = first; grp2[2 * g + 1] = cnt;
-    grp2[2 * (n_groups + g)] = n + first; grp2[2 * (n_groups + g) + 1] = cnt;
-    g++;
+    grp2[4 * g] = first; grp2[4 * g + 1] = cnt;                 // list 0 ...
+    grp2[4 * g + 2] = n + first; grp2[4 * g + 3] = cnt;         // ... and list 1 of the same CTU
   }
   c->ex.pipe_n_groups[0] = n_groups; c->ex.pipe_n_groups[1] = 2 * n_groups;
   auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
@@ -1034,6 +1042,12 @@ static int upload_tz_groups(CtxFull *c, int n_jobs, KeyOf key_of) {
     groups.back()++;
   }
   const int n_groups = (int)groups.size() / 2;
+  {   // longest groups first (see set_cus)
+    std::vector<std::pair<int, int>> g2((size_t)n_groups);
+    for (int g = 0; g < n_groups; g++) g2[(size_t)g] = std::make_pair(groups[2 * (size_t)g], groups[2 * (size_t)g + 1]);
+    std::stable_sort(g2.begin(), g2.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
+    for (int g = 0; g < n_groups; g++) { groups[2 * (size_t)g] = g2[(size_t)g].first; groups[2 * (size_t)g + 1] = g2[(size_t)g].second; }
+  }
   if (!ensure(c, &c->ex.d_job_index, &c->ex.job_index_cap, n_jobs) || !ensure(c, &c->ex.d_groups, &c->ex.groups_cap, 2 * n_groups))
     return -1;
   if (!ensure_tz_scratch(c, n_jobs)) return -1;
