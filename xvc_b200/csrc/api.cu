@@ -1024,7 +1024,7 @@ static bool ensure_tz_scratch(CtxFull *c, int n_jobs) {
   if (!ensure(c, &c->ex.d_tz_states, &st_cap_elems, (int)(n_jobs * xvcb::tz_state_bytes()))) return false;
   c->ex.tz_states_cap = st_cap_elems;
   if (!c->ex.d_counter && !c->check(cudaMalloc(&c->ex.d_counter, sizeof(int)), "cudaMalloc(counter)")) return false;
-  if (!ensure(c, &c->ex.d_subpel_lists, &c->ex.subpel_lists_cap, 11 * n_jobs + 16)) return false;
+  if (!ensure(c, &c->ex.d_subpel_lists, &c->ex.subpel_lists_cap, 15 * n_jobs + 32)) return false;
   return true;
 }
 

@@ -95,12 +95,16 @@ __global__ void __launch_bounds__(128) subpel_generic_kernel(const xvcb200_cu *_
 }
 
 // ---------------------------------------------------------------- job classes
-// lists: 11 segments of n ints + counts[11].  Segment 0: blocks of <= 1024 samples (CTA of 128),
-// 1: larger (CTA of 256), 2: generic kernel, 3..9: blocks of <= 256 samples (one warp each) by
-// shape -- the warp teams walk these seven lists as one, so that the four warps of a CTA (and
-// neighbouring CTAs) work on the same shape and run the same instructions at about the same
-// time: the kernel is instruction-fetch bound when every warp is somewhere else in the code.
-constexpr int kSubpelLists = 11;
+// lists: 15 segments of n ints + counts[16].  The classify kernel fills, by block area / shape:
+//   0: 1024 samples   1: 4096   2: generic kernel   3..9: blocks of <= 256 samples by shape
+//   11: 2048 samples  12: 512
+// and the concat kernel builds the three lists the team kernels walk:
+//   10 = 3..9 (one warp per job; shapes adjacent, so that the four warps of a CTA and neighbouring
+//        CTAs run the same instructions at about the same time: the kernel is instruction-fetch
+//        bound when every warp is somewhere else in the code)
+//   13 = 1, 11 (CTA of 256)   14 = 0, 12 (CTA of 128) -- larger blocks first: jobs are fetched
+//        one at a time, so the short ones fill the tail.
+constexpr int kSubpelLists = 15;
 __global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
                                        int *__restrict__ lists, int *__restrict__ counts) {
   const int ji = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,25 +113,34 @@ __global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const
   const int area = (int)cu.w * cu.h;
   int seg;
   if (cu.w < 8 || cu.h < 8) seg = 2;
-  else if (area > 1024) seg = 1;
-  else if (area > 256) seg = 0;
+  else if (area > 256) seg = area == 4096 ? 1 : (area == 2048 ? 11 : (area == 1024 ? 0 : 12));
   else seg = 3 + (28 - __clz((int)cu.w)) * 3 + (28 - __clz((int)cu.h));     // (log2 w - 3) * 3 + (log2 h - 3): 0,1,2,3,4,6
   lists[(size_t)seg * n + atomicAdd(&counts[seg], 1)] = ji;
 }
 
-// The seven shape lists of the small blocks -> one list (segment 10), its length -> counts[10].
 __global__ void subpel_concat_kernel(int n, int *__restrict__ lists, int *__restrict__ counts) {
-  int end[7], total = 0;
-#pragma unroll
-  for (int q = 0; q < 7; q++) { total += counts[3 + q]; end[q] = total; }
   const int li = blockIdx.x * blockDim.x + threadIdx.x;
-  if (li == 0) counts[10] = total;
-  if (li >= total) return;
-  int q = 0, first = 0;
+  {   // the seven shape lists of the small blocks -> list 10
+    int end[7], total = 0;
 #pragma unroll
-  for (int t = 0; t < 6; t++)
-    if (li >= end[t]) { q = t + 1; first = end[t]; }
-  lists[(size_t)10 * n + li] = lists[(size_t)(3 + q) * n + (li - first)];
+    for (int q = 0; q < 7; q++) { total += counts[3 + q]; end[q] = total; }
+    if (li == 0) counts[10] = total;
+    if (li < total) {
+      int q = 0, first = 0;
+#pragma unroll
+      for (int t = 0; t < 6; t++)
+        if (li >= end[t]) { q = t + 1; first = end[t]; }
+      lists[(size_t)10 * n + li] = lists[(size_t)(3 + q) * n + (li - first)];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 2; o++) {   // 4096 then 2048 -> list 13; 1024 then 512 -> list 14
+    const int a = o == 0 ? 1 : 0, b = o == 0 ? 11 : 12, out = 13 + o;
+    const int na = counts[a], nb = counts[b];
+    if (li == 0) counts[out] = na + nb;
+    if (li < na) lists[(size_t)out * n + li] = lists[(size_t)a * n + li];
+    else if (li < na + nb) lists[(size_t)out * n + li] = lists[(size_t)b * n + (li - na)];
+  }
 }
 
 // shared memory of one team (bytes): reference window, horizontal plane, prediction plane, original.
@@ -254,22 +267,34 @@ __device__ __forceinline__ void satd_candidates(const Sample *org, int op, const
 template <int T>
 __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_team_kernel(
     const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, const int *__restrict__ list,
-    const int *__restrict__ count, int *__restrict__ slow_list, int *__restrict__ slow_count, int team_bytes, int bitdepth,
+    const int *__restrict__ count, int *__restrict__ fetch, int *__restrict__ slow_list, int *__restrict__ slow_count,
+    int team_bytes, int bitdepth,
     uint32_t lambda, PlaneView orig, const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res) {
   extern __shared__ __align__(16) unsigned char subpel_smem[];
   __shared__ unsigned s_part[T == 32 ? 4 : (T / 32) * 4];
   __shared__ unsigned s_sd[T == 32 ? 4 : 1][20];
   unsigned *sd = s_sd[T == 32 ? (threadIdx.x >> 5) : 0];
   const int tid = T == 32 ? (threadIdx.x & 31) : threadIdx.x;
-  const int teams = T == 32 ? gridDim.x * 4 : gridDim.x;
-  const int team0 = T == 32 ? blockIdx.x * 4 + (threadIdx.x >> 5) : blockIdx.x;
+  __shared__ int s_li;
   unsigned char *base = subpel_smem + (T == 32 ? (threadIdx.x >> 5) * team_bytes : 0);
   const int n_list = *count;
   const int maxv = (1 << bitdepth) - 1;
   int sh1, off1, sh2, off2;
   filter_shift_offset(false, false, bitdepth, sh1, off1);     // horizontal stage of the 2-D filter
   filter_shift_offset(true, true, bitdepth, sh2, off2);       // vertical stage on the intermediate
-  for (int li = team0; li < n_list; li += teams) {
+  for (;;) {
+    // jobs are taken one at a time from the class list (a static stride leaves 2 vs 3 jobs per team)
+    int li = 0;
+    if (T == 32) {
+      if (tid == 0) li = atomicAdd(fetch, 1);
+      li = __shfl_sync(XVCB_FULL, li, 0);
+    } else {
+      if (tid == 0) s_li = atomicAdd(fetch, 1);
+      __syncthreads();
+      li = s_li;
+      __syncthreads();
+    }
+    if (li >= n_list) break;
     const int ji = list[li];
     const xvcb200_me_job job = jobs[ji];
     const xvcb200_cu cu = cus[job.cu];
@@ -492,7 +517,7 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
     if (occ2 < 1) occ2 = 1;
   }
   int *counts = d_lists + kSubpelLists * (size_t)n;
-  cudaError_t e = cudaMemsetAsync(counts, 0, kSubpelLists * sizeof(int), s);
+  cudaError_t e = cudaMemsetAsync(counts, 0, 20 * sizeof(int), s);      // list lengths [0..14] + the three fetch counters [16..18]
   if (e != cudaSuccess) return e;
   g_launch_count += 6;
   subpel_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, d_jobs, n, d_lists, counts);
@@ -510,11 +535,11 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
     cudaStreamWaitEvent(s2, fork_ev, 0);
   }
   // persistent grids: as many CTAs as fit, each strides over its class list (largest blocks first)
-  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + (size_t)n, counts + 1, slow, counts + 2,
+  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + 13 * (size_t)n, counts + 13, counts + 16, slow, counts + 2,
                                                          bytes2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s1>>>(d_cus, d_jobs, d_lists, counts, slow, counts + 2, bytes1, bitdepth,
+  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s1>>>(d_cus, d_jobs, d_lists + 14 * (size_t)n, counts + 14, counts + 17, slow, counts + 2, bytes1, bitdepth,
                                                            lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s2>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, slow,
+  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s2>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, counts + 18, slow,
                                                               counts + 2, bytes0, bitdepth, lambda_me, orig, d_ref_planes, d_res);
   if (fork) {
     cudaEventRecord(side_ev[0], s1);

@@ -123,7 +123,7 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
 // subpel.cu
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
-                                 xvcb200_me_result *d_res, int *d_lists /* 11n + 16 ints of scratch */,
+                                 xvcb200_me_result *d_res, int *d_lists /* 15n + 32 ints of scratch */,
                                  cudaStream_t *side, cudaEvent_t *side_ev, int n_side, cudaEvent_t fork_ev);
 cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_fullsearch_job *d_jobs, int n,
                                int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_planes,
