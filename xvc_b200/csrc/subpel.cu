@@ -123,14 +123,14 @@ __global__ void subpel_concat_kernel(int n, int *__restrict__ lists, int *__rest
   {   // the seven shape lists of the small blocks -> list 10
     int end[7], total = 0;
 #pragma unroll
-    for (int q = 0; q < 7; q++) { total += counts[3 + q]; end[q] = total; }
+    for (int q = 0; q < 7; q++) { total += counts[9 - q]; end[q] = total; }      // 32x8 / 16x16 ... first, 8x8 last
     if (li == 0) counts[10] = total;
     if (li < total) {
       int q = 0, first = 0;
 #pragma unroll
       for (int t = 0; t < 6; t++)
         if (li >= end[t]) { q = t + 1; first = end[t]; }
-      lists[(size_t)10 * n + li] = lists[(size_t)(3 + q) * n + (li - first)];
+      lists[(size_t)10 * n + li] = lists[(size_t)(9 - q) * n + (li - first)];
     }
   }
 #pragma unroll
