@@ -63,7 +63,7 @@ def launches(tag, path, cmd):
     total = sum(sum(v) for v in per.values())
     shutil.copy(path, os.path.join(PROF, tag + "_launches.csv"))
     with open(os.path.join(PROF, tag + "_launches_summary.md"), "w") as f:
-        f.write("# Launch list, %s\n\n`%s`\n(per-launch times under ncu are serialised and cold-cache -- shares, not absolutes; the T/Q kernels overlap on 16 side streams and the three sub-pel classes on 3 streams in the real step).\n\n" % (tag, cmd))
+        f.write("# Launch list, %s\n\n`%s`\n(per-launch times under ncu are serialised and cold-cache -- shares, not absolutes; the T/Q kernels overlap on one side stream per shape class and the three sub-pel classes on 3 streams in the real step).\n\n" % (tag, cmd))
         f.write("| kernel | launches | total us | share | us / launch |\n|---|---|---|---|---|\n")
         for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write("| `%s` | %d | %.1f | %.1f %% | %.1f |\n" % (k, len(v), sum(v), 100 * sum(v) / total, sum(v) / len(v)))

@@ -430,7 +430,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   uint32_t *d_pool = nullptr;
   int pool_cap = 1 << 16, pool_ctas = 0;
   // side streams for independent launches inside one stage (T/Q shape classes)
-  static constexpr int kSide = 16;
+  static constexpr int kSide = 36;
   cudaStream_t side[kSide] = {nullptr};
   cudaEvent_t side_ev[kSide] = {nullptr};
   cudaEvent_t fork_ev = nullptr;
