@@ -424,9 +424,6 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int cur_blob = -1;
   // successive-elimination support: 8-sample segment sums of every slot's luma plane, survivor pool
   std::vector<PlaneView> h_luma_views;
-  std::vector<Sample *> h_s8_base;
-  uint8_t *d_s8_arena = nullptr;
-  PlaneView *d_s8_views = nullptr;
   uint32_t *d_pool = nullptr;
   int pool_cap = 1 << 16, pool_ctas = 0;
   // side streams for independent launches inside one stage (T/Q shape classes)
@@ -534,23 +531,7 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
       c->ex.n_side = i + 1;
     }
   }
-  {   // 8-sample segment sums of every slot's luma plane (same geometry as the plane itself)
-    std::vector<PlaneView> s8v(num_slots);
-    c->ex.h_luma_views = views;
-    c->ex.h_s8_base.resize(num_slots);
-    if (!c->check(cudaMalloc(&c->ex.d_s8_arena, plane_bytes[0] * num_slots), "cudaMalloc(s8)") ||
-        !c->check(cudaMalloc(&c->ex.d_s8_views, sizeof(PlaneView) * num_slots), "cudaMalloc(s8 views)")) {
-      int st = c->status; xvcb200_ctx_destroy(c); return st;
-    }
-    for (int s = 0; s < num_slots; s++) {
-      s8v[s] = views[s];
-      s8v[s].base = reinterpret_cast<Sample *>(c->ex.d_s8_arena + (size_t)s * plane_bytes[0]) +
-                    (size_t)c->geom.margin_y[0] * c->geom.pitch[0] + c->geom.margin_x[0];
-      c->ex.h_s8_base[s] = s8v[s].base;
-    }
-    cudaMemcpyAsync(c->ex.d_s8_views, s8v.data(), sizeof(PlaneView) * num_slots, cudaMemcpyHostToDevice, c->stream);
-    cudaStreamSynchronize(c->stream);
-  }
+  c->ex.h_luma_views = views;
   c->map_w = width >> 2; c->map_h = height >> 2;
   const size_t cells = (size_t)c->map_w * c->map_h;
   if (!c->check(cudaMalloc(&c->ex.d_luma_views, sizeof(PlaneView) * num_slots), "cudaMalloc(views)") ||
@@ -589,7 +570,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   for (int i = 0; i < CtxExtra::kUpRing; i++) { cudaFree(c->ex.d_up_ring[i]); if (c->ex.up_ring_ev[i]) cudaEventDestroy(c->ex.up_ring_ev[i]); }
   for (int i = 0; i < CtxExtra::kDownRing; i++) { cudaFree(c->ex.d_down_ring[i]); if (c->ex.down_ring_ev[i]) cudaEventDestroy(c->ex.down_ring_ev[i]); }
   for (cudaEvent_t e : c->ex.dl_ev) if (e) cudaEventDestroy(e);
-  cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_s8_arena); cudaFree(c->ex.d_s8_views); cudaFree(c->ex.d_pool);
+  cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
@@ -1082,15 +1063,9 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
     return ((long long)jobs[i].ref_slot << 40) | ((long long)jobs[i].search_range << 28) | (long long)((u.y >> 6) * ctus_x + (u.x >> 6));
   });
   if (n_groups < 0) return c->status;
-  std::vector<int> ref_list;
-  for (int i = 0; i < n; i++)
-    if (std::find(ref_list.begin(), ref_list.end(), jobs[i].ref_slot) == ref_list.end()) ref_list.push_back(jobs[i].ref_slot);
-  const int margin[2] = {c->geom.margin_x[0], c->geom.margin_y[0]};
   c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
                             c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_job_index, c->ex.d_groups,
-                            n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
-                            c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), ref_list.data(), (int)ref_list.size(), margin,
-                            c->ex.d_pool, c->ex.pool_cap), "tz_search");
+                            n_groups, c->ex.d_tz_states, c->ex.d_counter, c->ex.d_pool, c->ex.pool_cap), "tz_search");
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n, c->bitdepth, lambda_me_of(lambda_sqrt),
                                 c->plane(orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev,
                                 c->ex.n_side, c->ex.fork_ev), "subpel_search");
@@ -1301,13 +1276,10 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
   mark();   // 1: jobs built
   {
-    const int margin[2] = {c->geom.margin_x[0], c->geom.margin_y[0]};
-    const int n_ref = (nl == 2 && slots[1] != slots[0]) ? 2 : 1;
     c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
                               c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_pipe_index[nl - 1],
-                              c->ex.d_pipe_groups[nl - 1], c->ex.pipe_n_groups[nl - 1], c->ex.d_tz_states, c->ex.d_counter, c->ex.d_s8_views,
-                              c->ex.h_luma_views.data(), c->ex.h_s8_base.data(), slots, n_ref, margin, c->ex.d_pool,
-                              c->ex.pool_cap, c->ex.n_side >= 4 ? c->ex.side[3] : nullptr, c->ex.fork_ev, c->ex.side_ev[3]), "tz_search");
+                              c->ex.d_pipe_groups[nl - 1], c->ex.pipe_n_groups[nl - 1], c->ex.d_tz_states, c->ex.d_counter,
+                              c->ex.d_pool, c->ex.pool_cap), "tz_search");
   }
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),

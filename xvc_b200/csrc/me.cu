@@ -330,26 +330,6 @@ __device__ __forceinline__ MeGeom me_geom(const xvcb200_cu &cu, int bitdepth, ui
   return g;
 }
 
-// S8[y][x] = sum of the 8 reference samples x..x+7 of row y, for every position of the padded
-// plane: the segment sums of the successive-elimination bound below.  <= 8 * 4095: fits uint16.
-__global__ void segment_sum_kernel(PlaneView src, Sample *__restrict__ dst00, int x_begin, int x_end, int y_begin,
-                                   int y_end) {
-  const int x = x_begin + (blockIdx.x * blockDim.x + threadIdx.x) * 8;   // 8 outputs per thread, sliding window
-  const int y = y_begin + blockIdx.y;
-  if (x >= x_end || y >= y_end) return;
-  const Sample *p = src.base + y * src.pitch + x;
-  Sample *d = dst00 + y * src.pitch + x;
-  int win = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) win += p[i];
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    if (x + i < x_end) d[i] = (Sample)win;
-    win += (int)p[i + 8] - (int)p[i];
-  }
-}
-
-// stages the box [rx0, rx0 + 8*cpr) x [ry0, ry0 + bh) of a plane into shared memory rows of `spw` words
 constexpr int kStageDepth = 4;
 __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int rx0, int ry0, int bh, int cpr, int spw,
                                           uint32_t *s_region, int tid, int nthreads) {
@@ -377,6 +357,49 @@ __device__ __forceinline__ void stage_box(const Sample *plane00, int pitch, int 
         if (left > 2) d[2] = v[u].z;
         if (left > 3) d[3] = v[u].w;
       }
+    }
+  }
+}
+
+// The staged sample box <-> its 8-sample segment sums, IN PLACE, a row per thread.  Forward:
+// word i of a row (samples 2i, 2i+1) becomes (S8[2i], S8[2i+1]), S8[x] = s[x] + ... + s[x+7], by a
+// sliding window over a four-word delay line; the last four words of the row stay raw samples
+// (no candidate reads S8 there: x <= box width - 8).  Inverse, right to left:
+// s[x] = S8[x] - S8[x+1] + s[x+8], the eight samples to the right being already restored (or
+// the raw tail).  All arithmetic mod 2^16, so the round trip is exact whatever the tail holds.
+// Replaces a second copy of every reference plane (its segment sums) and two stagings per group.
+__device__ __forceinline__ void box_to_s8(uint32_t *s_region, int spw, int bh, int tid, int nthreads) {
+  const int nconv = spw - 4;
+  for (int r = tid; r < bh; r += nthreads) {
+    uint32_t *row = s_region + r * spw;
+    uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
+    uint32_t S = (w0 & 0xffffu) + (w0 >> 16) + (w1 & 0xffffu) + (w1 >> 16) + (w2 & 0xffffu) + (w2 >> 16) + (w3 & 0xffffu) + (w3 >> 16);
+#pragma unroll 4
+    for (int i = 0; i < nconv; i++) {
+      const uint32_t w4 = row[i + 4];
+      const uint32_t S1 = S - (w0 & 0xffffu) + (w4 & 0xffffu);
+      row[i] = (S & 0xffffu) | (S1 << 16);
+      S = S1 - (w0 >> 16) + (w4 >> 16);
+      w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+    }
+  }
+}
+__device__ __forceinline__ void s8_to_box(uint32_t *s_region, int spw, int bh, int tid, int nthreads) {
+  const int nconv = spw - 4;
+  for (int r = tid; r < bh; r += nthreads) {
+    uint32_t *row = s_region + r * spw;
+    uint32_t w1 = row[nconv], w2 = row[nconv + 1], w3 = row[nconv + 2], w4 = row[nconv + 3];
+    uint32_t Snext = (w1 & 0xffffu) + (w1 >> 16) + (w2 & 0xffffu) + (w2 >> 16) + (w3 & 0xffffu) + (w3 >> 16) + (w4 & 0xffffu) + (w4 >> 16);
+#pragma unroll 4
+    for (int i = nconv - 1; i >= 0; i--) {
+      const uint32_t v = row[i];
+      const uint32_t a = v & 0xffffu, b = v >> 16;
+      const uint32_t hi = (b - Snext + (w4 >> 16)) & 0xffffu;
+      const uint32_t lo = (a - b + (w4 & 0xffffu)) & 0xffffu;
+      const uint32_t w0 = lo | (hi << 16);
+      row[i] = w0;
+      Snext = a;
+      w4 = w3; w3 = w2; w2 = w1; w1 = w0;
     }
   }
 }
@@ -472,7 +495,7 @@ __global__ void __launch_bounds__(kTzThreads, 1)
 tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
                  const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
                  int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
-                 const PlaneView *__restrict__ ref_planes, const PlaneView *__restrict__ s8_planes,
+                 const PlaneView *__restrict__ ref_planes,
                  xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states, int region_budget_words,
                  uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -505,7 +528,6 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     const TzGroup G = groups[grp];
     const int ref_slot = jobs[job_index[G.first]].ref_slot;
     const PlaneView ref = ref_planes[ref_slot];
-    const PlaneView s8 = s8_planes[ref_slot];
 
     for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
       const int kn = min(kMaxGroupJobs, G.count - k0);
@@ -573,8 +595,8 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         if (ph == 1) {
           if (s_any_raster) {
             // ---------------- raster pass 1: segment-sum bound, survivors -> pool
-            if (staged && s8.base != nullptr) {
-              stage_box(s8.base, s8.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+            if (staged) {
+              box_to_s8(s_region, spw, bh, tid, kTzThreads);
               __syncthreads();
               lap(3);
               const uint16_t *s8reg = reinterpret_cast<const uint16_t *>(s_region);
@@ -692,7 +714,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
                 kb = ke;
               }
               lap(4);
-              stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+              s8_to_box(s_region, spw, bh, tid, kTzThreads);
               __syncthreads();
               lap(5);
             }
@@ -959,9 +981,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
-                             const PlaneView *d_s8_planes, const PlaneView *h_ref_planes, Sample *const *h_s8_base,
-                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap,
-                             cudaStream_t side, cudaEvent_t fork_ev, cudaEvent_t join_ev) {
+                             uint32_t *d_pool, int pool_cap) {
   if (n <= 0 || n_groups <= 0) return cudaSuccess;
   static int smem_bytes = 0, num_sms = 0;
   if (!smem_bytes) {
@@ -977,23 +997,6 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   }
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  // 8-sample segment sums of the reference pictures this launch searches (two pictures: side by side)
-  const bool fork = side != nullptr && n_ref_slots == 2;
-  if (fork) {
-    cudaEventRecord(fork_ev, s);
-    cudaStreamWaitEvent(side, fork_ev, 0);
-  }
-  for (int i = 0; i < n_ref_slots; i++) {
-    const PlaneView rv = h_ref_planes[ref_slots[i]];
-    const int x0 = -margin[0], x1 = rv.width + margin[0] - 8, y0 = -margin[1], y1 = rv.height + margin[1];
-    dim3 grid(((x1 - x0 + 7) / 8 + 127) / 128, y1 - y0);
-    g_launch_count++;
-    segment_sum_kernel<<<grid, 128, 0, (fork && i == 1) ? side : s>>>(rv, h_s8_base[ref_slots[i]], x0, x1, y0, y1);
-  }
-  if (fork) {
-    cudaEventRecord(join_ev, side);
-    cudaStreamWaitEvent(s, join_ev, 0);
-  }
   static unsigned long long *prof = nullptr;
   static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
   if (want_prof && !prof) cudaMallocManaged(&prof, 24 * sizeof(*prof));
@@ -1003,7 +1006,7 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   g_launch_count++;
   tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
       d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
-      d_ref_planes, d_s8_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
+      d_ref_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
       want_prof ? prof : nullptr);
   if (want_prof) {
     cudaStreamSynchronize(s);

@@ -117,9 +117,7 @@ struct TqParams {
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
-                             const PlaneView *d_s8_planes, const PlaneView *h_ref_planes, Sample *const *h_s8_base,
-                             const int *ref_slots, int n_ref_slots, const int margin[2], uint32_t *d_pool, int pool_cap,
-                             cudaStream_t side = nullptr, cudaEvent_t fork_ev = nullptr, cudaEvent_t join_ev = nullptr);
+                             uint32_t *d_pool, int pool_cap);
 // subpel.cu
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
