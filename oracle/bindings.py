@@ -302,6 +302,15 @@ class Ref:
         L.xref_session_create.restype = c_void_p
         L.xref_session_create.argtypes = [c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_i64, c_int, c_int, c_int, c_int]
         L.xref_intra_scan.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.xref_conf_create.restype = c_void_p
+        L.xref_conf_create.argtypes = [c_int, c_int, c_int, c_int]
+        L.xref_conf_destroy.argtypes = [c_void_p]
+        L.xref_conf_push_picture.argtypes = [c_void_p, c_void_p]
+        L.xref_conf_flush.argtypes = [c_void_p]
+        L.xref_conf_inter_inputs.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.xref_conf_write_inter.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+        L.xref_conf_bitstream.restype = ctypes.c_size_t
+        L.xref_conf_bitstream.argtypes = [c_void_p, c_void_p, ctypes.c_size_t]
         L.xref_qp_info.argtypes = [c_int, c_int, c_double, c_int, c_int, c_int, c_void_p]
         L.xref_sad.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ssize, c_void_p, c_ssize]
         L.xref_ssd.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_ssize, c_void_p, c_ssize]
@@ -395,6 +404,60 @@ class Ref:
 
     def session(self, *args, **kw):
         return RefSession(self, *args, **kw)
+
+
+class RefConformance:
+    """A two-picture xvc bitstream (key picture by the reference encoder, inter picture written by the
+    reference's CuWriter from OUTSIDE decisions) for the reference decoder to verify; see
+    ref_shim.cc 'bitstream conformance'."""
+
+    def __init__(self, ref, width, height, bitdepth=10, qp=32):
+        self.L = ref.L
+        self.width, self.height, self.bitdepth = width, height, bitdepth
+        self.shapes = [(height, width), (height // 2, width // 2), (height // 2, width // 2)]
+        self.h = self.L.xref_conf_create(width, height, bitdepth, qp)
+        if not self.h:
+            raise RuntimeError("xref_conf_create failed")
+
+    def close(self):
+        if self.h:
+            self.L.xref_conf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def push(self, planes):
+        planes = [np.ascontiguousarray(p, dtype=np.uint16) for p in planes]
+        return self.L.xref_conf_push_picture(self.h, abi.plane_ptr_array(planes))
+
+    def flush(self):
+        return self.L.xref_conf_flush(self.h)
+
+    def inter_inputs(self, poc, ref_poc):
+        orig = [np.zeros(s, dtype=np.uint16) for s in self.shapes]
+        rec = [np.zeros(s, dtype=np.uint16) for s in self.shapes]
+        info = np.zeros(8, dtype=np.int32)
+        lam = ctypes.c_double(0)
+        if self.L.xref_conf_inter_inputs(self.h, poc, ref_poc, abi.plane_ptr_array(orig), abi.plane_ptr_array(rec), abi.ptr(info),
+                                         ctypes.byref(lam)) != 0:
+            raise RuntimeError("picture not found")
+        keys = ("qp", "chroma_table", "off_u", "off_v", "deblock", "beta_offset", "tc_offset", "pic_type")
+        return orig, rec, dict(zip(keys, [int(v) for v in info]), lam=lam.value)
+
+    def write_inter(self, poc, cus, splits, levels, rec):
+        cus = np.ascontiguousarray(cus, dtype=abi.cu_dtype)
+        splits = np.ascontiguousarray(splits, dtype=np.uint8)
+        levels = [np.ascontiguousarray(p, dtype=np.int16) for p in levels]
+        rec = [np.ascontiguousarray(p, dtype=np.uint16) for p in rec]
+        return self.L.xref_conf_write_inter(self.h, poc, abi.ptr(cus), len(cus), abi.ptr(splits), len(splits),
+                                            abi.plane_ptr_array(levels), abi.plane_ptr_array(rec))
+
+    def bitstream(self):
+        n = self.L.xref_conf_bitstream(self.h, None, 0)
+        buf = np.zeros(n, dtype=np.uint8)
+        self.L.xref_conf_bitstream(self.h, abi.ptr(buf), n)
+        return buf.tobytes()
 
 
 class RefSession:

@@ -11,6 +11,8 @@
 #include <cassert>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -35,7 +37,13 @@
 #include "xvc_common_lib/transform.h"
 #include "xvc_common_lib/transform_data.h"
 #include "xvc_common_lib/yuv_pic.h"
+#include "xvc_enc_lib/cu_writer.h"
+#include "xvc_enc_lib/encoder.h"
 #include "xvc_enc_lib/encoder_settings.h"
+#include "xvc_enc_lib/picture_encoder.h"
+#include "xvc_enc_lib/syntax_writer.h"
+#include "xvc_enc_lib/xvcenc.h"
+#include "xvc_common_lib/reference_list_sorter.h"
 #include "xvc_enc_lib/encoder_simd_functions.h"
 #include "xvc_enc_lib/inter_search.h"
 #include "xvc_enc_lib/inter_tz_search.h"
@@ -770,6 +778,270 @@ void xref_intra_scan(xref_session *s, const xvcb200_cu *cus, int n, int comp_i, 
     s->pic_data->MarkUsedInPic(cu);
     s->cus.push_back(cu);
   }
+}
+
+// ---------------------------------------------------------------- bitstream conformance
+// A real xvc bitstream whose inter picture carries decisions and levels made OUTSIDE the reference
+// (by the GPU path): the reference encoder (public API, low delay, one reference) codes the key
+// picture and provides all high-level plumbing; for the inter picture its own CTU loop is
+// replaced by "build the CU tree from the given partition, fill every CU from the given
+// decisions, write it with the reference's CuWriter / SyntaxWriter", and the picture checksum is
+// taken over the reconstruction that was handed in.  The reference DECODER (xvcdec) then
+// verifies that checksum against what it decodes.
+struct xref_conf {
+  const xvc_encoder_api *api = nullptr;
+  xvc_encoder_parameters *params = nullptr;
+  xvc_encoder *handle = nullptr;
+  Encoder *enc = nullptr;
+  int width = 0, height = 0, bitdepth = 0;
+  struct Nal { uint32_t type, poc; std::vector<uint8_t> bytes; };
+  std::vector<Nal> nals;
+};
+
+static void ConfCollect(xref_conf *c, xvc_enc_nal_unit *units, int n) {
+  for (int i = 0; i < n; i++) {
+    xref_conf::Nal nal;
+    nal.type = units[i].stats.nal_unit_type;
+    nal.poc = units[i].stats.poc;
+    nal.bytes.assign(units[i].bytes, units[i].bytes + units[i].size);
+    c->nals.push_back(std::move(nal));
+  }
+}
+
+static std::shared_ptr<PictureEncoder> ConfFind(xref_conf *c, int poc) {
+  for (auto &pe : c->enc->pic_encoders_)
+    if (static_cast<int>(pe->GetPoc()) == poc) return pe;
+  return nullptr;
+}
+
+xref_conf *xref_conf_create(int width, int height, int bitdepth, int qp) {
+  xref_conf *c = new xref_conf();
+  c->api = xvc_encoder_api_get();
+  c->params = c->api->parameters_create();
+  c->api->parameters_set_default(c->params);
+  c->params->width = width; c->params->height = height;
+  c->params->chroma_format = XVC_ENC_CHROMA_FORMAT_420;
+  c->params->input_bitdepth = bitdepth; c->params->internal_bitdepth = bitdepth;
+  c->params->framerate = 30;
+  c->params->sub_gop_length = 1; c->params->low_delay = 1; c->params->num_ref_pics = 1;
+  c->params->qp = qp; c->params->threads = 0; c->params->speed_mode = 2;
+  c->params->checksum_mode = 1;               // a checksum for every picture
+  c->handle = c->api->encoder_create(c->params);
+  if (!c->handle) { delete c; return nullptr; }
+  c->enc = reinterpret_cast<Encoder *>(c->handle);
+  // one QP per picture (no delta-QP syntax); set on the object: the API's explicit-settings string goes
+  // through std::stringstream, which is not safe inside a Python process that loaded another libstdc++
+  c->enc->encoder_settings_.adaptive_qp = 0;
+  c->enc->segment_header_->adaptive_qp = 0;
+  c->width = width; c->height = height; c->bitdepth = bitdepth;
+  return c;
+}
+
+void xref_conf_destroy(xref_conf *c) {
+  if (!c) return;
+  if (c->handle) c->api->encoder_destroy(c->handle);
+  if (c->params) c->api->parameters_destroy(c->params);
+  delete c;
+}
+
+// planes: tight 16-bit samples at the internal bit depth (input bit depth == internal bit depth)
+int xref_conf_push_picture(xref_conf *c, const uint16_t *const planes[3]) {
+  std::vector<uint8_t> bytes;
+  for (int p = 0; p < 3; p++) {
+    const size_t n = static_cast<size_t>(p ? c->width / 2 : c->width) * (p ? c->height / 2 : c->height);
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(planes[p]);
+    bytes.insert(bytes.end(), b, b + 2 * n);
+  }
+  xvc_enc_nal_unit *units = nullptr;
+  int n = 0;
+  if (c->api->encoder_encode(c->handle, bytes.data(), &units, &n, nullptr) != XVC_ENC_OK) return -1;
+  ConfCollect(c, units, n);
+  return n;
+}
+
+int xref_conf_flush(xref_conf *c) {
+  xvc_enc_nal_unit *units = nullptr;
+  int n = 0, total = 0;
+  while (c->api->encoder_flush(c->handle, &units, &n, nullptr) == XVC_ENC_OK && n > 0) {
+    ConfCollect(c, units, n);
+    total += n;
+  }
+  return total;
+}
+
+// What the outside encoder needs for picture `poc`: its original and the reconstruction of its
+// (single) reference picture `ref_poc` at the internal bit depth, the picture QP and lambda, the
+// segment's chroma QP mapping and the deblocking parameters.  info: qp, chroma table, offset u,
+// offset v, deblock, beta offset, tc offset, picture type (0 bi, 1 uni).
+int xref_conf_inter_inputs(xref_conf *c, int poc, int ref_poc, uint16_t *const orig[3], uint16_t *const ref_rec[3],
+                           int32_t info[8], double *lambda) {
+  auto pe = ConfFind(c, poc), re = ConfFind(c, ref_poc);
+  if (!pe || !re) return -1;
+  CopyOut(pe->orig_pic_.get(), orig);
+  CopyOut(re->rec_pic_.get(), ref_rec);
+  const Qp &qp = *pe->pic_data_->GetPicQp();
+  const SegmentHeader &seg = *c->enc->segment_header_;
+  info[0] = qp.GetQpRaw(YuvComponent::kY);
+  info[1] = seg.chroma_qp_offset_table; info[2] = seg.chroma_qp_offset_u; info[3] = seg.chroma_qp_offset_v;
+  info[4] = pe->pic_data_->GetDeblock() ? 1 : 0;
+  info[5] = pe->pic_data_->GetBetaOffset(); info[6] = pe->pic_data_->GetTcOffset();
+  info[7] = pe->pic_data_->GetPredictionType() == PicturePredictionType::kBi ? 0 : 1;
+  *lambda = qp.GetLambda();
+  return 0;
+}
+
+namespace {
+struct ConfTreeBuilder {
+  PictureData *pd;
+  InterPrediction *inter;
+  const xvcb200_cu *cus;
+  int n_cus, next_cu = 0;
+  const uint8_t *splits;
+  int n_splits, next_split = 0;
+  const int16_t *const *levels;
+  int width;
+  int pic_qp;
+  bool ok = true;
+
+  void Leaf(CodingUnit *cu) {
+    if (next_cu >= n_cus) { ok = false; return; }
+    const xvcb200_cu &d = cus[next_cu++];
+    if (d.x != cu->GetPosX(YuvComponent::kY) || d.y != cu->GetPosY(YuvComponent::kY) ||
+        d.w != cu->GetWidth(YuvComponent::kY) || d.h != cu->GetHeight(YuvComponent::kY) || d.ref_idx[0] != 0 ||
+        d.ref_idx[1] >= 0) { ok = false; return; }
+    cu->SetQp(pic_qp);
+    cu->SetPredMode(PredictionMode::kInter);
+    cu->SetSkipFlag(false);
+    cu->SetMergeFlag(false);
+    cu->SetInterDir(InterDir::kL0);
+    cu->SetUseAffine(false);
+    cu->SetUseLic(false);
+    cu->SetFullpelMv(false);
+    cu->SetRefIdx(0, RefPicList::kL0);
+    cu->SetRefIdx(-1, RefPicList::kL1);
+    const MotionVector mv(d.mv[0][0], d.mv[0][1]);
+    cu->SetMv(mv, RefPicList::kL0);
+    cu->SetMv(MotionVector(), RefPicList::kL1);
+    // any predictor of the list codes the vector; take the cheaper one like EvalFinalMvpIdx would
+    InterPredictorList mvp = inter->GetMvpList(*cu, RefPicList::kL0, 0);
+    int best = 0;
+    long best_cost = -1;
+    for (int i = 0; i < static_cast<int>(mvp.size()); i++) {
+      const MvDelta dd = mv - mvp[i];
+      const long cost = std::labs(dd.x) + std::labs(dd.y);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = i; }
+    }
+    cu->SetMvpIdx(best, RefPicList::kL0);
+    cu->SetMvDelta(mv - mvp[best], RefPicList::kL0);
+    cu->SetMvDelta(MvDelta(0, 0), RefPicList::kL1);
+    bool any = false;
+    for (int c = 0; c < 3; c++) {
+      const YuvComponent comp = static_cast<YuvComponent>(c);
+      const bool cbf = (d.flags & (XVCB200_CU_CBF_Y << c)) != 0;
+      cu->SetCbf(comp, cbf);
+      cu->SetTransformSkip(comp, false);
+      cu->SetTransformType(comp, TransformType::kDefault, TransformType::kDefault);
+      cu->SetDcCoeffOnly(comp, false);
+      any |= cbf;
+      const int w = cu->GetWidth(comp), h = cu->GetHeight(comp), x = cu->GetPosX(comp), y = cu->GetPosY(comp);
+      const int pw = c ? width / 2 : width;
+      CoeffBuffer cb = cu->GetCoeff(comp);
+      for (int r = 0; r < h; r++)
+        for (int q = 0; q < w; q++) cb.GetDataPtr()[r * cb.GetStride() + q] = cbf ? levels[c][static_cast<size_t>(y + r) * pw + x + q] : 0;
+    }
+    cu->SetRootCbf(any);
+    cu->SetTransformFromSelectIdx(YuvComponent::kY, -1);
+    pd->MarkUsedInPic(cu);
+  }
+
+  void Node(CodingUnit *cu) {
+    if (!ok) return;
+    if (next_split >= n_splits) { ok = false; return; }
+    const int s = splits[next_split++];
+    if (s == 0) { Leaf(cu); return; }
+    // only splits the syntax can signal (CuWriter::WriteSplit)
+    if (s == 1 && !(cu->GetDepth() < pd->GetMaxDepth(CuTree::Primary) && cu->GetBinaryDepth() == 0)) { ok = false; return; }
+    if (s >= 2 && !cu->IsBinarySplitValid()) { ok = false; return; }
+    cu->Split(static_cast<SplitType>(s));
+    for (int i = 0; i < constants::kQuadSplit; i++)
+      if (cu->GetSubCu(i)) Node(cu->GetSubCu(i));
+  }
+};
+}  // namespace
+
+// Re-codes picture `poc` (already coded once by the reference, which set up its headers and
+// reference lists) from outside decisions: cus = leaf CUs in coding order with the chosen vector
+// (list 0, reference index 0) and cbf flags, splits = the CU trees in pre-order (0 none, 1 quad,
+// 2 horizontal, 3 vertical), levels = quantised coefficients (picture-shaped planes), rec = the
+// reconstruction (after deblocking) the checksum is taken over.  Returns the NAL size or < 0.
+int xref_conf_write_inter(xref_conf *c, int poc, const xvcb200_cu *cus, int n_cus, const uint8_t *splits, int n_splits,
+                          const int16_t *const levels[3], const uint16_t *const rec[3]) {
+  auto pe = ConfFind(c, poc);
+  if (!pe) return -1;
+  const bool trace = getenv("XREF_TRACE") != nullptr;
+#define XT(msg) do { if (trace) { fprintf(stderr, "[conf] %s\n", msg); fflush(stderr); } } while (0)
+  Encoder *enc = c->enc;
+  XT("found picture");
+  const SegmentHeader &segment = *enc->segment_header_;
+  PictureData &pd = *pe->pic_data_;
+  const Qp base_qp = *pd.GetPicQp();
+  // reference lists first (PictureData::Init looks at them), as Encoder::EncodeOnePicture does
+  ReferenceListSorter<PictureEncoder> sorter(segment, enc->prev_segment_header_->open_gop);
+  sorter.Prepare(pe->GetPoc(), pd.GetTid(), pd.IsIntraPic(), enc->pic_encoders_, pd.GetRefPicLists(),
+                 segment.leading_pictures);
+  pd.Init(segment, base_qp, enc->encoder_settings_.adaptive_qp > 0);
+  pd.SetUseLocalIlluminationCompensation(false);
+  XT("init done");
+
+  XT("ref lists prepared");
+  BitWriter &bw = pe->bit_writer_;
+  bw.Clear();
+  pe->WriteHeader(segment, pd, static_cast<PicNum>(segment.max_sub_gop_length), pe->GetBufferFlag(), &bw);
+  SyntaxWriter writer(base_qp, pd.GetPredictionType(), &bw);
+  IntraPrediction intra_pred(c->bitdepth);
+  CuWriter cu_writer(pd, &intra_pred);
+  InterPrediction inter(Simd(1, c->bitdepth).inter_prediction, *pe->rec_pic_, c->bitdepth);
+  ConfTreeBuilder tb;
+  tb.pd = &pd; tb.inter = &inter; tb.cus = cus; tb.n_cus = n_cus; tb.splits = splits; tb.n_splits = n_splits;
+  tb.levels = levels; tb.width = c->width; tb.pic_qp = base_qp.GetQpRaw(YuvComponent::kY);
+  const int num_ctus = pd.GetNumberOfCtu();
+  for (int rsaddr = 0; rsaddr < num_ctus; rsaddr++) {
+    CodingUnit *ctu = pd.GetCtu(CuTree::Primary, rsaddr);
+    ctu->SetQp(tb.pic_qp);
+    XT("ctu: build");
+    tb.Node(ctu);
+    if (!tb.ok) return -2;
+    XT("ctu: write");
+    cu_writer.WriteCtu(ctu, &pd, &writer);
+    if (Restrictions::Get().disable_ext_implicit_last_ctu) writer.WriteEndOfSlice(false);
+  }
+  if (tb.next_cu != n_cus || tb.next_split != n_splits) return -3;
+  XT("ctus written");
+  writer.Finish();
+  CopyIn(pe->rec_pic_.get(), rec);
+  pe->rec_pic_->PadBorder();
+  pd.GetRefPicLists()->ZeroOutReferences();
+  pe->WriteChecksum(segment, &bw, segment.checksum_mode);
+  const std::vector<uint8_t> *bytes = bw.GetBytes();
+  for (auto &nal : c->nals)
+    if (nal.type != 16 && static_cast<int>(nal.poc) == poc) { nal.bytes = *bytes; return static_cast<int>(bytes->size()); }
+  return -4;
+}
+
+// The bitstream in the file framing of the reference applications (4-byte little-endian NAL
+// size before every NAL, encoder_app.cc:494-516).
+size_t xref_conf_bitstream(xref_conf *c, uint8_t *out, size_t cap) {
+  size_t need = 0;
+  for (auto &nal : c->nals) need += 4 + nal.bytes.size();
+  if (!out || cap < need) return need;
+  size_t off = 0;
+  for (auto &nal : c->nals) {
+    const uint32_t sz = static_cast<uint32_t>(nal.bytes.size());
+    for (int i = 0; i < 4; i++) out[off++] = static_cast<uint8_t>((sz >> (8 * i)) & 0xff);
+    std::memcpy(out + off, nal.bytes.data(), sz);
+    off += sz;
+  }
+  return need;
 }
 
 int xref_num_threads(void) {

@@ -106,6 +106,46 @@ def make_partition(width, height, seed=7, min_size=8, max_size=64, qp=32, unifor
     return cus
 
 
+def make_partition_tree(width, height, seed=7, min_size=8, qp=32, binary=True):
+    """A partition xvc's syntax can signal, with its CU trees: (cus, splits).  Quad splits down to
+    min_size; a quad-tree leaf may be split once more horizontally or vertically (binary depth 1, no
+    further split below a binary split, so no sibling split restriction ever applies --
+    coding_unit.cc:105-119, cu_writer.cc:58-76).  splits = the trees of all CTUs in raster order,
+    pre-order, one byte per node: 0 leaf, 1 quad, 2 horizontal, 3 vertical (SplitType, cu_types.h:37-42).
+    `depth` of a CU is its QUAD depth, as CodingUnit::GetDepth.  Picture size: multiples of 64."""
+    assert width % 64 == 0 and height % 64 == 0
+    rng = np.random.default_rng(seed)
+    out, splits = [], []
+
+    def node(x, y, w, h, depth):
+        r = rng.random()
+        if w == h and w // 2 >= min_size and r < 0.55:
+            splits.append(1)
+            hw = w // 2
+            for (sx, sy) in ((x, y), (x + hw, y), (x, y + hw), (x + hw, y + hw)):
+                node(sx, sy, hw, hw, depth + 1)
+            return
+        if binary and w == h and w // 2 >= min_size and r < 0.8:
+            hor = rng.random() < 0.5
+            splits.append(2 if hor else 3)
+            for k in range(2):
+                splits.append(0)
+                out.append((x + (0 if hor else k * w // 2), y + (k * h // 2 if hor else 0), w if hor else w // 2, h // 2 if hor else h, depth))
+            return
+        splits.append(0)
+        out.append((x, y, w, h, depth))
+
+    for cy in range(0, height, 64):
+        for cx in range(0, width, 64):
+            node(cx, cy, 64, 64, 0)
+    cus = np.zeros(len(out), dtype=abi.cu_dtype)
+    for i, (x, y, w, h, d) in enumerate(out):
+        cus[i]["x"], cus[i]["y"], cus[i]["w"], cus[i]["h"], cus[i]["depth"] = x, y, w, h, d
+    cus["qp"] = qp
+    cus["ref_idx"] = -1
+    return cus, np.array(splits, dtype=np.uint8)
+
+
 def check_partition(cus, width, height):
     """True when the CUs tile the picture exactly once."""
     cover = np.zeros((height // 4, width // 4), dtype=np.int32)
