@@ -18,46 +18,55 @@ from xvc_b200 import abi, workload
 XVCDEC = os.path.join(os.path.dirname(bindings.REF_SO), "xvcdec")
 
 
-def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=64):
-    """backend(cur, ref_rec, cus, prm, info) -> (cus_out, levels, rec planes incl. deblocking)."""
+def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=64, n_inter=1):
+    """backend(cur, ref_rec, cus, prm, info) -> (cus_out, levels, rec planes incl. deblocking).
+    n_inter inter pictures in a low-delay chain: picture k references picture k-1, i.e. from the second
+    inter picture on the reference picture is itself a reconstruction made by the backend."""
     canvas = workload.synth_canvas(width, height, seed)
-    pics = [workload.synth_frame(canvas, width, height, i, bd) for i in (0, 1)]
+    pics = [workload.synth_frame(canvas, width, height, i, bd) for i in range(1 + n_inter)]
     conf = bindings.RefConformance(ref, width, height, bd, qp)
     for p in pics:
         conf.push(p)
     conf.flush()
-    orig, ref_rec, info = conf.inter_inputs(1, 0)
-    assert all(np.array_equal(a, b) for a, b in zip(orig, pics[1]))
-    # With one reference picture the reference still signals a bi-predictive picture (both lists hold
-    # POC 0): the search runs on list 0 only, the deblocking decisions follow the signalled type.
-    cus, splits = workload.make_partition_tree(width, height, seed=seed + 1, min_size=8, qp=info["qp"])
-    prm = common.picture_params(1, info["lam"], ranges=(search_range, search_range), pocs=(0, 0),
-                                slots=dict(orig=0, ref0=1, ref1=-1, pred=2, rec=3, coeff=4), deblock=0, pad=0)
-    prm["chroma_offset_table"], prm["chroma_offset_u"], prm["chroma_offset_v"] = info["chroma_table"], info["off_u"], info["off_v"]
-    prm["beta_offset"], prm["tc_offset"] = info["beta_offset"], info["tc_offset"]
-    cus_out, levels, rec = backend(orig, ref_rec, cus, prm, info)
-    assert np.any(cus_out["mv"]) and any(np.any(l) for l in levels)
-    size = conf.write_inter(1, cus_out, splits, levels, rec)
-    assert size > 0, "the reference writer rejected the picture (%d)" % size
+    recs = []
+    for poc in range(1, 1 + n_inter):
+        orig, ref_rec, info = conf.inter_inputs(poc, poc - 1)
+        assert all(np.array_equal(a, b) for a, b in zip(orig, pics[poc]))
+        if recs:
+            assert all(np.array_equal(a, b) for a, b in zip(ref_rec, recs[-1]))
+        # With one reference picture the reference still signals a bi-predictive picture (both lists hold
+        # the same POC): the search runs on list 0 only, the deblocking decisions follow the signalled type.
+        cus, splits = workload.make_partition_tree(width, height, seed=seed + poc, min_size=8, qp=info["qp"])
+        prm = common.picture_params(1, info["lam"], ranges=(search_range, search_range), pocs=(poc - 1, poc - 1),
+                                    slots=dict(orig=0, ref0=1, ref1=-1, pred=2, rec=3, coeff=4), deblock=0, pad=0)
+        prm["chroma_offset_table"], prm["chroma_offset_u"], prm["chroma_offset_v"] = info["chroma_table"], info["off_u"], info["off_v"]
+        prm["beta_offset"], prm["tc_offset"] = info["beta_offset"], info["tc_offset"]
+        info["ref_poc"] = poc - 1
+        cus_out, levels, rec = backend(orig, ref_rec, cus, prm, info)
+        assert np.any(cus_out["mv"]) and any(np.any(l) for l in levels)
+        size = conf.write_inter(poc, cus_out, splits, levels, rec)
+        assert size > 0, "the reference writer rejected the picture (%d)" % size
+        recs.append(rec)
     stream = conf.bitstream()
     conf.close()
     with tempfile.TemporaryDirectory() as tmp:
         bit, yuv = os.path.join(tmp, "s.xvc"), os.path.join(tmp, "out.yuv")
         open(bit, "wb").write(stream)
         res = subprocess.run([XVCDEC, "-bitstream-file", bit, "-output-file", yuv, "-output-bitdepth", str(bd)],
-                             capture_output=True, text=True, timeout=120)
+                             capture_output=True, text=True, timeout=600)
         log = res.stdout + res.stderr
         dec = np.fromfile(yuv, dtype=np.uint16) if os.path.exists(yuv) else None
     assert "Conformance verified" in log and res.returncode == 0, log[-2000:]
-    # the decoder's output file: two pictures, the second one equals the backend's reconstruction
+    # the decoder's output file: every inter picture equals the backend's reconstruction
     per = width * height * 3 // 2
-    assert dec is not None and dec.size == 2 * per
-    second = dec[per:]
-    got = [second[:width * height].reshape(height, width),
-           second[width * height:width * height * 5 // 4].reshape(height // 2, width // 2),
-           second[width * height * 5 // 4:].reshape(height // 2, width // 2)]
-    for c in range(3):
-        assert np.array_equal(got[c], rec[c]), c
+    assert dec is not None and dec.size == (1 + n_inter) * per
+    for k, rec in enumerate(recs):
+        one = dec[(k + 1) * per:(k + 2) * per]
+        got = [one[:width * height].reshape(height, width),
+               one[width * height:width * height * 5 // 4].reshape(height // 2, width // 2),
+               one[width * height * 5 // 4:].reshape(height // 2, width // 2)]
+        for c in range(3):
+            assert np.array_equal(got[c], rec[c]), (k, c)
     return len(stream), log
 
 
@@ -68,7 +77,7 @@ def oracle_backend(oracle, width, height, bd):
         cus_o = cus.copy()
         levels, _, _ = oracle.encode_picture(Picture(width, height, 0, cur), refs, pred, rec, bd, cus_o, prm)
         if info["deblock"]:
-            oracle.deblock_picture(rec, bd, cus_o, info["pic_type"], {(0, 0): 0, (1, 0): 0}, info["beta_offset"], info["tc_offset"],
+            oracle.deblock_picture(rec, bd, cus_o, info["pic_type"], {(0, 0): info["ref_poc"], (1, 0): info["ref_poc"]}, info["beta_offset"], info["tc_offset"],
                                    info["chroma_table"], info["off_u"], info["off_v"])
         return cus_o, levels, rec.planes()
     return backend
@@ -85,7 +94,7 @@ def gpu_backend(width, height, bd):
         ctx.set_cus(cus)
         ctx.encode_picture(prm, want_results=False)
         if info["deblock"]:
-            ctx.deblock_picture(3, info["pic_type"], {(0, 0): 0, (1, 0): 0}, info["beta_offset"], info["tc_offset"],
+            ctx.deblock_picture(3, info["pic_type"], {(0, 0): info["ref_poc"], (1, 0): info["ref_poc"]}, info["beta_offset"], info["tc_offset"],
                                 info["chroma_table"], info["off_u"], info["off_v"])
         ctx.pad_border(3)
         ctx.sync()
