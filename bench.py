@@ -227,20 +227,36 @@ def run_ours(args):
     dev_prms[1]["rec_slot"] = base2 + 2 + rank
     dev_first_rec = [5, base2 + 2]
     works = [None, None]
+    # --exchange push (default): copy-engine pushes into the peers' arenas (CUDA IPC over NVLink), no SM
+    # involved; --exchange nccl: in-place all-gather on the NCCL stream (its copy kernels compete
+    # with the persistent search kernel for SMs)
+    peers = sharding.PeerExchange(ctx, dist, rank, world) if dist is not None and args.exchange == "push" else None
 
-    def device_step(i=0, flush_l2=False):
+    def device_step(i=0, flush_l2=False, ev=None):
+        """ev: list collecting (before wait, after wait, before kernels, after kernels) events."""
         s = i & 1 if dist is not None else 0
+        mark = (lambda: None) if ev is None else (lambda: (ev.append(torch.cuda.Event(enable_timing=True)), ev[-1].record(stream)))
+        mark()
         if works[s] is not None:
             works[s].wait()
             works[s] = None
+        if peers is not None:     # the slot about to be rewritten was pushed two steps ago
+            peers.wait_own(dev_first_rec[s] + rank)
+        mark()
         ctx.set_cus(cus)          # restores predictors / flags the previous step overwrote (device copy)
         if flush_l2:
             flush.zero_()
+        mark()
         ctx.encode_picture(dev_prms[s], want_results=False)
-        if dist is not None:      # finished, padded reconstructions to every GPU that will reference them
+        mark()
+        if peers is not None:     # finished, padded reconstructions to every GPU that will reference them
+            peers.push(dev_first_rec[s] + rank)
+        elif dist is not None:
             works[s] = sharding.frame_parallel_exchange(ctx, dist, rank, world, dev_first_rec[s], async_op=True)
 
     def drain():
+        if peers is not None:
+            peers.wait_own()
         for s in range(2):
             if works[s] is not None:
                 works[s].wait()
@@ -268,24 +284,26 @@ def run_ours(args):
                 stage_ms[k].append(v)
         total_ms = float(np.sum(step_ms))
     else:
-        # K steps in ONE device-timed window (the exchange of a step ends inside the next one);
-        # the L2 flushes sit in the window and are timed alone afterwards and subtracted
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        # Same timed region as N = 1 (the kernels of encode_picture; the untimed set_cus + L2 flush
+        # sit between steps) PLUS everything the exchange costs: it overlaps the next step's
+        # kernels (any slowdown shows in that step's time), the stream stall waiting for an
+        # unfinished exchange before its slot is rewritten, and the tail of the last exchanges.
+        ev = []
         for i in range(args.steps):
-            device_step(i, flush_l2=True)
+            device_step(i, flush_l2=True, ev=ev)
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
         drain()
-        e1.record(stream)
-        e1.synchronize()
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record(stream)
+        t1.synchronize()
         for k, v in ctx.stage_times_ms().items():
             stage_ms[k].append(v)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(args.steps):
-            flush.zero_()
-        f1.record(stream)
-        f1.synchronize()
-        total_ms = e0.elapsed_time(e1) - f0.elapsed_time(f1)
+        stall_ms = sum(ev[4 * i].elapsed_time(ev[4 * i + 1]) for i in range(args.steps))
+        step_ms = [ev[4 * i + 2].elapsed_time(ev[4 * i + 3]) for i in range(args.steps)]
+        tail_ms = t0.elapsed_time(t1)
+        total_ms = float(np.sum(step_ms)) + stall_ms + tail_ms
+        exchange_ms = {"stall_ms_per_step": stall_ms / args.steps, "tail_ms": tail_ms, "kernels_ms_per_step": float(np.mean(step_ms))}
     launches = lib.launch_count() - launches0
     barrier()
     sampler.stop_flag = True
@@ -323,11 +341,15 @@ def run_ours(args):
             s = i & 1
             if i + 1 < count:
                 ctx.upload_async(sets[1 - s]["orig"], h_orig)
+            if peers is not None:
+                peers.wait_own(sets[s]["first_rec"] + rank)
             ctx.set_cus(cus)
             if flush_l2:
                 flush.zero_()
             ctx.encode_picture(prms[s], want_results=False)
-            if dist is not None:
+            if peers is not None:
+                peers.push(sets[s]["first_rec"] + rank)
+            elif dist is not None:
                 sharding.frame_parallel_exchange(ctx, dist, rank, world, sets[s]["first_rec"])
             ctx.get_cus_async(h_cus[s])
             ctx.download_coeff_async(sets[s]["coeff"], h_lev[s])
@@ -424,7 +446,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16 samples / int32 arithmetic", "data": "synthetic",
-        "config": config_dict(n, {"parallelism": ("frame-parallel: one picture per GPU + NCCL all-gather of the padded reconstructions (%d x %.1f MB) per step, on the NCCL stream, overlapped with the next picture (two reconstruction slot sets); K steps timed as one window, L2 flushes subtracted" % (world, ctx.slot_region(0)[1] / 1e6)) if world > 1 else "single GPU"}),
+        "config": config_dict(n, {"parallelism": (("frame-parallel: one picture per GPU; per step every GPU's padded reconstruction (%.1f MB) goes to the %d others -- %s -- overlapped with the next picture (two reconstruction slot sets); timed: the kernels of every step (as at N=1) + stream stalls waiting for an exchange + the tail of the last exchanges" % (ctx.slot_region(0)[1] / 1e6, world - 1, "copy-engine pushes into the peers' slot arenas (CUDA IPC over NVLink, no SM)" if peers is not None else "in-place NCCL all-gather on the NCCL stream"))) if world > 1 else "single GPU"}),
         "frames_per_s": value * 1e6 / (WIDTH * HEIGHT),
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "pipeline": "2 pictures in flight: pinned-host H2D / D2H of neighbouring pictures on the copy stream overlap the kernels"},
@@ -435,6 +457,8 @@ def run_ours(args):
         "recon_bitexact_vs_cpu_baseline": bitexact,
         "me_sad_candidates_per_step": None,
     }
+    if dist is not None:
+        line["exchange"] = exchange_ms       # rank 0's own split of its timed total
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -446,6 +470,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
+                    help="N>1: how finished reconstructions reach the other GPUs (copy-engine pushes over CUDA IPC, or NCCL all-gather)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

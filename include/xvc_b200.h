@@ -272,6 +272,22 @@ int xvcb200_slot_ptr(xvcb200_ctx *ctx, int slot, int comp, void **dev_ptr);
  * e.g. the destination of an NCCL all-gather of reconstructed pictures. */
 int xvcb200_slot_region(xvcb200_ctx *ctx, int slot, void **base, uint64_t *bytes);
 
+/* Peer exchange of slots between the contexts of different PROCESSES on one NVLink / NVSwitch
+ * node (frame-parallel encoding: a finished, padded reconstruction goes to every GPU that will
+ * reference it -- thread_encoder.cc:99-131 has one address space, this is its multi-GPU form).
+ * Copy engines move the slot over NVLink; no SM takes part, so the exchange overlaps the next
+ * picture's kernels completely (an NCCL all-gather needs SMs, which the persistent search kernel
+ * occupies).  handle: 64 bytes (cudaIpcMemHandle_t of the slot arena), exchanged out of band.
+ * xvcb200_push_slot copies slot `slot` of this context into the same slot of every opened peer,
+ * ordered after the work enqueued on the context stream so far; xvcb200_wait_pushes makes the
+ * context stream wait for the last push of `slot` (slot < 0: of every slot) -- call it before the
+ * slot is overwritten.  Arrival at the consumer is the caller's rendezvous (after
+ * xvcb200_wait_pushes + xvcb200_sync on every rank the pushed slots are complete everywhere). */
+int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle64);
+int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle64, int *peer_index);
+int xvcb200_push_slot(xvcb200_ctx *ctx, int slot);
+int xvcb200_wait_pushes(xvcb200_ctx *ctx, int slot);
+
 /* host <-> device picture transfer; host planes are tight or strided (elements). */
 int xvcb200_upload_picture(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]);
 int xvcb200_download_picture(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]);

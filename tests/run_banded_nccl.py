@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Manual multi-GPU check (not collected by pytest):
-    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_banded_nccl.py
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_banded_nccl.py [W H]
+(BASELINE config 3: --nproc-per-node 4 ... run_banded_nccl.py 3840 2160)
 One picture split into CTU-row bands across the ranks (NCCL halo exchange for deblocking) must
 equal the single-GPU encode of the same picture bit for bit."""
 import os
@@ -22,6 +23,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, H, BD, QP = 1920, 1080, 10, 32
+    if len(sys.argv) >= 3:
+        W, H = int(sys.argv[1]), int(sys.argv[2])
     cur, r0, r1 = common.frames(W, H, BD, 77)
     cus = workload.make_partition(W, H, seed=41, min_size=4, qp=QP)
     prm = common.picture_params(0, workload.lambda_for_qp(QP), slots=dict(orig=0, ref0=1, ref1=2, pred=3, rec=4, coeff=5), pad=0)
@@ -51,7 +54,7 @@ def main():
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("banded encode on %d GPUs == single GPU: %s" % (world, bool(t.item())))
+        print("banded encode of %dx%d on %d GPUs (NCCL deblocking halo exchange) == single GPU: %s" % (W, H, world, bool(t.item())))
     dist.destroy_process_group()
     sys.exit(0 if t.item() else 1)
 

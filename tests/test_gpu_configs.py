@@ -173,3 +173,18 @@ def test_hierarchical_gop_chain(oracle):
         rec_o[poc] = rec
         slot_of[poc] = rec_slot
     ctx.close()
+
+
+def test_peer_push_two_processes_one_gpu():
+    """Frame-parallel exchange (config 5): padded reconstructions pushed between the slot arenas
+    of two PROCESSES (CUDA IPC + copy engines, xvcb200_push_slot) arrive bit for bit.  Both ranks
+    share cuda:0 here; tests/run_peer_push.py without `same-gpu` is the NVLink form."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29512", os.path.join(here, "run_peer_push.py"), "same-gpu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "True" in out.stdout

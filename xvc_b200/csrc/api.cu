@@ -392,6 +392,11 @@ void xvcb200_dequant(int w, int h, int bitdepth, int qp_bitdepth, const int16_t 
 
 // ---------------------------------------------------------------- (B) context
 struct CtxExtra {           // host-side state that is not needed by kernels
+  // peer arenas opened through CUDA IPC + the DMA streams that push slots into them
+  std::vector<uint8_t *> peer_arena;
+  std::vector<cudaStream_t> push_stream;
+  cudaEvent_t push_ready = nullptr, push_done = nullptr;
+  std::vector<cudaEvent_t> slot_pushed;       // per slot: its last push has left (all peers)
   PlaneView *d_luma_views = nullptr;          // luma PlaneView of every slot
   int *d_tu_list = nullptr;                   // TU ids (3*cu + comp) grouped by shape class
   int tu_cap = 0;
@@ -562,6 +567,14 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
     if (b.free_ev) cudaEventDestroy(b.free_ev);
     if (b.dl_ev) cudaEventDestroy(b.dl_ev);
   }
+  for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {
+    cudaStreamSynchronize(c->ex.push_stream[p]);
+    cudaStreamDestroy(c->ex.push_stream[p]);
+    cudaIpcCloseMemHandle(c->ex.peer_arena[p]);
+  }
+  if (c->ex.push_ready) cudaEventDestroy(c->ex.push_ready);
+  if (c->ex.push_done) cudaEventDestroy(c->ex.push_done);
+  for (cudaEvent_t e : c->ex.slot_pushed) if (e) cudaEventDestroy(e);
   if (c->ex.copy_stream) { cudaStreamSynchronize(c->ex.copy_stream); cudaStreamDestroy(c->ex.copy_stream); }
   for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) cudaFree(c->ex.d_stage[a][b]);
   if (c->ex.up_stream) { cudaStreamSynchronize(c->ex.up_stream); cudaStreamDestroy(c->ex.up_stream); }
@@ -617,6 +630,61 @@ int xvcb200_slot_region(xvcb200_ctx *c, int slot, void **base, uint64_t *bytes) 
   *base = c->slots[slot].alloc;
   *bytes = c->slot_stride;
   return XVCB200_OK;
+}
+
+int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle64) {
+  if (!ctx || !handle64 || ctx->slots.empty()) return XVCB200_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  if (!ctx->check(cudaIpcGetMemHandle(&h, ctx->slots[0].alloc), "cudaIpcGetMemHandle")) return ctx->status;
+  memcpy(handle64, &h, sizeof(h));
+  return XVCB200_OK;
+}
+int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle64, int *peer_index) {
+  if (!ctx || !handle64) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void *base = nullptr;
+  if (!c->check(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return c->status;
+  cudaStream_t st = nullptr;
+  if (!c->check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return c->status;
+  if (!c->ex.push_ready && (!c->check(cudaEventCreateWithFlags(&c->ex.push_ready, cudaEventDisableTiming), "cudaEventCreate") ||
+                            !c->check(cudaEventCreateWithFlags(&c->ex.push_done, cudaEventDisableTiming), "cudaEventCreate")))
+    return c->status;
+  c->ex.peer_arena.push_back(static_cast<uint8_t *>(base));
+  c->ex.push_stream.push_back(st);
+  if (peer_index) *peer_index = (int)c->ex.peer_arena.size() - 1;
+  return XVCB200_OK;
+}
+int xvcb200_push_slot(xvcb200_ctx *ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (c->ex.peer_arena.empty()) return XVCB200_OK;
+  const size_t off = (size_t)slot * c->slot_stride;
+  c->check(cudaEventRecord(c->ex.push_ready, c->stream), "cudaEventRecord");
+  for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {      // one DMA stream per peer: the copies run side by side
+    cudaStream_t st = c->ex.push_stream[p];
+    c->check(cudaStreamWaitEvent(st, c->ex.push_ready, 0), "cudaStreamWaitEvent");
+    c->check(cudaMemcpyAsync(c->ex.peer_arena[p] + off, c->slots[0].alloc + off, c->slot_stride, cudaMemcpyDeviceToDevice, st), "push slot");
+    if (p > 0) {      // funnel completion into the first push stream
+      c->check(cudaEventRecord(c->ex.push_done, st), "cudaEventRecord");
+      c->check(cudaStreamWaitEvent(c->ex.push_stream[0], c->ex.push_done, 0), "cudaStreamWaitEvent");
+    }
+  }
+  c->ex.slot_pushed.resize(c->slots.size(), nullptr);
+  cudaEvent_t &ev = c->ex.slot_pushed[slot];
+  if (!ev && !c->check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) return c->status;
+  c->check(cudaEventRecord(ev, c->ex.push_stream[0]), "cudaEventRecord");
+  return c->status;
+}
+int xvcb200_wait_pushes(xvcb200_ctx *ctx, int slot) {
+  if (!ctx || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  for (int s = 0; s < (int)c->ex.slot_pushed.size(); s++)
+    if ((slot < 0 || s == slot) && c->ex.slot_pushed[s])
+      c->check(cudaStreamWaitEvent(c->stream, c->ex.slot_pushed[s], 0), "cudaStreamWaitEvent");
+  return c->status;
 }
 
 static bool slot_ok(xvcb200_ctx *c, int slot) { return c && slot >= 0 && slot < (int)c->slots.size(); }

@@ -40,6 +40,7 @@ EXPORTS = [
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
     "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan",
+    "xvcb200_ipc_export", "xvcb200_ipc_open_peer", "xvcb200_push_slot", "xvcb200_wait_pushes",
 ]
 
 
@@ -90,6 +91,10 @@ def load():
     L.xvcb200_intra_ref_samples.argtypes = [c_int] * 8 + [c_void_p, c_ssize, c_void_p, c_void_p]
     L.xvcb200_intra_predict.argtypes = [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_ssize]
     L.xvcb200_intra_satd_scan.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
+    L.xvcb200_ipc_export.argtypes = [c_void_p, c_void_p]
+    L.xvcb200_ipc_open_peer.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.xvcb200_push_slot.argtypes = [c_void_p, c_int]
+    L.xvcb200_wait_pushes.argtypes = [c_void_p, c_int]
     L.xvcb200_ctx_create.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]
     L.xvcb200_ctx_destroy.argtypes = [c_void_p]
     L.xvcb200_ctx_set_stream.argtypes = [c_void_p, c_void_p]
@@ -318,6 +323,22 @@ class Context:
         p, n = c_void_p(), c_u64()
         self._ok(self.L.xvcb200_slot_region(self.h, slot, ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
+
+    def ipc_export(self):
+        """64-byte handle of the slot arena for the other processes of the node."""
+        h = np.zeros(64, dtype=np.uint8)
+        self._ok(self.L.xvcb200_ipc_export(self.h, abi.ptr(h)))
+        return h.tobytes()
+
+    def ipc_open_peer(self, handle):
+        h = np.frombuffer(handle, dtype=np.uint8).copy()
+        self._ok(self.L.xvcb200_ipc_open_peer(self.h, abi.ptr(h), None))
+
+    def push_slot(self, slot):
+        self._ok(self.L.xvcb200_push_slot(self.h, slot))
+
+    def wait_pushes(self, slot=-1):
+        self._ok(self.L.xvcb200_wait_pushes(self.h, slot))
 
     def slots_tensor(self, first, count=1):
         """torch uint8 CUDA tensor aliasing slots [first, first+count) (no copy)."""

@@ -177,3 +177,37 @@ def frame_parallel_exchange(ctx, dist, rank, world, first_slot, async_op=False):
     whole = ctx.slots_tensor(first_slot, world)
     mine = ctx.slots_tensor(first_slot + rank, 1)
     return dist.all_gather_into_tensor(whole, mine, async_op=async_op)
+
+
+class PeerExchange:
+    """Frame-parallel exchange without SMs: every rank pushes its finished, padded
+    reconstruction slot into the SAME slot of every other rank's arena with the copy engines
+    over NVLink (xvcb200_push_slot; arenas opened through CUDA IPC).  An NCCL all-gather needs
+    SMs for its copy kernels, which the persistent search kernel of the next picture occupies;
+    DMA pushes overlap it completely.  All contexts must have the same geometry / slot count.
+
+    push(slot) is ordered after the work enqueued on the context stream so far.  landed() is
+    the consumer-side guarantee: own pushes finished (context stream waits for them) and a
+    rendezvous of all ranks, after which slots pushed by the others may be referenced (or a
+    pushed slot overwritten)."""
+
+    def __init__(self, ctx, dist, rank, world):
+        self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export())
+        for r in range(world):
+            if r != rank:
+                ctx.ipc_open_peer(handles[r])
+
+    def push(self, slot):
+        self.ctx.push_slot(slot)
+
+    def wait_own(self, slot=-1):
+        """Context stream waits for this rank's last push of `slot` (-1: all) -- before the slot
+        is rewritten."""
+        self.ctx.wait_pushes(slot)
+
+    def landed(self):
+        self.ctx.wait_pushes()
+        self.ctx.sync()
+        self.dist.barrier()
