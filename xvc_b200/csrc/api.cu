@@ -646,7 +646,12 @@ int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle64, int *peer_inde
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, sizeof(h));
   void *base = nullptr;
-  if (!c->check(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return c->status;
+  cudaError_t oe = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (oe != cudaSuccess) {      // not sticky: the caller may fall back to another exchange (NCCL)
+    cudaGetLastError();
+    set_last_error(XVCB200_CUDA_ERROR, (std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(oe)).c_str());
+    return XVCB200_CUDA_ERROR;
+  }
   cudaStream_t st = nullptr;
   if (!c->check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) return c->status;
   if (!c->ex.push_ready && (!c->check(cudaEventCreateWithFlags(&c->ex.push_ready, cudaEventDisableTiming), "cudaEventCreate") ||

@@ -179,6 +179,10 @@ def frame_parallel_exchange(ctx, dist, rank, world, first_slot, async_op=False):
     return dist.all_gather_into_tensor(whole, mine, async_op=async_op)
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when some rank could not open a peer arena."""
+
+
 class PeerExchange:
     """Frame-parallel exchange without SMs: every rank pushes its finished, padded
     reconstruction slot into the SAME slot of every other rank's arena with the copy engines
@@ -195,9 +199,18 @@ class PeerExchange:
         self.ctx, self.dist, self.rank, self.world = ctx, dist, rank, world
         handles = [None] * world
         dist.all_gather_object(handles, ctx.ipc_export())
-        for r in range(world):
-            if r != rank:
-                ctx.ipc_open_peer(handles[r])
+        err = None
+        try:
+            for r in range(world):
+                if r != rank:
+                    ctx.ipc_open_peer(handles[r])
+        except RuntimeError as e:           # e.g. no peer access between two GPUs of this box
+            err = repr(e)
+        errs = [None] * world
+        dist.all_gather_object(errs, err)   # all ranks agree: usable everywhere or nowhere
+        bad = [(r, e) for r, e in enumerate(errs) if e]
+        if bad:
+            raise PeerExchangeUnavailable("rank %d: %s" % bad[0])
 
     def push(self, slot):
         self.ctx.push_slot(slot)
