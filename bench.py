@@ -282,7 +282,8 @@ def run_ours(args):
     if dist is None:
         for _ in range(args.steps):
             ctx.set_cus(cus)
-            flush.zero_()
+            if not os.environ.get("XVCB_BENCH_NOFLUSH"):      # experiments only; the default run always flushes
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             ctx.encode_picture(prm, want_results=False)
@@ -414,8 +415,10 @@ def run_ours(args):
     dom = max(stage_avg, key=stage_avg.get)
     achieved = alg_bytes[dom] / (stage_avg[dom] * 1e-3) / 1e9
     traffic, traffic_src, issue = None, None, None
-    tpath = os.path.join(ROOT, "profiles", "r1s2_traffic.json")     # ncu --set full capture of the dominant kernel
-    if os.path.exists(tpath):
+    import glob
+    tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), key=os.path.getmtime)
+    tpath = tpaths[-1] if tpaths else ""      # newest ncu --set full capture of the dominant kernel
+    if tpath:
         tj = json.load(open(tpath))
         if tj.get("kernel", "").startswith(dom):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]

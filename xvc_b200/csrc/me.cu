@@ -512,6 +512,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
   long long t_mark = prof ? clock64() : 0;
+  int n_staged = 0;
   auto lap = [&](int slot) {     // optional phase timing (XVCB_TZ_PROF=1): cycles of thread 0, summed over CTAs
     if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&prof[slot], (unsigned long long)(now - t_mark)); t_mark = now; }
   };
@@ -580,6 +581,11 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       }
       if (staged) stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
       __syncthreads();
+      if (prof && tid == 0) {      // first staging by the ordinal of the group in this CTA, and its bytes
+        atomicAdd(&prof[18 + min(n_staged, 3)], (unsigned long long)(clock64() - t_mark));
+        atomicAdd(&prof[22], (unsigned long long)(staged ? bh * cpr * 16 : 0));
+        n_staged++;
+      }
       lap(1);
 
       // ---------------- phase 1 (ph = 0: start points, first diamond pass, 2-point step), the raster
@@ -997,18 +1003,22 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   }
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
-  static unsigned long long *prof = nullptr;
-  static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
-  if (want_prof && !prof) cudaMallocManaged(&prof, 24 * sizeof(*prof));
-  if (want_prof) { cudaStreamSynchronize(s); memset(prof, 0, 24 * sizeof(*prof)); }
+    static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
+  // device memory, not managed: the first touch of a managed page from the kernel faults and stalls the
+  // SM for ~0.1 ms, which the laps then attribute to whatever phase comes first
+  static unsigned long long *d_prof = nullptr;
+  static unsigned long long prof[24];
+  if (want_prof && !d_prof) cudaMalloc(&d_prof, sizeof(prof));
+  if (want_prof) cudaMemsetAsync(d_prof, 0, sizeof(prof), s);
   const int grid = n_groups < num_sms ? n_groups : num_sms;
   const int fixed_words = kTileWords + kSegWords + kMaxGroupJobs * (int)(sizeof(SJob) / 4);
   g_launch_count++;
   tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
       d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
       d_ref_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
-      want_prof ? prof : nullptr);
+      want_prof ? d_prof : nullptr);
   if (want_prof) {
+    cudaMemcpyAsync(prof, d_prof, sizeof(prof), cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
     fprintf(stderr, "[tz prof] cycles/CTA: box %.0f stage %.0f phase1 %.0f stageS8 %.0f bound %.0f stageRef %.0f exact %.0f phase3 %.0f | raster candidates %llu survivors %llu (%.2f%%)\n",
             (double)prof[0] / grid, (double)prof[1] / grid, (double)prof[2] / grid, (double)prof[3] / grid, (double)prof[4] / grid,
@@ -1017,6 +1027,8 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
     fprintf(stderr, "[tz prof2] warp-cycles/CTA: fetch %.0f setup %.0f start %.0f diamond %.0f replay %.0f neighbour %.0f tail/idle %.0f | diamond passes (warp level) %llu\n",
             (double)prof[10] / grid, (double)prof[11] / grid, (double)prof[12] / grid, (double)prof[13] / grid, (double)prof[14] / grid,
             (double)prof[15] / grid, (double)prof[16] / grid, prof[17]);
+    fprintf(stderr, "[tz prof3] first staging, cycles/CTA by ordinal of the group in its CTA: 1st %.0f 2nd %.0f 3rd %.0f later %.0f | staged bytes/CTA %.0f groups %d\n",
+            (double)prof[18] / grid, (double)prof[19] / grid, (double)prof[20] / grid, (double)prof[21] / grid, (double)prof[22] / grid, n_groups);
   }
   return cudaGetLastError();
 }
