@@ -326,6 +326,21 @@ int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearc
  * context's CU array, all three components, into pred_slot.  ref_slots[list][ref_idx]. */
 int xvcb200_motion_compensate(xvcb200_ctx *ctx, const int32_t ref_slots[2][5], int pred_slot);
 
+/* Affine motion compensation (InterPrediction::MotionCompAffine,
+ * inter_prediction.cc:1044-1136, reached from MotionCompensation through MotionCompRefList's
+ * GetUseAffine branch :1021-1023 and from the encoder's affine search through
+ * MotionCompensationMv(cu, comp, ref_pic, MotionVector3, ...) :761-767).  For every entry: the CU
+ * `cu` of the context's CU array is predicted from its reference picture(s) (cu.ref_idx, as in
+ * xvcb200_motion_compensate; cu.mv is ignored) with the 4-parameter model given by the control-point
+ * MVs mv[list][corner: 0 top-left, 1 top-right, 2 bottom-left][x, y] in 1/16 pel (CodingUnit::
+ * GetMvAffine, coding_unit.h:258-264), all three components, into pred_slot. */
+typedef struct {
+  int32_t cu;
+  int32_t mv[2][3][2];
+} xvcb200_affine_cu;
+int xvcb200_motion_compensate_affine(xvcb200_ctx *ctx, const xvcb200_affine_cu *aff, int n,
+                                     const int32_t ref_slots[2][5], int pred_slot);
+
 /* TransformAndReconstruct for every CU x component: residual = orig - pred, forward
  * transform, QuantFast, dequant, inverse transform, AddClip into rec_slot; levels into
  * coeff_slot; per-TU results[3*n_cus] (order: cu-major, component-minor); cbf flags are

@@ -878,6 +878,92 @@ void xo_motion_compensate(const xo_picture *const refs[2][5], int bitdepth, cons
   }
 }
 
+/* ---- affine motion compensation -------------------------------
+ * InterPrediction::MotionCompAffine, inter_prediction.cc:1044-1136: the three control-point
+ * MVs (top-left, top-right, bottom-left) are clipped (ClipMv for MotionVector3, :783-799), the
+ * block is cut into sub-blocks whose size follows from the MV spread (get_subblock_size,
+ * :1071-1086), every sub-block gets the MV of the 4-parameter model at its centre (1/256 of the
+ * MV unit, rotation-zoom: ver = (-hor.y, hor.x)), clipped again, and is predicted by the plain
+ * MotionCompUniPred. */
+static int affine_subblock_size(const int32_t ref[2], const int32_t mv_uni[2], int size, int scale) {
+  const int dx = abs(mv_uni[0] - ref[0]), dy = abs(mv_uni[1] - ref[1]);
+  const int max_len = dx > dy ? dx : dy;
+  if (!max_len) return size;                 /* note: NOT scaled (inter_prediction.cc:1078-1080) */
+  int sub = (size >> 2) / max_len;           /* kSizeShift = 6 - kPrecisionShift */
+  if (sub < 1) sub = 1;
+  while (size % sub) sub--;
+  return (sub > 4 ? sub : 4) >> scale;
+}
+
+static void mc_affine(const xo_picture *ref, int comp, int bitdepth, const xvcb200_cu *cu, const int32_t mv_raw[3][2],
+                      int bipred, void *pred, ptrdiff_t ps) {
+  const int cs = comp ? 1 : 0, sh = 4 + cs;
+  const int px = cu->x >> cs, py = cu->y >> cs, w = cu->w >> cs, h = cu->h >> cs;
+  const int W = ref->width[0], H = ref->height[0];
+  int32_t mv[3][2];
+  const int min_x = -((64 + 8 + cu->x - 1) * 16), max_x = (W + 8 - cu->x - 1) * 16;
+  const int min_y = -((64 + 8 + cu->y - 1) * 16), max_y = (H + 8 - cu->y - 1) * 16;
+  for (int i = 0; i < 3; i++) {
+    mv[i][0] = mv_raw[i][0] < min_x ? min_x : mv_raw[i][0] > max_x ? max_x : mv_raw[i][0];
+    mv[i][1] = mv_raw[i][1] < min_y ? min_y : mv_raw[i][1] > max_y ? max_y : mv_raw[i][1];
+  }
+  const size_t esz = 2;                       /* both prediction types are 16 bits wide */
+  if (mv[0][0] == mv[1][0] && mv[0][1] == mv[1][1]) {      /* :1063-1069: translation, mv[2] ignored */
+    const uint16_t *r = ref->base[comp] + (py + (mv[0][1] >> sh)) * ref->stride[comp] + px + (mv[0][0] >> sh);
+    xo_interp(comp != 0, bipred, w, h, bitdepth, mv[0][0] & ((1 << sh) - 1), mv[0][1] & ((1 << sh) - 1), r,
+              ref->stride[comp], pred, ps);
+    return;
+  }
+  const int sbw = affine_subblock_size(mv[0], mv[1], w, cs), sbh = affine_subblock_size(mv[0], mv[2], h, cs);
+  const int dhx = ((mv[1][0] - mv[0][0]) * 256) / w, dhy = ((mv[1][1] - mv[0][1]) * 256) / w;   /* C division: toward zero */
+  const int dvx = -dhy, dvy = dhx;
+  int hor_x = mv[0][0] * 256, hor_y = mv[0][1] * 256, ver_x = hor_x, ver_y = hor_y;
+  for (int sy = 0; sy < h; sy += sbh) {
+    for (int sx = 0; sx < w; sx += sbw) {
+      int mx = (hor_x + dhx * (sbw >> 1) + dvx * (sbh >> 1)) >> 8;
+      int my = (hor_y + dhy * (sbw >> 1) + dvy * (sbh >> 1)) >> 8;
+      mx = mx < min_x ? min_x : mx > max_x ? max_x : mx;
+      my = my < min_y ? min_y : my > max_y ? max_y : my;
+      const uint16_t *r = ref->base[comp] + (py + sy + (my >> sh)) * ref->stride[comp] + px + sx + (mx >> sh);
+      xo_interp(comp != 0, bipred, sbw, sbh, bitdepth, mx & ((1 << sh) - 1), my & ((1 << sh) - 1), r, ref->stride[comp],
+                (char *)pred + ((size_t)sy * ps + sx) * esz, ps);
+      hor_x += dhx * sbw;
+      hor_y += dhy * sbw;
+    }
+    ver_x += dvx * sbh;
+    ver_y += dvy * sbh;
+    hor_x = ver_x;
+    hor_y = ver_y;
+  }
+}
+
+/* InterPrediction::MotionCompensation (:710-738) for CUs with use_affine: MotionCompRefList takes
+ * the GetUseAffine branch (:1021-1023) for each list in use; bi-prediction averages the two 14-bit
+ * intermediates with AddAvgBi as for translational CUs. */
+void xo_motion_compensate_affine(const xo_picture *const refs[2][5], int bitdepth, const xvcb200_cu *cus,
+                                 const xvcb200_affine_cu *aff, int n_aff, xo_picture *pred) {
+  int16_t t0[64 * 64], t1[64 * 64];
+  for (int i = 0; i < n_aff; i++) {
+    const xvcb200_cu *cu = &cus[aff[i].cu];
+    const int l0 = cu->ref_idx[0] >= 0, l1 = cu->ref_idx[1] >= 0;
+    if ((cu->flags & XVCB200_CU_INTRA) || (!l0 && !l1)) continue;
+    for (int c = 0; c < 3; c++) {
+      const int cs = c ? 1 : 0, w = cu->w >> cs, h = cu->h >> cs;
+      uint16_t *dst = pred->base[c] + (cu->y >> cs) * pred->stride[c] + (cu->x >> cs);
+      if (l0 && l1) {
+        mc_affine(refs[0][cu->ref_idx[0]], c, bitdepth, cu, aff[i].mv[0], 1, t0, 64);
+        mc_affine(refs[1][cu->ref_idx[1]], c, bitdepth, cu, aff[i].mv[1], 1, t1, 64);
+        const int head = K_INTERNAL_PREC - bitdepth;
+        const int shift = (head > 2 ? head : 2) + 1;
+        xo_add_avg(w, h, (1 << (shift - 1)) + 2 * K_INTERNAL_OFFSET, shift, bitdepth, t0, 64, t1, 64, dst, pred->stride[c]);
+      } else {
+        const int l = l1 ? 1 : 0;
+        mc_affine(refs[l][cu->ref_idx[l]], c, bitdepth, cu, aff[i].mv[l], 0, dst, pred->stride[c]);
+      }
+    }
+  }
+}
+
 /* ===================================================================================
  * Residual coding chain
  * =================================================================================== */
