@@ -120,6 +120,7 @@ class Oracle:
         L.xo_pad_border.argtypes = [c_void_p]
         L.xo_full_search.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u32, c_void_p, c_void_p]
         L.xo_motion_compensate.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p]
+        L.xo_motion_compensate_affine.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
         L.xo_tq_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         L.xo_dequant_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]
         L.xo_deblock_picture.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
@@ -246,6 +247,12 @@ class Oracle:
         p = pred.c_struct()
         self.L.xo_motion_compensate(ctypes.addressof(arr), bitdepth, abi.ptr(cus), len(cus), ctypes.byref(p))
 
+    def motion_compensate_affine(self, refs, bitdepth, cus, aff, pred):
+        arr, keep = _refs_array(refs)
+        p = pred.c_struct()
+        aff = np.ascontiguousarray(aff, dtype=abi.affine_cu_dtype)
+        self.L.xo_motion_compensate_affine(ctypes.addressof(arr), bitdepth, abi.ptr(cus), abi.ptr(aff), len(aff), ctypes.byref(p))
+
     def tq_reconstruct(self, orig, pred, rec, bitdepth, cus, intra_picture=0, table=1, off_u=0, off_v=0):
         levels = [np.zeros((orig.height[c], orig.width[c]), dtype=np.int16) for c in range(3)]
         res = np.zeros(3 * len(cus), dtype=abi.tu_result_dtype)
@@ -336,6 +343,7 @@ class Ref:
         L.xref_tz_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
         L.xref_full_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
         L.xref_motion_compensate.argtypes = [c_void_p, c_int]
+        L.xref_motion_compensate_affine.argtypes = [c_void_p, c_void_p, c_int, c_int]
         L.xref_tq_reconstruct.argtypes = [c_void_p, c_int, c_void_p]
         L.xref_deblock_picture.argtypes = [c_void_p, c_int, c_int]
         L.xref_pad_border_rec.argtypes = [c_void_p]
@@ -535,6 +543,10 @@ class RefSession:
 
     def motion_compensate(self, threads=1):
         self.L.xref_motion_compensate(self.h, threads)
+
+    def motion_compensate_affine(self, aff, threads=1):
+        aff = np.ascontiguousarray(aff, dtype=abi.affine_cu_dtype)
+        self.L.xref_motion_compensate_affine(self.h, abi.ptr(aff), len(aff), threads)
 
     def tq_reconstruct(self, n_cus, threads=1):
         res = np.zeros(3 * n_cus, dtype=abi.tu_result_dtype)

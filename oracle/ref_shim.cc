@@ -597,6 +597,36 @@ void xref_motion_compensate(xref_session *s, int threads) {
       });
 }
 
+// Affine CUs: CodingUnit::SetUseAffine + SetMv(MotionVector3) (coding_unit.h:250-257, 287), then the
+// reference's own InterPrediction::MotionCompensation, which reaches MotionCompAffine through
+// MotionCompRefList (inter_prediction.cc:1021-1023).  The CUs are restored to translational after.
+void xref_motion_compensate_affine(xref_session *s, const xvcb200_affine_cu *aff, int n, int threads) {
+  EnsureInit(s);
+  const auto &simd = Simd(s->use_simd, s->bitdepth);
+  ParallelFor<InterPrediction>(
+      n, threads, [&]() { return new InterPrediction(simd.inter_prediction, *s->rec, s->bitdepth); },
+      [&](InterPrediction *ip, int i) {
+        CodingUnit *cu = s->cus[aff[i].cu];
+        if (cu->IsIntra()) return;
+        MotionVector keep[2];
+        for (int l = 0; l < 2; l++) {
+          const RefPicList list = static_cast<RefPicList>(l);
+          keep[l] = cu->GetMv(list, MvCorner::kDefault);
+          MotionVector3 mv3;
+          for (int k = 0; k < 3; k++) mv3[k] = MotionVector(aff[i].mv[l][k][0], aff[i].mv[l][k][1]);
+          cu->SetMv(mv3, list);
+        }
+        cu->SetUseAffine(true);
+        for (int c = 0; c < 3; c++) {
+          YuvComponent comp = static_cast<YuvComponent>(c);
+          SampleBuffer pb = s->pred->GetSampleBuffer(comp, cu->GetPosX(comp), cu->GetPosY(comp));
+          ip->MotionCompensation(*cu, comp, &pb);
+        }
+        cu->SetUseAffine(false);
+        for (int l = 0; l < 2; l++) cu->SetMv(keep[l], static_cast<RefPicList>(l));
+      });
+}
+
 // ---------------------------------------------------------------- T/Q/recon chain
 // The body of TransformEncoder::TransformAndReconstruct (transform_encoder.cc:203-285),
 // driven class by class with RdoQuant::QuantFast in place of QuantRdo (rdo_quant is a

@@ -102,6 +102,32 @@ def picture_params(pic_type, lam, ranges=(128, 128), pocs=(0, 16), slots=None, d
     return prm
 
 
+def affine_cus(cus, rng):
+    """xvcb200_affine_cu entries for every CU that may use affine motion (CodingUnit::CanUseAffine,
+    coding_unit.h:285: w > 8 and h > 8): control points = a base MV plus spreads that exercise every
+    sub-block size (4 ... whole block), the translation shortcut (mv[0] == mv[1]), a zero vertical
+    spread, and MVs far outside the picture (clipping of control points and of sub-block MVs)."""
+    idx = [i for i in range(len(cus)) if cus[i]["w"] > 8 and cus[i]["h"] > 8 and (cus[i]["ref_idx"][0] >= 0 or cus[i]["ref_idx"][1] >= 0)]
+    aff = np.zeros(len(idx), dtype=abi.affine_cu_dtype)
+    for k, i in enumerate(idx):
+        aff[k]["cu"] = i
+        for l in range(2):
+            kind = (k + l) % 7
+            base = rng.integers(-600, 601, size=2) if kind != 5 else rng.integers(-40000, 40001, size=2)
+            spread = [1, 2, 3, 5, 9, 40, 200][(k // 7 + l) % 7]
+            d1 = rng.integers(-spread, spread + 1, size=2)
+            d2 = rng.integers(-spread, spread + 1, size=2)
+            if kind == 3:
+                d1[:] = 0           # translation shortcut, mv[2] ignored
+            if kind == 4:
+                d2[:] = 0           # sub-block height = whole block
+            if kind == 6:
+                base = (base // 16) * 16
+                d1, d2 = d1 * 16, d2 * 16       # full-pel phases
+            aff[k]["mv"][l] = [base, base + d1, base + d2]
+    return aff
+
+
 def oracle_refs(oracle, width, height, r0, r1=None):
     refs = {(0, 0): Picture(width, height, 80, r0)}
     oracle.pad_border(refs[(0, 0)])

@@ -22,3 +22,9 @@ def test_gpu_matches_golden(golden, kind):
             golden_check.run_case(be, z, c)
             n += 1
     assert n >= 2
+
+
+def test_affine_golden_gpu():
+    """Reference MotionCompAffine outputs (tests/golden/xvc_affine_golden.npz) == xvcb200_motion_compensate_affine."""
+    import affine_golden
+    affine_golden.replay(affine_golden.gpu_backend())

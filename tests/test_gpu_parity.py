@@ -292,6 +292,32 @@ def test_motion_compensate(oracle, bd):
         assert np.array_equal(p, pred.plane(c)), c
 
 
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_motion_compensate_affine(oracle, bd):
+    """xvcb200_motion_compensate_affine == MotionCompAffine (oracle pinned against the reference in
+    test_oracle_vs_ref.py::test_motion_compensate_affine), bit for bit."""
+    width, height = 200, 136
+    cur, r0, r1 = common.frames(width, height, bd, 128, "random")
+    ctx = _ctx(width, height, bd, cur, r0, r1)
+    rng = np.random.default_rng(129)
+    cus = common.mc_cus(width, height, rng, 8)
+    aff = common.affine_cus(cus, rng)
+    assert len(aff) >= 10
+    ctx.set_cus(cus)
+    ctx.motion_compensate({(0, 0): 1, (1, 0): 2}, 3)
+    ctx.motion_compensate_affine(aff, {(0, 0): 1, (1, 0): 2}, 3)
+    pred = Picture(width, height, 80)
+    refs = common.oracle_refs(oracle, width, height, r0, r1)
+    oracle.motion_compensate(refs, bd, cus, pred)
+    oracle.motion_compensate_affine(refs, bd, cus, aff, pred)
+    for c, p in enumerate(ctx.download(3)):
+        assert np.array_equal(p, pred.plane(c)), c
+    bad = aff[:1].copy()
+    bad["cu"] = len(cus)
+    with pytest.raises(lib.XvcB200Error):
+        ctx.motion_compensate_affine(bad, {(0, 0): 1, (1, 0): 2}, 3)
+
+
 @pytest.mark.parametrize("bd,qp,min_size", [(10, 32, 4), (10, 22, 8), (8, 37, 4), (12, 27, 8)])
 def test_tq_reconstruct(oracle, bd, qp, min_size):
     width, height = 200, 136

@@ -28,3 +28,10 @@ def test_golden_covers_every_stage(golden):
     z, cases = golden
     count = collections.Counter(c["kind"] for c in cases)
     assert count["metric"] >= 20 and count["interp"] >= 10 and count["tx"] >= 100 and count["quant"] >= 30 and count["picture"] == 2
+
+
+def test_affine_golden_oracle(oracle):
+    """tests/golden/xvc_affine_golden.npz (reference MotionCompAffine outputs) replayed against the C
+    restatement."""
+    import affine_golden
+    affine_golden.replay(affine_golden.oracle_backend(oracle))

@@ -9,6 +9,8 @@ import pytest
 from oracle.bindings import Picture
 from xvc_b200 import abi, workload
 
+import common
+
 SIZES = [4, 8, 16, 32, 64]
 CSIZES = [2, 4, 8, 16, 32]
 
@@ -233,10 +235,10 @@ def _session_inputs(width, height, bd, seed, content="synth"):
     return frames
 
 
-def _make(ref, oracle, width, height, bd, seed, pic_type=0, qp=32, content="synth", lam=None):
+def _make(ref, oracle, width, height, bd, seed, pic_type=0, qp=32, content="synth", lam=None, simd=1):
     cur, r0, r1 = _session_inputs(width, height, bd, seed, content)
     lam = workload.lambda_for_qp(qp) if lam is None else lam
-    s = ref.session(width, height, bd, pic_type, qp, lam, simd=1, poc=8, sub_gop=16)
+    s = ref.session(width, height, bd, pic_type, qp, lam, simd=simd, poc=8, sub_gop=16)
     s.set_orig(cur)
     s.add_ref(0, 0, 0, r0)
     if pic_type == 0:
@@ -344,6 +346,45 @@ def test_motion_compensate(oracle, ref, bd):
     oracle.motion_compensate(refs, bd, cus, pred)
     for c, p in enumerate(s.get_pred()):
         assert np.array_equal(p, pred.plane(c)), c
+
+
+@pytest.mark.parametrize("bd,simd", [(8, 0), (10, 0), (10, 1)])
+def test_motion_compensate_affine(oracle, ref, bd, simd):
+    """MotionCompAffine (inter_prediction.cc:1044-1136) through the reference's own
+    MotionCompensation on CUs with SetUseAffine(true): uni- and bi-predicted, all sub-block sizes.
+    With the C filter table the whole picture must agree.  The reference's SIMD chroma filters write
+    four columns for a 2-wide sub-block; inside the codec the overshoot of a CU's last sub-block lands
+    in the CU-sized scratch prediction buffer, in this picture-sized one it lands in the right
+    neighbour -- so with simd=1 the comparison is per affine CU (the data the codec consumes)."""
+    width, height = 200, 136
+    s, orig, refs, lam = _make(ref, oracle, width, height, bd, 28, content="random", simd=simd)
+    rng = np.random.default_rng(29)
+    cus = workload.make_partition(width, height, seed=9, min_size=8)
+    for i in range(len(cus)):
+        cus[i]["ref_idx"] = [(0, -1), (-1, 0), (0, 0)][i % 3]
+        cus[i]["mv"] = rng.integers(-300, 301, size=(2, 2))
+    aff = common.affine_cus(cus, rng)
+    assert len(aff) >= 10
+    s.set_cus(cus)
+    s.motion_compensate(threads=2)                 # translational prediction everywhere first
+    s.motion_compensate_affine(aff, threads=1)     # affine CUs overwrite theirs
+    pred = Picture(width, height, 80)
+    oracle.motion_compensate(refs, bd, cus, pred)
+    oracle.motion_compensate_affine(refs, bd, cus, aff, pred)
+    got = s.get_pred()
+    for a in aff:
+        cu = cus[a["cu"]]
+        for c in range(3):
+            cs = 1 if c else 0
+            x, y, w, h = cu["x"] >> cs, cu["y"] >> cs, cu["w"] >> cs, cu["h"] >> cs
+            assert np.array_equal(got[c][y:y + h, x:x + w], pred.plane(c)[y:y + h, x:x + w]), (a["cu"], c)
+    if not simd:
+        for c, p in enumerate(got):
+            assert np.array_equal(p, pred.plane(c)), c
+    # the affine CUs really differ from their translational prediction
+    plain = Picture(width, height, 80)
+    oracle.motion_compensate(refs, bd, cus, plain)
+    assert not np.array_equal(plain.plane(0), pred.plane(0))
 
 
 @pytest.mark.parametrize("bd,qp", [(10, 32), (10, 22), (8, 37)])

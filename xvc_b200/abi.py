@@ -19,6 +19,8 @@ cu_dtype = np.dtype([
     ("qp", "i1"), ("ref_idx", "i1", (2,)), ("tx_select", "u1"), ("mv", "<i4", (2, 2)),
 ], align=True)
 
+affine_cu_dtype = np.dtype([("cu", "<i4"), ("mv", "<i4", (2, 3, 2))], align=True)    # xvcb200_affine_cu
+
 me_job_dtype = np.dtype([
     ("cu", "<i4"), ("ref_slot", "<i4"), ("search_range", "<i4"), ("mvp", "<i4", (2,)),
     ("prev", "<i4", (2,)), ("list", "<i4"),

@@ -165,4 +165,159 @@ cudaError_t launch_motion_compensate(cudaStream_t s, const xvcb200_cu *d_cus, in
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- affine motion compensation
+// InterPrediction::MotionCompAffine (inter_prediction.cc:1044-1136).  The reference walks the
+// sub-blocks of a CU serially, accumulating the model MV, and runs MotionCompUniPred on each.
+// Here a CTA takes one (CU, component) and every thread takes samples: the MV of the sub-block a
+// sample lies in has a closed form (the accumulations are plain integer sums), and the sample is
+// filtered directly from the reference picture with the arithmetic of the separable passes
+// (first pass stored as int16, inter_prediction.cc:1387-1448) -- sub-blocks of 4x4 luma / 2x2
+// chroma samples with their own fractional phases leave nothing to share between neighbours
+// but reference samples, which the L1 holds.
+struct AffineModel {
+  int sbw, sbh;                      // sub-block size in samples of the component
+  int dhx, dhy;                      // MV change per sample along x, 1/256 MV units; along y: (-dhy, dhx)
+  int mv0x, mv0y;                    // clipped top-left control point
+  int min_x, max_x, min_y, max_y;    // ClipMv bounds of the CU
+};
+
+__device__ __forceinline__ int affine_subblock_size(int rx, int ry, int ux, int uy, int size, int scale) {
+  const int max_len = max(abs(ux - rx), abs(uy - ry));
+  if (!max_len) return size;
+  int sub = max(1, (size >> 2) / max_len);
+  while (size % sub) sub--;
+  return max(4, sub) >> scale;
+}
+
+__device__ __forceinline__ AffineModel affine_model(const xvcb200_cu &cu, int cs, int pic_w, int pic_h, const int32_t (*mv_raw)[2]) {
+  AffineModel m;
+  m.min_x = -((64 + 8 + cu.x - 1) * 16); m.max_x = (pic_w + 8 - cu.x - 1) * 16;
+  m.min_y = -((64 + 8 + cu.y - 1) * 16); m.max_y = (pic_h + 8 - cu.y - 1) * 16;
+  int mv[3][2];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    mv[i][0] = clip3i(mv_raw[i][0], m.min_x, m.max_x);
+    mv[i][1] = clip3i(mv_raw[i][1], m.min_y, m.max_y);
+  }
+  const int w = cu.w >> cs, h = cu.h >> cs;
+  m.sbw = affine_subblock_size(mv[0][0], mv[0][1], mv[1][0], mv[1][1], w, cs);
+  m.sbh = affine_subblock_size(mv[0][0], mv[0][1], mv[2][0], mv[2][1], h, cs);
+  m.dhx = ((mv[1][0] - mv[0][0]) * 256) / w;       // C++ division, toward zero
+  m.dhy = ((mv[1][1] - mv[0][1]) * 256) / w;
+  m.mv0x = mv[0][0]; m.mv0y = mv[0][1];
+  return m;
+}
+
+// One sample of MotionCompUniPred at reference position r (centre sample), phases (fx, fy).
+template <bool BIPRED, int NTAPS>
+__device__ __forceinline__ int mc_sample(const Sample *r, int rs, int fx, int fy, int bitdepth) {
+  constexpr int kBack = NTAPS / 2 - 1;
+  const int maxv = (1 << bitdepth) - 1;
+  const int head = 14 - bitdepth;
+  if (fx == 0 && fy == 0) {
+    const int s = *r;
+    return BIPRED ? (int)(int16_t)((int16_t)(s << head) - (int16_t)8192) : s;
+  }
+  const int16_t *tx = NTAPS == 4 ? c_chroma_taps[fx] : c_luma_taps[fx];
+  const int16_t *ty = NTAPS == 4 ? c_chroma_taps[fy] : c_luma_taps[fy];
+  int shift, offset;
+  if (fy == 0 || fx == 0) {
+    const int16_t *t = fy == 0 ? tx : ty;
+    const int step = fy == 0 ? 1 : rs;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < NTAPS; k++) sum += (int)r[(k - kBack) * step] * t[k];
+    filter_shift_offset(false, !BIPRED, bitdepth, shift, offset);
+    int val = (sum + offset) >> shift;
+    if (BIPRED) return (int)(int16_t)val;
+    if (fy != 0) val = (int)(int16_t)val;
+    return clip3i(val, 0, maxv);
+  }
+  int sh1, off1;
+  filter_shift_offset(false, false, bitdepth, sh1, off1);
+  int acc = 0;
+#pragma unroll
+  for (int j = 0; j < NTAPS; j++) {
+    const Sample *row = r + (j - kBack) * rs;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < NTAPS; k++) sum += (int)row[k - kBack] * tx[k];
+    acc += (int)(int16_t)((sum + off1) >> sh1) * ty[j];
+  }
+  filter_shift_offset(true, !BIPRED, bitdepth, shift, offset);
+  int val = (acc + offset) >> shift;
+  if (BIPRED) return (int)(int16_t)val;
+  return clip3i((int)(int16_t)val, 0, maxv);
+}
+
+template <bool BIPRED, int NTAPS>
+__device__ __forceinline__ int affine_sample(const AffineModel &m, PlaneView rp, int cs, int px, int py, int x, int y, int bitdepth) {
+  const int bx = x / m.sbw, by = y / m.sbh;
+  const int dvx = -m.dhy, dvy = m.dhx;
+  const int hx = m.mv0x * 256 + by * (dvx * m.sbh) + bx * (m.dhx * m.sbw);
+  const int hy = m.mv0y * 256 + by * (dvy * m.sbh) + bx * (m.dhy * m.sbw);
+  const int mx = clip3i((hx + m.dhx * (m.sbw >> 1) + dvx * (m.sbh >> 1)) >> 8, m.min_x, m.max_x);
+  const int my = clip3i((hy + m.dhy * (m.sbw >> 1) + dvy * (m.sbh >> 1)) >> 8, m.min_y, m.max_y);
+  const int sh = 4 + cs, mask = (1 << sh) - 1;
+  const Sample *r = rp.base + (py + y + (my >> sh)) * rp.pitch + px + x + (mx >> sh);
+  return mc_sample<BIPRED, NTAPS>(r, rp.pitch, mx & mask, my & mask, bitdepth);
+}
+
+template <int NTAPS>
+__device__ __forceinline__ void affine_cu(const xvcb200_cu &cu, const xvcb200_affine_cu &a, int comp, int bitdepth,
+                                          const McRefs &refs, PlaneView pred) {
+  const int cs = comp ? 1 : 0;
+  const int px = cu.x >> cs, py = cu.y >> cs, w = cu.w >> cs, h = cu.h >> cs;
+  const bool l0 = cu.ref_idx[0] >= 0, l1 = cu.ref_idx[1] >= 0;
+  const int lw = 31 - __clz(w);
+  Sample *dst = pred.base + py * pred.pitch + px;
+  if (l0 && l1) {
+    const PlaneView r0 = refs.r[0][cu.ref_idx[0]].p[comp], r1 = refs.r[1][cu.ref_idx[1]].p[comp];
+    const AffineModel m0 = affine_model(cu, cs, refs.r[0][cu.ref_idx[0]].p[0].width, refs.r[0][cu.ref_idx[0]].p[0].height, a.mv[0]);
+    const AffineModel m1 = affine_model(cu, cs, refs.r[1][cu.ref_idx[1]].p[0].width, refs.r[1][cu.ref_idx[1]].p[0].height, a.mv[1]);
+    const int head = 14 - bitdepth;
+    const int shift = (head > 2 ? head : 2) + 1;
+    const int offset = (1 << (shift - 1)) + 2 * 8192;
+    const int maxv = (1 << bitdepth) - 1;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+      const int y = i >> lw, x = i & (w - 1);
+      const int p0 = affine_sample<true, NTAPS>(m0, r0, cs, px, py, x, y, bitdepth);
+      const int p1 = affine_sample<true, NTAPS>(m1, r1, cs, px, py, x, y, bitdepth);
+      dst[y * pred.pitch + x] = add_avg_one(p0, p1, offset, shift, maxv);
+    }
+  } else {
+    const int l = l1 ? 1 : 0;
+    const PlaneView rp = refs.r[l][cu.ref_idx[l]].p[comp];
+    const AffineModel m = affine_model(cu, cs, refs.r[l][cu.ref_idx[l]].p[0].width, refs.r[l][cu.ref_idx[l]].p[0].height, a.mv[l]);
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+      const int y = i >> lw, x = i & (w - 1);
+      dst[y * pred.pitch + x] = (Sample)affine_sample<false, NTAPS>(m, rp, cs, px, py, x, y, bitdepth);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) affine_mc_kernel(const xvcb200_cu *__restrict__ cus, int n_cus,
+                                                        const xvcb200_affine_cu *__restrict__ aff, int bitdepth,
+                                                        const __grid_constant__ McRefs refs, Pic3 pred) {
+  const int i = blockIdx.x / 3, comp = blockIdx.x % 3;
+  const xvcb200_affine_cu a = aff[i];
+  if (a.cu < 0 || a.cu >= n_cus) return;
+  const xvcb200_cu cu = cus[a.cu];
+  if (cu.flags & XVCB200_CU_INTRA) return;
+  if (cu.ref_idx[0] < 0 && cu.ref_idx[1] < 0) return;
+  if (comp == 0) affine_cu<8>(cu, a, comp, bitdepth, refs, pred.p[0]);
+  else affine_cu<4>(cu, a, comp, bitdepth, refs, pred.p[comp]);
+}
+
+cudaError_t launch_motion_compensate_affine(cudaStream_t s, const xvcb200_cu *d_cus, int n_cus, const xvcb200_affine_cu *d_aff,
+                                            int n, int bitdepth, const Pic3 refs[2][5], Pic3 pred) {
+  if (n <= 0) return cudaSuccess;
+  McRefs r;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) r.r[l][i] = refs[l][i];
+  g_launch_count++;
+  affine_mc_kernel<<<3 * n, 128, 0, s>>>(d_cus, n_cus, d_aff, bitdepth, r, pred);
+  return cudaGetLastError();
+}
+
 }  // namespace xvcb
