@@ -118,6 +118,42 @@ class CpuArm:
         return dt, rec.planes()
 
 
+def xvcenc_cli_sample(n_frames=9):
+    """Context number (SURVEY 8d "CPU reference timing"): the reference's own encoder application
+    (oracle/_ref/xvcenc, the unmodified sources compiled by oracle/Makefile) with its full RDO mode
+    decision, RDOQ and CABAC on a bounded sample -- configs[0]'s 352x288 at qp 32 from the same
+    synthetic generator, all host threads (frame-parallel).  A 1080p picture costs that encoder
+    ~90 core-seconds, so the named resolution does not fit a bench run.  NOT the same work as the
+    step timed above (fixed partition, QuantFast, no entropy coding): reported beside it, never
+    used for a ratio."""
+    import re
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "xvcenc")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/xvcenc not built"}
+    w, h = 352, 288
+    threads = min(64, os.cpu_count() or 1)
+    canvas = workload.synth_canvas(w, h, 1234)
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "in.yuv")
+        with open(yuv, "wb") as f:
+            for i in range(n_frames):
+                for p in workload.synth_frame(canvas, w, h, i, 8):
+                    f.write(p.astype(np.uint8).tobytes())
+        cmd = [exe, "-input-file", yuv, "-input-width", str(w), "-input-height", str(h), "-framerate", "30", "-qp", str(QP),
+               "-max-pictures", str(n_frames), "-threads", str(threads), "-output-file", os.path.join(d, "out.xvc")]
+        try:
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=300).stdout
+        except Exception as e:  # noqa: BLE001
+            return {"unavailable": repr(e)}
+    m = re.search(r"Total time:\s+([0-9.]+) s", out)       # the application's own clock (encoder_app.cc:566-568)
+    if not m:
+        return {"unavailable": "no 'Total time' line in the xvcenc output"}
+    sec = float(m.group(1))
+    return {"frames_per_s": n_frames / sec, "mpixels_per_s": n_frames * w * h / sec / 1e6, "seconds": sec, "threads": threads,
+            "sample": "xvcenc -qp %d -threads %d, %d synthetic 352x288 frames (configs[0]), default (slow) preset: full RDO + RDOQ + CABAC" % (QP, threads, n_frames)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -137,6 +173,7 @@ def run_reference(args):
                          "sample": "one full 1920x1080 picture per step, %d steps, all host threads over CUs" % args.steps},
         "e2e": {"value": mpx, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "xvcenc_cli": xvcenc_cli_sample(),
     }
     print(json.dumps(line))
 
@@ -445,12 +482,16 @@ def run_ours(args):
         arm = CpuArm()
         frames0, cus0, prm0, lam0 = picture_inputs(index_offset=0)
         t_first, rec_cpu = arm.run(frames0, cus0, prm0, lam0)
-        reps = int(min(20, max(1, 8.0 / max(t_first, 1e-3)))) if arm.kind == "reference" else 1
+        reps = int(min(20, max(1, 8.0 / max(t_first, 1e-3)))) if arm.kind == "reference" and world == 1 else 1
         times = [t_first] + [arm.run(frames0, cus0, prm0, lam0)[0] for _ in range(reps - 1)]
         sec = float(np.mean(times[1:])) if len(times) > 1 else t_first
         cpu = {"value": WIDTH * HEIGHT / sec / 1e6, "unit": "Mpixels/s", "cores": arm.cores, "kind": arm.kind,
                "sample": "%d full 1920x1080 pictures of the same step (first one untimed warm-up)" % len(times)}
         bitexact = recon_digest(rec_cpu) == recon_digest(rec_out)
+        if world == 1:
+            cpu["xvcenc_cli"] = xvcenc_cli_sample()      # whole-encoder context, see its docstring
+        else:       # the CPU baseline is an N = 1 number; at N > 1 the one CPU run above only checks bit-exactness
+            cpu = None
     except Exception as e:  # noqa: BLE001
         cpu = {"value": None, "unit": "Mpixels/s", "cores": 0, "kind": "port", "sample": "unavailable: %r" % (e,)}
 
