@@ -128,6 +128,29 @@ def affine_cus(cus, rng):
     return aff
 
 
+# Hierarchical-B sub-GOP of 8 after a key picture (POC 0), coding order, (poc, pic_type, reference POCs):
+# waves of independent pictures 8 | 4 | 2 6 | 1 3 5 7 (thread_encoder.cc:99-131).
+GOP8 = [(8, 1, (0,)), (4, 0, (0, 8)), (2, 0, (0, 4)), (6, 0, (4, 8)), (1, 0, (0, 2)), (3, 0, (2, 4)), (5, 0, (4, 6)), (7, 0, (6, 8))]
+
+
+def gop_inputs(width, height, bd, qp, seed, min_size=8):
+    """frame(poc) and inputs(poc) -> (original planes, CU array, picture parameters without slots)."""
+    canvas = workload.synth_canvas(width, height, seed)
+    lam = workload.lambda_for_qp(qp)
+    by_poc = {p[0]: p for p in GOP8}
+
+    def frame(poc):
+        return workload.synth_frame(canvas, width, height, poc, bd)
+
+    def inputs(poc):
+        _, pic_type, refs = by_poc[poc]
+        cus = workload.make_partition(width, height, seed=seed + poc, min_size=min_size, qp=qp)
+        ranges = tuple(min(64, workload.search_range_uni(poc, r)) for r in refs) + ((64,) if len(refs) == 1 else ())
+        prm = picture_params(pic_type, lam, ranges=ranges[:2], pocs=(tuple(refs) + (0,))[:2])
+        return frame(poc), cus, prm
+    return frame, inputs
+
+
 def oracle_refs(oracle, width, height, r0, r1=None):
     refs = {(0, 0): Picture(width, height, 80, r0)}
     oracle.pad_border(refs[(0, 0)])

@@ -48,3 +48,34 @@ class OracleEngine:
 
     def finish(self):
         pass
+
+
+class OracleGopEngine:
+    """One rank of sharding.FrameParallelGop computed by the C oracle; reconstructions travel as
+    gloo broadcasts of the padded planes (the CPU stand-in for xvcb200_push_slot)."""
+
+    def __init__(self, width, height, bitdepth, dist, inputs):
+        self.o = Oracle()
+        self.W, self.H, self.bd, self.dist, self.inputs = width, height, bitdepth, dist, inputs
+        self.rec = {}
+
+    def load_done(self, poc, planes):
+        self.rec[poc] = Picture(self.W, self.H, 80, planes)
+        self.o.pad_border(self.rec[poc])
+
+    def encode(self, poc, pic_type, ref_pocs):
+        cur, cus, prm = self.inputs(poc)
+        refs = {(l, 0): self.rec[r] for l, r in enumerate(ref_pocs)}
+        pred, rec = Picture(self.W, self.H, 80), Picture(self.W, self.H, 80)
+        self.o.encode_picture(Picture(self.W, self.H, 0, cur), refs, pred, rec, self.bd, cus.copy(), prm)
+        self.rec[poc] = rec
+
+    def share(self, poc, owner):
+        if poc not in self.rec:
+            self.rec[poc] = Picture(self.W, self.H, 80)
+        for c in range(3):
+            t = torch.from_numpy(self.rec[poc].full[c].view(np.uint8))       # bytes: gloo has no 16-bit integer type
+            self.dist.broadcast(t, src=owner)
+
+    def fence(self):
+        pass

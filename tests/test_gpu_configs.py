@@ -188,3 +188,19 @@ def test_peer_push_two_processes_one_gpu():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "True" in out.stdout
+
+
+def test_frame_parallel_gop_two_processes_one_gpu():
+    """BASELINE config 5's mechanism end to end: a hierarchical-B sub-GOP encoded frame-parallel by two
+    processes whose reconstructions reach each other through xvcb200_push_slot and are referenced by
+    the next wave == the serial encode (tests/run_frame_parallel_gop.py; without `same-gpu` it runs one
+    rank per GPU over NVLink)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29516", os.path.join(here, "run_frame_parallel_gop.py"), "416", "240", "same-gpu"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "serial encode: True" in out.stdout

@@ -75,3 +75,49 @@ def test_band_rows_cover_picture():
             assert bands[0][0] == 0 and bands[-1][1] == h
             assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
             assert all(y0 % 64 == 0 or y0 == h for y0, _ in bands)
+
+
+# ---------------------------------------------------------------- frame-parallel GOP (config 5)
+GW, GH = 136, 72
+
+
+def test_gop_waves():
+    waves = sharding.gop_waves(common.GOP8, done=(0,))
+    assert waves == [[8], [4], [2, 6], [1, 3, 5, 7]]
+    sub16 = [(16, 1, (0,)), (8, 0, (0, 16)), (4, 0, (0, 8)), (12, 0, (8, 16))] + \
+            [(p, 0, (p - 2, p + 2)) for p in (2, 6, 10, 14)] + [(p, 0, (p - 1, p + 1)) for p in range(1, 16, 2)]
+    assert [len(w) for w in sharding.gop_waves(sub16, done=(0,))] == [1, 1, 2, 4, 8]
+    with pytest.raises(ValueError):
+        sharding.gop_waves([(4, 0, (0, 8))], done=(0,))
+
+
+def _gop_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleGopEngine
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    frame, inputs = common.gop_inputs(GW, GH, BD, QP, 500)
+    eng = OracleGopEngine(GW, GH, BD, dist, inputs)
+    eng.load_done(0, frame(0))
+    owners = sharding.FrameParallelGop(eng, rank, world).encode(common.GOP8, done=(0,))
+    assert sorted(set(owners.values())) == list(range(min(world, 4)))
+    np.savez(os.path.join(out_dir, "gop%d.npz" % rank), **{"p%d_%d" % (poc, c): eng.rec[poc].full[c] for poc in eng.rec for c in range(3)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_frame_parallel_gop_matches_single_process(tmp_path, world):
+    """Every rank ends up with every reconstruction of the sub-GOP, equal to the serial encode."""
+    mp.spawn(_gop_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from oracle_engine import OracleGopEngine
+    frame, inputs = common.gop_inputs(GW, GH, BD, QP, 500)
+    eng = OracleGopEngine(GW, GH, BD, None, inputs)
+    eng.load_done(0, frame(0))
+    for poc, pic_type, refs in common.GOP8:
+        eng.encode(poc, pic_type, refs)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "gop%d.npz" % r))
+        for poc in eng.rec:
+            for c in range(3):
+                assert np.array_equal(z["p%d_%d" % (poc, c)], eng.rec[poc].full[c]), (r, poc, c)

@@ -224,3 +224,86 @@ class PeerExchange:
         self.ctx.wait_pushes()
         self.ctx.sync()
         self.dist.barrier()
+
+
+# ---------------------------------------------------------------------------------------------
+# Frame-parallel encoding of a GOP (BASELINE config 5): the reference's own parallel model.
+# ThreadEncoder (thread_encoder.cc:99-159) starts a picture as soon as all of its reference
+# pictures are finished, lowest temporal layer first.  With one encoder per GPU the schedule is
+# computed identically on every rank; a finished (deblocked, padded) reconstruction is pushed to
+# every other GPU, where it lands in the slot the same POC has everywhere.
+# ---------------------------------------------------------------------------------------------
+def gop_waves(pictures, done=()):
+    """pictures: [(poc, pic_type, ref_pocs), ...] in coding order; done: POCs reconstructed already.
+    Returns the waves of mutually independent pictures: a picture belongs to the first wave after
+    the waves of all of its reference pictures (a hierarchical-B sub-GOP of 16: 1, 1, 2, 4, 8)."""
+    wave_of = {p: -1 for p in done}
+    waves = []
+    for poc, _, refs in pictures:
+        missing = [r for r in refs if r not in wave_of]
+        if missing:
+            raise ValueError("picture %d references %s before it is coded" % (poc, missing))
+        k = max([wave_of[r] for r in refs], default=-1) + 1
+        wave_of[poc] = k
+        while len(waves) <= k:
+            waves.append([])
+        waves[k].append(poc)
+    return waves
+
+
+class FrameParallelGop:
+    """Runs gop_waves() across `world` ranks: picture j of a wave is encoded by rank j % world; after
+    the wave every reconstruction is shared with all ranks (engine.share) and the ranks rendezvous
+    (engine.fence) before a later wave may reference it.  `engine` does the work of one rank:
+    sharding.GpuGopEngine (libxvc_b200 + PeerExchange) or the oracle engine of the gloo tests."""
+
+    def __init__(self, engine, rank, world):
+        self.e, self.rank, self.world = engine, rank, world
+
+    def encode(self, pictures, done=()):
+        by_poc = {p[0]: p for p in pictures}
+        owners = {}
+        for wave in gop_waves(pictures, done):
+            for j, poc in enumerate(wave):
+                owners[poc] = j % self.world
+                if owners[poc] == self.rank:
+                    self.e.encode(*by_poc[poc])
+            for poc in wave:
+                self.e.share(poc, owners[poc])
+            self.e.fence()
+        return owners
+
+
+class GpuGopEngine:
+    """One rank of FrameParallelGop on a B200.  Slots: 0 original, 1 prediction, 2 levels, then one
+    reconstruction slot per POC (the same slot index on every rank, so a push lands in place).
+    inputs(poc) -> (planes of the original picture, CU array, xvcb200_picture_params without slots)."""
+
+    def __init__(self, ctx, peers, rank, pocs, inputs):
+        self.ctx, self.peers, self.rank, self.inputs = ctx, peers, rank, inputs
+        self.slot_of = {poc: 3 + i for i, poc in enumerate(pocs)}
+
+    def load_done(self, poc, planes):
+        self.ctx.upload(self.slot_of[poc], planes)
+        self.ctx.pad_border(self.slot_of[poc])
+
+    def encode(self, poc, pic_type, ref_pocs):
+        cur, cus, prm = self.inputs(poc)
+        prm = prm.copy()
+        prm["orig_slot"], prm["pred_slot"], prm["coeff_slot"], prm["rec_slot"] = 0, 1, 2, self.slot_of[poc]
+        prm["ref_slots"] = -1
+        for l, r in enumerate(ref_pocs):
+            prm["ref_slots"][0, l, 0] = self.slot_of[r]
+        self.ctx.upload(0, cur)
+        self.ctx.set_cus(cus)
+        self.ctx.encode_picture(prm, want_results=False)
+
+    def share(self, poc, owner):
+        if owner == self.rank and self.peers is not None:
+            self.peers.push(self.slot_of[poc])
+
+    def fence(self):
+        if self.peers is not None:
+            self.peers.landed()
+        else:
+            self.ctx.sync()
