@@ -341,6 +341,25 @@ typedef struct {
 int xvcb200_motion_compensate_affine(xvcb200_ctx *ctx, const xvcb200_affine_cu *aff, int n,
                                      const int32_t ref_slots[2][5], int pred_slot);
 
+/* Motion compensation with local illumination compensation (SURVEY 8f rank 4;
+ * InterPrediction::MotionCompensation for CUs with GetUseLic(), inter_prediction.cc:710-738 ->
+ * MotionCompRefList :1031-1040 -> LocalIlluminationComp / DeriveLicParams :1555-1673).  For every
+ * entry the CU `cu` of the context's CU array (cu.ref_idx / cu.mv as in xvcb200_motion_compensate)
+ * is predicted per list, a linear model pred' = clip(((scale * pred) >> 5) + offset) is fitted on
+ * the row above / column left of the block -- reference picture at the rounded full-pel MV against
+ * the CURRENT picture's reconstruction in rec_slot -- and applied; bi-prediction averages the two
+ * compensated predictions through FilterCopyBipred + AddAvgBi ("intermediate rounding", :724-729).
+ * above_x/above_y, left_x/left_y: luma position of the CU covering (x, y-4) / (x-4, y)
+ * (CodingUnit::GetCodingUnitAbove / Left, coding_unit.cc:227-234, 275-282; its position enters the
+ * model through ClipMv :1604, 1618), -1 when there is none.  The neighbours' reconstruction must
+ * be final in rec_slot: the caller owns coding order (a CTU anti-diagonal at a time, as for intra). */
+typedef struct {
+  int32_t cu;
+  int16_t above_x, above_y, left_x, left_y;
+} xvcb200_lic_cu;
+int xvcb200_motion_compensate_lic(xvcb200_ctx *ctx, const xvcb200_lic_cu *lic, int n, const int32_t ref_slots[2][5],
+                                  int rec_slot, int pred_slot);
+
 /* TransformAndReconstruct for every CU x component: residual = orig - pred, forward
  * transform, QuantFast, dequant, inverse transform, AddClip into rec_slot; levels into
  * coeff_slot; per-TU results[3*n_cus] (order: cu-major, component-minor); cbf flags are

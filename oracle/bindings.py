@@ -120,6 +120,7 @@ class Oracle:
         L.xo_pad_border.argtypes = [c_void_p]
         L.xo_full_search.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u32, c_void_p, c_void_p]
         L.xo_motion_compensate.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p]
+        L.xo_motion_compensate_lic.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
         L.xo_motion_compensate_affine.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
         L.xo_tq_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         L.xo_dequant_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int]
@@ -253,6 +254,12 @@ class Oracle:
         aff = np.ascontiguousarray(aff, dtype=abi.affine_cu_dtype)
         self.L.xo_motion_compensate_affine(ctypes.addressof(arr), bitdepth, abi.ptr(cus), abi.ptr(aff), len(aff), ctypes.byref(p))
 
+    def motion_compensate_lic(self, refs, rec, bitdepth, cus, lic, pred):
+        arr, keep = _refs_array(refs)
+        p, r = pred.c_struct(), rec.c_struct()
+        lic = np.ascontiguousarray(lic, dtype=abi.lic_cu_dtype)
+        self.L.xo_motion_compensate_lic(ctypes.addressof(arr), ctypes.byref(r), bitdepth, abi.ptr(cus), abi.ptr(lic), len(lic), ctypes.byref(p))
+
     def tq_reconstruct(self, orig, pred, rec, bitdepth, cus, intra_picture=0, table=1, off_u=0, off_v=0):
         levels = [np.zeros((orig.height[c], orig.width[c]), dtype=np.int16) for c in range(3)]
         res = np.zeros(3 * len(cus), dtype=abi.tu_result_dtype)
@@ -343,6 +350,8 @@ class Ref:
         L.xref_tz_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
         L.xref_full_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
         L.xref_motion_compensate.argtypes = [c_void_p, c_int]
+        L.xref_motion_compensate_lic.argtypes = [c_void_p, c_void_p, c_int]
+        L.xref_lic_neighbours.argtypes = [c_void_p, c_void_p, c_int]
         L.xref_motion_compensate_affine.argtypes = [c_void_p, c_void_p, c_int, c_int]
         L.xref_tq_reconstruct.argtypes = [c_void_p, c_int, c_void_p]
         L.xref_deblock_picture.argtypes = [c_void_p, c_int, c_int]
@@ -547,6 +556,16 @@ class RefSession:
     def motion_compensate_affine(self, aff, threads=1):
         aff = np.ascontiguousarray(aff, dtype=abi.affine_cu_dtype)
         self.L.xref_motion_compensate_affine(self.h, abi.ptr(aff), len(aff), threads)
+
+    def motion_compensate_lic(self, lic):
+        lic = np.ascontiguousarray(lic, dtype=abi.lic_cu_dtype)
+        self.L.xref_motion_compensate_lic(self.h, abi.ptr(lic), len(lic))
+
+    def lic_neighbours(self, cu_indices):
+        lic = np.zeros(len(cu_indices), dtype=abi.lic_cu_dtype)
+        lic["cu"] = cu_indices
+        self.L.xref_lic_neighbours(self.h, abi.ptr(lic), len(lic))
+        return lic
 
     def tq_reconstruct(self, n_cus, threads=1):
         res = np.zeros(3 * n_cus, dtype=abi.tu_result_dtype)

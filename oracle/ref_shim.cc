@@ -94,7 +94,8 @@ void ParallelFor(int n, int threads, MakeState make_state, Body body) {
       for (int i = begin; i < end; i++) body(st.get(), i);
     }
   };
-  if (threads == 1) { worker(); return; }
+  // always on fresh threads, also for threads == 1: the calling thread's Restrictions may have been
+  // changed by an encoder / decoder that ran on it before (the conformance tests do)
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; t++) pool.emplace_back(worker);
   for (auto &t : pool) t.join();
@@ -625,6 +626,42 @@ void xref_motion_compensate_affine(xref_session *s, const xvcb200_affine_cu *aff
         cu->SetUseAffine(false);
         for (int l = 0; l < 2; l++) cu->SetMv(keep[l], static_cast<RefPicList>(l));
       });
+}
+
+// LIC CUs: CodingUnit::SetUseLic(true), then the reference's own MotionCompensation
+// (LocalIlluminationComp / DeriveLicParams read s->rec, the InterPrediction's rec_pic_, around the CU).
+// Serial: DeriveLicParams looks at neighbour CUs, which no other thread may be modifying.
+void xref_motion_compensate_lic(xref_session *s, const xvcb200_lic_cu *lic, int n) {
+  EnsureInit(s);
+  const auto &simd = Simd(s->use_simd, s->bitdepth);
+  std::thread([&]() {            // fresh thread: unrestricted thread_local Restrictions (see ParallelFor)
+    InterPrediction ip(simd.inter_prediction, *s->rec, s->bitdepth);
+    for (int i = 0; i < n; i++) {
+      CodingUnit *cu = s->cus[lic[i].cu];
+      if (cu->IsIntra()) continue;
+      cu->SetUseLic(true);
+      for (int c = 0; c < 3; c++) {
+        YuvComponent comp = static_cast<YuvComponent>(c);
+        SampleBuffer pb = s->pred->GetSampleBuffer(comp, cu->GetPosX(comp), cu->GetPosY(comp));
+        ip.MotionCompensation(*cu, comp, &pb);
+      }
+      cu->SetUseLic(false);
+    }
+  }).join();
+}
+
+// What the reference sees as the CU above / left of every CU (CodingUnit::GetCodingUnitAbove / Left):
+// fills above_x/above_y/left_x/left_y of lic[i] for lic[i].cu -- checks the host-side CU map of the tests.
+void xref_lic_neighbours(xref_session *s, xvcb200_lic_cu *lic, int n) {
+  EnsureInit(s);
+  for (int i = 0; i < n; i++) {
+    const CodingUnit *cu = s->cus[lic[i].cu];
+    const CodingUnit *a = cu->GetCodingUnitAbove(), *l = cu->GetCodingUnitLeft();
+    lic[i].above_x = a ? static_cast<int16_t>(a->GetPosX(YuvComponent::kY)) : -1;
+    lic[i].above_y = a ? static_cast<int16_t>(a->GetPosY(YuvComponent::kY)) : -1;
+    lic[i].left_x = l ? static_cast<int16_t>(l->GetPosX(YuvComponent::kY)) : -1;
+    lic[i].left_y = l ? static_cast<int16_t>(l->GetPosY(YuvComponent::kY)) : -1;
+  }
 }
 
 // ---------------------------------------------------------------- T/Q/recon chain

@@ -964,6 +964,119 @@ void xo_motion_compensate_affine(const xo_picture *const refs[2][5], int bitdept
   }
 }
 
+/* ---- local illumination compensation ---------------------------
+ * InterPrediction::DeriveLicParams, inter_prediction.cc:1578-1673.  `mv` is the CLIPPED 1/16-pel
+ * MV of the CU; the neighbour rows are read from the reference picture at the MV rounded to full
+ * samples of the component and "clipped" by ClipMv with the NEIGHBOUR CU's position -- ClipMv's
+ * bounds are in 1/16 pel while the value is in full samples, as in the reference (:1604, 1618). */
+static int size_to_log2(int size) {       /* util::SizeToLog2, utils.cc:29-35 (minimum 1) */
+  int l = 1;
+  while ((1 << l) < size) l++;
+  return l;
+}
+static int msb_len(unsigned x) { int m = 0; while (x) { m++; x >>= 1; } return m; }
+
+static void lic_params(const xo_picture *ref, const xo_picture *rec, int comp, int bitdepth, const xvcb200_cu *cu,
+                       const xvcb200_lic_cu *nb, const int32_t mv[2], int *scale_out, int *offset_out) {
+  const int cs = comp ? 1 : 0, sh = 4 + cs;
+  const int px = cu->x >> cs, py = cu->y >> cs, w = cu->w >> cs, h = cu->h >> cs;
+  const int has_above = nb->above_x >= 0, has_left = nb->left_x >= 0;
+  *scale_out = 32; *offset_out = 0;
+  if (!has_above && !has_left) return;
+  const int fx = (mv[0] + (1 << (sh - 1))) >> sh, fy = (mv[1] + (1 << (sh - 1))) >> sh;
+  const int step = (w < h ? w : h) > 8 ? 2 : 1;
+  const ptrdiff_t rs = ref->stride[comp], ss = rec->stride[comp];
+  const uint16_t *rbase = ref->base[comp] + py * rs + px;
+  const uint16_t *sbase = rec->base[comp] + py * ss + px;
+  int sum_x = 0, sum_y = 0, sum_xx = 0, sum_xy = 0, nbr = 0;
+  if (has_above) {
+    int32_t c[2] = {fx, fy};
+    xo_clip_mv(nb->above_x, nb->above_y, ref->width[0], ref->height[0], c);
+    const uint16_t *r = rbase + c[0] + c[1] * rs - rs, *s = sbase - ss;
+    const int dx = step * ((w / h) > 1 ? (w / h) : 1);
+    for (int x = 0; x < w; x += dx) {
+      sum_x += r[x]; sum_y += s[x]; sum_xx += r[x] * r[x]; sum_xy += r[x] * s[x]; nbr++;
+    }
+  }
+  if (has_left) {
+    int32_t c[2] = {fx, fy};
+    xo_clip_mv(nb->left_x, nb->left_y, ref->width[0], ref->height[0], c);
+    const uint16_t *r = rbase + c[0] + c[1] * rs - 1, *s = sbase - 1;
+    const int dy = step * ((h / w) > 1 ? (h / w) : 1);
+    for (int y = 0; y < h; y += dy) {
+      const int a = r[y * rs], b = s[y * ss];
+      sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b; nbr++;
+    }
+  }
+  const int size_shift = size_to_log2(nbr);
+  const int base_shift = bitdepth + size_shift - 15 > 0 ? bitdepth + size_shift - 15 : 0;
+  const int avg_x = sum_x >> base_shift, avg_y = sum_y >> base_shift;
+  const int xx_offset = sum_xx >> 7;
+  const int avg_xy = ((sum_xy + xx_offset) >> (2 * base_shift)) << size_shift;
+  const int avg_xx = ((sum_xx + xx_offset) >> (2 * base_shift)) << size_shift;
+  const int sd_xy = avg_xy - avg_x * avg_y, sd_xx = avg_xx - avg_x * avg_x;
+  int shift_xx = msb_len((unsigned)abs(sd_xx)) - 6;
+  if (shift_xx < 0) shift_xx = 0;
+  const int shift_xy = shift_xx - 12 > 0 ? shift_xx - 12 : 0;
+  const int total_shift = 15 - 5 + shift_xx - shift_xy;
+  const int sd_xy_s = sd_xy >> shift_xy;
+  int sd_xx_s = sd_xx >> shift_xx;
+  sd_xx_s = sd_xx_s < 0 ? 0 : sd_xx_s > 63 ? 63 : sd_xx_s;
+  if (sd_xx_s == 0) return;
+  const int sd_xx_scaled = ((1 << 15) + sd_xx_s / 2) / sd_xx_s;
+  int scale = (sd_xy_s * sd_xx_scaled) >> total_shift;
+  scale = scale < 0 ? 0 : scale > 128 ? 128 : scale;
+  int offset = (sum_y - ((scale * sum_x) >> 5) + (1 << (size_shift - 1))) >> size_shift;
+  const int lo = -(1 << (bitdepth - 1)), hi = (1 << (bitdepth - 1)) - 1;
+  *scale_out = scale;
+  *offset_out = offset < lo ? lo : offset > hi ? hi : offset;
+}
+
+/* MotionCompRefList with post_filter (:1024-1040): translational prediction into Samples, then
+ * LocalIlluminationComp (:1555-1576) = SampleBuffer::AddLinearModel (sample_buffer.h:108-122). */
+static void mc_block_lic(const xo_picture *ref, const xo_picture *rec, int comp, int bitdepth, const xvcb200_cu *cu,
+                         const xvcb200_lic_cu *nb, const int32_t mv_raw[2], uint16_t *pred, ptrdiff_t ps) {
+  int32_t mv[2] = {mv_raw[0], mv_raw[1]};
+  xo_clip_mv(cu->x, cu->y, ref->width[0], ref->height[0], mv);
+  mc_block(ref, comp, bitdepth, cu, mv, 0, pred, ps);
+  int scale, offset;
+  lic_params(ref, rec, comp, bitdepth, cu, nb, mv, &scale, &offset);
+  const int cs = comp ? 1 : 0, w = cu->w >> cs, h = cu->h >> cs, maxv = (1 << bitdepth) - 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const int v = ((scale * pred[y * ps + x]) >> 5) + offset;
+      pred[y * ps + x] = (uint16_t)(v < 0 ? 0 : v > maxv ? maxv : v);
+    }
+}
+
+/* InterPrediction::MotionCompensation (:710-738) for CUs with use_lic */
+void xo_motion_compensate_lic(const xo_picture *const refs[2][5], const xo_picture *rec, int bitdepth,
+                              const xvcb200_cu *cus, const xvcb200_lic_cu *lic, int n_lic, xo_picture *pred) {
+  int16_t t0[64 * 64], t1[64 * 64];
+  uint16_t tmp[64 * 64];
+  const int head = K_INTERNAL_PREC - bitdepth;
+  for (int i = 0; i < n_lic; i++) {
+    const xvcb200_cu *cu = &cus[lic[i].cu];
+    const int l0 = cu->ref_idx[0] >= 0, l1 = cu->ref_idx[1] >= 0;
+    if ((cu->flags & XVCB200_CU_INTRA) || (!l0 && !l1)) continue;
+    for (int c = 0; c < 3; c++) {
+      const int cs = c ? 1 : 0, w = cu->w >> cs, h = cu->h >> cs;
+      uint16_t *dst = pred->base[c] + (cu->y >> cs) * pred->stride[c] + (cu->x >> cs);
+      if (l0 && l1) {      /* bi-prediction with intermediate rounding, :724-729 */
+        mc_block_lic(refs[0][cu->ref_idx[0]], rec, c, bitdepth, cu, &lic[i], cu->mv[0], tmp, 64);
+        xo_filter_copy_bipred(w, h, K_INTERNAL_OFFSET, head, tmp, 64, t0, 64);
+        mc_block_lic(refs[1][cu->ref_idx[1]], rec, c, bitdepth, cu, &lic[i], cu->mv[1], tmp, 64);
+        xo_filter_copy_bipred(w, h, K_INTERNAL_OFFSET, head, tmp, 64, t1, 64);
+        const int shift = (head > 2 ? head : 2) + 1;
+        xo_add_avg(w, h, (1 << (shift - 1)) + 2 * K_INTERNAL_OFFSET, shift, bitdepth, t0, 64, t1, 64, dst, pred->stride[c]);
+      } else {
+        const int l = l1 ? 1 : 0;
+        mc_block_lic(refs[l][cu->ref_idx[l]], rec, c, bitdepth, cu, &lic[i], cu->mv[l], dst, pred->stride[c]);
+      }
+    }
+  }
+}
+
 /* ===================================================================================
  * Residual coding chain
  * =================================================================================== */

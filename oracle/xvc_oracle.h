@@ -92,6 +92,8 @@ void xo_motion_compensate(const xo_picture *const refs[2][5], int bitdepth, cons
 /* levels: picture-shaped tight int16 planes (stride = plane width) */
 void xo_motion_compensate_affine(const xo_picture *const refs[2][5], int bitdepth, const xvcb200_cu *cus,
                                  const xvcb200_affine_cu *aff, int n_aff, xo_picture *pred);
+void xo_motion_compensate_lic(const xo_picture *const refs[2][5], const xo_picture *rec, int bitdepth,
+                              const xvcb200_cu *cus, const xvcb200_lic_cu *lic, int n_lic, xo_picture *pred);
 void xo_tq_reconstruct(const xo_picture *orig, const xo_picture *pred, xo_picture *rec, int16_t *const levels[3],
                        int bitdepth, xvcb200_cu *cus, int n, int intra_picture, int table, int off_u, int off_v,
                        xvcb200_tu_result *results);

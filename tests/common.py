@@ -128,6 +128,24 @@ def affine_cus(cus, rng):
     return aff
 
 
+def lic_cus(cus, width, height, indices=None):
+    """xvcb200_lic_cu entries: the CU covering (x, y-4) / (x-4, y) on a 4x4 map of the picture
+    (CodingUnit::GetCodingUnitAbove / Left, coding_unit.cc:227-234, 275-282, with every CU of the
+    array present); checked against the reference in tests/test_oracle_vs_ref.py."""
+    cmap = np.full((height // 4, width // 4), -1, dtype=np.int32)
+    for i, cu in enumerate(cus):
+        cmap[cu["y"] // 4:(cu["y"] + cu["h"]) // 4, cu["x"] // 4:(cu["x"] + cu["w"]) // 4] = i
+    idx = [i for i in (range(len(cus)) if indices is None else indices)
+           if not (cus[i]["flags"] & abi.CU_INTRA) and (cus[i]["ref_idx"][0] >= 0 or cus[i]["ref_idx"][1] >= 0)]
+    lic = np.zeros(len(idx), dtype=abi.lic_cu_dtype)
+    for k, i in enumerate(idx):
+        x, y = int(cus[i]["x"]), int(cus[i]["y"])
+        a = cmap[y // 4 - 1, x // 4] if y > 0 else -1
+        l = cmap[y // 4, x // 4 - 1] if x > 0 else -1
+        lic[k] = (i, cus[a]["x"] if a >= 0 else -1, cus[a]["y"] if a >= 0 else -1, cus[l]["x"] if l >= 0 else -1, cus[l]["y"] if l >= 0 else -1)
+    return lic
+
+
 # Hierarchical-B sub-GOP of 8 after a key picture (POC 0), coding order, (poc, pic_type, reference POCs):
 # waves of independent pictures 8 | 4 | 2 6 | 1 3 5 7 (thread_encoder.cc:99-131).
 GOP8 = [(8, 1, (0,)), (4, 0, (0, 8)), (2, 0, (0, 4)), (6, 0, (4, 8)), (1, 0, (0, 2)), (3, 0, (2, 4)), (5, 0, (4, 6)), (7, 0, (6, 8))]

@@ -28,3 +28,9 @@ def test_affine_golden_gpu():
     """Reference MotionCompAffine outputs (tests/golden/xvc_affine_golden.npz) == xvcb200_motion_compensate_affine."""
     import affine_golden
     affine_golden.replay(affine_golden.gpu_backend())
+
+
+def test_lic_golden_gpu():
+    """Reference LocalIlluminationComp outputs (tests/golden/xvc_lic_golden.npz) == xvcb200_motion_compensate_lic."""
+    import affine_golden
+    affine_golden.replay_lic(affine_golden.gpu_lic_backend())

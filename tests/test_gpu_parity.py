@@ -318,6 +318,36 @@ def test_motion_compensate_affine(oracle, bd):
         ctx.motion_compensate_affine(bad, {(0, 0): 1, (1, 0): 2}, 3)
 
 
+@pytest.mark.parametrize("bd,content", [(8, "synth"), (10, "random"), (12, "synth")])
+def test_motion_compensate_lic(oracle, bd, content):
+    """xvcb200_motion_compensate_lic == MotionCompensation with use_lic (oracle pinned against the
+    reference in test_oracle_vs_ref.py::test_motion_compensate_lic), bit for bit; a subset of the CUs
+    uses LIC, the others keep their translational prediction."""
+    width, height = 200, 136
+    cur, r0, r1 = common.frames(width, height, bd, 138, content)
+    rng = np.random.default_rng(139)
+    cus = common.mc_cus(width, height, rng, 12, min_size=4)
+    rec_planes = [np.clip(p.astype(np.int32) * 7 // 8 + (3 << (bd - 8)) + rng.integers(-2, 3, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16)
+                  for p in cur]
+    ctx = lib.Context(width, height, bd, num_slots=5)
+    for slot, f in ((1, r0), (2, r1)):
+        ctx.upload(slot, f)
+        ctx.pad_border(slot)
+    ctx.upload(4, rec_planes)
+    ctx.set_cus(cus)
+    lic = common.lic_cus(cus, width, height, indices=[i for i in range(len(cus)) if i % 4 != 3])
+    assert len(lic) >= 20
+    ctx.motion_compensate({(0, 0): 1, (1, 0): 2}, 3)
+    ctx.motion_compensate_lic(lic, {(0, 0): 1, (1, 0): 2}, 4, 3)
+    refs = common.oracle_refs(oracle, width, height, r0, r1)
+    pred = Picture(width, height, 80)
+    oracle.motion_compensate(refs, bd, cus, pred)
+    oracle.motion_compensate_lic(refs, Picture(width, height, 80, rec_planes), bd, cus, lic, pred)
+    for c, p in enumerate(ctx.download(3)):
+        assert np.array_equal(p, pred.plane(c)), c
+    ctx.close()
+
+
 @pytest.mark.parametrize("bd,qp,min_size", [(10, 32, 4), (10, 22, 8), (8, 37, 4), (12, 27, 8)])
 def test_tq_reconstruct(oracle, bd, qp, min_size):
     width, height = 200, 136

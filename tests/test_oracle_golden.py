@@ -35,3 +35,9 @@ def test_affine_golden_oracle(oracle):
     restatement."""
     import affine_golden
     affine_golden.replay(affine_golden.oracle_backend(oracle))
+
+
+def test_lic_golden_oracle(oracle):
+    """tests/golden/xvc_lic_golden.npz (reference LocalIlluminationComp outputs) replayed against the C restatement."""
+    import affine_golden
+    affine_golden.replay_lic(affine_golden.oracle_lic_backend(oracle))

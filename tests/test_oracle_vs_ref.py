@@ -387,6 +387,34 @@ def test_motion_compensate_affine(oracle, ref, bd, simd):
     assert not np.array_equal(plain.plane(0), pred.plane(0))
 
 
+@pytest.mark.parametrize("bd,content", [(8, "synth"), (10, "synth"), (10, "random"), (12, "random")])
+def test_motion_compensate_lic(oracle, ref, bd, content):
+    """LocalIlluminationComp / DeriveLicParams (inter_prediction.cc:1555-1673) through the reference's own
+    MotionCompensation on CUs with SetUseLic(true): uni-predicted and bi-predicted ("intermediate
+    rounding"), all three components, blocks at the picture borders (one or no neighbour)."""
+    width, height = 200, 136
+    s, orig, refs, lam = _make(ref, oracle, width, height, bd, 48, content=content, simd=0)
+    rng = np.random.default_rng(49)
+    cus = common.mc_cus(width, height, rng, 10, min_size=4)
+    cur = [np.ascontiguousarray(orig.plane(c)) for c in range(3)]
+    # "reconstruction" of the current picture around the CUs: the original with a brightness change
+    # (so that the model has something to find) plus noise
+    rec_planes = [np.clip(p.astype(np.int32) * 7 // 8 + (3 << (bd - 8)) + rng.integers(-2, 3, size=p.shape), 0, (1 << bd) - 1).astype(np.uint16) for p in cur]
+    s.set_rec(rec_planes)
+    s.set_cus(cus)
+    lic = common.lic_cus(cus, width, height)
+    assert np.array_equal(lic, s.lic_neighbours(lic["cu"]))          # the host-side neighbour map is the reference's
+    s.motion_compensate(threads=2)
+    s.motion_compensate_lic(lic)
+    rec = Picture(width, height, 80, rec_planes)
+    pred, plain = Picture(width, height, 80), Picture(width, height, 80)
+    oracle.motion_compensate(refs, bd, cus, plain)
+    oracle.motion_compensate_lic(refs, rec, bd, cus, lic, pred)
+    for c, p in enumerate(s.get_pred()):
+        assert np.array_equal(p, pred.plane(c)), c
+    assert not np.array_equal(plain.plane(0), pred.plane(0))
+
+
 @pytest.mark.parametrize("bd,qp", [(10, 32), (10, 22), (8, 37)])
 def test_tq_reconstruct(oracle, ref, bd, qp):
     width, height = 136, 72

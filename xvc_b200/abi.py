@@ -21,6 +21,8 @@ cu_dtype = np.dtype([
 
 affine_cu_dtype = np.dtype([("cu", "<i4"), ("mv", "<i4", (2, 3, 2))], align=True)    # xvcb200_affine_cu
 
+lic_cu_dtype = np.dtype([("cu", "<i4"), ("above_x", "<i2"), ("above_y", "<i2"), ("left_x", "<i2"), ("left_y", "<i2")], align=True)    # xvcb200_lic_cu
+
 me_job_dtype = np.dtype([
     ("cu", "<i4"), ("ref_slot", "<i4"), ("search_range", "<i4"), ("mvp", "<i4", (2,)),
     ("prev", "<i4", (2,)), ("list", "<i4"),

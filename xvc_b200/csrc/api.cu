@@ -405,6 +405,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   xvcb200_me_job *d_jobs = nullptr; xvcb200_me_result *d_me = nullptr; xvcb200_tu_result *d_tu = nullptr;
   int jobs_cap = 0, me_cap = 0, tu_res_cap = 0;
   xvcb200_affine_cu *d_affine = nullptr; int affine_cap = 0;
+  xvcb200_lic_cu *d_lic = nullptr; int lic_cap = 0;
   // TZ search job groups (jobs sharing a reference picture and a CTU share one staged window)
   std::vector<xvcb200_cu> h_cus;              // host copy of the CU array (set_cus)
   int *d_job_index = nullptr; int job_index_cap = 0;
@@ -586,7 +587,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   for (cudaEvent_t e : c->ex.dl_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
-  cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine);
+  cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
   if (c->ex.fork_ev) cudaEventDestroy(c->ex.fork_ev);
@@ -1230,6 +1231,27 @@ int xvcb200_motion_compensate_affine(xvcb200_ctx *ctx, const xvcb200_affine_cu *
   refs_from_slots(c, ref_slots, refs);
   c->check(launch_motion_compensate_affine(c->stream, c->d_cus, c->n_cus, c->ex.d_affine, n, c->bitdepth, refs, pic3(c, pred_slot)),
            "motion_compensate_affine");
+  return c->status;
+}
+
+int xvcb200_motion_compensate_lic(xvcb200_ctx *ctx, const xvcb200_lic_cu *lic, int n, const int32_t ref_slots[2][5], int rec_slot,
+                                  int pred_slot) {
+  if (!slot_ok(ctx, pred_slot) || !slot_ok(ctx, rec_slot) || !ref_slots || n < 0 || (n > 0 && !lic)) return XVCB200_INVALID_ARGUMENT;
+  if (n == 0) return XVCB200_OK;
+  CtxFull *c = full(ctx);
+  for (int i = 0; i < n; i++)
+    if (lic[i].cu < 0 || lic[i].cu >= c->n_cus) return XVCB200_INVALID_ARGUMENT;
+  if (!ensure(c, &c->ex.d_lic, &c->ex.lic_cap, n)) return c->status;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) join_upload_slot(c, ref_slots[l][i]);
+  join_upload_slot(c, rec_slot);
+  join_downloads(c, pred_slot);
+  if (!c->check(cudaMemcpyAsync(c->ex.d_lic, lic, sizeof(*lic) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "lic upload"))
+    return c->status;
+  Pic3 refs[2][5];
+  refs_from_slots(c, ref_slots, refs);
+  c->check(launch_motion_compensate_lic(c->stream, c->d_cus, c->n_cus, c->ex.d_lic, n, c->bitdepth, refs, pic3(c, rec_slot),
+                                        pic3(c, pred_slot)), "motion_compensate_lic");
   return c->status;
 }
 

@@ -320,4 +320,146 @@ cudaError_t launch_motion_compensate_affine(cudaStream_t s, const xvcb200_cu *d_
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- motion compensation with LIC
+// InterPrediction::LocalIlluminationComp / DeriveLicParams (inter_prediction.cc:1555-1673).  One CTA
+// per (entry, component).  Warp 0 gathers the <= 64 neighbour pairs of each list in use (row above,
+// column left: reference picture at the rounded full-pel MV against the current reconstruction),
+// reduces the four sums with shuffles, lane 0 derives (scale, offset) with the reference's integer
+// recipe; then every thread predicts its samples (mc_sample, as the affine kernel) and applies
+// the model -- bi-prediction through FilterCopyBipred + AddAvgBi on the two compensated samples.
+struct LicModel { int scale, offset; };
+
+__device__ __forceinline__ int size_to_log2_dev(int size) { int l = 1; while ((1 << l) < size) l++; return l; }
+
+// all 32 lanes of one warp
+__device__ __forceinline__ LicModel lic_derive(const xvcb200_cu &cu, const xvcb200_lic_cu &nb, int cs, int bitdepth, PlaneView rp,
+                                               int pic_w, int pic_h, PlaneView rec, int mvx, int mvy, int lane) {
+  LicModel m; m.scale = 32; m.offset = 0;
+  const bool has_above = nb.above_x >= 0, has_left = nb.left_x >= 0;
+  if (!has_above && !has_left) return m;
+  const int sh = 4 + cs;
+  const int px = cu.x >> cs, py = cu.y >> cs, w = cu.w >> cs, h = cu.h >> cs;
+  const int fx = (mvx + (1 << (sh - 1))) >> sh, fy = (mvy + (1 << (sh - 1))) >> sh;
+  const int step = min(w, h) > 8 ? 2 : 1;
+  const int per_side = min(w, h) / step;                 // w / dx == h / dy == min(w, h) / step
+  const Sample *rbase = rp.base + py * rp.pitch + px;
+  const Sample *sbase = rec.base + py * rec.pitch + px;
+  int sum_x = 0, sum_y = 0, sum_xx = 0, sum_xy = 0, nbr = 0;
+  if (has_above) {
+    int cx = fx, cy = fy;
+    clip_mv(nb.above_x, nb.above_y, pic_w, pic_h, cx, cy);       // bounds in 1/16 pel on a full-sample value, as the reference
+    const Sample *r = rbase + cx + (cy - 1) * rp.pitch, *q = sbase - rec.pitch;
+    const int dx = step * max(1, w / h);
+    for (int k = lane; k < per_side; k += 32) {
+      const int a = r[k * dx], b = q[k * dx];
+      sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b;
+    }
+    nbr += per_side;
+  }
+  if (has_left) {
+    int cx = fx, cy = fy;
+    clip_mv(nb.left_x, nb.left_y, pic_w, pic_h, cx, cy);
+    const Sample *r = rbase + cx + cy * rp.pitch - 1, *q = sbase - 1;
+    const int dy = step * max(1, h / w);
+    for (int k = lane; k < per_side; k += 32) {
+      const int a = r[k * dy * rp.pitch], b = q[k * dy * rec.pitch];
+      sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b;
+    }
+    nbr += per_side;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    sum_x += __shfl_xor_sync(XVCB_FULL, sum_x, o); sum_y += __shfl_xor_sync(XVCB_FULL, sum_y, o);
+    sum_xx += __shfl_xor_sync(XVCB_FULL, sum_xx, o); sum_xy += __shfl_xor_sync(XVCB_FULL, sum_xy, o);
+  }
+  const int size_shift = size_to_log2_dev(nbr);
+  const int base_shift = max(0, bitdepth + size_shift - 15);
+  const int avg_x = sum_x >> base_shift, avg_y = sum_y >> base_shift;
+  const int xx_offset = sum_xx >> 7;
+  const int avg_xy = ((sum_xy + xx_offset) >> (2 * base_shift)) << size_shift;
+  const int avg_xx = ((sum_xx + xx_offset) >> (2 * base_shift)) << size_shift;
+  const int sd_xy = avg_xy - avg_x * avg_y, sd_xx = avg_xx - avg_x * avg_x;
+  const int shift_xx = max(0, (32 - __clz(abs(sd_xx))) - 6);
+  const int shift_xy = max(0, shift_xx - 12);
+  const int total_shift = 15 - 5 + shift_xx - shift_xy;
+  const int sd_xy_s = sd_xy >> shift_xy;
+  const int sd_xx_s = clip3i(sd_xx >> shift_xx, 0, 63);
+  if (sd_xx_s == 0) return m;
+  const int sd_xx_scaled = ((1 << 15) + sd_xx_s / 2) / sd_xx_s;
+  m.scale = clip3i((sd_xy_s * sd_xx_scaled) >> total_shift, 0, 128);
+  const int offset = (sum_y - ((m.scale * sum_x) >> 5) + (1 << (size_shift - 1))) >> size_shift;
+  m.offset = clip3i(offset, -(1 << (bitdepth - 1)), (1 << (bitdepth - 1)) - 1);
+  return m;
+}
+
+template <int NTAPS>
+__device__ __forceinline__ void lic_cu(const xvcb200_cu &cu, const xvcb200_lic_cu &nb, int comp, int bitdepth, const McRefs &refs,
+                                       PlaneView rec, PlaneView pred, LicModel *s_model) {
+  const int cs = comp ? 1 : 0, sh = 4 + cs, mask = (1 << sh) - 1;
+  const int px = cu.x >> cs, py = cu.y >> cs, w = cu.w >> cs, h = cu.h >> cs;
+  const int lw = 31 - __clz(w);
+  const int maxv = (1 << bitdepth) - 1;
+  int mvx[2], mvy[2];
+  PlaneView rp[2];
+#pragma unroll
+  for (int l = 0; l < 2; l++) {
+    if (cu.ref_idx[l] < 0) continue;
+    rp[l] = refs.r[l][cu.ref_idx[l]].p[comp];
+    const PlaneView rl = refs.r[l][cu.ref_idx[l]].p[0];
+    mvx[l] = cu.mv[l][0]; mvy[l] = cu.mv[l][1];
+    clip_mv(cu.x, cu.y, rl.width, rl.height, mvx[l], mvy[l]);
+    if (threadIdx.x < 32) {
+      const LicModel m = lic_derive(cu, nb, cs, bitdepth, rp[l], rl.width, rl.height, rec, mvx[l], mvy[l], threadIdx.x);
+      if (threadIdx.x == 0) s_model[l] = m;
+    }
+  }
+  __syncthreads();
+  Sample *dst = pred.base + py * pred.pitch + px;
+  const bool l0 = cu.ref_idx[0] >= 0, l1 = cu.ref_idx[1] >= 0;
+  const int head = 14 - bitdepth;
+  for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+    const int y = i >> lw, x = i & (w - 1);
+    int v[2] = {0, 0};
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      if (cu.ref_idx[l] < 0) continue;
+      const Sample *r = rp[l].base + (py + y + (mvy[l] >> sh)) * rp[l].pitch + px + x + (mvx[l] >> sh);
+      const int p = mc_sample<false, NTAPS>(r, rp[l].pitch, mvx[l] & mask, mvy[l] & mask, bitdepth);
+      v[l] = clip3i(((s_model[l].scale * p) >> 5) + s_model[l].offset, 0, maxv);     // AddLinearModel, sample_buffer.h:108-122
+    }
+    if (l0 && l1) {
+      const int a = (int)(int16_t)((int16_t)(v[0] << head) - (int16_t)8192);         // FilterCopyBipred_c, cc:1462-1473
+      const int b = (int)(int16_t)((int16_t)(v[1] << head) - (int16_t)8192);
+      const int shift = (head > 2 ? head : 2) + 1;
+      dst[y * pred.pitch + x] = add_avg_one(a, b, (1 << (shift - 1)) + 2 * 8192, shift, maxv);
+    } else {
+      dst[y * pred.pitch + x] = (Sample)v[l1 ? 1 : 0];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) lic_mc_kernel(const xvcb200_cu *__restrict__ cus, int n_cus, const xvcb200_lic_cu *__restrict__ lic,
+                                                     int bitdepth, const __grid_constant__ McRefs refs, Pic3 rec, Pic3 pred) {
+  __shared__ LicModel s_model[2];
+  const int i = blockIdx.x / 3, comp = blockIdx.x % 3;
+  const xvcb200_lic_cu nb = lic[i];
+  if (nb.cu < 0 || nb.cu >= n_cus) return;
+  const xvcb200_cu cu = cus[nb.cu];
+  if (cu.flags & XVCB200_CU_INTRA) return;
+  if (cu.ref_idx[0] < 0 && cu.ref_idx[1] < 0) return;
+  if (comp == 0) lic_cu<8>(cu, nb, comp, bitdepth, refs, rec.p[0], pred.p[0], s_model);
+  else lic_cu<4>(cu, nb, comp, bitdepth, refs, rec.p[comp], pred.p[comp], s_model);
+}
+
+cudaError_t launch_motion_compensate_lic(cudaStream_t s, const xvcb200_cu *d_cus, int n_cus, const xvcb200_lic_cu *d_lic, int n,
+                                         int bitdepth, const Pic3 refs[2][5], Pic3 rec, Pic3 pred) {
+  if (n <= 0) return cudaSuccess;
+  McRefs r;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) r.r[l][i] = refs[l][i];
+  g_launch_count++;
+  lic_mc_kernel<<<3 * n, 128, 0, s>>>(d_cus, n_cus, d_lic, bitdepth, r, rec, pred);
+  return cudaGetLastError();
+}
+
 }  // namespace xvcb

@@ -100,6 +100,8 @@ cudaError_t launch_block_interp(cudaStream_t s, int chroma, int bipred, int w, i
                                 const Sample *ref, int rs, void *pred, int ps);
 cudaError_t launch_motion_compensate(cudaStream_t s, const xvcb200_cu *d_cus, int n, int bitdepth,
                                      const Pic3 refs[2][5], Pic3 pred);
+cudaError_t launch_motion_compensate_lic(cudaStream_t s, const xvcb200_cu *d_cus, int n_cus, const xvcb200_lic_cu *d_lic, int n,
+                                         int bitdepth, const Pic3 refs[2][5], Pic3 rec, Pic3 pred);
 cudaError_t launch_motion_compensate_affine(cudaStream_t s, const xvcb200_cu *d_cus, int n_cus, const xvcb200_affine_cu *d_aff,
                                             int n, int bitdepth, const Pic3 refs[2][5], Pic3 pred);
 

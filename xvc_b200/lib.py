@@ -36,7 +36,7 @@ EXPORTS = [
     "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus",
     "xvcb200_upload_picture_async", "xvcb200_download_picture_async", "xvcb200_download_coeff_async",
     "xvcb200_get_cus_async", "xvcb200_sync_copies", "xvcb200_wait_download",
-    "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_tq_reconstruct",
+    "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_motion_compensate_lic", "xvcb200_tq_reconstruct",
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
     "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan",
@@ -116,6 +116,7 @@ def load():
     L.xvcb200_full_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
     L.xvcb200_motion_compensate.argtypes = [c_void_p, c_void_p, c_int]
     L.xvcb200_motion_compensate_affine.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int]
+    L.xvcb200_motion_compensate_lic.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int]
     L.xvcb200_tq_reconstruct.argtypes = [c_void_p] + [c_int] * 9 + [c_void_p]
     L.xvcb200_dequant_reconstruct.argtypes = [c_void_p] + [c_int] * 6
     L.xvcb200_deblock_picture.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
@@ -455,6 +456,12 @@ class Context:
         aff = np.ascontiguousarray(aff, dtype=abi.affine_cu_dtype)
         arr = self._ref_slots(ref_slots)
         self._ok(self.L.xvcb200_motion_compensate_affine(self.h, abi.ptr(aff), len(aff), abi.ptr(arr), pred_slot))
+
+    def motion_compensate_lic(self, lic, ref_slots, rec_slot, pred_slot):
+        """lic: abi.lic_cu_dtype array (CU index + position of the CU above / left, -1 = none)."""
+        lic = np.ascontiguousarray(lic, dtype=abi.lic_cu_dtype)
+        arr = self._ref_slots(ref_slots)
+        self._ok(self.L.xvcb200_motion_compensate_lic(self.h, abi.ptr(lic), len(lic), abi.ptr(arr), rec_slot, pred_slot))
 
     def tq_reconstruct(self, orig_slot, pred_slot, rec_slot, coeff_slot, intra_picture=0, table=1, off_u=0, off_v=0):
         res = np.zeros(3 * self.n_cus, dtype=abi.tu_result_dtype)
