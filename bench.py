@@ -129,6 +129,8 @@ def xvcenc_cli_sample(n_frames=9):
     import re
     import tempfile
     exe = os.path.join(ROOT, "oracle", "_ref", "xvcenc")
+    if os.environ.get("XVCB_BENCH_SKIP_XVCENC"):
+        return {"unavailable": "skipped (XVCB_BENCH_SKIP_XVCENC)"}
     if not os.path.exists(exe):
         return {"unavailable": "oracle/_ref/xvcenc not built"}
     w, h = 352, 288

@@ -1,0 +1,33 @@
+"""bench.py's contract on the CPU side: the file compiles, and the reference arm (the reference's own
+CPU implementation of the step through oracle/_ref, the one leg of bench.py that needs no GPU) prints
+one JSON line with the keys the driver reads."""
+import json
+import os
+import py_compile
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_compiles():
+    py_compile.compile(os.path.join(ROOT, "bench.py"), doraise=True)
+    py_compile.compile(os.path.join(ROOT, "__graft_entry__.py"), doraise=True)
+
+
+def test_reference_arm_line():
+    from oracle import bindings
+    if not bindings.have_ref():
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, XVCB_BENCH_SKIP_XVCENC="1")      # the CLI context sample takes ~15 s; not part of the contract
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpixels/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["workload"].startswith("1920x1080")
