@@ -52,7 +52,8 @@ void xvcb200_clear_error(void);
 uint64_t xvcb200_launch_count(void);
 const char *xvcb200_version(void);
 /* sizeof() of the structs below as compiled (0 cu, 1 me_job, 2 me_result, 3 fullsearch_job,
- * 4 tu_result, 5 picture_params, 6 plane_geom, 7 qp) -- lets bindings verify their layout */
+ * 4 tu_result, 5 picture_params, 6 plane_geom, 7 qp, 8 intra_job, 9 affine_cu, 10 lic_cu) -- lets
+ * bindings verify their layout */
 int xvcb200_abi_sizeof(int which);
 
 /* ------------------------------------------------------------------------------------

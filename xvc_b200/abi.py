@@ -75,6 +75,8 @@ ABI_STRUCTS = {
     6: ("xvcb200_plane_geom", plane_geom_dtype),
     7: ("xvcb200_qp", qp_dtype),
     8: ("xvcb200_intra_job", intra_job_dtype),
+    9: ("xvcb200_affine_cu", affine_cu_dtype),
+    10: ("xvcb200_lic_cu", lic_cu_dtype),
 }
 
 

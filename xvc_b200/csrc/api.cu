@@ -139,6 +139,8 @@ int xvcb200_abi_sizeof(int which) {
     case 6: return (int)sizeof(xvcb200_plane_geom);
     case 7: return (int)sizeof(xvcb200_qp);
     case 8: return (int)sizeof(xvcb200_intra_job);
+    case 9: return (int)sizeof(xvcb200_affine_cu);
+    case 10: return (int)sizeof(xvcb200_lic_cu);
     default: return -1;
   }
 }
