@@ -64,7 +64,8 @@ def recon_digest(planes):
 
 
 def config_dict(n_cus, extra=None):
-    cfg = {"workload": "1920x1080 synthetic YUV420 qp32, ME+transform+deblock (configs[1])",
+    cfg = {"workload": "1920x1080 synthetic YUV420 qp32, ME+transform+deblock (configs[1])" if (WIDTH, HEIGHT, QP) == (1920, 1080, 32)
+           else "%dx%d synthetic YUV420 qp%d, ME+transform+deblock (context run, not the metric's configuration)" % (WIDTH, HEIGHT, QP),
            "width": WIDTH, "height": HEIGHT, "bitdepth_internal": BITDEPTH, "qp": QP,
            "picture": "bi-predicted, 2 reference pictures (POC %d, refs %d/%d), search range %d" % (
                POC, REF_POCS[0], REF_POCS[1], workload.search_range_uni(POC, REF_POCS[0], SUB_GOP)),
@@ -457,7 +458,7 @@ def run_ours(args):
     import glob
     tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), key=os.path.getmtime)
     tpath = tpaths[-1] if tpaths else ""      # newest ncu --set full capture of the dominant kernel
-    if tpath:
+    if tpath and (WIDTH, HEIGHT) == (1920, 1080):      # the capture is of the 1080p step
         tj = json.load(open(tpath))
         if tj.get("kernel", "").startswith(dom):
             traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
@@ -528,7 +529,15 @@ def main():
     ap.add_argument("--distinct-pictures", action="store_true", help="N>1: rank r encodes picture r of the sequence instead of picture 0")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N>1: how finished reconstructions reach the other GPUs (copy-engine pushes over CUDA IPC, or NCCL all-gather)")
+    ap.add_argument("--size", default=None, metavar="WxH[@QP]",
+                    help="context runs only (DESIGN.md table): another picture size / qp, e.g. 3840x2160@27, 7680x4320; the "
+                         "default (and the only bench line the metric is quoted on) is 1920x1080@32")
     args = ap.parse_args()
+    if args.size:
+        global WIDTH, HEIGHT, QP
+        wh, _, q = args.size.partition("@")
+        WIDTH, HEIGHT = (int(v) for v in wh.lower().split("x"))
+        QP = int(q) if q else QP
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
