@@ -204,3 +204,20 @@ def test_frame_parallel_gop_two_processes_one_gpu():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "serial encode: True" in out.stdout
+
+
+def test_ipc_open_failure_is_not_sticky():
+    """A peer arena that cannot be opened (here: a handle that names nothing) is reported to the caller
+    without poisoning the context: bench.py / sharding.PeerExchange then fall back to the NCCL exchange."""
+    width, height, bd = 64, 64, 10
+    ctx = lib.Context(width, height, bd, num_slots=1)
+    with pytest.raises(lib.XvcB200Error):
+        ctx.ipc_open_peer(bytes(64))
+    cur = common.frames(width, height, bd, 3)[0]
+    ctx.upload(0, cur)
+    ctx.pad_border(0)
+    ctx.push_slot(0)          # no peers: a no-op
+    ctx.wait_pushes()
+    ctx.sync()
+    assert np.array_equal(ctx.download(0)[0], cur[0])
+    ctx.close()
