@@ -304,7 +304,9 @@ class Context:
 
     def _ok(self, st):
         if st != 0:
-            raise XvcB200Error("xvc_b200 call failed (%d): %s" % (st, self.L.xvcb200_ctx_error_string(self.h).decode()))
+            msg = self.L.xvcb200_ctx_error_string(self.h).decode() or self.L.xvcb200_last_error_string().decode()
+            self.L.xvcb200_clear_error()      # reported here: the thread's last-error slot is for the table-shaped entries
+            raise XvcB200Error("xvc_b200 call failed (%d): %s" % (st, msg))
 
     def sync(self):
         self._ok(self.L.xvcb200_sync(self.h))
