@@ -309,10 +309,13 @@ class Ref:
     """The compiled, unmodified reference behind oracle/ref_shim.cc."""
 
     def __init__(self):
+        # where ref_shim.cc's use_simd = 2 tables find the CUDA entries (resolved with dlopen at first use)
+        os.environ.setdefault("XVCB200_LIB", os.path.join(os.path.dirname(_HERE), "xvc_b200", "libxvc_b200.so"))
         L = self.L = ctypes.CDLL(REF_SO)
         L.xref_ssd.restype = c_u64
         L.xref_compare.restype = c_u64
         L.xref_transform_matrix.restype = ctypes.POINTER(ctypes.c_int16)
+        L.xref_table_entries_replaced.argtypes = [c_int, c_int]
         L.xref_session_create.restype = c_void_p
         L.xref_session_create.argtypes = [c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_i64, c_int, c_int, c_int, c_int]
         L.xref_intra_scan.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -58,20 +58,67 @@
 #undef private
 #undef protected
 
-#include "../include/xvc_b200.h"   // shared plain-C descriptor structs only
+#include <dlfcn.h>
+
+#include <cstddef>
+#include <mutex>
+
+#include "../include/xvc_b200.h"   // shared plain-C descriptor structs + the table structs
 
 using namespace xvc;  // NOLINT
 
 namespace {
 
+// Layout contract of INTEGRATION.md section 1: the two table structs of include/xvc_b200.h are the
+// reference's InterPrediction::SimdFunc / SampleMetric::SimdFunc member for member, so a maintainer
+// registers the CUDA entries with one call on the reference's own table object.
+#define XVCB_SAME_MEMBER(ours, theirs, m)                                                                   \
+  static_assert(offsetof(ours, m) == offsetof(theirs, m) && sizeof(((ours *)0)->m) == sizeof(((theirs *)0)->m), \
+                "table member " #m)
+static_assert(sizeof(xvcb200_inter_prediction_simd_func) == sizeof(InterPrediction::SimdFunc), "InterPrediction::SimdFunc layout");
+static_assert(sizeof(xvcb200_sample_metric_simd_func) == sizeof(SampleMetric::SimdFunc), "SampleMetric::SimdFunc layout");
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, add_avg);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_copy_bipred);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_h_sample_sample);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_h_sample_short);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_v_sample_sample);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_v_sample_short);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_v_short_sample);
+XVCB_SAME_MEMBER(xvcb200_inter_prediction_simd_func, InterPrediction::SimdFunc, filter_v_short_short);
+XVCB_SAME_MEMBER(xvcb200_sample_metric_simd_func, SampleMetric::SimdFunc, sad_sample_sample);
+XVCB_SAME_MEMBER(xvcb200_sample_metric_simd_func, SampleMetric::SimdFunc, sad_short_sample);
+XVCB_SAME_MEMBER(xvcb200_sample_metric_simd_func, SampleMetric::SimdFunc, ssd_sample_sample);
+XVCB_SAME_MEMBER(xvcb200_sample_metric_simd_func, SampleMetric::SimdFunc, ssd_short_sample);
+XVCB_SAME_MEMBER(xvcb200_sample_metric_simd_func, SampleMetric::SimdFunc, ssd_short_short);
+
+// use_simd: 0 = the reference's C entries, 1 = its runtime SIMD entries, 2 = the C entries
+// overwritten by libxvc_b200's Register functions (the drop-in of INTEGRATION.md section 1: the
+// reference's own classes then run with the CUDA entries behind their tables).  The library is
+// found through $XVCB200_LIB and resolved at run time, so libxvcref.so itself never links CUDA.
 const EncoderSimdFunctions &Simd(int use_simd, int bitdepth) {
   // index: [use_simd][bitdepth-8]
-  static std::unique_ptr<EncoderSimdFunctions> tables[2][9];
-  auto &slot = tables[use_simd ? 1 : 0][bitdepth - 8];
+  static std::unique_ptr<EncoderSimdFunctions> tables[3][9];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  auto &slot = tables[use_simd < 0 || use_simd > 2 ? 0 : use_simd][bitdepth - 8];
   if (!slot) {
     std::set<CpuCapability> caps;
-    if (use_simd) caps = SimdCpu::GetRuntimeCapabilities();
+    if (use_simd == 1) caps = SimdCpu::GetRuntimeCapabilities();
     slot.reset(new EncoderSimdFunctions(caps, bitdepth));
+    if (use_simd == 2) {
+      const char *path = getenv("XVCB200_LIB");
+      void *lib = dlopen(path ? path : "libxvc_b200.so", RTLD_NOW | RTLD_GLOBAL);
+      typedef void (*RegInter)(xvcb200_inter_prediction_simd_func *);
+      typedef void (*RegMetric)(int, xvcb200_sample_metric_simd_func *);
+      RegInter reg_inter = lib ? reinterpret_cast<RegInter>(dlsym(lib, "xvcb200_register_inter_prediction")) : nullptr;
+      RegMetric reg_metric = lib ? reinterpret_cast<RegMetric>(dlsym(lib, "xvcb200_register_sample_metric")) : nullptr;
+      if (!reg_inter || !reg_metric) {
+        fprintf(stderr, "ref_shim: cannot load the CUDA tables from %s: %s\n", path ? path : "libxvc_b200.so", dlerror());
+        abort();
+      }
+      reg_inter(reinterpret_cast<xvcb200_inter_prediction_simd_func *>(&slot->inter_prediction));
+      reg_metric(bitdepth, reinterpret_cast<xvcb200_sample_metric_simd_func *>(&slot->sample_metric));
+    }
   }
   return *slot;
 }
@@ -104,6 +151,19 @@ void ParallelFor(int n, int threads, MakeState make_state, Body body) {
 }  // namespace
 
 extern "C" {
+
+// How many entries of the use_simd tables differ from the reference's C entries (0 for use_simd = 0).
+int xref_table_entries_replaced(int use_simd, int bitdepth) {
+  const EncoderSimdFunctions &c = Simd(0, bitdepth), &t = Simd(use_simd, bitdepth);
+  int n = 0;
+  const void *const *a = reinterpret_cast<const void *const *>(&c.inter_prediction);
+  const void *const *b = reinterpret_cast<const void *const *>(&t.inter_prediction);
+  for (size_t i = 0; i < sizeof(c.inter_prediction) / sizeof(void *); i++) n += a[i] != b[i];
+  a = reinterpret_cast<const void *const *>(&c.sample_metric);
+  b = reinterpret_cast<const void *const *>(&t.sample_metric);
+  for (size_t i = 0; i < sizeof(c.sample_metric) / sizeof(void *); i++) n += a[i] != b[i];
+  return n;
+}
 
 // ---------------------------------------------------------------- leaf: metrics
 int xref_sad(int kind, int use_simd, int bitdepth, int w, int h, const void *a, ptrdiff_t sa,

@@ -526,3 +526,15 @@ def test_encode_picture(oracle, ref):
     for c in range(3):
         assert np.array_equal(s.get_rec_padded(c), rec.full[c]), c
         assert np.array_equal(s.get_coeff()[c], levels[c]), c
+
+
+def test_cuda_tables_register_into_reference_tables(ref):
+    """INTEGRATION.md section 1 on the host side: xvcb200_register_inter_prediction / _sample_metric write
+    into the reference's own InterPrediction::SimdFunc / SampleMetric::SimdFunc objects (layout equality
+    is a static_assert in oracle/ref_shim.cc, member by member); every entry of both tables that the
+    reference's classes call is replaced.  No kernel runs here -- tests/test_gpu_dropin.py runs the
+    reference's classes on top of these tables on the GPU."""
+    assert ref.L.xref_table_entries_replaced(0, 10) == 0
+    n = ref.L.xref_table_entries_replaced(2, 10)
+    # 8 x 2 interpolation entries; 5 x 6 metric entries (index 0 of the 7 is null in both tables)
+    assert n == 16 + 30, n
