@@ -433,6 +433,14 @@ typedef struct {
 int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const xvcb200_intra_job *jobs, int n,
                             uint32_t *satd);
 
+/* Chroma from luma: IntraPrediction::Predict(IntraMode::kLmChroma) -> PredLmChroma / RescaleLuma /
+ * DeriveLmParams (intra_prediction.cc:113-115, 560-686, 873-913) for n CUs at once, 4:2:0: both chroma
+ * blocks of every job (x, y, w, h = the CU's LUMA position and size; the neighbour flags are not used --
+ * the reference looks at the position only) predicted from rec_slot -- the CU's reconstructed luma
+ * and the luma / chroma samples above and left of it, which must be final -- into the U and V planes
+ * of pred_slot.  Asynchronous on the context stream. */
+int xvcb200_intra_lm_chroma(xvcb200_ctx *ctx, int rec_slot, const xvcb200_intra_job *jobs, int n, int pred_slot);
+
 /* ------------------------------------------------------------------------------------
  * (C) picture-level hot path
  * ---------------------------------------------------------------------------------- */

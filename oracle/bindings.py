@@ -120,6 +120,7 @@ class Oracle:
         L.xo_pad_border.argtypes = [c_void_p]
         L.xo_full_search.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u32, c_void_p, c_void_p]
         L.xo_motion_compensate.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p]
+        L.xo_intra_lm_chroma.argtypes = [c_int] * 5 + [c_void_p, c_ssize, c_void_p, c_ssize, c_void_p, c_ssize]
         L.xo_motion_compensate_lic.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
         L.xo_motion_compensate_affine.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
         L.xo_tq_reconstruct.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
@@ -260,6 +261,15 @@ class Oracle:
         lic = np.ascontiguousarray(lic, dtype=abi.lic_cu_dtype)
         self.L.xo_motion_compensate_lic(ctypes.addressof(arr), ctypes.byref(r), bitdepth, abi.ptr(cus), abi.ptr(lic), len(lic), ctypes.byref(p))
 
+    def intra_lm_chroma(self, rec_planes, comp, x, y, w, h, bitdepth):
+        """LM chroma prediction of component comp (1 / 2) of the CU at luma (x, y, w, h) from tight reconstructed planes."""
+        luma, chroma = rec_planes[0], rec_planes[comp]
+        pred = np.zeros((h // 2, w // 2), dtype=np.uint16)
+        lp = luma.ctypes.data + 2 * (y * luma.shape[1] + x)
+        cp = chroma.ctypes.data + 2 * ((y // 2) * chroma.shape[1] + x // 2)
+        self.L.xo_intra_lm_chroma(x, y, w, h, bitdepth, c_void_p(lp), luma.shape[1], c_void_p(cp), chroma.shape[1], abi.ptr(pred), w // 2)
+        return pred
+
     def tq_reconstruct(self, orig, pred, rec, bitdepth, cus, intra_picture=0, table=1, off_u=0, off_v=0):
         levels = [np.zeros((orig.height[c], orig.width[c]), dtype=np.int16) for c in range(3)]
         res = np.zeros(3 * len(cus), dtype=abi.tu_result_dtype)
@@ -316,6 +326,7 @@ class Ref:
         L.xref_compare.restype = c_u64
         L.xref_transform_matrix.restype = ctypes.POINTER(ctypes.c_int16)
         L.xref_table_entries_replaced.argtypes = [c_int, c_int]
+        L.xref_intra_lm_chroma.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p]
         L.xref_session_create.restype = c_void_p
         L.xref_session_create.argtypes = [c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_i64, c_int, c_int, c_int, c_int]
         L.xref_intra_scan.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -569,6 +580,19 @@ class RefSession:
         lic["cu"] = cu_indices
         self.L.xref_lic_neighbours(self.h, abi.ptr(lic), len(lic))
         return lic
+
+    def intra_lm_chroma(self, cus):
+        """[(U block, V block)] per CU: IntraPrediction::Predict(kLmChroma) from the session's reconstruction."""
+        cus = np.ascontiguousarray(cus, dtype=abi.cu_dtype)
+        total = int(sum((int(c["w"]) // 2) * (int(c["h"]) // 2) for c in cus))
+        pu, pv = np.zeros(total, dtype=np.uint16), np.zeros(total, dtype=np.uint16)
+        self.L.xref_intra_lm_chroma(self.h, abi.ptr(cus), len(cus), abi.ptr(pu), abi.ptr(pv))
+        out, off = [], 0
+        for c in cus:
+            w, h = int(c["w"]) // 2, int(c["h"]) // 2
+            out.append((pu[off:off + w * h].reshape(h, w).copy(), pv[off:off + w * h].reshape(h, w).copy()))
+            off += w * h
+        return out
 
     def tq_reconstruct(self, n_cus, threads=1):
         res = np.zeros(3 * n_cus, dtype=abi.tu_result_dtype)

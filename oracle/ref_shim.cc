@@ -907,6 +907,38 @@ void xref_intra_scan(xref_session *s, const xvcb200_cu *cus, int n, int comp_i, 
   }
 }
 
+// IntraPrediction::Predict(kLmChroma) -> PredLmChroma (intra_prediction.cc:560-584) for n CUs: U then V on
+// one IntraPrediction object (the second component reuses the reduced luma of the first, :574-580).
+// Reads s->rec (the CU's reconstructed luma + the luma / chroma neighbours).  pred_u / pred_v: the
+// blocks back to back, (w/2) x (h/2) each.  Fresh thread: unrestricted Restrictions (see ParallelFor).
+void xref_intra_lm_chroma(xref_session *s, const xvcb200_cu *cus, int n, uint16_t *pred_u, uint16_t *pred_v) {
+  EnsureInit(s);
+  std::thread([&]() {
+    IntraPrediction ip(s->bitdepth);
+    std::vector<Sample> tmp(64 * 64);
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+      const xvcb200_cu &d = cus[i];
+      CodingUnit *cu = s->pic_data->CreateCu(CuTree::Primary, d.depth, d.x, d.y, d.w, d.h);
+      cu->SetPredMode(PredictionMode::kIntra);
+      cu->SetQp(d.qp);
+      IntraPrediction::RefState state;
+      state.ref_samples.fill(0);
+      state.ref_filtered.fill(0);
+      const int w = d.w / 2, h = d.h / 2;
+      for (int c = 1; c <= 2; c++) {
+        SampleBuffer out(tmp.data(), 64);
+        ip.Predict(IntraMode::kLmChroma, *cu, static_cast<YuvComponent>(c), state, *s->rec, &out);
+        uint16_t *dst = (c == 1 ? pred_u : pred_v) + off;
+        for (int r = 0; r < h; r++) std::memcpy(dst + static_cast<size_t>(r) * w, tmp.data() + r * 64, sizeof(Sample) * w);
+      }
+      off += static_cast<size_t>(w) * h;
+      s->pic_data->MarkUsedInPic(cu);
+      s->cus.push_back(cu);
+    }
+  }).join();
+}
+
 // ---------------------------------------------------------------- bitstream conformance
 // A real xvc bitstream whose inter picture carries decisions and levels made OUTSIDE the reference
 // (by the GPU path): the reference encoder (public API, low delay, one reference) codes the key

@@ -116,6 +116,8 @@ void xo_intra_filter_ref(int w, int h, const uint16_t *src, uint16_t *dst);
 int xo_intra_use_filtered_ref(int mode, int w, int h);
 void xo_intra_predict(int mode, int w, int h, int bitdepth, int luma, const uint16_t *ref_samples,
                       const uint16_t *ref_filtered, uint16_t *out, ptrdiff_t os);
+void xo_intra_lm_chroma(int x, int y, int w, int h, int bitdepth, const uint16_t *luma, ptrdiff_t ls, const uint16_t *chroma,
+                        ptrdiff_t cs, uint16_t *pred, ptrdiff_t ps);
 void xo_intra_satd_scan(int w, int h, int bitdepth, const uint16_t *orig, ptrdiff_t ostride, const uint16_t *ref_samples,
                         const uint16_t *ref_filtered, uint32_t *satd);
 

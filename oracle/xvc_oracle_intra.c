@@ -181,3 +181,91 @@ void xo_intra_satd_scan(int w, int h, int bitdepth, const uint16_t *orig, ptrdif
     satd[mode] = (uint32_t)xo_satd(bitdepth, w, h, 0, orig, ostride, pred, 64);
   }
 }
+
+/* ---- chroma from luma (LM chroma) ----------------------------------------------------------
+ * IntraPrediction::PredLmChroma / RescaleLuma (4:2:0 branch) / DeriveLmParams,
+ * intra_prediction.cc:560-686, 873-913.  The CU's reconstructed luma (and one row above / one
+ * column left of it, when the CU is not at the picture border -- the reference tests the POSITION,
+ * not the availability) is reduced to chroma resolution with a [1 2 1; 1 2 1]/8 kernel, a linear
+ * model chroma ~ luma is fitted on that border against the reconstructed chroma neighbours, and
+ * applied to the reduced luma of the block.  Shift counts are masked to five bits where the
+ * reference shifts by a computed count (the behaviour of the x86 build this oracle is pinned to). */
+static int log2_floor(int x) { int l = 0; while (x > 1) { l++; x >>= 1; } return l; }   /* util::Log2Floor, utils.cc:46-53 */
+static int size_to_log2_lm(int size) { int l = 1; while ((1 << l) < size) l++; return l; }
+
+/* sub: (ch+1) x (cw+1) samples, row/column 0 = the border; sub[(y+1) * ss + (x+1)] = reduced luma (x, y) */
+static void lm_rescale_luma(const uint16_t *luma, ptrdiff_t ls, int cw, int ch, int has_above, int has_left, uint16_t *sub, int ss) {
+  for (int y = has_above ? -1 : 0; y < ch; y++) {
+    const uint16_t *s0 = luma + (ptrdiff_t)(2 * y) * ls, *s1 = s0 + ls;
+    for (int x = has_left ? -1 : 0; x < cw; x++) {
+      int v;
+      if (!has_left && x == 0) v = (s0[0] + s1[0] + 1) >> 1;                                            /* :897-903 */
+      else v = (s0[2 * x - 1] + 2 * s0[2 * x] + s0[2 * x + 1] + s1[2 * x - 1] + 2 * s1[2 * x] + s1[2 * x + 1] + 4) >> 3;
+      sub[(y + 1) * ss + (x + 1)] = (uint16_t)v;
+    }
+  }
+}
+
+static void lm_params(int bitdepth, int cw, int ch, int has_above, int has_left, const uint16_t *chroma, ptrdiff_t cs,
+                      const uint16_t *sub, int ss, int *scale_out, int *offset_out, int *shift_out) {
+  *scale_out = 0; *offset_out = 1 << (bitdepth - 1); *shift_out = 0;
+  if (!has_above && !has_left) return;
+  int sum_x = 0, sum_y = 0, sum_xx = 0, sum_xy = 0, nbr = 0;
+  if (has_above) {
+    const int dx = has_left ? ((cw / ch) > 1 ? cw / ch : 1) : 1;
+    for (int x = 0; x < cw; x += dx) {
+      const int a = sub[x + 1], b = chroma[-cs + x];
+      sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b; nbr++;
+    }
+  }
+  if (has_left) {
+    const int dy = has_above ? ((ch / cw) > 1 ? ch / cw : 1) : 1;
+    for (int y = 0; y < ch; y += dy) {
+      const int a = sub[(y + 1) * ss], b = chroma[y * cs - 1];
+      sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b; nbr++;
+    }
+  }
+  int size_shift = size_to_log2_lm(nbr);
+  if (size_shift > 15 - bitdepth) {
+    const int sh = size_shift + bitdepth - 15;
+    sum_x = (sum_x + (1 << (sh - 1))) >> sh; sum_y = (sum_y + (1 << (sh - 1))) >> sh;
+    sum_xx = (sum_xx + (1 << (sh - 1))) >> sh; sum_xy = (sum_xy + (1 << (sh - 1))) >> sh;
+    size_shift -= sh;
+  }
+  const int avg_x = sum_x >> size_shift, avg_y = sum_y >> size_shift;
+  const int x_frac = sum_x & ((1 << size_shift) - 1), y_frac = sum_y & ((1 << size_shift) - 1);
+  const int sd_xy = sum_xy - ((avg_x * avg_y) << size_shift) - avg_x * y_frac - avg_y * x_frac;
+  const int sd_xx = sum_xx - ((avg_x * avg_x) << size_shift) - 2 * avg_x * x_frac;
+  int shift_xy = 0, shift_xx = 0;
+  if (sd_xy != 0) { shift_xy = log2_floor(abs(sd_xy)) - bitdepth + 2; if (shift_xy < 0) shift_xy = 0; }
+  if (sd_xx != 0) { shift_xx = log2_floor(abs(sd_xx)) - 5; if (shift_xx < 0) shift_xx = 0; }
+  const int sd_xy_s = sd_xy >> shift_xy, sd_xx_s = sd_xx >> shift_xx;
+  const int total_shift = bitdepth + shift_xx + 4 + 7 - 13 - shift_xy;
+  if (sd_xx_s < 32) { *offset_out = avg_y; return; }
+  int scale = (int)((uint32_t)sd_xy_s * (uint32_t)(((1 << (bitdepth + 4)) + sd_xx_s / 2) / sd_xx_s));
+  scale = scale >> (total_shift & 31);
+  scale = scale < -256 ? -256 : scale > 255 ? 255 : scale;
+  scale *= 128;
+  const int base_shift = log2_floor(abs(scale) + (scale < 0 ? -1 : 0)) - (scale ? 5 : 0);
+  const int shift = 13 - base_shift;
+  scale >>= base_shift;
+  *scale_out = scale; *shift_out = shift;
+  *offset_out = avg_y - ((scale * avg_x) >> (shift & 31));
+}
+
+/* One chroma block: luma = the CU's top-left luma sample inside the reconstructed luma plane, chroma = the
+ * block's top-left sample inside the reconstructed chroma plane of the component, (x, y) = luma position. */
+void xo_intra_lm_chroma(int x, int y, int w, int h, int bitdepth, const uint16_t *luma, ptrdiff_t ls, const uint16_t *chroma,
+                        ptrdiff_t cs, uint16_t *pred, ptrdiff_t ps) {
+  uint16_t sub[33 * 33];
+  const int cw = w >> 1, ch = h >> 1, ss = 33, has_above = y > 0, has_left = x > 0;
+  lm_rescale_luma(luma, ls, cw, ch, has_above, has_left, sub, ss);
+  int scale, offset, shift;
+  lm_params(bitdepth, cw, ch, has_above, has_left, chroma, cs, sub, ss, &scale, &offset, &shift);
+  const int maxv = (1 << bitdepth) - 1;
+  for (int yy = 0; yy < ch; yy++)
+    for (int xx = 0; xx < cw; xx++) {
+      const int v = ((scale * sub[(yy + 1) * ss + xx + 1]) >> (shift & 31)) + offset;     /* AddLinearModel, sample_buffer.h:108-122 */
+      pred[yy * ps + xx] = (uint16_t)(v < 0 ? 0 : v > maxv ? maxv : v);
+    }
+}

@@ -73,3 +73,51 @@ def replay(backend):
         if comp == 0:
             assert np.array_equal(backend.scan(bd, cur, rec, jobs, ref_r, filt_r), z[c["name"] + "_satd"]), c["name"]
     assert n_pred > 500
+
+
+# ---------------------------------------------------------------- LM chroma
+LM_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "xvc_lm_golden.npz")
+
+
+def lm_jobs(cus):
+    jobs = np.zeros(len(cus), dtype=abi.intra_job_dtype)
+    jobs["x"], jobs["y"], jobs["w"], jobs["h"] = cus["x"], cus["y"], cus["w"], cus["h"]
+    return jobs
+
+
+def lm_oracle_backend(oracle):
+    def run(c, rec, cus):
+        pred = [np.zeros_like(rec[1]), np.zeros_like(rec[2])]
+        for cu in cus:
+            x, y, w, h = int(cu["x"]), int(cu["y"]), int(cu["w"]), int(cu["h"])
+            for comp in (1, 2):
+                pred[comp - 1][y // 2:(y + h) // 2, x // 2:(x + w) // 2] = oracle.intra_lm_chroma(rec, comp, x, y, w, h, c["bd"])
+        return pred
+    return run
+
+
+def lm_gpu_backend():
+    from xvc_b200 import lib
+
+    def run(c, rec, cus):
+        ctx = lib.Context(c["width"], c["height"], c["bd"], num_slots=2)
+        ctx.upload(0, rec)
+        ctx.intra_lm_chroma(0, lm_jobs(cus), 1)
+        out = ctx.download(1)
+        ctx.close()
+        return out[1:]
+    return run
+
+
+def replay_lm(run):
+    z = np.load(LM_GOLDEN)
+    cases = json.loads(bytes(z["__cases__"]).decode())
+    assert len(cases) >= 3
+    for c in cases:
+        n = c["name"]
+        rec = [z["%s_rec_%d" % (n, i)] for i in range(3)]
+        cus = z[n + "_cus"].view(abi.cu_dtype).copy()
+        assert len(cus) == c["n"]
+        got = run(c, rec, cus)
+        for comp in (1, 2):
+            assert np.array_equal(got[comp - 1], z["%s_pred_%d" % (n, comp)]), (n, comp)

@@ -108,3 +108,30 @@ def test_intra_scan_1080p(oracle):
 
 def test_intra_golden_gpu():
     intra_golden.replay(intra_golden.GpuBackend())
+
+
+def test_lm_golden_gpu():
+    """Reference LM chroma outputs (tests/golden/xvc_lm_golden.npz) == xvcb200_intra_lm_chroma."""
+    intra_golden.replay_lm(intra_golden.lm_gpu_backend())
+
+
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_lm_chroma_gpu_vs_oracle(oracle, bd):
+    """Every CU of a random partition 4..64 (chroma 2..32), picture borders included, both chroma components."""
+    width, height = 264, 136
+    _, rec, _ = common.frames(width, height, bd, 90 + bd, "random" if bd == 10 else "synth")
+    cus = workload.make_partition(width, height, seed=90 + bd, min_size=4)
+    ctx = lib.Context(width, height, bd, num_slots=2)
+    ctx.upload(0, rec)
+    ctx.intra_lm_chroma(0, intra_golden.lm_jobs(cus), 1)
+    got = ctx.download(1)
+    for cu in cus:
+        x, y, w, h = int(cu["x"]), int(cu["y"]), int(cu["w"]), int(cu["h"])
+        for comp in (1, 2):
+            exp = oracle.intra_lm_chroma(rec, comp, x, y, w, h, bd)
+            assert np.array_equal(got[comp][y // 2:(y + h) // 2, x // 2:(x + w) // 2], exp), (cu, comp)
+    bad = intra_golden.lm_jobs(cus[:1])
+    bad["x"] = width
+    with pytest.raises(lib.XvcB200Error):
+        ctx.intra_lm_chroma(0, bad, 1)
+    ctx.close()

@@ -58,3 +58,33 @@ def test_intra_golden_oracle(oracle):
     tests/golden/make_intra_golden.py) replayed against the C restatement."""
     import intra_golden
     intra_golden.replay(intra_golden.OracleBackend(oracle))
+
+
+@pytest.mark.parametrize("bd,content,seed", [(8, "synth", 71), (10, "synth", 72), (10, "random", 73), (12, "random", 74)])
+def test_lm_chroma_oracle_vs_reference(oracle, ref, bd, content, seed):
+    """IntraPrediction::Predict(kLmChroma) (PredLmChroma / RescaleLuma / DeriveLmParams,
+    intra_prediction.cc:560-686, 873-913) for every CU of a partition -- picture borders (no / one
+    neighbour side), all block shapes 8..64 (chroma 4..32), both chroma components."""
+    width, height = 200, 136
+    cur, rec, _ = common.frames(width, height, bd, seed, content)
+    if content == "synth":      # give chroma a relation to luma that is not the generator's own
+        rng = np.random.default_rng(seed)
+        rec = [rec[0]] + [np.clip(p.astype(np.int32) + rng.integers(-6, 7, size=p.shape) * (1 << (bd - 8)), 0, (1 << bd) - 1).astype(np.uint16)
+                          for p in rec[1:]]
+    cus = workload.make_partition(width, height, seed=seed, min_size=8)
+    cus["flags"] |= abi.CU_INTRA
+    ses = ref.session(width, height, bd, pic_type=2)
+    ses.set_orig(cur)
+    ses.set_rec(rec)
+    got = ses.intra_lm_chroma(cus)
+    ses.close()
+    for i, cu in enumerate(cus):
+        for comp in (1, 2):
+            p = oracle.intra_lm_chroma(rec, comp, int(cu["x"]), int(cu["y"]), int(cu["w"]), int(cu["h"]), bd)
+            assert np.array_equal(p, got[i][comp - 1]), (i, comp, cu)
+
+
+def test_lm_golden_oracle(oracle):
+    """tests/golden/xvc_lm_golden.npz (reference LM chroma outputs) replayed against the C restatement."""
+    import intra_golden
+    intra_golden.replay_lm(intra_golden.lm_oracle_backend(oracle))

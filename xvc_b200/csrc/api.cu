@@ -1194,6 +1194,27 @@ int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const
   return xvcb200_sync(c);
 }
 
+int xvcb200_intra_lm_chroma(xvcb200_ctx *ctx, int rec_slot, const xvcb200_intra_job *jobs, int n, int pred_slot) {
+  if (!slot_ok(ctx, rec_slot) || !slot_ok(ctx, pred_slot) || rec_slot == pred_slot || !jobs || n < 0) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  for (int i = 0; i < n; i++) {
+    const xvcb200_intra_job &j = jobs[i];
+    const bool pow2 = j.w >= 4 && j.w <= 64 && j.h >= 4 && j.h <= 64 && !(j.w & (j.w - 1)) && !(j.h & (j.h - 1));
+    if (!pow2 || j.x < 0 || j.y < 0 || (j.x & 1) || (j.y & 1) || j.x + j.w > c->width || j.y + j.h > c->height) return XVCB200_INVALID_ARGUMENT;
+  }
+  if (n == 0) return XVCB200_OK;
+  const size_t job_bytes = sizeof(*jobs) * (size_t)n;
+  uint8_t *d = static_cast<uint8_t *>(c->scratch(job_bytes));
+  if (!d) return c->status;
+  join_upload_slot(c, rec_slot);
+  join_downloads(c, pred_slot);
+  c->check(cudaMemcpyAsync(d, jobs, job_bytes, cudaMemcpyHostToDevice, c->stream), "lm chroma jobs");
+  c->check(launch_intra_lm_chroma(c->stream, reinterpret_cast<const xvcb200_intra_job *>(d), n, c->bitdepth, c->plane(rec_slot, 0),
+                                  c->plane(rec_slot, 1), c->plane(rec_slot, 2), c->plane(pred_slot, 1), c->plane(pred_slot, 2)),
+           "intra_lm_chroma");
+  return c->status;
+}
+
 static bool refs_from_slots(xvcb200_ctx *c, const int32_t ref_slots[2][5], Pic3 refs[2][5]) {
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) {

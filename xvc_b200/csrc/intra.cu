@@ -266,4 +266,108 @@ cudaError_t launch_intra_satd_scan(cudaStream_t s, const xvcb200_intra_job *d_jo
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- chroma from luma (LM chroma)
+// IntraPrediction::PredLmChroma / RescaleLuma (4:2:0) / DeriveLmParams (intra_prediction.cc:560-686,
+// 873-913).  One CTA per (block, chroma component): all threads reduce the CU's reconstructed luma
+// (plus the row above / column left when the CU is not at the picture border) to chroma resolution
+// into shared memory, warp 0 gathers the <= 64 (reduced luma, reconstructed chroma) neighbour pairs,
+// reduces the four sums with shuffles and lane 0 runs the reference's integer recipe, then all
+// threads apply the model to the reduced luma of the block.  Shift counts are masked to 5 bits where
+// the reference shifts by a computed count (the x86 behaviour the oracle is pinned to).
+__device__ __forceinline__ int log2_floor_dev(int x) { return x > 1 ? 31 - __clz(x) : 0; }
+
+__global__ void __launch_bounds__(128) intra_lm_chroma_kernel(const xvcb200_intra_job *__restrict__ jobs, int bitdepth, PlaneView luma,
+                                                              PlaneView cu_plane, PlaneView cv_plane, PlaneView pu_plane, PlaneView pv_plane) {
+  constexpr int SS = 33;
+  __shared__ uint16_t sub[SS * SS];
+  __shared__ int s_model[3];
+  const xvcb200_intra_job j = jobs[blockIdx.x];
+  const int comp = 1 + blockIdx.y;
+  const PlaneView cp = comp == 1 ? cu_plane : cv_plane, pp = comp == 1 ? pu_plane : pv_plane;
+  const int cw = j.w >> 1, ch = j.h >> 1;
+  const bool has_above = j.y > 0, has_left = j.x > 0;
+  const Sample *lbase = luma.base + j.y * luma.pitch + j.x;
+  const Sample *cbase = cp.base + (j.y >> 1) * cp.pitch + (j.x >> 1);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (ch + 1) * (cw + 1); i += blockDim.x) {
+    const int y = i / (cw + 1) - 1, x = i - (y + 1) * (cw + 1) - 1;
+    if ((y < 0 && !has_above) || (x < 0 && !has_left)) continue;
+    const Sample *s0 = lbase + (2 * y) * luma.pitch, *s1 = s0 + luma.pitch;
+    int v;
+    if (!has_left && x == 0) v = (s0[0] + s1[0] + 1) >> 1;
+    else v = (s0[2 * x - 1] + 2 * s0[2 * x] + s0[2 * x + 1] + s1[2 * x - 1] + 2 * s1[2 * x] + s1[2 * x + 1] + 4) >> 3;
+    sub[(y + 1) * SS + x + 1] = (uint16_t)v;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    int scale = 0, offset = 1 << (bitdepth - 1), shift = 0;
+    if (has_above || has_left) {
+      int sum_x = 0, sum_y = 0, sum_xx = 0, sum_xy = 0, nbr = 0;
+      if (has_above) {
+        const int dx = has_left ? max(1, cw / ch) : 1, cnt = (cw + dx - 1) / dx;
+        for (int k = tid; k < cnt; k += 32) {
+          const int a = sub[k * dx + 1], b = cbase[-cp.pitch + k * dx];
+          sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b;
+        }
+        nbr += cnt;
+      }
+      if (has_left) {
+        const int dy = has_above ? max(1, ch / cw) : 1, cnt = (ch + dy - 1) / dy;
+        for (int k = tid; k < cnt; k += 32) {
+          const int a = sub[(k * dy + 1) * SS], b = cbase[k * dy * cp.pitch - 1];
+          sum_x += a; sum_y += b; sum_xx += a * a; sum_xy += a * b;
+        }
+        nbr += cnt;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        sum_x += __shfl_xor_sync(XVCB_FULL, sum_x, o); sum_y += __shfl_xor_sync(XVCB_FULL, sum_y, o);
+        sum_xx += __shfl_xor_sync(XVCB_FULL, sum_xx, o); sum_xy += __shfl_xor_sync(XVCB_FULL, sum_xy, o);
+      }
+      int size_shift = 1;
+      while ((1 << size_shift) < nbr) size_shift++;
+      if (size_shift > 15 - bitdepth) {
+        const int sh = size_shift + bitdepth - 15, r = 1 << (sh - 1);
+        sum_x = (sum_x + r) >> sh; sum_y = (sum_y + r) >> sh; sum_xx = (sum_xx + r) >> sh; sum_xy = (sum_xy + r) >> sh;
+        size_shift -= sh;
+      }
+      const int avg_x = sum_x >> size_shift, avg_y = sum_y >> size_shift;
+      const int x_frac = sum_x & ((1 << size_shift) - 1), y_frac = sum_y & ((1 << size_shift) - 1);
+      const int sd_xy = sum_xy - ((avg_x * avg_y) << size_shift) - avg_x * y_frac - avg_y * x_frac;
+      const int sd_xx = sum_xx - ((avg_x * avg_x) << size_shift) - 2 * avg_x * x_frac;
+      const int shift_xy = sd_xy == 0 ? 0 : max(0, log2_floor_dev(abs(sd_xy)) - bitdepth + 2);
+      const int shift_xx = sd_xx == 0 ? 0 : max(0, log2_floor_dev(abs(sd_xx)) - 5);
+      const int sd_xy_s = sd_xy >> shift_xy, sd_xx_s = sd_xx >> shift_xx;
+      const int total_shift = bitdepth + shift_xx + 4 + 7 - 13 - shift_xy;
+      if (sd_xx_s < 32) {
+        offset = avg_y;
+      } else {
+        int sc = (int)((uint32_t)sd_xy_s * (uint32_t)(((1 << (bitdepth + 4)) + sd_xx_s / 2) / sd_xx_s));
+        sc = sc >> (total_shift & 31);
+        sc = clip3i(sc, -256, 255) * 128;
+        const int base_shift = log2_floor_dev(abs(sc) + (sc < 0 ? -1 : 0)) - (sc ? 5 : 0);
+        shift = 13 - base_shift;
+        scale = sc >> base_shift;
+        offset = avg_y - ((scale * avg_x) >> (shift & 31));
+      }
+    }
+    if (tid == 0) { s_model[0] = scale; s_model[1] = offset; s_model[2] = shift; }
+  }
+  __syncthreads();
+  const int scale = s_model[0], offset = s_model[1], shift = s_model[2] & 31, maxv = (1 << bitdepth) - 1;
+  Sample *dst = pp.base + (j.y >> 1) * pp.pitch + (j.x >> 1);
+  for (int i = tid; i < cw * ch; i += blockDim.x) {
+    const int y = i / cw, x = i - y * cw;
+    dst[y * pp.pitch + x] = (Sample)clip3i(((scale * (int)sub[(y + 1) * SS + x + 1]) >> shift) + offset, 0, maxv);
+  }
+}
+
+cudaError_t launch_intra_lm_chroma(cudaStream_t s, const xvcb200_intra_job *d_jobs, int n, int bitdepth, PlaneView luma, PlaneView rec_u,
+                                   PlaneView rec_v, PlaneView pred_u, PlaneView pred_v) {
+  if (n <= 0) return cudaSuccess;
+  g_launch_count++;
+  intra_lm_chroma_kernel<<<dim3(n, 2), 128, 0, s>>>(d_jobs, bitdepth, luma, rec_u, rec_v, pred_u, pred_v);
+  return cudaGetLastError();
+}
+
 }  // namespace xvcb

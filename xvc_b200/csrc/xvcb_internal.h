@@ -139,6 +139,8 @@ cudaError_t launch_intra_ref(cudaStream_t s, int w, int h, int bitdepth, const i
                              Sample *d_filt);
 cudaError_t launch_intra_predict(cudaStream_t s, int mode, int w, int h, int bitdepth, int luma, const Sample *d_ref,
                                  const Sample *d_filt, Sample *d_out, int os);
+cudaError_t launch_intra_lm_chroma(cudaStream_t s, const xvcb200_intra_job *d_jobs, int n, int bitdepth, PlaneView luma, PlaneView rec_u,
+                                   PlaneView rec_v, PlaneView pred_u, PlaneView pred_v);
 cudaError_t launch_intra_satd_scan(cudaStream_t s, const xvcb200_intra_job *d_jobs, int n, int bitdepth, PlaneView orig,
                                    PlaneView src, uint32_t *d_satd);
 // deblock.cu

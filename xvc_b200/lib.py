@@ -39,7 +39,7 @@ EXPORTS = [
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_motion_compensate_lic", "xvcb200_tq_reconstruct",
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
-    "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan",
+    "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan", "xvcb200_intra_lm_chroma",
     "xvcb200_ipc_export", "xvcb200_ipc_open_peer", "xvcb200_push_slot", "xvcb200_wait_pushes",
 ]
 
@@ -91,6 +91,7 @@ def load():
     L.xvcb200_intra_ref_samples.argtypes = [c_int] * 8 + [c_void_p, c_ssize, c_void_p, c_void_p]
     L.xvcb200_intra_predict.argtypes = [c_int] * 5 + [c_void_p, c_void_p, c_void_p, c_ssize]
     L.xvcb200_intra_satd_scan.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]
+    L.xvcb200_intra_lm_chroma.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int]
     L.xvcb200_ipc_export.argtypes = [c_void_p, c_void_p]
     L.xvcb200_ipc_open_peer.argtypes = [c_void_p, c_void_p, c_void_p]
     L.xvcb200_push_slot.argtypes = [c_void_p, c_int]
@@ -458,6 +459,11 @@ class Context:
         aff = np.ascontiguousarray(aff, dtype=abi.affine_cu_dtype)
         arr = self._ref_slots(ref_slots)
         self._ok(self.L.xvcb200_motion_compensate_affine(self.h, abi.ptr(aff), len(aff), abi.ptr(arr), pred_slot))
+
+    def intra_lm_chroma(self, rec_slot, jobs, pred_slot):
+        """LM chroma prediction of both chroma blocks of every job (abi.intra_job_dtype, luma x/y/w/h) into pred_slot."""
+        jobs = np.ascontiguousarray(jobs, dtype=abi.intra_job_dtype)
+        self._ok(self.L.xvcb200_intra_lm_chroma(self.h, rec_slot, abi.ptr(jobs), len(jobs), pred_slot))
 
     def motion_compensate_lic(self, lic, ref_slots, rec_slot, pred_slot):
         """lic: abi.lic_cu_dtype array (CU index + position of the CU above / left, -1 = none)."""
