@@ -54,3 +54,13 @@ def test_no_cpu_fallback():
     a = np.zeros((8, 8), dtype=np.uint16)
     with pytest.raises(lib.XvcB200Error):
         lib.sad(a, a, 8, 8)
+
+
+def test_header_is_plain_c_and_cpp():
+    """include/xvc_b200.h is the drop-in boundary: it must compile on its own as C99 and as C++11
+    (what the reference is built with), without warnings under -Wall -Wextra -pedantic."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "xvc_b200.h")
+    for cmd in (["gcc", "-std=c99", "-x", "c"], ["g++", "-std=c++11", "-x", "c++"]):
+        out = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
