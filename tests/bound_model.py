@@ -4,13 +4,13 @@ gives the final best cost of each sampled job): what fraction of the raster cand
 below the threshold after HALF of the rows of the segment-sum bound, against the fraction that
 survives the whole bound.  Decision aid for the two-stage bound of DESIGN.md section 8; thresholds use
 the FINAL best cost (<= the cost the kernel holds when the raster starts) and ignore the MV rate, so
-both fractions are brackets, their ratio is what matters.  Test/analysis tooling: imports oracle/."""
+both fractions are brackets, their ratio is what matters.  Analysis tooling kept under tests/ because it uses the oracle (test infrastructure); not collected by pytest."""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # lives under tests/: it uses the oracle (test infrastructure)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
