@@ -121,3 +121,45 @@ def test_frame_parallel_gop_matches_single_process(tmp_path, world):
         for poc in eng.rec:
             for c in range(3):
                 assert np.array_equal(z["p%d_%d" % (poc, c)], eng.rec[poc].full[c]), (r, poc, c)
+
+
+# ---------------------------------------------------------------- peer exchange: agreed fallback
+class _FakeCtx:
+    """Stands in for lib.Context: rank `bad` cannot open its peers' arenas."""
+
+    def __init__(self, rank, bad):
+        self.rank, self.bad, self.opened = rank, bad, 0
+
+    def ipc_export(self):
+        return bytes([self.rank]) * 64
+
+    def ipc_open_peer(self, handle):
+        if self.rank == self.bad:
+            raise RuntimeError("cudaIpcOpenMemHandle: invalid device context")
+        self.opened += 1
+
+
+def _peer_worker(rank, world, port, bad, out_dir):
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    ctx = _FakeCtx(rank, bad)
+    try:
+        sharding.PeerExchange(ctx, dist, rank, world)
+        outcome = "ok %d" % ctx.opened
+    except sharding.PeerExchangeUnavailable as e:
+        outcome = "unavailable: %s" % e
+    open(os.path.join(out_dir, "peer%d.txt" % rank), "w").write(outcome)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bad", [-1, 1])
+def test_peer_exchange_all_ranks_agree(tmp_path, bad):
+    """Either every rank opens every peer, or EVERY rank gets PeerExchangeUnavailable (naming the rank that
+    failed) -- so that bench.py / an encoder falls back to the NCCL exchange on all ranks together."""
+    world = 3
+    mp.spawn(_peer_worker, args=(world, _free_port(), bad, str(tmp_path)), nprocs=world, join=True)
+    got = [open(os.path.join(str(tmp_path), "peer%d.txt" % r)).read() for r in range(world)]
+    if bad < 0:
+        assert got == ["ok 2"] * world
+    else:
+        assert all(g.startswith("unavailable: rank %d" % bad) for g in got), got
