@@ -64,3 +64,23 @@ def test_header_is_plain_c_and_cpp():
     for cmd in (["gcc", "-std=c99", "-x", "c"], ["g++", "-std=c++11", "-x", "c++"]):
         out = subprocess.run(cmd + ["-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr
+
+
+def test_cpp_host_example_builds_and_links(tmp_path):
+    """examples/encode_step.cc -- the batched step from plain C++ -- compiles against the header, links
+    against libxvc_b200.so and, on a machine without a CUDA device, fails loudly (exit 3: no CPU fallback);
+    with a device it runs the step (exit 0)."""
+    import subprocess
+    lib.load()
+    exe = str(tmp_path / "encode_step")
+    libdir = os.path.join(ROOT, "xvc_b200")
+    cmd = ["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "encode_step.cc"),
+           "-o", exe, "-L", libdir, "-lxvc_b200", "-Wl,-rpath," + libdir]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode in (0, 3), (run.returncode, run.stdout, run.stderr)
+    if run.returncode == 3:
+        assert "no CUDA device" in run.stderr
+    else:
+        assert "recon checksum" in run.stdout
