@@ -37,6 +37,7 @@ int Fail(xvcb200_ctx *ctx, const char *what, int st) {
 int main(int argc, char **argv) {
   const int width = argc > 2 ? std::atoi(argv[1]) : 256, height = argc > 2 ? std::atoi(argv[2]) : 128;
   const int bitdepth = 10, qp = 32;
+  if (width < 32 || height < 32 || width % 32 || height % 32) { std::fprintf(stderr, "width and height must be multiples of 32\n"); return 2; }
   enum { ORIG, REF0, REF1, PRED, REC, LEV, NUM_SLOTS };
   xvcb200_ctx *ctx = nullptr;
   int st = xvcb200_ctx_create(&ctx, /*device*/ 0, width, height, bitdepth, /*4:2:0*/ 1, NUM_SLOTS);
@@ -52,15 +53,17 @@ int main(int argc, char **argv) {
   xvcb200_pad_border(ctx, REF0);           // references are padded once, when they are finished
   xvcb200_pad_border(ctx, REF1);
 
-  std::vector<xvcb200_cu> cus;             // leaf CUs in coding order; mv[list] = the predictor of the search
-  for (int y = 0; y < height; y += 32)
-    for (int x = 0; x < width; x += 32) {
-      xvcb200_cu cu = {};
-      cu.x = int16_t(x); cu.y = int16_t(y);
-      cu.w = uint8_t(width - x < 32 ? width - x : 32); cu.h = uint8_t(height - y < 32 ? height - y : 32);
-      cu.depth = 1; cu.qp = int8_t(qp); cu.ref_idx[0] = 0; cu.ref_idx[1] = 0;
-      cus.push_back(cu);
-    }
+  std::vector<xvcb200_cu> cus;             // leaf CUs in coding order (CTUs in raster order, quadrants in z-order);
+  for (int cy = 0; cy < height; cy += 64)  // mv[list] = the predictor of the search (zero here)
+    for (int cx = 0; cx < width; cx += 64)
+      for (int q = 0; q < 4; q++) {
+        const int x = cx + 32 * (q & 1), y = cy + 32 * (q >> 1);
+        if (x >= width || y >= height) continue;
+        xvcb200_cu cu = {};
+        cu.x = int16_t(x); cu.y = int16_t(y); cu.w = 32; cu.h = 32;
+        cu.depth = 1; cu.qp = int8_t(qp); cu.ref_idx[0] = -1; cu.ref_idx[1] = -1;    // the step writes the chosen list back
+        cus.push_back(cu);
+      }
   const int n = int(cus.size());
   xvcb200_set_cus(ctx, cus.data(), n);
 
