@@ -500,3 +500,26 @@ def test_async_transfers_pipeline(oracle):
         for f in ("flags", "ref_idx", "mv"):
             assert np.array_equal(cus_t[f], cus_g[f]), (i, f)
     assert any(np.any(l[0]) for _, l, _ in got)      # the pictures have non-zero levels
+
+
+def test_empty_inputs():
+    """Edge case: a picture with no inter CU at all / empty job lists are no-ops that succeed (the
+    reference's loops simply do not execute), and leave the context usable."""
+    width, height, bd = 64, 64, 10
+    cur, r0, r1 = common.frames(width, height, bd, 171)
+    ctx = _ctx(width, height, bd, cur, r0, r1)
+    ctx.set_cus(np.zeros(0, dtype=abi.cu_dtype))
+    prm = common.picture_params(0, workload.lambda_for_qp(32), slots=dict(orig=0, ref0=1, ref1=2, pred=3, rec=4, coeff=5))
+    me, tu = ctx.encode_picture(prm)
+    assert len(me) == 0 and len(tu) == 0
+    ctx.motion_compensate({(0, 0): 1, (1, 0): 2}, 3)
+    ctx.motion_compensate_affine(np.zeros(0, dtype=abi.affine_cu_dtype), {(0, 0): 1, (1, 0): 2}, 3)
+    ctx.motion_compensate_lic(np.zeros(0, dtype=abi.lic_cu_dtype), {(0, 0): 1, (1, 0): 2}, 4, 3)
+    ctx.intra_lm_chroma(4, np.zeros(0, dtype=abi.intra_job_dtype), 3)
+    ctx.sync()
+    # and the context still works
+    cus = workload.make_partition(width, height, seed=172, min_size=8)
+    ctx.set_cus(cus)
+    me, tu = ctx.encode_picture(prm)
+    ctx.sync()
+    assert len(me) == 2 * len(cus) and len(tu) == 3 * len(cus)

@@ -1195,7 +1195,7 @@ int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const
 }
 
 int xvcb200_intra_lm_chroma(xvcb200_ctx *ctx, int rec_slot, const xvcb200_intra_job *jobs, int n, int pred_slot) {
-  if (!slot_ok(ctx, rec_slot) || !slot_ok(ctx, pred_slot) || rec_slot == pred_slot || !jobs || n < 0) return XVCB200_INVALID_ARGUMENT;
+  if (!slot_ok(ctx, rec_slot) || !slot_ok(ctx, pred_slot) || rec_slot == pred_slot || (!jobs && n > 0) || n < 0) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int i = 0; i < n; i++) {
     const xvcb200_intra_job &j = jobs[i];
