@@ -22,7 +22,7 @@
  * Sample = uint16_t (reference default build HIGH_BITDEPTH=ON, common.h:34-38),
  * Coeff = Residual = int16_t (common.h:39-40).  Strides are in elements, not bytes.
  * Error convention: table-shaped calls return their value / void like the reference and
- * record failures in a process-wide sticky status (xvcb200_last_error); batched calls
+ * record failures in a sticky status of the calling thread (xvcb200_last_error); batched calls
  * return an xvcb200_status and never throw.
  */
 #ifndef XVC_B200_H_
@@ -44,13 +44,15 @@ typedef enum {
   XVCB200_UNSUPPORTED = 5
 } xvcb200_status;
 
-/* sticky process-wide status for the void/value-returning table calls */
+/* sticky status of the calling thread for the void/value-returning table calls */
 int xvcb200_last_error(void);
 const char *xvcb200_last_error_string(void);
 void xvcb200_clear_error(void);
 /* number of kernels this library has launched since load (bench.py gpu_launches) */
 uint64_t xvcb200_launch_count(void);
 const char *xvcb200_version(void);
+/* CUDA devices visible to the library (0: none -- every compute entry then fails, there is no CPU path) */
+int xvcb200_device_count(void);
 /* sizeof() of the structs below as compiled (0 cu, 1 me_job, 2 me_result, 3 fullsearch_job,
  * 4 tu_result, 5 picture_params, 6 plane_geom, 7 qp, 8 intra_job, 9 affine_cu, 10 lic_cu) -- lets
  * bindings verify their layout */
@@ -265,7 +267,9 @@ void *xvcb200_stream(xvcb200_ctx *ctx);              /* the cudaStream_t work is
 int xvcb200_sync(xvcb200_ctx *ctx);                 /* waits, returns sticky status */
 const char *xvcb200_ctx_error_string(xvcb200_ctx *ctx);
 int xvcb200_get_geometry(xvcb200_ctx *ctx, xvcb200_plane_geom *geom);
-/* device address of sample (0,0) of a plane of a slot (uint16_t*); coefficient slots: int16_t* */
+/* device address of sample (0,0) of a plane of a slot (uint16_t*); coefficient slots: int16_t*.
+ * Raw pointers (here and xvcb200_slot_region) are ordered with the library's work only through the
+ * context stream: use them on xvcb200_stream(ctx), or after xvcb200_sync(ctx). */
 int xvcb200_slot_ptr(xvcb200_ctx *ctx, int slot, int comp, void **dev_ptr);
 
 /* the whole device allocation of a slot (three padded planes).  All slots of a context live
@@ -278,14 +282,18 @@ int xvcb200_slot_region(xvcb200_ctx *ctx, int slot, void **base, uint64_t *bytes
  * reference it -- thread_encoder.cc:99-131 has one address space, this is its multi-GPU form).
  * Copy engines move the slot over NVLink; no SM takes part, so the exchange overlaps the next
  * picture's kernels completely (an NCCL all-gather needs SMs, which the persistent search kernel
- * occupies).  handle: 64 bytes (cudaIpcMemHandle_t of the slot arena), exchanged out of band.
+ * occupies).  handle: XVCB200_IPC_HANDLE_BYTES = the cudaIpcMemHandle_t of the slot arena followed by
+ * the arena layout (slot stride, slot count), exchanged out of band; xvcb200_ipc_open_peer returns
+ * XVCB200_INVALID_ARGUMENT for a peer whose layout differs from this context's (pushes address the
+ * peer by slot * stride).
  * xvcb200_push_slot copies slot `slot` of this context into the same slot of every opened peer,
  * ordered after the work enqueued on the context stream so far; xvcb200_wait_pushes makes the
  * context stream wait for the last push of `slot` (slot < 0: of every slot) -- call it before the
  * slot is overwritten.  Arrival at the consumer is the caller's rendezvous (after
  * xvcb200_wait_pushes + xvcb200_sync on every rank the pushed slots are complete everywhere). */
-int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle64);
-int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle64, int *peer_index);
+#define XVCB200_IPC_HANDLE_BYTES 80
+int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle /* XVCB200_IPC_HANDLE_BYTES */);
+int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle, int *peer_index);
 int xvcb200_push_slot(xvcb200_ctx *ctx, int slot);
 int xvcb200_wait_pushes(xvcb200_ctx *ctx, int slot);
 

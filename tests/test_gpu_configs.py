@@ -212,7 +212,17 @@ def test_ipc_open_failure_is_not_sticky():
     width, height, bd = 64, 64, 10
     ctx = lib.Context(width, height, bd, num_slots=1)
     with pytest.raises(lib.XvcB200Error):
-        ctx.ipc_open_peer(bytes(64))
+        ctx.ipc_open_peer(bytes(lib.IPC_HANDLE_BYTES))        # no magic: refused before CUDA sees it
+    mine = bytearray(ctx.ipc_export())
+    with pytest.raises(lib.XvcB200Error):                    # a peer arena with another slot count is refused
+        other = lib.Context(width, height, bd, num_slots=2)
+        try:
+            ctx.ipc_open_peer(other.ipc_export())
+        finally:
+            other.close()
+    mine[0] ^= 0xff                                          # right layout, handle that names nothing
+    with pytest.raises(lib.XvcB200Error):
+        ctx.ipc_open_peer(bytes(mine))
     cur = common.frames(width, height, bd, 3)[0]
     ctx.upload(0, cur)
     ctx.pad_border(0)

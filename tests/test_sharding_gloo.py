@@ -131,7 +131,7 @@ class _FakeCtx:
         self.rank, self.bad, self.opened = rank, bad, 0
 
     def ipc_export(self):
-        return bytes([self.rank]) * 64
+        return bytes([self.rank]) * 80
 
     def ipc_open_peer(self, handle):
         if self.rank == self.bad:

@@ -126,7 +126,12 @@ int xvcb200_last_error(void) { return t_last_error; }
 const char *xvcb200_last_error_string(void) { return t_last_error_str; }
 void xvcb200_clear_error(void) { t_last_error = XVCB200_OK; t_last_error_str[0] = 0; }
 uint64_t xvcb200_launch_count(void) { return g_launch_count.load(); }
-const char *xvcb200_version(void) { return "xvc_b200 0.1 (sm_100a)"; }
+const char *xvcb200_version(void) { return "xvc_b200 0.2 (sm_100a)"; }
+int xvcb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 int xvcb200_abi_sizeof(int which) {
   switch (which) {
@@ -458,6 +463,9 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   std::vector<char> up_tight;                 // per slot: staging index of the pending upload, -1 = written directly
   std::vector<cudaEvent_t> dl_ev; std::vector<char> dl_pending;   // per slot, last entry = the CU array
   // optional per-stage timing of xvcb200_encode_picture (CUDA events on the context stream)
+  // highest ref_idx per list any inter CU of the current array may carry (set_cus; raised by encode_picture's decisions):
+  // every (list, ref_idx) up to it must name a valid slot in the calls that dereference reference pictures
+  int max_ref_idx[2] = {-1, -1};
   bool profile = false;
   cudaEvent_t ev[9] = {nullptr};
   bool ev_valid = false;
@@ -556,6 +564,7 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
 }
 
 void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx) return;
   CtxFull *c = full(ctx);
   cudaSetDevice(c->device);
@@ -598,6 +607,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
 }
 
 int xvcb200_ctx_set_stream(xvcb200_ctx *c, void *cuda_stream) {
+  xvcb::DevGuard dev_guard(c);
   if (!c) return XVCB200_INVALID_ARGUMENT;
   cudaStreamSynchronize(c->stream);
   if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
@@ -611,6 +621,7 @@ int xvcb200_ctx_set_stream(xvcb200_ctx *c, void *cuda_stream) {
 }
 
 int xvcb200_sync(xvcb200_ctx *c) {
+  xvcb::DevGuard dev_guard(c);
   if (!c) return XVCB200_INVALID_ARGUMENT;
   c->check(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
   return c->status;
@@ -618,37 +629,63 @@ int xvcb200_sync(xvcb200_ctx *c) {
 const char *xvcb200_ctx_error_string(xvcb200_ctx *c) { return c ? c->error.c_str() : "null context"; }
 
 int xvcb200_get_geometry(xvcb200_ctx *c, xvcb200_plane_geom *g) {
+  xvcb::DevGuard dev_guard(c);
   if (!c || !g) return XVCB200_INVALID_ARGUMENT;
   *g = c->geom;
   return XVCB200_OK;
 }
 int xvcb200_slot_ptr(xvcb200_ctx *c, int slot, int comp, void **p) {
+  xvcb::DevGuard dev_guard(c);
   if (!c || !p || slot < 0 || slot >= (int)c->slots.size() || comp < 0 || comp > 2) return XVCB200_INVALID_ARGUMENT;
+  join_upload_slot(full(c), slot);          // raw access: a deferred upload is unpacked (on the context stream) first
   *p = c->slots[slot].base[comp];
   return XVCB200_OK;
 }
 void *xvcb200_stream(xvcb200_ctx *c) { return c ? c->stream : nullptr; }
 // whole allocation of a slot (three padded planes); consecutive slots are contiguous
 int xvcb200_slot_region(xvcb200_ctx *c, int slot, void **base, uint64_t *bytes) {
+  xvcb::DevGuard dev_guard(c);
   if (!c || !base || !bytes || slot < 0 || slot >= (int)c->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  join_upload_slot(full(c), slot);          // raw access: a deferred upload is unpacked (on the context stream) first
   *base = c->slots[slot].alloc;
   *bytes = c->slot_stride;
   return XVCB200_OK;
 }
 
-int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle64) {
-  if (!ctx || !handle64 || ctx->slots.empty()) return XVCB200_INVALID_ARGUMENT;
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+// handle = [cudaIpcMemHandle_t of the slot arena (64 bytes)][slot stride in bytes (u64)][number of slots (u32)][magic (u32)]:
+// the layout travels with the handle, so a peer whose arena is laid out differently is refused
+// instead of being written out of bounds by xvcb200_push_slot.
+static const uint32_t kIpcMagic = 0x58564342u;   // "XVCB"
+int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || !handle || ctx->slots.empty()) return XVCB200_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64 && XVCB200_IPC_HANDLE_BYTES == 80, "handle size");
   cudaIpcMemHandle_t h;
   if (!ctx->check(cudaIpcGetMemHandle(&h, ctx->slots[0].alloc), "cudaIpcGetMemHandle")) return ctx->status;
-  memcpy(handle64, &h, sizeof(h));
+  uint8_t *out = static_cast<uint8_t *>(handle);
+  const uint64_t stride = ctx->slot_stride;
+  const uint32_t nslots = (uint32_t)ctx->slots.size();
+  memcpy(out, &h, sizeof(h));
+  memcpy(out + 64, &stride, 8);
+  memcpy(out + 72, &nslots, 4);
+  memcpy(out + 76, &kIpcMagic, 4);
   return XVCB200_OK;
 }
-int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle64, int *peer_index) {
-  if (!ctx || !handle64) return XVCB200_INVALID_ARGUMENT;
+int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle, int *peer_index) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || !handle) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, sizeof(h));
+  memcpy(&h, handle, sizeof(h));
+  {
+    const uint8_t *in = static_cast<const uint8_t *>(handle);
+    uint64_t stride; uint32_t nslots, magic;
+    memcpy(&stride, in + 64, 8); memcpy(&nslots, in + 72, 4); memcpy(&magic, in + 76, 4);
+    if (magic != kIpcMagic || stride != (uint64_t)c->slot_stride || nslots != (uint32_t)c->slots.size()) {
+      set_last_error(XVCB200_INVALID_ARGUMENT, "xvcb200_ipc_open_peer: the peer's slot arena has another layout (slot stride / slot count)");
+      return XVCB200_INVALID_ARGUMENT;
+    }
+  }
   void *base = nullptr;
   cudaError_t oe = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
   if (oe != cudaSuccess) {      // not sticky: the caller may fall back to another exchange (NCCL)
@@ -667,9 +704,11 @@ int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle64, int *peer_inde
   return XVCB200_OK;
 }
 int xvcb200_push_slot(xvcb200_ctx *ctx, int slot) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (c->ex.peer_arena.empty()) return XVCB200_OK;
+  join_upload_slot(c, slot);
   const size_t off = (size_t)slot * c->slot_stride;
   c->check(cudaEventRecord(c->ex.push_ready, c->stream), "cudaEventRecord");
   for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {      // one DMA stream per peer: the copies run side by side
@@ -688,6 +727,7 @@ int xvcb200_push_slot(xvcb200_ctx *ctx, int slot) {
   return c->status;
 }
 int xvcb200_wait_pushes(xvcb200_ctx *ctx, int slot) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int s = 0; s < (int)c->ex.slot_pushed.size(); s++)
@@ -704,6 +744,7 @@ static bool slot_ok(xvcb200_ctx *c, int slot) { return c && slot >= 0 && slot < 
 // rate.  Strided host planes take the 2-D copy.  set: 0 = context stream, 1 = copy stream.
 static int transfer_picture(xvcb200_ctx *ctx, int slot, void *const planes[3], const ptrdiff_t strides[3], bool to_device,
                             cudaStream_t st, int set) {
+  xvcb::DevGuard dev_guard(ctx);
   CtxFull *c = full(ctx);
   bool tight = (c->geom.width[0] & 7) == 0;
   size_t samples = 0, off[3];
@@ -742,6 +783,7 @@ static int transfer_picture(xvcb200_ctx *ctx, int slot, void *const planes[3], c
 }
 
 int xvcb200_upload_picture(xvcb200_ctx *c, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(c);
   if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
   join_upload_slot(full(c), slot);          // an async upload nobody consumed must not land on top of this one
   join_downloads(full(c), slot);
@@ -749,20 +791,26 @@ int xvcb200_upload_picture(xvcb200_ctx *c, int slot, const uint16_t *const plane
   return transfer_picture(c, slot, reinterpret_cast<void *const *>(const_cast<uint16_t *const *>(planes)), strides, true, c->stream, 0);
 }
 static int download_planes(xvcb200_ctx *c, int slot, void *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(c);
   if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
+  join_upload_slot(full(c), slot);          // a deferred (tight) async upload is unpacked into the slot first
   const int st = transfer_picture(c, slot, planes, strides, false, c->stream, 0);
   if (st != XVCB200_OK) return st;
   return xvcb200_sync(c);
 }
 int xvcb200_download_picture(xvcb200_ctx *c, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(c);
   return download_planes(c, slot, reinterpret_cast<void *const *>(planes), strides);
 }
 int xvcb200_download_coeff(xvcb200_ctx *c, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(c);
   return download_planes(c, slot, reinterpret_cast<void *const *>(planes), strides);
 }
 // full padded allocation of one plane (tests of PadBorder): rows x cols = (h+2*pad) x (w+2*pad), pad = 80 / 40
 int xvcb200_download_padded(xvcb200_ctx *c, int slot, int comp, uint16_t *dst) {
+  xvcb::DevGuard dev_guard(c);
   if (!slot_ok(c, slot) || comp < 0 || comp > 2 || !dst) return XVCB200_INVALID_ARGUMENT;
+  join_upload_slot(full(c), slot);
   const int pad = 80 >> (comp ? 1 : 0), w = c->geom.width[comp] + 2 * pad, h = c->geom.height[comp] + 2 * pad;
   const Sample *src = c->slots[slot].base[comp] - (ptrdiff_t)pad * c->geom.pitch[comp] - pad;
   if (!c->check(cudaMemcpy2DAsync(dst, (size_t)w * 2, src, (size_t)c->geom.pitch[comp] * 2, (size_t)w * 2, h,
@@ -817,6 +865,10 @@ static void join_upload_slot(CtxFull *c, int slot) {
   c->ex.up_pending[slot] = 0;
   const int k = c->ex.up_tight[slot];
   if (k >= 0) {                 // the picture sits in a tight staging buffer: unpack it into the slot, here, in program order
+    if (slot < (int)c->ex.dl_pending.size() && c->ex.dl_pending[slot]) {     // a strided async download still reads the slot
+      c->check(cudaStreamWaitEvent(c->stream, c->ex.dl_ev[slot], 0), "cudaStreamWaitEvent");
+      c->ex.dl_pending[slot] = 0;
+    }
     c->check(launch_plane_pack(c->stream, pic3(c, slot), c->ex.d_up_ring[k], 0), "plane_unpack");
     c->check(cudaEventRecord(c->ex.up_ring_ev[k], c->stream), "cudaEventRecord");
     c->ex.up_tight[slot] = -1;
@@ -847,6 +899,7 @@ static bool host_planes_tight(const CtxFull *c, const ptrdiff_t strides[3]) {
 static int download_planes_async(CtxFull *c, int slot, void *const planes[3], const ptrdiff_t strides[3]) {
   if (!slot_ok(c, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
   if (!copy_setup(c)) return c->status;
+  join_upload_slot(c, slot);
   if (host_planes_tight(c, strides)) {
     // pack on the context stream (program order: the slot may be rewritten right after), DMA on the copy stream
     const int k = (int)(c->ex.down_ring_next++ % CtxExtra::kDownRing);
@@ -876,6 +929,7 @@ static int download_planes_async(CtxFull *c, int slot, void *const planes[3], co
 extern "C" {
 
 int xvcb200_upload_picture_async(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, slot) || !planes || !strides) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (!copy_setup(c)) return c->status;
@@ -912,14 +966,17 @@ int xvcb200_upload_picture_async(xvcb200_ctx *ctx, int slot, const uint16_t *con
   return c->status;
 }
 int xvcb200_download_picture_async(xvcb200_ctx *ctx, int slot, uint16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx) return XVCB200_INVALID_ARGUMENT;
   return download_planes_async(full(ctx), slot, reinterpret_cast<void *const *>(planes), strides);
 }
 int xvcb200_download_coeff_async(xvcb200_ctx *ctx, int slot, int16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx) return XVCB200_INVALID_ARGUMENT;
   return download_planes_async(full(ctx), slot, reinterpret_cast<void *const *>(planes), strides);
 }
 int xvcb200_get_cus_async(xvcb200_ctx *ctx, xvcb200_cu *cus, int n) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || !cus || n < 0 || n > ctx->n_cus) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (!copy_setup(c) || !copy_after_compute(c, c->ex.copy_stream)) return c->status;
@@ -933,6 +990,7 @@ int xvcb200_get_cus_async(xvcb200_ctx *ctx, xvcb200_cu *cus, int n) {
 }
 // host waits for the last async download of one slot (slot < 0: the CU array)
 int xvcb200_wait_download(xvcb200_ctx *ctx, int slot) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (slot < 0) {
@@ -945,6 +1003,7 @@ int xvcb200_wait_download(xvcb200_ctx *ctx, int slot) {
   return c->status;
 }
 int xvcb200_sync_copies(xvcb200_ctx *ctx) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (c->ex.copy_stream) c->check(cudaStreamSynchronize(c->ex.copy_stream), "cudaStreamSynchronize(copy)");
@@ -953,6 +1012,7 @@ int xvcb200_sync_copies(xvcb200_ctx *ctx) {
 }
 
 int xvcb200_pad_border(xvcb200_ctx *c, int slot) {
+  xvcb::DevGuard dev_guard(c);
   if (!slot_ok(c, slot)) return XVCB200_INVALID_ARGUMENT;
   join_upload_slot(full(c), slot);
   join_downloads(full(c), slot);
@@ -964,15 +1024,21 @@ int xvcb200_pad_border(xvcb200_ctx *c, int slot) {
 // CU array -> device, plus the shape-class lists of the transform units (host bucketing:
 // shapes are fixed for the picture, only mv / flags change on the device afterwards)
 int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || (!cus && n > 0) || n < 0) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int i = 0; i < n; i++) {
     const xvcb200_cu &u = cus[i];
     const bool pow2 = (u.w & (u.w - 1)) == 0 && (u.h & (u.h - 1)) == 0;
     if (!pow2 || u.w < 4 || u.h < 4 || u.w > 64 || u.h > 64 || u.x < 0 || u.y < 0 || u.x + u.w > c->width ||
-        u.y + u.h > c->height || (u.x & 3) || (u.y & 3))
+        u.y + u.h > c->height || (u.x & 3) || (u.y & 3) || u.ref_idx[0] < -1 || u.ref_idx[0] > 4 || u.ref_idx[1] < -1 ||
+        u.ref_idx[1] > 4)
       return XVCB200_INVALID_ARGUMENT;
   }
+  c->ex.max_ref_idx[0] = c->ex.max_ref_idx[1] = -1;
+  for (int i = 0; i < n; i++)
+    for (int l = 0; l < 2; l++)
+      if (!(cus[i].flags & XVCB200_CU_INTRA) && cus[i].ref_idx[l] > c->ex.max_ref_idx[l]) c->ex.max_ref_idx[l] = cus[i].ref_idx[l];
   c->n_cus = n;
   if (n == 0) { c->ex.h_cus.clear(); return XVCB200_OK; }
   if (!copy_setup(c)) return c->status;
@@ -1062,6 +1128,7 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
 }
 
 int xvcb200_get_cus(xvcb200_ctx *c, xvcb200_cu *cus, int n) {
+  xvcb::DevGuard dev_guard(c);
   if (!c || !cus || n < 0 || n > c->n_cus) return XVCB200_INVALID_ARGUMENT;
   if (!c->check(cudaMemcpyAsync(cus, c->d_cus, sizeof(xvcb200_cu) * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "get_cus"))
     return c->status;
@@ -1123,6 +1190,7 @@ static uint32_t lambda_me_of(double lambda_sqrt) { return (uint32_t)std::floor(6
 
 int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *jobs, int n, double lambda_sqrt,
                       xvcb200_me_result *results) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, orig_slot) || !jobs || !results || n < 0) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int i = 0; i < n; i++)
@@ -1152,6 +1220,7 @@ int xvcb200_me_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_me_job *job
 
 int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearch_job *jobs, int n, double lambda_sqrt,
                         xvcb200_me_result *results) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, orig_slot) || !jobs || !results || n < 0) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int i = 0; i < n; i++)
@@ -1171,6 +1240,7 @@ int xvcb200_full_search(xvcb200_ctx *ctx, int orig_slot, const xvcb200_fullsearc
 
 int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const xvcb200_intra_job *jobs, int n,
                             uint32_t *satd) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, orig_slot) || !slot_ok(ctx, src_slot) || !jobs || !satd || n < 0) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int i = 0; i < n; i++) {
@@ -1195,6 +1265,7 @@ int xvcb200_intra_satd_scan(xvcb200_ctx *ctx, int orig_slot, int src_slot, const
 }
 
 int xvcb200_intra_lm_chroma(xvcb200_ctx *ctx, int rec_slot, const xvcb200_intra_job *jobs, int n, int pred_slot) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, rec_slot) || !slot_ok(ctx, pred_slot) || rec_slot == pred_slot || (!jobs && n > 0) || n < 0) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   for (int i = 0; i < n; i++) {
@@ -1215,29 +1286,35 @@ int xvcb200_intra_lm_chroma(xvcb200_ctx *ctx, int rec_slot, const xvcb200_intra_
   return c->status;
 }
 
+// ref_slots[list][ref_idx] -> plane views.  Every entry a CU of the current array can reference must be
+// a valid slot (false otherwise: the kernels would read another picture or a wild pointer); entries
+// beyond that may be unset and get a placeholder view that is never dereferenced.
 static bool refs_from_slots(xvcb200_ctx *c, const int32_t ref_slots[2][5], Pic3 refs[2][5]) {
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) {
       int s = ref_slots[l][i];
-      if (s < 0 || s >= (int)c->slots.size()) s = 0;   // unused entries: any valid view (never dereferenced)
-      refs[l][i] = pic3(c, s);
+      const bool valid = s >= 0 && s < (int)c->slots.size();
+      if (!valid && i <= full(c)->ex.max_ref_idx[l]) return false;
+      refs[l][i] = pic3(c, valid ? s : 0);
     }
   return true;
 }
 
 int xvcb200_motion_compensate(xvcb200_ctx *c, const int32_t ref_slots[2][5], int pred_slot) {
+  xvcb::DevGuard dev_guard(c);
   if (!slot_ok(c, pred_slot) || !ref_slots) return XVCB200_INVALID_ARGUMENT;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) join_upload_slot(full(c), ref_slots[l][i]);
   join_downloads(full(c), pred_slot);
   Pic3 refs[2][5];
-  refs_from_slots(c, ref_slots, refs);
+  if (!refs_from_slots(c, ref_slots, refs)) return XVCB200_INVALID_ARGUMENT;
   c->check(launch_motion_compensate(c->stream, c->d_cus, c->n_cus, c->bitdepth, refs, pic3(c, pred_slot)), "motion_compensate");
   return c->status;
 }
 
 int xvcb200_motion_compensate_affine(xvcb200_ctx *ctx, const xvcb200_affine_cu *aff, int n, const int32_t ref_slots[2][5],
                                      int pred_slot) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, pred_slot) || !ref_slots || n < 0 || (n > 0 && !aff)) return XVCB200_INVALID_ARGUMENT;
   if (n == 0) return XVCB200_OK;
   CtxFull *c = full(ctx);
@@ -1251,7 +1328,7 @@ int xvcb200_motion_compensate_affine(xvcb200_ctx *ctx, const xvcb200_affine_cu *
   if (!c->check(cudaMemcpyAsync(c->ex.d_affine, aff, sizeof(*aff) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "affine upload"))
     return c->status;
   Pic3 refs[2][5];
-  refs_from_slots(c, ref_slots, refs);
+  if (!refs_from_slots(c, ref_slots, refs)) return XVCB200_INVALID_ARGUMENT;
   c->check(launch_motion_compensate_affine(c->stream, c->d_cus, c->n_cus, c->ex.d_affine, n, c->bitdepth, refs, pic3(c, pred_slot)),
            "motion_compensate_affine");
   return c->status;
@@ -1259,6 +1336,7 @@ int xvcb200_motion_compensate_affine(xvcb200_ctx *ctx, const xvcb200_affine_cu *
 
 int xvcb200_motion_compensate_lic(xvcb200_ctx *ctx, const xvcb200_lic_cu *lic, int n, const int32_t ref_slots[2][5], int rec_slot,
                                   int pred_slot) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, pred_slot) || !slot_ok(ctx, rec_slot) || !ref_slots || n < 0 || (n > 0 && !lic)) return XVCB200_INVALID_ARGUMENT;
   if (n == 0) return XVCB200_OK;
   CtxFull *c = full(ctx);
@@ -1272,7 +1350,7 @@ int xvcb200_motion_compensate_lic(xvcb200_ctx *ctx, const xvcb200_lic_cu *lic, i
   if (!c->check(cudaMemcpyAsync(c->ex.d_lic, lic, sizeof(*lic) * (size_t)n, cudaMemcpyHostToDevice, c->stream), "lic upload"))
     return c->status;
   Pic3 refs[2][5];
-  refs_from_slots(c, ref_slots, refs);
+  if (!refs_from_slots(c, ref_slots, refs)) return XVCB200_INVALID_ARGUMENT;
   c->check(launch_motion_compensate_lic(c->stream, c->d_cus, c->n_cus, c->ex.d_lic, n, c->bitdepth, refs, pic3(c, rec_slot),
                                         pic3(c, pred_slot)), "motion_compensate_lic");
   return c->status;
@@ -1280,6 +1358,7 @@ int xvcb200_motion_compensate_lic(xvcb200_ctx *ctx, const xvcb200_lic_cu *lic, i
 
 static int tq_common(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slot, int coeff_slot, int intra_picture,
                      int table, int off_u, int off_v, int decode_only, xvcb200_tu_result *results) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!slot_ok(ctx, pred_slot) || !slot_ok(ctx, rec_slot) || !slot_ok(ctx, coeff_slot) || (!decode_only && !slot_ok(ctx, orig_slot)))
     return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
@@ -1310,14 +1389,17 @@ static int tq_common(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slo
 
 int xvcb200_tq_reconstruct(xvcb200_ctx *c, int orig_slot, int pred_slot, int rec_slot, int coeff_slot, int pic_qp_unused,
                            int intra_picture, int table, int off_u, int off_v, xvcb200_tu_result *results) {
+  xvcb::DevGuard dev_guard(c);
   (void)pic_qp_unused;
   return tq_common(c, orig_slot, pred_slot, rec_slot, coeff_slot, intra_picture, table, off_u, off_v, 0, results);
 }
 int xvcb200_dequant_reconstruct(xvcb200_ctx *c, int pred_slot, int rec_slot, int coeff_slot, int table, int off_u, int off_v) {
+  xvcb::DevGuard dev_guard(c);
   return tq_common(c, 0, pred_slot, rec_slot, coeff_slot, 0, table, off_u, off_v, 1, nullptr);
 }
 // levels into a coefficient slot (decoder side input)
 int xvcb200_upload_coeff(xvcb200_ctx *c, int slot, const int16_t *const planes[3], const ptrdiff_t strides[3]) {
+  xvcb::DevGuard dev_guard(c);
   return xvcb200_upload_picture(c, slot, reinterpret_cast<const uint16_t *const *>(planes), strides);
 }
 
@@ -1325,10 +1407,12 @@ int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_of
                          int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end);
 int xvcb200_deblock_picture(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset,
                             const int64_t ref_poc[2][5]) {
+  xvcb::DevGuard dev_guard(c);
   return xvcb200_deblock_picture_ex(c, rec_slot, pic_type, beta_offset, tc_offset, 1, 0, 0, ref_poc);
 }
 int xvcb200_deblock_picture_ex(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table,
                                int off_u, int off_v, const int64_t ref_poc[2][5]) {
+  xvcb::DevGuard dev_guard(c);
   if (!c) return XVCB200_INVALID_ARGUMENT;
   return xvcb200_deblock_band(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, 3, 0, c->height);
 }
@@ -1336,10 +1420,12 @@ static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_off
                         int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready);
 int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
                          int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end) {
+  xvcb::DevGuard dev_guard(c);
   return deblock_impl(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, pass_mask, y_begin, y_end, false);
 }
 static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
                         int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready) {
+  xvcb::DevGuard dev_guard(c);
   if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1 || y_begin < 0 || y_end > c->height ||
       y_begin > y_end || (y_begin & 3) || (y_end & 3) || (pass_mask & ~3))
     return XVCB200_INVALID_ARGUMENT;
@@ -1358,6 +1444,7 @@ static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_off
 // per-stage device times of the last xvcb200_encode_picture: ms[0..6] = make jobs, full-pel TZ
 // search, sub-pel search + list decision, motion compensation, T/Q/recon, deblocking, padding
 int xvcb200_set_profiling(xvcb200_ctx *ctx, int enable) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (enable && !c->ex.ev[0])
@@ -1368,6 +1455,7 @@ int xvcb200_set_profiling(xvcb200_ctx *ctx, int enable) {
   return XVCB200_OK;
 }
 int xvcb200_get_stage_times(xvcb200_ctx *ctx, float ms[7]) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || !ms) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   if (!c->ex.ev_valid) return XVCB200_INVALID_ARGUMENT;
@@ -1380,6 +1468,7 @@ int xvcb200_get_stage_times(xvcb200_ctx *ctx, float ms[7]) {
 // ---------------------------------------------------------------- (C) picture pipeline
 int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, xvcb200_me_result *me_results,
                            xvcb200_tu_result *tu_results) {
+  xvcb::DevGuard dev_guard(ctx);
   if (!ctx || !prm) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   const int n = c->n_cus;

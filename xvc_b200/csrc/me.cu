@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "xvcb_interp.cuh"
 #include "xvcb_satd.cuh"
@@ -989,25 +990,38 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
                              uint32_t *d_pool, int pool_cap) {
   if (n <= 0 || n_groups <= 0) return cudaSuccess;
-  static int smem_bytes = 0, num_sms = 0;
-  if (!smem_bytes) {
-    int dev = 0, max_optin = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, tz_search_kernel);
-    smem_bytes = max_optin - (int)fa.sharedSizeBytes - 512;
-    cudaError_t e = cudaFuncSetAttribute(tz_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) { smem_bytes = 0; return e; }
+  // launch configuration per device (a process may hold contexts on several GPUs; the dynamic
+  // shared-memory opt-in is a per-device function attribute)
+  static std::mutex cfg_mutex;
+  static int smem_by_dev[kMaxDevices] = {0}, sms_by_dev[kMaxDevices] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  int smem_bytes, num_sms;
+  {
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    if (!smem_by_dev[dev]) {
+      int max_optin = 0, sms = 0;
+      cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, tz_search_kernel);
+      const int bytes = max_optin - (int)fa.sharedSizeBytes - 512;
+      cudaError_t e = cudaFuncSetAttribute(tz_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) return e;
+      smem_by_dev[dev] = bytes; sms_by_dev[dev] = sms;
+    }
+    smem_bytes = smem_by_dev[dev]; num_sms = sms_by_dev[dev];
   }
   cudaError_t e = cudaMemsetAsync(d_counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return e;
     static const bool want_prof = getenv("XVCB_TZ_PROF") != nullptr;
   // device memory, not managed: the first touch of a managed page from the kernel faults and stalls the
   // SM for ~0.1 ms, which the laps then attribute to whatever phase comes first
-  static unsigned long long *d_prof = nullptr;
-  static unsigned long long prof[24];
+  // (debugging aid, XVCB_TZ_PROF=1: one counter block per device, single-threaded use)
+  static unsigned long long *d_prof_by_dev[kMaxDevices] = {nullptr};
+  unsigned long long prof[24];
+  unsigned long long *&d_prof = d_prof_by_dev[dev];
   if (want_prof && !d_prof) cudaMalloc(&d_prof, sizeof(prof));
   if (want_prof) cudaMemsetAsync(d_prof, 0, sizeof(prof), s);
   const int grid = n_groups < num_sms ? n_groups : num_sms;

@@ -25,6 +25,8 @@
 // device-built job list.  Jobs whose candidates would be moved by InterPrediction::ClipMv
 // (inter_prediction.cc:769-782) or with a 4-sample side go to the generic kernel, which
 // interpolates every candidate on its own exactly as the reference does.
+#include <mutex>
+
 #include "xvcb_interp.cuh"
 #include "xvcb_satd.cuh"
 
@@ -497,25 +499,39 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
                                  xvcb200_me_result *d_res, int *d_lists, cudaStream_t *side, cudaEvent_t *side_ev,
                                  int n_side, cudaEvent_t fork_ev) {
   if (n <= 0) return cudaSuccess;
-  static int num_sms = 0, bytes0 = 0, bytes1 = 0, bytes2 = 0, occ0 = 1, occ1 = 1, occ2 = 1;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    bytes0 = max_team_bytes(256, 0);
-    bytes1 = max_team_bytes(1024, 256);
-    bytes2 = max_team_bytes(4096, 1024);
-    cudaError_t e = cudaFuncSetAttribute(subpel_team_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * bytes0);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes2);
-    if (e != cudaSuccess) { num_sms = 0; return e; }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, subpel_team_kernel<32>, 128, 4 * bytes0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, subpel_team_kernel<128>, 128, bytes1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, subpel_team_kernel<256>, 256, bytes2);
-    if (occ0 < 1) occ0 = 1;
-    if (occ1 < 1) occ1 = 1;
-    if (occ2 < 1) occ2 = 1;
+  // launch configuration per device (see launch_tz_search)
+  struct Cfg { int num_sms = 0, bytes0 = 0, bytes1 = 0, bytes2 = 0, occ0 = 1, occ1 = 1, occ2 = 1; };
+  static std::mutex cfg_mutex;
+  static Cfg cfg_by_dev[kMaxDevices];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  Cfg cfg;
+  {
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    Cfg &c = cfg_by_dev[dev];
+    if (!c.num_sms) {
+      int sms = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      c.bytes0 = max_team_bytes(256, 0);
+      c.bytes1 = max_team_bytes(1024, 256);
+      c.bytes2 = max_team_bytes(4096, 1024);
+      cudaError_t e = cudaFuncSetAttribute(subpel_team_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * c.bytes0);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.bytes1);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.bytes2);
+      if (e != cudaSuccess) return e;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.occ0, subpel_team_kernel<32>, 128, 4 * c.bytes0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.occ1, subpel_team_kernel<128>, 128, c.bytes1);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.occ2, subpel_team_kernel<256>, 256, c.bytes2);
+      if (c.occ0 < 1) c.occ0 = 1;
+      if (c.occ1 < 1) c.occ1 = 1;
+      if (c.occ2 < 1) c.occ2 = 1;
+      c.num_sms = sms;
+    }
+    cfg = c;
   }
+  const int num_sms = cfg.num_sms, bytes0 = cfg.bytes0, bytes1 = cfg.bytes1, bytes2 = cfg.bytes2, occ0 = cfg.occ0, occ1 = cfg.occ1,
+            occ2 = cfg.occ2;
   int *counts = d_lists + kSubpelLists * (size_t)n;
   cudaError_t e = cudaMemsetAsync(counts, 0, 20 * sizeof(int), s);      // list lengths [0..14] + the three fetch counters [16..18]
   if (e != cudaSuccess) return e;

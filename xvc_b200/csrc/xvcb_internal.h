@@ -77,6 +77,22 @@ struct xvcb_ctx_impl {
   void *pinned(size_t bytes);
 };
 
+// Binds the calling thread to the context's device for the duration of an entry point (the CUDA
+// current device is per host thread: the reference's ThreadEncoder workers, or a second context
+// on another GPU of the same process, call in with whatever device was current) and restores it.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(const xvcb_ctx_impl *c) {
+    if (!c) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+  DevGuard(const DevGuard &) = delete;
+  DevGuard &operator=(const DevGuard &) = delete;
+};
+constexpr int kMaxDevices = 64;      // per-device caches of launch configurations (indexed by cudaGetDevice)
+
 struct Pic3 { PlaneView p[3]; };
 inline Pic3 pic3(const xvcb_ctx_impl *c, int slot) {
   Pic3 r; for (int i = 0; i < 3; i++) r.p[i] = c->plane(slot, i); return r;

@@ -13,6 +13,7 @@ from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libxvc_b200.so")
+IPC_HANDLE_BYTES = 80      # XVCB200_IPC_HANDLE_BYTES
 
 c_int, c_void_p, c_double, c_u64 = ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_uint64
 c_ssize = ctypes.c_ssize_t
@@ -41,6 +42,7 @@ EXPORTS = [
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
     "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan", "xvcb200_intra_lm_chroma",
     "xvcb200_ipc_export", "xvcb200_ipc_open_peer", "xvcb200_push_slot", "xvcb200_wait_pushes",
+    "xvcb200_device_count",
 ]
 
 
@@ -49,6 +51,10 @@ class XvcB200Error(RuntimeError):
 
 
 _lib = None
+
+
+def device_count():
+    return int(load().xvcb200_device_count())
 
 
 def load():
@@ -330,12 +336,15 @@ class Context:
         return p.value, n.value
 
     def ipc_export(self):
-        """64-byte handle of the slot arena for the other processes of the node."""
-        h = np.zeros(64, dtype=np.uint8)
+        """Handle of the slot arena (CUDA IPC handle + arena layout, XVCB200_IPC_HANDLE_BYTES) for the other
+        processes of the node."""
+        h = np.zeros(IPC_HANDLE_BYTES, dtype=np.uint8)
         self._ok(self.L.xvcb200_ipc_export(self.h, abi.ptr(h)))
         return h.tobytes()
 
     def ipc_open_peer(self, handle):
+        if len(handle) != IPC_HANDLE_BYTES:
+            raise XvcB200Error("ipc_open_peer: handle must be %d bytes" % IPC_HANDLE_BYTES)
         h = np.frombuffer(handle, dtype=np.uint8).copy()
         self._ok(self.L.xvcb200_ipc_open_peer(self.h, abi.ptr(h), None))
 
