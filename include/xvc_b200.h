@@ -463,11 +463,21 @@ typedef struct {
   int32_t chroma_offset_table, chroma_offset_u, chroma_offset_v;
   int32_t beta_offset, tc_offset;
   int32_t deblock, pad;
+  int32_t bi_iterations;             /* EncoderSettings::bipred_refinement_iterations (encoder_settings.h:70); 0: no bi-prediction */
+  int32_t bits_mode;                 /* 0: the cost of the sub-pel search picks the list (round-1 rule, one picture per list);
+                                        1: InterSearch::GetInterPredBits with fast_inter_pred_bits (inter_search.cc:1084-1130) */
 } xvcb200_picture_params;
 
-/* ME for every (CU, list 0/1 ref_idx 0) with the CU's mv[list] as predictor -> best list
- * by cost -> MC -> T/Q/recon -> deblock -> pad.  Results: per-CU chosen mv/ref written back
- * into the CU array, me_results[2*n] (may be NULL), tu_results[3*n] (may be NULL). */
+/* InterSearch::SearchMotion (inter_search.cc:199-259) for every CU at once -> MC -> T/Q/recon ->
+ * deblock -> pad.  Per list l the num_ref[l] pictures ref_slots[l][0..] are searched (TZ + sub-pel,
+ * search_range[l][r]); a list-1 picture whose POC equals a list-0 picture's is not searched again
+ * (same_poc_in_l0_mapping_, :536-543).  With bi_iterations > 0 (bi-predicted pictures) the
+ * SearchBiIterative passes follow (:392-433: FullSearch +-4 and sub-pel search on the weighted
+ * original 2 * orig - pred(other list)).  The predictor of list l is the CU's mv[l] as uploaded
+ * (one predictor per list); CUs flagged INTRA or SKIP_ME are left as they are.  Results: the
+ * chosen ref_idx / mv written back into the CU array, me_results[n * (num_ref[0] + num_ref[1])]
+ * laid out [cu][list 0 pictures, list 1 pictures] (uni searches; may be NULL), tu_results[3*n]
+ * (may be NULL).  num_ref[l] <= 0 reads as one picture (list 1: none for pic_type 1). */
 int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *params,
                            xvcb200_me_result *me_results, xvcb200_tu_result *tu_results);
 

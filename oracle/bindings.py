@@ -360,6 +360,7 @@ class Ref:
         L.xref_session_get_rec_padded.argtypes = [c_void_p, c_int, c_void_p]
         L.xref_session_set_cus.argtypes = [c_void_p, c_void_p, c_int]
         L.xref_session_get_cus.argtypes = [c_void_p, c_void_p, c_int]
+        L.xref_search_motion_single.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.xref_me_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p]
         L.xref_tz_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
         L.xref_full_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
@@ -625,9 +626,17 @@ class RefSession:
     def pad_border_rec(self):
         self.L.xref_pad_border_rec(self.h)
 
+    def search_motion_single(self, params, cu):
+        """(ref_shim's restated SearchMotion, InterSearch::SearchMotion itself) for a picture holding only `cu`."""
+        out = np.zeros(2, dtype=abi.cu_dtype)
+        costs = np.zeros(2, dtype=np.uint64)
+        one = np.array([cu], dtype=abi.cu_dtype)
+        prm = np.array([params], dtype=abi.picture_params_dtype) if not isinstance(params, np.ndarray) else params
+        self.L.xref_search_motion_single(self.h, abi.ptr(prm), abi.ptr(one), abi.ptr(out), abi.ptr(costs))
+        return out[0], out[1]
+
     def encode_picture(self, params, cus, threads=1):
-        nl = 2 if params["pic_type"] == 0 else 1
-        me = np.zeros(nl * len(cus), dtype=abi.me_result_dtype)
+        me = np.zeros(abi.num_me_columns(params) * len(cus), dtype=abi.me_result_dtype)
         tu = np.zeros(3 * len(cus), dtype=abi.tu_result_dtype)
         out = cus.copy()
         prm = np.array([params], dtype=abi.picture_params_dtype) if not isinstance(params, np.ndarray) else params

@@ -807,38 +807,145 @@ void xref_session_get_rec_padded(xref_session *s, int comp, uint16_t *out) {
 
 // ---------------------------------------------------------------- whole-picture hot path
 // Same step as xvcb200_encode_picture, executed by the reference's own classes:
-// ME (list 0 and 1, ref_idx 0, predictor = cu mv[list]) -> pick list by sub-pel cost
-// (ties -> L0) -> MC -> T/Q/recon -> deblock -> pad.  The control glue mirrors
-// xvc_b200/csrc/pipeline; every sample is produced by reference code.
+// InterSearch::SearchMotion's control flow (inter_search.cc:199-259: SearchRefIdx per list :456-578,
+// SearchBiIterative :392-433, final choice :245-258) around the reference's TzSearch::Search /
+// FullSearch / SubpelSearch / MotionCompensation / SubtractWeighted / GetInterPredBits, with the two
+// simplifications of the batched design (include/xvc_b200.h, xvcb200_picture_params): one predictor
+// per list (the CU's mv[list] as handed over) and previous_fullpel_ = 0 -> MC -> T/Q/recon ->
+// deblock -> pad.  Every sample, distortion and bit count is produced by reference code.
+namespace {
+struct PipeWorker {
+  explicit PipeWorker(xref_session *s)
+      : me(s), base_qp(s->pic_qp, ChromaFormat::k420, s->bitdepth, s->lambda, s->chroma_table, s->off_u, s->off_v),
+        writer(base_qp, s->pic_data->GetPredictionType(), &bw), pred(constants::kMaxBlockSize, constants::kMaxBlockSize) {}
+  MeWorker me;
+  Qp base_qp;
+  BitWriter bw;
+  SyntaxWriter writer;
+  SampleBufferStorage pred;
+};
+
+void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params *p, const int R[2], double lambda, int i,
+                    const xvcb200_cu &in, xvcb200_me_result *res /* J entries */) {
+  CodingUnit *cu = s->cus[i];
+  if (in.flags & (XVCB200_CU_INTRA | XVCB200_CU_SKIP_ME)) return;
+  InterSearch &search = w->me.search;
+  const YuvComponent comp = YuvComponent::kY;
+  Qp qp(cu->GetQp(comp), ChromaFormat::k420, s->bitdepth, lambda, s->chroma_table, s->off_u, s->off_v);
+  const uint32_t lam = static_cast<uint32_t>(std::floor(65536.0 * qp.GetLambdaSqrt()));
+  const MotionVector mvp[2] = {MotionVector(in.mv[0][0], in.mv[0][1]), MotionVector(in.mv[1][0], in.mv[1][1])};
+  const Distortion kMax = std::numeric_limits<Distortion>::max();
+  auto list_of = [](int l) { return static_cast<RefPicList>(l); };
+  auto dir_of = [](int l) { return l == 0 ? InterDir::kL0 : InterDir::kL1; };
+  int uni_ref[2] = {-1, -1}, l1u_ref = -1, bi_ref[2] = {-1, -1};
+  MotionVector uni_mv[2], l1u_mv, bi_mv[2];
+  Distortion cost_uni[2] = {kMax, kMax}, cost_l1u = kMax, cost_bi = kMax;
+  for (int l = 0; l < 2; l++) {
+    cu->SetInterDir(dir_of(l));
+    cu->SetMv(MotionVector(), list_of(1 - l));          // SearchRefIdx clears the other list (:476-480)
+    cu->SetRefIdx(-1, list_of(1 - l));
+    for (int r = 0; r < R[l]; r++) {
+      const int col = l * R[0] + r;
+      const int dup = (l == 1 && p->bits_mode) ? search.same_poc_in_l0_mapping_[r] : -1;
+      if (dup >= 0) {
+        res[col] = res[dup];                              // :536-543
+      } else {
+        xvcb200_me_job job;
+        job.cu = i; job.ref_slot = r; job.list = l; job.search_range = p->search_range[l][r];
+        job.mvp[0] = in.mv[l][0]; job.mvp[1] = in.mv[l][1]; job.prev[0] = job.prev[1] = 0;
+        RunMeJob(s, &w->me, job, lambda, &res[col]);
+      }
+      const MotionVector mv(res[col].mv[0], res[col].mv[1]);
+      Distortion cost = res[col].cost;
+      if (p->bits_mode) {
+        cu->SetRefIdx(r, list_of(l));
+        cu->SetMvpIdx(0, list_of(l));
+        cu->SetMv(mv, list_of(l));
+        search.SetMvd(cu, list_of(l), mvp[l], mv);
+        cost = res[col].dist + ((search.GetInterPredBits(*cu, w->writer) * lam) >> 16);
+      }
+      if (cost < cost_uni[l]) { cost_uni[l] = cost; uni_ref[l] = r; uni_mv[l] = mv; }
+      if (l == 1 && dup < 0 && cost < cost_l1u) { cost_l1u = cost; l1u_ref = r; l1u_mv = mv; }
+    }
+  }
+  if (p->bi_iterations > 0 && uni_ref[0] >= 0 && uni_ref[1] >= 0) {
+    const int x = cu->GetPosX(comp), y = cu->GetPosY(comp), cw = cu->GetWidth(comp), ch = cu->GetHeight(comp);
+    SampleBufferConst orig_luma = s->orig->GetSampleBuffer(comp, x, y);
+    SampleMetric fullpel_metric(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth, search.GetFullpelMetric(*cu));
+    SampleMetric subpel_metric(Simd(s->use_simd, s->bitdepth).sample_metric, s->bitdepth, search.GetSubpelMetric(*cu));
+    for (int l = 0; l < 2; l++) { bi_ref[l] = uni_ref[l]; bi_mv[l] = uni_mv[l]; }
+    int sl = cost_uni[0] <= cost_uni[1] ? 1 : 0;         // the list with the higher uni cost first (:402-403)
+    for (int it = 0; it < p->bi_iterations; it++) {
+      const int other = 1 - sl;
+      cu->SetInterDir(dir_of(other));
+      cu->SetRefIdx(bi_ref[other], list_of(other));
+      cu->SetMv(bi_mv[other], list_of(other));
+      search.MotionCompensation(*cu, comp, &search.bipred_pred_buffer_);
+      search.bipred_orig_buffer_.SubtractWeighted(cw, ch, orig_luma, search.bipred_pred_buffer_);
+      cu->SetInterDir(InterDir::kBi);
+      const Distortion prev_best = cost_bi;
+      for (int r = 0; r < R[sl]; r++) {
+        const int col = sl * R[0] + r;
+        const YuvPicture *ref_pic = s->refs[sl][r].get();
+        const MotionVector bootstrap(res[col].mv[0], res[col].mv[1]);   // GetBestUniPredMv (:497)
+        MvFullpel clip_min, clip_max;
+        search.DetermineMinMaxMv(*cu, *ref_pic, bootstrap, EncoderSettings::inter_search_range_bi, &clip_min, &clip_max);
+        const MvFullpel mv_full = search.FullSearch(*cu, qp, fullpel_metric, mvp[sl], *ref_pic, clip_min, clip_max);
+        Distortion dist = kMax;
+        MotionVector mv;
+        if (cu->GetFullpelMv()) {
+          mv = MotionVector(mv_full);
+          dist = search.GetSubpelDist(*cu, qp, *ref_pic, subpel_metric, mv, search.bipred_orig_buffer_, &w->pred);
+        } else {
+          mv = search.SubpelSearch(*cu, qp, subpel_metric, *ref_pic, mvp[sl], mv_full, search.bipred_orig_buffer_, &w->pred, &dist);
+        }
+        dist >>= 1;                                        // MotionEstNormal, :660
+        if (p->bi_iterations > 1) { res[col].mv[0] = mv.x; res[col].mv[1] = mv.y; }   // SetBestUniPredMv (:549-553)
+        cu->SetRefIdx(r, list_of(sl));
+        cu->SetMvpIdx(0, list_of(sl));
+        cu->SetMvpIdx(0, list_of(other));
+        cu->SetMv(mv, list_of(sl));
+        search.SetMvd(cu, list_of(sl), mvp[sl], mv);
+        search.SetMvd(cu, list_of(other), mvp[other], bi_mv[other]);
+        const Distortion cost = dist + ((search.GetInterPredBits(*cu, w->writer) * lam) >> 16);
+        if (cost < cost_bi) { cost_bi = cost; bi_ref[sl] = r; bi_mv[sl] = mv; }
+      }
+      if (cost_bi == prev_best) break;                    // :425-427
+      sl = other;
+    }
+  }
+  int ref[2] = {-1, -1};
+  MotionVector mv[2];
+  if (p->bi_iterations > 0 && cost_bi != kMax && cost_bi <= cost_uni[0] && cost_bi <= cost_l1u) {
+    for (int l = 0; l < 2; l++) { ref[l] = bi_ref[l]; mv[l] = bi_mv[l]; }
+  } else if (cost_uni[0] <= cost_l1u) {
+    ref[0] = uni_ref[0]; mv[0] = uni_mv[0];
+  } else {
+    ref[1] = l1u_ref; mv[1] = l1u_mv;
+  }
+  for (int l = 0; l < 2; l++) {
+    cu->SetRefIdx(ref[l], list_of(l));
+    cu->SetMv(mv[l], list_of(l));
+  }
+  cu->SetInterDir(ref[0] >= 0 && ref[1] >= 0 ? InterDir::kBi : (ref[1] >= 0 ? InterDir::kL1 : InterDir::kL0));
+}
+}  // namespace
+
 void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const xvcb200_cu *cus_in, int n,
                          int threads, xvcb200_me_result *me_results, xvcb200_tu_result *tu_results,
                          xvcb200_cu *cus_out) {
   xref_session_set_cus(s, cus_in, n);
+  s->pic_data->force_bipred_l1_mvd_zero_ = false;       // the low-delay "L1 mvd = 0" rule is not part of the batched step
+  s->settings.fast_inter_pred_bits = p->bits_mode ? 1 : 0;
   const double lambda = p->lambda_sqrt * p->lambda_sqrt;
-  const int nl = p->pic_type == 0 ? 2 : 1;
-  std::vector<xvcb200_me_job> jobs(static_cast<size_t>(n) * nl);
-  for (int i = 0; i < n; i++)
-    for (int l = 0; l < nl; l++) {
-      xvcb200_me_job &j = jobs[static_cast<size_t>(i) * nl + l];
-      j.cu = i; j.ref_slot = 0; j.list = l; j.search_range = p->search_range[l][0];
-      j.mvp[0] = cus_in[i].mv[l][0]; j.mvp[1] = cus_in[i].mv[l][1];
-      j.prev[0] = 0; j.prev[1] = 0;
-    }
-  std::vector<xvcb200_me_result> res(jobs.size());
+  const int R[2] = {p->num_ref[0] > 0 ? p->num_ref[0] : 1, p->pic_type == 1 ? 0 : (p->num_ref[1] > 0 ? p->num_ref[1] : 1)};
+  const int J = R[0] + R[1];
+  std::vector<xvcb200_me_result> res(static_cast<size_t>(n) * J);
+  std::memset(res.data(), 0, res.size() * sizeof(res[0]));
   // lambda_sqrt is authoritative: build Qp from lambda = lambda_sqrt^2 and check the sqrt
   // round-trips (it does for the values bench.py uses; asserted in tests).
-  xref_me_search(s, jobs.data(), static_cast<int>(jobs.size()), lambda, threads, res.data());
-  for (int i = 0; i < n; i++) {
-    int best = 0;
-    if (nl == 2 && res[2 * i + 1].cost < res[2 * i].cost) best = 1;
-    CodingUnit *cu = s->cus[i];
-    for (int l = 0; l < 2; l++) {
-      cu->SetRefIdx(l == best ? 0 : -1, static_cast<RefPicList>(l));
-      const xvcb200_me_result &r = res[static_cast<size_t>(i) * nl + (nl == 2 ? l : 0)];
-      cu->SetMv(l == best ? MotionVector(r.mv[0], r.mv[1]) : MotionVector(), static_cast<RefPicList>(l));
-    }
-    cu->SetInterDir(best == 0 ? InterDir::kL0 : InterDir::kL1);
-  }
+  ParallelFor<PipeWorker>(n, threads, [s]() { return new PipeWorker(s); },
+                          [&](PipeWorker *w, int i) { SearchMotionCu(s, w, p, R, lambda, i, cus_in[i], &res[static_cast<size_t>(i) * J]); });
   if (me_results) std::memcpy(me_results, res.data(), res.size() * sizeof(res[0]));
   xref_motion_compensate(s, threads);
   xref_tq_reconstruct(s, threads, tu_results);
@@ -847,6 +954,40 @@ void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const
   if (cus_out) {
     std::memcpy(cus_out, cus_in, sizeof(xvcb200_cu) * n);
     xref_session_get_cus(s, cus_out, n);
+  }
+}
+
+// Pins the control flow above to the reference's own InterSearch::SearchMotion: for a picture holding
+// ONE CU (no neighbours: both predictors of GetMvpList are zero, previous_fullpel_ is zero) the two
+// coincide when the CU's predictor is zero.  out[0] = SearchMotionCu, out[1] = InterSearch::SearchMotion
+// (ref_idx / mv of the CU); costs[0..1] likewise.
+void xref_search_motion_single(xref_session *s, const xvcb200_picture_params *p, const xvcb200_cu *cu_in, xvcb200_cu *out,
+                               uint64_t *costs) {
+  xvcb200_cu in = *cu_in;
+  std::memset(in.mv, 0, sizeof(in.mv));
+  xref_session_set_cus(s, &in, 1);
+  s->pic_data->force_bipred_l1_mvd_zero_ = false;
+  s->settings.fast_inter_pred_bits = 1;
+  s->settings.bipred_refinement_iterations = p->bi_iterations;
+  const double lambda = p->lambda_sqrt * p->lambda_sqrt;
+  const int R[2] = {p->num_ref[0] > 0 ? p->num_ref[0] : 1, p->pic_type == 1 ? 0 : (p->num_ref[1] > 0 ? p->num_ref[1] : 1)};
+  std::vector<xvcb200_me_result> res(R[0] + R[1]);
+  CodingUnit *cu = s->cus[0];
+  {
+    PipeWorker w(s);
+    SearchMotionCu(s, &w, p, R, lambda, 0, in, res.data());
+    out[0] = in;
+    xref_session_get_cus(s, &out[0], 1);
+    costs[0] = 0;
+  }
+  {
+    PipeWorker w(s);
+    Qp qp(cu->GetQp(YuvComponent::kY), ChromaFormat::k420, s->bitdepth, lambda, s->chroma_table, s->off_u, s->off_v);
+    const InterSearchFlags flags = (in.flags & XVCB200_CU_FULLPEL_MV) ? InterSearchFlags::kFullPelMv : InterSearchFlags(0);
+    costs[1] = p->pic_type == 1 ? w.me.search.SearchMotion(cu, qp, w.writer, flags | InterSearchFlags::kUniPredOnly, &w.pred)
+                                : w.me.search.SearchMotion(cu, qp, w.writer, flags, &w.pred);
+    out[1] = in;
+    xref_session_get_cus(s, &out[1], 1);
   }
 }
 

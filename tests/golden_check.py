@@ -12,6 +12,13 @@ from xvc_b200 import abi
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "xvc_hotpath_golden.npz")
 
 
+def _picture_params(raw):
+    """Stored picture parameters -> today's struct (fields appended since the vectors were made read as 0)."""
+    buf = np.zeros(abi.picture_params_dtype.itemsize, dtype=np.uint8)
+    buf[:len(raw)] = raw
+    return buf.view(abi.picture_params_dtype).copy()
+
+
 def load():
     z = np.load(GOLDEN)
     cases = json.loads(bytes(z["__cases__"]).decode())
@@ -49,7 +56,7 @@ class OracleBackend:
         jobs = z[c["me_jobs"]].view(abi.me_job_dtype).copy()
         out["me"] = o.me_search(orig, refs, bd, cus, jobs, np.sqrt(c["lam"]))
         cus2 = z[c["enc_cus"]].view(abi.cu_dtype).copy()
-        prm = z[c["enc_prm"]].view(abi.picture_params_dtype).copy()
+        prm = _picture_params(z[c["enc_prm"]])
         pred, rec = Picture(W, H, 80), Picture(W, H, 80)
         lev, me2, tu2 = o.encode_picture(orig, refs, pred, rec, bd, cus2, prm)
         out.update(enc_me=me2, enc_tu=tu2, enc_cus=cus2, enc_rec=rec.full, enc_lev=lev)
@@ -98,7 +105,7 @@ class GpuBackend:
         ctx.set_cus(cus)
         out["me"] = ctx.me_search(0, jobs, np.sqrt(c["lam"]))
         cus2 = z[c["enc_cus"]].view(abi.cu_dtype).copy()
-        prm = z[c["enc_prm"]].view(abi.picture_params_dtype).copy()
+        prm = _picture_params(z[c["enc_prm"]])
         prm["orig_slot"], prm["pred_slot"], prm["rec_slot"], prm["coeff_slot"] = 0, 3, 4, 5
         prm["ref_slots"][0, 0, 0], prm["ref_slots"][0, 1, 0] = 1, (2 if pt == 0 else -1)
         ctx.set_cus(cus2)

@@ -538,3 +538,40 @@ def test_cuda_tables_register_into_reference_tables(ref):
     n = ref.L.xref_table_entries_replaced(2, 10)
     # 8 x 2 interpolation entries; 5 x 6 metric entries (index 0 of the 7 is null in both tables)
     assert n == 16 + 30, n
+
+
+@pytest.mark.parametrize("pic_type,pocs,iters", [(0, ((0, 16), (16, 0)), 1), (0, ((4, 0), (12, 16)), 1), (0, ((0,), (16,)), 4),
+                                                 (0, ((4, 0, 2), (12,)), 2), (1, ((4, 0), ()), 0)])
+def test_search_motion_flow_is_the_references(ref, pic_type, pocs, iters):
+    """The control flow xvcb200_encode_picture is checked against (oracle/ref_shim.cc SearchMotionCu: loops over
+    lists and reference pictures, reuse of list-0 results for repeated POCs, SearchBiIterative, final choice)
+    equals the reference's own InterSearch::SearchMotion wherever the two are comparable: a picture holding a
+    single CU (no neighbours, so both of the reference's predictors are zero, like the CU's predictor here)."""
+    width, height, bd, qp, poc = 136, 72, 10, 32, 8
+    canvas = workload.synth_canvas(width, height, 55)
+    lam = workload.lambda_for_qp(qp)
+    prm = np.zeros(1, dtype=abi.picture_params_dtype)
+    prm["pic_type"], prm["lambda_sqrt"], prm["chroma_offset_table"] = pic_type, np.sqrt(lam), 1
+    prm["bi_iterations"], prm["bits_mode"] = iters, 1
+    for l in range(2):
+        prm["num_ref"][0, l] = len(pocs[l])
+        for r, p in enumerate(pocs[l]):
+            prm["ref_poc"][0, l, r] = p
+            prm["search_range"][0, l, r] = workload.search_range_uni(poc, p)
+    cus = workload.make_partition(width, height, seed=5, min_size=8, qp=qp)
+    n_bi = 0
+    for k in range(0, len(cus), 3):
+        cu = cus[k].copy()
+        if k % 5 == 0:
+            cu["flags"] |= abi.CU_FULLPEL_MV
+        s = ref.session(width, height, bd, pic_type, qp, lam, simd=1, poc=poc, sub_gop=16)
+        s.set_orig(workload.synth_frame(canvas, width, height, poc, bd, frame_noise=4.0))
+        for l in range(2):
+            for r, p in enumerate(pocs[l]):
+                s.add_ref(l, r, p, workload.synth_frame(canvas, width, height, p, bd, frame_noise=4.0))
+        flow, reference = s.search_motion_single(prm, cu)
+        s.close()
+        assert np.array_equal(flow["ref_idx"], reference["ref_idx"]), (k, flow, reference)
+        assert np.array_equal(flow["mv"], reference["mv"]), (k, flow, reference)
+        n_bi += int(flow["ref_idx"][0] >= 0 and flow["ref_idx"][1] >= 0)
+    assert iters == 0 or n_bi > 0

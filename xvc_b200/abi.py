@@ -46,6 +46,7 @@ picture_params_dtype = np.dtype([
     ("pic_type", "<i4"), ("search_range", "<i4", (2, 5)), ("lambda_sqrt", "<f8"),
     ("chroma_offset_table", "<i4"), ("chroma_offset_u", "<i4"), ("chroma_offset_v", "<i4"),
     ("beta_offset", "<i4"), ("tc_offset", "<i4"), ("deblock", "<i4"), ("pad", "<i4"),
+    ("bi_iterations", "<i4"), ("bits_mode", "<i4"),
 ], align=True)
 
 plane_geom_dtype = np.dtype([
@@ -78,6 +79,14 @@ ABI_STRUCTS = {
     9: ("xvcb200_affine_cu", affine_cu_dtype),
     10: ("xvcb200_lic_cu", lic_cu_dtype),
 }
+
+
+def num_me_columns(params):
+    """Search results per CU of xvcb200_encode_picture: one per (list, reference picture)."""
+    prm = params[0] if isinstance(params, np.ndarray) and params.ndim else params
+    r0 = max(int(prm["num_ref"][0]), 1)
+    r1 = 0 if int(prm["pic_type"]) == 1 else max(int(prm["num_ref"][1]), 1)
+    return r0 + r1
 
 
 def ptr(arr):

@@ -420,11 +420,17 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   uint8_t *d_tz_states = nullptr; int tz_states_cap = 0;
   int *d_counter = nullptr;
   int *d_subpel_lists = nullptr; int subpel_lists_cap = 0;   // job lists by block-size class + their counters
-  // the picture pipeline's own grouping (job = cu * nl + list), built by set_cus for nl = 1 and 2
-  int *d_pipe_index[2] = {nullptr, nullptr};
-  int *d_pipe_groups[2] = {nullptr, nullptr};
-  int pipe_n_groups[2] = {0, 0};
-  // Everything set_cus sends ([cus][tu list][index nl=1][index nl=2][groups nl=1][groups nl=2]) is ONE blob,
+  // the picture pipeline's own grouping, built by set_cus: the searched CUs by CTU (jobs are cu * J + column)
+  int *d_pipe_index = nullptr;
+  int *d_pipe_groups = nullptr;
+  int pipe_n_groups = 0;
+  // motion decision of the picture pipeline (me_pipe.cu): per-CU state, the bi-prediction passes' jobs / results,
+  // the int16 weighted original (luma, laid out like a slot's luma plane)
+  uint8_t *d_me_state = nullptr; int me_state_cap = 0;
+  xvcb200_me_job *d_bi_jobs = nullptr; int bi_jobs_cap = 0;
+  xvcb200_me_result *d_bi_res = nullptr; int bi_res_cap = 0;
+  int16_t *d_worig = nullptr;
+  // Everything set_cus sends ([cus][tu list][CU index by CTU][groups]) is ONE blob,
   // double-buffered: the upload for the next picture goes to the other blob on the upload stream
   // while the kernels of the current picture still use theirs.  d_cus / d_tu_list / d_pipe_* point
   // into the current blob.
@@ -598,6 +604,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   for (cudaEvent_t e : c->ex.dl_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
+  cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
@@ -1042,18 +1049,23 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   c->n_cus = n;
   if (n == 0) { c->ex.h_cus.clear(); return XVCB200_OK; }
   if (!copy_setup(c)) return c->status;
-  // CU groups by CTU (counting sort: coding order inside a CTU is kept)
+  // CU groups by CTU (counting sort: coding order inside a CTU is kept).  Only CUs that take part in the
+  // motion search: XVCB200_CU_INTRA / XVCB200_CU_SKIP_ME are set by the host and never searched.
+  auto searched = [&](int i) { return !(cus[i].flags & (XVCB200_CU_INTRA | XVCB200_CU_SKIP_ME)); };
   const int ctus_x = (c->width + 63) >> 6, n_ctus = ctus_x * ((c->height + 63) >> 6);
   std::vector<int> ctu_first((size_t)n_ctus + 1, 0), by_ctu((size_t)n);
-  for (int i = 0; i < n; i++) ctu_first[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6)) + 1]++;
+  for (int i = 0; i < n; i++)
+    if (searched(i)) ctu_first[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6)) + 1]++;
   int n_groups = 0;
   for (int t = 0; t < n_ctus; t++) { n_groups += ctu_first[(size_t)t + 1] != 0; ctu_first[(size_t)t + 1] += ctu_first[(size_t)t]; }
   {
     std::vector<int> fill(ctu_first.begin(), ctu_first.end() - 1);
-    for (int i = 0; i < n; i++) by_ctu[(size_t)fill[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6))]++] = i;
+    for (int i = 0; i < n; i++)
+      if (searched(i)) by_ctu[(size_t)fill[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6))]++] = i;
   }
-  // blob layout: [cus][tu list 3n][index nl=1: n][index nl=2: 2n][groups nl=1: 2g][groups nl=2: 4g]
-  const size_t ints = 3 * (size_t)n + 3 * (size_t)n + 6 * (size_t)n_groups;
+  const int n_search = ctu_first[(size_t)n_ctus];
+  // blob layout: [cus][tu list 3n][CU index by CTU: n][groups: 2g]
+  const size_t ints = 3 * (size_t)n + (size_t)n + 2 * (size_t)n_groups;
   const size_t need = sizeof(xvcb200_cu) * (size_t)n + sizeof(int) * ints;
   const int nb = c->ex.cur_blob < 0 ? 0 : c->ex.cur_blob ^ 1;
   CtxExtra::CuBlob &B = c->ex.blob[nb];
@@ -1077,10 +1089,10 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   }
   xvcb200_cu *hc = static_cast<xvcb200_cu *>(B.h);
   int *list = reinterpret_cast<int *>(hc + n);
-  int *idx1 = list + 3 * (size_t)n, *idx2 = idx1 + n, *grp1 = idx2 + 2 * (size_t)n, *grp2 = grp1 + 2 * (size_t)n_groups;
+  int *idx1 = list + 3 * (size_t)n, *grp1 = idx1 + n;
   memcpy(hc, cus, sizeof(xvcb200_cu) * (size_t)n);
   c->ex.h_cus.assign(cus, cus + n);
-  for (int i = 0; i < n; i++) { idx1[i] = by_ctu[(size_t)i]; idx2[i] = 2 * by_ctu[(size_t)i]; idx2[n + i] = 2 * by_ctu[(size_t)i] + 1; }
+  for (int i = 0; i < n; i++) idx1[i] = i < n_search ? by_ctu[(size_t)i] : 0;
   // Groups are handed to the persistent search CTAs in this order: longest first (cost grows with
   // the number of jobs), so that the groups still running when the counter runs out are the short ones.
   std::vector<int> ctu_order;
@@ -1092,12 +1104,9 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   });
   for (int g = 0; g < n_groups; g++) {
     const int t = ctu_order[(size_t)g];
-    const int first = ctu_first[(size_t)t], cnt = ctu_first[(size_t)t + 1] - first;
-    grp1[2 * g] = first; grp1[2 * g + 1] = cnt;
-    grp2[4 * g] = first; grp2[4 * g + 1] = cnt;                 // list 0 ...
-    grp2[4 * g + 2] = n + first; grp2[4 * g + 3] = cnt;         // ... and list 1 of the same CTU
+    grp1[2 * g] = ctu_first[(size_t)t]; grp1[2 * g + 1] = ctu_first[(size_t)t + 1] - ctu_first[(size_t)t];
   }
-  c->ex.pipe_n_groups[0] = n_groups; c->ex.pipe_n_groups[1] = 2 * n_groups;
+  c->ex.pipe_n_groups = n_groups;
   auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
   memset(c->ex.class_count, 0, sizeof(c->ex.class_count));
   for (int i = 0; i < n; i++)
@@ -1120,10 +1129,8 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   c->d_cus = reinterpret_cast<xvcb200_cu *>(B.d);
   int *dl = reinterpret_cast<int *>(c->d_cus + n);
   c->ex.d_tu_list = dl;
-  c->ex.d_pipe_index[0] = dl + 3 * (size_t)n;
-  c->ex.d_pipe_index[1] = c->ex.d_pipe_index[0] + n;
-  c->ex.d_pipe_groups[0] = c->ex.d_pipe_index[1] + 2 * (size_t)n;
-  c->ex.d_pipe_groups[1] = c->ex.d_pipe_groups[0] + 2 * (size_t)n_groups;
+  c->ex.d_pipe_index = dl + 3 * (size_t)n;
+  c->ex.d_pipe_groups = c->ex.d_pipe_index + n;
   return XVCB200_OK;
 }
 
@@ -1472,25 +1479,56 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   if (!ctx || !prm) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   const int n = c->n_cus;
-  const int nl = prm->pic_type == 0 ? 2 : 1;
   if (!slot_ok(c, prm->orig_slot) || !slot_ok(c, prm->pred_slot) || !slot_ok(c, prm->rec_slot) || !slot_ok(c, prm->coeff_slot) ||
-      prm->pic_type < 0 || prm->pic_type > 1 || !slot_ok(c, prm->ref_slots[0][0]) || (nl == 2 && !slot_ok(c, prm->ref_slots[1][0])))
+      prm->pic_type < 0 || prm->pic_type > 1 || prm->num_ref[0] > 5 || prm->num_ref[1] > 5 || prm->bi_iterations < 0 ||
+      prm->bi_iterations > 8 || prm->bits_mode < 0 || prm->bits_mode > 1)
     return XVCB200_INVALID_ARGUMENT;
+  // InterSearch::SearchMotion's loops over lists and reference pictures (inter_search.cc:199-259, 456-578)
+  MePipe P;
+  memset(&P, 0, sizeof(P));
+  P.n = n;
+  P.R[0] = prm->num_ref[0] > 0 ? prm->num_ref[0] : 1;
+  P.R[1] = prm->pic_type == 1 ? 0 : (prm->num_ref[1] > 0 ? prm->num_ref[1] : 1);
+  P.J = P.R[0] + P.R[1]; P.Rmax = P.R[0] > P.R[1] ? P.R[0] : P.R[1];
+  P.pic_uni = prm->pic_type == 1; P.bits_mode = prm->bits_mode; P.bitdepth = c->bitdepth;
+  P.bi_iterations = P.R[1] > 0 ? prm->bi_iterations : 0;
+  P.lambda = lambda_me_of(prm->lambda_sqrt);
+  if (P.bits_mode == 0 && (P.R[0] > 1 || P.R[1] > 1 || P.bi_iterations > 0)) return XVCB200_INVALID_ARGUMENT;
+  int cols[10], n_cols = 0;
+  for (int l = 0; l < 2; l++)
+    for (int r = 0; r < P.R[l]; r++) {
+      // GetSearchRangeUniPred yields 96..256; the search kernel holds a pass of <= 9 rounds
+      if (!slot_ok(c, prm->ref_slots[l][r]) || prm->search_range[l][r] < 1 || prm->search_range[l][r] > 256) return XVCB200_INVALID_ARGUMENT;
+      P.ref_slot[l][r] = prm->ref_slots[l][r]; P.range[l][r] = prm->search_range[l][r];
+      if (l == 1) {       // ReferencePictureLists::GetSamePocMappingFor (reference_picture_lists.cc:105-122); one picture per list (bits_mode 0): always searched
+        P.dup_of[r] = -1;
+        for (int q = 0; q < P.R[0] && P.bits_mode; q++)
+          if (prm->ref_poc[1][r] == prm->ref_poc[0][q]) { P.dup_of[r] = q; break; }
+        if (P.dup_of[r] >= 0 && prm->ref_slots[1][r] != prm->ref_slots[0][P.dup_of[r]]) return XVCB200_INVALID_ARGUMENT;
+      }
+      if (l == 0 || P.dup_of[r] < 0) cols[n_cols++] = l * P.R[0] + r;
+    }
   if (n == 0) return XVCB200_OK;
-  if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, n * nl) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, n * nl) ||
-      !ensure(c, &c->ex.d_tu, &c->ex.tu_res_cap, 3 * n))
+  const int nj = n * P.J, nbj = n * P.Rmax;
+  if (!ensure(c, &c->ex.d_jobs, &c->ex.jobs_cap, nj) || !ensure(c, &c->ex.d_me, &c->ex.me_cap, nj) ||
+      !ensure(c, &c->ex.d_tu, &c->ex.tu_res_cap, 3 * n) ||
+      !ensure(c, &c->ex.d_me_state, &c->ex.me_state_cap, (int)(n * me_cu_state_bytes())))
     return c->status;
-  const int slots[2] = {prm->ref_slots[0][0], nl == 2 ? prm->ref_slots[1][0] : prm->ref_slots[0][0]};
-  const int ranges[2] = {prm->search_range[0][0], prm->search_range[1][0]};
-  for (int l = 0; l < nl; l++)      // GetSearchRangeUniPred yields 96..256; the search kernel holds a pass of <= 9 rounds
-    if (ranges[l] < 1 || ranges[l] > 256) return XVCB200_INVALID_ARGUMENT;
-  if (!ensure_tz_scratch(c, n * nl)) return c->status;
+  if (P.bi_iterations > 0) {
+    if (!ensure(c, &c->ex.d_bi_jobs, &c->ex.bi_jobs_cap, nbj) || !ensure(c, &c->ex.d_bi_res, &c->ex.bi_res_cap, nbj)) return c->status;
+    if (!c->ex.d_worig &&
+        !c->check(cudaMalloc(&c->ex.d_worig, sizeof(int16_t) * (size_t)c->geom.pitch[0] * c->height), "cudaMalloc(weighted original)"))
+      return c->status;
+  }
+  if (!ensure_tz_scratch(c, nj)) return c->status;
   join_upload_slot(c, prm->orig_slot);           // explicit read set: an upload made ahead for the NEXT picture is not waited for
-  for (int l = 0; l < nl; l++) join_upload_slot(c, prm->ref_slots[l][0]);
+  for (int l = 0; l < 2; l++)
+    for (int r = 0; r < P.R[l]; r++) join_upload_slot(c, prm->ref_slots[l][r]);
   join_downloads(c, prm->pred_slot);
   join_downloads(c, prm->rec_slot);
   join_downloads(c, prm->coeff_slot);
   join_downloads(c, -1);
+  for (int l = 0; l < 2; l++) c->ex.max_ref_idx[l] = std::max(c->ex.max_ref_idx[l], P.R[l] - 1);
   int stage = 0;
   auto mark = [&]() { if (c->ex.profile) cudaEventRecord(c->ex.ev[stage], c->stream); stage++; };
   mark();   // 0: start
@@ -1502,22 +1540,34 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
     cudaStreamWaitEvent(c->ex.side[2], c->ex.fork_ev, 0);
     c->check(launch_cu_map(c->ex.side[2], c->d_cus, n, c->d_cu_map, c->map_w, c->map_h), "cu_map");
   }
-  c->check(launch_make_me_jobs(c->stream, c->d_cus, n, nl, slots, ranges, c->ex.d_jobs), "make_me_jobs");
+  const PlaneView orig = c->plane(prm->orig_slot, 0);
+  c->check(launch_make_me_jobs(c->stream, c->d_cus, P, c->ex.d_jobs), "make_me_jobs");
   mark();   // 1: jobs built
-  {
-    c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                              c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_pipe_index[nl - 1],
-                              c->ex.d_pipe_groups[nl - 1], c->ex.pipe_n_groups[nl - 1], c->ex.d_tz_states, c->ex.d_counter,
-                              c->ex.d_pool, c->ex.pool_cap), "tz_search");
-  }
+  c->check(launch_tz_search(c->stream, c->d_cus, c->ex.d_jobs, nj, c->bitdepth, P.lambda, orig, c->ex.d_luma_views, c->ex.d_me,
+                            c->ex.d_pipe_index, c->ex.d_pipe_groups, c->ex.pipe_n_groups, c->ex.d_tz_states, c->ex.d_counter,
+                            c->ex.d_pool, c->ex.pool_cap, P.J, n_cols, cols), "tz_search");
   mark();   // 2: full-pel search done
-  c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, n * nl, c->bitdepth, lambda_me_of(prm->lambda_sqrt),
-                                c->plane(prm->orig_slot, 0), c->ex.d_luma_views, c->ex.d_me, c->ex.d_subpel_lists, c->ex.side,
-                                c->ex.side_ev, c->ex.n_side, c->ex.fork_ev), "subpel_search");
-  c->check(launch_me_decide(c->stream, c->d_cus, n, nl, c->ex.d_me), "me_decide");
-  mark();   // 3: sub-pel search + list decision done
+  c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, nj, c->bitdepth, P.lambda, orig, c->ex.d_luma_views, c->ex.d_me,
+                                c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev, c->ex.n_side, c->ex.fork_ev), "subpel_search");
+  c->check(launch_me_uni_decide(c->stream, c->d_cus, P, c->ex.d_me, c->ex.d_me_state), "me_uni_decide");
+  if (P.bi_iterations > 0) {
+    PlaneView worig = orig;
+    worig.base = reinterpret_cast<Sample *>(c->ex.d_worig);
+    for (int it = 0; it < P.bi_iterations; it++) {
+      c->check(launch_bi_prepare(c->stream, c->d_cus, P, it, c->ex.d_me, c->ex.d_me_state, orig, c->ex.d_luma_views, worig,
+                                 c->ex.d_bi_jobs), "bi_prepare");
+      c->check(launch_full_search_worig(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
+                                        c->ex.d_bi_res), "full_search");
+      c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
+                                    c->ex.d_bi_res, c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev, c->ex.n_side, c->ex.fork_ev),
+               "subpel_search(bi)");
+      c->check(launch_me_bi_decide(c->stream, c->d_cus, P, c->ex.d_bi_res, c->ex.d_me, c->ex.d_me_state), "me_bi_decide");
+    }
+  }
+  c->check(launch_me_final_decide(c->stream, c->d_cus, P, c->ex.d_me_state), "me_final_decide");
+  mark();   // 3: sub-pel search + decision done
   Pic3 refs[2][5];
-  refs_from_slots(c, prm->ref_slots, refs);
+  if (!refs_from_slots(c, prm->ref_slots, refs)) return XVCB200_INVALID_ARGUMENT;
   c->check(launch_motion_compensate(c->stream, c->d_cus, n, c->bitdepth, refs, pic3(c, prm->pred_slot)), "motion_compensate");
   mark();   // 4: prediction done
   int st = tq_common(c, prm->orig_slot, prm->pred_slot, prm->rec_slot, prm->coeff_slot, 0, prm->chroma_offset_table,
@@ -1534,7 +1584,7 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   mark();   // 7: padding done
   c->ex.ev_valid = c->ex.profile;
   if (me_results)
-    c->check(cudaMemcpyAsync(me_results, c->ex.d_me, sizeof(*me_results) * (size_t)n * nl, cudaMemcpyDeviceToHost, c->stream), "me results");
+    c->check(cudaMemcpyAsync(me_results, c->ex.d_me, sizeof(*me_results) * (size_t)nj, cudaMemcpyDeviceToHost, c->stream), "me results");
   if (tu_results)
     c->check(cudaMemcpyAsync(tu_results, c->ex.d_tu, sizeof(*tu_results) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream), "tu results");
   return c->status;   // asynchronous: xvcb200_sync() completes it

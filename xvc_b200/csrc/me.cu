@@ -452,6 +452,11 @@ constexpr int kSegWords = 256;           // segment sums of the blocks being bou
 
 struct TzGroup { int first, count; };    // run of entries in job_index: jobs sharing a reference picture and a CTU
 
+// Picture pipeline: jobs are laid out [cu][J] (J = reference pictures searched per CU); `groups` then
+// describes runs of the CU list `job_index` (the CUs of one CTU) and launch group G stands for run
+// G / n of it searched on job column j[G % n].  J == 0: `job_index` holds job indices, one run per group.
+struct TzJobSel { int J, n, j[10]; };
+
 struct SJob {                            // one job of the current group, in shared memory
   int ji;
   short x, y; unsigned char w, h, depth, fullpel;
@@ -495,7 +500,7 @@ __device__ __forceinline__ MeGeom sjob_geom(const SJob &j, int bitdepth, uint32_
 __global__ void __launch_bounds__(kTzThreads, 1)
 tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
                  const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
-                 int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
+                 const __grid_constant__ TzJobSel sel, int *__restrict__ counter, int bitdepth, uint32_t lambda, PlaneView orig,
                  const PlaneView *__restrict__ ref_planes,
                  xvcb200_me_result *__restrict__ res, TzJobState *__restrict__ states, int region_budget_words,
                  uint32_t *__restrict__ pool_all, int pool_cap, unsigned long long *__restrict__ prof) {
@@ -527,8 +532,10 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     __syncthreads();
     const int grp = s_group;
     if (grp >= n_groups) break;
-    const TzGroup G = groups[grp];
-    const int ref_slot = jobs[job_index[G.first]].ref_slot;
+    const TzGroup G = groups[sel.J ? grp / sel.n : grp];
+    const int jcol = sel.J ? sel.j[grp % sel.n] : 0;
+    auto job_of = [&](int k) { const int e = job_index[G.first + k]; return sel.J ? e * sel.J + jcol : e; };
+    const int ref_slot = jobs[job_of(0)].ref_slot;
     const PlaneView ref = ref_planes[ref_slot];
 
     for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
@@ -542,7 +549,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       __syncthreads();
       // job descriptors -> shared memory; bounding box of the search windows (block extent included)
       for (int k = tid; k < kn; k += kTzThreads) {
-        const int ji = job_index[G.first + k0 + k];
+        const int ji = job_of(k0 + k);
         const xvcb200_me_job job = jobs[ji];
         const xvcb200_cu cu = cus[job.cu];
         SJob &sj = s_job[k];
@@ -988,8 +995,13 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
-                             uint32_t *d_pool, int pool_cap) {
+                             uint32_t *d_pool, int pool_cap, int J, int n_cols, const int *cols) {
   if (n <= 0 || n_groups <= 0) return cudaSuccess;
+  TzJobSel sel;
+  sel.J = J; sel.n = J ? n_cols : 1;
+  for (int k = 0; k < 10; k++) sel.j[k] = (J && k < n_cols) ? cols[k] : 0;
+  if (J) n_groups *= n_cols;
+  if (n_groups <= 0) return cudaSuccess;
   // launch configuration per device (a process may hold contexts on several GPUs; the dynamic
   // shared-memory opt-in is a per-device function attribute)
   static std::mutex cfg_mutex;
@@ -1028,7 +1040,7 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   const int fixed_words = kTileWords + kSegWords + kMaxGroupJobs * (int)(sizeof(SJob) / 4);
   g_launch_count++;
   tz_search_kernel<<<grid, kTzThreads, smem_bytes, s>>>(
-      d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, d_counter, bitdepth, lambda_me, orig,
+      d_cus, d_jobs, d_job_index, static_cast<const TzGroup *>(d_groups), n_groups, sel, d_counter, bitdepth, lambda_me, orig,
       d_ref_planes, d_res, static_cast<TzJobState *>(d_states), smem_bytes / 4 - fixed_words, d_pool, pool_cap,
       want_prof ? d_prof : nullptr);
   if (want_prof) {
@@ -1048,118 +1060,5 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
 }
 size_t tz_state_bytes() { return sizeof(TzJobState); }
 int tz_max_ctas() { int dev = 0, n = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
-
-// ---------------------------------------------------------------- bi-prediction full search
-// InterSearch::FullSearch (inter_search.cc:853-891): every full-pel position of the clipped
-// +-range window, row-major, on the weighted original 2*orig - other_pred
-// (ResidualBuffer::SubtractWeighted, sample_buffer.h:147-161).  One warp per job, one
-// candidate per lane pass; metric on int16 vs Sample.
-__global__ void __launch_bounds__(128) full_search_kernel(const xvcb200_cu *__restrict__ cus,
-                                                          const xvcb200_fullsearch_job *__restrict__ jobs, int n,
-                                                          int bitdepth, uint32_t lambda, PlaneView orig,
-                                                          const PlaneView *__restrict__ planes,
-                                                          xvcb200_me_result *__restrict__ res) {
-  __shared__ int16_t worig[4][64 * 64];
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const int ji = blockIdx.x * 4 + wi;
-  if (ji >= n) return;
-  const xvcb200_fullsearch_job job = jobs[ji];
-  const xvcb200_cu cu = cus[job.cu];
-  const PlaneView ref = planes[job.ref_slot], other = planes[job.other_pred_slot];
-  const int w = cu.w, h = cu.h;
-  int16_t *wo = worig[wi];
-  for (int i = lane; i < w * h; i += 32) {
-    const int y = i / w, x = i - y * w;
-    wo[y * 64 + x] = (int16_t)(2 * (int)orig.base[(cu.y + y) * orig.pitch + cu.x + x] -
-                               (int)other.base[(cu.y + y) * other.pitch + cu.x + x]);
-  }
-  __syncwarp();
-  int lo[2], hi[2];
-  min_max_mv(cu.x, cu.y, ref.width, ref.height, job.center[0], job.center[1], job.range, lo, hi);
-  const bool fast = h > 8;
-  const int rows = fast ? h >> 1 : h, rstep = fast ? 2 : 1;
-  const int down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
-  const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, total = nx * ny;
-  const Sample *ref0 = ref.base + cu.y * ref.pitch + cu.x;
-  uint32_t best = 0xffffffffu;
-  int bx = 0, by = 0;
-  for (int t0 = 0; t0 < total; t0 += 32) {
-    const int t = t0 + lane;
-    uint32_t key = 0xffffffffu;
-    int cx = 0, cy = 0;
-    if (t < total) {
-      cy = lo[1] + t / nx; cx = lo[0] + t % nx;
-      const Sample *r = ref0 + cy * ref.pitch + cx;
-      uint32_t sad = 0;
-      for (int y = 0; y < rows; y++)
-        for (int x = 0; x < w; x++) sad += abs((int)wo[y * rstep * 64 + x] - (int)__ldg(r + y * rstep * ref.pitch + x));
-      const uint32_t dist = fast ? (sad * 2) >> (bitdepth - 8) : sad >> (bitdepth - 8);
-      const uint32_t cost = dist + ((lambda * mvd_bits_fullpel(job.mvp[0], job.mvp[1], cx, cy, down)) >> 16);
-      key = (cost << 5) | lane;
-    }
-    const uint32_t win = __reduce_min_sync(XVCB_FULL, key);
-    if (win != 0xffffffffu && (win >> 5) < best) {
-      best = win >> 5;
-      bx = __shfl_sync(XVCB_FULL, cx, win & 31);
-      by = __shfl_sync(XVCB_FULL, cy, win & 31);
-    }
-  }
-  if (lane == 0) {
-    res[ji].mv_fullpel[0] = bx; res[ji].mv_fullpel[1] = by;
-    res[ji].mv[0] = bx * 16; res[ji].mv[1] = by * 16;
-    res[ji].cost_fullpel = best; res[ji].dist = 0; res[ji].cost = best; res[ji].num_sad = total;
-  }
-}
-
-cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_fullsearch_job *d_jobs, int n,
-                               int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_planes,
-                               xvcb200_me_result *d_res) {
-  if (n <= 0) return cudaSuccess;
-  g_launch_count++;
-  full_search_kernel<<<(n + 3) / 4, 128, 0, s>>>(d_cus, d_jobs, n, bitdepth, lambda_me, orig, d_planes, d_res);
-  return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------- picture pipeline glue
-// jobs for (CU i, list l, ref_idx 0) with the CU's mv[l] as predictor
-__global__ void make_me_jobs_kernel(const xvcb200_cu *__restrict__ cus, int n, int nl, int slot0, int slot1, int range0,
-                                    int range1, xvcb200_me_job *__restrict__ jobs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * nl) return;
-  const int c = i / nl, l = i - c * nl;
-  xvcb200_me_job j;
-  j.cu = c; j.ref_slot = l ? slot1 : slot0; j.search_range = l ? range1 : range0;
-  j.mvp[0] = cus[c].mv[l][0]; j.mvp[1] = cus[c].mv[l][1];
-  j.prev[0] = 0; j.prev[1] = 0; j.list = l;
-  jobs[i] = j;
-}
-
-cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, int n, int nl, const int ref_slot[2],
-                                const int range[2], xvcb200_me_job *d_jobs) {
-  if (n <= 0) return cudaSuccess;
-  g_launch_count++;
-  make_me_jobs_kernel<<<(n * nl + 255) / 256, 256, 0, s>>>(d_cus, n, nl, ref_slot[0], ref_slot[1], range[0], range[1], d_jobs);
-  return cudaGetLastError();
-}
-
-// best list by sub-pel cost (ties -> L0); the loser is cleared like SearchRefIdx does for
-// uni-prediction (inter_search.cc:476-480)
-__global__ void me_decide_kernel(xvcb200_cu *__restrict__ cus, int n, int nl, const xvcb200_me_result *__restrict__ res) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int best = (nl == 2 && res[2 * i + 1].cost < res[2 * i].cost) ? 1 : 0;
-  for (int l = 0; l < 2; l++) {
-    cus[i].ref_idx[l] = (int8_t)(l == best ? 0 : -1);
-    cus[i].mv[l][0] = l == best ? res[i * nl + l].mv[0] : 0;
-    cus[i].mv[l][1] = l == best ? res[i * nl + l].mv[1] : 0;
-  }
-}
-
-cudaError_t launch_me_decide(cudaStream_t s, xvcb200_cu *d_cus, int n, int nl, const xvcb200_me_result *d_res) {
-  if (n <= 0) return cudaSuccess;
-  g_launch_count++;
-  me_decide_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, n, nl, d_res);
-  return cudaGetLastError();
-}
 
 }  // namespace xvcb

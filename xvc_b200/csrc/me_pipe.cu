@@ -1,0 +1,367 @@
+// The motion search of the picture pipeline around the search kernels (me.cu, subpel.cu):
+// InterSearch::SearchMotion (inter_search.cc:199-259) for every CU of a picture at once.
+//
+//   uni-prediction   SearchRefIdx (inter_search.cc:456-578) per list: every reference picture of the
+//                    list is searched (TZ + sub-pel, MotionEstNormal :606-662), a list-1 picture with
+//                    the POC of a list-0 picture reuses that result (same_poc_in_l0_mapping_, :536-543)
+//                    and does not count as a "unique" list-1 candidate (:568-571).
+//   bi-prediction    SearchBiIterative (:392-433): the list with the higher uni cost is searched
+//                    first against the weighted original 2 * orig - pred(other list)
+//                    (ResidualBuffer::SubtractWeighted, sample_buffer.h:147-161) with FullSearch
+//                    (:853-891, +-inter_search_range_bi = 4 around the list's best uni vector) and the
+//                    sub-pel search on the same int16 original; distortion halved (:660); lists
+//                    alternate until an iteration brings no gain.
+//   decision         bi if its cost is <= both uni costs, else list 0 unless unique list 1 is
+//                    cheaper (:245-258).
+//
+// Rate: the reference's CABAC-independent estimate (GetInterPredBits with fast_inter_pred_bits,
+// inter_search.cc:1084-1130): uni = (1 | 3) + ref_idx bits + 1 (mvp flag) + exp-Golomb(mvd), bi = 5 +
+// both lists' ref_idx bits + 1 + exp-Golomb(mvd); cost = dist + ((bits * lambda) >> 16).  The
+// predictor of a list is the vector the CU array carries in mv[list] when the picture is handed
+// over (one predictor per list: the mvp list of the reference collapsed to its first entry).
+// bits_mode 0 keeps round 1's rule (the cost of the sub-pel search alone picks list 0 or 1).
+//
+// CUs flagged XVCB200_CU_INTRA or XVCB200_CU_SKIP_ME take no part: no job of theirs is searched and
+// their mv / ref_idx are left as the host set them.
+#include "xvcb_interp.cuh"
+
+namespace xvcb {
+
+struct MeCuState {
+  int32_t uni_mv[2][2];      // best uni-prediction vector per list (list 1: over all its pictures)
+  int32_t l1u_mv[2];         // best vector among the unique list-1 pictures
+  int32_t bi_mv[2][2];       // bi-prediction state (SearchBiIterative's CU state)
+  uint32_t cost_uni[2], cost_l1u, cost_bi;
+  int8_t uni_ref[2], l1u_ref, bi_ref[2];
+  int8_t search_list, active, bi_done;
+};
+size_t me_cu_state_bytes() { return sizeof(MeCuState); }
+
+__device__ __forceinline__ bool cu_searched(const xvcb200_cu &cu) {
+  return !(cu.flags & (XVCB200_CU_INTRA | XVCB200_CU_SKIP_ME));
+}
+__device__ __forceinline__ uint32_t ref_idx_bits(int r, int R) { return R <= 1 ? 0u : (uint32_t)(r + 1 - (r == R - 1)); }
+__device__ __forceinline__ uint32_t mvd_bits_down(const int32_t mvp[2], const int32_t mv[2], int down) {
+  return exp_golomb_bits((mv[0] - mvp[0]) >> (2 + down)) + exp_golomb_bits((mv[1] - mvp[1]) >> (2 + down));
+}
+
+// jobs[cu * J + j]; search_range = 0 marks a job that is not searched
+__global__ void make_me_jobs_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
+                                    xvcb200_me_job *__restrict__ jobs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n * P.J) return;
+  const int c = i / P.J, jc = i - c * P.J;
+  const int l = jc >= P.R[0] ? 1 : 0, r = l ? jc - P.R[0] : jc;
+  const xvcb200_cu cu = cus[c];
+  xvcb200_me_job j;
+  j.cu = c; j.ref_slot = P.ref_slot[l][r];
+  j.search_range = (!cu_searched(cu) || (l == 1 && P.dup_of[r] >= 0)) ? 0 : P.range[l][r];
+  j.mvp[0] = cu.mv[l][0]; j.mvp[1] = cu.mv[l][1];
+  j.prev[0] = 0; j.prev[1] = 0; j.list = l;
+  jobs[i] = j;
+}
+
+cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_job *d_jobs) {
+  if (P.n <= 0) return cudaSuccess;
+  g_launch_count++;
+  make_me_jobs_kernel<<<(P.n * P.J + 255) / 256, 256, 0, s>>>(d_cus, P, d_jobs);
+  return cudaGetLastError();
+}
+
+// SearchRefIdx per list on the finished uni searches (a thread per CU)
+__global__ void me_uni_decide_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
+                                     xvcb200_me_result *__restrict__ res, MeCuState *__restrict__ state) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  const xvcb200_cu cu = cus[i];
+  MeCuState st;
+  memset(&st, 0, sizeof(st));
+  st.active = cu_searched(cu) ? 1 : 0;
+  st.uni_ref[0] = st.uni_ref[1] = st.l1u_ref = st.bi_ref[0] = st.bi_ref[1] = -1;
+  st.cost_uni[0] = st.cost_uni[1] = st.cost_l1u = st.cost_bi = 0xffffffffu;
+  if (st.active) {
+    const int down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
+    for (int l = 0; l < 2; l++)
+      for (int r = 0; r < P.R[l]; r++) {
+        const int j = l ? P.R[0] + r : r;
+        const bool dup = l == 1 && P.dup_of[r] >= 0;
+        xvcb200_me_result q = res[(size_t)i * P.J + (dup ? P.dup_of[r] : j)];
+        if (dup) res[(size_t)i * P.J + j] = q;          // unipred_best_mv_[L1][r] = the list-0 vector (:536-549)
+        uint32_t cost = q.cost;
+        if (P.bits_mode) {
+          const uint32_t bits = (P.pic_uni ? 1u : 3u) + ref_idx_bits(r, P.R[l]) + 1u + mvd_bits_down(cu.mv[l], q.mv, down);
+          cost = q.dist + ((bits * P.lambda) >> 16);
+        }
+        if (cost < st.cost_uni[l]) { st.cost_uni[l] = cost; st.uni_ref[l] = (int8_t)r; st.uni_mv[l][0] = q.mv[0]; st.uni_mv[l][1] = q.mv[1]; }
+        if (l == 1 && !dup && cost < st.cost_l1u) { st.cost_l1u = cost; st.l1u_ref = (int8_t)r; st.l1u_mv[0] = q.mv[0]; st.l1u_mv[1] = q.mv[1]; }
+      }
+  }
+  state[i] = st;
+}
+
+cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_result *d_res, void *d_state) {
+  if (P.n <= 0) return cudaSuccess;
+  g_launch_count++;
+  me_uni_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, d_res, static_cast<MeCuState *>(d_state));
+  return cudaGetLastError();
+}
+
+// One CTA per CU: prediction of the list that is kept (luma, uni-prediction: MotionCompensation with
+// InterDir = that list, inter_search.cc:415-418), weighted original into `worig`, jobs of the list
+// that is searched.  job.prev carries the bootstrap vector (GetBestUniPredMv, :497) in 1/16 pel.
+__global__ void __launch_bounds__(128) bi_prepare_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
+                                                         int iteration, const xvcb200_me_result *__restrict__ res,
+                                                         MeCuState *__restrict__ state, PlaneView orig,
+                                                         const PlaneView *__restrict__ luma, PlaneView worig,
+                                                         xvcb200_me_job *__restrict__ bi_jobs) {
+  __shared__ int16_t tmp[64 * 71];
+  __shared__ Sample pred[64 * 64];
+  __shared__ int s_sl;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const xvcb200_cu cu = cus[i];
+  MeCuState *st = &state[i];
+  const bool run = st->active && !st->bi_done && st->uni_ref[0] >= 0 && st->uni_ref[1] >= 0;
+  if (tid == 0) {
+    int sl = st->search_list;
+    if (run && iteration == 0) {
+      // the list with the higher uni cost first (:402-403); CU state = best of both lists (:231-233)
+      sl = st->cost_uni[0] <= st->cost_uni[1] ? 1 : 0;
+      st->search_list = (int8_t)sl;
+      for (int l = 0; l < 2; l++) { st->bi_ref[l] = st->uni_ref[l]; st->bi_mv[l][0] = st->uni_mv[l][0]; st->bi_mv[l][1] = st->uni_mv[l][1]; }
+    }
+    if (!run && !st->bi_done) st->bi_done = 1;
+    s_sl = sl;
+    for (int r = 0; r < P.Rmax; r++) {
+      xvcb200_me_job j;
+      j.cu = i; j.list = sl; j.ref_slot = 0; j.search_range = 0;
+      j.mvp[0] = cu.mv[sl][0]; j.mvp[1] = cu.mv[sl][1]; j.prev[0] = j.prev[1] = 0;
+      if (run && r < P.R[sl]) {
+        const xvcb200_me_result q = res[(size_t)i * P.J + (sl ? P.R[0] + r : r)];
+        j.ref_slot = P.ref_slot[sl][r];
+        j.search_range = 4;                              // encoder_settings.h:65 inter_search_range_bi
+        j.prev[0] = q.mv[0]; j.prev[1] = q.mv[1];
+      }
+      bi_jobs[(size_t)i * P.Rmax + r] = j;
+    }
+  }
+  __syncthreads();
+  if (!run) return;
+  const int other = 1 - s_sl;
+  const PlaneView rp = luma[P.ref_slot[other][st->bi_ref[other]]];
+  int mx = st->bi_mv[other][0], my = st->bi_mv[other][1];
+  clip_mv(cu.x, cu.y, rp.width, rp.height, mx, my);
+  const Sample *r = rp.base + (cu.y + (my >> 4)) * rp.pitch + cu.x + (mx >> 4);
+  interp_cta<false, 8>(cu.w, cu.h, P.bitdepth, mx & 15, my & 15, r, rp.pitch, pred, 64, tmp, tid, 128);
+  __syncthreads();
+  const int lw = 31 - __clz((int)cu.w);
+  int16_t *dst = reinterpret_cast<int16_t *>(worig.base);
+  for (int k = tid; k < cu.w * cu.h; k += 128) {
+    const int y = k >> lw, x = k & (cu.w - 1);
+    dst[(cu.y + y) * worig.pitch + cu.x + x] = (int16_t)(2 * (int)orig.base[(cu.y + y) * orig.pitch + cu.x + x] - (int)pred[y * 64 + x]);
+  }
+}
+
+cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_result *d_res,
+                              void *d_state, PlaneView orig, const PlaneView *d_luma_views, PlaneView worig, xvcb200_me_job *d_bi_jobs) {
+  if (P.n <= 0) return cudaSuccess;
+  g_launch_count++;
+  bi_prepare_kernel<<<P.n, 128, 0, s>>>(d_cus, P, iteration, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig, d_bi_jobs);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- InterSearch::FullSearch
+// Every full-pel position of the clipped +-range window around the bootstrap vector, row-major, on
+// the int16 weighted original (SampleMetric on Residual vs Sample: SAD, or SAD over every second
+// row x 2 for blocks higher than 8, inter_search.cc:1059-1069).  One CTA of 128 threads per job:
+// the window (w + 2 range) x (h + 2 range) and the weighted original are staged in shared memory
+// as packed 16-bit pairs, both biased by 2^bitdepth so that the signed difference becomes an
+// unsigned one (|a - b| = max - min per 16-bit lane, VIMNMX.U16x2); a thread per candidate.
+constexpr int kFsRange = 8;                                   // largest range served (the reference searches +-4)
+constexpr int kFsWinPitch = (64 + 2 * kFsRange) / 2 + 3;      // words per window row incl. the word the funnel shift reads ahead; odd: rows land in different banks
+constexpr int kFsOrgPitch = 33;
+
+__device__ __forceinline__ uint32_t fs_absdiff2(uint32_t a, uint32_t b) { return __vmaxu2(a, b) - __vminu2(a, b); }
+
+template <class GetWorig>
+__device__ __forceinline__ void full_search_cta(const xvcb200_cu &cu, int ref_w, int ref_h, const Sample *ref_base, int ref_pitch,
+                                                int mvpx, int mvpy, int cx16, int cy16, int range, int bitdepth, uint32_t lambda,
+                                                GetWorig get_worig, uint32_t *s_win, uint32_t *s_org, unsigned long long *s_best,
+                                                xvcb200_me_result *out) {
+  const int tid = threadIdx.x;
+  const int w = cu.w, h = cu.h;
+  int lo[2], hi[2];
+  min_max_mv(cu.x, cu.y, ref_w, ref_h, cx16, cy16, range, lo, hi);
+  const int nx = hi[0] - lo[0] + 1, ny = hi[1] - lo[1] + 1, total = nx * ny;
+  const uint32_t bias = (uint32_t)1 << bitdepth, bias2 = bias | (bias << 16);
+  const int fast = h > 8, rstep = fast ? 2 : 1, rows = fast ? h >> 1 : h;
+  // window rows that the metric visits: candidate row offsets 0 .. ny-1 plus block rows 0, rstep, ...
+  const int wx0 = (cu.x + lo[0]) & ~1;                       // even start: aligned 32-bit loads
+  const int wpairs = ((cu.x + hi[0] + w + 1) >> 1) - (wx0 >> 1);
+  const int wrows = h + ny - 1;
+  if (tid == 0) *s_best = ~0ull;
+  for (int k = tid; k < wrows * wpairs; k += 128) {
+    const int y = k / wpairs, x = k - y * wpairs;
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(ref_base + (cu.y + lo[1] + y) * ref_pitch + wx0) + x);
+    s_win[y * kFsWinPitch + x] = v + bias2;
+  }
+  const int lw2 = 30 - __clz(w);
+  for (int k = tid; k < (rows << lw2); k += 128) {
+    const int y = (k >> lw2) * rstep, x = (k & ((w >> 1) - 1)) * 2;
+    const uint32_t a = (uint32_t)(get_worig(x, y) + (int)bias) & 0xffffu, b = (uint32_t)(get_worig(x + 1, y) + (int)bias) & 0xffffu;
+    s_org[(k >> lw2) * kFsOrgPitch + (x >> 1)] = a | (b << 16);
+  }
+  __syncthreads();
+  const int down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
+  for (int t = tid; t < total; t += 128) {
+    const int cyi = t / nx, cxi = t - cyi * nx;
+    const int ox = cu.x + lo[0] + cxi - wx0;                 // sample offset of the candidate inside the window row
+    const int sh = (ox & 1) << 4;
+    const uint32_t *wp = s_win + cyi * kFsWinPitch + (ox >> 1);
+    uint32_t sad = 0;
+    for (int r = 0; r < rows; r++) {
+      const uint32_t *wr = wp + r * rstep * kFsWinPitch, *op = s_org + r * kFsOrgPitch;
+      uint32_t prev = wr[0];
+      for (int c = 0; c < (w >> 1); c += 4) {                // <= 4 differences of <= 3 * 2^bitdepth per 16-bit lane
+        uint32_t acc = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (c + u < (w >> 1)) {
+            const uint32_t nxt = wr[c + u + 1];
+            acc += fs_absdiff2(op[c + u], __funnelshift_r(prev, nxt, sh));
+            prev = nxt;
+          }
+        }
+        sad += (acc & 0xffffu) + (acc >> 16);
+      }
+    }
+    const uint32_t dist = fast ? (sad * 2) >> (bitdepth - 8) : sad >> (bitdepth - 8);
+    const int cx = lo[0] + cxi, cy = lo[1] + cyi;
+    const uint32_t cost = dist + ((lambda * mvd_bits_fullpel(mvpx, mvpy, cx, cy, down)) >> 16);
+    atomicMin(s_best, ((unsigned long long)cost << 32) | (unsigned)t);     // first minimum in scan order (:868-886)
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned long long b = *s_best;
+    const int t = (int)(b & 0xffffffffu);
+    const int bx = lo[0] + t % nx, by = lo[1] + t / nx;
+    out->mv_fullpel[0] = bx; out->mv_fullpel[1] = by;
+    out->mv[0] = bx * 16; out->mv[1] = by * 16;
+    out->cost_fullpel = (uint32_t)(b >> 32); out->dist = 0; out->cost = (uint32_t)(b >> 32); out->num_sad = (uint32_t)total;
+  }
+}
+
+__global__ void __launch_bounds__(128) full_search_worig_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
+                                                                int bitdepth, uint32_t lambda, PlaneView worig,
+                                                                const PlaneView *__restrict__ luma, xvcb200_me_result *__restrict__ res) {
+  __shared__ uint32_t s_win[(64 + 2 * kFsRange) * kFsWinPitch];
+  __shared__ uint32_t s_org[64 * kFsOrgPitch];
+  __shared__ unsigned long long s_best;
+  const xvcb200_me_job job = jobs[blockIdx.x];
+  if (job.search_range == 0) return;
+  const xvcb200_cu cu = cus[job.cu];
+  const PlaneView ref = luma[job.ref_slot];
+  const int16_t *wo = reinterpret_cast<const int16_t *>(worig.base) + cu.y * worig.pitch + cu.x;
+  const int wp = worig.pitch;
+  full_search_cta(cu, ref.width, ref.height, ref.base, ref.pitch, job.mvp[0], job.mvp[1], job.prev[0], job.prev[1],
+                  min(job.search_range, kFsRange), bitdepth, lambda, [&](int x, int y) { return (int)wo[y * wp + x]; }, s_win, s_org,
+                  &s_best, &res[blockIdx.x]);
+}
+
+cudaError_t launch_full_search_worig(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
+                                     uint32_t lambda_me, PlaneView worig, const PlaneView *d_luma_views, xvcb200_me_result *d_res) {
+  if (n <= 0) return cudaSuccess;
+  g_launch_count++;
+  full_search_worig_kernel<<<n, 128, 0, s>>>(d_cus, d_jobs, bitdepth, lambda_me, worig, d_luma_views, d_res);
+  return cudaGetLastError();
+}
+
+// xvcb200_full_search: the same search for explicit jobs, weighted original = 2 * orig - luma of other_pred_slot
+__global__ void __launch_bounds__(128) full_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_fullsearch_job *__restrict__ jobs,
+                                                          int bitdepth, uint32_t lambda, PlaneView orig,
+                                                          const PlaneView *__restrict__ planes, xvcb200_me_result *__restrict__ res) {
+  __shared__ uint32_t s_win[(64 + 2 * kFsRange) * kFsWinPitch];
+  __shared__ uint32_t s_org[64 * kFsOrgPitch];
+  __shared__ unsigned long long s_best;
+  const xvcb200_fullsearch_job job = jobs[blockIdx.x];
+  const xvcb200_cu cu = cus[job.cu];
+  const PlaneView ref = planes[job.ref_slot], other = planes[job.other_pred_slot];
+  const Sample *po = orig.base + cu.y * orig.pitch + cu.x, *pp = other.base + cu.y * other.pitch + cu.x;
+  const int opitch = orig.pitch, ppitch = other.pitch;
+  full_search_cta(cu, ref.width, ref.height, ref.base, ref.pitch, job.mvp[0], job.mvp[1], job.center[0], job.center[1], job.range,
+                  bitdepth, lambda, [&](int x, int y) { return 2 * (int)po[y * opitch + x] - (int)pp[y * ppitch + x]; }, s_win, s_org,
+                  &s_best, &res[blockIdx.x]);
+}
+
+cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_fullsearch_job *d_jobs, int n,
+                               int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_planes,
+                               xvcb200_me_result *d_res) {
+  if (n <= 0) return cudaSuccess;
+  g_launch_count++;
+  full_search_kernel<<<n, 128, 0, s>>>(d_cus, d_jobs, bitdepth, lambda_me, orig, d_planes, d_res);
+  return cudaGetLastError();
+}
+
+// SearchRefIdx of one SearchBiIterative pass on the finished bi searches (a thread per CU)
+__global__ void me_bi_decide_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
+                                    const xvcb200_me_result *__restrict__ bi_res, xvcb200_me_result *__restrict__ res,
+                                    MeCuState *__restrict__ state) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  MeCuState st = state[i];
+  if (!st.active || st.bi_done) return;
+  const xvcb200_cu cu = cus[i];
+  const int down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
+  const int sl = st.search_list, other = 1 - sl;
+  const uint32_t prev_best = st.cost_bi;
+  const uint32_t bits_other = ref_idx_bits(st.bi_ref[other], P.R[other]) + 1u + mvd_bits_down(cu.mv[other], st.bi_mv[other], down);
+  for (int r = 0; r < P.R[sl]; r++) {
+    const xvcb200_me_result q = bi_res[(size_t)i * P.Rmax + r];
+    if (P.bi_iterations > 1) {                      // SetBestUniPredMv also after a bi search (:549-553)
+      xvcb200_me_result *u = &res[(size_t)i * P.J + (sl ? P.R[0] + r : r)];
+      u->mv[0] = q.mv[0]; u->mv[1] = q.mv[1];
+    }
+    const uint32_t bits = 5u + bits_other + ref_idx_bits(r, P.R[sl]) + 1u + mvd_bits_down(cu.mv[sl], q.mv, down);
+    const uint32_t cost = (q.dist >> 1) + ((bits * P.lambda) >> 16);       // MotionEstNormal halves the bi distortion (:660)
+    if (cost < st.cost_bi) { st.cost_bi = cost; st.bi_ref[sl] = (int8_t)r; st.bi_mv[sl][0] = q.mv[0]; st.bi_mv[sl][1] = q.mv[1]; }
+  }
+  if (st.cost_bi == prev_best) st.bi_done = 1;      // :425-427
+  st.search_list = (int8_t)other;                   // :428
+  state[i] = st;
+}
+
+cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_result *d_bi_res,
+                                xvcb200_me_result *d_res, void *d_state) {
+  if (P.n <= 0) return cudaSuccess;
+  g_launch_count++;
+  me_bi_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, d_bi_res, d_res, static_cast<MeCuState *>(d_state));
+  return cudaGetLastError();
+}
+
+// SearchMotion's final choice (:245-258) written into the CU array
+__global__ void me_final_decide_kernel(xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
+                                       const MeCuState *__restrict__ state) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  const MeCuState st = state[i];
+  if (!st.active) return;
+  xvcb200_cu *cu = &cus[i];
+  int8_t ref[2] = {-1, -1};
+  int32_t mv[2][2] = {{0, 0}, {0, 0}};
+  if (P.bi_iterations > 0 && st.cost_bi != 0xffffffffu && st.cost_bi <= st.cost_uni[0] && st.cost_bi <= st.cost_l1u) {
+    for (int l = 0; l < 2; l++) { ref[l] = st.bi_ref[l]; mv[l][0] = st.bi_mv[l][0]; mv[l][1] = st.bi_mv[l][1]; }
+  } else if (st.cost_uni[0] <= st.cost_l1u) {
+    ref[0] = st.uni_ref[0]; mv[0][0] = st.uni_mv[0][0]; mv[0][1] = st.uni_mv[0][1];
+  } else {
+    ref[1] = st.l1u_ref; mv[1][0] = st.l1u_mv[0]; mv[1][1] = st.l1u_mv[1];
+  }
+  for (int l = 0; l < 2; l++) { cu->ref_idx[l] = ref[l]; cu->mv[l][0] = mv[l][0]; cu->mv[l][1] = mv[l][1]; }
+}
+
+cudaError_t launch_me_final_decide(cudaStream_t s, xvcb200_cu *d_cus, const MePipe &P, const void *d_state) {
+  if (P.n <= 0) return cudaSuccess;
+  g_launch_count++;
+  me_final_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, static_cast<const MeCuState *>(d_state));
+  return cudaGetLastError();
+}
+
+}  // namespace xvcb

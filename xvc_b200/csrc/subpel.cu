@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) subpel_generic_kernel(const xvcb200_cu *_
                                                              xvcb200_me_result *__restrict__ res) {
   __shared__ int16_t tmp[64 * 71];
   __shared__ Sample pred[64 * 64];
-  __shared__ Sample org[64 * 64];
+  __shared__ int16_t org[64 * 64];       // original block, or the int16 weighted original of a bi-prediction pass
   __shared__ unsigned part[4];
   const int tid = threadIdx.x;
   const int n_list = *count;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) subpel_generic_kernel(const xvcb200_cu *_
     __syncthreads();
     for (int i = tid; i < w * h; i += 128) {
       const int y = i >> lw, x = i & (w - 1);
-      org[y * 64 + x] = orig.base[(cu.y + y) * orig.pitch + cu.x + x];
+      org[y * 64 + x] = (int16_t)orig.base[(cu.y + y) * orig.pitch + cu.x + x];
     }
     const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;
     const bool fullpel_only = (cu.flags & XVCB200_CU_FULLPEL_MV) != 0;
@@ -110,7 +110,7 @@ constexpr int kSubpelLists = 15;
 __global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
                                        int *__restrict__ lists, int *__restrict__ counts) {
   const int ji = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ji >= n) return;
+  if (ji >= n || jobs[ji].search_range == 0) return;       // range 0: a column that is not searched (see MePipe)
   const xvcb200_cu cu = cus[jobs[ji].cu];
   const int area = (int)cu.w * cu.h;
   int seg;
@@ -187,7 +187,7 @@ template <int T> __device__ __forceinline__ void team_sync() {
 // (packed two bits per candidate in `offs`).  The candidates are stacked into one list of tile
 // rows so that small blocks still fill the team.
 template <int TW, int TH>
-__device__ __forceinline__ void satd_stacked(const Sample *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
+__device__ __forceinline__ void satd_stacked(const int16_t *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
                                              int w, int h, int tid, int nthreads, unsigned (&acc)[4]) {
   const int ltx = 31 - __clz(w / TW);
   const int lper = ltx + (31 - __clz(h));      // log2(tile rows per candidate)
@@ -200,7 +200,8 @@ __device__ __forceinline__ void satd_stacked(const Sample *org, int op, const Sa
     const int tile = gi / TH, r = gi % TH;
     const int tx = (tile & ((1 << ltx) - 1)) * TW, ty = (tile >> ltx) * TH + r;
     const int ox = (offs >> (2 * c)) & 1, oy = (offs >> (2 * c + 1)) & 1;
-    const Sample *po = org + ty * op + tx, *pq = pred + (ty + oy) * pp + tx + ox;
+    const int16_t *po = org + ty * op + tx;
+    const Sample *pq = pred + (ty + oy) * pp + tx + ox;
     int v[TW];
 #pragma unroll
     for (int i = 0; i < TW; i++) v[i] = active ? (int)po[i] - (int)pq[i] : 0;
@@ -238,7 +239,7 @@ __device__ __forceinline__ void satd_stacked(const Sample *org, int op, const Sa
 
 // Tile choice by block shape (sample_metric.cc:322-387) for sides >= 8, then the team-wide sums.
 template <int T>
-__device__ __forceinline__ void satd_candidates(const Sample *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
+__device__ __forceinline__ void satd_candidates(const int16_t *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
                                                 int w, int h, int tid, unsigned *s_part, unsigned (&sum)[4]) {
   unsigned acc[4] = {0, 0, 0, 0};
   if (w > h) satd_stacked<16, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
     Sample *sref = reinterpret_cast<Sample *>(base);
     int16_t *tmp = reinterpret_cast<int16_t *>(sref + (h + 9) * RP);
     Sample *pred = reinterpret_cast<Sample *>(tmp + (h + 9) * TP);
-    Sample *org = pred + (h + 1) * PP;
+    int16_t *org = reinterpret_cast<int16_t *>(pred + (h + 1) * PP);    // signed: also holds a weighted original
     team_sync<T>();                      // the previous job of this team is done with the buffers
     // reference window: rows Y0-4 .. Y0+h+3, columns from the even sample at or left of X0-4
     // (aligned 32-bit loads; `co` = 0/1 is where X0-4 sits in the staged row), original block.

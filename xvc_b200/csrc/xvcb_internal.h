@@ -137,18 +137,45 @@ struct TqParams {
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                              uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes, xvcb200_me_result *d_res,
                              const int *d_job_index, const void *d_groups, int n_groups, void *d_states, int *d_counter,
-                             uint32_t *d_pool, int pool_cap);
+                             uint32_t *d_pool, int pool_cap, int J = 0, int n_cols = 0, const int *cols = nullptr);
 // subpel.cu
 cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n,
                                  int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_ref_planes,
                                  xvcb200_me_result *d_res, int *d_lists /* 15n + 32 ints of scratch */,
                                  cudaStream_t *side, cudaEvent_t *side_ev, int n_side, cudaEvent_t fork_ev);
+// (orig may be a plane of int16 weighted-original samples: the kernels read it as signed 16 bit;
+//  jobs with search_range == 0 are skipped)
+
+// me_pipe.cu: the motion search of the picture pipeline around the search kernels.  Jobs / results are laid
+// out [cu][J]: column j < R[0] = (list 0, ref_idx j), else (list 1, ref_idx j - R[0]).
+struct MePipe {
+  int n, J, R[2], Rmax;
+  int ref_slot[2][5], range[2][5];
+  int dup_of[5];            // list-1 ref_idx -> list-0 ref_idx with the same POC (searched once), -1: unique
+  int pic_uni;              // 1: uni-predicted picture
+  int bits_mode;            // 0: legacy (cost of the sub-pel search decides); 1: fast_inter_pred_bits rule
+  int bi_iterations;        // SearchBiIterative passes (0: no bi-prediction)
+  int bitdepth;
+  uint32_t lambda;
+};
+struct MeCuState;            // per-CU decision state (me_pipe.cu)
+size_t me_cu_state_bytes();
+cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_job *d_jobs);
+cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_result *d_res, void *d_state);
+// one pass of InterSearch::SearchBiIterative for every CU still refining: weighted original of the list
+// that is kept -> luma plane of `worig` (int16), jobs of the list that is searched -> d_bi_jobs [cu][Rmax]
+cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_result *d_res,
+                              void *d_state, PlaneView orig, const PlaneView *d_luma_views, PlaneView worig, xvcb200_me_job *d_bi_jobs);
+// InterSearch::FullSearch on the weighted original for jobs [0, n): mv_fullpel / cost_fullpel of d_res
+cudaError_t launch_full_search_worig(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
+                                     uint32_t lambda_me, PlaneView worig, const PlaneView *d_luma_views, xvcb200_me_result *d_res);
+cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_result *d_bi_res,
+                                xvcb200_me_result *d_res, void *d_state);
+cudaError_t launch_me_final_decide(cudaStream_t s, xvcb200_cu *d_cus, const MePipe &P, const void *d_state);
+// xvcb200_full_search (API): weighted original built per job from `orig` and the luma plane of other_pred_slot
 cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_fullsearch_job *d_jobs, int n,
                                int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_planes,
                                xvcb200_me_result *d_res);
-cudaError_t launch_me_decide(cudaStream_t s, xvcb200_cu *d_cus, int n, int nl, const xvcb200_me_result *d_res);
-cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, int n, int nl, const int ref_slot[2],
-                                const int range[2], xvcb200_me_job *d_jobs);
 
 // intra.cu
 cudaError_t launch_intra_ref(cudaStream_t s, int w, int h, int bitdepth, const int nb[5], const Sample *d_edges, Sample *d_ref,

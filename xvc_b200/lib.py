@@ -522,8 +522,7 @@ class Context:
 
     def encode_picture(self, params, want_results=True):
         prm = params if isinstance(params, np.ndarray) else np.array([params], dtype=abi.picture_params_dtype)
-        nl = 2 if int(prm["pic_type"][0]) == 0 else 1
-        me = np.zeros(nl * self.n_cus, dtype=abi.me_result_dtype) if want_results else None
+        me = np.zeros(abi.num_me_columns(prm) * self.n_cus, dtype=abi.me_result_dtype) if want_results else None
         tu = np.zeros(3 * self.n_cus, dtype=abi.tu_result_dtype) if want_results else None
         self._ok(self.L.xvcb200_encode_picture(self.h, abi.ptr(prm), abi.ptr(me), abi.ptr(tu)))
         return me, tu

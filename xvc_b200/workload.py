@@ -27,10 +27,16 @@ def synth_canvas(width, height, seed=1234):
     return np.clip(np.rint(box), 0, 255).astype(np.uint16)
 
 
-def synth_frame(canvas, width, height, index, bitdepth=10):
-    """Returns (Y, U, V) uint16 planes (tight) of frame `index`."""
+def synth_frame(canvas, width, height, index, bitdepth=10, frame_noise=0.0):
+    """Returns (Y, U, V) uint16 planes (tight) of frame `index`.  frame_noise > 0 adds N(0, frame_noise)
+    (8-bit units, seeded by the frame index) to the luma crop before chroma is derived: camera noise that
+    does not follow the pan, so that no reference picture predicts a block exactly (residuals to code,
+    bi-prediction averaging two noisy references pays off -- as on real video)."""
     ox, oy = (2 * index) % 32, index % 32
     y8 = canvas[oy:oy + height, ox:ox + width].astype(np.int32)
+    if frame_noise > 0:
+        rng = np.random.default_rng([977, int(index) & 0xffff, width, height])
+        y8 = np.clip(y8 + np.rint(rng.normal(0.0, frame_noise, size=y8.shape)).astype(np.int32), 0, 255)
     sub = (y8[0::2, 0::2] + y8[0::2, 1::2] + y8[1::2, 0::2] + y8[1::2, 1::2] + 2) >> 2
     u8 = np.clip(np.rint(128 + 0.25 * (sub - 128)), 0, 255).astype(np.int32)
     v8 = np.clip(np.rint(128 - 0.25 * (sub - 128)), 0, 255).astype(np.int32)
@@ -164,3 +170,24 @@ def search_range_uni(poc, ref_poc, sub_gop_length=16, rmin=96, rmax=256):
     """InterSearch::GetSearchRangeUniPred, inter_search.cc:1050-1057."""
     r = (rmax * abs(poc - ref_poc) + sub_gop_length // 2) // sub_gop_length
     return max(rmin, min(rmax, r))
+
+
+def true_motion(poc, ref_poc):
+    """Displacement of the synthetic content between frame `poc` and frame `ref_poc` (1/16 pel)."""
+    return (16 * ((2 * poc) % 32 - (2 * ref_poc) % 32), 16 * (poc % 32 - ref_poc % 32))
+
+
+def set_predictors(cus, poc, ref_pocs, seed=0, jitter=6, exact=0.5):
+    """Predictor field of a picture: cus[i].mv[list] = the content's motion towards the first picture of
+    the list, exact for a fraction `exact` of the CUs and off by up to `jitter`/16 pel for the rest -- what
+    a neighbour-derived predictor looks like on panned content.  ref_pocs = (poc of L0[0], poc of L1[0] or None)."""
+    rng = np.random.default_rng(seed)
+    n = len(cus)
+    for l, rp in enumerate(ref_pocs):
+        if rp is None:
+            continue
+        mv = np.array(true_motion(poc, rp), dtype=np.int32)
+        noise = rng.integers(-jitter, jitter + 1, size=(n, 2)).astype(np.int32)
+        noise[rng.random(n) < exact] = 0
+        cus["mv"][:, l, :] = mv[None, :] + noise
+    return cus
