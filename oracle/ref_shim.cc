@@ -489,6 +489,10 @@ void xref_session_set_cus(xref_session *s, const xvcb200_cu *cus, int n) {
     const xvcb200_cu &d = cus[i];
     CodingUnit *cu = s->pic_data->CreateCu(CuTree::Primary, d.depth, d.x, d.y, d.w, d.h);
     cu->SetPredMode((d.flags & XVCB200_CU_INTRA) ? PredictionMode::kIntra : PredictionMode::kInter);
+    if (d.flags & XVCB200_CU_INTRA) {      // DC: the mode-dependent coefficient scan stays diagonal (transform.cc:1614-1636)
+      cu->SetIntraModeLuma(IntraMode::kDc);
+      cu->SetIntraModeChroma(IntraChromaMode::kDmChroma);
+    }
     cu->SetQp(d.qp);
     cu->SetFullpelMv((d.flags & XVCB200_CU_FULLPEL_MV) != 0);
     cu->SetCbf(YuvComponent::kY, (d.flags & XVCB200_CU_CBF_Y) != 0);
