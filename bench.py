@@ -1,11 +1,17 @@
 #!/usr/bin/env python3
 """bench.py -- the xvc hot path on B200: encoded Mpixels/s at 1080p qp32.
 
-A step = one inter (bi-predicted) picture through the whole hot path
-    ME (TZ full-pel + sub-pel, 2 reference pictures) -> list decision -> motion compensation
+A step = one bi-predicted picture through the whole hot path
+    InterSearch::SearchMotion for every CU (TZ full-pel + sub-pel search on every reference picture of
+    both lists, SearchBiIterative: FullSearch + sub-pel on the weighted original, uni / bi decision)
+    -> motion compensation (uni and bi-predicted CUs)
     -> residual / forward transform / QuantFast / dequant / inverse transform / reconstruction
     -> deblocking -> border padding
 on a seeded CU partition of a synthetic 1920x1080 4:2:0 picture, 10-bit internal, qp 32.
+--workload encode (default): xvc's default reference lists at POC 8 of a sub-GOP of 16 (two pictures per
+list), one bi-prediction pass, predictors near the content's motion, camera noise on every frame.
+--workload raster: round 1's step (one picture per list, zero predictors -> the raster scan of the
++-128 window fires for most CUs, list chosen by the sub-pel cost, noise-free pan).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]      our arm (CUDA through the C ABI)
   python bench.py --impl reference ...                      the reference's own CPU code on the
@@ -37,23 +43,47 @@ POC, REF_POCS, SUB_GOP = 8, (0, 16), 16
 METRIC = "encoded Mpixels/sec at 1080p qp32; bit-exact recon vs reference"
 
 
+WORKLOAD = "encode"
+# reference lists (POCs) per workload: xvc's default two pictures per list at POC 8 (list 1 repeats list 0's
+# pictures in the opposite order, ReferenceListSorter), or one picture per list
+LISTS = {"encode": ((0, 16), (16, 0)), "raster": ((0,), (16,))}
+
+
 def picture_inputs(index_offset=0, seed=1234, partition_seed=7):
-    """(current, ref L0, ref L1) planes + CU partition + picture parameters of one step."""
+    """(current, ref POC 0, ref POC 16) planes + CU partition + picture parameters of one step."""
+    enc = WORKLOAD == "encode"
     canvas = workload.synth_canvas(WIDTH, HEIGHT, seed)
-    frames = [workload.synth_frame(canvas, WIDTH, HEIGHT, i + index_offset, BITDEPTH) for i in (POC, REF_POCS[0], REF_POCS[1])]
+    frames = [workload.synth_frame(canvas, WIDTH, HEIGHT, i + index_offset, BITDEPTH, frame_noise=4.0 if enc else 0.0)
+              for i in (POC, REF_POCS[0], REF_POCS[1])]
     cus = workload.make_partition(WIDTH, HEIGHT, seed=partition_seed, min_size=8, qp=QP)
     lam = workload.lambda_for_qp(QP)
     prm = np.zeros(1, dtype=abi.picture_params_dtype)
     prm["pic_type"] = 0
-    for l in range(2):
-        prm["search_range"][0, l, 0] = workload.search_range_uni(POC, REF_POCS[l], SUB_GOP)
-        prm["ref_poc"][0, l, 0] = REF_POCS[l]
+    for l, pocs in enumerate(LISTS[WORKLOAD]):
+        prm["num_ref"][0, l] = len(pocs)
+        for r, p in enumerate(pocs):
+            prm["search_range"][0, l, r] = workload.search_range_uni(POC, p, SUB_GOP)
+            prm["ref_poc"][0, l, r] = p
     prm["lambda_sqrt"] = np.sqrt(lam)
     prm["chroma_offset_table"] = 1
-    prm["num_ref"] = 1
     prm["deblock"], prm["pad"] = 1, 1
+    prm["bi_iterations"], prm["bits_mode"] = (1, 1) if enc else (0, 0)
     prm["ref_slots"] = -1
     return frames, cus, prm, lam
+
+
+def mv_predictors(cus, index_offset=0, partition_seed=7):
+    """encode workload: a predictor per (CU, list, reference picture) near the content's motion (None: raster workload)."""
+    if WORKLOAD != "encode":
+        return None
+    lists = tuple(tuple(p + index_offset for p in l) for l in LISTS[WORKLOAD])
+    return workload.mv_predictors(cus, POC + index_offset, lists, seed=partition_seed + 1)
+
+
+def set_ref_slots(prm, slot_of_poc):
+    for l, pocs in enumerate(LISTS[WORKLOAD]):
+        for r, p in enumerate(pocs):
+            prm["ref_slots"][0, l, r] = slot_of_poc[p]
 
 
 def recon_digest(planes):
@@ -67,9 +97,17 @@ def config_dict(n_cus, extra=None):
     cfg = {"workload": "1920x1080 synthetic YUV420 qp32, ME+transform+deblock (configs[1])" if (WIDTH, HEIGHT, QP) == (1920, 1080, 32)
            else "%dx%d synthetic YUV420 qp%d, ME+transform+deblock (context run, not the metric's configuration)" % (WIDTH, HEIGHT, QP),
            "width": WIDTH, "height": HEIGHT, "bitdepth_internal": BITDEPTH, "qp": QP,
-           "picture": "bi-predicted, 2 reference pictures (POC %d, refs %d/%d), search range %d" % (
-               POC, REF_POCS[0], REF_POCS[1], workload.search_range_uni(POC, REF_POCS[0], SUB_GOP)),
-           "partition": "seeded random quad/binary CU tree, 8..64, %d CUs; predictor mvp = 0 for every CU" % n_cus,
+           "picture": ("bi-predicted picture, POC %d of a sub-GOP of 16; reference lists L0 = POC %s, L1 = POC %s (xvc's default two pictures "
+                       "per list; the list-1 pictures repeat list 0's and are searched once), search range %d, one SearchBiIterative pass "
+                       "(FullSearch +-4 + sub-pel search on the weighted original), uni/bi decision by GetInterPredBits(fast_inter_pred_bits); "
+                       "camera noise N(0,4) on every frame" if WORKLOAD == "encode" else
+                       "bi-predicted picture type, one reference picture per list (POC %d, refs %s / %s), search range %d, list chosen by the "
+                       "sub-pel cost (round 1's step), noise-free pan") % (
+               POC, "/".join(map(str, LISTS[WORKLOAD][0])), "/".join(map(str, LISTS[WORKLOAD][1])), workload.search_range_uni(POC, REF_POCS[0], SUB_GOP)),
+           "partition": "seeded random quad/binary CU tree, 8..64, %d CUs; %s" % (
+               n_cus, "one predictor per (CU, list, reference picture) = the content's motion towards that picture (what POC-scaled neighbour vectors give), exact for half of the CUs, off by <= 6/16 pel for the rest"
+               if WORKLOAD == "encode" else "predictor mvp = 0 for every CU (the raster scan of the window fires for most jobs)"),
+           "workload_name": WORKLOAD,
            "l2": "flushed between timed iterations (256 MiB write)"}
     if extra:
         cfg.update(extra)
@@ -94,19 +132,23 @@ class CpuArm:
             self.oracle = bindings.Oracle()
             self.cores = 1
 
-    def run(self, frames, cus, prm, lam):
+    def run(self, frames, cus, prm, lam, mvp=None):
         """One step; returns (seconds, reconstruction planes)."""
         if self.kind == "reference":
             s = self.ref.session(WIDTH, HEIGHT, BITDEPTH, 0, QP, lam, simd=1, poc=POC, sub_gop=SUB_GOP)
             s.set_orig(frames[0])
-            s.add_ref(0, 0, REF_POCS[0], frames[1])
-            s.add_ref(1, 0, REF_POCS[1], frames[2])
+            by_poc = {REF_POCS[0]: frames[1], REF_POCS[1]: frames[2]}
+            for l, pocs in enumerate(LISTS[WORKLOAD]):
+                for r, p in enumerate(pocs):
+                    s.add_ref(l, r, p, by_poc[p])
             t0 = time.perf_counter()
-            s.encode_picture(prm, cus, threads=self.cores)
+            s.encode_picture(prm, cus, threads=self.cores, mvp=mvp)
             dt = time.perf_counter() - t0
             rec = s.get_rec()
             s.close()
             return dt, rec
+        if WORKLOAD != "raster":
+            raise RuntimeError("the C restatement runs the raster workload only; build oracle/_ref for the encode workload")
         P = self.b.Picture
         orig = P(WIDTH, HEIGHT, 0, frames[0])
         refs = {(0, 0): P(WIDTH, HEIGHT, 80, frames[1]), (1, 0): P(WIDTH, HEIGHT, 80, frames[2])}
@@ -162,10 +204,11 @@ def run_reference(args):
     if rank != 0:
         return
     frames, cus, prm, lam = picture_inputs()
+    mvp = mv_predictors(cus)
     arm = CpuArm()
     for _ in range(args.warmup):
-        arm.run(frames, cus, prm, lam)
-    times = [arm.run(frames, cus, prm, lam)[0] for _ in range(args.steps)]
+        arm.run(frames, cus, prm, lam, mvp)
+    times = [arm.run(frames, cus, prm, lam, mvp)[0] for _ in range(args.steps)]
     sec = float(np.mean(times))
     mpx = WIDTH * HEIGHT / sec / 1e6
     line = {
@@ -237,7 +280,13 @@ def run_ours(args):
     # dependent -- pictures rank..rank+N-1 of the synthetic sequence differ by up to 18 % in search time,
     # which a max over ranks would report as a scaling loss); --distinct-pictures gives rank r picture r
     frames, cus, prm, lam = picture_inputs(index_offset=rank if args.distinct_pictures else 0)
+    mvp = mv_predictors(cus, index_offset=rank if args.distinct_pictures else 0)
     n = len(cus)
+
+    def set_cus():
+        ctx.set_cus(cus)          # restores the flags the previous step overwrote (device copy)
+        ctx.set_mv_predictors(mvp)
+
     # slots: 0 orig, 1/2 references, 3 prediction, 4 levels, 5.. one reconstruction slot per rank
     # (contiguous: the frame-parallel all-gather lands every rank's reconstruction in place)
     # e2e pipeline: a second set (orig, levels, reconstructions) after the first one
@@ -248,12 +297,12 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
     SL = dict(orig=0, ref0=1, ref1=2, pred=3, coeff=4, rec=5 + rank)
     prm["orig_slot"], prm["pred_slot"], prm["rec_slot"], prm["coeff_slot"] = SL["orig"], SL["pred"], SL["rec"], SL["coeff"]
-    prm["ref_slots"][0, 0, 0], prm["ref_slots"][0, 1, 0] = SL["ref0"], SL["ref1"]
+    set_ref_slots(prm, {REF_POCS[0]: SL["ref0"], REF_POCS[1]: SL["ref1"]})
     ctx.upload(SL["orig"], frames[0])
     for slot, f in ((SL["ref0"], frames[1]), (SL["ref1"], frames[2])):
         ctx.upload(slot, f)
         ctx.pad_border(slot)
-    ctx.set_cus(cus)
+    set_cus()
     ctx.sync()
     ctx.set_profiling(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -292,7 +341,7 @@ def run_ours(args):
         if peers is not None:     # the slot about to be rewritten was pushed two steps ago
             peers.wait_own(dev_first_rec[s] + rank)
         mark()
-        ctx.set_cus(cus)          # restores predictors / flags the previous step overwrote (device copy)
+        set_cus()
         if flush_l2:
             flush.zero_()
         mark()
@@ -321,7 +370,7 @@ def run_ours(args):
     step_ms, stage_ms = [], {k: [] for k in lib.Context.STAGES}
     if dist is None:
         for _ in range(args.steps):
-            ctx.set_cus(cus)
+            set_cus()
             if not os.environ.get("XVCB_BENCH_NOFLUSH"):      # experiments only; the default run always flushes
                 flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,7 +423,7 @@ def run_ours(args):
     h_rec = [[pin(np.zeros_like(p)) for p in frames[0]] for _ in range(2)]
     h_lev = [[pin(np.zeros(p.shape, dtype=np.int16)) for p in frames[0]] for _ in range(2)]
     h_cus = [pin(np.zeros(n, dtype=abi.cu_dtype).view(np.uint8)).view(abi.cu_dtype) for _ in range(2)]
-    h2d = sum(p.nbytes for p in h_orig) + cus.nbytes
+    h2d = sum(p.nbytes for p in h_orig) + cus.nbytes + (mvp.nbytes if mvp is not None else 0)
     d2h = sum(p.nbytes for p in h_rec[0]) + sum(p.nbytes for p in h_lev[0]) + cus.nbytes
     sets = [dict(orig=SL["orig"], coeff=SL["coeff"], first_rec=5),
             dict(orig=base2, coeff=base2 + 1, first_rec=base2 + 2)]
@@ -393,7 +442,7 @@ def run_ours(args):
                 ctx.upload_async(sets[1 - s]["orig"], h_orig)
             if peers is not None:
                 peers.wait_own(sets[s]["first_rec"] + rank)
-            ctx.set_cus(cus)
+            set_cus()
             if flush_l2:
                 flush.zero_()
             ctx.encode_picture(prms[s], want_results=False)
@@ -484,9 +533,10 @@ def run_ours(args):
     try:
         arm = CpuArm()
         frames0, cus0, prm0, lam0 = picture_inputs(index_offset=0)
-        t_first, rec_cpu = arm.run(frames0, cus0, prm0, lam0)
+        mvp0 = mv_predictors(cus0)
+        t_first, rec_cpu = arm.run(frames0, cus0, prm0, lam0, mvp0)
         reps = int(min(20, max(1, 8.0 / max(t_first, 1e-3)))) if arm.kind == "reference" and world == 1 else 1
-        times = [t_first] + [arm.run(frames0, cus0, prm0, lam0)[0] for _ in range(reps - 1)]
+        times = [t_first] + [arm.run(frames0, cus0, prm0, lam0, mvp0)[0] for _ in range(reps - 1)]
         sec = float(np.mean(times[1:])) if len(times) > 1 else t_first
         cpu = {"value": WIDTH * HEIGHT / sec / 1e6, "unit": "Mpixels/s", "cores": arm.cores, "kind": arm.kind,
                "sample": "%d full 1920x1080 pictures of the same step (first one untimed warm-up)" % len(times)}
@@ -529,10 +579,13 @@ def main():
     ap.add_argument("--distinct-pictures", action="store_true", help="N>1: rank r encodes picture r of the sequence instead of picture 0")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N>1: how finished reconstructions reach the other GPUs (copy-engine pushes over CUDA IPC, or NCCL all-gather)")
+    ap.add_argument("--workload", default="encode", choices=["encode", "raster"], help="see the module docstring")
     ap.add_argument("--size", default=None, metavar="WxH[@QP]",
                     help="context runs only (DESIGN.md table): another picture size / qp, e.g. 3840x2160@27, 7680x4320; the "
                          "default (and the only bench line the metric is quoted on) is 1920x1080@32")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.size:
         global WIDTH, HEIGHT, QP
         wh, _, q = args.size.partition("@")

@@ -478,6 +478,14 @@ typedef struct {
  * chosen ref_idx / mv written back into the CU array, me_results[n * (num_ref[0] + num_ref[1])]
  * laid out [cu][list 0 pictures, list 1 pictures] (uni searches; may be NULL), tu_results[3*n]
  * (may be NULL).  num_ref[l] <= 0 reads as one picture (list 1: none for pic_type 1). */
+/* Optional: one predictor per (CU, list, reference picture) instead of the CU's mv[list] -- what
+ * InterSearch::GetMvpList (inter_search.cc:489-492: per ref_idx, neighbour vectors scaled by POC distance)
+ * gives the reference's search.  mvp: HOST array [n_cus][n_cols][2], 1/16 pel, columns ordered like
+ * me_results (list 0 pictures, then list 1 pictures); n_cols must equal num_ref[0] + num_ref[1] of the
+ * xvcb200_encode_picture calls that follow.  Belongs to the current CU array: xvcb200_set_cus drops it;
+ * n_cols = 0 drops it explicitly. */
+int xvcb200_set_mv_predictors(xvcb200_ctx *ctx, const int32_t *mvp, int n_cols);
+
 int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *params,
                            xvcb200_me_result *me_results, xvcb200_tu_result *tu_results);
 

@@ -360,6 +360,7 @@ class Ref:
         L.xref_session_get_rec_padded.argtypes = [c_void_p, c_int, c_void_p]
         L.xref_session_set_cus.argtypes = [c_void_p, c_void_p, c_int]
         L.xref_session_get_cus.argtypes = [c_void_p, c_void_p, c_int]
+        L.xref_encode_picture_mvp.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
         L.xref_search_motion_single.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.xref_me_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p]
         L.xref_tz_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_void_p]
@@ -635,10 +636,14 @@ class RefSession:
         self.L.xref_search_motion_single(self.h, abi.ptr(prm), abi.ptr(one), abi.ptr(out), abi.ptr(costs))
         return out[0], out[1]
 
-    def encode_picture(self, params, cus, threads=1):
+    def encode_picture(self, params, cus, threads=1, mvp=None):
+        """mvp: optional int32 [n][columns][2] predictors per (CU, list, reference picture)."""
         me = np.zeros(abi.num_me_columns(params) * len(cus), dtype=abi.me_result_dtype)
         tu = np.zeros(3 * len(cus), dtype=abi.tu_result_dtype)
         out = cus.copy()
         prm = np.array([params], dtype=abi.picture_params_dtype) if not isinstance(params, np.ndarray) else params
-        self.L.xref_encode_picture(self.h, abi.ptr(prm), abi.ptr(cus), len(cus), threads, abi.ptr(me), abi.ptr(tu), abi.ptr(out))
+        if mvp is not None:
+            mvp = np.ascontiguousarray(mvp, dtype=np.int32)
+            assert mvp.shape == (len(cus), abi.num_me_columns(params), 2)
+        self.L.xref_encode_picture_mvp(self.h, abi.ptr(prm), abi.ptr(cus), len(cus), abi.ptr(mvp), threads, abi.ptr(me), abi.ptr(tu), abi.ptr(out))
         return me, tu, out

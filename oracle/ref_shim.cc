@@ -830,14 +830,18 @@ struct PipeWorker {
 };
 
 void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params *p, const int R[2], double lambda, int i,
-                    const xvcb200_cu &in, xvcb200_me_result *res /* J entries */) {
+                    const xvcb200_cu &in, const int32_t *mvp_cols /* J x 2 or null */, xvcb200_me_result *res /* J entries */) {
   CodingUnit *cu = s->cus[i];
   if (in.flags & (XVCB200_CU_INTRA | XVCB200_CU_SKIP_ME)) return;
   InterSearch &search = w->me.search;
   const YuvComponent comp = YuvComponent::kY;
   Qp qp(cu->GetQp(comp), ChromaFormat::k420, s->bitdepth, lambda, s->chroma_table, s->off_u, s->off_v);
   const uint32_t lam = static_cast<uint32_t>(std::floor(65536.0 * qp.GetLambdaSqrt()));
-  const MotionVector mvp[2] = {MotionVector(in.mv[0][0], in.mv[0][1]), MotionVector(in.mv[1][0], in.mv[1][1])};
+  // predictor of (list, ref_idx): the caller's column (GetMvpList is per ref_idx), else the CU's mv[list]
+  auto mvp_of = [&](int l, int r) {
+    const int col = l * R[0] + r;
+    return mvp_cols ? MotionVector(mvp_cols[2 * col], mvp_cols[2 * col + 1]) : MotionVector(in.mv[l][0], in.mv[l][1]);
+  };
   const Distortion kMax = std::numeric_limits<Distortion>::max();
   auto list_of = [](int l) { return static_cast<RefPicList>(l); };
   auto dir_of = [](int l) { return l == 0 ? InterDir::kL0 : InterDir::kL1; };
@@ -856,7 +860,7 @@ void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params
       } else {
         xvcb200_me_job job;
         job.cu = i; job.ref_slot = r; job.list = l; job.search_range = p->search_range[l][r];
-        job.mvp[0] = in.mv[l][0]; job.mvp[1] = in.mv[l][1]; job.prev[0] = job.prev[1] = 0;
+        job.mvp[0] = mvp_of(l, r).x; job.mvp[1] = mvp_of(l, r).y; job.prev[0] = job.prev[1] = 0;
         RunMeJob(s, &w->me, job, lambda, &res[col]);
       }
       const MotionVector mv(res[col].mv[0], res[col].mv[1]);
@@ -865,7 +869,7 @@ void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params
         cu->SetRefIdx(r, list_of(l));
         cu->SetMvpIdx(0, list_of(l));
         cu->SetMv(mv, list_of(l));
-        search.SetMvd(cu, list_of(l), mvp[l], mv);
+        search.SetMvd(cu, list_of(l), mvp_of(l, r), mv);
         cost = res[col].dist + ((search.GetInterPredBits(*cu, w->writer) * lam) >> 16);
       }
       if (cost < cost_uni[l]) { cost_uni[l] = cost; uni_ref[l] = r; uni_mv[l] = mv; }
@@ -894,14 +898,15 @@ void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params
         const MotionVector bootstrap(res[col].mv[0], res[col].mv[1]);   // GetBestUniPredMv (:497)
         MvFullpel clip_min, clip_max;
         search.DetermineMinMaxMv(*cu, *ref_pic, bootstrap, EncoderSettings::inter_search_range_bi, &clip_min, &clip_max);
-        const MvFullpel mv_full = search.FullSearch(*cu, qp, fullpel_metric, mvp[sl], *ref_pic, clip_min, clip_max);
+        const MotionVector mvp_sl = mvp_of(sl, r);
+        const MvFullpel mv_full = search.FullSearch(*cu, qp, fullpel_metric, mvp_sl, *ref_pic, clip_min, clip_max);
         Distortion dist = kMax;
         MotionVector mv;
         if (cu->GetFullpelMv()) {
           mv = MotionVector(mv_full);
           dist = search.GetSubpelDist(*cu, qp, *ref_pic, subpel_metric, mv, search.bipred_orig_buffer_, &w->pred);
         } else {
-          mv = search.SubpelSearch(*cu, qp, subpel_metric, *ref_pic, mvp[sl], mv_full, search.bipred_orig_buffer_, &w->pred, &dist);
+          mv = search.SubpelSearch(*cu, qp, subpel_metric, *ref_pic, mvp_sl, mv_full, search.bipred_orig_buffer_, &w->pred, &dist);
         }
         dist >>= 1;                                        // MotionEstNormal, :660
         if (p->bi_iterations > 1) { res[col].mv[0] = mv.x; res[col].mv[1] = mv.y; }   // SetBestUniPredMv (:549-553)
@@ -909,8 +914,8 @@ void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params
         cu->SetMvpIdx(0, list_of(sl));
         cu->SetMvpIdx(0, list_of(other));
         cu->SetMv(mv, list_of(sl));
-        search.SetMvd(cu, list_of(sl), mvp[sl], mv);
-        search.SetMvd(cu, list_of(other), mvp[other], bi_mv[other]);
+        search.SetMvd(cu, list_of(sl), mvp_sl, mv);
+        search.SetMvd(cu, list_of(other), mvp_of(other, bi_ref[other]), bi_mv[other]);
         const Distortion cost = dist + ((search.GetInterPredBits(*cu, w->writer) * lam) >> 16);
         if (cost < cost_bi) { cost_bi = cost; bi_ref[sl] = r; bi_mv[sl] = mv; }
       }
@@ -935,9 +940,9 @@ void SearchMotionCu(xref_session *s, PipeWorker *w, const xvcb200_picture_params
 }
 }  // namespace
 
-void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const xvcb200_cu *cus_in, int n,
-                         int threads, xvcb200_me_result *me_results, xvcb200_tu_result *tu_results,
-                         xvcb200_cu *cus_out) {
+void xref_encode_picture_mvp(xref_session *s, const xvcb200_picture_params *p, const xvcb200_cu *cus_in, int n,
+                             const int32_t *mvp /* n x J x 2 or null: xvcb200_set_mv_predictors */, int threads,
+                             xvcb200_me_result *me_results, xvcb200_tu_result *tu_results, xvcb200_cu *cus_out) {
   xref_session_set_cus(s, cus_in, n);
   s->pic_data->force_bipred_l1_mvd_zero_ = false;       // the low-delay "L1 mvd = 0" rule is not part of the batched step
   s->settings.fast_inter_pred_bits = p->bits_mode ? 1 : 0;
@@ -949,7 +954,10 @@ void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const
   // lambda_sqrt is authoritative: build Qp from lambda = lambda_sqrt^2 and check the sqrt
   // round-trips (it does for the values bench.py uses; asserted in tests).
   ParallelFor<PipeWorker>(n, threads, [s]() { return new PipeWorker(s); },
-                          [&](PipeWorker *w, int i) { SearchMotionCu(s, w, p, R, lambda, i, cus_in[i], &res[static_cast<size_t>(i) * J]); });
+                          [&](PipeWorker *w, int i) {
+                            SearchMotionCu(s, w, p, R, lambda, i, cus_in[i], mvp ? mvp + static_cast<size_t>(i) * J * 2 : nullptr,
+                                           &res[static_cast<size_t>(i) * J]);
+                          });
   if (me_results) std::memcpy(me_results, res.data(), res.size() * sizeof(res[0]));
   xref_motion_compensate(s, threads);
   xref_tq_reconstruct(s, threads, tu_results);
@@ -959,6 +967,12 @@ void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const
     std::memcpy(cus_out, cus_in, sizeof(xvcb200_cu) * n);
     xref_session_get_cus(s, cus_out, n);
   }
+}
+
+void xref_encode_picture(xref_session *s, const xvcb200_picture_params *p, const xvcb200_cu *cus_in, int n,
+                         int threads, xvcb200_me_result *me_results, xvcb200_tu_result *tu_results,
+                         xvcb200_cu *cus_out) {
+  xref_encode_picture_mvp(s, p, cus_in, n, nullptr, threads, me_results, tu_results, cus_out);
 }
 
 // Pins the control flow above to the reference's own InterSearch::SearchMotion: for a picture holding
@@ -979,7 +993,7 @@ void xref_search_motion_single(xref_session *s, const xvcb200_picture_params *p,
   CodingUnit *cu = s->cus[0];
   {
     PipeWorker w(s);
-    SearchMotionCu(s, &w, p, R, lambda, 0, in, res.data());
+    SearchMotionCu(s, &w, p, R, lambda, 0, in, nullptr, res.data());
     out[0] = in;
     xref_session_get_cus(s, &out[0], 1);
     costs[0] = 0;

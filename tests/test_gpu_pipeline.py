@@ -34,8 +34,11 @@ def run_both(ref, width, height, bd, qp, pic_type, pocs, bi_iterations, seed, pr
     lam = workload.lambda_for_qp(qp)
     cus = workload.make_partition(width, height, seed=seed + 1, min_size=min_size, qp=qp)
     rng = np.random.default_rng(seed + 2)
-    if predictors == "field":
+    mvp = None
+    if predictors == "field":            # one predictor per list: the CU's mv[list]
         workload.set_predictors(cus, POC, (pocs[0][0], pocs[1][0] if pocs[1] else None), seed=seed + 3)
+    elif predictors == "per_ref":        # one per (list, reference picture): xvcb200_set_mv_predictors
+        mvp = workload.mv_predictors(cus, POC, pocs, seed=seed + 3)
     elif predictors == "random":
         cus["mv"] = rng.integers(-400, 401, size=cus["mv"].shape)
     if mixed:
@@ -75,6 +78,7 @@ def run_both(ref, width, height, bd, qp, pic_type, pocs, bi_iterations, seed, pr
         ctx.pad_border(slot_of[p])
     ctx.upload(slots["pred"], stale_pred)
     ctx.set_cus(cus)
+    ctx.set_mv_predictors(mvp)
     me_g, tu_g = ctx.encode_picture(prm)
     ctx.sync()
     gpu = dict(me=me_g, tu=tu_g, cus=ctx.get_cus(), rec=[ctx.download_padded(slots["rec"], c) for c in range(3)],
@@ -86,7 +90,7 @@ def run_both(ref, width, height, bd, qp, pic_type, pocs, bi_iterations, seed, pr
         for r, p in enumerate(pocs[l]):
             s.add_ref(l, r, p, frame(p))
     s.set_pred(stale_pred)
-    me_r, tu_r, cus_r = s.encode_picture(prm, cus, threads=threads)
+    me_r, tu_r, cus_r = s.encode_picture(prm, cus, threads=threads, mvp=mvp)
     cpu = dict(me=me_r, tu=tu_r, cus=cus_r, rec=[s.get_rec_padded(c) for c in range(3)], lev=s.get_coeff())
     s.close()
     return gpu, cpu, cus, prm
@@ -109,6 +113,8 @@ def assert_equal(gpu, cpu, cus_in, prm):
 CASES = {
     # name: (pic_type, (L0 POCs, L1 POCs), bi_iterations, predictors, mixed flags, bitdepth)
     "two_refs_same_pocs": (0, ((0, 16), (16, 0)), 1, "field", False, 10),      # xvc's default lists at POC 8: every L1 picture repeats an L0 one
+    "two_refs_per_ref_predictors": (0, ((0, 16), (16, 0)), 1, "per_ref", True, 10),
+    "three_and_one_per_ref_predictors": (0, ((4, 0, 2), (12,)), 2, "per_ref", False, 10),
     "unique_l1": (0, ((4, 0), (12, 16)), 1, "field", True, 10),
     "one_ref_four_iterations": (0, ((0,), (16,)), 4, "zero", False, 10),
     "three_and_one": (0, ((4, 0, 2), (12,)), 2, "random", True, 8),
@@ -145,19 +151,19 @@ FULL_SIZE = [
 ]
 
 
-@pytest.mark.parametrize("predictors", ["field", "zero"])
+@pytest.mark.parametrize("predictors", ["per_ref", "zero"])
 @pytest.mark.parametrize("width,height,bd,qp", FULL_SIZE)
 def test_whole_picture_equals_reference(ref, width, height, bd, qp, predictors):
     """BASELINE.json's configurations at full size: EVERY search result, CU decision, level and sample of the
     padded, deblocked reconstruction equals what the unmodified reference's classes produce on all host
-    threads (encode_decode_test.cc:106-111's whole-picture equality).  "field": xvc's default reference
+    threads (encode_decode_test.cc:106-111's whole-picture equality).  "per_ref": xvc's default reference
     lists at POC 8 of a sub-GOP of 16 (two pictures per list, the list-1 pictures repeating list 0),
-    one SearchBiIterative pass, predictors near the content's motion (the first diamond converges, as with
-    neighbour-derived predictors in an encoder).  "zero": round 1's step -- one picture per list, zero
+    one SearchBiIterative pass, a predictor per (list, picture) near the content's motion towards that
+    picture (the first diamond converges, as with neighbour-derived, POC-scaled predictors in an encoder).  "zero": round 1's step -- one picture per list, zero
     predictors (the raster scan of the +-128 window fires for most CUs), list chosen by the sub-pel cost."""
     threads = max(4, os.cpu_count() or 4)
-    if predictors == "field":
-        gpu, cpu, cus, prm = run_both(ref, width, height, bd, qp, 0, ((0, 16), (16, 0)), 1, seed=1234, predictors="field",
+    if predictors == "per_ref":
+        gpu, cpu, cus, prm = run_both(ref, width, height, bd, qp, 0, ((0, 16), (16, 0)), 1, seed=1234, predictors="per_ref",
                                       max_range=256, threads=threads)
         bi = (gpu["cus"]["ref_idx"][:, 0] >= 0) & (gpu["cus"]["ref_idx"][:, 1] >= 0)
         assert bi.mean() > 0.05, "bi-prediction hardly ever chosen"

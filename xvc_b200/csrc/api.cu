@@ -430,6 +430,10 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   xvcb200_me_job *d_bi_jobs = nullptr; int bi_jobs_cap = 0;
   xvcb200_me_result *d_bi_res = nullptr; int bi_res_cap = 0;
   int16_t *d_worig = nullptr;
+  int32_t *d_mvp = nullptr; int mvp_cap = 0;   // xvcb200_set_mv_predictors: [cu][column][2]
+  int mvp_cols = 0;                            // 0: none given for the current CU array
+  int32_t *h_mvp[2] = {nullptr, nullptr}; size_t h_mvp_cap[2] = {0, 0}; cudaEvent_t mvp_ev[2] = {nullptr, nullptr};   // page-locked staging, alternating
+  unsigned mvp_next = 0;
   // Everything set_cus sends ([cus][tu list][CU index by CTU][groups]) is ONE blob,
   // double-buffered: the upload for the next picture goes to the other blob on the upload stream
   // while the kernels of the current picture still use theirs.  d_cus / d_tu_list / d_pipe_* point
@@ -604,7 +608,8 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   for (cudaEvent_t e : c->ex.dl_ev) if (e) cudaEventDestroy(e);
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
-  cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
+  for (int b = 0; b < 2; b++) { if (c->ex.h_mvp[b]) cudaFreeHost(c->ex.h_mvp[b]); if (c->ex.mvp_ev[b]) cudaEventDestroy(c->ex.mvp_ev[b]); }
+  cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
@@ -1047,6 +1052,7 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
     for (int l = 0; l < 2; l++)
       if (!(cus[i].flags & XVCB200_CU_INTRA) && cus[i].ref_idx[l] > c->ex.max_ref_idx[l]) c->ex.max_ref_idx[l] = cus[i].ref_idx[l];
   c->n_cus = n;
+  c->ex.mvp_cols = 0;                       // predictors belong to a CU array
   if (n == 0) { c->ex.h_cus.clear(); return XVCB200_OK; }
   if (!copy_setup(c)) return c->status;
   // CU groups by CTU (counting sort: coding order inside a CTU is kept).  Only CUs that take part in the
@@ -1131,6 +1137,33 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   c->ex.d_tu_list = dl;
   c->ex.d_pipe_index = dl + 3 * (size_t)n;
   c->ex.d_pipe_groups = c->ex.d_pipe_index + n;
+  return XVCB200_OK;
+}
+
+int xvcb200_set_mv_predictors(xvcb200_ctx *ctx, const int32_t *mvp, int n_cols) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || n_cols < 0 || n_cols > 10 || (n_cols > 0 && !mvp)) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  c->ex.mvp_cols = 0;
+  if (n_cols == 0 || c->n_cus == 0) return XVCB200_OK;
+  const int count = 2 * c->n_cus * n_cols;
+  if (!ensure(c, &c->ex.d_mvp, &c->ex.mvp_cap, count)) return c->status;
+  // through page-locked staging (two buffers, alternating): the call never waits for the kernels in flight
+  const int b = (int)(c->ex.mvp_next++ & 1);
+  const size_t bytes = sizeof(int32_t) * (size_t)count;
+  if (!c->ex.mvp_ev[b] && !c->check(cudaEventCreateWithFlags(&c->ex.mvp_ev[b], cudaEventDisableTiming), "cudaEventCreate")) return c->status;
+  if (!c->check(cudaEventSynchronize(c->ex.mvp_ev[b]), "mv predictors staging")) return c->status;
+  if (bytes > c->ex.h_mvp_cap[b]) {
+    if (c->ex.h_mvp[b]) cudaFreeHost(c->ex.h_mvp[b]);
+    c->ex.h_mvp[b] = nullptr; c->ex.h_mvp_cap[b] = 0;
+    if (!c->check(cudaHostAlloc(&c->ex.h_mvp[b], bytes + bytes / 4, cudaHostAllocDefault), "cudaHostAlloc")) return c->status;
+    c->ex.h_mvp_cap[b] = bytes + bytes / 4;
+  }
+  memcpy(c->ex.h_mvp[b], mvp, bytes);
+  if (!c->check(cudaMemcpyAsync(c->ex.d_mvp, c->ex.h_mvp[b], bytes, cudaMemcpyHostToDevice, c->stream), "mv predictors") ||
+      !c->check(cudaEventRecord(c->ex.mvp_ev[b], c->stream), "mv predictors"))
+    return c->status;
+  c->ex.mvp_cols = n_cols;
   return XVCB200_OK;
 }
 
@@ -1494,6 +1527,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   P.bi_iterations = P.R[1] > 0 ? prm->bi_iterations : 0;
   P.lambda = lambda_me_of(prm->lambda_sqrt);
   if (P.bits_mode == 0 && (P.R[0] > 1 || P.R[1] > 1 || P.bi_iterations > 0)) return XVCB200_INVALID_ARGUMENT;
+  if (c->ex.mvp_cols != 0 && c->ex.mvp_cols != P.J) return XVCB200_INVALID_ARGUMENT;    // predictors given for other lists
+  P.mvp = c->ex.mvp_cols ? c->ex.d_mvp : nullptr;
   int cols[10], n_cols = 0;
   for (int l = 0; l < 2; l++)
     for (int r = 0; r < P.R[l]; r++) {
@@ -1549,19 +1584,19 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   mark();   // 2: full-pel search done
   c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_jobs, nj, c->bitdepth, P.lambda, orig, c->ex.d_luma_views, c->ex.d_me,
                                 c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev, c->ex.n_side, c->ex.fork_ev), "subpel_search");
-  c->check(launch_me_uni_decide(c->stream, c->d_cus, P, c->ex.d_me, c->ex.d_me_state), "me_uni_decide");
+  c->check(launch_me_uni_decide(c->stream, c->d_cus, P, c->ex.d_jobs, c->ex.d_me, c->ex.d_me_state), "me_uni_decide");
   if (P.bi_iterations > 0) {
     PlaneView worig = orig;
     worig.base = reinterpret_cast<Sample *>(c->ex.d_worig);
     for (int it = 0; it < P.bi_iterations; it++) {
-      c->check(launch_bi_prepare(c->stream, c->d_cus, P, it, c->ex.d_me, c->ex.d_me_state, orig, c->ex.d_luma_views, worig,
+      c->check(launch_bi_prepare(c->stream, c->d_cus, P, it, c->ex.d_jobs, c->ex.d_me, c->ex.d_me_state, orig, c->ex.d_luma_views, worig,
                                  c->ex.d_bi_jobs), "bi_prepare");
       c->check(launch_full_search_worig(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
                                         c->ex.d_bi_res), "full_search");
       c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
                                     c->ex.d_bi_res, c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev, c->ex.n_side, c->ex.fork_ev),
                "subpel_search(bi)");
-      c->check(launch_me_bi_decide(c->stream, c->d_cus, P, c->ex.d_bi_res, c->ex.d_me, c->ex.d_me_state), "me_bi_decide");
+      c->check(launch_me_bi_decide(c->stream, c->d_cus, P, c->ex.d_jobs, c->ex.d_bi_res, c->ex.d_me, c->ex.d_me_state), "me_bi_decide");
     }
   }
   c->check(launch_me_final_decide(c->stream, c->d_cus, P, c->ex.d_me_state), "me_final_decide");

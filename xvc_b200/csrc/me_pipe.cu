@@ -17,8 +17,10 @@
 // Rate: the reference's CABAC-independent estimate (GetInterPredBits with fast_inter_pred_bits,
 // inter_search.cc:1084-1130): uni = (1 | 3) + ref_idx bits + 1 (mvp flag) + exp-Golomb(mvd), bi = 5 +
 // both lists' ref_idx bits + 1 + exp-Golomb(mvd); cost = dist + ((bits * lambda) >> 16).  The
-// predictor of a list is the vector the CU array carries in mv[list] when the picture is handed
-// over (one predictor per list: the mvp list of the reference collapsed to its first entry).
+// predictor of a (list, reference picture) is the one given with xvcb200_set_mv_predictors (GetMvpList
+// is per ref_idx: neighbour vectors scaled by POC distance), else the vector the CU array carries in
+// mv[list] when the picture is handed over; the two-entry mvp list of the reference is collapsed to
+// its first entry.
 // bits_mode 0 keeps round 1's rule (the cost of the sub-pel search alone picks list 0 or 1).
 //
 // CUs flagged XVCB200_CU_INTRA or XVCB200_CU_SKIP_ME take no part: no job of theirs is searched and
@@ -56,7 +58,8 @@ __global__ void make_me_jobs_kernel(const xvcb200_cu *__restrict__ cus, const __
   xvcb200_me_job j;
   j.cu = c; j.ref_slot = P.ref_slot[l][r];
   j.search_range = (!cu_searched(cu) || (l == 1 && P.dup_of[r] >= 0)) ? 0 : P.range[l][r];
-  j.mvp[0] = cu.mv[l][0]; j.mvp[1] = cu.mv[l][1];
+  if (P.mvp) { j.mvp[0] = P.mvp[2 * (size_t)i]; j.mvp[1] = P.mvp[2 * (size_t)i + 1]; }      // GetMvpList is per (list, ref_idx)
+  else { j.mvp[0] = cu.mv[l][0]; j.mvp[1] = cu.mv[l][1]; }
   j.prev[0] = 0; j.prev[1] = 0; j.list = l;
   jobs[i] = j;
 }
@@ -70,7 +73,8 @@ cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, const M
 
 // SearchRefIdx per list on the finished uni searches (a thread per CU)
 __global__ void me_uni_decide_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
-                                     xvcb200_me_result *__restrict__ res, MeCuState *__restrict__ state) {
+                                     const xvcb200_me_job *__restrict__ jobs, xvcb200_me_result *__restrict__ res,
+                                     MeCuState *__restrict__ state) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
   const xvcb200_cu cu = cus[i];
@@ -89,7 +93,7 @@ __global__ void me_uni_decide_kernel(const xvcb200_cu *__restrict__ cus, const _
         if (dup) res[(size_t)i * P.J + j] = q;          // unipred_best_mv_[L1][r] = the list-0 vector (:536-549)
         uint32_t cost = q.cost;
         if (P.bits_mode) {
-          const uint32_t bits = (P.pic_uni ? 1u : 3u) + ref_idx_bits(r, P.R[l]) + 1u + mvd_bits_down(cu.mv[l], q.mv, down);
+          const uint32_t bits = (P.pic_uni ? 1u : 3u) + ref_idx_bits(r, P.R[l]) + 1u + mvd_bits_down(jobs[(size_t)i * P.J + j].mvp, q.mv, down);
           cost = q.dist + ((bits * P.lambda) >> 16);
         }
         if (cost < st.cost_uni[l]) { st.cost_uni[l] = cost; st.uni_ref[l] = (int8_t)r; st.uni_mv[l][0] = q.mv[0]; st.uni_mv[l][1] = q.mv[1]; }
@@ -99,10 +103,11 @@ __global__ void me_uni_decide_kernel(const xvcb200_cu *__restrict__ cus, const _
   state[i] = st;
 }
 
-cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_result *d_res, void *d_state) {
+cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
+                                 xvcb200_me_result *d_res, void *d_state) {
   if (P.n <= 0) return cudaSuccess;
   g_launch_count++;
-  me_uni_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, d_res, static_cast<MeCuState *>(d_state));
+  me_uni_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, d_jobs, d_res, static_cast<MeCuState *>(d_state));
   return cudaGetLastError();
 }
 
@@ -110,7 +115,8 @@ cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const 
 // InterDir = that list, inter_search.cc:415-418), weighted original into `worig`, jobs of the list
 // that is searched.  job.prev carries the bootstrap vector (GetBestUniPredMv, :497) in 1/16 pel.
 __global__ void __launch_bounds__(128) bi_prepare_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
-                                                         int iteration, const xvcb200_me_result *__restrict__ res,
+                                                         int iteration, const xvcb200_me_job *__restrict__ jobs,
+                                                         const xvcb200_me_result *__restrict__ res,
                                                          MeCuState *__restrict__ state, PlaneView orig,
                                                          const PlaneView *__restrict__ luma, PlaneView worig,
                                                          xvcb200_me_job *__restrict__ bi_jobs) {
@@ -134,9 +140,11 @@ __global__ void __launch_bounds__(128) bi_prepare_kernel(const xvcb200_cu *__res
     for (int r = 0; r < P.Rmax; r++) {
       xvcb200_me_job j;
       j.cu = i; j.list = sl; j.ref_slot = 0; j.search_range = 0;
-      j.mvp[0] = cu.mv[sl][0]; j.mvp[1] = cu.mv[sl][1]; j.prev[0] = j.prev[1] = 0;
+      j.mvp[0] = j.mvp[1] = 0; j.prev[0] = j.prev[1] = 0;
       if (run && r < P.R[sl]) {
-        const xvcb200_me_result q = res[(size_t)i * P.J + (sl ? P.R[0] + r : r)];
+        const size_t col = (size_t)i * P.J + (sl ? P.R[0] + r : r);
+        const xvcb200_me_result q = res[col];
+        j.mvp[0] = jobs[col].mvp[0]; j.mvp[1] = jobs[col].mvp[1];
         j.ref_slot = P.ref_slot[sl][r];
         j.search_range = 4;                              // encoder_settings.h:65 inter_search_range_bi
         j.prev[0] = q.mv[0]; j.prev[1] = q.mv[1];
@@ -161,11 +169,12 @@ __global__ void __launch_bounds__(128) bi_prepare_kernel(const xvcb200_cu *__res
   }
 }
 
-cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_result *d_res,
-                              void *d_state, PlaneView orig, const PlaneView *d_luma_views, PlaneView worig, xvcb200_me_job *d_bi_jobs) {
+cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
+                              const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
+                              PlaneView worig, xvcb200_me_job *d_bi_jobs) {
   if (P.n <= 0) return cudaSuccess;
   g_launch_count++;
-  bi_prepare_kernel<<<P.n, 128, 0, s>>>(d_cus, P, iteration, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig, d_bi_jobs);
+  bi_prepare_kernel<<<P.n, 128, 0, s>>>(d_cus, P, iteration, d_jobs, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig, d_bi_jobs);
   return cudaGetLastError();
 }
 
@@ -303,7 +312,7 @@ cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xv
 
 // SearchRefIdx of one SearchBiIterative pass on the finished bi searches (a thread per CU)
 __global__ void me_bi_decide_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
-                                    const xvcb200_me_result *__restrict__ bi_res, xvcb200_me_result *__restrict__ res,
+                                    const xvcb200_me_job *__restrict__ jobs, const xvcb200_me_result *__restrict__ bi_res, xvcb200_me_result *__restrict__ res,
                                     MeCuState *__restrict__ state) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
@@ -313,14 +322,15 @@ __global__ void me_bi_decide_kernel(const xvcb200_cu *__restrict__ cus, const __
   const int down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
   const int sl = st.search_list, other = 1 - sl;
   const uint32_t prev_best = st.cost_bi;
-  const uint32_t bits_other = ref_idx_bits(st.bi_ref[other], P.R[other]) + 1u + mvd_bits_down(cu.mv[other], st.bi_mv[other], down);
+  const size_t col_other = (size_t)i * P.J + (other ? P.R[0] + st.bi_ref[other] : st.bi_ref[other]);
+  const uint32_t bits_other = ref_idx_bits(st.bi_ref[other], P.R[other]) + 1u + mvd_bits_down(jobs[col_other].mvp, st.bi_mv[other], down);
   for (int r = 0; r < P.R[sl]; r++) {
     const xvcb200_me_result q = bi_res[(size_t)i * P.Rmax + r];
     if (P.bi_iterations > 1) {                      // SetBestUniPredMv also after a bi search (:549-553)
       xvcb200_me_result *u = &res[(size_t)i * P.J + (sl ? P.R[0] + r : r)];
       u->mv[0] = q.mv[0]; u->mv[1] = q.mv[1];
     }
-    const uint32_t bits = 5u + bits_other + ref_idx_bits(r, P.R[sl]) + 1u + mvd_bits_down(cu.mv[sl], q.mv, down);
+    const uint32_t bits = 5u + bits_other + ref_idx_bits(r, P.R[sl]) + 1u + mvd_bits_down(jobs[(size_t)i * P.J + (sl ? P.R[0] + r : r)].mvp, q.mv, down);
     const uint32_t cost = (q.dist >> 1) + ((bits * P.lambda) >> 16);       // MotionEstNormal halves the bi distortion (:660)
     if (cost < st.cost_bi) { st.cost_bi = cost; st.bi_ref[sl] = (int8_t)r; st.bi_mv[sl][0] = q.mv[0]; st.bi_mv[sl][1] = q.mv[1]; }
   }
@@ -329,11 +339,11 @@ __global__ void me_bi_decide_kernel(const xvcb200_cu *__restrict__ cus, const __
   state[i] = st;
 }
 
-cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_result *d_bi_res,
-                                xvcb200_me_result *d_res, void *d_state) {
+cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
+                                const xvcb200_me_result *d_bi_res, xvcb200_me_result *d_res, void *d_state) {
   if (P.n <= 0) return cudaSuccess;
   g_launch_count++;
-  me_bi_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, d_bi_res, d_res, static_cast<MeCuState *>(d_state));
+  me_bi_decide_kernel<<<(P.n + 127) / 128, 128, 0, s>>>(d_cus, P, d_jobs, d_bi_res, d_res, static_cast<MeCuState *>(d_state));
   return cudaGetLastError();
 }
 

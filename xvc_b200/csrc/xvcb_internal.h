@@ -157,20 +157,23 @@ struct MePipe {
   int bi_iterations;        // SearchBiIterative passes (0: no bi-prediction)
   int bitdepth;
   uint32_t lambda;
+  const int32_t *mvp;       // device, [cu][J][2]: predictor per (CU, list, ref_idx), 1/16 pel; nullptr: the CU's mv[list]
 };
 struct MeCuState;            // per-CU decision state (me_pipe.cu)
 size_t me_cu_state_bytes();
 cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_job *d_jobs);
-cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_result *d_res, void *d_state);
+cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
+                                 xvcb200_me_result *d_res, void *d_state);
 // one pass of InterSearch::SearchBiIterative for every CU still refining: weighted original of the list
 // that is kept -> luma plane of `worig` (int16), jobs of the list that is searched -> d_bi_jobs [cu][Rmax]
-cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_result *d_res,
-                              void *d_state, PlaneView orig, const PlaneView *d_luma_views, PlaneView worig, xvcb200_me_job *d_bi_jobs);
+cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
+                              const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
+                              PlaneView worig, xvcb200_me_job *d_bi_jobs);
 // InterSearch::FullSearch on the weighted original for jobs [0, n): mv_fullpel / cost_fullpel of d_res
 cudaError_t launch_full_search_worig(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
                                      uint32_t lambda_me, PlaneView worig, const PlaneView *d_luma_views, xvcb200_me_result *d_res);
-cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_result *d_bi_res,
-                                xvcb200_me_result *d_res, void *d_state);
+cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
+                                const xvcb200_me_result *d_bi_res, xvcb200_me_result *d_res, void *d_state);
 cudaError_t launch_me_final_decide(cudaStream_t s, xvcb200_cu *d_cus, const MePipe &P, const void *d_state);
 // xvcb200_full_search (API): weighted original built per job from `orig` and the luma plane of other_pred_slot
 cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_fullsearch_job *d_jobs, int n,

@@ -34,7 +34,7 @@ EXPORTS = [
     "xvcb200_ctx_create", "xvcb200_ctx_destroy", "xvcb200_ctx_set_stream", "xvcb200_stream", "xvcb200_sync",
     "xvcb200_ctx_error_string", "xvcb200_get_geometry", "xvcb200_slot_ptr", "xvcb200_slot_region",
     "xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff",
-    "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus",
+    "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus", "xvcb200_set_mv_predictors",
     "xvcb200_upload_picture_async", "xvcb200_download_picture_async", "xvcb200_download_coeff_async",
     "xvcb200_get_cus_async", "xvcb200_sync_copies", "xvcb200_wait_download",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_motion_compensate_lic", "xvcb200_tq_reconstruct",
@@ -119,6 +119,7 @@ def load():
     L.xvcb200_pad_border.argtypes = [c_void_p, c_int]
     L.xvcb200_set_cus.argtypes = [c_void_p, c_void_p, c_int]
     L.xvcb200_get_cus.argtypes = [c_void_p, c_void_p, c_int]
+    L.xvcb200_set_mv_predictors.argtypes = [c_void_p, c_void_p, c_int]
     L.xvcb200_me_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
     L.xvcb200_full_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
     L.xvcb200_motion_compensate.argtypes = [c_void_p, c_void_p, c_int]
@@ -434,6 +435,15 @@ class Context:
         cus = np.ascontiguousarray(cus, dtype=abi.cu_dtype)
         self._ok(self.L.xvcb200_set_cus(self.h, abi.ptr(cus), len(cus)))
         self.n_cus = len(cus)
+
+    def set_mv_predictors(self, mvp):
+        """mvp: int32 [n_cus][columns][2] (1/16 pel) or None to drop them; after set_cus."""
+        if mvp is None:
+            self._ok(self.L.xvcb200_set_mv_predictors(self.h, None, 0))
+            return
+        mvp = np.ascontiguousarray(mvp, dtype=np.int32)
+        assert mvp.ndim == 3 and mvp.shape[0] == self.n_cus and mvp.shape[2] == 2
+        self._ok(self.L.xvcb200_set_mv_predictors(self.h, abi.ptr(mvp), mvp.shape[1]))
 
     def get_cus(self):
         out = np.zeros(self.n_cus, dtype=abi.cu_dtype)

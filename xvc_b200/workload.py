@@ -191,3 +191,19 @@ def set_predictors(cus, poc, ref_pocs, seed=0, jitter=6, exact=0.5):
         noise[rng.random(n) < exact] = 0
         cus["mv"][:, l, :] = mv[None, :] + noise
     return cus
+
+
+def mv_predictors(cus, poc, lists, seed=0, jitter=6, exact=0.5):
+    """Predictor per (CU, list, reference picture) -> int32 [n][columns][2]: the content's motion towards
+    THAT picture (what InterSearch::GetMvpList returns on panned content: neighbour vectors scaled by POC
+    distance), exact for a fraction `exact` of the CUs, off by up to `jitter`/16 pel for the rest.
+    lists = (POCs of list 0, POCs of list 1); columns ordered list 0 then list 1."""
+    rng = np.random.default_rng(seed)
+    n = len(cus)
+    pocs = list(lists[0]) + list(lists[1])
+    out = np.zeros((n, len(pocs), 2), dtype=np.int32)
+    noise = rng.integers(-jitter, jitter + 1, size=(n, 2)).astype(np.int32)      # a CU's neighbourhood is off by the same amount for every picture
+    noise[rng.random(n) < exact] = 0
+    for c, rp in enumerate(pocs):
+        out[:, c, :] = np.array(true_motion(poc, rp), dtype=np.int32)[None, :] + noise
+    return out
