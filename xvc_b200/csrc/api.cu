@@ -430,6 +430,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   xvcb200_me_job *d_bi_jobs = nullptr; int bi_jobs_cap = 0;
   xvcb200_me_result *d_bi_res = nullptr; int bi_res_cap = 0;
   int16_t *d_worig = nullptr;
+  std::vector<CUtensorMap> luma_tmaps;         // per slot: [2 * slot + 0 / 1] = narrow / wide box over the padded luma plane (full search)
   int32_t *d_mvp = nullptr; int mvp_cap = 0;   // xvcb200_set_mv_predictors: [cu][column][2]
   int mvp_cols = 0;                            // 0: none given for the current CU array
   int32_t *h_mvp[2] = {nullptr, nullptr}; size_t h_mvp_cap[2] = {0, 0}; cudaEvent_t mvp_ev[2] = {nullptr, nullptr};   // page-locked staging, alternating
@@ -498,6 +499,35 @@ template <typename T> static bool ensure(xvcb200_ctx *c, T **ptr, int *cap, int 
   return true;
 }
 
+// TMA descriptors of every slot's luma plane (see FsTensorMaps).  cuTensorMapEncodeTiled comes from the
+// driver through the runtime's entry-point query, so the library does not link libcuda.
+static bool encode_luma_tensor_maps(CtxFull *c) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+  if (!c->check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q), "cudaGetDriverEntryPoint") || !fn ||
+      q != cudaDriverEntryPointSuccess)
+    return c->fail(XVCB200_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  EncodeTiled encode = reinterpret_cast<EncodeTiled>(fn);
+  const int pitch = c->geom.pitch[0], rows = c->geom.height[0] + 2 * c->geom.margin_y[0];
+  c->ex.luma_tmaps.resize(2 * c->slots.size());
+  for (size_t s = 0; s < c->slots.size(); s++)
+    for (int k = 0; k < 2; k++) {
+      void *base = c->slots[s].base[0] - ((size_t)c->geom.margin_y[0] * pitch + c->geom.margin_x[0]);    // allocation start of the plane
+      const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+      const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(Sample)};
+      const cuuint32_t box[2] = {(cuuint32_t)(k ? kFsBoxWide : kFsBoxNarrow), (cuuint32_t)kFsBoxRows};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = encode(&c->ex.luma_tmaps[2 * s + k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return c->fail(XVCB200_CUDA_ERROR, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    }
+  return true;
+}
+
 extern "C" {
 
 int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int bitdepth, int chroma_format,
@@ -559,6 +589,7 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
     }
   }
   c->ex.h_luma_views = views;
+  if (!encode_luma_tensor_maps(c)) { int st = c->status; xvcb200_ctx_destroy(c); return st; }
   c->map_w = width >> 2; c->map_h = height >> 2;
   const size_t cells = (size_t)c->map_w * c->map_h;
   if (!c->check(cudaMalloc(&c->ex.d_luma_views, sizeof(PlaneView) * num_slots), "cudaMalloc(views)") ||
@@ -1588,11 +1619,14 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
   if (P.bi_iterations > 0) {
     PlaneView worig = orig;
     worig.base = reinterpret_cast<Sample *>(c->ex.d_worig);
+    FsTensorMaps fs_maps;
+    memset(&fs_maps, 0, sizeof(fs_maps));
+    for (int l = 0; l < 2; l++)
+      for (int r = 0; r < P.R[l]; r++)
+        for (int k = 0; k < 2; k++) fs_maps.m[l * P.R[0] + r][k] = c->ex.luma_tmaps[2 * (size_t)P.ref_slot[l][r] + k];
     for (int it = 0; it < P.bi_iterations; it++) {
-      c->check(launch_bi_prepare(c->stream, c->d_cus, P, it, c->ex.d_jobs, c->ex.d_me, c->ex.d_me_state, orig, c->ex.d_luma_views, worig,
-                                 c->ex.d_bi_jobs), "bi_prepare");
-      c->check(launch_full_search_worig(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
-                                        c->ex.d_bi_res), "full_search");
+      c->check(launch_bi_search(c->stream, c->d_cus, P, it, c->ex.d_jobs, c->ex.d_me, c->ex.d_me_state, orig, c->ex.d_luma_views, worig,
+                                fs_maps, c->geom.margin_x[0], c->geom.margin_y[0], c->ex.d_bi_jobs, c->ex.d_bi_res), "bi_search");
       c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
                                     c->ex.d_bi_res, c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev, c->ex.n_side, c->ex.fork_ev),
                "subpel_search(bi)");

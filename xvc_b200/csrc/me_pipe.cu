@@ -111,73 +111,6 @@ cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const 
   return cudaGetLastError();
 }
 
-// One CTA per CU: prediction of the list that is kept (luma, uni-prediction: MotionCompensation with
-// InterDir = that list, inter_search.cc:415-418), weighted original into `worig`, jobs of the list
-// that is searched.  job.prev carries the bootstrap vector (GetBestUniPredMv, :497) in 1/16 pel.
-__global__ void __launch_bounds__(128) bi_prepare_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P,
-                                                         int iteration, const xvcb200_me_job *__restrict__ jobs,
-                                                         const xvcb200_me_result *__restrict__ res,
-                                                         MeCuState *__restrict__ state, PlaneView orig,
-                                                         const PlaneView *__restrict__ luma, PlaneView worig,
-                                                         xvcb200_me_job *__restrict__ bi_jobs) {
-  __shared__ int16_t tmp[64 * 71];
-  __shared__ Sample pred[64 * 64];
-  __shared__ int s_sl;
-  const int i = blockIdx.x, tid = threadIdx.x;
-  const xvcb200_cu cu = cus[i];
-  MeCuState *st = &state[i];
-  const bool run = st->active && !st->bi_done && st->uni_ref[0] >= 0 && st->uni_ref[1] >= 0;
-  if (tid == 0) {
-    int sl = st->search_list;
-    if (run && iteration == 0) {
-      // the list with the higher uni cost first (:402-403); CU state = best of both lists (:231-233)
-      sl = st->cost_uni[0] <= st->cost_uni[1] ? 1 : 0;
-      st->search_list = (int8_t)sl;
-      for (int l = 0; l < 2; l++) { st->bi_ref[l] = st->uni_ref[l]; st->bi_mv[l][0] = st->uni_mv[l][0]; st->bi_mv[l][1] = st->uni_mv[l][1]; }
-    }
-    if (!run && !st->bi_done) st->bi_done = 1;
-    s_sl = sl;
-    for (int r = 0; r < P.Rmax; r++) {
-      xvcb200_me_job j;
-      j.cu = i; j.list = sl; j.ref_slot = 0; j.search_range = 0;
-      j.mvp[0] = j.mvp[1] = 0; j.prev[0] = j.prev[1] = 0;
-      if (run && r < P.R[sl]) {
-        const size_t col = (size_t)i * P.J + (sl ? P.R[0] + r : r);
-        const xvcb200_me_result q = res[col];
-        j.mvp[0] = jobs[col].mvp[0]; j.mvp[1] = jobs[col].mvp[1];
-        j.ref_slot = P.ref_slot[sl][r];
-        j.search_range = 4;                              // encoder_settings.h:65 inter_search_range_bi
-        j.prev[0] = q.mv[0]; j.prev[1] = q.mv[1];
-      }
-      bi_jobs[(size_t)i * P.Rmax + r] = j;
-    }
-  }
-  __syncthreads();
-  if (!run) return;
-  const int other = 1 - s_sl;
-  const PlaneView rp = luma[P.ref_slot[other][st->bi_ref[other]]];
-  int mx = st->bi_mv[other][0], my = st->bi_mv[other][1];
-  clip_mv(cu.x, cu.y, rp.width, rp.height, mx, my);
-  const Sample *r = rp.base + (cu.y + (my >> 4)) * rp.pitch + cu.x + (mx >> 4);
-  interp_cta<false, 8>(cu.w, cu.h, P.bitdepth, mx & 15, my & 15, r, rp.pitch, pred, 64, tmp, tid, 128);
-  __syncthreads();
-  const int lw = 31 - __clz((int)cu.w);
-  int16_t *dst = reinterpret_cast<int16_t *>(worig.base);
-  for (int k = tid; k < cu.w * cu.h; k += 128) {
-    const int y = k >> lw, x = k & (cu.w - 1);
-    dst[(cu.y + y) * worig.pitch + cu.x + x] = (int16_t)(2 * (int)orig.base[(cu.y + y) * orig.pitch + cu.x + x] - (int)pred[y * 64 + x]);
-  }
-}
-
-cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
-                              const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
-                              PlaneView worig, xvcb200_me_job *d_bi_jobs) {
-  if (P.n <= 0) return cudaSuccess;
-  g_launch_count++;
-  bi_prepare_kernel<<<P.n, 128, 0, s>>>(d_cus, P, iteration, d_jobs, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig, d_bi_jobs);
-  return cudaGetLastError();
-}
-
 // ---------------------------------------------------------------- InterSearch::FullSearch
 // Every full-pel position of the clipped +-range window around the bootstrap vector, row-major, on
 // the int16 weighted original (SampleMetric on Residual vs Sample: SAD, or SAD over every second
@@ -259,28 +192,237 @@ __device__ __forceinline__ void full_search_cta(const xvcb200_cu &cu, int ref_w,
   }
 }
 
-__global__ void __launch_bounds__(128) full_search_worig_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
-                                                                int bitdepth, uint32_t lambda, PlaneView worig,
-                                                                const PlaneView *__restrict__ luma, xvcb200_me_result *__restrict__ res) {
-  __shared__ uint32_t s_win[(64 + 2 * kFsRange) * kFsWinPitch];
-  __shared__ uint32_t s_org[64 * kFsOrgPitch];
-  __shared__ unsigned long long s_best;
-  const xvcb200_me_job job = jobs[blockIdx.x];
-  if (job.search_range == 0) return;
-  const xvcb200_cu cu = cus[job.cu];
-  const PlaneView ref = luma[job.ref_slot];
-  const int16_t *wo = reinterpret_cast<const int16_t *>(worig.base) + cu.y * worig.pitch + cu.x;
-  const int wp = worig.pitch;
-  full_search_cta(cu, ref.width, ref.height, ref.base, ref.pitch, job.mvp[0], job.mvp[1], job.prev[0], job.prev[1],
-                  min(job.search_range, kFsRange), bitdepth, lambda, [&](int x, int y) { return (int)wo[y * wp + x]; }, s_win, s_org,
-                  &s_best, &res[blockIdx.x]);
+// ---- one SearchBiIterative pass up to the full-pel vector, one CTA per CU -------------------------------
+//   1. thread 0 picks the list to search (:402-403, :428), writes the pass's jobs, and -- the search windows
+//      depend on nothing the CTA computes -- issues cp.async.bulk.tensor.2d loads (TMA) of the windows of
+//      the first two reference pictures of that list: (w + 8) x (h + 8) samples of the padded plane as
+//      boxes of kFsBoxRows rows, narrow or wide by block width, starting at the window origin rounded
+//      down to 8 samples (the copy engine wants 16-byte aligned box origins), arrival on an mbarrier each;
+//   2. while they fly, all threads build the prediction of the list that is kept (luma, uni-prediction:
+//      MotionCompensation with InterDir = that list, :415-418) and the weighted original 2 * orig - pred
+//      (ResidualBuffer::SubtractWeighted) -- to the `worig` plane for the sub-pel search that follows, and
+//      packed (rows the metric visits, biased by 2^bitdepth) into shared memory;
+//   3. InterSearch::FullSearch per reference picture (:853-891): the window is copied once more shifted
+//      by one sample, so that candidates at odd and at even offsets both read aligned 32-bit words; a
+//      thread per (candidate, half of the block's rows): SAD = VIMNMX.U16x2 max - min on pairs biased by
+//      2^bitdepth (the original is a broadcast read, neighbouring candidates share window words), halves
+//      joined by a shared-memory atomicAdd, the first minimum in scan order through a 64-bit
+//      (cost << 32 | position) atomicMin.  A third and later picture of the list re-uses a window buffer
+//      as soon as its search is done.  (Measured: a warp per candidate with a REDUX.SUM per candidate costs
+//      6x the instructions on the small blocks that make up most of a picture.)
+// job.prev of the pass's jobs carries the bootstrap vector (GetBestUniPredMv, :497) in 1/16 pel.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-cudaError_t launch_full_search_worig(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
-                                     uint32_t lambda_me, PlaneView worig, const PlaneView *d_luma_views, xvcb200_me_result *d_res) {
-  if (n <= 0) return cudaSuccess;
+constexpr int kFsWinRows = 72;                         // (64 + 8) rows at most
+constexpr int kFsBiRange = 4;                          // encoder_settings.h:65 inter_search_range_bi
+constexpr int kFsOrgPitch16 = 2 * kFsOrgPitch;         // the packed original addressed as uint16
+
+struct FsGeom { int nx, ny, lox, loy, ox0, wp, wrows, wide, mvpx, mvpy, ref_slot; };
+
+constexpr int kBiThreads = 192;
+constexpr int kFsCands = (2 * kFsBiRange + 1) * (2 * kFsBiRange + 1);
+
+__global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P, int iteration,
+                                                        const xvcb200_me_job *__restrict__ jobs, const xvcb200_me_result *__restrict__ res,
+                                                        MeCuState *__restrict__ state, PlaneView orig, const PlaneView *__restrict__ luma,
+                                                        PlaneView worig, const __grid_constant__ FsTensorMaps maps, int margin_x,
+                                                        int margin_y, xvcb200_me_job *__restrict__ bi_jobs,
+                                                        xvcb200_me_result *__restrict__ bi_res) {
+  // interpolation scratch (64 x 71 int16) + prediction (64 x 64); the shifted window re-uses it afterwards
+  __shared__ __align__(16) uint16_t s_scratch[64 * 71 + 64 * 64];
+  __shared__ __align__(128) uint16_t s_win[2][kFsWinRows * kFsBoxWide];
+  __shared__ uint32_t s_org[32 * kFsOrgPitch];
+  __shared__ unsigned long long s_best;
+  __shared__ uint2 s_cand[kFsCands];
+  __shared__ uint32_t s_sad[kFsCands];
+  __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ int s_sl;
+  int16_t *tmp = reinterpret_cast<int16_t *>(s_scratch);
+  Sample *pred = s_scratch + 64 * 71;
+  uint16_t *s_shift = s_scratch;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  const xvcb200_cu cu = cus[i];
+  MeCuState *st = &state[i];
+  const bool run = st->active && !st->bi_done && st->uni_ref[0] >= 0 && st->uni_ref[1] >= 0;
+  const int w = cu.w, h = cu.h;
+  const int fast = h > 8, rstep = fast ? 2 : 1, rows = fast ? h >> 1 : h;
+
+  // window geometry of the pass's job r (list sl)
+  auto geom = [&](int sl, int r) {
+    FsGeom g;
+    const size_t col = (size_t)i * P.J + (sl ? P.R[0] + r : r);
+    g.mvpx = jobs[col].mvp[0]; g.mvpy = jobs[col].mvp[1];
+    g.ref_slot = P.ref_slot[sl][r];
+    const PlaneView ref = luma[g.ref_slot];
+    int lo[2], hi[2];
+    min_max_mv(cu.x, cu.y, ref.width, ref.height, res[col].mv[0], res[col].mv[1], kFsBiRange, lo, hi);
+    g.nx = hi[0] - lo[0] + 1; g.ny = hi[1] - lo[1] + 1; g.lox = lo[0]; g.loy = lo[1];
+    g.ox0 = (cu.x + lo[0]) & 7;                                     // window origin inside the 16-byte aligned box
+    g.wide = w + 2 * kFsBiRange + 7 > kFsBoxNarrow;
+    g.wp = (g.wide ? kFsBoxWide : kFsBoxNarrow) >> 1;
+    g.wrows = h + g.ny - 1;
+    return g;
+  };
+  auto issue_window = [&](int sl, int r, int stage) {               // one thread
+    const FsGeom g = geom(sl, r);
+    const int box_w = 2 * g.wp, nbox = (g.wrows + kFsBoxRows - 1) / kFsBoxRows;
+    const CUtensorMap *map = &maps.m[sl ? P.R[0] + r : r][g.wide];
+    mbar_arrive_expect_tx(&s_full[stage], (uint32_t)(nbox * box_w * kFsBoxRows * 2));
+    const int x0 = margin_x + cu.x + g.lox - g.ox0, y0 = margin_y + cu.y + g.loy;
+    for (int k = 0; k < nbox; k++) tma_load_2d(&s_win[stage][k * kFsBoxRows * box_w], map, x0, y0 + k * kFsBoxRows, &s_full[stage]);
+  };
+
+  if (tid == 0) {
+    int sl = st->search_list;
+    if (run && iteration == 0) {
+      // the list with the higher uni cost first (:402-403); CU state = best of both lists (:231-233)
+      sl = st->cost_uni[0] <= st->cost_uni[1] ? 1 : 0;
+      st->search_list = (int8_t)sl;
+      for (int l = 0; l < 2; l++) { st->bi_ref[l] = st->uni_ref[l]; st->bi_mv[l][0] = st->uni_mv[l][0]; st->bi_mv[l][1] = st->uni_mv[l][1]; }
+    }
+    if (!run && !st->bi_done) st->bi_done = 1;
+    s_sl = sl;
+    for (int r = 0; r < P.Rmax; r++) {
+      xvcb200_me_job j;
+      j.cu = i; j.list = sl; j.ref_slot = 0; j.search_range = 0;
+      j.mvp[0] = j.mvp[1] = 0; j.prev[0] = j.prev[1] = 0;
+      if (run && r < P.R[sl]) {
+        const size_t col = (size_t)i * P.J + (sl ? P.R[0] + r : r);
+        const xvcb200_me_result q = res[col];
+        j.mvp[0] = jobs[col].mvp[0]; j.mvp[1] = jobs[col].mvp[1];
+        j.ref_slot = P.ref_slot[sl][r];
+        j.search_range = kFsBiRange;
+        j.prev[0] = q.mv[0]; j.prev[1] = q.mv[1];
+      }
+      bi_jobs[(size_t)i * P.Rmax + r] = j;
+    }
+    if (run) {
+      mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+      mbar_init_fence();
+      for (int r = 0; r < min(P.R[sl], 2); r++) issue_window(sl, r, r);
+    }
+  }
+  __syncthreads();
+  if (!run) return;
+  const int sl = s_sl, other = 1 - sl;
+  {
+    const PlaneView rp = luma[P.ref_slot[other][st->bi_ref[other]]];
+    int mx = st->bi_mv[other][0], my = st->bi_mv[other][1];
+    clip_mv(cu.x, cu.y, rp.width, rp.height, mx, my);
+    const Sample *r = rp.base + (cu.y + (my >> 4)) * rp.pitch + cu.x + (mx >> 4);
+    interp_cta<false, 8>(w, h, P.bitdepth, mx & 15, my & 15, r, rp.pitch, pred, 64, tmp, tid, kBiThreads);
+  }
+  __syncthreads();
+  const int bias = 1 << P.bitdepth;
+  const uint32_t bias2 = (uint32_t)bias | ((uint32_t)bias << 16);
+  const int lw = 31 - __clz(w), lpw = lw - 1, nelem = rows << lpw;
+  {
+    int16_t *dst = reinterpret_cast<int16_t *>(worig.base);
+    uint16_t *org16 = reinterpret_cast<uint16_t *>(s_org);
+    for (int k = tid; k < w * h; k += kBiThreads) {
+      const int y = k >> lw, x = k & (w - 1);
+      const int v = 2 * (int)orig.base[(cu.y + y) * orig.pitch + cu.x + x] - (int)pred[y * 64 + x];
+      dst[(cu.y + y) * worig.pitch + cu.x + x] = (int16_t)v;
+      if (!(y & (rstep - 1))) org16[(y >> (rstep - 1)) * kFsOrgPitch16 + x] = (uint16_t)(v + bias);
+    }
+  }
+  __syncthreads();                                                   // the scratch is free from here on: s_shift
+  const int down = (cu.flags & XVCB200_CU_FULLPEL_MV) ? 2 : 0;
+  for (int r = 0; r < P.R[sl]; r++) {
+    const int stage = r & 1;
+    const FsGeom g = geom(sl, r);
+    mbar_wait(&s_full[stage], (uint32_t)(r >> 1) & 1);
+    {   // the window once more, one sample to the left (the word after a row's last one is never read by a candidate)
+      const uint32_t *src = reinterpret_cast<const uint32_t *>(s_win[stage]);
+      uint32_t *dstw = reinterpret_cast<uint32_t *>(s_shift);
+      for (int k = tid; k < g.wrows * g.wp - 1; k += kBiThreads) dstw[k] = __funnelshift_r(src[k], src[k + 1], 16);
+    }
+    // per candidate, once: where its window starts (word offset, bit 31 = odd sample offset -> shifted copy) and its rate
+    const int total = g.nx * g.ny;
+    if (tid < total) {
+      const int cyi = tid / g.nx, cxi = tid - cyi * g.nx, ox = g.ox0 + cxi;
+      s_cand[tid] = make_uint2((uint32_t)(cyi * g.wp + (ox >> 1)) | ((uint32_t)(ox & 1) << 31),
+                               (P.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, g.lox + cxi, g.loy + cyi, down)) >> 16);
+    }
+    if (tid < kFsCands) s_sad[tid] = 0;
+    if (tid == 0) s_best = ~0ull;
+    __syncthreads();
+    // a thread per (candidate, half of the rows): the original is a broadcast read, neighbouring candidates share words
+    if (tid < 2 * kFsCands) {
+      const int half = tid >= kFsCands, t = tid - half * kFsCands;
+      if (t < total) {
+        const uint2 cd = s_cand[t];
+        const int hrows = rows >> 1, pairs = 1 << lpw;
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>((cd.x >> 31) ? s_shift : s_win[stage]) + (cd.x & 0x7fffffffu) + half * hrows * rstep * g.wp;
+        const uint32_t *po = s_org + half * hrows * kFsOrgPitch;
+        uint32_t sad = 0;
+        for (int r = 0; r < hrows; r++) {
+          if (pairs == 2) {
+            const uint32_t acc = fs_absdiff2(po[0], pw[0] + bias2) + fs_absdiff2(po[1], pw[1] + bias2);
+            sad += (acc & 0xffffu) + (acc >> 16);
+          } else {
+            for (int c = 0; c < pairs; c += 4) {          // 4 differences of <= 3 * 2^bitdepth per 16-bit lane
+              const uint32_t acc = fs_absdiff2(po[c], pw[c] + bias2) + fs_absdiff2(po[c + 1], pw[c + 1] + bias2) +
+                                   fs_absdiff2(po[c + 2], pw[c + 2] + bias2) + fs_absdiff2(po[c + 3], pw[c + 3] + bias2);
+              sad += (acc & 0xffffu) + (acc >> 16);
+            }
+          }
+          pw += rstep * g.wp; po += kFsOrgPitch;
+        }
+        atomicAdd(&s_sad[t], sad);
+      }
+    }
+    __syncthreads();
+    if (tid < total) {
+      const uint32_t sad = s_sad[tid];
+      const uint32_t dist = fast ? (sad * 2) >> (P.bitdepth - 8) : sad >> (P.bitdepth - 8);
+      atomicMin(&s_best, ((unsigned long long)(dist + s_cand[tid].y) << 32) | (unsigned)tid);
+    }
+    __syncthreads();                                                 // every read of the window and of s_shift is done
+    if (tid == 0) {
+      const unsigned long long b = s_best;
+      const int t = (int)(b & 0xffffffffu);
+      const int bx = g.lox + t % g.nx, by = g.loy + t / g.nx;
+      xvcb200_me_result *out = &bi_res[(size_t)i * P.Rmax + r];
+      out->mv_fullpel[0] = bx; out->mv_fullpel[1] = by;
+      out->mv[0] = bx * 16; out->mv[1] = by * 16;
+      out->cost_fullpel = (uint32_t)(b >> 32); out->dist = 0; out->cost = (uint32_t)(b >> 32); out->num_sad = (uint32_t)total;
+      if (r + 2 < P.R[sl]) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_window(sl, r + 2, stage);
+      }
+    }
+  }
+}
+
+cudaError_t launch_bi_search(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
+                             const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
+                             PlaneView worig, const FsTensorMaps &maps, int margin_x, int margin_y, xvcb200_me_job *d_bi_jobs,
+                             xvcb200_me_result *d_bi_res) {
+  if (P.n <= 0) return cudaSuccess;
   g_launch_count++;
-  full_search_worig_kernel<<<n, 128, 0, s>>>(d_cus, d_jobs, bitdepth, lambda_me, worig, d_luma_views, d_res);
+  bi_search_kernel<<<P.n, kBiThreads, 0, s>>>(d_cus, P, iteration, d_jobs, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig,
+                                       maps, margin_x, margin_y, d_bi_jobs, d_bi_res);
   return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 #ifndef XVCB_INTERNAL_H_
 #define XVCB_INTERNAL_H_
 
+#include <cuda.h>             // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no libcuda link)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -164,14 +165,22 @@ size_t me_cu_state_bytes();
 cudaError_t launch_make_me_jobs(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, xvcb200_me_job *d_jobs);
 cudaError_t launch_me_uni_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
                                  xvcb200_me_result *d_res, void *d_state);
-// one pass of InterSearch::SearchBiIterative for every CU still refining: weighted original of the list
-// that is kept -> luma plane of `worig` (int16), jobs of the list that is searched -> d_bi_jobs [cu][Rmax]
-cudaError_t launch_bi_prepare(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
-                              const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
-                              PlaneView worig, xvcb200_me_job *d_bi_jobs);
-// InterSearch::FullSearch on the weighted original for jobs [0, n): mv_fullpel / cost_fullpel of d_res
-cudaError_t launch_full_search_worig(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
-                                     uint32_t lambda_me, PlaneView worig, const PlaneView *d_luma_views, xvcb200_me_result *d_res);
+// Tensor maps (TMA descriptors) of the padded luma planes the bi-prediction full search reads: per job
+// column (list 0 pictures, then list 1 pictures) a narrow (kFsBoxNarrow x kFsBoxRows samples) and a wide
+// (kFsBoxWide x kFsBoxRows) box over the WHOLE allocation of the plane (margins included), so that box
+// coordinates are (margin_x + x, margin_y + y) and rows beyond the allocation read as zero.  The
+// innermost box coordinate must sit on a 16-byte boundary (measured: an odd sample offset raises
+// "illegal instruction", tools/tma_probe.cu), so a box starts at the window origin rounded down to 8
+// samples and is 7 samples wider than the window: 16 + 8 + 7 <= 40, 64 + 8 + 7 <= 80.
+constexpr int kFsBoxNarrow = 40, kFsBoxWide = 80, kFsBoxRows = 8;
+struct FsTensorMaps { CUtensorMap m[10][2]; };
+// One pass of InterSearch::SearchBiIterative up to the full-pel vectors, for every CU still refining: the
+// weighted original of the list that is kept -> luma plane of `worig` (int16), InterSearch::FullSearch
+// (+-4) of every picture of the list that is searched -> jobs d_bi_jobs / results d_bi_res, [cu][Rmax]
+cudaError_t launch_bi_search(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
+                             const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
+                             PlaneView worig, const FsTensorMaps &maps, int margin_x, int margin_y, xvcb200_me_job *d_bi_jobs,
+                             xvcb200_me_result *d_bi_res);
 cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
                                 const xvcb200_me_result *d_bi_res, xvcb200_me_result *d_res, void *d_state);
 cudaError_t launch_me_final_decide(cudaStream_t s, xvcb200_cu *d_cus, const MePipe &P, const void *d_state);
