@@ -478,6 +478,25 @@ typedef struct {
  * chosen ref_idx / mv written back into the CU array, me_results[n * (num_ref[0] + num_ref[1])]
  * laid out [cu][list 0 pictures, list 1 pictures] (uni searches; may be NULL), tu_results[3*n]
  * (may be NULL).  num_ref[l] <= 0 reads as one picture (list 1: none for pic_type 1). */
+/* Optional: transform modes per CU for the residual-coding entries below (what CodingUnit carries in tx_:
+ * coding_unit.h:173-191).  Without them every unit is coded with the default transform -- DCT-2, or the 4 x 4
+ * DST for the luma block of an intra CU (transform.cc:87-89, 873-875) --, no transform skip, diagonal scan.
+ *   tx_ver / tx_hor  luma transform types XVCB200_TX_* (cu.GetTransformType(kY, 0 / 1)): what
+ *                    CodingUnit::SetTransformFromSelectIdx (coding_unit.cc:359-424) derived; chroma is DCT-2
+ *   tskip            bit c: transform skip of component c (blocks of <= 16 samples, coding_unit.h:202-204)
+ *   scan             per component TransformHelper::DetermineScanOrder (transform.cc:1614-1636):
+ *                    0 diagonal, 1 horizontal, 2 vertical (sign hiding walks the block in this order)
+ * The choice between the candidates (TransformEncoder::CompressAndEvalTransform) compares entropy-coded
+ * bit counts and stays with the caller.  modes: HOST array [n_cus]; belongs to the current CU array
+ * (xvcb200_set_cus drops it), NULL drops it explicitly. */
+typedef struct {
+  uint8_t tx_ver, tx_hor;
+  uint8_t tskip;
+  uint8_t scan[3];
+  uint8_t reserved[2];
+} xvcb200_tu_mode;
+int xvcb200_set_tu_modes(xvcb200_ctx *ctx, const xvcb200_tu_mode *modes);
+
 /* Optional: one predictor per (CU, list, reference picture) instead of the CU's mv[list] -- what
  * InterSearch::GetMvpList (inter_search.cc:489-492: per ref_idx, neighbour vectors scaled by POC distance)
  * gives the reference's search.  mvp: HOST array [n_cus][n_cols][2], 1/16 pel, columns ordered like

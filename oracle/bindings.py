@@ -360,6 +360,8 @@ class Ref:
         L.xref_session_get_rec_padded.argtypes = [c_void_p, c_int, c_void_p]
         L.xref_session_set_cus.argtypes = [c_void_p, c_void_p, c_int]
         L.xref_session_get_cus.argtypes = [c_void_p, c_void_p, c_int]
+        L.xref_session_set_tu_modes.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
+        L.xref_session_scan_orders.argtypes = [c_void_p, c_void_p]
         L.xref_encode_picture_mvp.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
         L.xref_search_motion_single.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         L.xref_me_search.argtypes = [c_void_p, c_void_p, c_int, c_double, c_int, c_void_p]
@@ -626,6 +628,21 @@ class RefSession:
 
     def pad_border_rec(self):
         self.L.xref_pad_border_rec(self.h)
+
+    def set_tu_modes(self, modes, intra_luma_modes=None):
+        """After set_cus: transform types / transform skip per CU and the luma intra mode (uint8 per CU) the
+        reference derives the coefficient scan from."""
+        n = len(modes) if modes is not None else len(intra_luma_modes)
+        if modes is not None:
+            modes = np.ascontiguousarray(modes, dtype=abi.tu_mode_dtype)
+        if intra_luma_modes is not None:
+            intra_luma_modes = np.ascontiguousarray(intra_luma_modes, dtype=np.uint8)
+        self.L.xref_session_set_tu_modes(self.h, abi.ptr(modes), abi.ptr(intra_luma_modes), n)
+
+    def scan_orders(self, n):
+        out = np.zeros((n, 3), dtype=np.uint8)
+        self.L.xref_session_scan_orders(self.h, abi.ptr(out))
+        return out
 
     def search_motion_single(self, params, cu):
         """(ref_shim's restated SearchMotion, InterSearch::SearchMotion itself) for a picture holding only `cu`."""

@@ -528,6 +528,34 @@ void xref_session_get_cus(xref_session *s, xvcb200_cu *cus, int n) {
   }
 }
 
+// Transform modes of the session's CUs (xvcb200_set_tu_modes) + the luma intra mode the reference derives the
+// coefficient scan from (TransformHelper::DetermineScanOrder; chroma follows luma: kDmChroma).  The scan
+// entries of `modes` are NOT used here -- the reference computes its own from the intra mode.
+void xref_session_set_tu_modes(xref_session *s, const xvcb200_tu_mode *modes, const uint8_t *intra_luma_mode, int n) {
+  for (int i = 0; i < n && i < static_cast<int>(s->cus.size()); i++) {
+    CodingUnit *cu = s->cus[i];
+    if (cu->IsIntra() && intra_luma_mode) {
+      cu->SetIntraModeLuma(static_cast<IntraMode>(intra_luma_mode[i]));
+      cu->SetIntraModeChroma(IntraChromaMode::kDmChroma);
+    }
+    if (!modes) continue;
+    cu->SetTransformType(YuvComponent::kY, static_cast<TransformType>(modes[i].tx_ver), static_cast<TransformType>(modes[i].tx_hor));
+    for (int c = 0; c < 3; c++) {
+      YuvComponent comp = static_cast<YuvComponent>(c);
+      cu->SetTransformSkip(comp, cu->CanTransformSkip(comp) && ((modes[i].tskip >> c) & 1));
+    }
+  }
+}
+
+// TransformHelper::DetermineScanOrder for every CU and component (0 diagonal, 1 horizontal, 2 vertical)
+void xref_session_scan_orders(xref_session *s, uint8_t *out /* n x 3 */) {
+  for (size_t i = 0; i < s->cus.size(); i++)
+    for (int c = 0; c < 3; c++) {
+      const ScanOrder o = TransformHelper::DetermineScanOrder(*s->cus[i], static_cast<YuvComponent>(c));
+      out[3 * i + c] = o == ScanOrder::kDiagonal ? 0 : (o == ScanOrder::kHorizontal ? 1 : 2);
+    }
+}
+
 // ---------------------------------------------------------------- motion estimation
 namespace {
 struct MeWorker {
@@ -761,7 +789,9 @@ void xref_tq_reconstruct(xref_session *s, int threads, xvcb200_tu_result *result
       SampleBuffer pred = s->pred->GetSampleBuffer(comp, x, y);
       SampleBuffer reco = s->rec->GetSampleBuffer(comp, x, y);
       t->resi_orig.Subtract(w, h, orig, pred);
-      t->fwd.Transform(*cu, comp, t->resi_orig, &t->tmp);
+      const bool skip_transform = cu->GetTransformSkip(comp);      // transform_encoder.cc:213-227
+      if (!skip_transform) t->fwd.Transform(*cu, comp, t->resi_orig, &t->tmp);
+      else t->fwd.TransformSkip(w, h, t->resi_orig, &t->tmp);
       int nz = t->q.QuantFast(*cu, comp, qp, cu->GetPicType(), t->tmp.GetDataPtr(), t->tmp.GetStride(),
                               t->lev.GetDataPtr(), t->lev.GetStride());
       cu->SetDcCoeffOnly(comp, false);   // the batched path never takes the DC shortcut
@@ -775,7 +805,8 @@ void xref_tq_reconstruct(xref_session *s, int threads, xvcb200_tu_result *result
       if (cbf) {
         t->dq.Inverse(comp, qp, w, h, bd, t->lev.GetDataPtr(), t->lev.GetStride(), t->tmp.GetDataPtr(),
                       t->tmp.GetStride());
-        t->inv.Transform(*cu, comp, t->tmp, &t->resi);
+        if (!skip_transform) t->inv.Transform(*cu, comp, t->tmp, &t->resi);
+        else t->inv.TransformSkip(w, h, t->tmp, &t->resi);
         reco.AddClip(w, h, pred, t->resi, 0, max_pel);
       } else {
         reco.CopyFrom(w, h, pred);

@@ -49,6 +49,8 @@ picture_params_dtype = np.dtype([
     ("bi_iterations", "<i4"), ("bits_mode", "<i4"),
 ], align=True)
 
+tu_mode_dtype = np.dtype([("tx_ver", "u1"), ("tx_hor", "u1"), ("tskip", "u1"), ("scan", "u1", (3,)), ("reserved", "u1", (2,))], align=True)    # xvcb200_tu_mode
+
 plane_geom_dtype = np.dtype([
     ("width", "<i4", (3,)), ("height", "<i4", (3,)), ("pitch", "<i4", (3,)),
     ("margin_x", "<i4", (3,)), ("margin_y", "<i4", (3,)),
@@ -78,6 +80,7 @@ ABI_STRUCTS = {
     8: ("xvcb200_intra_job", intra_job_dtype),
     9: ("xvcb200_affine_cu", affine_cu_dtype),
     10: ("xvcb200_lic_cu", lic_cu_dtype),
+    11: ("xvcb200_tu_mode", tu_mode_dtype),
 }
 
 

@@ -146,6 +146,7 @@ int xvcb200_abi_sizeof(int which) {
     case 8: return (int)sizeof(xvcb200_intra_job);
     case 9: return (int)sizeof(xvcb200_affine_cu);
     case 10: return (int)sizeof(xvcb200_lic_cu);
+    case 11: return (int)sizeof(xvcb200_tu_mode);
     default: return -1;
   }
 }
@@ -431,6 +432,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   xvcb200_me_result *d_bi_res = nullptr; int bi_res_cap = 0;
   int16_t *d_worig = nullptr;
   std::vector<CUtensorMap> luma_tmaps;         // per slot: [2 * slot + 0 / 1] = narrow / wide box over the padded luma plane (full search)
+  xvcb200_tu_mode *d_tu_modes = nullptr; int tu_modes_cap = 0; bool tu_modes_set = false;   // xvcb200_set_tu_modes
   int32_t *d_mvp = nullptr; int mvp_cap = 0;   // xvcb200_set_mv_predictors: [cu][column][2]
   int mvp_cols = 0;                            // 0: none given for the current CU array
   int32_t *h_mvp[2] = {nullptr, nullptr}; size_t h_mvp_cap[2] = {0, 0}; cudaEvent_t mvp_ev[2] = {nullptr, nullptr};   // page-locked staging, alternating
@@ -640,7 +642,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   for (int b = 0; b < 2; b++) { if (c->ex.h_mvp[b]) cudaFreeHost(c->ex.h_mvp[b]); if (c->ex.mvp_ev[b]) cudaEventDestroy(c->ex.mvp_ev[b]); }
-  cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
+  cudaFree(c->ex.d_tu_modes); cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
@@ -1083,7 +1085,8 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
     for (int l = 0; l < 2; l++)
       if (!(cus[i].flags & XVCB200_CU_INTRA) && cus[i].ref_idx[l] > c->ex.max_ref_idx[l]) c->ex.max_ref_idx[l] = cus[i].ref_idx[l];
   c->n_cus = n;
-  c->ex.mvp_cols = 0;                       // predictors belong to a CU array
+  c->ex.mvp_cols = 0;                       // predictors and transform modes belong to a CU array
+  c->ex.tu_modes_set = false;
   if (n == 0) { c->ex.h_cus.clear(); return XVCB200_OK; }
   if (!copy_setup(c)) return c->status;
   // CU groups by CTU (counting sort: coding order inside a CTU is kept).  Only CUs that take part in the
@@ -1168,6 +1171,24 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   c->ex.d_tu_list = dl;
   c->ex.d_pipe_index = dl + 3 * (size_t)n;
   c->ex.d_pipe_groups = c->ex.d_pipe_index + n;
+  return XVCB200_OK;
+}
+
+int xvcb200_set_tu_modes(xvcb200_ctx *ctx, const xvcb200_tu_mode *modes) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  c->ex.tu_modes_set = false;
+  if (!modes || c->n_cus == 0) return XVCB200_OK;
+  for (int i = 0; i < c->n_cus; i++)
+    if (modes[i].tx_ver > XVCB200_TX_DST7 || modes[i].tx_hor > XVCB200_TX_DST7 || modes[i].tskip > 7 || modes[i].scan[0] > 2 ||
+        modes[i].scan[1] > 2 || modes[i].scan[2] > 2)
+      return XVCB200_INVALID_ARGUMENT;
+  if (!ensure(c, &c->ex.d_tu_modes, &c->ex.tu_modes_cap, c->n_cus)) return c->status;
+  // pageable host array: staged by the runtime before the call returns (the caller owns `modes`)
+  if (!c->check(cudaMemcpyAsync(c->ex.d_tu_modes, modes, sizeof(*modes) * (size_t)c->n_cus, cudaMemcpyHostToDevice, c->stream), "tu modes"))
+    return c->status;
+  c->ex.tu_modes_set = true;
   return XVCB200_OK;
 }
 
@@ -1445,6 +1466,7 @@ static int tq_common(xvcb200_ctx *ctx, int orig_slot, int pred_slot, int rec_slo
   join_downloads(c, -1);
   p.bitdepth = c->bitdepth; p.intra_picture = intra_picture; p.table = table; p.off_u = off_u; p.off_v = off_v;
   p.decode_only = decode_only;
+  p.modes = c->ex.tu_modes_set ? c->ex.d_tu_modes : nullptr;
   int16_t *lev[3]; int pitch[3];
   for (int k = 0; k < 3; k++) { lev[k] = reinterpret_cast<int16_t *>(c->slots[coeff_slot].base[k]); pitch[k] = c->geom.pitch[k]; }
   c->check(launch_tq_reconstruct_classes(c->stream, c->d_cus, c->ex.d_tu_list, c->ex.class_count, c->ex.class_offset, p,

@@ -24,14 +24,18 @@ static const int16_t h_mats[XVCB_MAT_TOTAL] = {XVCB_MAT_VALUES};
 __constant__ int c_dct2[XVCB_MAT_DCT2_TOTAL];
 static bool g_dct2_loaded[16] = {false};
 
-// The same matrices for the fused kernel, int32 in global memory (L1 resident; every thread of a
-// warp reads the same 16 bytes).  Per size N (offset = offset of the N x N matrix above), with
-// R = min(N, 32) the number of coefficients a 64-point transform keeps (kTransformZeroOutMinSize):
+// The same matrices for the fused kernel, int32 in global memory (L1 resident; the threads of a
+// transform unit read the same 16 bytes).  Per transform type and size N (offset = c_mat_off[type][log2 N],
+// the offset of the N x N matrix above; the 4 x 4 DST of intra luma blocks follows at XVCB_MAT_TOTAL),
+// with R = min(N, 32) the number of coefficients a 64-point transform keeps (kTransformZeroOutMinSize):
 //   g_tq_fwdT[j * R + k] = m[k][j]   forward: the R outputs of one input sample are contiguous
 //   g_tq_inv [k * N + j] = m[k][j]   inverse: the N outputs of one coefficient are contiguous
-constexpr int kTqTableInts = 3412;
+constexpr int kTqDst4Off = XVCB_MAT_TOTAL;
+constexpr int kTqTableInts = XVCB_MAT_TOTAL + 16;
 __device__ __align__(16) int g_tq_fwdT[kTqTableInts];
 __device__ __align__(16) int g_tq_inv[kTqTableInts];
+static const int h_mat_off[6][7] = XVCB_MAT_OFFSETS;
+static const int h_dst4[4][4] = {{29, 55, 74, 84}, {74, 74, 0, -74}, {84, -29, -74, 55}, {55, -84, 74, -29}};
 
 static cudaError_t ensure_dct2_constant() {
   int dev = 0;
@@ -39,16 +43,20 @@ static cudaError_t ensure_dct2_constant() {
   if (dev < 16 && g_dct2_loaded[dev]) return cudaSuccess;
   static int h_dct2[XVCB_MAT_DCT2_TOTAL], h_fwdT[kTqTableInts], h_inv[kTqTableInts];
   for (int i = 0; i < XVCB_MAT_DCT2_TOTAL; i++) h_dct2[i] = h_mats[i];
-  int off = 0;
-  for (int n = 2; n <= 64; n <<= 1) {
-    const int r = n > 32 ? 32 : n;
-    for (int k = 0; k < r; k++)
-      for (int j = 0; j < n; j++) {
-        h_fwdT[off + j * r + k] = h_mats[off + k * n + j];
-        h_inv[off + k * n + j] = h_mats[off + k * n + j];
-      }
-    off += (n / 2) * (n / 2) * 4;       // = n * n: the matrices lie back to back
-  }
+  for (int type = XVCB200_TX_DCT2; type <= XVCB200_TX_DST7; type++)
+    for (int lg = (type == XVCB200_TX_DCT2 ? 1 : 2); lg <= 6; lg++) {
+      const int n = 1 << lg, r = n > 32 ? 32 : n, off = h_mat_off[type][lg];
+      for (int k = 0; k < r; k++)
+        for (int j = 0; j < n; j++) {
+          h_fwdT[off + j * r + k] = h_mats[off + k * n + j];
+          h_inv[off + k * n + j] = h_mats[off + k * n + j];
+        }
+    }
+  for (int k = 0; k < 4; k++)
+    for (int j = 0; j < 4; j++) {
+      h_fwdT[kTqDst4Off + j * 4 + k] = h_dst4[k][j];
+      h_inv[kTqDst4Off + k * 4 + j] = h_dst4[k][j];
+    }
   cudaError_t e = cudaMemcpyToSymbol(c_dct2, h_dct2, sizeof(h_dct2));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tq_fwdT, h_fwdT, sizeof(h_fwdT));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tq_inv, h_inv, sizeof(h_inv));
@@ -336,7 +344,7 @@ template <int N> struct Split { static constexpr int kS = N >= 64 ? 4 : (N >= 32
 // forward line: in = N contiguous int16 (4-byte aligned); out[k*os] for k < N.  This thread: outputs
 // [split * KPT, (split + 1) * KPT) of the R = min(N, 32) computed ones (+ its share of the zeros).
 template <int N>
-__device__ __forceinline__ void fwd_line(const int16_t *in, int split, int16_t *out, int os, int shift, bool zero_line) {
+__device__ __forceinline__ void fwd_line(const int16_t *in, int split, int16_t *out, int os, int shift, bool zero_line, int mat_off) {
   constexpr int R = N > 32 ? 32 : N, S = Split<N>::kS, KPT = R / S;
   const int k0 = split * KPT;
   if (!zero_line) {
@@ -350,7 +358,7 @@ __device__ __forceinline__ void fwd_line(const int16_t *in, int split, int16_t *
     int acc[KPT];
 #pragma unroll
     for (int i = 0; i < KPT; i++) acc[i] = 1 << (shift - 1);
-    const int *mt = g_tq_fwdT + Dct2<N>::kOff + k0;
+    const int *mt = g_tq_fwdT + mat_off + k0;
 #pragma unroll
     for (int j = 0; j < N; j++) {
       if (KPT >= 4) {
@@ -379,7 +387,7 @@ __device__ __forceinline__ void fwd_line(const int16_t *in, int split, int16_t *
 // inverse line: in[k*is] for k < min(N,32); out = N contiguous int16, clipped.  This thread:
 // outputs [split * JPT, (split + 1) * JPT).
 template <int N>
-__device__ __forceinline__ void inv_line(const int16_t *in, int is, int split, int16_t *out, int shift, bool zero_line) {
+__device__ __forceinline__ void inv_line(const int16_t *in, int is, int split, int16_t *out, int shift, bool zero_line, int mat_off) {
   constexpr int R = N > 32 ? 32 : N, S = Split<N>::kS, JPT = N / S;
   const int j0 = split * JPT;
   if (zero_line) {
@@ -393,7 +401,7 @@ __device__ __forceinline__ void inv_line(const int16_t *in, int is, int split, i
   int acc[JPT];
 #pragma unroll
   for (int i = 0; i < JPT; i++) acc[i] = 1 << (shift - 1);
-  const int *m = g_tq_inv + Dct2<N>::kOff + j0;
+  const int *m = g_tq_inv + mat_off + j0;
 #pragma unroll
   for (int k = 0; k < R; k++) {
     if (JPT >= 4) {
@@ -452,6 +460,21 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
   const int bd = prm.bitdepth;
   int16_t *A = s_a[t], *B = s_b[t], *C = s_c[t], *D = s_b[t];   // D (levels, [H][PA]) lives in B between the transforms
 
+  // transform types, transform skip and coefficient scan of this unit (xvcb200_set_tu_modes; none: DCT-2 -- or the
+  // 4 x 4 DST of an intra CU's luma block, transform.cc:87-89, 873-875 --, no skip, diagonal scan)
+  int ty_ver = XVCB200_TX_DEFAULT, ty_hor = XVCB200_TX_DEFAULT, scan = 0;
+  bool tskip = false;
+  if (prm.modes) {
+    const xvcb200_tu_mode md = prm.modes[ci];
+    if (comp == 0) { ty_ver = md.tx_ver; ty_hor = md.tx_hor; }
+    tskip = W * H <= 16 && ((md.tskip >> comp) & 1);
+    scan = md.scan[comp];
+  }
+  const bool dst4 = W == 4 && H == 4 && comp == 0 && (cu.flags & XVCB200_CU_INTRA) && ty_ver == XVCB200_TX_DEFAULT && ty_hor == XVCB200_TX_DEFAULT;
+  const int hp = dst4 ? 0 : 2;            // the 4 x 4 DST has no high-precision variant (transform.cc:220, 1001)
+  const int off_hor = dst4 ? kTqDst4Off : c_mat_off[ty_hor == XVCB200_TX_DEFAULT ? XVCB200_TX_DCT2 : ty_hor][LW];
+  const int off_ver = dst4 ? kTqDst4Off : c_mat_off[ty_ver == XVCB200_TX_DEFAULT ? XVCB200_TX_DCT2 : ty_ver][LH];
+
   int qp_raw = cu.qp;
   if (comp) qp_raw = chroma_qp_raw(cu.qp, comp == 1 ? prm.off_u : prm.off_v, prm.table, c_chroma_scale);
   const int qp_bd = max(0, qp_raw + 6 * (bd - 8));
@@ -474,10 +497,21 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
         A[y * PA + x] = (int16_t)((int)orig[y * po.pitch + x] - (int)pred[y * pp.pitch + x]);
       }
     __syncthreads();
-    // forward: rows (N = W, lines = H) into B[k][y]; columns (N = H, lines = W) into C[x][y']
-    if (valid && ti < T1) fwd_line<W>(A + (ti % H) * PA, ti / H, B + (ti % H), PB, LW + bd - 9 + 2, false);
+    // (barriers are unconditional: the units sharing a CTA may differ in their modes)
+    if (W * H <= 16 && tskip) {
+      // ForwardTransform::TransformSkip (transform.cc:963-995)
+      const int odd = (LW + LH) & 1, sh = transform_shift(LW, LH, bd) + (odd ? -8 : 0), scale = odd ? 181 : 1;
+      if (valid)
+        for (int e = ti; e < W * H; e += TT) {
+          const int y = e / W, x = e % W, v = (int)A[y * PA + x] * scale;
+          C[y * PA + x] = (int16_t)(sh > 0 ? v * (1 << sh) : (v + (1 << (-sh - 1))) >> -sh);
+        }
+    } else if (valid && ti < T1) {
+      // forward: rows (N = W, lines = H) into B[k][y]; columns (N = H, lines = W) into C[x][y']
+      fwd_line<W>(A + (ti % H) * PA, ti / H, B + (ti % H), PB, LW + bd - 9 + hp, false, off_hor);
+    }
     __syncthreads();
-    if (valid && ti < T2) fwd_line<H>(B + (ti % W) * PB, ti / W, C + (ti % W), PA, LH + 6 + 2, (ti % W) >= 32);
+    if (!tskip && valid && ti < T2) fwd_line<H>(B + (ti % W) * PB, ti / W, C + (ti % W), PA, LH + 6 + hp, (ti % W) >= 32, off_ver);
     __syncthreads();
     // QuantFast (rdo_quant.cc:156-201)
     const QuantParams q = quant_params(LW, LH, bd, qp_bd, prm.intra_picture);
@@ -493,7 +527,7 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
       }
     if (mine) atomicAdd(&s_nnz[t], mine);
     __syncthreads();
-    if (W >= 4 && H >= 4) {   // sign hiding, diagonal scan (inter CU: transform.cc:1618-1621)
+    if (W >= 4 && H >= 4) {   // sign hiding in the unit's scan order (TransformHelper::DetermineScanOrder, transform.cc:1614-1636)
       constexpr int BW = W >= 4 ? W / 4 : 1, BH = H >= 4 ? H / 4 : 1;
       const bool run = valid && s_nnz[t] > 1;
       if (run)
@@ -502,13 +536,13 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
           bool any = false;
 #pragma unroll
           for (int i = 0; i < 16; i++) any |= D[(sy * 4 + (i >> 2)) * PA + sx * 4 + (i & 3)] != 0;
-          if (any) atomicMax(&s_last[t], subblock_scan_index(0, BW, BH, sx, sy));
+          if (any) atomicMax(&s_last[t], subblock_scan_index(scan, BW, BH, sx, sy));
         }
       __syncthreads();
       if (run)
         for (int sb = ti; sb < BW * BH; sb += TT) {
           const int sx = sb % BW, sy = sb / BW;
-          sign_hide_subblock(0, subblock_scan_index(0, BW, BH, sx, sy) == s_last[t], C + sy * 4 * PA + sx * 4, PA,
+          sign_hide_subblock(scan, subblock_scan_index(scan, BW, BH, sx, sy) == s_last[t], C + sy * 4 * PA + sx * 4, PA,
                              A + sy * 4 * PA + sx * 4, PA, D + sy * 4 * PA + sx * 4, PA);
         }
       __syncthreads();
@@ -546,10 +580,20 @@ tq_kernel(xvcb200_cu *__restrict__ cus, const int *__restrict__ tu_list, int n_t
       C[y * PA + x] = dequant_one(D[y * PA + x], dq);
     }
   __syncthreads();
-  // inverse: columns (N = H, lines = W) into B[x][j]; rows (N = W, lines = H) into A[y][x]
-  if (valid && cbf && ti < T2) inv_line<H>(C + (ti % W), PA, ti / W, B + (ti % W) * PB, 7 + 2, (ti % W) >= 32);
+  if (W * H <= 16 && tskip) {
+    // InverseTransform::TransformSkip (transform.cc:184-215)
+    const int odd = (LW + LH) & 1, sh = transform_shift(LW, LH, bd) + (odd ? 7 : 0), scale = odd ? 181 : 1;
+    if (valid && cbf)
+      for (int e = ti; e < W * H; e += TT) {
+        const int y = e / W, x = e % W, v = (int)C[y * PA + x] * scale;
+        A[y * PA + x] = (int16_t)(sh > 0 ? (v + (1 << (sh - 1))) >> sh : (int)((unsigned)v << -sh));
+      }
+  } else if (valid && cbf && ti < T2) {
+    // inverse: columns (N = H, lines = W) into B[x][j]; rows (N = W, lines = H) into A[y][x]
+    inv_line<H>(C + (ti % W), PA, ti / W, B + (ti % W) * PB, 7 + hp, (ti % W) >= 32, off_ver);
+  }
   __syncthreads();
-  if (valid && cbf && ti < T1) inv_line<W>(B + (ti % H), PB, ti / H, A + (ti % H) * PA, 20 - bd + 2, false);
+  if (!tskip && valid && cbf && ti < T1) inv_line<W>(B + (ti % H), PB, ti / H, A + (ti % H) * PA, 20 - bd + hp, false, off_hor);
   __syncthreads();
 
   // reconstruct (SampleBuffer::AddClip, sample_buffer.h:72-87; cbf == 0: copy of the prediction)

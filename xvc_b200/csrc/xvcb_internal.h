@@ -132,6 +132,7 @@ cudaError_t launch_block_dequant(cudaStream_t s, int w, int h, int bitdepth, int
 struct TqParams {
   int bitdepth, intra_picture, table, off_u, off_v;
   int decode_only;        // 1: dequant + inverse + reconstruct from levels (CuDecoder::DecompressComponent)
+  const xvcb200_tu_mode *modes;   // device, per CU (xvcb200_set_tu_modes), or nullptr
 };
 
 // me.cu

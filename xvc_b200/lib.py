@@ -34,7 +34,7 @@ EXPORTS = [
     "xvcb200_ctx_create", "xvcb200_ctx_destroy", "xvcb200_ctx_set_stream", "xvcb200_stream", "xvcb200_sync",
     "xvcb200_ctx_error_string", "xvcb200_get_geometry", "xvcb200_slot_ptr", "xvcb200_slot_region",
     "xvcb200_upload_picture", "xvcb200_download_picture", "xvcb200_download_coeff", "xvcb200_upload_coeff",
-    "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus", "xvcb200_set_mv_predictors",
+    "xvcb200_download_padded", "xvcb200_pad_border", "xvcb200_set_cus", "xvcb200_get_cus", "xvcb200_set_mv_predictors", "xvcb200_set_tu_modes",
     "xvcb200_upload_picture_async", "xvcb200_download_picture_async", "xvcb200_download_coeff_async",
     "xvcb200_get_cus_async", "xvcb200_sync_copies", "xvcb200_wait_download",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_motion_compensate_lic", "xvcb200_tq_reconstruct",
@@ -120,6 +120,7 @@ def load():
     L.xvcb200_set_cus.argtypes = [c_void_p, c_void_p, c_int]
     L.xvcb200_get_cus.argtypes = [c_void_p, c_void_p, c_int]
     L.xvcb200_set_mv_predictors.argtypes = [c_void_p, c_void_p, c_int]
+    L.xvcb200_set_tu_modes.argtypes = [c_void_p, c_void_p]
     L.xvcb200_me_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
     L.xvcb200_full_search.argtypes = [c_void_p, c_int, c_void_p, c_int, c_double, c_void_p]
     L.xvcb200_motion_compensate.argtypes = [c_void_p, c_void_p, c_int]
@@ -435,6 +436,13 @@ class Context:
         cus = np.ascontiguousarray(cus, dtype=abi.cu_dtype)
         self._ok(self.L.xvcb200_set_cus(self.h, abi.ptr(cus), len(cus)))
         self.n_cus = len(cus)
+
+    def set_tu_modes(self, modes):
+        """modes: abi.tu_mode_dtype [n_cus] or None to drop them; after set_cus."""
+        if modes is not None:
+            modes = np.ascontiguousarray(modes, dtype=abi.tu_mode_dtype)
+            assert len(modes) == self.n_cus
+        self._ok(self.L.xvcb200_set_tu_modes(self.h, abi.ptr(modes)))
 
     def set_mv_predictors(self, mvp):
         """mvp: int32 [n_cus][columns][2] (1/16 pel) or None to drop them; after set_cus."""
