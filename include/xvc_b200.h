@@ -391,6 +391,26 @@ int xvcb200_deblock_picture_ex(xvcb200_ctx *ctx, int rec_slot, int pic_type, int
                                int chroma_offset_table, int chroma_offset_u, int chroma_offset_v,
                                const int64_t ref_poc[2][5]);
 
+/* The two cases the CU array alone does not describe (deblocking_filter.cc:56-77, 88-91, 166-176):
+ *   affine / n_affine            CUs coded with affine motion (entries as for xvcb200_motion_compensate_affine):
+ *                                the boundary strength compares the vectors at the CU CORNERS nearest to the
+ *                                edge segment (up-left / up-right / down-left control points, down-right =
+ *                                up-right + down-left - up-left; CodingUnit::SetMv(MotionVector3), coding_unit.h:251-257)
+ *   chroma_cus / n_chroma_cus    the SECONDARY CU tree of an intra picture (PictureData::HasSecondaryCuTree): leaf CUs
+ *                                of the chroma tree in luma units (x, y, w, h, qp, flags |= XVCB200_CU_INTRA); chroma
+ *                                edges are then taken from this tree on an 8-sample luma grid (four chroma lines
+ *                                per segment) and the primary tree filters luma only
+ * Either pointer may be NULL (count 0).  HOST arrays, copied before the call returns. */
+typedef struct {
+  const xvcb200_affine_cu *affine;
+  int32_t n_affine;
+  const xvcb200_cu *chroma_cus;
+  int32_t n_chroma_cus;
+} xvcb200_deblock_ext;
+int xvcb200_deblock_picture_ext(xvcb200_ctx *ctx, int rec_slot, int pic_type, int beta_offset, int tc_offset,
+                                int chroma_offset_table, int chroma_offset_u, int chroma_offset_v,
+                                const int64_t ref_poc[2][5], const xvcb200_deblock_ext *ext);
+
 /* One band of the picture for CTB-row sharding across GPUs.  pass_mask: 1 = vertical edges of
  * rows [y_begin, y_end), 2 = horizontal edges whose q side lies in [y_begin, y_end) (the edge
  * ON y_begin belongs to this band and reads/writes up to 4/3 rows above it: the caller

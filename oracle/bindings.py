@@ -360,6 +360,7 @@ class Ref:
         L.xref_session_get_rec_padded.argtypes = [c_void_p, c_int, c_void_p]
         L.xref_session_set_cus.argtypes = [c_void_p, c_void_p, c_int]
         L.xref_session_get_cus.argtypes = [c_void_p, c_void_p, c_int]
+        L.xref_deblock_picture_ext.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int]
         L.xref_session_set_tu_modes.argtypes = [c_void_p, c_void_p, c_void_p, c_int]
         L.xref_session_scan_orders.argtypes = [c_void_p, c_void_p]
         L.xref_encode_picture_mvp.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
@@ -605,6 +606,16 @@ class RefSession:
 
     def deblock_picture(self, beta_offset=0, tc_offset=0):
         self.L.xref_deblock_picture(self.h, beta_offset, tc_offset)
+
+    def deblock_picture_ext(self, beta_offset=0, tc_offset=0, affine=None, chroma_cus=None):
+        """DeblockPicture with affine CUs (abi.affine_cu_dtype) and / or the secondary CU tree (abi.cu_dtype) of an intra picture."""
+        if affine is not None:
+            affine = np.ascontiguousarray(affine, dtype=abi.affine_cu_dtype)
+        if chroma_cus is not None:
+            chroma_cus = np.ascontiguousarray(chroma_cus, dtype=abi.cu_dtype)
+            assert self.L.xref_session_has_secondary_tree(self.h), "the session's picture has no secondary CU tree (not an intra picture)"
+        self.L.xref_deblock_picture_ext(self.h, beta_offset, tc_offset, abi.ptr(affine), 0 if affine is None else len(affine),
+                                        abi.ptr(chroma_cus), 0 if chroma_cus is None else len(chroma_cus))
 
     def intra_scan(self, cus, comp=0, want_pred=True):
         """CUs in coding order -> (jobs, ref_samples, ref_filtered, predictions per CU [67][h][w], satd [n][67])."""

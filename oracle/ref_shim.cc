@@ -828,6 +828,42 @@ void xref_deblock_picture(xref_session *s, int beta_offset, int tc_offset) {
   f.DeblockPicture();
 }
 
+// DeblockPicture with the two things the CU descriptors alone do not carry: affine CUs (corner vectors,
+// deblocking_filter.cc:166-176) and the secondary CU tree of an intra picture (:65-68, 88-91).  The affine
+// CUs keep SetUseAffine / SetMv(MotionVector3) for the duration of the call.
+void xref_deblock_picture_ext(xref_session *s, int beta_offset, int tc_offset, const xvcb200_affine_cu *aff, int n_aff,
+                              const xvcb200_cu *chroma_cus, int n_chroma) {
+  EnsureInit(s);
+  for (int i = 0; i < n_aff; i++) {
+    CodingUnit *cu = s->cus[aff[i].cu];
+    cu->SetUseAffine(true);
+    for (int l = 0; l < 2; l++) {
+      if (cu->GetRefIdx(static_cast<RefPicList>(l)) < 0) continue;
+      MotionVector3 mv;
+      for (int k = 0; k < 3; k++) mv[k] = MotionVector(aff[i].mv[l][k][0], aff[i].mv[l][k][1]);
+      cu->SetMv(mv, static_cast<RefPicList>(l));
+    }
+  }
+  if (n_chroma > 0 && s->pic_data->HasSecondaryCuTree())
+    for (int i = 0; i < n_chroma; i++) {
+      const xvcb200_cu &d = chroma_cus[i];
+      CodingUnit *cu = s->pic_data->CreateCu(CuTree::Secondary, d.depth, d.x, d.y, d.w, d.h);
+      cu->SetPredMode(PredictionMode::kIntra);
+      cu->SetQp(d.qp);
+      s->pic_data->MarkUsedInPic(cu);
+    }
+  DeblockingFilter f(s->pic_data.get(), s->rec.get(), beta_offset, tc_offset);
+  f.DeblockPicture();
+  for (int i = 0; i < n_aff; i++) {
+    CodingUnit *cu = s->cus[aff[i].cu];
+    cu->SetUseAffine(false);
+    for (int l = 0; l < 2; l++)
+      if (cu->GetRefIdx(static_cast<RefPicList>(l)) >= 0)
+        cu->SetMv(MotionVector(aff[i].mv[l][0][0], aff[i].mv[l][0][1]), static_cast<RefPicList>(l));
+  }
+}
+int xref_session_has_secondary_tree(xref_session *s) { EnsureInit(s); return s->pic_data->HasSecondaryCuTree() ? 1 : 0; }
+
 void xref_pad_border_rec(xref_session *s) { s->rec->PadBorder(); }
 
 void xref_session_get_rec_padded(xref_session *s, int comp, uint16_t *out) {

@@ -433,6 +433,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int16_t *d_worig = nullptr;
   std::vector<CUtensorMap> luma_tmaps;         // per slot: [2 * slot + 0 / 1] = narrow / wide box over the padded luma plane (full search)
   xvcb200_tu_mode *d_tu_modes = nullptr; int tu_modes_cap = 0; bool tu_modes_set = false;   // xvcb200_set_tu_modes
+  int32_t *d_cu_map2 = nullptr;                // 4x4 CU map of the secondary (chroma) tree (xvcb200_deblock_picture_ext)
   int32_t *d_mvp = nullptr; int mvp_cap = 0;   // xvcb200_set_mv_predictors: [cu][column][2]
   int mvp_cols = 0;                            // 0: none given for the current CU array
   int32_t *h_mvp[2] = {nullptr, nullptr}; size_t h_mvp_cap[2] = {0, 0}; cudaEvent_t mvp_ev[2] = {nullptr, nullptr};   // page-locked staging, alternating
@@ -642,7 +643,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   for (int b = 0; b < 2; b++) { if (c->ex.h_mvp[b]) cudaFreeHost(c->ex.h_mvp[b]); if (c->ex.mvp_ev[b]) cudaEventDestroy(c->ex.mvp_ev[b]); }
-  cudaFree(c->ex.d_tu_modes); cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
+  cudaFree(c->ex.d_cu_map2); cudaFree(c->ex.d_tu_modes); cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < c->ex.n_side; i++) { cudaStreamDestroy(c->ex.side[i]); cudaEventDestroy(c->ex.side_ev[i]); }
@@ -1510,16 +1511,24 @@ int xvcb200_deblock_picture_ex(xvcb200_ctx *c, int rec_slot, int pic_type, int b
   return xvcb200_deblock_band(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, 3, 0, c->height);
 }
 static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
-                        int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready);
+                        int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready,
+                        const xvcb200_deblock_ext *ext = nullptr);
+int xvcb200_deblock_picture_ext(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table,
+                                int off_u, int off_v, const int64_t ref_poc[2][5], const xvcb200_deblock_ext *ext) {
+  xvcb::DevGuard dev_guard(c);
+  if (!c) return XVCB200_INVALID_ARGUMENT;
+  return deblock_impl(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, 3, 0, c->height, false, ext);
+}
 int xvcb200_deblock_band(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
                          int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end) {
   xvcb::DevGuard dev_guard(c);
   return deblock_impl(c, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v, ref_poc, pass_mask, y_begin, y_end, false);
 }
 static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_offset, int tc_offset, int table, int off_u,
-                        int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready) {
+                        int off_v, const int64_t ref_poc[2][5], int pass_mask, int y_begin, int y_end, bool map_ready,
+                        const xvcb200_deblock_ext *ext) {
   xvcb::DevGuard dev_guard(c);
-  if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 1 || y_begin < 0 || y_end > c->height ||
+  if (!slot_ok(c, rec_slot) || !ref_poc || pic_type < 0 || pic_type > 2 || y_begin < 0 || y_end > c->height ||
       y_begin > y_end || (y_begin & 3) || (y_end & 3) || (pass_mask & ~3))
     return XVCB200_INVALID_ARGUMENT;
   join_upload_slot(full(c), rec_slot);
@@ -1529,6 +1538,39 @@ static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_off
   p.table = table; p.off_u = off_u; p.off_v = off_v;
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) p.ref_poc[l][i] = ref_poc[l][i];
+  if (ext && ((ext->n_affine > 0 && ext->affine) || (ext->n_chroma_cus > 0 && ext->chroma_cus))) {
+    CtxFull *f = full(c);
+    const int na = ext->affine ? ext->n_affine : 0, nc = ext->chroma_cus ? ext->n_chroma_cus : 0;
+    if (na < 0 || nc < 0) return XVCB200_INVALID_ARGUMENT;
+    for (int i = 0; i < na; i++)
+      if (ext->affine[i].cu < 0 || ext->affine[i].cu >= c->n_cus) return XVCB200_INVALID_ARGUMENT;
+    for (int i = 0; i < nc; i++) {
+      const xvcb200_cu &u = ext->chroma_cus[i];
+      if (u.w < 4 || u.h < 4 || u.w > 64 || u.h > 64 || u.x < 0 || u.y < 0 || u.x + u.w > c->width || u.y + u.h > c->height || (u.x & 3) || (u.y & 3))
+        return XVCB200_INVALID_ARGUMENT;
+    }
+    // one staging image: [affine index per CU][affine entries][chroma CUs]
+    const size_t off_aff = (sizeof(int) * (size_t)(na ? c->n_cus : 0) + 15) & ~(size_t)15;
+    const size_t off_cus = (off_aff + sizeof(xvcb200_affine_cu) * (size_t)na + 15) & ~(size_t)15;
+    const size_t bytes = off_cus + sizeof(xvcb200_cu) * (size_t)nc;
+    std::vector<uint8_t> img(bytes, 0);
+    if (na) {
+      int *index = reinterpret_cast<int *>(img.data());
+      for (int i = 0; i < c->n_cus; i++) index[i] = -1;
+      for (int i = 0; i < na; i++) index[ext->affine[i].cu] = i;
+      memcpy(img.data() + off_aff, ext->affine, sizeof(xvcb200_affine_cu) * (size_t)na);
+    }
+    if (nc) memcpy(img.data() + off_cus, ext->chroma_cus, sizeof(xvcb200_cu) * (size_t)nc);
+    uint8_t *d = static_cast<uint8_t *>(c->scratch(bytes));
+    if (!d) return c->status;
+    if (nc && !f->ex.d_cu_map2 &&
+        !c->check(cudaMalloc(&f->ex.d_cu_map2, sizeof(int32_t) * (size_t)c->map_w * c->map_h), "cudaMalloc(chroma map)"))
+      return c->status;
+    // pageable source: the runtime stages it before the call returns
+    if (!c->check(cudaMemcpyAsync(d, img.data(), bytes, cudaMemcpyHostToDevice, c->stream), "deblock ext")) return c->status;
+    if (na) { p.aff_index = reinterpret_cast<const int *>(d); p.aff = reinterpret_cast<const xvcb200_affine_cu *>(d + off_aff); }
+    if (nc) { p.chroma_cus = reinterpret_cast<const xvcb200_cu *>(d + off_cus); p.n_chroma_cus = nc; p.chroma_map = f->ex.d_cu_map2; }
+  }
   c->check(launch_deblock(c->stream, c->d_cus, c->n_cus, p, pic3(c, rec_slot), c->d_cu_map, c->d_edge_bs[0], c->d_edge_bs[1],
                           c->map_w, c->map_h, pass_mask, y_begin, y_end, map_ready), "deblock");
   return c->status;

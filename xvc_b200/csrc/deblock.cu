@@ -47,26 +47,51 @@ __device__ __forceinline__ bool mv_far(const int32_t a[2], const int32_t b[2]) {
   return abs(a[0] - b[0]) >= 16 || abs(a[1] - b[1]) >= 16;               // one integer sample at 1/16 pel
 }
 
-// DeblockingFilter::GetBoundaryStrength, deblocking_filter.cc:154-241.  Without affine motion the
-// four corner MVs of a CU are equal, so the corner selection (:166-176) reads the same value.
-__device__ int boundary_strength(const xvcb200_cu &p, const xvcb200_cu &q, int pic_type, const DbRefPoc &rp) {
+// The vector of a CU at one of its corners (CodingUnit::GetMv(list, corner), coding_unit.h:245-257): the control
+// points of an affine CU (up-left, up-right, down-left; down-right = up-right + down-left - up-left), else the
+// CU's one vector.  corner: 0 up-left, 1 up-right, 2 down-left, 3 down-right (MvCorner, cu_types.h:214-220).
+struct DbAffine { const int *index; const xvcb200_affine_cu *cus; };
+__device__ __forceinline__ void corner_mv(const xvcb200_cu &cu, int ci, int list, int corner, const DbAffine &af, int32_t out[2]) {
+  const int a = af.index ? af.index[ci] : -1;
+  if (a < 0) { out[0] = cu.mv[list][0]; out[1] = cu.mv[list][1]; return; }
+  const int32_t (*m)[2] = af.cus[a].mv[list];
+  if (corner < 3) { out[0] = m[corner][0]; out[1] = m[corner][1]; }
+  else { out[0] = m[1][0] + m[2][0] - m[0][0]; out[1] = m[1][1] + m[2][1] - m[0][1]; }
+}
+
+// DeblockingFilter::GetBoundaryStrength, deblocking_filter.cc:154-241, for the edge segment whose q side starts at
+// luma position (pos_x, pos_y); dir 0: vertical edge (p left of q), 1: horizontal edge (p above q).  The corner
+// whose vector is compared depends on which half of the CU the segment lies in (:166-176).
+__device__ int boundary_strength(const xvcb200_cu &p, const xvcb200_cu &q, int ip, int iq, int pos_x, int pos_y, int dir,
+                                 int pic_type, const DbRefPoc &rp, const DbAffine &af) {
   if ((p.flags | q.flags) & XVCB200_CU_INTRA) return 2;
   if ((p.flags | q.flags) & XVCB200_CU_CBF_Y) return 1;
+  int corner_p, corner_q;
+  if (dir == 0) {
+    corner_p = (pos_y - p.y) < (p.h >> 1) ? 1 : 3;
+    corner_q = (pos_y - q.y) < (q.h >> 1) ? 0 : 2;
+  } else {
+    corner_p = (pos_x - p.x) < (p.w >> 1) ? 2 : 3;
+    corner_q = (pos_x - q.x) < (q.w >> 1) ? 0 : 1;
+  }
+  int32_t mp0[2], mp1[2], mq0[2], mq1[2];
+  corner_mv(p, ip, 0, corner_p, af, mp0); corner_mv(q, iq, 0, corner_q, af, mq0);
   if (pic_type == 0) {
+    corner_mv(p, ip, 1, corner_p, af, mp1); corner_mv(q, iq, 1, corner_q, af, mq1);
     const long long p0 = ref_poc_of(p, 0, rp), p1 = ref_poc_of(p, 1, rp), q0 = ref_poc_of(q, 0, rp), q1 = ref_poc_of(q, 1, rp);
     if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
-    const bool straight = mv_far(p.mv[0], q.mv[0]) || mv_far(p.mv[1], q.mv[1]);
-    const bool crossed = mv_far(p.mv[0], q.mv[1]) || mv_far(p.mv[1], q.mv[0]);
+    const bool straight = mv_far(mp0, mq0) || mv_far(mp1, mq1);
+    const bool crossed = mv_far(mp0, mq1) || mv_far(mp1, mq0);
     if (p0 != p1) return (p0 == q0) ? straight : crossed;
     return straight && crossed;
   }
   if (p.ref_idx[0] != q.ref_idx[0]) return 1;
-  return mv_far(p.mv[0], q.mv[0]);
+  return mv_far(mp0, mq0);
 }
 
 // boundary strength of the left (bs_v) and top (bs_h) edge of every 4x4 block; 0 = no edge
 __global__ void edge_bs_kernel(const xvcb200_cu *__restrict__ cus, const int32_t *__restrict__ map, int map_w, int map_h,
-                               int pic_type, const __grid_constant__ DbRefPoc rp, uint8_t *__restrict__ bs_v,
+                               int pic_type, const __grid_constant__ DbRefPoc rp, DbAffine af, uint8_t *__restrict__ bs_v,
                                uint8_t *__restrict__ bs_h) {
   const int cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= map_w * map_h) return;
@@ -77,11 +102,11 @@ __global__ void edge_bs_kernel(const xvcb200_cu *__restrict__ cus, const int32_t
     const xvcb200_cu q = cus[iq];
     if (cx > 0) {
       const int ip = map[cell - 1];
-      if (ip >= 0 && ip != iq) v = (uint8_t)boundary_strength(cus[ip], q, pic_type, rp);
+      if (ip >= 0 && ip != iq) v = (uint8_t)boundary_strength(cus[ip], q, ip, iq, cx * 4, cy * 4, 0, pic_type, rp, af);
     }
     if (cy > 0) {
       const int ip = map[cell - map_w];
-      if (ip >= 0 && ip != iq) h = (uint8_t)boundary_strength(cus[ip], q, pic_type, rp);
+      if (ip >= 0 && ip != iq) h = (uint8_t)boundary_strength(cus[ip], q, ip, iq, cx * 4, cy * 4, 1, pic_type, rp, af);
     }
   }
   bs_v[cell] = v;
@@ -147,12 +172,14 @@ __device__ void luma_segment(Sample *s, int across, int along, int bitdepth, int
   }
 }
 
-// FilterEdgeChroma + FilterChroma<2> (:403-450): 2 chroma lines per 4-sample luma segment in 4:2:0
+// FilterEdgeChroma + FilterChroma<N> (:403-450): N = 2 chroma lines per 4-sample luma segment in 4:2:0, 4 per
+// 8-sample segment of the secondary tree
+template <int NLINES>
 __device__ void chroma_segment(Sample *s, int across, int along, int bitdepth, int qp, int tc_off) {
   const int tc = c_tc[min(clip3i(qp + tc_off + 2, 0, 54), 53)] << (bitdepth - 8);   // index clip as in luma
   const int maxv = (1 << bitdepth) - 1;
 #pragma unroll
-  for (int l = 0; l < 2; l++) {
+  for (int l = 0; l < NLINES; l++) {
     const int p1 = s[l * along - 2 * across], p0 = s[l * along - across], q0 = s[l * along], q1 = s[l * along + across];
     const int delta = clip3i((((q0 - p0) * 4) + p1 - q1 + 4) >> 3, -tc, tc);
     s[l * along - across] = (Sample)clip3i(p0 + delta, 0, maxv);
@@ -178,8 +205,9 @@ __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restri
   const PlaneView ly = rec.p[0];
   const int across = DIR == 0 ? 1 : ly.pitch, along = DIR == 0 ? ly.pitch : 1;
 
-  // chroma: bs == 2 edges whose chroma coordinate is a multiple of 8 (:131-149)
-  if (bs0 == 2 && ((DIR == 0 ? cx : cy) & 3) == 0) {
+  // chroma: bs == 2 edges whose chroma coordinate is a multiple of 8 (:131-149); with a secondary CU tree the
+  // chroma edges are that tree's (:88-91)
+  if (bs0 == 2 && ((DIR == 0 ? cx : cy) & 3) == 0 && !prm.chroma_cus) {
     const int iq = map[cell], ip = map[cell - step];
     const int qpp = chroma_qp_raw(cus[ip].qp, prm.off_u, prm.table, c_db_chroma_scale);   // cu.GetQp(kU) for both planes (:127)
     const int qpq = chroma_qp_raw(cus[iq].qp, prm.off_u, prm.table, c_db_chroma_scale);
@@ -187,7 +215,7 @@ __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restri
     for (int c = 1; c < 3; c++) {
       const PlaneView pc = rec.p[c];
       Sample *s = pc.base + (cy * 2) * pc.pitch + cx * 2;
-      chroma_segment(s, DIR == 0 ? 1 : pc.pitch, DIR == 0 ? pc.pitch : 1, prm.bitdepth, cqp, prm.tc_offset);
+      chroma_segment<2>(s, DIR == 0 ? 1 : pc.pitch, DIR == 0 ? pc.pitch : 1, prm.bitdepth, cqp, prm.tc_offset);
     }
   }
 
@@ -202,6 +230,36 @@ __global__ void __launch_bounds__(128) deblock_kernel(const xvcb200_cu *__restri
     const int ex = DIR == 0 ? k : cx, ey = DIR == 0 ? cy : k;
     Sample *s = ly.base + (ey * 4) * ly.pitch + ex * 4;
     luma_segment(s, across, along, prm.bitdepth, bs, qp, prm.beta_offset, prm.tc_offset);
+  }
+}
+
+// Chroma edges of the secondary CU tree (intra pictures, deblocking_filter.cc:65-68, 88-91): DeblockCtu walks that
+// tree on an 8-sample luma grid; an edge between two of its CUs with boundary strength 2 is filtered where its
+// chroma coordinate is a multiple of 8, four chroma lines per segment.  A thread per 8 x 8 luma cell.
+template <int DIR>
+__global__ void __launch_bounds__(128) deblock_chroma_tree_kernel(const xvcb200_cu *__restrict__ cus2, const int32_t *__restrict__ map2,
+                                                                  int map_w, int map_h, DeblockParams prm, Pic3 rec) {
+  const int gw = map_w >> 1, gh = map_h >> 1;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= gw * gh) return;
+  const int cx = (g % gw) * 2, cy = (g / gw) * 2;            // 4x4 cell of the luma position (8 gx, 8 gy)
+  if (((DIR == 0 ? cx : cy) & 3) != 0) return;                // chroma coordinate (4 cx / 2) multiple of 8
+  if ((DIR == 0 ? cx : cy) == 0) return;
+  const int cell = cy * map_w + cx, step = DIR == 0 ? 1 : map_w;
+  const int iq = map2[cell], ip = map2[cell - step];
+  if (iq < 0 || ip < 0 || ip == iq) return;
+  DbRefPoc rp;
+  for (int l = 0; l < 2; l++)
+    for (int i = 0; i < 5; i++) rp.poc[l][i] = prm.ref_poc[l][i];
+  const DbAffine none = {nullptr, nullptr};
+  if (boundary_strength(cus2[ip], cus2[iq], ip, iq, cx * 4, cy * 4, DIR, prm.pic_type, rp, none) != 2) return;
+  const int qpp = chroma_qp_raw(cus2[ip].qp, prm.off_u, prm.table, c_db_chroma_scale);
+  const int qpq = chroma_qp_raw(cus2[iq].qp, prm.off_u, prm.table, c_db_chroma_scale);
+  const int cqp = (qpp + qpq + 1) >> 1;
+  for (int c = 1; c < 3; c++) {
+    const PlaneView pc = rec.p[c];
+    Sample *s = pc.base + (cy * 2) * pc.pitch + cx * 2;
+    chroma_segment<4>(s, DIR == 0 ? 1 : pc.pitch, DIR == 0 ? pc.pitch : 1, prm.bitdepth, cqp, prm.tc_offset);
   }
 }
 
@@ -232,14 +290,30 @@ cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const
   for (int l = 0; l < 2; l++)
     for (int i = 0; i < 5; i++) rp.poc[l][i] = p.ref_poc[l][i];
   g_launch_count++;
-  edge_bs_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, map_w, map_h, p.pic_type, rp, d_bs_v, d_bs_h);
+  const DbAffine af = {p.aff_index, p.aff};
+  edge_bs_kernel<<<(cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, map_w, map_h, p.pic_type, rp, af, d_bs_v, d_bs_h);
+  const bool tree2 = p.chroma_cus && p.n_chroma_cus > 0 && p.chroma_map;
+  const int cells2 = (map_w >> 1) * (map_h >> 1);
+  if (tree2) {
+    cudaError_t e = launch_cu_map(s, p.chroma_cus, p.n_chroma_cus, p.chroma_map, map_w, map_h);
+    if (e != cudaSuccess) return e;
+  }
+  // luma and chroma touch different planes; within chroma the vertical pass precedes the horizontal one (:62-76)
   if (pass_mask & 1) {
     g_launch_count++;
     deblock_kernel<0><<<(band_cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_v, map_w, map_h, p, rec, cy0, cy1);
+    if (tree2) {
+      g_launch_count++;
+      deblock_chroma_tree_kernel<0><<<(cells2 + 127) / 128, 128, 0, s>>>(p.chroma_cus, p.chroma_map, map_w, map_h, p, rec);
+    }
   }
   if (pass_mask & 2) {
     g_launch_count++;
     deblock_kernel<1><<<(band_cells + 127) / 128, 128, 0, s>>>(d_cus, d_map, d_bs_h, map_w, map_h, p, rec, cy0, cy1);
+    if (tree2) {
+      g_launch_count++;
+      deblock_chroma_tree_kernel<1><<<(cells2 + 127) / 128, 128, 0, s>>>(p.chroma_cus, p.chroma_map, map_w, map_h, p, rec);
+    }
   }
   return cudaGetLastError();
 }

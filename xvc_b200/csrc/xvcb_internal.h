@@ -206,6 +206,13 @@ cudaError_t launch_plane_pack(cudaStream_t s, Pic3 pic, uint16_t *tight, int to_
 struct DeblockParams {
   int bitdepth, pic_type, beta_offset, tc_offset, table, off_u, off_v;
   long long ref_poc[2][5];
+  // CUs with affine motion: aff_index[cu] = entry of `aff` or -1 (nullptr: none); their corner vectors enter the boundary strength
+  const int *aff_index = nullptr;
+  const xvcb200_affine_cu *aff = nullptr;
+  // secondary (chroma) CU tree of an intra picture: chroma edges come from it, not from the primary tree
+  const xvcb200_cu *chroma_cus = nullptr;
+  int n_chroma_cus = 0;
+  int32_t *chroma_map = nullptr;
 };
 cudaError_t launch_deblock(cudaStream_t s, const xvcb200_cu *d_cus, int n, const DeblockParams &p, Pic3 rec,
                            int32_t *d_map, uint8_t *d_bs_v, uint8_t *d_bs_h, int map_w, int map_h, int pass_mask,

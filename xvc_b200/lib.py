@@ -38,7 +38,7 @@ EXPORTS = [
     "xvcb200_upload_picture_async", "xvcb200_download_picture_async", "xvcb200_download_coeff_async",
     "xvcb200_get_cus_async", "xvcb200_sync_copies", "xvcb200_wait_download",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_motion_compensate_lic", "xvcb200_tq_reconstruct",
-    "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_band",
+    "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_picture_ext", "xvcb200_deblock_band",
     "xvcb200_encode_picture", "xvcb200_set_profiling", "xvcb200_get_stage_times",
     "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan", "xvcb200_intra_lm_chroma",
     "xvcb200_ipc_export", "xvcb200_ipc_open_peer", "xvcb200_push_slot", "xvcb200_wait_pushes",
@@ -130,6 +130,7 @@ def load():
     L.xvcb200_dequant_reconstruct.argtypes = [c_void_p] + [c_int] * 6
     L.xvcb200_deblock_picture.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     L.xvcb200_deblock_picture_ex.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p]
+    L.xvcb200_deblock_picture_ext.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p, c_void_p]
     L.xvcb200_deblock_band.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 3
     L.xvcb200_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.xvcb200_set_profiling.argtypes = [c_void_p, c_int]
@@ -513,6 +514,22 @@ class Context:
             poc[l, i] = p
         self._ok(self.L.xvcb200_deblock_picture_ex(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
                                                    abi.ptr(poc)))
+
+    def deblock_picture_ext(self, rec_slot, pic_type, ref_poc, affine=None, chroma_cus=None, beta_offset=0, tc_offset=0, table=1,
+                            off_u=0, off_v=0):
+        """Deblocking with affine CUs (abi.affine_cu_dtype) and / or the secondary CU tree of an intra picture (abi.cu_dtype)."""
+        poc = np.zeros((2, 5), dtype=np.int64)
+        for (l, i), p in ref_poc.items():
+            poc[l, i] = p
+        ext = np.zeros(4, dtype=np.uint64)        # xvcb200_deblock_ext: pointer, int32 (+ padding), pointer, int32 (+ padding)
+        if affine is not None:
+            affine = np.ascontiguousarray(affine, dtype=abi.affine_cu_dtype)
+            ext[0], ext[1] = affine.ctypes.data, len(affine)
+        if chroma_cus is not None:
+            chroma_cus = np.ascontiguousarray(chroma_cus, dtype=abi.cu_dtype)
+            ext[2], ext[3] = chroma_cus.ctypes.data, len(chroma_cus)
+        self._ok(self.L.xvcb200_deblock_picture_ext(self.h, rec_slot, pic_type, beta_offset, tc_offset, table, off_u, off_v,
+                                                    abi.ptr(poc), abi.ptr(ext)))
 
     def deblock_band(self, rec_slot, pic_type, ref_poc, pass_mask, y_begin, y_end, beta_offset=0, tc_offset=0, table=1,
                      off_u=0, off_v=0):
