@@ -528,6 +528,29 @@ int xvcb200_set_mv_predictors(xvcb200_ctx *ctx, const int32_t *mvp, int n_cols);
 int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *params,
                            xvcb200_me_result *me_results, xvcb200_tu_result *tu_results);
 
+/* GPU pre-analysis: the CU partition of an inter picture.  The reference decides the
+ * partition inside CuEncoder::CompressCu's serial RD recursion (cu_encoder.cc:123-273); this entry decides it
+ * from motion-compensated distortion for all CTUs at once: SAD of every 8 x 8 block at every full-pel vector
+ * within +-8 of `center` on the luma of ref_slot, summed bottom-up over the quad tree ("SAD tree"), and per
+ * node the cheapest of: one CU, two horizontal / vertical halves (each with its own vector), four quadrants
+ * -- cost = SAD + ((lambda * bits) >> 16) with exp-Golomb vector bits against `center` plus header_bits_cu per
+ * CU and header_bits_split per split decision (0: 8 / 1).  Output: the leaf CUs in coding order (CTU raster,
+ * quadrants in z order; depth = quad depth, qp, mv[0] = mv[1] = the winning vector in 1/16 pel: the
+ * predictor for the search of xvcb200_encode_picture) and the split flags of all CTUs in raster order,
+ * pre-order, one byte per node: 0 leaf, 1 quad, 2 horizontal, 3 vertical (SplitType, cu_types.h:37-42; the
+ * two children of a binary split are leaves; splits forced by the picture edge are implicit and not listed).
+ * The trees are ones xvc's syntax can carry.  Synchronous; HOST output arrays with capacities (a 64 x 64 CTU
+ * yields at most 64 CUs and 128 flags).  tests/partition_model.py states the same rule in numpy. */
+typedef struct {
+  int32_t orig_slot, ref_slot;
+  int32_t center[2];                 /* picture-level predictor, 1/16 pel (rounded down to full samples) */
+  double lambda_sqrt;
+  int32_t qp;                        /* written into every CU */
+  int32_t header_bits_cu, header_bits_split;
+} xvcb200_partition_params;
+int xvcb200_decide_partition(xvcb200_ctx *ctx, const xvcb200_partition_params *params, xvcb200_cu *cus_out, int cus_cap,
+                             int *n_cus, uint8_t *splits_out, int splits_cap, int *n_splits);
+
 /* Optional per-stage device timing of xvcb200_encode_picture (CUDA events on the context
  * stream): ms[0..6] = job set-up, full-pel TZ search, sub-pel search + list decision, motion
  * compensation, T/Q/recon, deblocking, padding -- of the last call. */

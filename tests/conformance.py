@@ -18,7 +18,19 @@ from xvc_b200 import abi, workload
 XVCDEC = os.path.join(os.path.dirname(bindings.REF_SO), "xvcdec")
 
 
-def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=64, n_inter=1):
+def gpu_partition(width, height, bd, cur, ref_rec, lam, qp):
+    """(cus, splits) from xvcb200_decide_partition (the GPU pre-analysis) for one inter picture."""
+    from xvc_b200 import lib
+    ctx = lib.Context(width, height, bd, num_slots=2)
+    ctx.upload(0, cur)
+    ctx.upload(1, ref_rec)
+    ctx.pad_border(1)
+    out = ctx.decide_partition(0, 1, float(np.sqrt(lam)), qp)
+    ctx.close()
+    return out
+
+
+def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=64, n_inter=1, partition="seeded"):
     """backend(cur, ref_rec, cus, prm, info) -> (cus_out, levels, rec planes incl. deblocking).
     n_inter inter pictures in a low-delay chain: picture k references picture k-1, i.e. from the second
     inter picture on the reference picture is itself a reconstruction made by the backend."""
@@ -36,7 +48,11 @@ def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=
             assert all(np.array_equal(a, b) for a, b in zip(ref_rec, recs[-1]))
         # With one reference picture the reference still signals a bi-predictive picture (both lists hold
         # the same POC): the search runs on list 0 only, the deblocking decisions follow the signalled type.
-        cus, splits = workload.make_partition_tree(width, height, seed=seed + poc, min_size=8, qp=info["qp"])
+        if partition == "gpu":
+            cus, splits = gpu_partition(width, height, bd, orig, ref_rec, info["lam"], info["qp"])
+            assert workload.check_partition(cus, width, height)
+        else:
+            cus, splits = workload.make_partition_tree(width, height, seed=seed + poc, min_size=8, qp=info["qp"])
         prm = common.picture_params(1, info["lam"], ranges=(search_range, search_range), pocs=(poc - 1, poc - 1),
                                     slots=dict(orig=0, ref0=1, ref1=-1, pred=2, rec=3, coeff=4), deblock=0, pad=0)
         prm["chroma_offset_table"], prm["chroma_offset_u"], prm["chroma_offset_v"] = info["chroma_table"], info["off_u"], info["off_v"]

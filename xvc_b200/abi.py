@@ -51,6 +51,9 @@ picture_params_dtype = np.dtype([
 
 tu_mode_dtype = np.dtype([("tx_ver", "u1"), ("tx_hor", "u1"), ("tskip", "u1"), ("scan", "u1", (3,)), ("reserved", "u1", (2,))], align=True)    # xvcb200_tu_mode
 
+partition_params_dtype = np.dtype([("orig_slot", "<i4"), ("ref_slot", "<i4"), ("center", "<i4", (2,)), ("lambda_sqrt", "<f8"), ("qp", "<i4"),
+                                   ("header_bits_cu", "<i4"), ("header_bits_split", "<i4")], align=True)    # xvcb200_partition_params
+
 plane_geom_dtype = np.dtype([
     ("width", "<i4", (3,)), ("height", "<i4", (3,)), ("pitch", "<i4", (3,)),
     ("margin_x", "<i4", (3,)), ("margin_y", "<i4", (3,)),
@@ -81,6 +84,7 @@ ABI_STRUCTS = {
     9: ("xvcb200_affine_cu", affine_cu_dtype),
     10: ("xvcb200_lic_cu", lic_cu_dtype),
     11: ("xvcb200_tu_mode", tu_mode_dtype),
+    12: ("xvcb200_partition_params", partition_params_dtype),
 }
 
 

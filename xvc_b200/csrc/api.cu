@@ -147,6 +147,7 @@ int xvcb200_abi_sizeof(int which) {
     case 9: return (int)sizeof(xvcb200_affine_cu);
     case 10: return (int)sizeof(xvcb200_lic_cu);
     case 11: return (int)sizeof(xvcb200_tu_mode);
+    case 12: return (int)sizeof(xvcb200_partition_params);
     default: return -1;
   }
 }
@@ -1574,6 +1575,46 @@ static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_off
   c->check(launch_deblock(c->stream, c->d_cus, c->n_cus, p, pic3(c, rec_slot), c->d_cu_map, c->d_edge_bs[0], c->d_edge_bs[1],
                           c->map_w, c->map_h, pass_mask, y_begin, y_end, map_ready), "deblock");
   return c->status;
+}
+
+int xvcb200_decide_partition(xvcb200_ctx *ctx, const xvcb200_partition_params *prm, xvcb200_cu *cus_out, int cus_cap, int *n_cus,
+                             uint8_t *splits_out, int splits_cap, int *n_splits) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || !prm || !cus_out || !n_cus || !splits_out || !n_splits || !slot_ok(ctx, prm->orig_slot) || !slot_ok(ctx, prm->ref_slot) ||
+      prm->header_bits_cu < 0 || prm->header_bits_split < 0 || prm->header_bits_cu > 255 || prm->header_bits_split > 255)
+    return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  const int n_ctus = ((c->width + 63) >> 6) * ((c->height + 63) >> 6);
+  const size_t b_cus = sizeof(xvcb200_cu) * 64 * (size_t)n_ctus, b_spl = 128 * (size_t)n_ctus, b_cnt = sizeof(int) * (size_t)n_ctus;
+  const size_t total = b_cus + b_spl + 2 * b_cnt;
+  uint8_t *d = static_cast<uint8_t *>(c->scratch(total));
+  uint8_t *h = static_cast<uint8_t *>(c->pinned(total));
+  if (!d || !h) return c->status;
+  join_upload_slot(c, prm->orig_slot);
+  join_upload_slot(c, prm->ref_slot);
+  const uint32_t lam = lambda_me_of(prm->lambda_sqrt);
+  const int bits_cu = prm->header_bits_cu ? prm->header_bits_cu : 8, bits_split = prm->header_bits_split ? prm->header_bits_split : 1;
+  xvcb200_cu *d_cus = reinterpret_cast<xvcb200_cu *>(d);
+  uint8_t *d_spl = d + b_cus;
+  int *d_ncu = reinterpret_cast<int *>(d + b_cus + b_spl), *d_nsp = d_ncu + n_ctus;
+  c->check(launch_partition(c->stream, c->plane(prm->orig_slot, 0), c->plane(prm->ref_slot, 0), prm->center[0], prm->center[1], lam,
+                            (int)(((unsigned long long)lam * bits_cu) >> 16), (int)(((unsigned long long)lam * bits_split) >> 16), prm->qp,
+                            d_cus, d_ncu, d_spl, d_nsp), "partition");
+  c->check(cudaMemcpyAsync(h, d, total, cudaMemcpyDeviceToHost, c->stream), "partition results");
+  const int st = xvcb200_sync(c);
+  if (st != XVCB200_OK) return st;
+  const xvcb200_cu *h_cus = reinterpret_cast<const xvcb200_cu *>(h);
+  const uint8_t *h_spl = h + b_cus;
+  const int *h_ncu = reinterpret_cast<const int *>(h + b_cus + b_spl), *h_nsp = h_ncu + n_ctus;
+  int nc = 0, ns = 0;
+  for (int t = 0; t < n_ctus; t++) {
+    if (nc + h_ncu[t] > cus_cap || ns + h_nsp[t] > splits_cap) return XVCB200_INVALID_ARGUMENT;
+    memcpy(cus_out + nc, h_cus + 64 * (size_t)t, sizeof(xvcb200_cu) * (size_t)h_ncu[t]);
+    memcpy(splits_out + ns, h_spl + 128 * (size_t)t, (size_t)h_nsp[t]);
+    nc += h_ncu[t]; ns += h_nsp[t];
+  }
+  *n_cus = nc; *n_splits = ns;
+  return XVCB200_OK;
 }
 
 // per-stage device times of the last xvcb200_encode_picture: ms[0..6] = make jobs, full-pel TZ

@@ -190,6 +190,10 @@ cudaError_t launch_full_search(cudaStream_t s, const xvcb200_cu *d_cus, const xv
                                int bitdepth, uint32_t lambda_me, PlaneView orig, const PlaneView *d_planes,
                                xvcb200_me_result *d_res);
 
+// partition.cu: per CTU 64 CUs / 128 split flags / counts
+cudaError_t launch_partition(cudaStream_t s, PlaneView orig, PlaneView ref, int cx16, int cy16, uint32_t lambda_me, int hdr_cu, int hdr_split,
+                             int qp, xvcb200_cu *d_cus, int *d_n_cus, uint8_t *d_splits, int *d_n_splits);
+
 // intra.cu
 cudaError_t launch_intra_ref(cudaStream_t s, int w, int h, int bitdepth, const int nb[5], const Sample *d_edges, Sample *d_ref,
                              Sample *d_filt);
