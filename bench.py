@@ -2,15 +2,19 @@
 """bench.py -- the xvc hot path on B200: encoded Mpixels/s at 1080p qp32.
 
 A step = one bi-predicted picture through the whole hot path
-    InterSearch::SearchMotion for every CU (TZ full-pel + sub-pel search on every reference picture of
+    partition pre-analysis on the GPU (encode workload: SAD tree over the quad tree, xvcb200_decide_partition)
+    -> InterSearch::SearchMotion for every CU (TZ full-pel + sub-pel search on every reference picture of
     both lists, SearchBiIterative: FullSearch + sub-pel on the weighted original, uni / bi decision)
     -> motion compensation (uni and bi-predicted CUs)
     -> residual / forward transform / QuantFast / dequant / inverse transform / reconstruction
     -> deblocking -> border padding
-on a seeded CU partition of a synthetic 1920x1080 4:2:0 picture, 10-bit internal, qp 32.
---workload encode (default): xvc's default reference lists at POC 8 of a sub-GOP of 16 (two pictures per
-list), one bi-prediction pass, predictors near the content's motion, camera noise on every frame.
---workload raster: round 1's step (one picture per list, zero predictors -> the raster scan of the
+of a synthetic 1920x1080 4:2:0 picture, 10-bit internal, qp 32.
+--workload encode (default): panned background + objects with their own motion + camera noise; the CU partition
+is decided from the content by the pre-analysis inside the timed step; xvc's default reference lists at POC 8
+of a sub-GOP of 16 (two pictures per list), one bi-prediction pass, the pre-analysis vectors (scaled by POC
+distance) as predictors.  The reference arm codes the same partition with the same predictors (it gets
+them from the numpy statement of the pre-analysis rule, outside its timed region).
+--workload raster: round 1's step (seeded random partition, one picture per list, zero predictors -> the raster scan of the
 +-128 window fires for most CUs, list chosen by the sub-pel cost, noise-free pan).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]      our arm (CUDA through the C ABI)
@@ -50,12 +54,15 @@ LISTS = {"encode": ((0, 16), (16, 0)), "raster": ((0,), (16,))}
 
 
 def picture_inputs(index_offset=0, seed=1234, partition_seed=7):
-    """(current, ref POC 0, ref POC 16) planes + CU partition + picture parameters of one step."""
+    """(current, ref POC 0, ref POC 16) planes + CU partition (raster workload; None: decided by the pre-analysis)
+    + picture parameters of one step."""
     enc = WORKLOAD == "encode"
     canvas = workload.synth_canvas(WIDTH, HEIGHT, seed)
-    frames = [workload.synth_frame(canvas, WIDTH, HEIGHT, i + index_offset, BITDEPTH, frame_noise=4.0 if enc else 0.0)
-              for i in (POC, REF_POCS[0], REF_POCS[1])]
-    cus = workload.make_partition(WIDTH, HEIGHT, seed=partition_seed, min_size=8, qp=QP)
+    frames = []
+    for i in (POC, REF_POCS[0], REF_POCS[1]):
+        f = [p.copy() for p in workload.synth_frame(canvas, WIDTH, HEIGHT, i + index_offset, BITDEPTH, frame_noise=4.0 if enc else 0.0)]
+        frames.append(tuple(workload.add_objects(f, WIDTH, HEIGHT, i + index_offset, BITDEPTH)) if enc else tuple(f))
+    cus = None if enc else workload.make_partition(WIDTH, HEIGHT, seed=partition_seed, min_size=8, qp=QP)
     lam = workload.lambda_for_qp(QP)
     prm = np.zeros(1, dtype=abi.picture_params_dtype)
     prm["pic_type"] = 0
@@ -72,12 +79,27 @@ def picture_inputs(index_offset=0, seed=1234, partition_seed=7):
     return frames, cus, prm, lam
 
 
-def mv_predictors(cus, index_offset=0, partition_seed=7):
-    """encode workload: a predictor per (CU, list, reference picture) near the content's motion (None: raster workload)."""
+def global_motion(index_offset=0):
+    """Picture-level predictor of the pre-analysis: the content's global motion towards POC 0 (an encoder takes it
+    from the previous picture's vectors), 1/16 pel."""
+    return workload.true_motion(POC + index_offset, REF_POCS[0] + index_offset)
+
+
+def predictors_from_partition(cus, index_offset=0):
+    """Predictor per (CU, list, reference picture) from the pre-analysis vector of the CU (towards POC 0), scaled by
+    POC distance like the reference's neighbour predictors (POC 16 lies as far ahead as POC 0 lies behind: -1)."""
     if WORKLOAD != "encode":
         return None
-    lists = tuple(tuple(p + index_offset for p in l) for l in LISTS[WORKLOAD])
-    return workload.mv_predictors(cus, POC + index_offset, lists, seed=partition_seed + 1)
+    mv0 = cus["mv"][:, 0, :].astype(np.int32)
+    cols = [mv0 if p == REF_POCS[0] else -mv0 for l in LISTS[WORKLOAD] for p in l]
+    return np.ascontiguousarray(np.stack(cols, axis=1).astype(np.int32))
+
+
+def cpu_partition(frames, lam):
+    """The reference arm's partition: the numpy statement of the pre-analysis rule (tests/partition_model.py)."""
+    import partition_model
+    cus, _ = partition_model.decide(frames[0][0], frames[1][0], global_motion(), float(np.sqrt(lam)), QP)
+    return cus
 
 
 def set_ref_slots(prm, slot_of_poc):
@@ -104,9 +126,11 @@ def config_dict(n_cus, extra=None):
                        "bi-predicted picture type, one reference picture per list (POC %d, refs %s / %s), search range %d, list chosen by the "
                        "sub-pel cost (round 1's step), noise-free pan") % (
                POC, "/".join(map(str, LISTS[WORKLOAD][0])), "/".join(map(str, LISTS[WORKLOAD][1])), workload.search_range_uni(POC, REF_POCS[0], SUB_GOP)),
-           "partition": "seeded random quad/binary CU tree, 8..64, %d CUs; %s" % (
-               n_cus, "one predictor per (CU, list, reference picture) = the content's motion towards that picture (what POC-scaled neighbour vectors give), exact for half of the CUs, off by <= 6/16 pel for the rest"
-               if WORKLOAD == "encode" else "predictor mvp = 0 for every CU (the raster scan of the window fires for most jobs)"),
+           "partition": ("decided from the content by the pre-analysis (SAD tree, +-8 around the picture's global motion; ours: on the GPU inside every "
+                         "timed step, reference arm: the numpy statement of the same rule outside its timed region), %d CUs; one predictor per (CU, list, "
+                         "reference picture) = the CU's pre-analysis vector scaled by POC distance" % n_cus) if WORKLOAD == "encode" else
+                        ("seeded random quad/binary CU tree, 8..64, %d CUs; predictor mvp = 0 for every CU (the raster scan of the window fires for most jobs)" % n_cus),
+           "content": "panned background + %s" % ("objects with their own motion + camera noise N(0,4)" if WORKLOAD == "encode" else "nothing else"),
            "workload_name": WORKLOAD,
            "l2": "flushed between timed iterations (256 MiB write)"}
     if extra:
@@ -204,7 +228,9 @@ def run_reference(args):
     if rank != 0:
         return
     frames, cus, prm, lam = picture_inputs()
-    mvp = mv_predictors(cus)
+    if cus is None:
+        cus = cpu_partition(frames, lam)
+    mvp = predictors_from_partition(cus)
     arm = CpuArm()
     for _ in range(args.warmup):
         arm.run(frames, cus, prm, lam, mvp)
@@ -279,13 +305,32 @@ def run_ours(args):
     # grows: every rank encodes a picture with the content of the N = 1 run (the search is data
     # dependent -- pictures rank..rank+N-1 of the synthetic sequence differ by up to 18 % in search time,
     # which a max over ranks would report as a scaling loss); --distinct-pictures gives rank r picture r
-    frames, cus, prm, lam = picture_inputs(index_offset=rank if args.distinct_pictures else 0)
-    mvp = mv_predictors(cus, index_offset=rank if args.distinct_pictures else 0)
-    n = len(cus)
+    index_offset = rank if args.distinct_pictures else 0
+    frames, cus, prm, lam = picture_inputs(index_offset=index_offset)
+    enc = WORKLOAD == "encode"
+    gm = global_motion(index_offset)
+    lam_sqrt = float(prm["lambda_sqrt"][0])
+    cur = {"cus": cus, "mvp": None}      # CU array + predictors of the picture coded next
+
+    def decide_begin(orig_slot):
+        """Enqueues the GPU pre-analysis of the picture in orig_slot (kernel + copy of its result)."""
+        if enc:
+            ctx.decide_partition_begin(orig_slot, SL["ref0"], lam_sqrt, QP, center=gm)
+
+    def decide_end():
+        """Collects it -> CU array + predictors (host work: runs while the kernels enqueued after decide_begin execute)."""
+        if not enc:
+            return None
+        c, _ = ctx.decide_partition_end()
+        return {"cus": c, "mvp": predictors_from_partition(c, index_offset)}
+
+    def decide(orig_slot):
+        decide_begin(orig_slot)
+        return decide_end()
 
     def set_cus():
-        ctx.set_cus(cus)          # restores the flags the previous step overwrote (device copy)
-        ctx.set_mv_predictors(mvp)
+        ctx.set_cus(cur["cus"])          # also restores the flags / vectors the previous step overwrote (device copy)
+        ctx.set_mv_predictors(cur["mvp"])
 
     # slots: 0 orig, 1/2 references, 3 prediction, 4 levels, 5.. one reconstruction slot per rank
     # (contiguous: the frame-parallel all-gather lands every rank's reconstruction in place)
@@ -302,6 +347,11 @@ def run_ours(args):
     for slot, f in ((SL["ref0"], frames[1]), (SL["ref1"], frames[2])):
         ctx.upload(slot, f)
         ctx.pad_border(slot)
+    if enc:
+        cur.update(decide(SL["orig"]))
+    n = len(cur["cus"])
+    cus = cur["cus"]
+    mvp = cur["mvp"]
     set_cus()
     ctx.sync()
     ctx.set_profiling(True)
@@ -341,16 +391,20 @@ def run_ours(args):
         if peers is not None:     # the slot about to be rewritten was pushed two steps ago
             peers.wait_own(dev_first_rec[s] + rank)
         mark()
-        set_cus()
         if flush_l2:
             flush.zero_()
         mark()
+        decide_begin(SL["orig"])                       # pre-analysis of the NEXT picture, ahead of this picture's kernels
         ctx.encode_picture(dev_prms[s], want_results=False)
         mark()
         if peers is not None:     # finished, padded reconstructions to every GPU that will reference them
             peers.push(dev_first_rec[s] + rank)
         elif dist is not None:
             works[s] = sharding.frame_parallel_exchange(ctx, dist, rank, world, dev_first_rec[s], async_op=True)
+        nxt = decide_end()        # host work of the next picture (partition, predictors, CU classes, upload) overlaps this picture's kernels
+        if nxt is not None:
+            cur.update(nxt)
+        set_cus()
 
     def drain():
         if peers is not None:
@@ -369,18 +423,26 @@ def run_ours(args):
     launches0 = lib.launch_count()
     step_ms, stage_ms = [], {k: [] for k in lib.Context.STAGES}
     if dist is None:
+        part_ms = []
         for _ in range(args.steps):
-            set_cus()
             if not os.environ.get("XVCB_BENCH_NOFLUSH"):      # experiments only; the default run always flushes
                 flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, ea, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record(stream)
+            decide_begin(SL["orig"])                           # pre-analysis of the NEXT picture, ahead of this picture's kernels
+            ea.record(stream)
             ctx.encode_picture(prm, want_results=False)
             e1.record(stream)
+            nxt = decide_end()                                 # host work of the next picture (partition, predictors, CU classes,
+            if nxt is not None:                                # upload) overlaps this picture's kernels
+                cur.update(nxt)
+            set_cus()
             e1.synchronize()
             step_ms.append(e0.elapsed_time(e1))
+            part_ms.append(e0.elapsed_time(ea))
             for k, v in ctx.stage_times_ms().items():
                 stage_ms[k].append(v)
+        stage_ms["partition"] = part_ms
         total_ms = float(np.sum(step_ms))
     else:
         # Same timed region as N = 1 (the kernels of encode_picture; the untimed set_cus + L2 flush
@@ -422,9 +484,11 @@ def run_ours(args):
     h_orig = [pin(p) for p in frames[0]]
     h_rec = [[pin(np.zeros_like(p)) for p in frames[0]] for _ in range(2)]
     h_lev = [[pin(np.zeros(p.shape, dtype=np.int16)) for p in frames[0]] for _ in range(2)]
-    h_cus = [pin(np.zeros(n, dtype=abi.cu_dtype).view(np.uint8)).view(abi.cu_dtype) for _ in range(2)]
+    n_cu_max = 64 * ((WIDTH + 63) // 64) * ((HEIGHT + 63) // 64)
+    h_cus = [pin(np.zeros(n_cu_max, dtype=abi.cu_dtype).view(np.uint8)).view(abi.cu_dtype) for _ in range(2)]
+    part_d2h = (n_cu_max * abi.cu_dtype.itemsize + 136 * (n_cu_max // 64)) if enc else 0       # what xvcb200_decide_partition brings back
     h2d = sum(p.nbytes for p in h_orig) + cus.nbytes + (mvp.nbytes if mvp is not None else 0)
-    d2h = sum(p.nbytes for p in h_rec[0]) + sum(p.nbytes for p in h_lev[0]) + cus.nbytes
+    d2h = sum(p.nbytes for p in h_rec[0]) + sum(p.nbytes for p in h_lev[0]) + cus.nbytes + part_d2h
     sets = [dict(orig=SL["orig"], coeff=SL["coeff"], first_rec=5),
             dict(orig=base2, coeff=base2 + 1, first_rec=base2 + 2)]
     prms = []
@@ -436,28 +500,40 @@ def run_ours(args):
     def e2e_run(count, flush_l2=True):
         """count pictures through the pipeline; returns the last picture's outputs (host arrays)."""
         ctx.upload_async(sets[0]["orig"], h_orig)
+        if enc:
+            cur.update(decide(sets[0]["orig"]))
+        set_cus()
+        n_of = [0, 0]
         for i in range(count):
             s = i & 1
             if i + 1 < count:
                 ctx.upload_async(sets[1 - s]["orig"], h_orig)
             if peers is not None:
                 peers.wait_own(sets[s]["first_rec"] + rank)
-            set_cus()
             if flush_l2:
                 flush.zero_()
+            # pre-analysis of picture i+1 (its upload is joined inside) ahead of the kernels of picture i
+            if i + 1 < count:
+                decide_begin(sets[1 - s]["orig"])
             ctx.encode_picture(prms[s], want_results=False)
             if peers is not None:
                 peers.push(sets[s]["first_rec"] + rank)
             elif dist is not None:
                 sharding.frame_parallel_exchange(ctx, dist, rank, world, sets[s]["first_rec"])
-            ctx.get_cus_async(h_cus[s])
+            n_of[s] = len(cur["cus"])
+            ctx.get_cus_async(h_cus[s][:n_of[s]])
             ctx.download_coeff_async(sets[s]["coeff"], h_lev[s])
             ctx.download_async(sets[s]["first_rec"] + rank, h_rec[s])
             if i >= 1:                       # picture i-1 is complete on the host from here on
                 ctx.wait_download(sets[1 - s]["first_rec"] + rank)
+            if i + 1 < count:
+                nxt = decide_end()
+                if nxt is not None:
+                    cur.update(nxt)
+                set_cus()                    # host work of picture i+1 overlaps the kernels of picture i
         last = (count - 1) & 1
         ctx.wait_download(sets[last]["first_rec"] + rank)
-        return h_cus[last], h_rec[last], h_lev[last]
+        return h_cus[last][:n_of[last]], h_rec[last], h_lev[last]
 
     ctx.set_profiling(False)
     e2e_run(max(2, args.warmup))
@@ -499,6 +575,7 @@ def run_ours(args):
         "deblock": int(2 * 1.5 * P * 2) + 2 * P,
         "pad_border": int(0.2 * 1.5 * P * 2),
         "me_jobs": 60 * n,
+        "partition": P * 2 * 2 + 28 * n,      # original + one reference picture once, CU array out
     }
     stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     dom = max(stage_avg, key=stage_avg.get)
@@ -533,7 +610,9 @@ def run_ours(args):
     try:
         arm = CpuArm()
         frames0, cus0, prm0, lam0 = picture_inputs(index_offset=0)
-        mvp0 = mv_predictors(cus0)
+        if cus0 is None:      # the partition the GPU decided for this content (equal to the numpy rule: tests/test_gpu_partition.py)
+            cus0 = cus if index_offset == 0 else cpu_partition(frames0, lam0)
+        mvp0 = predictors_from_partition(cus0)
         t_first, rec_cpu = arm.run(frames0, cus0, prm0, lam0, mvp0)
         reps = int(min(20, max(1, 8.0 / max(t_first, 1e-3)))) if arm.kind == "reference" and world == 1 else 1
         times = [t_first] + [arm.run(frames0, cus0, prm0, lam0, mvp0)[0] for _ in range(reps - 1)]

@@ -550,6 +550,12 @@ typedef struct {
 } xvcb200_partition_params;
 int xvcb200_decide_partition(xvcb200_ctx *ctx, const xvcb200_partition_params *params, xvcb200_cu *cus_out, int cus_cap,
                              int *n_cus, uint8_t *splits_out, int splits_cap, int *n_splits);
+/* The same in two halves: _begin enqueues the kernel and the copy of its result on the context stream and returns;
+ * _end waits for that copy only and compacts the result.  Work enqueued between the two (the kernels of the picture
+ * before) runs while the host processes the partition.  One pre-analysis in flight per context. */
+int xvcb200_decide_partition_begin(xvcb200_ctx *ctx, const xvcb200_partition_params *params);
+int xvcb200_decide_partition_end(xvcb200_ctx *ctx, xvcb200_cu *cus_out, int cus_cap, int *n_cus, uint8_t *splits_out,
+                                 int splits_cap, int *n_splits);
 
 /* Optional per-stage device timing of xvcb200_encode_picture (CUDA events on the context
  * stream): ms[0..6] = job set-up, full-pel TZ search, sub-pel search + list decision, motion

@@ -565,10 +565,10 @@ def test_search_motion_flow_is_the_references(ref, pic_type, pocs, iters):
         if k % 5 == 0:
             cu["flags"] |= abi.CU_FULLPEL_MV
         s = ref.session(width, height, bd, pic_type, qp, lam, simd=1, poc=poc, sub_gop=16)
-        s.set_orig(workload.synth_frame(canvas, width, height, poc, bd, frame_noise=4.0))
+        s.set_orig(workload.synth_frame(canvas, width, height, poc, bd, frame_noise=8.0))
         for l in range(2):
             for r, p in enumerate(pocs[l]):
-                s.add_ref(l, r, p, workload.synth_frame(canvas, width, height, p, bd, frame_noise=4.0))
+                s.add_ref(l, r, p, workload.synth_frame(canvas, width, height, p, bd, frame_noise=8.0))
         flow, reference = s.search_motion_single(prm, cu)
         s.close()
         assert np.array_equal(flow["ref_idx"], reference["ref_idx"]), (k, flow, reference)

@@ -434,6 +434,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int16_t *d_worig = nullptr;
   std::vector<CUtensorMap> luma_tmaps;         // per slot: [2 * slot + 0 / 1] = narrow / wide box over the padded luma plane (full search)
   xvcb200_tu_mode *d_tu_modes = nullptr; int tu_modes_cap = 0; bool tu_modes_set = false;   // xvcb200_set_tu_modes
+  uint8_t *d_part = nullptr, *h_part = nullptr; cudaEvent_t part_ev = nullptr; bool part_pending = false;   // xvcb200_decide_partition_begin / _end
   int32_t *d_cu_map2 = nullptr;                // 4x4 CU map of the secondary (chroma) tree (xvcb200_deblock_picture_ext)
   int32_t *d_mvp = nullptr; int mvp_cap = 0;   // xvcb200_set_mv_predictors: [cu][column][2]
   int mvp_cols = 0;                            // 0: none given for the current CU array
@@ -644,6 +645,7 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   for (int b = 0; b < 2; b++) { if (c->ex.h_mvp[b]) cudaFreeHost(c->ex.h_mvp[b]); if (c->ex.mvp_ev[b]) cudaEventDestroy(c->ex.mvp_ev[b]); }
+  cudaFree(c->ex.d_part); if (c->ex.h_part) cudaFreeHost(c->ex.h_part); if (c->ex.part_ev) cudaEventDestroy(c->ex.part_ev);
   cudaFree(c->ex.d_cu_map2); cudaFree(c->ex.d_tu_modes); cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
@@ -1098,8 +1100,14 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   std::vector<int> ctu_first((size_t)n_ctus + 1, 0), by_ctu((size_t)n);
   for (int i = 0; i < n; i++)
     if (searched(i)) ctu_first[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6)) + 1]++;
+  // A search group = a run of at most kGroupCus (32) searched CUs of one CTU (coding order): the unit the persistent search
+  // CTAs take from their counter.  Whole CTUs of 64 small CUs next to CTUs of one CU balance badly across 148 CTAs.
+  static const int kGroupCus = getenv("XVCB_GROUP_CUS") ? std::max(1, atoi(getenv("XVCB_GROUP_CUS"))) : 32;   // (the variable: experiments)
   int n_groups = 0;
-  for (int t = 0; t < n_ctus; t++) { n_groups += ctu_first[(size_t)t + 1] != 0; ctu_first[(size_t)t + 1] += ctu_first[(size_t)t]; }
+  for (int t = 0; t < n_ctus; t++) {
+    n_groups += (ctu_first[(size_t)t + 1] + kGroupCus - 1) / kGroupCus;
+    ctu_first[(size_t)t + 1] += ctu_first[(size_t)t];
+  }
   {
     std::vector<int> fill(ctu_first.begin(), ctu_first.end() - 1);
     for (int i = 0; i < n; i++)
@@ -1137,17 +1145,18 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   for (int i = 0; i < n; i++) idx1[i] = i < n_search ? by_ctu[(size_t)i] : 0;
   // Groups are handed to the persistent search CTAs in this order: longest first (cost grows with
   // the number of jobs), so that the groups still running when the counter runs out are the short ones.
-  std::vector<int> ctu_order;
-  ctu_order.reserve((size_t)n_groups);
-  for (int t = 0; t < n_ctus; t++)
-    if (ctu_first[(size_t)t + 1] > ctu_first[(size_t)t]) ctu_order.push_back(t);
-  std::stable_sort(ctu_order.begin(), ctu_order.end(), [&](int a, int b) {
-    return ctu_first[(size_t)a + 1] - ctu_first[(size_t)a] > ctu_first[(size_t)b + 1] - ctu_first[(size_t)b];
-  });
-  for (int g = 0; g < n_groups; g++) {
-    const int t = ctu_order[(size_t)g];
-    grp1[2 * g] = ctu_first[(size_t)t]; grp1[2 * g + 1] = ctu_first[(size_t)t + 1] - ctu_first[(size_t)t];
+  std::vector<std::pair<int, int>> runs;       // (first, count)
+  runs.reserve((size_t)n_groups);
+  for (int t = 0; t < n_ctus; t++) {
+    const int first = ctu_first[(size_t)t], cnt = ctu_first[(size_t)t + 1] - first;
+    const int pieces = (cnt + kGroupCus - 1) / kGroupCus;
+    for (int k = 0; k < pieces; k++) {
+      const int a = (int)((long long)cnt * k / pieces), b = (int)((long long)cnt * (k + 1) / pieces);
+      runs.emplace_back(first + a, b - a);
+    }
   }
+  std::stable_sort(runs.begin(), runs.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.second > b.second; });
+  for (int g = 0; g < n_groups; g++) { grp1[2 * g] = runs[(size_t)g].first; grp1[2 * g + 1] = runs[(size_t)g].second; }
   c->ex.pipe_n_groups = n_groups;
   auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
   memset(c->ex.class_count, 0, sizeof(c->ex.class_count));
@@ -1577,32 +1586,51 @@ static int deblock_impl(xvcb200_ctx *c, int rec_slot, int pic_type, int beta_off
   return c->status;
 }
 
-int xvcb200_decide_partition(xvcb200_ctx *ctx, const xvcb200_partition_params *prm, xvcb200_cu *cus_out, int cus_cap, int *n_cus,
-                             uint8_t *splits_out, int splits_cap, int *n_splits) {
+// The pre-analysis in two halves, so that a caller can enqueue other work (the previous picture's kernels) between
+// them: _begin enqueues the kernel and the copy of its result into page-locked memory, _end waits for that copy only.
+int xvcb200_decide_partition_begin(xvcb200_ctx *ctx, const xvcb200_partition_params *prm) {
   xvcb::DevGuard dev_guard(ctx);
-  if (!ctx || !prm || !cus_out || !n_cus || !splits_out || !n_splits || !slot_ok(ctx, prm->orig_slot) || !slot_ok(ctx, prm->ref_slot) ||
-      prm->header_bits_cu < 0 || prm->header_bits_split < 0 || prm->header_bits_cu > 255 || prm->header_bits_split > 255)
+  if (!ctx || !prm || !slot_ok(ctx, prm->orig_slot) || !slot_ok(ctx, prm->ref_slot) || prm->header_bits_cu < 0 ||
+      prm->header_bits_split < 0 || prm->header_bits_cu > 255 || prm->header_bits_split > 255)
     return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
   const int n_ctus = ((c->width + 63) >> 6) * ((c->height + 63) >> 6);
   const size_t b_cus = sizeof(xvcb200_cu) * 64 * (size_t)n_ctus, b_spl = 128 * (size_t)n_ctus, b_cnt = sizeof(int) * (size_t)n_ctus;
   const size_t total = b_cus + b_spl + 2 * b_cnt;
-  uint8_t *d = static_cast<uint8_t *>(c->scratch(total));
-  uint8_t *h = static_cast<uint8_t *>(c->pinned(total));
-  if (!d || !h) return c->status;
+  if (!c->ex.d_part) {
+    if (!c->check(cudaMalloc(&c->ex.d_part, total), "cudaMalloc(partition)") ||
+        !c->check(cudaHostAlloc(&c->ex.h_part, total, cudaHostAllocDefault), "cudaHostAlloc(partition)") ||
+        !c->check(cudaEventCreateWithFlags(&c->ex.part_ev, cudaEventDisableTiming), "cudaEventCreate"))
+      return c->status;
+  }
   join_upload_slot(c, prm->orig_slot);
   join_upload_slot(c, prm->ref_slot);
   const uint32_t lam = lambda_me_of(prm->lambda_sqrt);
   const int bits_cu = prm->header_bits_cu ? prm->header_bits_cu : 8, bits_split = prm->header_bits_split ? prm->header_bits_split : 1;
+  uint8_t *d = c->ex.d_part;
   xvcb200_cu *d_cus = reinterpret_cast<xvcb200_cu *>(d);
   uint8_t *d_spl = d + b_cus;
   int *d_ncu = reinterpret_cast<int *>(d + b_cus + b_spl), *d_nsp = d_ncu + n_ctus;
   c->check(launch_partition(c->stream, c->plane(prm->orig_slot, 0), c->plane(prm->ref_slot, 0), prm->center[0], prm->center[1], lam,
                             (int)(((unsigned long long)lam * bits_cu) >> 16), (int)(((unsigned long long)lam * bits_split) >> 16), prm->qp,
                             d_cus, d_ncu, d_spl, d_nsp), "partition");
-  c->check(cudaMemcpyAsync(h, d, total, cudaMemcpyDeviceToHost, c->stream), "partition results");
-  const int st = xvcb200_sync(c);
-  if (st != XVCB200_OK) return st;
+  c->check(cudaMemcpyAsync(c->ex.h_part, d, total, cudaMemcpyDeviceToHost, c->stream), "partition results");
+  c->check(cudaEventRecord(c->ex.part_ev, c->stream), "cudaEventRecord");
+  c->ex.part_pending = true;
+  return c->status;
+}
+
+int xvcb200_decide_partition_end(xvcb200_ctx *ctx, xvcb200_cu *cus_out, int cus_cap, int *n_cus, uint8_t *splits_out, int splits_cap,
+                                 int *n_splits) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || !cus_out || !n_cus || !splits_out || !n_splits) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  if (!c->ex.part_pending) return XVCB200_INVALID_ARGUMENT;
+  c->ex.part_pending = false;
+  if (!c->check(cudaEventSynchronize(c->ex.part_ev), "partition results")) return c->status;
+  const int n_ctus = ((c->width + 63) >> 6) * ((c->height + 63) >> 6);
+  const size_t b_cus = sizeof(xvcb200_cu) * 64 * (size_t)n_ctus, b_spl = 128 * (size_t)n_ctus;
+  const uint8_t *h = c->ex.h_part;
   const xvcb200_cu *h_cus = reinterpret_cast<const xvcb200_cu *>(h);
   const uint8_t *h_spl = h + b_cus;
   const int *h_ncu = reinterpret_cast<const int *>(h + b_cus + b_spl), *h_nsp = h_ncu + n_ctus;
@@ -1615,6 +1643,14 @@ int xvcb200_decide_partition(xvcb200_ctx *ctx, const xvcb200_partition_params *p
   }
   *n_cus = nc; *n_splits = ns;
   return XVCB200_OK;
+}
+
+int xvcb200_decide_partition(xvcb200_ctx *ctx, const xvcb200_partition_params *prm, xvcb200_cu *cus_out, int cus_cap, int *n_cus,
+                             uint8_t *splits_out, int splits_cap, int *n_splits) {
+  if (!cus_out || !n_cus || !splits_out || !n_splits) return XVCB200_INVALID_ARGUMENT;
+  const int st = xvcb200_decide_partition_begin(ctx, prm);
+  if (st != XVCB200_OK) return st;
+  return xvcb200_decide_partition_end(ctx, cus_out, cus_cap, n_cus, splits_out, splits_cap, n_splits);
 }
 
 // per-stage device times of the last xvcb200_encode_picture: ms[0..6] = make jobs, full-pel TZ

@@ -538,17 +538,15 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     const int ref_slot = jobs[job_of(0)].ref_slot;
     const PlaneView ref = ref_planes[ref_slot];
 
-    for (int k0 = 0; k0 < G.count; k0 += kMaxGroupJobs) {
-      const int kn = min(kMaxGroupJobs, G.count - k0);
+    // The jobs of a group are searched in chunks: as many consecutive jobs (<= kMaxGroupJobs) as have the
+    // bounding box of their search windows inside the shared-memory region -- predictors that differ between
+    // the CUs of a CTU widen the box (with one predictor for all of them a +-128 window just fits).
+    int kn_adv = 0;
+    for (int k0 = 0; k0 < G.count; k0 += kn_adv) {
+      const int kmax = min(kMaxGroupJobs, G.count - k0);
       __syncthreads();
-      if (tid == 0) {
-        s_box[0] = s_box[1] = 1 << 30; s_box[2] = s_box[3] = -(1 << 30);
-        s_pool_used = 0; s_next = 0; s_any_raster = 0;
-      }
-      if (tid < 10) s_cls[tid] = 0;
-      __syncthreads();
-      // job descriptors -> shared memory; bounding box of the search windows (block extent included)
-      for (int k = tid; k < kn; k += kTzThreads) {
+      // job descriptors -> shared memory; the search window of each (block extent included) parked in the raster fields
+      for (int k = tid; k < kmax; k += kTzThreads) {
         const int ji = job_of(k0 + k);
         const xvcb200_me_job job = jobs[ji];
         const xvcb200_cu cu = cus[job.cu];
@@ -560,10 +558,27 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         sj.key = ~0ull;
         int lo[2], hi[2];
         min_max_mv(cu.x, cu.y, ref.width, ref.height, job.mvp[0], job.mvp[1], job.search_range, lo, hi);
-        atomicMin(&s_box[0], cu.x + lo[0]); atomicMin(&s_box[1], cu.y + lo[1]);
-        atomicMax(&s_box[2], cu.x + hi[0] + cu.w); atomicMax(&s_box[3], cu.y + hi[1] + cu.h);
-        atomicAdd(&s_cls[__clz((int)cu.w * cu.h) - 19], 1);       // area 4096 -> class 0 ... 16 -> class 8
+        sj.slox = cu.x + lo[0]; sj.sloy = cu.y + lo[1]; sj.nx = cu.x + hi[0] + cu.w; sj.ny = cu.y + hi[1] + cu.h;
       }
+      __syncthreads();
+      if (tid == 0) {
+        int b0 = s_job[0].slox, b1 = s_job[0].sloy, b2 = s_job[0].nx, b3 = s_job[0].ny, kfit = 1;
+        for (; kfit < kmax; kfit++) {
+          const SJob &sj = s_job[kfit];
+          const int n0 = min(b0, sj.slox), n1 = min(b1, sj.sloy), n2 = max(b2, sj.nx), n3 = max(b3, sj.ny);
+          const int nbw = n2 - (n0 & ~7);
+          if ((long long)((((nbw + 1) / 2 + 1) | 1)) * (n3 - n1) > region_budget_words) break;
+          b0 = n0; b1 = n1; b2 = n2; b3 = n3;
+        }
+        s_box[0] = b0; s_box[1] = b1; s_box[2] = b2; s_box[3] = b3;
+        s_count = kfit;
+        s_pool_used = 0; s_next = 0; s_any_raster = 0;
+      }
+      if (tid < 10) s_cls[tid] = 0;
+      __syncthreads();
+      const int kn = s_count;
+      kn_adv = kn;
+      for (int k = tid; k < kn; k += kTzThreads) atomicAdd(&s_cls[__clz((int)s_job[k].w * s_job[k].h) - 19], 1);   // area 4096 -> class 0 ... 16 -> class 8
       __syncthreads();
       if (tid == 0) {          // class counts -> first slot of each class; blocks of >= 2048 samples are searched CTA-wide
         s_ncoop = s_cls[0] + s_cls[1];

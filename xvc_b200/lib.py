@@ -39,7 +39,7 @@ EXPORTS = [
     "xvcb200_get_cus_async", "xvcb200_sync_copies", "xvcb200_wait_download",
     "xvcb200_me_search", "xvcb200_full_search", "xvcb200_motion_compensate", "xvcb200_motion_compensate_affine", "xvcb200_motion_compensate_lic", "xvcb200_tq_reconstruct",
     "xvcb200_dequant_reconstruct", "xvcb200_deblock_picture", "xvcb200_deblock_picture_ex", "xvcb200_deblock_picture_ext", "xvcb200_deblock_band",
-    "xvcb200_encode_picture", "xvcb200_decide_partition", "xvcb200_set_profiling", "xvcb200_get_stage_times",
+    "xvcb200_encode_picture", "xvcb200_decide_partition", "xvcb200_decide_partition_begin", "xvcb200_decide_partition_end", "xvcb200_set_profiling", "xvcb200_get_stage_times",
     "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan", "xvcb200_intra_lm_chroma",
     "xvcb200_ipc_export", "xvcb200_ipc_open_peer", "xvcb200_push_slot", "xvcb200_wait_pushes",
     "xvcb200_device_count",
@@ -134,6 +134,8 @@ def load():
     L.xvcb200_deblock_band.argtypes = [c_void_p] + [c_int] * 7 + [c_void_p] + [c_int] * 3
     L.xvcb200_encode_picture.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.xvcb200_decide_partition.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
+    L.xvcb200_decide_partition_begin.argtypes = [c_void_p, c_void_p]
+    L.xvcb200_decide_partition_end.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]
     L.xvcb200_set_profiling.argtypes = [c_void_p, c_int]
     L.xvcb200_get_stage_times.argtypes = [c_void_p, c_void_p]
     _lib = L
@@ -556,18 +558,27 @@ class Context:
         self._ok(self.L.xvcb200_get_stage_times(self.h, abi.ptr(ms)))
         return dict(zip(self.STAGES, [float(v) for v in ms]))
 
-    def decide_partition(self, orig_slot, ref_slot, lambda_sqrt, qp, center=(0, 0), header_bits_cu=0, header_bits_split=0):
-        """GPU pre-analysis -> (CU array in coding order with mv = the winning vectors, split flags)."""
+    def decide_partition_begin(self, orig_slot, ref_slot, lambda_sqrt, qp, center=(0, 0), header_bits_cu=0, header_bits_split=0):
+        """Enqueues the GPU pre-analysis (kernel + copy of its result); decide_partition_end() collects it."""
         prm = np.zeros(1, dtype=abi.partition_params_dtype)
         prm["orig_slot"], prm["ref_slot"], prm["center"], prm["lambda_sqrt"], prm["qp"] = orig_slot, ref_slot, center, lambda_sqrt, qp
         prm["header_bits_cu"], prm["header_bits_split"] = header_bits_cu, header_bits_split
+        self._ok(self.L.xvcb200_decide_partition_begin(self.h, abi.ptr(prm)))
+
+    def decide_partition_end(self):
+        """-> (CU array in coding order with mv = the winning vectors, split flags)."""
         n_ctus = ((self.width + 63) // 64) * ((self.height + 63) // 64)
-        cus = np.zeros(64 * n_ctus, dtype=abi.cu_dtype)
-        splits = np.zeros(128 * n_ctus, dtype=np.uint8)
-        n = np.zeros(2, dtype=np.int32)
-        self._ok(self.L.xvcb200_decide_partition(self.h, abi.ptr(prm), abi.ptr(cus), len(cus), ctypes.c_void_p(n.ctypes.data),
-                                                 abi.ptr(splits), len(splits), ctypes.c_void_p(n.ctypes.data + 4)))
+        if getattr(self, "_part_buf", None) is None:
+            self._part_buf = (np.zeros(64 * n_ctus, dtype=abi.cu_dtype), np.zeros(128 * n_ctus, dtype=np.uint8), np.zeros(2, dtype=np.int32))
+        cus, splits, n = self._part_buf
+        self._ok(self.L.xvcb200_decide_partition_end(self.h, abi.ptr(cus), len(cus), ctypes.c_void_p(n.ctypes.data),
+                                                     abi.ptr(splits), len(splits), ctypes.c_void_p(n.ctypes.data + 4)))
         return cus[:n[0]].copy(), splits[:n[1]].copy()
+
+    def decide_partition(self, orig_slot, ref_slot, lambda_sqrt, qp, center=(0, 0), header_bits_cu=0, header_bits_split=0):
+        """GPU pre-analysis -> (CU array in coding order with mv = the winning vectors, split flags)."""
+        self.decide_partition_begin(orig_slot, ref_slot, lambda_sqrt, qp, center, header_bits_cu, header_bits_split)
+        return self.decide_partition_end()
 
     def encode_picture(self, params, want_results=True):
         prm = params if isinstance(params, np.ndarray) else np.array([params], dtype=abi.picture_params_dtype)

@@ -2,7 +2,7 @@
 
 Content generator = the one BASELINE.md section 2 records for the reference probes
 (seed 1234): 8x8-block uniform noise in [0,255], 5x5 box filter, + N(0,6) per-pixel noise,
-clipped to 8 bit; frame i is the (W x H) crop at offset (2i mod 32, i mod 32);
+clipped to 8 bit; frame i is the (W x H) crop at offset (2i mod 64, i mod 64) -- a steady pan over 32 frames;
 U = 128 + 0.25*(Y_sub - 128), V = 128 - 0.25*(Y_sub - 128).  Samples are returned at the
 encoder's internal bit depth (8-bit input shifted left by bitdepth-8, as
 Resampler::ConvertFrom does for the default 10-bit internal pipeline, encoder.cc:445-480).
@@ -32,7 +32,7 @@ def synth_frame(canvas, width, height, index, bitdepth=10, frame_noise=0.0):
     (8-bit units, seeded by the frame index) to the luma crop before chroma is derived: camera noise that
     does not follow the pan, so that no reference picture predicts a block exactly (residuals to code,
     bi-prediction averaging two noisy references pays off -- as on real video)."""
-    ox, oy = (2 * index) % 32, index % 32
+    ox, oy = (2 * index) % 64, index % 64
     y8 = canvas[oy:oy + height, ox:ox + width].astype(np.int32)
     if frame_noise > 0:
         rng = np.random.default_rng([977, int(index) & 0xffff, width, height])
@@ -174,7 +174,7 @@ def search_range_uni(poc, ref_poc, sub_gop_length=16, rmin=96, rmax=256):
 
 def true_motion(poc, ref_poc):
     """Displacement of the synthetic content between frame `poc` and frame `ref_poc` (1/16 pel)."""
-    return (16 * ((2 * poc) % 32 - (2 * ref_poc) % 32), 16 * (poc % 32 - ref_poc % 32))
+    return (16 * ((2 * poc) % 64 - (2 * ref_poc) % 64), 16 * (poc % 64 - ref_poc % 64))
 
 
 def set_predictors(cus, poc, ref_pocs, seed=0, jitter=6, exact=0.5):
@@ -207,3 +207,29 @@ def mv_predictors(cus, poc, lists, seed=0, jitter=6, exact=0.5):
     for c, rp in enumerate(pocs):
         out[:, c, :] = np.array(true_motion(poc, rp), dtype=np.int32)[None, :] + noise
     return out
+
+
+def add_objects(planes, width, height, index, bitdepth=10, n_obj=None, seed=4321):
+    """Textured rectangles that move on their own (constant velocity, up to 0.75 samples per frame on top of the
+    pan; about an eighth of the picture is covered) pasted into frame `index` in place: content whose motion is not one global vector, so that a partition
+    decided from the content has something to find.  Object k of frame i sits at p_k + v_k * i; luma and chroma
+    are both replaced.  Returns `planes`."""
+    rng = np.random.default_rng(seed)
+    if n_obj is None:
+        n_obj = max(4, width * height // 40000)
+    tex = synth_frame(synth_canvas(width, height, seed + 1), width, height, 0, bitdepth)
+    for _ in range(n_obj):
+        ow, oh = 2 * int(rng.integers(8, 65)), 2 * int(rng.integers(8, 65))
+        px, py = float(rng.integers(0, max(1, width - ow))), float(rng.integers(0, max(1, height - oh)))
+        vx, vy = float(rng.uniform(-0.75, 0.75)), float(rng.uniform(-0.75, 0.75))
+        tx, ty = 2 * int(rng.integers(0, max(1, (width - ow) // 2))), 2 * int(rng.integers(0, max(1, (height - oh) // 2)))
+        x = 2 * (int(round(px + vx * index)) // 2)
+        y = 2 * (int(round(py + vy * index)) // 2)
+        x0, y0, x1, y1 = max(0, x), max(0, y), min(width, x + ow), min(height, y + oh)
+        if x1 <= x0 or y1 <= y0:
+            continue
+        sx, sy = tx + (x0 - x), ty + (y0 - y)
+        planes[0][y0:y1, x0:x1] = tex[0][sy:sy + (y1 - y0), sx:sx + (x1 - x0)]
+        for c in (1, 2):
+            planes[c][y0 // 2:y1 // 2, x0 // 2:x1 // 2] = tex[c][sy // 2:sy // 2 + (y1 - y0) // 2, sx // 2:sx // 2 + (x1 - x0) // 2]
+    return planes
