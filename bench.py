@@ -286,6 +286,142 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(seen), "samples": len(self.samples)}
 
 
+def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_gops):
+    """BASELINE config 5's mechanism at this run's size: a hierarchical-B sequence (key picture + n_sub_gops sub-GOPs of
+    16) encoded frame-parallel -- ThreadEncoder's rule (a picture starts when its reference pictures are finished),
+    waves across sub-GOPs, picture j of a wave on GPU j mod N, every finished reconstruction pushed into the slot the
+    same POC has on every GPU (CUDA IPC + copy engines over NVLink) and referenced there by later waves after a
+    rendezvous.  Each picture = GPU partition pre-analysis + the whole step.  Returns the dict for the bench line
+    (rank 0) -- throughput, per-wave times and the fraction of GPU time spent idle."""
+    from xvc_b200 import gop
+    pics = gop.hierarchical_gop(n_sub_gops)
+    wave_in = gop.as_wave_input(pics)
+    waves = sharding.gop_waves(wave_in, done=(0,))
+    n_frames = 1 + 16 * n_sub_gops
+    ctx = lib.Context(WIDTH, HEIGHT, BITDEPTH, num_slots=3 + 56, device=local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    peers = sharding.PeerExchange(ctx, dist, rank, world) if dist is not None else None
+    canvas = workload.synth_canvas(WIDTH, HEIGHT, 1234)
+    mine = set()
+    for wave in waves:
+        for j, poc in enumerate(wave):
+            if j % world == rank:
+                mine.add(poc)
+
+    def make(poc):      # the sequence loops after 32 frames (the synthetic pan wraps there)
+        f = [p.copy() for p in workload.synth_frame(canvas, WIDTH, HEIGHT, poc % 32, BITDEPTH, frame_noise=4.0)]
+        return workload.add_objects(f, WIDTH, HEIGHT, poc % 32, BITDEPTH)
+    warm_pocs = (pics[0][0], pics[1][0])   # every rank warms up on the first anchor and the first B picture (local, nothing pushed)
+    dev_orig = {poc: [torch.from_numpy(p.view(np.int16)).cuda() for p in make(poc)] for poc in sorted(mine | set(warm_pocs))}
+    eng = gop.GopEngine(ctx, peers, rank, pics, lambda poc: dev_orig[poc], QP, BITDEPTH,
+                        time_events=lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+    eng.load_done(0, make(0))          # the key picture is not coded here: its original stands in for its reconstruction
+    # warm-up (kernels, allocations), then the real run from the key picture again
+    for p in warm_pocs:
+        eng.encode(p)
+    ctx.sync()
+    eng.events.clear()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wave_ms = []
+    t_all = time.perf_counter()
+    for wave in waves:
+        t0 = time.perf_counter()
+        for j, poc in enumerate(wave):
+            if j % world == rank:
+                eng.encode(poc)
+        for j, poc in enumerate(wave):
+            eng.share(poc, j % world)
+        eng.fence()
+        wave_ms.append((time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    total_s = time.perf_counter() - t_all
+    busy_ms = sum(a.elapsed_time(b) for _, a, b in eng.events)
+    # every rank holds every reconstruction: digest of the last pictures' slots
+    digest = recon_digest([ctx.download_padded(eng.slot_of(poc), 0) for poc in (16 * n_sub_gops, 16 * n_sub_gops - 1)])
+    if dist is not None:
+        t = torch.tensor([total_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_s = float(t.item())
+        b = torch.tensor([busy_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        busy_ms = float(b.item())
+        w = torch.tensor(wave_ms, dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+        wave_ms = [float(v) for v in w.tolist()]
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+    else:
+        digests = [digest]
+    ctx.close()
+    coded = 16 * n_sub_gops
+    return {"frames": n_frames, "pictures_coded": coded, "sub_gops": n_sub_gops,
+            "value": coded * WIDTH * HEIGHT / total_s / 1e6, "unit": "Mpixels/s", "ms_total": total_s * 1e3,
+            "waves": [{"pictures": len(wv), "ms": ms} for wv, ms in zip(waves, wave_ms)],
+            "gpu_busy_frac": busy_ms / (world * total_s * 1e3), "gpu_idle_frac": 1.0 - busy_ms / (world * total_s * 1e3),
+            "reconstructions_identical_on_all_ranks": len(set(digests)) == 1,
+            "how": "ThreadEncoder's readiness rule as waves across sub-GOPs; picture j of a wave on GPU j mod N; per picture: device copy of the "
+                   "original, GPU partition pre-analysis (synchronous), set_cus, the whole step; finished reconstructions pushed to every GPU "
+                   "(copy engines over NVLink) and a rendezvous per wave (own pushes done, stream idle, barrier) before they are referenced; wall "
+                   "clock between barriers, max over ranks; busy = CUDA-event time of the pictures' work summed over GPUs",
+            "search_range": "InterSearch::GetSearchRangeUniPred capped at 128 (it yields 256 for the anchor pictures; the search kernel stages +-128 windows)",
+            "key_picture": "not coded: its original is uploaded as its reconstruction"}
+
+
+def banded_measurement(torch, dist, lib, sharding, rank, world, local_rank, steps):
+    """BASELINE config 4's mechanism: ONE picture split into CTU-row bands across the GPUs, NCCL exchange of the CU
+    decisions and of the deblocking halo rows.  At N = 4 the picture is 3840x2160 (config 4 itself), else this run's
+    size.  Returns the dict for the bench line (rank 0)."""
+    import common
+    W, H = (3840, 2160) if world == 4 else (WIDTH, HEIGHT)
+    canvas = workload.synth_canvas(W, H, 1234)
+    frames = [workload.synth_frame(canvas, W, H, i, BITDEPTH, frame_noise=4.0) for i in (POC, REF_POCS[0], REF_POCS[1])]
+    cus = workload.make_partition(W, H, seed=7, min_size=8, qp=QP)
+    workload.set_predictors(cus, POC, REF_POCS, seed=8)
+    lam = workload.lambda_for_qp(QP)
+    prm = common.picture_params(0, lam, ranges=(128, 128), pocs=REF_POCS, slots=dict(orig=0, ref0=1, ref1=2, pred=3, rec=4, coeff=5), pad=0)
+    prm["bits_mode"], prm["bi_iterations"] = 1, 1
+    ctx = lib.Context(W, H, BITDEPTH, 6, device=local_rank)
+    ctx.upload(0, frames[0])
+    for s_, f in ((1, frames[1]), (2, frames[2])):
+        ctx.upload(s_, f)
+        ctx.pad_border(s_)
+    eng = sharding.GpuEngine(ctx, dict(rec=4), BITDEPTH, {(0, 0): REF_POCS[0], (1, 0): REF_POCS[1]})
+    enc = sharding.BandedPictureEncoder(eng, dist, rank, world, H)
+    for _ in range(2):
+        enc.encode(cus, prm)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        enc.encode(cus, prm)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    # one GPU, the same picture, the same calls without the exchange (rank 0's device)
+    single_ms = None
+    if rank == 0:
+        ctx.set_cus(cus)
+        ctx.encode_picture(prm, want_results=False)
+        ctx.sync()
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            ctx.set_cus(cus)
+            ctx.encode_picture(prm, want_results=False)
+        ctx.sync()
+        single_ms = (time.perf_counter() - t1) / steps * 1e3
+    ctx.close()
+    return {"width": W, "height": H, "bands": world, "ms_per_picture": sec / steps * 1e3, "value": W * H * steps / sec / 1e6, "unit": "Mpixels/s",
+            "single_gpu_ms_per_picture": single_ms, "steps": steps,
+            "how": "CTU-row bands; per picture: band search / MC / T-Q on every GPU, NCCL all-gather of the CU decisions, vertical edges, halo rows "
+                   "down (4 luma + 2x2 chroma), horizontal edges, modified rows back (3 + 2x1); host-synchronous protocol, wall clock, max over ranks"}
+
+
 def run_ours(args):
     import torch
     from xvc_b200 import lib, sharding
@@ -299,7 +435,9 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a rank that fails must not leave the others waiting for ten minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 
     # frame-parallel sharding (weak scaling): one picture per rank and step.  Per-GPU work is FIXED as N
     # grows: every rank encodes a picture with the content of the N = 1 run (the search is data
@@ -555,6 +693,20 @@ def run_ours(args):
         e2e_sec = float(t.item())
     e2e_value = world * WIDTH * HEIGHT * args.steps / e2e_sec / 1e6
 
+    # ---- multi-GPU mechanisms beside the weak-scaling number: the frame-parallel GOP (config 5) and the banded picture (config 4)
+    gop_info = banded_info = None
+    slot_mb = ctx.slot_region(0)[1] / 1e6
+    if args.gop != "off":
+        ctx.close()
+        try:
+            gop_info = gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, max(2, world) if args.gop_sub_gops <= 0 else args.gop_sub_gops)
+        except Exception as e:  # noqa: BLE001
+            gop_info = {"unavailable": repr(e)}
+        if dist is not None:
+            try:
+                banded_info = banded_measurement(torch, dist, lib, sharding, rank, world, local_rank, 10)
+            except Exception as e:  # noqa: BLE001
+                banded_info = {"unavailable": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -631,7 +783,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16 samples / int32 arithmetic", "data": "synthetic",
-        "config": config_dict(n, {"parallelism": (("frame-parallel: one picture per GPU (%s); per step every GPU's padded reconstruction (%.1f MB) goes to the %d others -- %s -- overlapped with the next picture (two reconstruction slot sets); timed: the kernels of every step (as at N=1) + stream stalls waiting for an exchange + the tail of the last exchanges" % ("rank r encodes picture r of the sequence" if args.distinct_pictures else "the same picture content on every GPU: fixed per-GPU work", ctx.slot_region(0)[1] / 1e6, world - 1, "copy-engine pushes into the peers' slot arenas (CUDA IPC over NVLink, no SM)" if peers is not None else "in-place NCCL all-gather on the NCCL stream"))) if world > 1 else "single GPU"}),
+        "config": config_dict(n, {"parallelism": (("frame-parallel: one picture per GPU (%s); per step every GPU's padded reconstruction (%.1f MB) goes to the %d others -- %s -- overlapped with the next picture (two reconstruction slot sets); timed: the kernels of every step (as at N=1) + stream stalls waiting for an exchange + the tail of the last exchanges" % ("rank r encodes picture r of the sequence" if args.distinct_pictures else "the same picture content on every GPU: fixed per-GPU work", slot_mb, world - 1, "copy-engine pushes into the peers' slot arenas (CUDA IPC over NVLink, no SM)" if peers is not None else "in-place NCCL all-gather on the NCCL stream"))) if world > 1 else "single GPU"}),
         "frames_per_s": value * 1e6 / (WIDTH * HEIGHT),
         "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "pipeline": "2 pictures in flight: pinned-host H2D / D2H of neighbouring pictures on the copy stream overlap the kernels"},
@@ -642,6 +794,10 @@ def run_ours(args):
         "recon_bitexact_vs_cpu_baseline": bitexact,
         "me_sad_candidates_per_step": None,
     }
+    if gop_info is not None:
+        line["gop"] = gop_info
+    if banded_info is not None:
+        line["banded"] = banded_info
     if dist is not None:
         line["exchange"] = exchange_ms       # rank 0's own split of its timed total
     print(json.dumps(line))
@@ -658,6 +814,9 @@ def main():
     ap.add_argument("--distinct-pictures", action="store_true", help="N>1: rank r encodes picture r of the sequence instead of picture 0")
     ap.add_argument("--exchange", default="push", choices=["push", "nccl"],
                     help="N>1: how finished reconstructions reach the other GPUs (copy-engine pushes over CUDA IPC, or NCCL all-gather)")
+    ap.add_argument("--gop", default="on", choices=["on", "off"],
+                    help="the frame-parallel hierarchical-B GOP measurement (and, at N > 1, the banded picture) beside the step")
+    ap.add_argument("--gop-sub-gops", type=int, default=0, help="sub-GOPs of 16 pictures in the GOP measurement (default: max(2, N))")
     ap.add_argument("--workload", default="encode", choices=["encode", "raster"], help="see the module docstring")
     ap.add_argument("--size", default=None, metavar="WxH[@QP]",
                     help="context runs only (DESIGN.md table): another picture size / qp, e.g. 3840x2160@27, 7680x4320; the "
