@@ -32,6 +32,13 @@ def hierarchical_gop(n_sub_gops, sub_gop=SUB_GOP):
     return pics
 
 
+def seq_index(poc, span=31):
+    """Frame of the synthetic content shown at POC `poc`: the pan runs forward for `span` frames, then backward
+    (the canvas is finite), so that long sequences have no jump in the content."""
+    k = poc % (2 * span)
+    return k if k <= span else 2 * span - k
+
+
 def as_wave_input(pics):
     """-> the (poc, pic_type, reference POCs) tuples sharding.gop_waves takes."""
     return [(poc, t, tuple(sorted(set(l0) | set(l1)))) for poc, t, l0, l1 in pics]
@@ -89,7 +96,7 @@ class GopEngine:
             my, mx, h, w = self.views[c]
             self.orig_t[c][my:my + h, mx:mx + w].copy_(t)
         # partition from the content, against the first list-0 picture, around the sequence's global motion
-        center = workload.true_motion(poc, l0[0])
+        center = workload.true_motion(seq_index(poc), seq_index(l0[0]))
         cus, _ = ctx.decide_partition(0, self.slot_of(l0[0]), float(np.sqrt(self.lam)), self.qp, center=center)
         mv0 = cus["mv"][:, 0, :].astype(np.int64)
         d0 = poc - l0[0]
