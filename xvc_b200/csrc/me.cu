@@ -244,13 +244,17 @@ struct SearchEval {
   // kEvalDiamond: slots = the points of rounds 0..nrounds-1 around (ax, ay), valid if inside the
   // window [lo, hi].  kEvalList: slot k < nslots = the candidate held by lane k (ex, ey, evalid).
   // cost[q] of lane l = cost of slot 32 q + l, 0xffffffff for invalid / non-existent slots.
-  __device__ __forceinline__ void run(int mode, int lg, int nslots, int ax, int ay, const int lo[2], const int hi[2], int ex,
+  // Only the slots [s_lo, nslots) are evaluated (s_lo > 0: the rest of a pass whose first rounds were evaluated
+  // before; cost[] of the earlier slots is then unspecified).
+  __device__ __forceinline__ void run(int mode, int lg, int s_lo, int nslots, int ax, int ay, const int lo[2], const int hi[2], int ex,
                                       int ey, bool evalid, uint32_t (&cost)[4]) {
     const int spp = 32 >> lg;
     const int npass = (nslots + spp - 1) >> (5 - lg);
+    if (s_lo == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) cost[q] = 0xffffffffu;
-    for (int p = tw; p < npass; p += 1 << lt) {
+      for (int q = 0; q < 4; q++) cost[q] = 0xffffffffu;
+    }
+    for (int p = (s_lo >> (5 - lg)) + tw; p < npass; p += 1 << lt) {
       const int s0 = p << (5 - lg);
       const int s = s0 + (lane >> lg), sub = lane & ((1 << lg) - 1);
       int cx, cy;
@@ -261,7 +265,7 @@ struct SearchEval {
         else if (s < 28) { ri = 1 + ((s - 4) >> 3); k = (s - 4) & 7; }
         else { ri = 4 + ((s - 28) >> 4); k = (s - 28) & 15; }
         pattern_point(s_pat, ri, k, ax, ay, cx, cy, pos, rep);
-        valid = s < nslots && inside(cx, cy, pos, lo, hi);
+        valid = s >= s_lo && s < nslots && inside(cx, cy, pos, lo, hi);
       } else {
         cx = __shfl_sync(XVCB_FULL, ex, s & 31);
         cy = __shfl_sync(XVCB_FULL, ey, s & 31);
@@ -444,6 +448,7 @@ __device__ __forceinline__ void seg_bound_cols(const uint16_t *rp, int row_strid
   }
 }
 
+constexpr int kProfGroups = 4096;        // XVCB_TZ_PROF: per-group records kept
 constexpr int kTzThreads = 512;
 constexpr int kTzWarps = kTzThreads / 32;
 constexpr int kMaxGroupJobs = 64;        // jobs handled per pass over a group
@@ -518,6 +523,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *pool = pool_all + (size_t)blockIdx.x * pool_cap;
   long long t_mark = prof ? clock64() : 0;
+  const long long t_kernel = t_mark;
   int n_staged = 0;
   auto lap = [&](int slot) {     // optional phase timing (XVCB_TZ_PROF=1): cycles of thread 0, summed over CTAs
     if (prof && threadIdx.x == 0) { const long long now = clock64(); atomicAdd(&prof[slot], (unsigned long long)(now - t_mark)); t_mark = now; }
@@ -532,6 +538,8 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     __syncthreads();
     const int grp = s_group;
     if (grp >= n_groups) break;
+    const long long t_group = prof ? clock64() : 0;
+    int g_raster = 0;
     const TzGroup G = groups[sel.J ? grp / sel.n : grp];
     const int jcol = sel.J ? sel.j[grp % sel.n] : 0;
     auto job_of = [&](int k) { const int e = job_index[G.first + k]; return sel.J ? e * sel.J + jcol : e; };
@@ -590,11 +598,11 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       for (int k = tid; k < kn; k += kTzThreads)
         s_order[atomicAdd(&s_cls[__clz((int)s_job[k].w * s_job[k].h) - 19], 1)] = (unsigned char)k;
       __syncthreads();
-      const int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
-      const int bw = rx1 - rx0, bh = ry1 - ry0;
-      const int spw = ((bw + 1) / 2 + 1) | 1;
-      const int cpr = (bw + 7) >> 3;
-      const bool staged = (long long)spw * bh <= region_budget_words;
+      int rx0 = s_box[0] & ~7, ry0 = s_box[1], rx1 = s_box[2], ry1 = s_box[3];
+      int bw = rx1 - rx0, bh = ry1 - ry0;
+      int spw = ((bw + 1) / 2 + 1) | 1;
+      int cpr = (bw + 7) >> 3;
+      bool staged = (long long)spw * bh <= region_budget_words;
       const int ctu_x = s_job[0].x & ~63, ctu_y = s_job[0].y & ~63;
       lap(0);
       // original CTU -> shared memory (all jobs of a group lie in one CTU)
@@ -622,9 +630,59 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
 #pragma unroll 1
       for (int ph = 0; ph < 2; ph++) {
         if (ph == 1) {
-          if (s_any_raster) {
+          if (!s_any_raster) break;                // every job of the chunk finished in the first loop
+          if (prof && tid == 0)
+            for (int k = 0; k < kn; k++) g_raster += s_job[k].need != 0;
+          // Two rounds (SJob::need: 1 = scan window inside the staged box, 2 = outside, 3 = scanned).  Round 0 scans
+          // the jobs whose window lies in the staged box.  A start point other than the predictor re-centres the
+          // scan window (DetermineMinMaxMv around the best start, :121-125), typically for several CUs of the CTU
+          // alike: round 1 stages the bounding box of THOSE windows (as many as fit) and scans them the same way;
+          // only what still does not fit is scanned from global memory.  The refinement then runs on the box
+          // staged last (candidates outside it are read from global memory).
+#pragma unroll 1
+          for (int rr = 0; rr < 2; rr++) {
+            if (rr == 1) {
+              if (tid == 0) {
+                int b0 = 0, b1 = 0, b2 = 0, b3 = 0, taken = 0;
+                for (int k = 0; k < kn; k++) {
+                  SJob &sj = s_job[k];
+                  if (sj.need != 2) continue;
+                  const int X0 = sj.x + sj.slox, Y0 = sj.y + sj.sloy, X1 = X0 + 5 * (sj.nx - 1) + sj.w, Y1 = Y0 + 5 * (sj.ny - 1) + sj.h;
+                  const int n0 = taken ? min(b0, X0) : X0, n1 = taken ? min(b1, Y0) : Y0, n2 = taken ? max(b2, X1) : X1, n3 = taken ? max(b3, Y1) : Y1;
+                  const int nbw = n2 - (n0 & ~7);
+                  if ((long long)((((nbw + 1) / 2 + 1) | 1)) * (n3 - n1) > region_budget_words) continue;
+                  b0 = n0; b1 = n1; b2 = n2; b3 = n3; taken++;
+                  sj.need = 1; sj.list_off = -1; sj.list_cnt = 0;
+                }
+                int left = 0;
+                for (int k = 0; k < kn; k++) left += s_job[k].need == 2;
+                s_box[0] = b0; s_box[1] = b1; s_box[2] = b2; s_box[3] = b3;
+                s_batch_tasks = taken; s_batch_end = left;
+                s_pool_used = 0;
+              }
+              __syncthreads();
+              if (s_batch_tasks == 0 && s_batch_end == 0) break;      // no scan window outside the box (uniform)
+              if (s_batch_tasks > 0) {
+                rx0 = s_box[0] & ~7; ry0 = s_box[1]; rx1 = s_box[2]; ry1 = s_box[3];
+                bw = rx1 - rx0; bh = ry1 - ry0;
+                spw = ((bw + 1) / 2 + 1) | 1;
+                cpr = (bw + 7) >> 3;
+                staged = true;
+                stage_box(ref.base, ref.pitch, rx0, ry0, bh, cpr, spw, s_region, tid, kTzThreads);
+              }
+              __syncthreads();
+            } else {
+              if (tid == 0) {
+                int n1 = 0;
+                for (int k = 0; k < kn; k++) n1 += s_job[k].need == 1;
+                s_batch_tasks = n1;
+              }
+              __syncthreads();
+            }
+            const bool any_in_box = s_batch_tasks > 0;
+            __syncthreads();                                   // s_batch_tasks is written again below
             // ---------------- raster pass 1: segment-sum bound, survivors -> pool
-            if (staged) {
+            if (staged && any_in_box) {
               box_to_s8(s_region, spw, bh, tid, kTzThreads);
               __syncthreads();
               lap(3);
@@ -749,30 +807,60 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             }
 
             // ---------------- raster pass 2a: survivors of all jobs, one flat loop, one candidate per lane
+            // A group holds a few hundred survivors -- fewer than the CTA has threads -- so a survivor per lane
+            // leaves the pass waiting for the one lane that walks a 64x64 block alone.  A warp takes 32
+            // consecutive entries and spreads each over 2^lgw lanes (rows sub, sub + 2^lgw, ... of the block;
+            // lgw from the largest block among the 32 so that a lane sums about 16 sample pairs), the partial
+            // sums meet in lgw shuffles.
             {
               const int total = s_pool_used;
-              for (int e = tid; e < total; e += kTzThreads) {
-                const uint32_t ent = pool[e];
-                const int k = (int)(ent >> 16);
-                const uint32_t t = ent & 0xffffu;
-                SJob &sj = s_job[k];
-                if (sj.list_off < 0 || e < sj.list_off || e >= sj.list_off + sj.list_cnt) continue;   // list of an overflowed job
-                const MeGeom g = sjob_geom(sj, bitdepth, lambda);
-                const int j = (int)t / sj.nx, i = (int)t - j * sj.nx;
-                const int cx = sj.slox + 5 * i, cy = sj.sloy + 5 * j;
-                const int ox = g.x + cx - rx0, oy = g.y + cy - ry0;
-                const uint32_t sad = sad_rows_lpw(g.lpw, s_region + oy * spw + (ox >> 1), g.rstep * spw,
-                                                         s_tile + (sj.y - ctu_y) * 33 + ((sj.x - ctu_x) >> 1), 33 * g.rstep, g.rows,
-                                                         (ox & 1) << 4);
-                const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
-                const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
-                atomicMin(&sj.key, ((unsigned long long)cost << 32) | t);
+              for (int e0 = warp * 32; e0 < total; e0 += kTzThreads) {
+                const int e = e0 + lane;
+                uint32_t ent = 0;
+                int lgj = 0;
+                bool live = false;
+                if (e < total) {
+                  ent = pool[e];
+                  const SJob &sj = s_job[ent >> 16];
+                  live = !(sj.list_off < 0 || e < sj.list_off || e >= sj.list_off + sj.list_cnt);   // not the list of an overflowed job
+                  const int rows = sj.h > 8 ? sj.h >> 1 : sj.h;
+                  const int lpairs = (31 - __clz(rows)) + (30 - __clz((int)sj.w));
+                  lgj = live ? min(31 - __clz(rows), max(0, lpairs - 4)) : 0;
+                }
+                const int lgw = __reduce_max_sync(XVCB_FULL, lgj);
+                const unsigned live_mask = __ballot_sync(XVCB_FULL, live);
+                for (int q = 0; q < (1 << lgw); q++) {
+                  const int src = ((q << 5) + lane) >> lgw, sub = lane & ((1 << lgw) - 1);
+                  const uint32_t en = __shfl_sync(XVCB_FULL, ent, src);
+                  const bool on = (live_mask >> src) & 1u;
+                  if (!__ballot_sync(XVCB_FULL, on)) continue;
+                  SJob &sj = s_job[en >> 16];
+                  const uint32_t t = en & 0xffffu;
+                  const MeGeom g = sjob_geom(sj, bitdepth, lambda);
+                  const int j = (int)t / sj.nx, i = (int)t - j * sj.nx;
+                  const int cx = sj.slox + 5 * i, cy = sj.sloy + 5 * j;
+                  uint32_t sad = 0;
+                  if (on && sub < g.rows) {
+                    const int ox = g.x + cx - rx0, oy = g.y + cy - ry0 + sub * g.rstep;
+                    sad = sad_rows_lpw(g.lpw, s_region + oy * spw + (ox >> 1), (g.rstep * spw) << lgw,
+                                       s_tile + (sj.y - ctu_y + sub * g.rstep) * 33 + ((sj.x - ctu_x) >> 1), (33 * g.rstep) << lgw,
+                                       (g.rows - sub + (1 << lgw) - 1) >> lgw, (ox & 1) << 4);
+                  }
+#pragma unroll
+                  for (int off = 16; off > 0; off >>= 1)
+                    if (off < (1 << lgw)) sad += __shfl_xor_sync(XVCB_FULL, sad, off);
+                  if (on && sub == 0) {
+                    const uint32_t dist = g.fast ? (sad * 2) >> g.bd_shift : sad >> g.bd_shift;
+                    const uint32_t cost = dist + ((g.lambda * mvd_bits_fullpel(g.mvpx, g.mvpy, cx, cy, g.down)) >> 16);
+                    atomicMin(&sj.key, ((unsigned long long)cost << 32) | t);
+                  }
+                }
               }
             }
             // ---------------- raster pass 2b: dense scans (no survivor list), CTA-wide per job
             for (int k = 0; k < kn; k++) {
               SJob &sj = s_job[k];
-              if (sj.need == 0 || sj.list_off >= 0) continue;      // uniform
+              if (!((sj.need == 1 && sj.list_off < 0) || (rr == 1 && sj.need == 2))) continue;      // uniform
               const MeGeom g = sjob_geom(sj, bitdepth, lambda);
               const int slox = sj.slox, sloy = sj.sloy, nx = sj.nx, ny = sj.ny;
               const bool in_box = sj.need == 1;
@@ -807,7 +895,8 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             // winners -> job state (strict compare: ties keep the earlier best, :266-268)
             for (int k = tid; k < kn; k += kTzThreads) {
               SJob &sj = s_job[k];
-              if (sj.need == 0) continue;
+              if (!(sj.need == 1 || (rr == 1 && sj.need == 2))) continue;
+              sj.need = 3;
               TzJobState *stp = &states[sj.ji];
               const uint32_t c = (uint32_t)(sj.key >> 32), t = (uint32_t)sj.key;
               if (sj.key != ~0ull && c < sj.cost_in) {
@@ -820,6 +909,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
               stp->need_raster = 0;
             }
             __threadfence_block();
+            __syncthreads();
           }
           if (tid == 0) s_next = 0;
           __syncthreads();
@@ -844,6 +934,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
           }
           if (o >= kn) break;
           SJob &sj = s_job[s_order[o]];
+          if (ph == 1 && sj.need == 0) continue;      // finished in the first loop
           const int area = (int)sj.w * sj.h;
           const int want = area >= 2048 ? kTzWarps : (area >= 512 ? 4 : 1);
           if (want < tsize) {
@@ -881,7 +972,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             const bool use_zero = px != 0 || py != 0, use_prev = sj.depth != 0;
             const int ex = lane == 0 ? px : (lane == 1 ? 0 : qx), ey = lane == 0 ? py : (lane == 1 ? 0 : qy);
             tick(11);                                 // setup
-            ev.run(kEvalList, lg_l, 3, 0, 0, lo, hi, ex, ey, lane == 0 || (lane == 1 && use_zero) || (lane == 2 && use_prev), cost);
+            ev.run(kEvalList, lg_l, 0, 3, 0, 0, lo, hi, ex, ey, lane == 0 || (lane == 1 && use_zero) || (lane == 2 && use_prev), cost);
             tick(12);                                 // start eval
             evals = 1 + use_zero + use_prev;
             const uint32_t c0 = __shfl_sync(XVCB_FULL, cost[0], 0), c1 = __shfl_sync(XVCB_FULL, cost[0], 1),
@@ -899,53 +990,64 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             lo[0] = stp->lo[0]; lo[1] = stp->lo[1]; hi[0] = stp->hi[0]; hi[1] = stp->hi[1];
             slo[0] = slo[1] = shi[0] = shi[1] = 0;
             evals = stp->evals;
-            if (stp->need_raster) b.last_range = 5;        // empty scan window (:146-147)
             tick(11);
           }
-          // ph 0: the first diamond pass around the start point, stops after three rounds without
-          // a hit (:133-143), then the 2-point step.  ph 1: re-centre until the centre wins (:157-168).
+          // The first diamond pass around the start point stops after three rounds without a hit (:133-143),
+          // then the 2-point step; a job that needs no raster scan goes straight on to the refinement
+          // (re-centre until the centre wins, every round of every pass, :157-168) -- no CTA-wide barrier
+          // between the two for the majority of the jobs.  A job that needs the scan parks its state and
+          // is picked up again (ph 1) after the CTA-wide raster passes.
+          // The rounds of the first pass are evaluated in two instalments, radii 1..8 (28 slots) and the
+          // rest: with a good predictor the three-miss rule ends the pass inside the first one.
+          bool first = ph == 0, parked = false;
           while (b.last_range > 0) {
             const int ax = b.x, ay = b.y;
             b.last_range = 0;
-            tick(11);
-            ev.run(kEvalDiamond, lg_d, nslots, ax, ay, lo, hi, 0, 0, false, cost);
-            tick(13);                                 // diamond eval
-            if (prof && lane == 0) atomicAdd(&prof[17], 1ull);
-            // FullpelDiamondSearch replayed (:173-210).  The winner of every round (first minimum in
-            // the reference's candidate order) and its number of evaluated points do not depend on
-            // the running best: ten independent warp reductions, then the sequential decisions
-            // (strict compare, three-miss rule of the first pass) on uniform values.
             uint32_t win[10];
-            uint32_t nv_lo = 0, nv_hi = 0;                   // evaluated points per round, 5 bits each
-#pragma unroll
-            for (int ri = 0; ri < 10; ri++) {
-              constexpr int kBeg[10] = {0, 4, 12, 20, 28, 44, 60, 76, 92, 108};
-              const int K = ri == 0 ? 4 : (ri <= 3 ? 8 : 16);
-              const int sbeg = kBeg[ri], q0 = sbeg >> 5, q1 = (sbeg + K - 1) >> 5;
-              win[ri] = 0xffffffffu;
-              if (ri < nrounds) {
-                uint32_t key = 0xffffffffu;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                  if (q != q0 && q != q1) continue;
-                  const int rel = 32 * q + lane - sbeg;
-                  if ((unsigned)rel < (unsigned)K && cost[q] != 0xffffffffu) key = min(key, (cost[q] << 5) | (uint32_t)rel);
-                }
-                win[ri] = __reduce_min_sync(XVCB_FULL, key);
-                const uint32_t nv = __popc(__ballot_sync(XVCB_FULL, key != 0xffffffffu));
-                if (ri < 6) nv_lo |= nv << (5 * ri); else nv_hi |= nv << (5 * (ri - 6));
-              }
-            }
             int misses = 0, wri = -1, wk = 0;
             bool stopped = false;
+            const int split = first && nrounds > 4 ? 4 : nrounds;      // rounds in the first instalment
+#pragma unroll 1
+            for (int inst = 0; inst < 2; inst++) {
+              const int r_lo = inst == 0 ? 0 : split, r_hi = inst == 0 ? split : nrounds;
+              if (r_lo >= r_hi || stopped) break;
+              tick(11);
+              ev.run(kEvalDiamond, lg_d, r_lo == 0 ? 0 : 28, r_hi == nrounds ? nslots : 28, ax, ay, lo, hi, 0, 0, false, cost);
+              tick(13);                               // diamond eval
+              if (prof && lane == 0) atomicAdd(&prof[17], 1ull);
+              // FullpelDiamondSearch replayed (:173-210).  The winner of every round (first minimum in
+              // the reference's candidate order) and its number of evaluated points do not depend on
+              // the running best: independent warp reductions, then the sequential decisions
+              // (strict compare, three-miss rule of the first pass) on uniform values.
+              uint32_t nv_lo = 0, nv_hi = 0;                   // evaluated points per round, 5 bits each
 #pragma unroll
-            for (int ri = 0; ri < 10; ri++) {
-              if (ri < nrounds && !stopped) {
-                evals += ((ri < 6 ? nv_lo >> (5 * ri) : nv_hi >> (5 * (ri - 6))) & 31u);
-                if (win[ri] != 0xffffffffu && (win[ri] >> 5) < b.cost) {
-                  b.cost = win[ri] >> 5; wri = ri; wk = win[ri] & 31; misses = 0;
-                } else if (ph == 0 && ++misses >= 3) {
-                  stopped = true;
+              for (int ri = 0; ri < 10; ri++) {
+                constexpr int kBeg[10] = {0, 4, 12, 20, 28, 44, 60, 76, 92, 108};
+                const int K = ri == 0 ? 4 : (ri <= 3 ? 8 : 16);
+                const int sbeg = kBeg[ri], q0 = sbeg >> 5, q1 = (sbeg + K - 1) >> 5;
+                win[ri] = 0xffffffffu;
+                if (ri >= r_lo && ri < r_hi) {
+                  uint32_t key = 0xffffffffu;
+#pragma unroll
+                  for (int q = 0; q < 4; q++) {
+                    if (q != q0 && q != q1) continue;
+                    const int rel = 32 * q + lane - sbeg;
+                    if ((unsigned)rel < (unsigned)K && cost[q] != 0xffffffffu) key = min(key, (cost[q] << 5) | (uint32_t)rel);
+                  }
+                  win[ri] = __reduce_min_sync(XVCB_FULL, key);
+                  const uint32_t nv = __popc(__ballot_sync(XVCB_FULL, key != 0xffffffffu));
+                  if (ri < 6) nv_lo |= nv << (5 * ri); else nv_hi |= nv << (5 * (ri - 6));
+                }
+              }
+#pragma unroll
+              for (int ri = 0; ri < 10; ri++) {
+                if (ri >= r_lo && ri < r_hi && !stopped) {
+                  evals += ((ri < 6 ? nv_lo >> (5 * ri) : nv_hi >> (5 * (ri - 6))) & 31u);
+                  if (win[ri] != 0xffffffffu && (win[ri] >> 5) < b.cost) {
+                    b.cost = win[ri] >> 5; wri = ri; wk = win[ri] & 31; misses = 0;
+                  } else if (first && ++misses >= 3) {
+                    stopped = true;
+                  }
                 }
               }
             }
@@ -960,37 +1062,38 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
               const unsigned vm = __ballot_sync(XVCB_FULL, valid);
               if (vm) {
                 evals += __popc(vm);
-                ev.run(kEvalList, lg_l, 2, 0, 0, lo, hi, cx, cy, valid, cost);
+                ev.run(kEvalList, lg_l, 0, 2, 0, 0, lo, hi, cx, cy, valid, cost);
                 const uint32_t key = lane < 2 && cost[0] != 0xffffffffu ? (cost[0] << 5) | (uint32_t)lane : 0xffffffffu;
-                const uint32_t win = __reduce_min_sync(XVCB_FULL, key);
-                if (win != 0xffffffffu && (win >> 5) < b.cost) {
-                  b.cost = win >> 5;
+                const uint32_t win2 = __reduce_min_sync(XVCB_FULL, key);
+                if (win2 != 0xffffffffu && (win2 >> 5) < b.cost) {
+                  b.cost = win2 >> 5;
                   int wx = 0, wy = 0, wpos = 0;
-                  two_point(b.last_pos, win & 31, wx, wy, wpos);
+                  two_point(b.last_pos, win2 & 31, wx, wy, wpos);
                   b.x += wx; b.y += wy; b.last_pos = wpos; b.last_range = 1;
                 }
               }
             }
             tick(15);                                 // neighbour
-            if (ph == 0) break;
+            if (first) {
+              first = false;
+              if (b.last_range > 5) {                        // kFullSearchGranularity (:91, :146)
+                if (shi[0] >= slo[0] && shi[1] >= slo[1]) { parked = true; break; }
+                b.last_range = 5;                            // empty scan window (:146-147)
+              }
+            }
           }
           if (tw == 0 && lane == 0) {
-            if (ph == 0) {
+            if (parked) {
               stp->bx = b.x; stp->by = b.y; stp->cost = b.cost; stp->last_pos = b.last_pos; stp->last_range = b.last_range;
               stp->lo[0] = lo[0]; stp->lo[1] = lo[1]; stp->hi[0] = hi[0]; stp->hi[1] = hi[1];
-              stp->slo[0] = slo[0]; stp->slo[1] = slo[1]; stp->shi[0] = shi[0]; stp->shi[1] = shi[1];
               stp->evals = evals;
-              const int need_raster = b.last_range > 5;       // kFullSearchGranularity (:91, :146)
-              stp->need_raster = need_raster;
-              if (need_raster && shi[0] >= slo[0] && shi[1] >= slo[1]) {
-                sj.slox = slo[0]; sj.sloy = slo[1];
-                sj.nx = (shi[0] - slo[0]) / 5 + 1; sj.ny = (shi[1] - slo[1]) / 5 + 1;
-                sj.cost_in = b.cost;
-                const bool fits = staged && g.x + slo[0] >= rx0 && g.x + shi[0] + g.w <= rx1 && g.y + slo[1] >= ry0 &&
-                                  g.y + shi[1] + g.h <= ry1;
-                sj.need = fits ? 1 : 2;
-                s_any_raster = 1;
-              }
+              sj.slox = slo[0]; sj.sloy = slo[1];
+              sj.nx = (shi[0] - slo[0]) / 5 + 1; sj.ny = (shi[1] - slo[1]) / 5 + 1;
+              sj.cost_in = b.cost;
+              const bool fits = staged && g.x + slo[0] >= rx0 && g.x + shi[0] + g.w <= rx1 && g.y + slo[1] >= ry0 &&
+                                g.y + shi[1] + g.h <= ry1;
+              sj.need = fits ? 1 : 2;
+              s_any_raster = 1;
             } else {
               xvcb200_me_result *out = &res[sj.ji];
               out->mv_fullpel[0] = b.x; out->mv_fullpel[1] = b.y;
@@ -1004,7 +1107,15 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
         lap(ph == 0 ? 2 : 7);
       }
     }
+    if (prof && tid == 0 && grp < kProfGroups) {
+      unsigned long long *pg = prof + 24 + 4 * grp;
+      pg[0] = (unsigned long long)(clock64() - t_group); pg[1] = (unsigned long long)G.count; pg[3] = (unsigned long long)g_raster;
+      unsigned long long area = 0;
+      for (int k = 0; k < G.count; k++) { const xvcb200_cu cu = cus[jobs[job_of(k)].cu]; area += (unsigned long long)cu.w * cu.h; }
+      pg[2] = area;
+    }
   }
+  if (prof && tid == 0) prof[24 + 4 * kProfGroups + blockIdx.x] = (unsigned long long)(clock64() - t_kernel);
 }
 
 cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb200_me_job *d_jobs, int n, int bitdepth,
@@ -1047,7 +1158,7 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
   // SM for ~0.1 ms, which the laps then attribute to whatever phase comes first
   // (debugging aid, XVCB_TZ_PROF=1: one counter block per device, single-threaded use)
   static unsigned long long *d_prof_by_dev[kMaxDevices] = {nullptr};
-  unsigned long long prof[24];
+  static unsigned long long prof[24 + 4 * kProfGroups + 256];
   unsigned long long *&d_prof = d_prof_by_dev[dev];
   if (want_prof && !d_prof) cudaMalloc(&d_prof, sizeof(prof));
   if (want_prof) cudaMemsetAsync(d_prof, 0, sizeof(prof), s);
@@ -1068,6 +1179,14 @@ cudaError_t launch_tz_search(cudaStream_t s, const xvcb200_cu *d_cus, const xvcb
     fprintf(stderr, "[tz prof2] warp-cycles/CTA: fetch %.0f setup %.0f start %.0f diamond %.0f replay %.0f neighbour %.0f tail/idle %.0f | diamond passes (warp level) %llu\n",
             (double)prof[10] / grid, (double)prof[11] / grid, (double)prof[12] / grid, (double)prof[13] / grid, (double)prof[14] / grid,
             (double)prof[15] / grid, (double)prof[16] / grid, prof[17]);
+    if (const char *path = getenv("XVCB_TZ_PROF_GROUPS")) {      // per-group records: cycles, jobs, samples, raster jobs
+      if (FILE *f = fopen(path, "w")) {
+        for (int g = 0; g < n_groups && g < kProfGroups; g++)
+          fprintf(f, "g %d %llu %llu %llu %llu\n", g, prof[24 + 4 * g], prof[24 + 4 * g + 1], prof[24 + 4 * g + 2], prof[24 + 4 * g + 3]);
+        for (int b = 0; b < grid && b < 256; b++) fprintf(f, "cta %d %llu\n", b, prof[24 + 4 * kProfGroups + b]);
+        fclose(f);
+      }
+    }
     fprintf(stderr, "[tz prof3] first staging, cycles/CTA by ordinal of the group in its CTA: 1st %.0f 2nd %.0f 3rd %.0f later %.0f | staged bytes/CTA %.0f groups %d\n",
             (double)prof[18] / grid, (double)prof[19] / grid, (double)prof[20] / grid, (double)prof[21] / grid, (double)prof[22] / grid, n_groups);
   }

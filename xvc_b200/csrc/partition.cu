@@ -80,28 +80,46 @@ __global__ void __launch_bounds__(kPaThreads) partition_kernel(PlaneView orig, P
   for (int m = tid; m < kPaVec; m += kPaThreads) s_rate[m] = pa_rate(m, lambda);
   __syncthreads();
 
-  // 2. T8 (64 * 1023 fits 16 bits; 12-bit content saturates at 65 535 where a block is off by > 1023 on average)
-  for (int p = tid; p < 64 * kPaVec; p += kPaThreads) {
-    const int b = p / kPaVec, m = p - b * kPaVec;
-    const int by = b >> 3, bx = b & 7, my = m / kPaSide, mx = m - my * kPaSide;
-    const int wx = bx * 8 + mx, sh = (wx & 1) << 4;
-    const uint32_t *w = s_win + (by * 8 + my) * kPaWinPitch + (wx >> 1);
+  // 2. T8 (64 * 1023 fits 16 bits; 12-bit content saturates at 65 535 where a block is off by > 1023 on average).
+  // A thread takes one block and one row of the vector window (17 vectors, my fixed): per block row the 12 window
+  // words and the 4 original words are loaded once and serve all 17 vectors -- even mx read the words as they
+  // are, odd mx the 11 words shifted by one sample (one funnel shift each, shared by the 8 odd vectors).  The
+  // per-lane 16-bit sums are folded every 4 rows (4 rows x 4 pairs x 4095 = 65 520 fits).
+  for (int p = tid; p < 64 * kPaSide; p += kPaThreads) {
+    const int b = p / kPaSide, my = p - b * kPaSide;
+    const int by = b >> 3, bx = b & 7;
+    const uint32_t *w = s_win + (by * 8 + my) * kPaWinPitch + bx * 4;
     const uint32_t *o = s_org + by * 8 * 32 + bx * 4;
-    uint32_t sad = 0;
+    uint32_t sad[kPaSide], acc[kPaSide];
+#pragma unroll
+    for (int m = 0; m < kPaSide; m++) sad[m] = acc[m] = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-      uint32_t acc = 0, prev = w[0];
+      uint32_t ww[12], sw[11], oo[4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const uint32_t nxt = w[c + 1];
-        const uint32_t v = __funnelshift_r(prev, nxt, sh), a = o[c];
-        acc += __vmaxu2(a, v) - __vminu2(a, v);
-        prev = nxt;
+      for (int c = 0; c < 12; c++) ww[c] = w[c];
+#pragma unroll
+      for (int c = 0; c < 4; c++) oo[c] = o[c];
+#pragma unroll
+      for (int c = 0; c < 11; c++) sw[c] = __funnelshift_r(ww[c], ww[c + 1], 16);
+#pragma unroll
+      for (int m = 0; m < kPaSide; m++) {
+        const int k = m >> 1;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const uint32_t v = (m & 1) ? sw[k + c] : ww[k + c];
+          acc[m] += __vmaxu2(oo[c], v) - __vminu2(oo[c], v);
+        }
       }
-      sad += (acc & 0xffffu) + (acc >> 16);
+      if ((r & 3) == 3) {
+#pragma unroll
+        for (int m = 0; m < kPaSide; m++) { sad[m] += (acc[m] & 0xffffu) + (acc[m] >> 16); acc[m] = 0; }
+      }
       w += kPaWinPitch; o += 32;
     }
-    s_t8[p] = (uint16_t)min(sad, 65535u);
+    uint16_t *t = s_t8 + b * kPaVec + my * kPaSide;
+#pragma unroll
+    for (int m = 0; m < kPaSide; m++) t[m] = (uint16_t)min(sad[m], 65535u);
   }
   __syncthreads();
 
