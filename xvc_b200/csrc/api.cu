@@ -1100,9 +1100,9 @@ int xvcb200_set_cus(xvcb200_ctx *ctx, const xvcb200_cu *cus, int n) {
   std::vector<int> ctu_first((size_t)n_ctus + 1, 0), by_ctu((size_t)n);
   for (int i = 0; i < n; i++)
     if (searched(i)) ctu_first[(size_t)((cus[i].y >> 6) * ctus_x + (cus[i].x >> 6)) + 1]++;
-  // A search group = a run of at most kGroupCus (32) searched CUs of one CTU (coding order): the unit the persistent search
+  // A search group = a run of at most kGroupCus (48: CTUs of more are halved) searched CUs of one CTU (coding order): the unit the persistent search
   // CTAs take from their counter.  Whole CTUs of 64 small CUs next to CTUs of one CU balance badly across 148 CTAs.
-  static const int kGroupCus = getenv("XVCB_GROUP_CUS") ? std::max(1, atoi(getenv("XVCB_GROUP_CUS"))) : 32;   // (the variable: experiments)
+  static const int kGroupCus = getenv("XVCB_GROUP_CUS") ? std::max(1, atoi(getenv("XVCB_GROUP_CUS"))) : 48;   // (the variable: experiments)
   int n_groups = 0;
   for (int t = 0; t < n_ctus; t++) {
     n_groups += (ctu_first[(size_t)t + 1] + kGroupCus - 1) / kGroupCus;

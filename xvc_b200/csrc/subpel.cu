@@ -148,8 +148,10 @@ __global__ void subpel_concat_kernel(int n, int *__restrict__ lists, int *__rest
 // shared memory of one team (bytes): reference window, horizontal plane, prediction plane, original.
 // Row pitches are chosen odd in 32-bit words so that threads working on consecutive rows hit
 // distinct banks.
-__host__ __device__ inline int subpel_team_bytes(int w, int h) {
-  const int samples = (h + 9) * (w + 10) + (h + 9) * (w + 2) + (h + 1) * (w + 2) + h * (w + 2);
+// `fused` (the one-warp teams): three intermediate planes and eight prediction planes, see the quarter-pel pass.
+__host__ __device__ inline int subpel_team_bytes(int w, int h, bool fused) {
+  const int nt = fused ? 3 : 1, np = fused ? 8 : 1;
+  const int samples = (h + 9) * (w + 10) + nt * (h + 9) * (w + 2) + np * (h + 1) * (w + 2) + h * (w + 2);
   return (2 * samples + 15) & ~15;
 }
 
@@ -188,7 +190,7 @@ template <int T> __device__ __forceinline__ void team_sync() {
 // rows so that small blocks still fill the team.
 template <int TW, int TH>
 __device__ __forceinline__ void satd_stacked(const int16_t *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
-                                             int w, int h, int tid, int nthreads, unsigned (&acc)[4]) {
+                                             int w, int h, int tid, int nthreads, unsigned (&acc)[4], int cstride) {
   const int ltx = 31 - __clz(w / TW);
   const int lper = ltx + (31 - __clz(h));      // log2(tile rows per candidate)
   const int total = nc << lper;
@@ -201,7 +203,7 @@ __device__ __forceinline__ void satd_stacked(const int16_t *org, int op, const S
     const int tx = (tile & ((1 << ltx) - 1)) * TW, ty = (tile >> ltx) * TH + r;
     const int ox = (offs >> (2 * c)) & 1, oy = (offs >> (2 * c + 1)) & 1;
     const int16_t *po = org + ty * op + tx;
-    const Sample *pq = pred + (ty + oy) * pp + tx + ox;
+    const Sample *pq = pred + c * cstride + (ty + oy) * pp + tx + ox;      // cstride: candidates in planes of their own
     int v[TW];
 #pragma unroll
     for (int i = 0; i < TW; i++) v[i] = active ? (int)po[i] - (int)pq[i] : 0;
@@ -240,11 +242,11 @@ __device__ __forceinline__ void satd_stacked(const int16_t *org, int op, const S
 // Tile choice by block shape (sample_metric.cc:322-387) for sides >= 8, then the team-wide sums.
 template <int T>
 __device__ __forceinline__ void satd_candidates(const int16_t *org, int op, const Sample *pred, int pp, unsigned offs, int nc,
-                                                int w, int h, int tid, unsigned *s_part, unsigned (&sum)[4]) {
+                                                int w, int h, int tid, unsigned *s_part, unsigned (&sum)[4], int cstride = 0) {
   unsigned acc[4] = {0, 0, 0, 0};
-  if (w > h) satd_stacked<16, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
-  else if (w < h) satd_stacked<8, 16>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
-  else satd_stacked<8, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc);
+  if (w > h) satd_stacked<16, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc, cstride);
+  else if (w < h) satd_stacked<8, 16>(org, op, pred, pp, offs, nc, w, h, tid, T, acc, cstride);
+  else satd_stacked<8, 8>(org, op, pred, pp, offs, nc, w, h, tid, T, acc, cstride);
 #pragma unroll
   for (int c = 0; c < 4; c++) acc[c] = warp_sum(acc[c]);
   if (T == 32) {
@@ -279,6 +281,11 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
   unsigned *sd = s_sd[T == 32 ? (threadIdx.x >> 5) : 0];
   const int tid = T == 32 ? (threadIdx.x & 31) : threadIdx.x;
   __shared__ int s_li;
+  __shared__ int s_taps[16][8];          // the luma filters: tasks of one fused pass use different phases per lane
+  if (T == 32) {
+    if (threadIdx.x < 128) s_taps[threadIdx.x >> 3][threadIdx.x & 7] = (int)c_luma_taps[threadIdx.x >> 3][threadIdx.x & 7];
+    __syncthreads();
+  }
   unsigned char *base = subpel_smem + (T == 32 ? (threadIdx.x >> 5) * team_bytes : 0);
   const int n_list = *count;
   const int maxv = (1 << bitdepth) - 1;
@@ -318,8 +325,9 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
     const int RP = w + 10, TP = w + 2, PP = w + 2, OP = w + 2;
     Sample *sref = reinterpret_cast<Sample *>(base);
     int16_t *tmp = reinterpret_cast<int16_t *>(sref + (h + 9) * RP);
-    Sample *pred = reinterpret_cast<Sample *>(tmp + (h + 9) * TP);
-    int16_t *org = reinterpret_cast<int16_t *>(pred + (h + 1) * PP);    // signed: also holds a weighted original
+    const int tstride = (h + 9) * TP, pstride = (h + 1) * PP;          // one intermediate / prediction plane
+    Sample *pred = reinterpret_cast<Sample *>(tmp + (T == 32 ? 3 : 1) * tstride);
+    int16_t *org = reinterpret_cast<int16_t *>(pred + (T == 32 ? 8 : 1) * pstride);    // signed: also holds a weighted original
     team_sync<T>();                      // the previous job of this team is done with the buffers
     // reference window: rows Y0-4 .. Y0+h+3, columns from the even sample at or left of X0-4
     // (aligned 32-bit loads; `co` = 0/1 is where X0-4 sits in the staged row), original block.
@@ -419,17 +427,19 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
     // 9 + 3j + k = quarter-pel candidate (x index j, y index k).
     int bx = fx0, by = fy0;
 #pragma unroll 1
-    for (int s = 0; s < 16; s++) {
+    for (int s = 0; s < (T == 32 ? 7 : 16); s++) {
       int kind = 0;            // 0 none, 1 horizontal, 2 vertical from the reference, 3 vertical from the intermediate
       int frac = 8, col0 = 0, row0 = 0, nrows = h, ncols = w, want_pred = 0, nc = 1, dst = 0;
       unsigned offs = 0;
       const Sample *pq = pred;
-      int ppitch = PP;
+      int ppitch = PP, cstride = 0;
       if (s == 0) { pq = sref + 4 * RP + 4 + co; ppitch = RP; }
       else if (s == 1) { kind = 2; col0 = 4; nrows = h + 1; nc = 2; offs = 2u << 2; dst = 1; }             // (0,-1) (0,1)
       else if (s == 2) { kind = 1; ncols = w + 1; want_pred = 1; row0 = 4; nc = 2; offs = 1u << 2; dst = 3; }  // (-1,0) (1,0)
       else if (s == 3) { kind = 3; nrows = h + 1; ncols = w + 1; nc = 4; offs = (1u << 2) | (2u << 4) | (3u << 6); dst = 5; }
-      else {
+      else if (T == 32 && s > 4) {      // one-warp teams: SATD of the quarter-pel candidates, four planes at a time
+        nc = 4; cstride = pstride; pq = pred + (s - 5) * 4 * pstride; dst = s == 5 ? 9 : 14;
+      } else {
         if (s == 4) {          // half-pel decisions in list order, then the quarter-pel pass around the winner
           team_sync<T>();
           consider(sd[0], fx0, fy0);
@@ -437,7 +447,62 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
 #pragma unroll
           for (int i = 0; i < 8; i++) consider(sd[1 + i], fx0 + hx[i] * 8, fy0 + hy[i] * 8);
           bx = best_x; by = best_y;
+          if (T == 32) {
+            // One-warp teams (blocks of <= 256 samples, most of them 8 x 8): a step of the list above keeps 8 or 16
+            // lanes busy on such a block.  Here the quarter-pel pass is three fused steps over planes of their own:
+            // all horizontal planes at once (x indices with a fractional column; on an integer row they also give
+            // candidate (j, 1) directly), all vertical passes at once (a task = candidate, column, run of 8 rows, each
+            // with its own filter phase), then (steps 5, 6) the SATD of the eight candidates four at a time.
+            const bool xint = (bx & 15) == 0, yint = (by & 15) == 0;
+            {
+              const int rows_n = h + 8, per = rows_n * (w >> 3), prow0 = 4 + ((by >> 4) - mfy);
+              for (int task = tid; task < (xint ? 2 : 3) * per; task += T) {
+                const int p = task / per, rem = task - p * per;
+                const int j = xint ? 2 * p : p;
+                const int xv = bx + (j - 1) * 4, ixr = (xv >> 4) - mfx;
+                const int run = rem / rows_n, row = rem - run * rows_n, c0 = run * 8;
+                const bool to_pred = yint && j != 1 && row >= prow0 && row < prow0 + h;
+                const int idx = 3 * j + 1, slot = idx < 4 ? idx : idx - 1;
+                int16_t *tp = tmp + p * tstride + row * TP + c0;
+                Sample *pp = pred + slot * pstride + (row - prow0) * PP + c0;
+                Taps8 taps;
+#pragma unroll
+                for (int k = 0; k < 8; k++) taps.t[k] = s_taps[xv & 15][k];
+                fir_run(sref + row * RP + co + ixr + 1 + c0, 1, 8, taps, [&](int r, int sum) {
+                  tp[r] = (int16_t)((sum + off1) >> sh1);
+                  if (to_pred) pp[r] = (Sample)clip3i((sum + 32) >> 6, 0, maxv);
+                });
+              }
+            }
+            team_sync<T>();
+            {
+              const int per = w * (h >> 3);
+              for (int task = tid; task < 8 * per; task += T) {
+                const int slot = task / per, rem = task - slot * per;
+                const int idx = slot < 4 ? slot : slot + 1, j = idx / 3, k = idx - 3 * j;
+                const int yv = by + (k - 1) * 4, iyr = (yv >> 4) - mfy;
+                if ((yv & 15) == 0) continue;                 // came out of the horizontal pass
+                const int xv = bx + (j - 1) * 4, ixr = (xv >> 4) - mfx;
+                const int run = rem / w, col = rem - run * w, r0 = run * 8;
+                Sample *pp = pred + slot * pstride + r0 * PP + col;
+                Taps8 taps;
+#pragma unroll
+                for (int t = 0; t < 8; t++) taps.t[t] = s_taps[yv & 15][t];
+                if ((xv & 15) != 0) {
+                  fir_run(tmp + (xint ? j >> 1 : j) * tstride + (iyr + 1 + r0) * TP + col, TP, 8, taps, [&](int r, int sum) {
+                    pp[r * PP] = (Sample)clip3i((int)(int16_t)((sum + off2) >> sh2), 0, maxv);
+                  });
+                } else {
+                  fir_run(sref + (iyr + 1 + r0) * RP + co + 4 + ixr + col, RP, 8, taps, [&](int r, int sum) {
+                    pp[r * PP] = (Sample)clip3i((int)(int16_t)((sum + 32) >> 6), 0, maxv);
+                  });
+                }
+              }
+            }
+            nc = 0;                                          // the planes are complete after the step's barrier; steps 5, 6: SATD
+          }
         }
+        if (T != 32) {
         const int q = s - 4, j = q >> 2, kk = q & 3;
         const int xv = bx + (j - 1) * 4;
         const int ixr = (xv >> 4) - mfx, fxj = xv & 15;
@@ -456,13 +521,14 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
           if (fyk == 0 || (j == 1 && k == 1)) continue;
           kind = fxj != 0 ? 3 : 2; frac = fyk; col0 = 4 + ixr; row0 = iyr + 1; dst = 9 + 3 * j + k;
         }
+        }
       }
       if (kind == 1) h_product(frac, col0, ncols, want_pred != 0, row0);
       else if (kind != 0) v_product(kind == 3, frac, col0, row0, nrows, ncols);
       team_sync<T>();
       if (nc > 0) {
         unsigned sum[4];
-        satd_candidates<T>(org, OP, pq, ppitch, offs, nc, w, h, tid, s_part, sum);
+        satd_candidates<T>(org, OP, pq, ppitch, offs, nc, w, h, tid, s_part, sum, cstride);
         if (tid == 0) {
 #pragma unroll
           for (int c = 0; c < 4; c++)
@@ -487,11 +553,11 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
   }
 }
 
-static int max_team_bytes(int max_area, int min_area) {
+static int max_team_bytes(int max_area, int min_area, bool fused) {
   int best = 0;
   for (int w = 8; w <= 64; w <<= 1)
     for (int h = 8; h <= 64; h <<= 1)
-      if (w * h <= max_area && w * h > min_area && subpel_team_bytes(w, h) > best) best = subpel_team_bytes(w, h);
+      if (w * h <= max_area && w * h > min_area && subpel_team_bytes(w, h, fused) > best) best = subpel_team_bytes(w, h, fused);
   return best;
 }
 
@@ -514,9 +580,9 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
     if (!c.num_sms) {
       int sms = 0;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      c.bytes0 = max_team_bytes(256, 0);
-      c.bytes1 = max_team_bytes(1024, 256);
-      c.bytes2 = max_team_bytes(4096, 1024);
+      c.bytes0 = max_team_bytes(256, 0, true);
+      c.bytes1 = max_team_bytes(1024, 256, false);
+      c.bytes2 = max_team_bytes(4096, 1024, false);
       cudaError_t e = cudaFuncSetAttribute(subpel_team_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * c.bytes0);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.bytes1);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(subpel_team_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.bytes2);
