@@ -337,7 +337,7 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
     wave_in = gop.as_wave_input(pics)
     waves = sharding.gop_waves(wave_in, done=(0,))
     n_frames = 1 + 16 * n_sub_gops
-    ctx = lib.Context(WIDTH, HEIGHT, BITDEPTH, num_slots=3 + 56, device=local_rank)
+    ctx = lib.Context(WIDTH, HEIGHT, BITDEPTH, num_slots=gop.GopEngine.FIRST_RING_SLOT + 56, device=local_rank)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -358,9 +358,28 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
     eng = gop.GopEngine(ctx, peers, rank, pics, lambda poc: dev_orig[poc], QP, BITDEPTH,
                         time_events=lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
     eng.load_done(0, make(0))          # the key picture is not coded here: its original stands in for its reconstruction
-    # warm-up (kernels, allocations), then the real run from the key picture again
+    # warm-up: the whole sequence once, untimed, pushes included -- the device buffers that grow with the CU count of the
+    # deeper temporal layers and the first transfer into every peer slot are one-time costs (measured: 35 of the 43 ms
+    # of the first 15-picture wave at N = 4) -- then the timed run from the key picture again (same pictures, same
+    # slots, same results).
+    def run_waves(times):
+        for wave in waves:
+            t0 = time.perf_counter()
+            eng.encode_many([poc for j, poc in enumerate(wave) if j % world == rank])
+            t1 = time.perf_counter()
+            for j, poc in enumerate(wave):
+                eng.share(poc, j % world)
+            t2 = time.perf_counter()
+            eng.fence()
+            times.append((time.perf_counter() - t0) * 1e3)
+            if os.environ.get("XVCB_GOP_DEBUG"):
+                print("[gop] rank %d wave of %d: enqueue %.2f ms, push calls %.2f ms, fence %.2f ms" %
+                      (rank, len(wave), (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3), file=sys.stderr)
+
     for p in warm_pocs:
         eng.encode(p)
+    ctx.sync()
+    run_waves([])
     ctx.sync()
     eng.events.clear()
     if dist is not None:
@@ -368,15 +387,7 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
     torch.cuda.synchronize()
     wave_ms = []
     t_all = time.perf_counter()
-    for wave in waves:
-        t0 = time.perf_counter()
-        for j, poc in enumerate(wave):
-            if j % world == rank:
-                eng.encode(poc)
-        for j, poc in enumerate(wave):
-            eng.share(poc, j % world)
-        eng.fence()
-        wave_ms.append((time.perf_counter() - t0) * 1e3)
+    run_waves(wave_ms)
     torch.cuda.synchronize()
     total_s = time.perf_counter() - t_all
     busy_ms = sum(a.elapsed_time(b) for _, a, b in eng.events)
@@ -404,9 +415,10 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
             "gpu_busy_frac": busy_ms / (world * total_s * 1e3), "gpu_idle_frac": 1.0 - busy_ms / (world * total_s * 1e3),
             "reconstructions_identical_on_all_ranks": len(set(digests)) == 1,
             "how": "ThreadEncoder's readiness rule as waves across sub-GOPs; picture j of a wave on GPU j mod N; per picture: device copy of the "
-                   "original, GPU partition pre-analysis (synchronous), set_cus, the whole step; finished reconstructions pushed to every GPU "
+                   "original, GPU partition pre-analysis (a rank's next picture ahead of the kernels of its current one), set_cus, the whole step; finished reconstructions pushed to every GPU "
                    "(copy engines over NVLink) and a rendezvous per wave (own pushes done, stream idle, barrier) before they are referenced; wall "
-                   "clock between barriers, max over ranks; busy = CUDA-event time of the pictures' work summed over GPUs",
+                   "clock between barriers, max over ranks; busy = CUDA-event time of the pictures' work summed over GPUs; the whole sequence runs "
+                   "once untimed before the timed pass (buffer growth, first transfer into every peer slot)",
             "search_range": "InterSearch::GetSearchRangeUniPred capped at 128 (it yields 256 for the anchor pictures; the search kernel stages +-128 windows)",
             "key_picture": "not coded: its original is uploaded as its reconstruction"}
 

@@ -3,6 +3,8 @@
 summaries kept under profiles/ (tracked):
 
   python tools/profile_summary.py <tag> <launches.csv> <full.ncu-rep> [bench.json]
+  (PROFILE_WORKLOAD = the bench workload the captures were taken on, default "encode";
+   PROFILE_LAUNCH_CMD / PROFILE_FULL_CMD = the commands, quoted in the summaries)
 
   profiles/<tag>_launches.csv / _launches_summary.md   per-kernel totals of the launch list
   profiles/<tag>_kernels_full.md                        key metrics of the `--set full` captures
@@ -81,7 +83,7 @@ def full(tag, rep, cmd):
             kernels.append(k)
     kernels.sort(key=lambda k: "tz_search" not in k[ik])
     with open(os.path.join(PROF, tag + "_kernels_full.md"), "w") as f:
-        f.write("# `ncu --set full` captures, %s\n\n`%s`\n(one 1080p picture of bench.py: 5478 CUs x 2 reference lists = 10956 search jobs; the .ncu-rep stays in gpurun_out/, scratch).\n\n" % (tag, cmd))
+        f.write("# `ncu --set full` captures, %s\n\n`%s`\n(one 1080p picture of bench.py, workload '%s'; the .ncu-rep stays in gpurun_out/, scratch).\n\n" % (tag, cmd, WORKLOAD))
         f.write("| metric | " + " | ".join("`%s`" % short(k[ik]) for k in kernels) + " |\n|---|" + "---|" * len(kernels) + "\n")
         for label, m in RAW:
             if m not in hdr:
@@ -94,13 +96,16 @@ def full(tag, rep, cmd):
     json.dump({"kernel": short(dom[ik]).replace("_kernel", ""), "dram_bytes_per_launch": traffic,
                "warp_instructions_per_launch": float(dom[hdr.index("smsp__inst_executed.sum")].replace(",", "")),
                "shared_wavefronts_per_launch": float(dom[hdr.index("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")].replace(",", "")),
+               "workload": WORKLOAD,
                "source": "profiles/%s_kernels_full.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" % tag},
               open(os.path.join(PROF, tag + "_traffic.json"), "w"))
 
 
+WORKLOAD = os.environ.get("PROFILE_WORKLOAD", "encode")
+
 if __name__ == "__main__":
     tag, lcsv, rep = sys.argv[1:4]
-    launches(tag, lcsv, "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3")
-    full(tag, rep, "ncu --set full --import-source on --clock-control none -k regex:'tz_search_kernel|subpel_team_kernel|tq_kernel<6,6>' -s 5 -c 5 python bench.py --steps 1 --warmup 3")
+    launches(tag, lcsv, os.environ.get("PROFILE_LAUNCH_CMD", "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --gop off --steps 2 --warmup 3"))
+    full(tag, rep, os.environ.get("PROFILE_FULL_CMD", "ncu --set full --import-source on --clock-control none -k regex:'tz_search|subpel_team|bi_search|partition_kernel|motion_compensate' -c 12 python bench.py --gop off --steps 1 --warmup 3"))
     if len(sys.argv) > 4:
         shutil.copy(sys.argv[4], os.path.join(PROF, tag + "_bench.json"))

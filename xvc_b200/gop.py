@@ -45,10 +45,13 @@ def as_wave_input(pics):
 
 
 class GopEngine:
-    """One rank of sharding.FrameParallelGop on a B200.  Slots: 0 original, 1 prediction, 2 levels, then a ring of
+    """One rank of sharding.FrameParallelGop on a B200.  Slots: 0 and 3 originals (alternating: the pre-analysis of a
+    rank's next picture runs ahead of the kernels of its current one), 1 prediction, 2 levels, then a ring of
     reconstruction slots indexed by POC (the same slot on every rank, so a pushed reconstruction lands in place; the
     ring is longer than the span of POCs alive at any time).  originals(poc) -> three device tensors (int16 views of
     the tight planes) resident before the timed region."""
+    FIRST_RING_SLOT = 4
+    ORIG_SLOTS = (0, 3)
 
     def __init__(self, ctx, peers, rank, pics, originals, qp, bitdepth, ring=56, max_range=128, time_events=None):
         self.ctx, self.peers, self.rank, self.originals, self.qp = ctx, peers, rank, originals, qp
@@ -59,10 +62,10 @@ class GopEngine:
         self.events = []
         g = ctx.geom
         self.views = [(int(g["margin_y"][c]), int(g["margin_x"][c]), int(g["height"][c]), int(g["width"][c])) for c in range(3)]
-        self.orig_t = [ctx.plane_tensor(0, c) for c in range(3)]
+        self.orig_t = {o: [ctx.plane_tensor(o, c) for c in range(3)] for o in self.ORIG_SLOTS}
 
     def slot_of(self, poc):
-        return 3 + poc % self.ring
+        return self.FIRST_RING_SLOT + poc % self.ring
 
     def load_done(self, poc, planes):
         self.ctx.upload(self.slot_of(poc), planes)
@@ -86,27 +89,55 @@ class GopEngine:
                 prm["search_range"][0, l, r] = min(self.max_range, workload.search_range_uni(poc, p))
         return prm, l0, l1
 
-    def encode(self, poc, pic_type=None, ref_pocs=None):
-        ctx = self.ctx
-        prm, l0, l1 = self.params(poc)
-        ev = self.busy() if self.busy else None
-        if ev:
-            ev[0].record()
-        for c, t in enumerate(self.originals(poc)):            # original picture: device copy into slot 0
+    def _begin(self, poc, oslot):
+        """Original picture -> slot oslot (device copy), pre-analysis enqueued: the partition from the content, against
+        the first list-0 picture, around the sequence's global motion."""
+        _, _, l0, _ = self.by_poc[poc]
+        for c, t in enumerate(self.originals(poc)):
             my, mx, h, w = self.views[c]
-            self.orig_t[c][my:my + h, mx:mx + w].copy_(t)
-        # partition from the content, against the first list-0 picture, around the sequence's global motion
+            self.orig_t[oslot][c][my:my + h, mx:mx + w].copy_(t)
         center = workload.true_motion(seq_index(poc), seq_index(l0[0]))
-        cus, _ = ctx.decide_partition(0, self.slot_of(l0[0]), float(np.sqrt(self.lam)), self.qp, center=center)
+        self.ctx.decide_partition_begin(oslot, self.slot_of(l0[0]), float(np.sqrt(self.lam)), self.qp, center=center)
+
+    def _end(self, poc):
+        """-> (CU array, predictors per (CU, list, reference picture): the pre-analysis vector scaled by POC distance)."""
+        _, _, l0, l1 = self.by_poc[poc]
+        cus, _ = self.ctx.decide_partition_end()
         mv0 = cus["mv"][:, 0, :].astype(np.int64)
         d0 = poc - l0[0]
-        cols = [(mv0 * (poc - p)) // d0 for p in tuple(l0) + tuple(l1)]       # predictors scaled by POC distance
-        ctx.set_cus(cus)
-        ctx.set_mv_predictors(np.ascontiguousarray(np.stack(cols, axis=1).astype(np.int32)))
-        ctx.encode_picture(prm, want_results=False)
-        if ev:
-            ev[1].record()
-            self.events.append((poc, ev[0], ev[1]))
+        cols = [(mv0 * (poc - p)) // d0 for p in tuple(l0) + tuple(l1)]
+        return cus, np.ascontiguousarray(np.stack(cols, axis=1).astype(np.int32))
+
+    def encode_many(self, pocs):
+        """This rank's pictures of one wave (independent of each other), pipelined: the pre-analysis kernel of picture
+        k+1 is enqueued ahead of the kernels of picture k, so the host turns its result into the CU array and the
+        predictors while picture k runs (the bench step's scheme)."""
+        ctx = self.ctx
+        if not pocs:
+            return
+        self._begin(pocs[0], self.ORIG_SLOTS[0])
+        nxt = self._end(pocs[0])
+        for i, poc in enumerate(pocs):
+            oslot = self.ORIG_SLOTS[i & 1]
+            prm, _, _ = self.params(poc)
+            prm["orig_slot"] = oslot
+            ev = self.busy() if self.busy else None
+            cus, mvp = nxt
+            ctx.set_cus(cus)
+            ctx.set_mv_predictors(mvp)
+            if ev:
+                ev[0].record()
+            if i + 1 < len(pocs):
+                self._begin(pocs[i + 1], self.ORIG_SLOTS[(i + 1) & 1])
+            ctx.encode_picture(prm, want_results=False)
+            if ev:
+                ev[1].record()
+                self.events.append((poc, ev[0], ev[1]))
+            if i + 1 < len(pocs):
+                nxt = self._end(pocs[i + 1])
+
+    def encode(self, poc, pic_type=None, ref_pocs=None):
+        self.encode_many([poc])
 
     def share(self, poc, owner):
         if owner == self.rank and self.peers is not None:
