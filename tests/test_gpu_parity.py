@@ -255,6 +255,34 @@ def test_me_search_far_predictors(oracle):
         assert np.array_equal(rg[f], ro[f]), f
 
 
+def test_me_search_recentred_raster(oracle):
+    """A start point other than the predictor re-centres the raster window (DetermineMinMaxMv around the best
+    start, inter_tz_search.cc:121-125): with a predictor far from the content's motion the zero vector wins the
+    start, the first pass ends far out and the scan window lies outside the box staged around the predictors'
+    windows -- the kernel stages a second box for those jobs (and scans from global memory what does not fit:
+    the second list's predictors are scattered so that the windows of a CTU cannot share one box)."""
+    width, height, bd = 448, 256, 10
+    cur, r0, r1 = common.frames(width, height, bd, 118, "synth")
+    lam = workload.lambda_for_qp(32)
+    ctx = _ctx(width, height, bd, cur, r0, r1)
+    rng = np.random.default_rng(119)
+    cus = workload.make_partition(width, height, seed=9, min_size=8)
+    ctx.set_cus(cus)
+    jobs = common.me_jobs(cus, rng, 2, (128, 96), 0, slots=(1, 2))
+    jobs["mvp"][0::2] = (-1500, -900)                                        # one far predictor for every CU
+    jobs["mvp"][1::2] = rng.integers(-2400, 2401, size=(len(cus), 2))         # scattered far predictors
+    jobs["prev"] = 0
+    rg = ctx.me_search(0, jobs, np.sqrt(lam))
+    ojobs = jobs.copy()
+    ojobs["ref_slot"] = 0
+    ro = oracle.me_search(Picture(width, height, 0, cur), common.oracle_refs(oracle, width, height, r0, r1), bd, cus,
+                          ojobs, np.sqrt(lam))
+    for f in ("mv_fullpel", "cost_fullpel", "num_sad", "mv", "dist", "cost"):
+        assert np.array_equal(rg[f], ro[f]), f
+    scanned = ro["num_sad"] > 1000                                           # the raster scan ran
+    assert scanned[0::2].mean() > 0.3 and scanned[1::2].mean() > 0.3
+
+
 def test_full_search(oracle):
     width, height, bd = 136, 72, 10
     cur, r0, r1 = common.frames(width, height, bd, 116)

@@ -155,11 +155,14 @@ __host__ __device__ inline int subpel_team_bytes(int w, int h, bool fused) {
   return (2 * samples + 15) & ~15;
 }
 
-struct Taps8 { int t[8]; };
+// The eight taps of a phase as four pairs of int8 (every tap of kLumaFilterHighPrec lies in -11 .. 63), the second
+// operand of IDP.2A: t[j] = tap 2j | tap 2j+1 << 8.
+struct Taps8 { int t[4]; };
+__device__ __forceinline__ int pack_taps(int a, int b) { return (a & 0xff) | ((b & 0xff) << 8); }
 __device__ __forceinline__ Taps8 luma_taps(int frac) {
   Taps8 r;
 #pragma unroll
-  for (int k = 0; k < 8; k++) r.t[k] = (int)c_luma_taps[frac][k];
+  for (int k = 0; k < 4; k++) r.t[k] = pack_taps((int)c_luma_taps[frac][2 * k], (int)c_luma_taps[frac][2 * k + 1]);
   return r;
 }
 
@@ -167,15 +170,20 @@ __device__ __forceinline__ Taps8 luma_taps(int frac) {
 // sum_k taps[k] * in[(r + k) * step].  Reads 16 inputs (the last one only matters for count 9).
 template <typename ST, class Emit>
 __device__ __forceinline__ void fir_run(const ST *in, int step, int count, const Taps8 &taps, Emit emit) {
+  // inputs are 16-bit (samples, or the signed 14-bit intermediate): neighbours packed in pairs (one PRMT each), then
+  // two multiply-adds per instruction (IDP.2A: a signed 16-bit pair times a signed 8-bit pair) -- 4 instead of 8 per output
   int win[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) win[k] = (int)in[k * step];
+  int pr[15];
+#pragma unroll
+  for (int k = 0; k < 15; k++) pr[k] = (int)__byte_perm((unsigned)win[k], (unsigned)win[k + 1], 0x5410);
 #pragma unroll
   for (int r = 0; r < 9; r++) {
     if (r < count) {
       int sum = 0;
 #pragma unroll
-      for (int k = 0; k < 8; k++) sum += win[r + k] * taps.t[k];
+      for (int k = 0; k < 4; k++) sum = __dp2a_lo(pr[r + 2 * k], taps.t[k], sum);
       emit(r, sum);
     }
   }
@@ -228,7 +236,7 @@ __device__ __forceinline__ void satd_stacked(const int16_t *org, int op, const S
     }
     int s = 0;
 #pragma unroll
-    for (int i = 0; i < TW; i++) s += abs(v[i]);
+    for (int i = 0; i < TW; i++) s = (int)__sad(v[i], 0, (unsigned)s);      // |v| + s in one instruction
 #pragma unroll
     for (int o = 1; o < TH; o <<= 1) s += __shfl_xor_sync(XVCB_FULL, s, o);
     if (active && r == 0) {
@@ -281,9 +289,11 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
   unsigned *sd = s_sd[T == 32 ? (threadIdx.x >> 5) : 0];
   const int tid = T == 32 ? (threadIdx.x & 31) : threadIdx.x;
   __shared__ int s_li;
-  __shared__ int s_taps[16][8];          // the luma filters: tasks of one fused pass use different phases per lane
+  __shared__ int s_taps[16][4];          // the luma filters as IDP.2A operands: tasks of one fused pass use different phases per lane
   if (T == 32) {
-    if (threadIdx.x < 128) s_taps[threadIdx.x >> 3][threadIdx.x & 7] = (int)c_luma_taps[threadIdx.x >> 3][threadIdx.x & 7];
+    if (threadIdx.x < 64)
+      s_taps[threadIdx.x >> 2][threadIdx.x & 3] = pack_taps((int)c_luma_taps[threadIdx.x >> 2][2 * (threadIdx.x & 3)],
+                                                            (int)c_luma_taps[threadIdx.x >> 2][2 * (threadIdx.x & 3) + 1]);
     __syncthreads();
   }
   unsigned char *base = subpel_smem + (T == 32 ? (threadIdx.x >> 5) * team_bytes : 0);
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
                 Sample *pp = pred + slot * pstride + (row - prow0) * PP + c0;
                 Taps8 taps;
 #pragma unroll
-                for (int k = 0; k < 8; k++) taps.t[k] = s_taps[xv & 15][k];
+                for (int k = 0; k < 4; k++) taps.t[k] = s_taps[xv & 15][k];
                 fir_run(sref + row * RP + co + ixr + 1 + c0, 1, 8, taps, [&](int r, int sum) {
                   tp[r] = (int16_t)((sum + off1) >> sh1);
                   if (to_pred) pp[r] = (Sample)clip3i((sum + 32) >> 6, 0, maxv);
@@ -487,7 +497,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
                 Sample *pp = pred + slot * pstride + r0 * PP + col;
                 Taps8 taps;
 #pragma unroll
-                for (int t = 0; t < 8; t++) taps.t[t] = s_taps[yv & 15][t];
+                for (int t = 0; t < 4; t++) taps.t[t] = s_taps[yv & 15][t];
                 if ((xv & 15) != 0) {
                   fir_run(tmp + (xint ? j >> 1 : j) * tstride + (iyr + 1 + r0) * TP + col, TP, 8, taps, [&](int r, int sum) {
                     pp[r * PP] = (Sample)clip3i((int)(int16_t)((sum + off2) >> sh2), 0, maxv);
