@@ -108,13 +108,23 @@ __global__ void __launch_bounds__(128) subpel_generic_kernel(const xvcb200_cu *_
 //        one at a time, so the short ones fill the tail.
 constexpr int kSubpelLists = 15;
 __global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, int n,
+                                       const PlaneView *__restrict__ ref_planes, const xvcb200_me_result *__restrict__ res,
                                        int *__restrict__ lists, int *__restrict__ counts) {
   const int ji = blockIdx.x * blockDim.x + threadIdx.x;
   if (ji >= n || jobs[ji].search_range == 0) return;       // range 0: a column that is not searched (see MePipe)
-  const xvcb200_cu cu = cus[jobs[ji].cu];
+  const xvcb200_me_job job = jobs[ji];
+  const xvcb200_cu cu = cus[job.cu];
   const int area = (int)cu.w * cu.h;
+  // every candidate lies within +-12/16 of the full-pel vector: where ClipMv would move one of them the job goes
+  // to the generic kernel (decided here, so that kernel runs beside the team kernels instead of after them)
+  const PlaneView ref = ref_planes[job.ref_slot];
+  const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;
+  int ax = fx0 - 12, ay = fy0 - 12, bx = fx0 + 12, by = fy0 + 12;
+  clip_mv(cu.x, cu.y, ref.width, ref.height, ax, ay);
+  clip_mv(cu.x, cu.y, ref.width, ref.height, bx, by);
+  const bool clipped = ax != fx0 - 12 || ay != fy0 - 12 || bx != fx0 + 12 || by != fy0 + 12;
   int seg;
-  if (cu.w < 8 || cu.h < 8) seg = 2;
+  if (cu.w < 8 || cu.h < 8 || clipped) seg = 2;
   else if (area > 256) seg = area == 4096 ? 1 : (area == 2048 ? 11 : (area == 1024 ? 0 : 12));
   else seg = 3 + (28 - __clz((int)cu.w)) * 3 + (28 - __clz((int)cu.h));     // (log2 w - 3) * 3 + (log2 h - 3): 0,1,2,3,4,6
   lists[(size_t)seg * n + atomicAdd(&counts[seg], 1)] = ji;
@@ -280,8 +290,7 @@ __device__ __forceinline__ void satd_candidates(const int16_t *org, int op, cons
 template <int T>
 __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_team_kernel(
     const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs, const int *__restrict__ list,
-    const int *__restrict__ count, int *__restrict__ fetch, int *__restrict__ slow_list, int *__restrict__ slow_count,
-    int team_bytes, int bitdepth,
+    const int *__restrict__ count, int *__restrict__ fetch, int team_bytes, int bitdepth,
     uint32_t lambda, PlaneView orig, const PlaneView *__restrict__ ref_planes, xvcb200_me_result *__restrict__ res) {
   extern __shared__ __align__(16) unsigned char subpel_smem[];
   __shared__ unsigned s_part[T == 32 ? 4 : (T / 32) * 4];
@@ -322,15 +331,7 @@ __global__ void __launch_bounds__(T == 32 ? 128 : T, T == 32 ? 6 : 1) subpel_tea
     const int w = cu.w, h = cu.h;
     const int mfx = res[ji].mv_fullpel[0], mfy = res[ji].mv_fullpel[1];
     const int fx0 = mfx * 16, fy0 = mfy * 16;
-    {   // every candidate lies within +-12/16 of the full-pel vector: ClipMv must leave that range alone
-      int ax = fx0 - 12, ay = fy0 - 12, bx = fx0 + 12, by = fy0 + 12;
-      clip_mv(cu.x, cu.y, ref.width, ref.height, ax, ay);
-      clip_mv(cu.x, cu.y, ref.width, ref.height, bx, by);
-      if (ax != fx0 - 12 || ay != fy0 - 12 || bx != fx0 + 12 || by != fy0 + 12) {
-        if (tid == 0) slow_list[atomicAdd(slow_count, 1)] = ji;
-        continue;
-      }
-    }
+    // (jobs whose candidates ClipMv would move were handed to the generic kernel by the classification)
     const bool fullpel_only = (cu.flags & XVCB200_CU_FULLPEL_MV) != 0;
     const int RP = w + 10, TP = w + 2, PP = w + 2, OP = w + 2;
     Sample *sref = reinterpret_cast<Sample *>(base);
@@ -613,34 +614,38 @@ cudaError_t launch_subpel_search(cudaStream_t s, const xvcb200_cu *d_cus, const 
   cudaError_t e = cudaMemsetAsync(counts, 0, 20 * sizeof(int), s);      // list lengths [0..14] + the three fetch counters [16..18]
   if (e != cudaSuccess) return e;
   g_launch_count += 6;
-  subpel_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, d_jobs, n, d_lists, counts);
+  subpel_classify_kernel<<<(n + 255) / 256, 256, 0, s>>>(d_cus, d_jobs, n, d_ref_planes, d_res, d_lists, counts);
   subpel_concat_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, d_lists, counts);
   int *slow = d_lists + 2 * (size_t)n;
-  // The three size classes are independent persistent grids, each sized to fill the register
-  // file on its own; on separate streams the next class's CTAs move in as soon as CTAs of the
-  // previous one retire (its tail) instead of after its last CTA.  The generic kernel consumes
-  // the list of jobs all three hand over, so it joins them.
+  // The three size classes and the generic kernel (4-wide blocks, vectors at the picture border) are independent
+  // persistent grids, each sized to fill the register file on its own; on separate streams the next class's CTAs
+  // move in as soon as CTAs of the previous one retire (its tail) instead of after its last CTA.
   const bool fork = n_side >= 2;
-  cudaStream_t s1 = fork ? side[0] : s, s2 = fork ? side[1] : s;
+  cudaStream_t s1 = fork ? side[0] : s, s2 = fork ? side[1] : s, s3 = n_side >= 3 ? side[2] : s;
   if (fork) {
     cudaEventRecord(fork_ev, s);
     cudaStreamWaitEvent(s1, fork_ev, 0);
     cudaStreamWaitEvent(s2, fork_ev, 0);
+    if (n_side >= 3) cudaStreamWaitEvent(s3, fork_ev, 0);
   }
   // persistent grids: as many CTAs as fit, each strides over its class list (largest blocks first)
-  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + 13 * (size_t)n, counts + 13, counts + 16, slow, counts + 2,
+  subpel_team_kernel<256><<<num_sms * occ2, 256, bytes2, s>>>(d_cus, d_jobs, d_lists + 13 * (size_t)n, counts + 13, counts + 16,
                                                          bytes2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s1>>>(d_cus, d_jobs, d_lists + 14 * (size_t)n, counts + 14, counts + 17, slow, counts + 2, bytes1, bitdepth,
+  subpel_team_kernel<128><<<num_sms * occ1, 128, bytes1, s1>>>(d_cus, d_jobs, d_lists + 14 * (size_t)n, counts + 14, counts + 17, bytes1, bitdepth,
                                                            lambda_me, orig, d_ref_planes, d_res);
-  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s2>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, counts + 18, slow,
-                                                              counts + 2, bytes0, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_team_kernel<32><<<num_sms * occ0, 128, 4 * bytes0, s2>>>(d_cus, d_jobs, d_lists + 10 * (size_t)n, counts + 10, counts + 18,
+                                                              bytes0, bitdepth, lambda_me, orig, d_ref_planes, d_res);
+  subpel_generic_kernel<<<num_sms * 2, 128, 0, s3>>>(d_cus, d_jobs, slow, counts + 2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
   if (fork) {
     cudaEventRecord(side_ev[0], s1);
     cudaEventRecord(side_ev[1], s2);
     cudaStreamWaitEvent(s, side_ev[0], 0);
     cudaStreamWaitEvent(s, side_ev[1], 0);
+    if (n_side >= 3) {
+      cudaEventRecord(side_ev[2], s3);
+      cudaStreamWaitEvent(s, side_ev[2], 0);
+    }
   }
-  subpel_generic_kernel<<<num_sms * 4, 128, 0, s>>>(d_cus, d_jobs, slow, counts + 2, bitdepth, lambda_me, orig, d_ref_planes, d_res);
   return cudaGetLastError();
 }
 
