@@ -434,7 +434,7 @@ struct CtxExtra {           // host-side state that is not needed by kernels
   int16_t *d_worig = nullptr;
   std::vector<CUtensorMap> luma_tmaps;         // per slot: [2 * slot + 0 / 1] = narrow / wide box over the padded luma plane (full search)
   xvcb200_tu_mode *d_tu_modes = nullptr; int tu_modes_cap = 0; bool tu_modes_set = false;   // xvcb200_set_tu_modes
-  uint8_t *d_part = nullptr, *h_part = nullptr; cudaEvent_t part_ev = nullptr; bool part_pending = false;   // xvcb200_decide_partition_begin / _end
+  uint8_t *d_part = nullptr, *h_part = nullptr; cudaEvent_t part_ev = nullptr, part_k_ev = nullptr; cudaStream_t part_stream = nullptr; bool part_pending = false;   // xvcb200_decide_partition_begin / _end
   int32_t *d_cu_map2 = nullptr;                // 4x4 CU map of the secondary (chroma) tree (xvcb200_deblock_picture_ext)
   int32_t *d_mvp = nullptr; int mvp_cap = 0;   // xvcb200_set_mv_predictors: [cu][column][2]
   int mvp_cols = 0;                            // 0: none given for the current CU array
@@ -645,7 +645,8 @@ void xvcb200_ctx_destroy(xvcb200_ctx *ctx) {
   cudaFree(c->ex.d_subpel_lists); cudaFree(c->ex.d_pool);
   cudaFree(c->ex.d_job_index); cudaFree(c->ex.d_groups); cudaFree(c->ex.d_tz_states); cudaFree(c->ex.d_counter);
   for (int b = 0; b < 2; b++) { if (c->ex.h_mvp[b]) cudaFreeHost(c->ex.h_mvp[b]); if (c->ex.mvp_ev[b]) cudaEventDestroy(c->ex.mvp_ev[b]); }
-  cudaFree(c->ex.d_part); if (c->ex.h_part) cudaFreeHost(c->ex.h_part); if (c->ex.part_ev) cudaEventDestroy(c->ex.part_ev);
+  cudaFree(c->ex.d_part); if (c->ex.h_part) cudaFreeHost(c->ex.h_part); if (c->ex.part_ev) cudaEventDestroy(c->ex.part_ev); if (c->ex.part_k_ev) cudaEventDestroy(c->ex.part_k_ev);
+  if (c->ex.part_stream) { cudaStreamSynchronize(c->ex.part_stream); cudaStreamDestroy(c->ex.part_stream); }
   cudaFree(c->ex.d_cu_map2); cudaFree(c->ex.d_tu_modes); cudaFree(c->ex.d_mvp); cudaFree(c->ex.d_me_state); cudaFree(c->ex.d_bi_jobs); cudaFree(c->ex.d_bi_res); cudaFree(c->ex.d_worig);
   cudaFree(c->ex.d_luma_views); cudaFree(c->ex.d_jobs); cudaFree(c->ex.d_me); cudaFree(c->ex.d_tu); cudaFree(c->ex.d_affine); cudaFree(c->ex.d_lic);
   for (auto &e : c->ex.ev) if (e) cudaEventDestroy(e);
@@ -1600,8 +1601,13 @@ int xvcb200_decide_partition_begin(xvcb200_ctx *ctx, const xvcb200_partition_par
   if (!c->ex.d_part) {
     if (!c->check(cudaMalloc(&c->ex.d_part, total), "cudaMalloc(partition)") ||
         !c->check(cudaHostAlloc(&c->ex.h_part, total, cudaHostAllocDefault), "cudaHostAlloc(partition)") ||
-        !c->check(cudaEventCreateWithFlags(&c->ex.part_ev, cudaEventDisableTiming), "cudaEventCreate"))
+        !c->check(cudaEventCreateWithFlags(&c->ex.part_ev, cudaEventDisableTiming), "cudaEventCreate") ||
+        !c->check(cudaEventCreateWithFlags(&c->ex.part_k_ev, cudaEventDisableTiming), "cudaEventCreate") ||
+        !c->check(cudaStreamCreateWithFlags(&c->ex.part_stream, cudaStreamNonBlocking), "cudaStreamCreate(partition)"))
       return c->status;
+  } else {
+    // the kernel rewrites d_part: not before the previous result has left it (a caller that skipped _end)
+    c->check(cudaStreamWaitEvent(c->stream, c->ex.part_ev, 0), "cudaStreamWaitEvent");
   }
   join_upload_slot(c, prm->orig_slot);
   join_upload_slot(c, prm->ref_slot);
@@ -1614,8 +1620,12 @@ int xvcb200_decide_partition_begin(xvcb200_ctx *ctx, const xvcb200_partition_par
   c->check(launch_partition(c->stream, c->plane(prm->orig_slot, 0), c->plane(prm->ref_slot, 0), prm->center[0], prm->center[1], lam,
                             (int)(((unsigned long long)lam * bits_cu) >> 16), (int)(((unsigned long long)lam * bits_split) >> 16), prm->qp,
                             d_cus, d_ncu, d_spl, d_nsp), "partition");
-  c->check(cudaMemcpyAsync(c->ex.h_part, d, total, cudaMemcpyDeviceToHost, c->stream), "partition results");
-  c->check(cudaEventRecord(c->ex.part_ev, c->stream), "cudaEventRecord");
+  // the result travels on a copy stream of its own behind the kernel: on the context stream the 1 MB transfer
+  // (~40 us of PCIe) would hold back the kernels of the picture enqueued next
+  c->check(cudaEventRecord(c->ex.part_k_ev, c->stream), "cudaEventRecord");
+  c->check(cudaStreamWaitEvent(c->ex.part_stream, c->ex.part_k_ev, 0), "cudaStreamWaitEvent");
+  c->check(cudaMemcpyAsync(c->ex.h_part, d, total, cudaMemcpyDeviceToHost, c->ex.part_stream), "partition results");
+  c->check(cudaEventRecord(c->ex.part_ev, c->ex.part_stream), "cudaEventRecord");
   c->ex.part_pending = true;
   return c->status;
 }

@@ -111,23 +111,32 @@ __global__ void subpel_classify_kernel(const xvcb200_cu *__restrict__ cus, const
                                        const PlaneView *__restrict__ ref_planes, const xvcb200_me_result *__restrict__ res,
                                        int *__restrict__ lists, int *__restrict__ counts) {
   const int ji = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ji >= n || jobs[ji].search_range == 0) return;       // range 0: a column that is not searched (see MePipe)
-  const xvcb200_me_job job = jobs[ji];
-  const xvcb200_cu cu = cus[job.cu];
-  const int area = (int)cu.w * cu.h;
-  // every candidate lies within +-12/16 of the full-pel vector: where ClipMv would move one of them the job goes
-  // to the generic kernel (decided here, so that kernel runs beside the team kernels instead of after them)
-  const PlaneView ref = ref_planes[job.ref_slot];
-  const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;
-  int ax = fx0 - 12, ay = fy0 - 12, bx = fx0 + 12, by = fy0 + 12;
-  clip_mv(cu.x, cu.y, ref.width, ref.height, ax, ay);
-  clip_mv(cu.x, cu.y, ref.width, ref.height, bx, by);
-  const bool clipped = ax != fx0 - 12 || ay != fy0 - 12 || bx != fx0 + 12 || by != fy0 + 12;
-  int seg;
-  if (cu.w < 8 || cu.h < 8 || clipped) seg = 2;
-  else if (area > 256) seg = area == 4096 ? 1 : (area == 2048 ? 11 : (area == 1024 ? 0 : 12));
-  else seg = 3 + (28 - __clz((int)cu.w)) * 3 + (28 - __clz((int)cu.h));     // (log2 w - 3) * 3 + (log2 h - 3): 0,1,2,3,4,6
-  lists[(size_t)seg * n + atomicAdd(&counts[seg], 1)] = ji;
+  int seg = -1;
+  if (ji < n && jobs[ji].search_range != 0) {                // range 0: a column that is not searched (see MePipe)
+    const xvcb200_me_job job = jobs[ji];
+    const xvcb200_cu cu = cus[job.cu];
+    const int area = (int)cu.w * cu.h;
+    // every candidate lies within +-12/16 of the full-pel vector: where ClipMv would move one of them the job goes
+    // to the generic kernel (decided here, so that kernel runs beside the team kernels instead of after them)
+    const PlaneView ref = ref_planes[job.ref_slot];
+    const int fx0 = res[ji].mv_fullpel[0] * 16, fy0 = res[ji].mv_fullpel[1] * 16;
+    int ax = fx0 - 12, ay = fy0 - 12, bx = fx0 + 12, by = fy0 + 12;
+    clip_mv(cu.x, cu.y, ref.width, ref.height, ax, ay);
+    clip_mv(cu.x, cu.y, ref.width, ref.height, bx, by);
+    const bool clipped = ax != fx0 - 12 || ay != fy0 - 12 || bx != fx0 + 12 || by != fy0 + 12;
+    if (cu.w < 8 || cu.h < 8 || clipped) seg = 2;
+    else if (area > 256) seg = area == 4096 ? 1 : (area == 2048 ? 11 : (area == 1024 ? 0 : 12));
+    else seg = 3 + (28 - __clz((int)cu.w)) * 3 + (28 - __clz((int)cu.h));     // (log2 w - 3) * 3 + (log2 h - 3): 0,1,2,3,4,6
+  }
+  // one atomic per (warp, class): most jobs of a picture fall into two or three classes
+  const unsigned peers = __match_any_sync(XVCB_FULL, seg);
+  if (seg >= 0) {
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&counts[seg], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    lists[(size_t)seg * n + base + __popc(peers & ((1u << lane) - 1))] = ji;
+  }
 }
 
 __global__ void subpel_concat_kernel(int n, int *__restrict__ lists, int *__restrict__ counts) {
