@@ -1777,7 +1777,8 @@ int xvcb200_encode_picture(xvcb200_ctx *ctx, const xvcb200_picture_params *prm, 
         for (int k = 0; k < 2; k++) fs_maps.m[l * P.R[0] + r][k] = c->ex.luma_tmaps[2 * (size_t)P.ref_slot[l][r] + k];
     for (int it = 0; it < P.bi_iterations; it++) {
       c->check(launch_bi_search(c->stream, c->d_cus, P, it, c->ex.d_jobs, c->ex.d_me, c->ex.d_me_state, orig, c->ex.d_luma_views, worig,
-                                fs_maps, c->geom.margin_x[0], c->geom.margin_y[0], c->ex.d_bi_jobs, c->ex.d_bi_res), "bi_search");
+                                fs_maps, c->geom.margin_x[0], c->geom.margin_y[0], c->ex.d_bi_jobs, c->ex.d_bi_res,
+                                c->ex.n_side >= 1 ? c->ex.side[0] : nullptr, c->ex.n_side >= 1 ? c->ex.side_ev[0] : nullptr, c->ex.fork_ev), "bi_search");
       c->check(launch_subpel_search(c->stream, c->d_cus, c->ex.d_bi_jobs, nbj, c->bitdepth, P.lambda, worig, c->ex.d_luma_views,
                                     c->ex.d_bi_res, c->ex.d_subpel_lists, c->ex.side, c->ex.side_ev, c->ex.n_side, c->ex.fork_ev),
                "subpel_search(bi)");

@@ -239,29 +239,37 @@ constexpr int kFsOrgPitch16 = 2 * kFsOrgPitch;         // the packed original ad
 
 struct FsGeom { int nx, ny, lox, loy, ox0, wp, wrows, wide, mvpx, mvpy, ref_slot; };
 
-constexpr int kBiThreads = 192;
 constexpr int kFsCands = (2 * kFsBiRange + 1) * (2 * kFsBiRange + 1);
 
+// Two size classes, each a launch over all CUs (a CTA whose CU belongs to the other class leaves at once): the
+// CTA's life is a chain of dependent global loads and barriers, so what counts is how many CTAs an SM holds.
+// Blocks up to 16 x 16 (most CUs of a picture) need 6 KB of shared memory and 96 threads (a thread per candidate),
+// larger ones 46 KB and 352 threads (a thread per candidate and quarter of the rows); the two launches run side by
+// side on two streams (the small class alone is issue bound, the large one latency bound).
+template <int MAXD, int kBiThreads>
 __global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu *__restrict__ cus, const __grid_constant__ MePipe P, int iteration,
                                                         const xvcb200_me_job *__restrict__ jobs, const xvcb200_me_result *__restrict__ res,
                                                         MeCuState *__restrict__ state, PlaneView orig, const PlaneView *__restrict__ luma,
                                                         PlaneView worig, const __grid_constant__ FsTensorMaps maps, int margin_x,
                                                         int margin_y, xvcb200_me_job *__restrict__ bi_jobs,
                                                         xvcb200_me_result *__restrict__ bi_res) {
-  // interpolation scratch (64 x 71 int16) + prediction (64 x 64); the shifted window re-uses it afterwards
-  __shared__ __align__(16) uint16_t s_scratch[64 * 71 + 64 * 64];
-  __shared__ __align__(128) uint16_t s_win[2][kFsWinRows * kFsBoxWide];
-  __shared__ uint32_t s_org[32 * kFsOrgPitch];
+  // interpolation scratch (MAXD x (MAXD + 7) int16) + prediction (MAXD x MAXD); the shifted window re-uses it afterwards
+  constexpr int kBox = MAXD <= 16 ? kFsBoxNarrow : kFsBoxWide, kWinRows = MAXD + 2 * kFsBiRange;
+  constexpr int kScratch = MAXD * (MAXD + 7) + MAXD * MAXD > kWinRows * kBox ? MAXD * (MAXD + 7) + MAXD * MAXD : kWinRows * kBox;
+  __shared__ __align__(16) uint16_t s_scratch[kScratch];
+  __shared__ __align__(128) uint16_t s_win[2][kWinRows * kBox];
+  __shared__ uint32_t s_org[(MAXD <= 16 ? 8 : MAXD / 2) * kFsOrgPitch];
   __shared__ unsigned long long s_best;
   __shared__ uint2 s_cand[kFsCands];
   __shared__ uint32_t s_sad[kFsCands];
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ int s_sl;
   int16_t *tmp = reinterpret_cast<int16_t *>(s_scratch);
-  Sample *pred = s_scratch + 64 * 71;
+  Sample *pred = s_scratch + MAXD * (MAXD + 7);
   uint16_t *s_shift = s_scratch;
-  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
+  const int i = blockIdx.x, tid = threadIdx.x;
   const xvcb200_cu cu = cus[i];
+  if ((cu.w <= 16 && cu.h <= 16) != (MAXD <= 16)) return;            // the other class's CU
   MeCuState *st = &state[i];
   const bool run = st->active && !st->bi_done && st->uni_ref[0] >= 0 && st->uni_ref[1] >= 0;
   const int w = cu.w, h = cu.h;
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu 
     int mx = st->bi_mv[other][0], my = st->bi_mv[other][1];
     clip_mv(cu.x, cu.y, rp.width, rp.height, mx, my);
     const Sample *r = rp.base + (cu.y + (my >> 4)) * rp.pitch + cu.x + (mx >> 4);
-    interp_cta<false, 8>(w, h, P.bitdepth, mx & 15, my & 15, r, rp.pitch, pred, 64, tmp, tid, kBiThreads);
+    interp_cta<false, 8>(w, h, P.bitdepth, mx & 15, my & 15, r, rp.pitch, pred, MAXD, tmp, tid, kBiThreads);
   }
   __syncthreads();
   const int bias = 1 << P.bitdepth;
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu 
     uint16_t *org16 = reinterpret_cast<uint16_t *>(s_org);
     for (int k = tid; k < w * h; k += kBiThreads) {
       const int y = k >> lw, x = k & (w - 1);
-      const int v = 2 * (int)orig.base[(cu.y + y) * orig.pitch + cu.x + x] - (int)pred[y * 64 + x];
+      const int v = 2 * (int)orig.base[(cu.y + y) * orig.pitch + cu.x + x] - (int)pred[y * MAXD + x];
       dst[(cu.y + y) * worig.pitch + cu.x + x] = (int16_t)v;
       if (!(y & (rstep - 1))) org16[(y >> (rstep - 1)) * kFsOrgPitch16 + x] = (uint16_t)(v + bias);
     }
@@ -359,6 +367,7 @@ __global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu 
     }
     // per candidate, once: where its window starts (word offset, bit 31 = odd sample offset -> shifted copy) and its rate
     const int total = g.nx * g.ny;
+    static_assert(kBiThreads >= kFsCands, "a thread per candidate");
     if (tid < total) {
       const int cyi = tid / g.nx, cxi = tid - cyi * g.nx, ox = g.ox0 + cxi;
       s_cand[tid] = make_uint2((uint32_t)(cyi * g.wp + (ox >> 1)) | ((uint32_t)(ox & 1) << 31),
@@ -367,12 +376,13 @@ __global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu 
     if (tid < kFsCands) s_sad[tid] = 0;
     if (tid == 0) s_best = ~0ull;
     __syncthreads();
-    // a thread per (candidate, half of the rows): the original is a broadcast read, neighbouring candidates share words
-    if (tid < 2 * kFsCands) {
-      const int half = tid >= kFsCands, t = tid - half * kFsCands;
+    // a thread per (candidate, part of the rows): the original is a broadcast read, neighbouring candidates share words
+    constexpr int kParts = kBiThreads >= 4 * kFsCands ? 4 : (kBiThreads >= 2 * kFsCands ? 2 : 1);
+    if (tid < kParts * kFsCands) {
+      const int half = tid / kFsCands, t = tid - half * kFsCands;
       if (t < total) {
         const uint2 cd = s_cand[t];
-        const int hrows = rows >> 1, pairs = 1 << lpw;
+        const int hrows = rows / kParts, pairs = 1 << lpw;
         const uint32_t *pw = reinterpret_cast<const uint32_t *>((cd.x >> 31) ? s_shift : s_win[stage]) + (cd.x & 0x7fffffffu) + half * hrows * rstep * g.wp;
         const uint32_t *po = s_org + half * hrows * kFsOrgPitch;
         uint32_t sad = 0;
@@ -418,11 +428,22 @@ __global__ void __launch_bounds__(kBiThreads) bi_search_kernel(const xvcb200_cu 
 cudaError_t launch_bi_search(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
                              const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
                              PlaneView worig, const FsTensorMaps &maps, int margin_x, int margin_y, xvcb200_me_job *d_bi_jobs,
-                             xvcb200_me_result *d_bi_res) {
+                             xvcb200_me_result *d_bi_res, cudaStream_t side, cudaEvent_t side_ev, cudaEvent_t fork_ev) {
   if (P.n <= 0) return cudaSuccess;
-  g_launch_count++;
-  bi_search_kernel<<<P.n, kBiThreads, 0, s>>>(d_cus, P, iteration, d_jobs, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig,
-                                       maps, margin_x, margin_y, d_bi_jobs, d_bi_res);
+  g_launch_count += 2;
+  cudaStream_t s1 = side ? side : s;
+  if (side) {
+    cudaEventRecord(fork_ev, s);
+    cudaStreamWaitEvent(s1, fork_ev, 0);
+  }
+  bi_search_kernel<64, 352><<<P.n, 352, 0, s>>>(d_cus, P, iteration, d_jobs, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig,
+                                             maps, margin_x, margin_y, d_bi_jobs, d_bi_res);
+  bi_search_kernel<16, 96><<<P.n, 96, 0, s1>>>(d_cus, P, iteration, d_jobs, d_res, static_cast<MeCuState *>(d_state), orig, d_luma_views, worig,
+                                            maps, margin_x, margin_y, d_bi_jobs, d_bi_res);
+  if (side) {
+    cudaEventRecord(side_ev, s1);
+    cudaStreamWaitEvent(s, side_ev, 0);
+  }
   return cudaGetLastError();
 }
 

@@ -181,7 +181,7 @@ struct FsTensorMaps { CUtensorMap m[10][2]; };
 cudaError_t launch_bi_search(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, int iteration, const xvcb200_me_job *d_jobs,
                              const xvcb200_me_result *d_res, void *d_state, PlaneView orig, const PlaneView *d_luma_views,
                              PlaneView worig, const FsTensorMaps &maps, int margin_x, int margin_y, xvcb200_me_job *d_bi_jobs,
-                             xvcb200_me_result *d_bi_res);
+                             xvcb200_me_result *d_bi_res, cudaStream_t side, cudaEvent_t side_ev, cudaEvent_t fork_ev);
 cudaError_t launch_me_bi_decide(cudaStream_t s, const xvcb200_cu *d_cus, const MePipe &P, const xvcb200_me_job *d_jobs,
                                 const xvcb200_me_result *d_bi_res, xvcb200_me_result *d_res, void *d_state);
 cudaError_t launch_me_final_decide(cudaStream_t s, xvcb200_cu *d_cus, const MePipe &P, const void *d_state);
