@@ -30,18 +30,30 @@ def gpu_partition(width, height, bd, cur, ref_rec, lam, qp):
     return out
 
 
-def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=64, n_inter=1, partition="seeded"):
+def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=64, n_inter=1, partition="seeded", report=None):
     """backend(cur, ref_rec, cus, prm, info) -> (cus_out, levels, rec planes incl. deblocking).
     n_inter inter pictures in a low-delay chain: picture k references picture k-1, i.e. from the second
     inter picture on the reference picture is itself a reconstruction made by the backend."""
     canvas = workload.synth_canvas(width, height, seed)
     pics = [workload.synth_frame(canvas, width, height, i, bd) for i in range(1 + n_inter)]
     conf = bindings.RefConformance(ref, width, height, bd, qp)
-    for p in pics:
-        conf.push(p)
-    conf.flush()
+    if report is not None:      # the reference encoder's own stream of the same pictures (same key picture, same QP)
+        own = bindings.RefConformance(ref, width, height, bd, qp)
+        for p in pics:
+            own.push(p)
+        own.flush()
+        report["reference_stream"] = own.bitstream()
+        own.close()
+        report["originals"] = pics
+        report["inter_nal_bytes"] = []
+    # The reference encoder keeps only a few pictures alive: picture k+1 is pushed after picture k has been replaced
+    # (its reconstruction in the encoder's buffer is then the backend's, which is what picture k+1 references).
+    conf.push(pics[0])
     recs = []
     for poc in range(1, 1 + n_inter):
+        conf.push(pics[poc])
+        if poc == n_inter:
+            conf.flush()
         orig, ref_rec, info = conf.inter_inputs(poc, poc - 1)
         assert all(np.array_equal(a, b) for a, b in zip(orig, pics[poc]))
         if recs:
@@ -63,6 +75,8 @@ def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=
         size = conf.write_inter(poc, cus_out, splits, levels, rec)
         assert size > 0, "the reference writer rejected the picture (%d)" % size
         recs.append(rec)
+        if report is not None:
+            report["inter_nal_bytes"].append(size)
     stream = conf.bitstream()
     conf.close()
     with tempfile.TemporaryDirectory() as tmp:
@@ -83,7 +97,29 @@ def run(ref, backend, width=256, height=128, bd=10, qp=32, seed=3, search_range=
                one[width * height * 5 // 4:].reshape(height // 2, width // 2)]
         for c in range(3):
             assert np.array_equal(got[c], rec[c]), (k, c)
+    if report is not None:
+        report["stream"], report["reconstructions"] = stream, recs
     return len(stream), log
+
+
+def decode(stream, width, height, bd, n_pictures):
+    """The UNMODIFIED xvcdec on a stream -> list of pictures (three planes each)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        bit, yuv = os.path.join(tmp, "s.xvc"), os.path.join(tmp, "out.yuv")
+        open(bit, "wb").write(stream)
+        res = subprocess.run([XVCDEC, "-bitstream-file", bit, "-output-file", yuv, "-output-bitdepth", str(bd)],
+                             capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0 and "Conformance verified" in res.stdout + res.stderr
+        dec = np.fromfile(yuv, dtype=np.uint16)
+    per = width * height * 3 // 2
+    assert dec.size == n_pictures * per
+    out = []
+    for k in range(n_pictures):
+        one = dec[k * per:(k + 1) * per]
+        out.append([one[:width * height].reshape(height, width),
+                    one[width * height:width * height * 5 // 4].reshape(height // 2, width // 2),
+                    one[width * height * 5 // 4:].reshape(height // 2, width // 2)])
+    return out
 
 
 def oracle_backend(oracle, width, height, bd):

@@ -74,10 +74,11 @@ def test_partition_follows_the_content():
     assert in_ctu.sum() > 1 and (~in_ctu).sum() == (width // 64) * (height // 64) - 1
 
 
-@pytest.mark.parametrize("width,height,qp,n_inter", [(256, 128, 32, 2), (1920, 1088, 32, 1)])
+@pytest.mark.parametrize("width,height,qp,n_inter", [(256, 128, 32, 2), (1920, 1088, 32, 1), (448, 256, 32, 32)])
 def test_conformance_on_gpu_partition(ref, width, height, qp, n_inter):
     """The partition the GPU decided, searched / coded / filtered on the GPU, written by the reference's writer and
-    decoded by the UNMODIFIED xvcdec: "Conformance verified" and decoder output == GPU reconstruction."""
+    decoded by the UNMODIFIED xvcdec: "Conformance verified" and decoder output == GPU reconstruction -- up to a
+    33-frame low-delay chain in which every inter picture references the GPU reconstruction of the one before."""
     if not os.path.exists(conformance.XVCDEC):
         pytest.skip("oracle/_ref/xvcdec not built (needs /root/reference)")
     size, log = conformance.run(ref, conformance.gpu_backend(width, height, 10), width, height, 10, qp, 21, n_inter=n_inter,
