@@ -355,8 +355,11 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
         return workload.add_objects(f, WIDTH, HEIGHT, k, BITDEPTH)
     warm_pocs = (pics[0][0], pics[1][0])   # every rank warms up on the first anchor and the first B picture (local, nothing pushed)
     dev_orig = {poc: [torch.from_numpy(p.view(np.int16)).cuda() for p in make(poc)] for poc in sorted(mine | set(warm_pocs))}
+    owners = {poc: j % world for wave in waves for j, poc in enumerate(wave)}
+    device_rendezvous = peers is not None and os.environ.get("XVCB_GOP_RENDEZVOUS", "device") == "device"
     eng = gop.GopEngine(ctx, peers, rank, pics, lambda poc: dev_orig[poc], QP, BITDEPTH,
-                        time_events=lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                        time_events=lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)),
+                        owners=owners if device_rendezvous else None)
     eng.load_done(0, make(0))          # the key picture is not coded here: its original stands in for its reconstruction
     # warm-up: the whole sequence once, untimed, pushes included -- the device buffers that grow with the CU count of the
     # deeper temporal layers and the first transfer into every peer slot are one-time costs (measured: 35 of the 43 ms
@@ -370,7 +373,8 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
             for j, poc in enumerate(wave):
                 eng.share(poc, j % world)
             t2 = time.perf_counter()
-            eng.fence()
+            if not device_rendezvous:
+                eng.fence()
             times.append((time.perf_counter() - t0) * 1e3)
             if os.environ.get("XVCB_GOP_DEBUG"):
                 print("[gop] rank %d wave of %d: enqueue %.2f ms, push calls %.2f ms, fence %.2f ms" %
@@ -380,7 +384,8 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
         eng.encode(p)
     ctx.sync()
     run_waves([])
-    ctx.sync()
+    eng.fence()
+    eng.pass_index = 1
     eng.events.clear()
     if dist is not None:
         dist.barrier()
@@ -388,6 +393,7 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
     wave_ms = []
     t_all = time.perf_counter()
     run_waves(wave_ms)
+    eng.fence()
     torch.cuda.synchronize()
     total_s = time.perf_counter() - t_all
     busy_ms = sum(a.elapsed_time(b) for _, a, b in eng.events)
@@ -411,14 +417,17 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
     coded = 16 * n_sub_gops
     return {"frames": n_frames, "pictures_coded": coded, "sub_gops": n_sub_gops,
             "value": coded * WIDTH * HEIGHT / total_s / 1e6, "unit": "Mpixels/s", "ms_total": total_s * 1e3,
-            "waves": [{"pictures": len(wv), "ms": ms} for wv, ms in zip(waves, wave_ms)],
+            "waves": [{"pictures": len(wv), "host_ms" if device_rendezvous else "ms": ms} for wv, ms in zip(waves, wave_ms)],
             "gpu_busy_frac": busy_ms / (world * total_s * 1e3), "gpu_idle_frac": 1.0 - busy_ms / (world * total_s * 1e3),
             "reconstructions_identical_on_all_ranks": len(set(digests)) == 1,
             "how": "ThreadEncoder's readiness rule as waves across sub-GOPs; picture j of a wave on GPU j mod N; per picture: device copy of the "
                    "original, GPU partition pre-analysis (a rank's next picture ahead of the kernels of its current one), set_cus, the whole step; finished reconstructions pushed to every GPU "
-                   "(copy engines over NVLink) and a rendezvous per wave (own pushes done, stream idle, barrier) before they are referenced; wall "
+                   "(copy engines over NVLink); rendezvous: " + ("on the device -- an arrival tag written behind every pushed slot on the same copy stream, "
+                   "the consumer's stream waits for the tags of its reference pictures (cuStreamWaitValue32), no host barrier between waves" if device_rendezvous else
+                   "per wave on the host (own pushes done, stream idle, barrier) before they are referenced") + "; wall "
                    "clock between barriers, max over ranks; busy = CUDA-event time of the pictures' work summed over GPUs; the whole sequence runs "
                    "once untimed before the timed pass (buffer growth, first transfer into every peer slot)",
+            "rendezvous": "device" if device_rendezvous else "host",
             "search_range": "InterSearch::GetSearchRangeUniPred capped at 128 (it yields 256 for the anchor pictures; the search kernel stages +-128 windows)",
             "key_picture": "not coded: its original is uploaded as its reconstruction"}
 

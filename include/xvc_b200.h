@@ -296,6 +296,16 @@ int xvcb200_ipc_export(xvcb200_ctx *ctx, void *handle /* XVCB200_IPC_HANDLE_BYTE
 int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle, int *peer_index);
 int xvcb200_push_slot(xvcb200_ctx *ctx, int slot);
 int xvcb200_wait_pushes(xvcb200_ctx *ctx, int slot);
+/* The rendezvous on the device (no host takes part): xvcb200_push_slot_tagged pushes the slot like
+ * xvcb200_push_slot and then, on the same copy stream per peer, writes `tag` into the arrival word of that slot in
+ * the PEER's arena (one 32-bit word per slot behind the slots, part of the exported allocation);
+ * xvcb200_wait_slot_tag makes the consumer's context stream wait (cuStreamWaitValue32, >=) until the arrival word
+ * of `slot` in its OWN arena has reached `tag` -- the kernels enqueued afterwards see the pushed content.  Tags of
+ * one slot must increase from push to push (a picture counter); the producer of a slot does not wait for its own
+ * tag (its content is ordered by its stream).  What ThreadEncoder's "picture done" notification is between
+ * threads (thread_encoder.cc:133-159), between GPUs. */
+int xvcb200_push_slot_tagged(xvcb200_ctx *ctx, int slot, uint32_t tag);
+int xvcb200_wait_slot_tag(xvcb200_ctx *ctx, int slot, uint32_t tag);
 
 /* host <-> device picture transfer; host planes are tight or strided (elements). */
 int xvcb200_upload_picture(xvcb200_ctx *ctx, int slot, const uint16_t *const planes[3], const ptrdiff_t strides[3]);

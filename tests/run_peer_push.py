@@ -44,6 +44,22 @@ def main():
         probe.pad_border(0)
         for c in range(3):
             ok &= bool(np.array_equal(ctx.download_padded(first + r, c), probe.download_padded(0, c)))
+    # The rendezvous on the device (xvcb200_push_slot_tagged / xvcb200_wait_slot_tag): new content, no host barrier
+    # between the push and its consumption -- the consumer's stream waits for the arrival tag written behind the slot.
+    for tag in (1, 2):
+        pics2 = [common.frames(W, H, BD, 200 + 10 * tag + r)[0] for r in range(world)]
+        ex.wait_own(first + rank)
+        ctx.upload(first + rank, pics2[rank])
+        ctx.pad_border(first + rank)
+        ex.push_tagged(first + rank, tag)
+        for r in range(world):
+            if r != rank:
+                ex.wait_tag(first + r, tag)
+            probe.upload(0, pics2[r])
+            probe.pad_border(0)
+            for c in range(3):
+                ok &= bool(np.array_equal(ctx.download_padded(first + r, c), probe.download_padded(0, c)))
+        ex.landed()          # (before the slots are rewritten by the next round)
     t = torch.tensor([1 if ok else 0])
     if not same_gpu:
         t = t.cuda()

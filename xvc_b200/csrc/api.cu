@@ -572,8 +572,10 @@ int xvcb200_ctx_create(xvcb200_ctx **out, int device, int width, int height, int
   c->slots.resize(num_slots);
   std::vector<PlaneView> views(num_slots);
   uint8_t *arena = nullptr;
-  if (!c->check(cudaMalloc(&arena, total * num_slots), "cudaMalloc(slots)")) { int st = c->status; delete c; return st; }
-  cudaMemsetAsync(arena, 0, total * num_slots, c->stream);
+  // (+ a tail of one 32-bit arrival tag per slot, inside the allocation a peer maps: xvcb200_push_slot_tagged)
+  const size_t tag_bytes = (sizeof(uint32_t) * (size_t)num_slots + 255) & ~(size_t)255;
+  if (!c->check(cudaMalloc(&arena, total * num_slots + tag_bytes), "cudaMalloc(slots)")) { int st = c->status; delete c; return st; }
+  cudaMemsetAsync(arena, 0, total * num_slots + tag_bytes, c->stream);
   c->slot_stride = total;
   for (int s = 0; s < num_slots; s++) {
     DevPicture &d = c->slots[s];
@@ -774,6 +776,65 @@ int xvcb200_push_slot(xvcb200_ctx *ctx, int slot) {
   cudaEvent_t &ev = c->ex.slot_pushed[slot];
   if (!ev && !c->check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) return c->status;
   c->check(cudaEventRecord(ev, c->ex.push_stream[0]), "cudaEventRecord");
+  return c->status;
+}
+// Driver entry points of the arrival tags (stream memory operations), through the runtime's query like
+// cuTensorMapEncodeTiled: the library does not link libcuda.
+typedef CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*MemsetD32Async)(CUdeviceptr, unsigned int, size_t, CUstream);
+static bool tag_entry_points(CtxFull *c, StreamWaitValue32 *wait, MemsetD32Async *set) {
+  static void *fn_wait = nullptr, *fn_set = nullptr;
+  if (!fn_wait || !fn_set) {
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (!c->check(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn_wait, cudaEnableDefault, &q), "cudaGetDriverEntryPoint") || !fn_wait ||
+        q != cudaDriverEntryPointSuccess)
+      return c->fail(XVCB200_CUDA_ERROR, "cuStreamWaitValue32 is not available from this driver");
+    if (!c->check(cudaGetDriverEntryPoint("cuMemsetD32Async", &fn_set, cudaEnableDefault, &q), "cudaGetDriverEntryPoint") || !fn_set ||
+        q != cudaDriverEntryPointSuccess)
+      return c->fail(XVCB200_CUDA_ERROR, "cuMemsetD32Async is not available from this driver");
+  }
+  *wait = reinterpret_cast<StreamWaitValue32>(fn_wait);
+  *set = reinterpret_cast<MemsetD32Async>(fn_set);
+  return true;
+}
+static size_t tag_offset(const xvcb200_ctx *c, int slot) { return c->slot_stride * c->slots.size() + sizeof(uint32_t) * (size_t)slot; }
+
+int xvcb200_push_slot_tagged(xvcb200_ctx *ctx, int slot, uint32_t tag) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  StreamWaitValue32 wait; MemsetD32Async set;
+  if (!tag_entry_points(c, &wait, &set)) return c->status;
+  if (c->ex.peer_arena.empty()) return XVCB200_OK;
+  join_upload_slot(c, slot);
+  const size_t off = (size_t)slot * c->slot_stride;
+  c->check(cudaEventRecord(c->ex.push_ready, c->stream), "cudaEventRecord");
+  for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {      // per peer: the slot, then its tag, in stream order
+    cudaStream_t st = c->ex.push_stream[p];
+    c->check(cudaStreamWaitEvent(st, c->ex.push_ready, 0), "cudaStreamWaitEvent");
+    c->check(cudaMemcpyAsync(c->ex.peer_arena[p] + off, c->slots[0].alloc + off, c->slot_stride, cudaMemcpyDeviceToDevice, st), "push slot");
+    if (set(reinterpret_cast<CUdeviceptr>(c->ex.peer_arena[p] + tag_offset(c, slot)), tag, 1, st) != CUDA_SUCCESS)
+      return c->fail(XVCB200_CUDA_ERROR, "cuMemsetD32Async (arrival tag) failed");
+    if (p > 0) {
+      c->check(cudaEventRecord(c->ex.push_done, st), "cudaEventRecord");
+      c->check(cudaStreamWaitEvent(c->ex.push_stream[0], c->ex.push_done, 0), "cudaStreamWaitEvent");
+    }
+  }
+  c->ex.slot_pushed.resize(c->slots.size(), nullptr);
+  cudaEvent_t &ev = c->ex.slot_pushed[slot];
+  if (!ev && !c->check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) return c->status;
+  c->check(cudaEventRecord(ev, c->ex.push_stream[0]), "cudaEventRecord");
+  return c->status;
+}
+int xvcb200_wait_slot_tag(xvcb200_ctx *ctx, int slot, uint32_t tag) {
+  xvcb::DevGuard dev_guard(ctx);
+  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
+  CtxFull *c = full(ctx);
+  StreamWaitValue32 wait; MemsetD32Async set;
+  if (!tag_entry_points(c, &wait, &set)) return c->status;
+  // (tag - value) as a signed difference >= 0: CU_STREAM_WAIT_VALUE_GEQ compares cyclically, tags may wrap
+  if (wait(c->stream, reinterpret_cast<CUdeviceptr>(c->slots[0].alloc + tag_offset(c, slot)), tag, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+    return c->fail(XVCB200_CUDA_ERROR, "cuStreamWaitValue32 (arrival tag) failed");
   return c->status;
 }
 int xvcb200_wait_pushes(xvcb200_ctx *ctx, int slot) {

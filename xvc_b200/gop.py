@@ -53,9 +53,14 @@ class GopEngine:
     FIRST_RING_SLOT = 4
     ORIG_SLOTS = (0, 3)
 
-    def __init__(self, ctx, peers, rank, pics, originals, qp, bitdepth, ring=56, max_range=128, time_events=None):
+    def __init__(self, ctx, peers, rank, pics, originals, qp, bitdepth, ring=56, max_range=128, time_events=None, owners=None):
         self.ctx, self.peers, self.rank, self.originals, self.qp = ctx, peers, rank, originals, qp
         self.by_poc = {p[0]: p for p in pics}
+        # device-side rendezvous (owners: POC -> rank that codes it): a consumer's stream waits for the arrival tag
+        # of every reference picture another rank produced; tags grow with the coding order and from pass to pass
+        self.owners = owners
+        self.order = {p[0]: k + 1 for k, p in enumerate(pics)}
+        self.pass_index = 0
         self.ring, self.max_range = ring, max_range
         self.lam = workload.lambda_for_qp(qp)
         self.busy = time_events            # callable returning a (start, stop) pair of recorded-on-demand events, or None
@@ -89,10 +94,17 @@ class GopEngine:
                 prm["search_range"][0, l, r] = min(self.max_range, workload.search_range_uni(poc, p))
         return prm, l0, l1
 
+    def tag_of(self, poc):
+        return self.pass_index * (len(self.order) + 1) + self.order[poc]
+
     def _begin(self, poc, oslot):
         """Original picture -> slot oslot (device copy), pre-analysis enqueued: the partition from the content, against
         the first list-0 picture, around the sequence's global motion."""
-        _, _, l0, _ = self.by_poc[poc]
+        _, _, l0, l1 = self.by_poc[poc]
+        if self.owners is not None and self.peers is not None:
+            for p in sorted(set(l0) | set(l1)):
+                if p in self.owners and self.owners[p] != self.rank:      # (the key picture is resident everywhere)
+                    self.peers.wait_tag(self.slot_of(p), self.tag_of(p))
         for c, t in enumerate(self.originals(poc)):
             my, mx, h, w = self.views[c]
             self.orig_t[oslot][c][my:my + h, mx:mx + w].copy_(t)
@@ -141,7 +153,10 @@ class GopEngine:
 
     def share(self, poc, owner):
         if owner == self.rank and self.peers is not None:
-            self.peers.push(self.slot_of(poc))
+            if self.owners is not None:
+                self.peers.push_tagged(self.slot_of(poc), self.tag_of(poc))
+            else:
+                self.peers.push(self.slot_of(poc))
 
     def fence(self):
         if self.peers is not None:

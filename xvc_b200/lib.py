@@ -42,6 +42,7 @@ EXPORTS = [
     "xvcb200_encode_picture", "xvcb200_decide_partition", "xvcb200_decide_partition_begin", "xvcb200_decide_partition_end", "xvcb200_set_profiling", "xvcb200_get_stage_times",
     "xvcb200_intra_ref_samples", "xvcb200_intra_predict", "xvcb200_intra_satd_scan", "xvcb200_intra_lm_chroma",
     "xvcb200_ipc_export", "xvcb200_ipc_open_peer", "xvcb200_push_slot", "xvcb200_wait_pushes",
+    "xvcb200_push_slot_tagged", "xvcb200_wait_slot_tag",
     "xvcb200_device_count",
 ]
 
@@ -102,6 +103,8 @@ def load():
     L.xvcb200_ipc_open_peer.argtypes = [c_void_p, c_void_p, c_void_p]
     L.xvcb200_push_slot.argtypes = [c_void_p, c_int]
     L.xvcb200_wait_pushes.argtypes = [c_void_p, c_int]
+    L.xvcb200_push_slot_tagged.argtypes = [c_void_p, c_int, ctypes.c_uint32]
+    L.xvcb200_wait_slot_tag.argtypes = [c_void_p, c_int, ctypes.c_uint32]
     L.xvcb200_ctx_create.argtypes = [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int]
     L.xvcb200_ctx_destroy.argtypes = [c_void_p]
     L.xvcb200_ctx_set_stream.argtypes = [c_void_p, c_void_p]
@@ -359,6 +362,14 @@ class Context:
 
     def wait_pushes(self, slot=-1):
         self._ok(self.L.xvcb200_wait_pushes(self.h, slot))
+
+    def push_slot_tagged(self, slot, tag):
+        """push_slot + the arrival tag written behind it into every peer's arena (device-side rendezvous)."""
+        self._ok(self.L.xvcb200_push_slot_tagged(self.h, slot, tag))
+
+    def wait_slot_tag(self, slot, tag):
+        """The context stream waits until a peer's tagged push of `slot` has arrived (no host wait)."""
+        self._ok(self.L.xvcb200_wait_slot_tag(self.h, slot, tag))
 
     def slots_tensor(self, first, count=1):
         """torch uint8 CUDA tensor aliasing slots [first, first+count) (no copy)."""

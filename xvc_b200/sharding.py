@@ -225,6 +225,14 @@ class PeerExchange:
         self.ctx.sync()
         self.dist.barrier()
 
+    # The same rendezvous on the device: the producer writes an arrival tag behind the pushed slot (same copy
+    # stream), the consumer's context stream waits for the tag -- no host, no barrier between waves.
+    def push_tagged(self, slot, tag):
+        self.ctx.push_slot_tagged(slot, tag)
+
+    def wait_tag(self, slot, tag):
+        self.ctx.wait_slot_tag(slot, tag)
+
 
 # ---------------------------------------------------------------------------------------------
 # Frame-parallel encoding of a GOP (BASELINE config 5): the reference's own parallel model.
