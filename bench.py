@@ -833,6 +833,7 @@ def run_ours(args):
     # 81 per picture of the searched list; SubpelSearch 17 per search) -- one more picture with the results brought back
     sad_candidates = None
     try:
+        set_cus()           # (the CU array on the device carries the previous picture's chosen vectors)
         me, _ = ctx.encode_picture(prm, want_results=True)
         ctx.sync()
         l0, l1 = LISTS[WORKLOAD]

@@ -539,7 +539,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     const int grp = s_group;
     if (grp >= n_groups) break;
     const long long t_group = prof ? clock64() : 0;
-    int g_raster = 0;
+    int g_raster = 0, g_chunks = 0;
     const TzGroup G = groups[sel.J ? grp / sel.n : grp];
     const int jcol = sel.J ? sel.j[grp % sel.n] : 0;
     auto job_of = [&](int k) { const int e = job_index[G.first + k]; return sel.J ? e * sel.J + jcol : e; };
@@ -586,6 +586,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
       __syncthreads();
       const int kn = s_count;
       kn_adv = kn;
+      g_chunks++;
       for (int k = tid; k < kn; k += kTzThreads) atomicAdd(&s_cls[__clz((int)s_job[k].w * s_job[k].h) - 19], 1);   // area 4096 -> class 0 ... 16 -> class 8
       __syncthreads();
       if (tid == 0) {          // class counts -> first slot of each class; blocks of >= 2048 samples are searched CTA-wide
@@ -814,6 +815,9 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
             // sums meet in lgw shuffles.
             {
               const int total = s_pool_used;
+              // ... as long as there are fewer lane tasks than about eight per thread: with thousands of survivors (poor
+              // predictors: most jobs of the group are scanned) a survivor per lane keeps every lane busy anyway
+              const int lg_cap = total >= 8 * kTzThreads ? 0 : 31 - __clz((8 * kTzThreads) / max(total, 1));
               for (int e0 = warp * 32; e0 < total; e0 += kTzThreads) {
                 const int e = e0 + lane;
                 uint32_t ent = 0;
@@ -827,7 +831,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
                   const int lpairs = (31 - __clz(rows)) + (30 - __clz((int)sj.w));
                   lgj = live ? min(31 - __clz(rows), max(0, lpairs - 4)) : 0;
                 }
-                const int lgw = __reduce_max_sync(XVCB_FULL, lgj);
+                const int lgw = min(__reduce_max_sync(XVCB_FULL, lgj), lg_cap);
                 const unsigned live_mask = __ballot_sync(XVCB_FULL, live);
                 for (int q = 0; q < (1 << lgw); q++) {
                   const int src = ((q << 5) + lane) >> lgw, sub = lane & ((1 << lgw) - 1);
@@ -1109,7 +1113,7 @@ tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__res
     }
     if (prof && tid == 0 && grp < kProfGroups) {
       unsigned long long *pg = prof + 24 + 4 * grp;
-      pg[0] = (unsigned long long)(clock64() - t_group); pg[1] = (unsigned long long)G.count; pg[3] = (unsigned long long)g_raster;
+      pg[0] = (unsigned long long)(clock64() - t_group); pg[1] = (unsigned long long)G.count; pg[3] = (unsigned long long)g_raster | ((unsigned long long)g_chunks << 32);
       unsigned long long area = 0;
       for (int k = 0; k < G.count; k++) { const xvcb200_cu cu = cus[jobs[job_of(k)].cu]; area += (unsigned long long)cu.w * cu.h; }
       pg[2] = area;
