@@ -754,6 +754,23 @@ def run_ours(args):
         e2e_sec = float(t.item())
     e2e_value = world * WIDTH * HEIGHT * args.steps / e2e_sec / 1e6
 
+    # ---- candidates per step, by the reference's own count (TzSearch evaluates `num_sad` positions per search; FullSearch
+    # 81 per picture of the searched list; SubpelSearch 17 per search) -- one more picture with the results brought back
+    sad_candidates = None
+    try:
+        set_cus()           # (the CU array on the device carries the previous picture's chosen vectors)
+        me, _ = ctx.encode_picture(prm, want_results=True)
+        ctx.sync()
+        l0, l1 = LISTS[WORKLOAD]
+        J = len(l0) + len(l1)
+        cols = list(range(len(l0))) + [len(l0) + r for r, p in enumerate(l1) if p not in l0 or WORKLOAD == "raster"]
+        per = me["num_sad"].reshape(-1, J)[:, cols].astype(np.int64)
+        n_bi = int(prm["bi_iterations"][0]) * len(per) * max(len(l0), len(l1))
+        sad_candidates = {"tz_search_sad": int(per.sum()), "tz_searches": int(per.size),
+                          "bi_full_search_sad": 81 * n_bi, "subpel_satd": 17 * (int(per.size) + n_bi)}
+    except Exception as e:  # noqa: BLE001
+        sad_candidates = {"unavailable": repr(e)}
+
     # ---- round 1's step beside it (context: the raster-dominated workload the round-1 numbers were quoted on)
     other = None
     if world == 1 and WORKLOAD == "encode" and not args.size and args.gop != "off":
@@ -828,23 +845,6 @@ def run_ours(args):
                 "compute_ceilings": issue,
                 "stages_ms": stage_avg,
                 "stages_frac_of_hbm": {k: alg_bytes[k] / (v * 1e-3) / 1e9 / peak for k, v in stage_avg.items() if v > 0}}
-
-    # ---- candidates per step, by the reference's own count (TzSearch evaluates `num_sad` positions per search; FullSearch
-    # 81 per picture of the searched list; SubpelSearch 17 per search) -- one more picture with the results brought back
-    sad_candidates = None
-    try:
-        set_cus()           # (the CU array on the device carries the previous picture's chosen vectors)
-        me, _ = ctx.encode_picture(prm, want_results=True)
-        ctx.sync()
-        l0, l1 = LISTS[WORKLOAD]
-        J = len(l0) + len(l1)
-        cols = list(range(len(l0))) + [len(l0) + r for r, p in enumerate(l1) if p not in l0 or WORKLOAD == "raster"]
-        per = me["num_sad"].reshape(-1, J)[:, cols].astype(np.int64)
-        n_bi = int(prm["bi_iterations"][0]) * len(per) * max(len(l0), len(l1))
-        sad_candidates = {"tz_search_sad": int(per.sum()), "tz_searches": int(per.size),
-                          "bi_full_search_sad": 81 * n_bi, "subpel_satd": 17 * (int(per.size) + n_bi)}
-    except Exception as e:  # noqa: BLE001
-        sad_candidates = {"unavailable": repr(e)}
 
     # ---- CPU baseline beside it (bounded sample) + bit-exact reconstruction check
     cpu = None

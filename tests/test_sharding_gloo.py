@@ -163,3 +163,31 @@ def test_peer_exchange_all_ranks_agree(tmp_path, bad):
         assert got == ["ok 2"] * world
     else:
         assert all(g.startswith("unavailable: rank %d" % bad) for g in got), got
+
+
+def test_gop_arrival_tags_increase_per_slot():
+    """Device-side rendezvous of the frame-parallel GOP (xvcb200_push_slot_tagged / xvcb200_wait_slot_tag): the
+    consumer waits for `tag >=`, so the tags written into one slot's arrival word must grow from push to push --
+    within a pass (ring slots reused by later POCs) and from the warm-up pass to the timed one."""
+    from xvc_b200 import gop
+
+    class NoCtx:
+        geom = {"margin_y": [0, 0, 0], "margin_x": [0, 0, 0], "height": [8, 4, 4], "width": [8, 4, 4]}
+
+        def plane_tensor(self, slot, comp):
+            return None
+
+    for n_sub in (2, 4, 8):
+        pics = gop.hierarchical_gop(n_sub)
+        eng = gop.GopEngine(NoCtx(), None, 0, pics, None, 32, 10)
+        last = {}
+        for pass_index in (0, 1):
+            eng.pass_index = pass_index
+            for poc, _, _, _ in pics:                      # coding order = push order of a slot's producers
+                slot, tag = eng.slot_of(poc), eng.tag_of(poc)
+                assert tag > last.get(slot, 0), (n_sub, poc, slot)
+                last[slot] = tag
+        # every reference picture of a picture is coded before it (the wait can be satisfied)
+        order = {p[0]: k for k, p in enumerate(pics)}
+        for poc, _, l0, l1 in pics:
+            assert all(r == 0 or order[r] < order[poc] for r in tuple(l0) + tuple(l1))
