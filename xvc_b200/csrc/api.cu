@@ -755,29 +755,6 @@ int xvcb200_ipc_open_peer(xvcb200_ctx *ctx, const void *handle, int *peer_index)
   if (peer_index) *peer_index = (int)c->ex.peer_arena.size() - 1;
   return XVCB200_OK;
 }
-int xvcb200_push_slot(xvcb200_ctx *ctx, int slot) {
-  xvcb::DevGuard dev_guard(ctx);
-  if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
-  CtxFull *c = full(ctx);
-  if (c->ex.peer_arena.empty()) return XVCB200_OK;
-  join_upload_slot(c, slot);
-  const size_t off = (size_t)slot * c->slot_stride;
-  c->check(cudaEventRecord(c->ex.push_ready, c->stream), "cudaEventRecord");
-  for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {      // one DMA stream per peer: the copies run side by side
-    cudaStream_t st = c->ex.push_stream[p];
-    c->check(cudaStreamWaitEvent(st, c->ex.push_ready, 0), "cudaStreamWaitEvent");
-    c->check(cudaMemcpyAsync(c->ex.peer_arena[p] + off, c->slots[0].alloc + off, c->slot_stride, cudaMemcpyDeviceToDevice, st), "push slot");
-    if (p > 0) {      // funnel completion into the first push stream
-      c->check(cudaEventRecord(c->ex.push_done, st), "cudaEventRecord");
-      c->check(cudaStreamWaitEvent(c->ex.push_stream[0], c->ex.push_done, 0), "cudaStreamWaitEvent");
-    }
-  }
-  c->ex.slot_pushed.resize(c->slots.size(), nullptr);
-  cudaEvent_t &ev = c->ex.slot_pushed[slot];
-  if (!ev && !c->check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate")) return c->status;
-  c->check(cudaEventRecord(ev, c->ex.push_stream[0]), "cudaEventRecord");
-  return c->status;
-}
 // Driver entry points of the arrival tags (stream memory operations), through the runtime's query like
 // cuTensorMapEncodeTiled: the library does not link libcuda.
 typedef CUresult (*StreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
@@ -799,23 +776,25 @@ static bool tag_entry_points(CtxFull *c, StreamWaitValue32 *wait, MemsetD32Async
 }
 static size_t tag_offset(const xvcb200_ctx *c, int slot) { return c->slot_stride * c->slots.size() + sizeof(uint32_t) * (size_t)slot; }
 
-int xvcb200_push_slot_tagged(xvcb200_ctx *ctx, int slot, uint32_t tag) {
+// The slot into the same slot of every opened peer, one DMA stream per peer (the copies run side by side), ordered after
+// the work enqueued on the context stream so far; with `tagged` the arrival tag follows the slot on the same stream.
+static int push_slot_impl(xvcb200_ctx *ctx, int slot, bool tagged, uint32_t tag) {
   xvcb::DevGuard dev_guard(ctx);
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
-  StreamWaitValue32 wait; MemsetD32Async set;
-  if (!tag_entry_points(c, &wait, &set)) return c->status;
+  StreamWaitValue32 wait = nullptr; MemsetD32Async set = nullptr;
+  if (tagged && !tag_entry_points(c, &wait, &set)) return c->status;
   if (c->ex.peer_arena.empty()) return XVCB200_OK;
   join_upload_slot(c, slot);
   const size_t off = (size_t)slot * c->slot_stride;
   c->check(cudaEventRecord(c->ex.push_ready, c->stream), "cudaEventRecord");
-  for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {      // per peer: the slot, then its tag, in stream order
+  for (size_t p = 0; p < c->ex.peer_arena.size(); p++) {
     cudaStream_t st = c->ex.push_stream[p];
     c->check(cudaStreamWaitEvent(st, c->ex.push_ready, 0), "cudaStreamWaitEvent");
     c->check(cudaMemcpyAsync(c->ex.peer_arena[p] + off, c->slots[0].alloc + off, c->slot_stride, cudaMemcpyDeviceToDevice, st), "push slot");
-    if (set(reinterpret_cast<CUdeviceptr>(c->ex.peer_arena[p] + tag_offset(c, slot)), tag, 1, st) != CUDA_SUCCESS)
+    if (tagged && set(reinterpret_cast<CUdeviceptr>(c->ex.peer_arena[p] + tag_offset(c, slot)), tag, 1, st) != CUDA_SUCCESS)
       return c->fail(XVCB200_CUDA_ERROR, "cuMemsetD32Async (arrival tag) failed");
-    if (p > 0) {
+    if (p > 0) {      // funnel completion into the first push stream
       c->check(cudaEventRecord(c->ex.push_done, st), "cudaEventRecord");
       c->check(cudaStreamWaitEvent(c->ex.push_stream[0], c->ex.push_done, 0), "cudaStreamWaitEvent");
     }
@@ -826,6 +805,8 @@ int xvcb200_push_slot_tagged(xvcb200_ctx *ctx, int slot, uint32_t tag) {
   c->check(cudaEventRecord(ev, c->ex.push_stream[0]), "cudaEventRecord");
   return c->status;
 }
+int xvcb200_push_slot(xvcb200_ctx *ctx, int slot) { return push_slot_impl(ctx, slot, false, 0); }
+int xvcb200_push_slot_tagged(xvcb200_ctx *ctx, int slot, uint32_t tag) { return push_slot_impl(ctx, slot, true, tag); }
 int xvcb200_wait_slot_tag(xvcb200_ctx *ctx, int slot, uint32_t tag) {
   xvcb::DevGuard dev_guard(ctx);
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
