@@ -23,7 +23,13 @@ them from the numpy statement of the pre-analysis rule, outside its timed region
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM),
 `e2e` the same step through the C ABI with host buffers (H2D of the picture + CU array, D2H of
-reconstruction, levels and CU decisions inside the timed region).
+reconstruction, levels and CU decisions inside the timed region).  Beside them (--gop on, the default):
+`raster_workload` (N = 1: round 1's step on the same context), `gop` (BASELINE config 5: a hierarchical-B
+sequence of max(2, N) sub-GOPs encoded frame-parallel, waves across sub-GOPs, reconstructions pushed between
+the GPUs and referenced after a rendezvous on the device -- arrival tags, XVCB_GOP_RENDEZVOUS=host for the
+host barrier per wave) and, at N > 1, `banded` (config 4: one picture in CTU-row bands with the deblocking
+halo exchange).  The line is complete before `gop` / `banded` start; they run under a watchdog
+(XVCB_BENCH_EXTRAS_TIMEOUT seconds, default 180): if they do not finish, the line is printed with the reason.
 """
 import argparse
 import hashlib
