@@ -351,6 +351,8 @@ class Ref:
         L.xref_inv_transform.argtypes = [c_int] * 8 + [c_void_p, c_ssize, c_void_p, c_ssize]
         L.xref_transform_skip.argtypes = [c_int] * 4 + [c_void_p, c_ssize, c_void_p, c_ssize]
         L.xref_quant_fast.argtypes = [c_int] * 8 + [c_void_p, c_ssize, c_void_p, c_ssize]
+        if hasattr(L, "xref_quant_rdo_frozen"):
+            L.xref_quant_rdo_frozen.argtypes = [c_int] * 5 + [ctypes.c_double] + [c_int] * 3 + [c_void_p, c_ssize, c_void_p, c_ssize]
         L.xref_dequant.argtypes = [c_int] * 5 + [c_void_p, c_ssize, c_void_p, c_ssize]
         for name in ("xref_session_destroy", "xref_session_set_orig", "xref_session_set_rec", "xref_session_get_rec",
                      "xref_session_set_pred", "xref_session_get_pred", "xref_session_get_coeff"):
@@ -431,6 +433,14 @@ class Ref:
     def quant_fast(self, w, h, bitdepth, comp, qp, intra_pic, coeff, intra_cu=0, intra_mode=0):
         out = np.zeros((h, w), dtype=np.int16)
         nz = self.L.xref_quant_fast(w, h, bitdepth, comp, qp, intra_pic, intra_cu, intra_mode, abi.ptr(coeff), coeff.shape[1], abi.ptr(out), w)
+        return out, nz
+
+    def quant_rdo_frozen(self, w, h, bitdepth, comp, qp, lam, intra_pic, coeff, intra_cu=0, intra_mode=0):
+        """RdoQuant::QuantRdo against the context state a picture starts from (never advanced): the definition of
+        'RDOQ with frozen contexts' (SURVEY 8(f) rank 4)."""
+        out = np.zeros((h, w), dtype=np.int16)
+        nz = self.L.xref_quant_rdo_frozen(w, h, bitdepth, comp, qp, float(lam), intra_pic, intra_cu, intra_mode,
+                                          abi.ptr(coeff), coeff.shape[1], abi.ptr(out), w)
         return out, nz
 
     def dequant(self, w, h, bitdepth, comp, qp, lev):

@@ -317,6 +317,26 @@ int xref_quant_fast(int w, int h, int bitdepth, int comp, int qp, int intra_pic,
                      intra_pic ? PicturePredictionType::kIntra : PicturePredictionType::kBi, in, is, out, os);
 }
 
+// RDOQ with FROZEN contexts (the definition the GPU kernel of a later round has to meet):
+// RdoQuant::QuantRdo (rdo_quant.cc:203-446) with the context state every picture starts from -- a SyntaxWriter
+// freshly initialised for the picture's qp and prediction type (Contexts::ResetStates through its constructor,
+// syntax_writer.cc:35-41), never advanced: QuantRdo only reads the writer, so the result of a transform unit does
+// not depend on the units coded before it and all units of a picture can be quantised at once.  lambda is the
+// picture's lambda (Qp carries it: rdo_quant.cc uses qp.GetLambda()); qp is the raw LUMA qp, comp selects the
+// component (chroma qp via table 1, offsets 0), like xref_quant_fast.
+int xref_quant_rdo_frozen(int w, int h, int bitdepth, int comp, int qp, double lambda, int intra_pic, int intra_cu,
+                          int intra_mode, const int16_t *in, ptrdiff_t is, int16_t *out, ptrdiff_t os) {
+  TxCu t(w, h, bitdepth, comp, intra_cu != 0, 0, 0);
+  if (intra_cu) t.cu->SetIntraModeLuma(static_cast<IntraMode>(intra_mode));
+  EncoderSettings settings;
+  RdoQuant q(bitdepth, settings);
+  Qp qpo(qp, ChromaFormat::k420, bitdepth, lambda, 1, 0, 0);
+  const PicturePredictionType pic_type = intra_pic ? PicturePredictionType::kIntra : PicturePredictionType::kBi;
+  BitWriter bw;
+  SyntaxWriter writer(qpo, pic_type, &bw);
+  return q.QuantRdo(*t.cu, static_cast<YuvComponent>(comp), qpo, pic_type, writer, in, is, out, os);
+}
+
 void xref_dequant(int w, int h, int bitdepth, int comp, int qp, const int16_t *in, ptrdiff_t is,
                   int16_t *out, ptrdiff_t os) {
   Quantize q;
