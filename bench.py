@@ -909,9 +909,9 @@ def run_ours(args):
             os._exit(0)
 
         threading.Thread(target=give_up, daemon=True).start()
-        ctx.close()
         gop_info = banded_info = None
         try:
+            ctx.close()
             gop_info = gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, max(2, world) if args.gop_sub_gops <= 0 else args.gop_sub_gops)
         except Exception as e:  # noqa: BLE001
             gop_info = {"unavailable": repr(e)}
