@@ -26,8 +26,8 @@ Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs al
 reconstruction, levels and CU decisions inside the timed region).  Beside them (--gop on, the default):
 `raster_workload` (N = 1: round 1's step on the same context), `gop` (BASELINE config 5: a hierarchical-B
 sequence of max(2, N) sub-GOPs encoded frame-parallel, waves across sub-GOPs, reconstructions pushed between
-the GPUs and referenced after a rendezvous on the device -- arrival tags, XVCB_GOP_RENDEZVOUS=host for the
-host barrier per wave) and, at N > 1, `banded` (config 4: one picture in CTU-row bands with the deblocking
+the GPUs and referenced after a rendezvous -- on the device through arrival tags at N = 2, a host barrier per
+wave at N > 2, XVCB_GOP_RENDEZVOUS=device / host overrides) and, at N > 1, `banded` (config 4: one picture in CTU-row bands with the deblocking
 halo exchange).  The line is complete before `gop` / `banded` start; they run under a watchdog
 (XVCB_BENCH_EXTRAS_TIMEOUT seconds, default 180): if they do not finish, the line is printed with the reason.
 """
@@ -365,7 +365,9 @@ def gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, n_sub_g
     warm_pocs = (pics[0][0], pics[1][0])   # every rank warms up on the first anchor and the first B picture (local, nothing pushed)
     dev_orig = {poc: [torch.from_numpy(p.view(np.int16)).cuda() for p in make(poc)] for poc in sorted(mine | set(warm_pocs))}
     owners = {poc: j % world for wave in waves for j, poc in enumerate(wave)}
-    device_rendezvous = peers is not None and os.environ.get("XVCB_GOP_RENDEZVOUS", "device") == "device"
+    # default: on the device where that was run on hardware in this round (N = 2), on the host (barrier per wave) at
+    # N > 2 -- the device rendezvous at 4 / 8 GPUs is implemented but unverified
+    device_rendezvous = peers is not None and os.environ.get("XVCB_GOP_RENDEZVOUS", "device" if world <= 2 else "host") == "device"
     eng = gop.GopEngine(ctx, peers, rank, pics, lambda poc: dev_orig[poc], QP, BITDEPTH,
                         time_events=lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)),
                         owners=owners if device_rendezvous else None, ring=ring)
