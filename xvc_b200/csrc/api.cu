@@ -811,8 +811,8 @@ int xvcb200_wait_slot_tag(xvcb200_ctx *ctx, int slot, uint32_t tag) {
   xvcb::DevGuard dev_guard(ctx);
   if (!ctx || slot < 0 || slot >= (int)ctx->slots.size()) return XVCB200_INVALID_ARGUMENT;
   CtxFull *c = full(ctx);
-  StreamWaitValue32 wait; MemsetD32Async set;
-  if (!tag_entry_points(c, &wait, &set)) return c->status;
+  StreamWaitValue32 wait = nullptr; MemsetD32Async unused = nullptr;
+  if (!tag_entry_points(c, &wait, &unused)) return c->status;
   // (tag - value) as a signed difference >= 0: CU_STREAM_WAIT_VALUE_GEQ compares cyclically, tags may wrap
   if (wait(c->stream, reinterpret_cast<CUdeviceptr>(c->slots[0].alloc + tag_offset(c, slot)), tag, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
     return c->fail(XVCB200_CUDA_ERROR, "cuStreamWaitValue32 (arrival tag) failed");

@@ -483,25 +483,33 @@ __device__ __forceinline__ MeGeom sjob_geom(const SJob &j, int bitdepth, uint32_
 }
 
 // TzSearch::Search (inter_tz_search.cc:84-171) for job groups.  One persistent CTA per SM takes
-// groups from a counter.  A group = the jobs of one CTU on one reference picture: the bounding
-// box of their search windows and the original CTU are staged in shared memory once and shared
-// by all phases of all its jobs.
+// groups from a counter.  A group = a run of jobs of one CTU on one reference picture, searched in
+// chunks: as many consecutive jobs as have the bounding box of their search windows inside the
+// shared-memory region; that box and the original CTU are staged once per chunk and shared by all
+// phases of all its jobs.
 //
-//   phase 1   start points + first diamond pass + 2-point step, one warp per job (sub-group
-//             evaluation, see RoundEval), reading the staged box
-//   raster    jobs whose first pass ended far out (last_range > 5) scan the window on the
-//             5-sample grid (:145-155), CTA-wide, ONE CANDIDATE PER LANE: a warp takes one grid
-//             column (fixed x: warp-uniform alignment) and 32 grid rows (5 picture rows apart; the
-//             odd row pitch of the box puts them in 32 distinct banks).
-//             Successive elimination (exact): first a lower bound of every candidate's SAD from
-//             8-sample segment sums,  sum_rows sum_k |A8[r][k] - S8[y+r][x+8k]| <= SAD  (triangle
-//             inequality per segment), hence bound_cost <= cost.  A candidate can only replace
-//             the incoming best if cost < cost_in (strict compare of CheckCostBest, :266), so
-//             candidates with bound_cost >= cost_in are dropped without changing the result.  The
-//             S8 box is staged for the bound pass, survivors go to a per-CTA pool, then the
-//             sample box is staged again and the survivors of all jobs are evaluated exactly in
-//             one flat loop (per-job winners through a 64-bit shared-memory atomicMin).
-//   phase 3   re-centre until the centre wins, one warp per job.
+//   first loop  per job (warp teams of 16 / 4 / 1 by block size, fetched largest first): start points,
+//               the first diamond pass -- evaluated in two instalments, radii 1..8 and the rest: the
+//               three-miss rule (:133-143) usually ends it inside the first -- and the 2-point step;
+//               a job that needs no raster scan goes straight on to the refinement (re-centre until
+//               the centre wins, :157-168) and is finished.  A job whose first pass ended far out
+//               (last_range > 5) parks its state (SJob::need = 1: scan window inside the staged box,
+//               2: outside -- a start point other than the predictor re-centres the window, :121-125).
+//   raster      two rounds, CTA-wide: the jobs with need == 1 on the staged box, then the bounding box
+//               of the OTHER windows is staged (as many as fit) and scanned the same way; what still
+//               does not fit is scanned densely from global memory.  A scan (:145-155) visits the
+//               window on the 5-sample grid, ONE CANDIDATE PER LANE: a warp takes grid columns (fixed
+//               x: warp-uniform alignment) and 32 grid rows (5 picture rows apart; the odd row pitch
+//               of the box puts them in 32 distinct banks).
+//               Successive elimination (exact): first a lower bound of every candidate's SAD from
+//               8-sample segment sums,  sum_rows sum_k |A8[r][k] - S8[y+r][x+8k]| <= SAD  (triangle
+//               inequality per segment), hence bound_cost <= cost.  A candidate can only replace
+//               the incoming best if cost < cost_in (strict compare of CheckCostBest, :266), so
+//               candidates with bound_cost >= cost_in are dropped without changing the result.  The
+//               box is converted to its segment sums in place for the bound pass and back; survivors
+//               go to a per-CTA pool and are evaluated exactly, each spread over 2^lgw lanes by block
+//               size and survivor count (per-job winners through a 64-bit shared-memory atomicMin).
+//   second loop the refinement of the scanned jobs (need == 3), on the box staged last.
 __global__ void __launch_bounds__(kTzThreads, 1)
 tz_search_kernel(const xvcb200_cu *__restrict__ cus, const xvcb200_me_job *__restrict__ jobs,
                  const int *__restrict__ job_index, const TzGroup *__restrict__ groups, int n_groups,
