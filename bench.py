@@ -503,6 +503,29 @@ def banded_measurement(torch, dist, lib, sharding, rank, world, local_rank, step
                    "down (4 luma + 2x2 chroma), horizontal edges, modified rows back (3 + 2x1); host-synchronous protocol, wall clock, max over ranks"}
 
 
+def run_extras_guarded(line, rank, limit, work):
+    """work() -> dict merged into `line`.  The line is complete without it: work runs under a watchdog -- if it does not
+    return within `limit` seconds (a rank stuck in a collective or in a device-side wait), rank 0 prints the line with
+    the reason and the process leaves with exit code 0 (every rank runs its own watchdog)."""
+    finished = threading.Event()
+
+    def give_up():
+        if finished.wait(limit):
+            return
+        if rank == 0:
+            line["gop"] = {"unavailable": "the GOP / banded measurements did not finish within %.0f s and were abandoned" % limit}
+            print(json.dumps(line))
+            sys.stdout.flush()
+        os._exit(0)
+
+    threading.Thread(target=give_up, daemon=True).start()
+    extra = work()
+    finished.set()
+    for k, v in (extra or {}).items():
+        if v is not None:
+            line[k] = v
+
+
 def run_ours(args):
     import torch
     from xvc_b200 import lib, sharding
@@ -898,35 +921,22 @@ def run_ours(args):
     # (config 4).  The line above is complete without them: they run under a watchdog -- if they do not finish (a rank
     # stuck in a collective or in a device-side wait) rank 0 prints the line with the reason and every rank leaves.
     if args.gop != "off":
-        limit = float(os.environ.get("XVCB_BENCH_EXTRAS_TIMEOUT", "180"))
-        finished = threading.Event()
-
-        def give_up():
-            if finished.wait(limit):
-                return
-            if rank == 0:
-                line["gop"] = {"unavailable": "the GOP / banded measurements did not finish within %.0f s and were abandoned" % limit}
-                print(json.dumps(line))
-                sys.stdout.flush()
-            os._exit(0)
-
-        threading.Thread(target=give_up, daemon=True).start()
-        gop_info = banded_info = None
-        try:
-            ctx.close()
-            gop_info = gop_measurement(torch, dist, lib, sharding, rank, world, local_rank, max(2, world) if args.gop_sub_gops <= 0 else args.gop_sub_gops)
-        except Exception as e:  # noqa: BLE001
-            gop_info = {"unavailable": repr(e)}
-        if dist is not None:
+        def extras():
+            out = {}
             try:
-                banded_info = banded_measurement(torch, dist, lib, sharding, rank, world, local_rank, 10)
+                ctx.close()
+                out["gop"] = gop_measurement(torch, dist, lib, sharding, rank, world, local_rank,
+                                             max(2, world) if args.gop_sub_gops <= 0 else args.gop_sub_gops)
             except Exception as e:  # noqa: BLE001
-                banded_info = {"unavailable": repr(e)}
-        finished.set()
-        if gop_info is not None:
-            line["gop"] = gop_info
-        if banded_info is not None:
-            line["banded"] = banded_info
+                out["gop"] = {"unavailable": repr(e)}
+            if dist is not None:
+                try:
+                    out["banded"] = banded_measurement(torch, dist, lib, sharding, rank, world, local_rank, 10)
+                except Exception as e:  # noqa: BLE001
+                    out["banded"] = {"unavailable": repr(e)}
+            return out
+
+        run_extras_guarded(line, rank, float(os.environ.get("XVCB_BENCH_EXTRAS_TIMEOUT", "180")), extras)
     if rank == 0:
         print(json.dumps(line))
         sys.stdout.flush()
